@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the B200-native QOI codec.
+
+Metric (BASELINE.json): Gpixels/s of an encode + decode round trip over a batch of synthetic
+4096x4096 RGBA images, per-GPU batch fixed (weak scaling), 1/2/4/8 GPUs, next to the fraction of the
+HBM roofline of the dominant kernel and the reference qoi.h timed on the host cores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--dist D] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  A "step" = qoi_gpu_encode of the whole batch followed by
+qoi_gpu_decode of the streams it wrote (segment-parallel, using the restart index the encoder left
+in the plan).  `value` is device resident; `e2e` runs the same step through the host-buffer C ABI
+(qoi_gpu_encode_host / qoi_gpu_decode_host) from pinned host memory, copies inside the timed region.
+The oracle / compiled reference is executed only in the cpu_baseline leg and under --impl reference.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W = H = 4096
+CH = 4
+METRIC = "Gpixels/s encode+decode round trip, 4096x4096 RGBA batch"
+DIST_NAMES = ["noise_rgba", "noise_opaque", "gradient", "grad2", "photo", "tiles32", "palette16", "const0"]
+
+
+def shard_images(global_batch, world, rank):
+    """Contiguous block partition of image indices: rank r owns [lo, hi)."""
+    per = (global_batch + world - 1) // world
+    lo = min(global_batch, rank * per)
+    hi = min(global_batch, lo + per)
+    return lo, hi
+
+
+def load_synth():
+    so = os.path.join(ROOT, "tools", "libqoi_synth.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    lib = C.CDLL(so)
+    lib.qoi_synth_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_uint]
+    return lib
+
+
+def load_cpu_codec():
+    """(kind, lib, prefix): the compiled reference if it travelled with the repo, else the oracle port."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "libqoi_ref.so")
+    ora = os.path.join(ROOT, "oracle", "liboracle.so")
+    if os.path.exists(ref):
+        kind, path, prefix = "reference", ref, "ref_"
+    else:
+        if not os.path.exists(ora):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+        kind, path, prefix = "port", ora, "ora_"
+    lib = C.CDLL(path)
+    eb = getattr(lib, prefix + "encode_batch")
+    eb.restype = C.c_double
+    eb.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    db = getattr(lib, prefix + "decode_batch")
+    db.restype = C.c_double
+    db.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    ht = getattr(lib, prefix + "host_threads")
+    ht.restype = C.c_int
+    return kind, eb, db, ht()
+
+
+class DescC(C.Structure):
+    _fields_ = [("width", C.c_uint), ("height", C.c_uint), ("channels", C.c_ubyte), ("colorspace", C.c_ubyte)]
+
+
+def cpu_round_trip(eb, db, threads, pixels, n, keep_streams, keep_lens, slot):
+    """one encode + decode pass of the CPU codec over n images; returns seconds (encode, decode)."""
+    d = DescC(W, H, CH, 0)
+    te = eb(pixels.ctypes.data, W * H * CH, n, C.byref(d), threads, keep_streams.ctypes.data, slot, keep_lens.ctypes.data)
+    td = db(keep_streams.ctypes.data, slot, keep_lens.ctypes.data, n, 4, threads, None, 0)
+    if te < 0 or td < 0:
+        raise RuntimeError("CPU codec returned NULL")
+    return te, td
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.file = tempfile.NamedTemporaryFile(prefix="qoi_clocks_", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.file, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.file.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.file.name):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        finally:
+            os.unlink(self.file.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation on the host cores, all threads, same config."""
+    if rank != 0:
+        return
+    kind, eb, db, threads = load_cpu_codec()
+    synth = load_synth()
+    n = args.batch
+    pixels = np.empty(n * W * H * CH, dtype=np.uint8)
+    synth.qoi_synth_batch(pixels.ctypes.data, W * H * CH, n, W, H, CH, args.dist, 0)
+    slot = W * H * (CH + 1) + 22
+    streams = np.empty(n * slot, dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.int32)
+    for _ in range(args.warmup):
+        cpu_round_trip(eb, db, threads, pixels, n, streams, lens, slot)
+    t_enc = t_dec = 0.0
+    for _ in range(args.steps):
+        te, td = cpu_round_trip(eb, db, threads, pixels, n, streams, lens, slot)
+        t_enc += te
+        t_dec += td
+    total = t_enc + t_dec
+    px = n * W * H * args.steps
+    value = px / total / 1e9
+    sample = f"{n} x {W}x{H} RGBA images per step (one per-GPU batch), OpenMP over images, malloc+free inside the call as qoibench.c:446-450,471-481"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gpx/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{W}x{H} RGBA batch, encode+decode round trip", "batch_per_gpu": args.batch,
+                   "distribution": DIST_NAMES[args.dist], "decode_channels": 4},
+        "cpu_baseline": {"value": value, "unit": "Gpx/s", "cores": threads, "kind": kind, "sample": sample,
+                         "encode_gpx": px / t_enc / 1e9, "decode_gpx": px / t_dec / 1e9},
+        "e2e": {"value": value, "unit": "Gpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU (weak scaling)")
+    ap.add_argument("--dist", type=int, default=4, help="synthetic distribution id (4 = photo, headline)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+
+    import qoi_b200
+    from qoi_b200.api import pinned_array
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.batch
+    img_bytes = W * H * CH
+    synth = load_synth()
+    ctx = qoi_b200.Context(local_rank)
+    descs = [qoi_b200.Desc(W, H, CH, 0)] * n
+    plan = qoi_b200.Plan(ctx, descs, decoded_channels=4)
+
+    # ---- inputs: this rank's shard of the global batch, generated on the host (untimed), pinned
+    lo, hi = shard_images(n * world, world, rank)
+    assert hi - lo == n
+    h_pix = pinned_array(plan.pixel_bytes)
+    synth.qoi_synth_batch(h_pix.ctypes.data, img_bytes, n, W, H, CH, args.dist, lo)
+    d_pix = torch.empty(plan.pixel_bytes, dtype=torch.uint8, device="cuda")
+    d_pix.copy_(torch.from_numpy(h_pix))
+    d_streams = torch.empty(plan.stream_bytes, dtype=torch.uint8, device="cuda")
+    d_lens = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_dec = torch.empty(plan.decoded_bytes, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(events=None):
+        if events is not None:
+            events[0].record()
+        plan.encode(d_pix.data_ptr(), d_streams.data_ptr(), d_lens.data_ptr(), stream)
+        if events is not None:
+            events[1].record()
+        plan.decode(d_streams.data_ptr(), d_lens.data_ptr(), d_dec.data_ptr(), True, None, stream)
+        if events is not None:
+            events[2].record()
+
+    def barrier():
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up + correctness of the round trip (untimed)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if not torch.equal(d_dec, d_pix):
+        raise SystemExit("round trip mismatch: decode(encode(x)) != x")
+    lens = d_lens.cpu().numpy().astype(np.int64)
+    enc_bytes = int(lens.sum())
+    px_rank = n * W * H
+    e_bpp = enc_bytes / px_rank
+
+    # ---- timed region: exactly K steps, events on the launching stream, clocks sampled meanwhile
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = qoi_b200.launch_count()
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_stop = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(args.steps):
+        step(evs[k])
+    t_stop.record()
+    barrier()
+    launches = qoi_b200.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    total_ms = t_start.elapsed_time(t_stop)
+    enc_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    dec_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+
+    # ---- e2e: same step through the host-buffer C ABI, pinned host memory, copies inside
+    h_streams = pinned_array(plan.stream_bytes)
+    h_lens = np.zeros(n, dtype=np.int32)
+    h_dec = pinned_array(plan.decoded_bytes)
+
+    def e2e_step():
+        plan.encode_host(h_pix, h_streams, h_lens)
+        plan.decode_host(h_streams, h_lens, h_dec, use_index=True)
+
+    e2e_step()
+    if not np.array_equal(h_dec, h_pix):
+        raise SystemExit("e2e round trip mismatch")
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    h2d = plan.pixel_bytes + enc_bytes + 4 * n
+    d2h = enc_bytes + plan.decoded_bytes + 4 * n
+
+    # ---- foreign-stream decode (no restart index): reported beside the headline, not part of it
+    fe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    plan.decode(d_streams.data_ptr(), d_lens.data_ptr(), d_dec.data_ptr(), False, None, stream)
+    fe[0].record()
+    plan.decode(d_streams.data_ptr(), d_lens.data_ptr(), d_dec.data_ptr(), False, None, stream)
+    fe[1].record()
+    torch.cuda.synchronize()
+    foreign_ms = fe[0].elapsed_time(fe[1])
+
+    # ---- max over ranks
+    vals = torch.tensor([total_ms, enc_ms, dec_ms, e2e_s * 1e3, foreign_ms], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([float(enc_bytes), float(launches)], dtype=torch.float64, device="cuda")
+    if dist_on:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)  # sizes exchange (the only collective; outside the timed region)
+    total_ms, enc_ms, dec_ms, e2e_ms, foreign_ms = [float(x) for x in vals.tolist()]
+    enc_bytes_all, launches_all = [float(x) for x in sums.tolist()]
+
+    if rank == 0:
+        px_all = px_rank * world
+        ms_per_step = total_ms / args.steps
+        value = px_all / (ms_per_step * 1e-3) / 1e9
+        peak, peak_src = measured_peak()
+        enc_alg = px_rank * CH + enc_bytes          # bytes one encode launch must move (read ch B/px + write e B/px)
+        dec_alg = enc_bytes + px_rank * 4           # bytes one decode launch must move (read e B/px + write 4 B/px)
+        enc_gbs = enc_alg / (enc_ms * 1e-3) / 1e9
+        dec_gbs = dec_alg / (dec_ms * 1e-3) / 1e9
+        dominant = "decode" if dec_ms >= enc_ms else "encode"
+        traffic = recorded_traffic()
+        roofline = {
+            "bound": "hbm", "kernel": "qoi_decode_kernel<4,128>" if dominant == "decode" else "qoi_encode_kernel<4,false>",
+            "achieved": dec_gbs if dominant == "decode" else enc_gbs, "peak": peak, "unit": "GB/s",
+            "frac": (dec_gbs if dominant == "decode" else enc_gbs) / peak, "peak_source": peak_src,
+            "traffic": (traffic or {}).get(dominant),
+            "encode": {"ms": enc_ms, "achieved": enc_gbs, "frac": enc_gbs / peak, "algorithmic_bytes": enc_alg,
+                       "gpx_per_s": px_rank / (enc_ms * 1e-3) / 1e9, "traffic": (traffic or {}).get("encode")},
+            "decode": {"ms": dec_ms, "achieved": dec_gbs, "frac": dec_gbs / peak, "algorithmic_bytes": dec_alg,
+                       "gpx_per_s": px_rank / (dec_ms * 1e-3) / 1e9, "traffic": (traffic or {}).get("decode")},
+        }
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu:
+            kind, eb, db, threads = load_cpu_codec()
+            slot = W * H * (CH + 1) + 22
+            keep = np.empty(n * slot, dtype=np.uint8)
+            klens = np.zeros(n, dtype=np.int32)
+            cpu_round_trip(eb, db, threads, h_pix, min(n, threads), keep, klens, slot)  # first-touch warm-up
+            te, td = cpu_round_trip(eb, db, threads, h_pix, n, keep, klens, slot)
+            ok = all(np.array_equal(keep[i * slot:i * slot + klens[i]], h_streams[int(plan.stream_off[i]):int(plan.stream_off[i]) + klens[i]]) for i in range(n))
+            if not ok or not np.array_equal(klens, h_lens):
+                raise SystemExit("GPU streams differ from the CPU codec's")
+            cpu_baseline = {"value": px_rank / (te + td) / 1e9, "unit": "Gpx/s", "cores": threads, "kind": kind,
+                            "sample": f"{n} x {W}x{H} RGBA images, one encode+decode pass, OpenMP over images; GPU streams verified identical",
+                            "encode_gpx": px_rank / te / 1e9, "decode_gpx": px_rank / td / 1e9}
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{W}x{H} RGBA batch, encode+decode round trip", "batch_per_gpu": n,
+                       "global_batch": n * world, "distribution": DIST_NAMES[args.dist], "decode_channels": 4,
+                       "encoded_bytes_per_px": e_bpp, "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
+                       "l2": f"inputs {plan.pixel_bytes >> 20} MiB per GPU per step, larger than the 126 MB L2 (no flush needed)",
+                       "decode_path": "segment-parallel with the encoder's restart index (side table, 0.07 B/px, outside the bit-exact stream)"},
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": px_all / (e2e_ms * 1e-3) / 1e9, "unit": "Gpx/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "api": "qoi_gpu_encode_host + qoi_gpu_decode_host (pinned host buffers)"},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "extra": {"decode_foreign_stream_gpx_per_s": px_rank / (foreign_ms * 1e-3) / 1e9,
+                      "decode_foreign_note": "same streams decoded WITHOUT the restart index: one lane per image (qoi.h's loop is sequential per stream)",
+                      "encoded_bytes_all_ranks": enc_bytes_all},
+        }
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

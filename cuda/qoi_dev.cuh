@@ -1,0 +1,173 @@
+/*
+ * qoi_dev.cuh -- the handful of sm_100a primitives the kernels are written on:
+ * mbarrier + bulk async copies (TMA, SASS UBLKCP), acquire/release flag
+ * accesses for the decoupled look-back, and byte helpers.
+ *
+ * When QOI_EMU is defined (tests/emu only) the same names are provided on top
+ * of tests/emu/cuda_emu.h so the kernel source can be stepped on the CPU.
+ */
+#pragma once
+#include <stdint.h>
+
+#ifdef QOI_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+namespace qoidev {
+
+#define QOI_FULL_MASK 0xFFFFFFFFu
+
+#ifndef QOI_EMU
+/* ------------------------------------------------------------------ real */
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
+}
+/* make the initialised barriers visible to the async (TMA) proxy */
+__device__ __forceinline__ void mbar_fence_init() {
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+/* one arrival that also announces `bytes` of bulk-copy traffic for the current phase */
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+	    "selp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(ok)
+	    : "r"(smem_addr(bar)), "r"(parity)
+	    : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	while (!mbar_try_wait(bar, parity)) {
+	}
+}
+/* global -> shared bulk copy (1-D TMA); both addresses 16-byte aligned, bytes a multiple of 16, bytes > 0 */
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+	             "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+	             : "memory");
+}
+/* shared -> global bulk copy; same alignment rules; completion tracked by the bulk group */
+__device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes)
+	             : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+/* wait until all committed bulk stores of this thread have finished READING shared memory */
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+/* wait until they are complete (writes performed) */
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+/* order generic-proxy shared-memory writes before a following bulk store */
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p) {
+	uint64_t v;
+	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v) {
+	asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void spin_pause() { __nanosleep(32); }
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+	uint32_t m;
+	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+	return m;
+}
+__device__ __forceinline__ uint32_t lanemask_gt() {
+	uint32_t m;
+	asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
+	return m;
+}
+#define QOI_DYNAMIC_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+
+#else
+/* ------------------------------------------------------------------ emulation */
+struct EmuBar {
+	uint8_t phase, count;
+	int16_t arrivals_left;
+	int32_t tx;
+};
+static_assert(sizeof(EmuBar) == 8, "");
+static inline void emubar_check(EmuBar *b) {
+	if (b->arrivals_left == 0 && b->tx == 0) {
+		b->phase ^= 1;
+		b->arrivals_left = b->count;
+		qemu::progress++;
+	}
+}
+static inline void mbar_init(uint64_t *bar, uint32_t arrivals) {
+	EmuBar *b = (EmuBar *)bar;
+	b->phase = 0;
+	b->count = (uint8_t)arrivals;
+	b->arrivals_left = (int16_t)arrivals;
+	b->tx = 0;
+}
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+	EmuBar *b = (EmuBar *)bar;
+	b->tx += (int32_t)bytes;
+	b->arrivals_left--;
+	emubar_check(b);
+}
+static inline bool mbar_try_wait(uint64_t *bar, uint32_t parity) { return ((EmuBar *)bar)->phase != (uint8_t)parity; }
+static inline void mbar_wait(uint64_t *bar, uint32_t parity) {
+	while (!mbar_try_wait(bar, parity)) qemu::yield("mbarrier wait");
+}
+static inline void emu_check_bulk(const void *a, const void *b, uint32_t bytes) {
+	if (((uintptr_t)a & 15) || ((uintptr_t)b & 15) || (bytes & 15) || bytes == 0) {
+		fprintf(stderr, "cuda_emu: bulk copy violates the 16-byte rules: %p %p %u\n", a, b, bytes);
+		abort();
+	}
+}
+static inline void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+	emu_check_bulk(dst_smem, src_gmem, bytes);
+	memcpy(dst_smem, src_gmem, bytes);
+	EmuBar *b = (EmuBar *)bar;
+	b->tx -= (int32_t)bytes;
+	emubar_check(b);
+}
+static inline void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+	emu_check_bulk(dst_gmem, src_smem, bytes);
+	memcpy(dst_gmem, src_smem, bytes);
+	qemu::progress++;
+}
+static inline void tma_store_commit() {}
+static inline void tma_store_wait_read() {}
+static inline void tma_store_wait_all() {}
+static inline void fence_proxy_async_smem() {}
+static inline uint32_t ld_acquire_u32(const uint32_t *p) { return *p; }
+static inline void st_release_u32(uint32_t *p, uint32_t v) { *p = v; qemu::progress++; }
+static inline uint64_t ld_acquire_u64(const uint64_t *p) { return *p; }
+static inline void st_release_u64(uint64_t *p, uint64_t v) { *p = v; qemu::progress++; }
+static inline void spin_pause() { qemu::yield("spin wait"); }
+static inline uint32_t lane_id() { return threadIdx.x & 31u; }
+static inline uint32_t lanemask_lt() { return (1u << lane_id()) - 1u; }
+static inline uint32_t lanemask_gt() { return lane_id() == 31 ? 0u : ~((2u << lane_id()) - 1u); }
+#define QOI_DYNAMIC_SMEM(name) unsigned char *name = qemu::cur->blk->smem
+#endif
+
+/* ------------------------------------------------------------------ common helpers */
+
+/* QOI_COLOR_HASH & 63 (reference qoi.h:322,430,577) on a packed r|g<<8|b<<16|a<<24 pixel: one IDP4A */
+__device__ __forceinline__ uint32_t qoi_slot(uint32_t px) { return __dp4a(px, 0x0B070503u, 0u) & 63u; }
+
+}  // namespace qoidev

@@ -1,0 +1,413 @@
+/*
+ * qoi_gpu.cu -- C ABI of the B200-native QOI codec (libqoi_gpu.so).
+ *
+ * Exports (all extern "C", plain pointers and sizes):
+ *   - the reference's own entry points  qoi_encode / qoi_decode   (reference qoi.h:278,289; bodies qoi.h:356-590)
+ *   - the batch / device-resident API declared in include/qoi_gpu.h
+ *
+ * There is NO CPU implementation in this library.  Every pixel is coded by the sm_100a kernels in
+ * qoi_enc.cuh / qoi_dec.cuh; if CUDA is unavailable the functions fail (NULL / QOI_GPU_E_CUDA).
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../include/qoi_gpu.h"
+#include "qoi_dec.cuh"
+#include "qoi_enc.cuh"
+#include "qoi_plan.h"
+
+static_assert(sizeof(qoi_desc) == sizeof(QoiDescPOD), "qoi_desc layout");
+static_assert(QOI_GPU_TILE_PX == QOI_TILE_PX, "tile size");
+
+static std::atomic<uint64_t> g_launches{0};
+
+struct qoi_gpu_ctx {
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	char err[256] = {0};
+	int enc_blocks_per_sm[3] = {0, 0, 0}; /* <4,false>, <4,true>, <3,true> */
+};
+
+struct qoi_gpu_plan {
+	qoi_gpu_ctx *ctx = nullptr;
+	QoiPlanGeom geom;
+	QoiStateLayout layout;
+	QoiImgMeta *d_metas = nullptr;
+	unsigned char *d_state = nullptr;
+	QoiTileState st;
+	uint32_t epoch = 0;
+	bool pix_off_aligned16 = true;
+	/* lazily allocated device mirrors for the *_host entry points */
+	unsigned char *d_pixels = nullptr, *d_streams = nullptr, *d_decoded = nullptr;
+	int32_t *d_lens = nullptr;
+	int32_t *h_lens_pinned = nullptr;
+};
+
+#define CK(ctx, call)                                                                         \
+	do {                                                                                      \
+		cudaError_t e_ = (call);                                                              \
+		if (e_ != cudaSuccess) {                                                              \
+			if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), "%s: %s", #call, cudaGetErrorString(e_)); \
+			return QOI_GPU_E_CUDA;                                                            \
+		}                                                                                     \
+	} while (0)
+
+template <int CH, bool EXPAND>
+static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
+	using L = qoienc::Layout<CH, EXPAND>;
+	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+	int nb = 0;
+	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qoienc::qoi_encode_kernel<CH, EXPAND>, QOI_ENC_THREADS, L::TOTAL));
+	*out = nb > 0 ? nb : 1;
+	return QOI_GPU_OK;
+}
+
+template <int OUT_CH, int BLOCK>
+static void launch_decode(const QoiDecParams &D, cudaStream_t s) {
+	const uint32_t grid = (D.n_jobs + BLOCK - 1) / BLOCK;
+	qoidec::qoi_decode_kernel<OUT_CH, BLOCK><<<grid, BLOCK, 64 * BLOCK * 4, s>>>(D);
+}
+
+extern "C" {
+
+int qoi_gpu_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+uint64_t qoi_gpu_launch_count(void) { return g_launches.load(); }
+
+int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
+	if (!out) return QOI_GPU_E_ARG;
+	*out = nullptr;
+	int n = qoi_gpu_device_count();
+	if (device < 0 || device >= n) return QOI_GPU_E_CUDA;
+	qoi_gpu_ctx *c = new (std::nothrow) qoi_gpu_ctx;
+	if (!c) return QOI_GPU_E_NOMEM;
+	c->device = device;
+	cudaError_t e = cudaSetDevice(device);
+	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	if (e != cudaSuccess) {
+		delete c;
+		return QOI_GPU_E_CUDA;
+	}
+	int rc = enc_occupancy<4, false>(c, &c->enc_blocks_per_sm[0]);
+	if (!rc) rc = enc_occupancy<4, true>(c, &c->enc_blocks_per_sm[1]);
+	if (!rc) rc = enc_occupancy<3, true>(c, &c->enc_blocks_per_sm[2]);
+	if (rc) {
+		fprintf(stderr, "qoi_gpu: kernel setup failed: %s\n", c->err);
+		cudaStreamDestroy(c->stream);
+		delete c;
+		return rc;
+	}
+	*out = c;
+	return QOI_GPU_OK;
+}
+
+void qoi_gpu_ctx_destroy(qoi_gpu_ctx *c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+const char *qoi_gpu_last_error(const qoi_gpu_ctx *c) { return c ? c->err : ""; }
+
+size_t qoi_gpu_max_stream_size(const qoi_desc *d) {
+	if (!d) return 0;
+	QoiDescPOD p = {d->width, d->height, d->channels, d->colorspace};
+	return qoi_max_stream(p);
+}
+
+int qoi_gpu_plan_create(qoi_gpu_ctx *ctx, qoi_gpu_plan **out, int n, const qoi_desc *descs, const uint64_t *pixel_off,
+                        const uint64_t *stream_off, const uint64_t *decoded_off, int decoded_channels) {
+	if (!ctx || !out) return QOI_GPU_E_ARG;
+	*out = nullptr;
+	qoi_gpu_plan *p = new (std::nothrow) qoi_gpu_plan;
+	if (!p) return QOI_GPU_E_NOMEM;
+	p->ctx = ctx;
+	if (qoi_plan_geometry(p->geom, n, (const QoiDescPOD *)descs, pixel_off, stream_off, decoded_off, decoded_channels)) {
+		delete p;
+		return QOI_GPU_E_ARG;
+	}
+	for (const QoiImgMeta &m : p->geom.metas)
+		if (m.pix_off & 15u) p->pix_off_aligned16 = false;
+	p->layout = qoi_state_layout(p->geom.n_tiles);
+	cudaError_t e = cudaSetDevice(ctx->device);
+	if (e == cudaSuccess) e = cudaMalloc(&p->d_metas, sizeof(QoiImgMeta) * (size_t)n);
+	if (e == cudaSuccess) e = cudaMalloc(&p->d_state, p->layout.total);
+	if (e == cudaSuccess) e = cudaMemset(p->d_state, 0, p->layout.total);
+	if (e == cudaSuccess) e = cudaMemcpy(p->d_metas, p->geom.metas.data(), sizeof(QoiImgMeta) * (size_t)n, cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) {
+		snprintf(ctx->err, sizeof ctx->err, "plan allocation: %s", cudaGetErrorString(e));
+		qoi_gpu_plan_destroy(p);
+		return e == cudaErrorMemoryAllocation ? QOI_GPU_E_NOMEM : QOI_GPU_E_CUDA;
+	}
+	qoi_state_bind(p->st, p->d_state, p->layout);
+	*out = p;
+	return QOI_GPU_OK;
+}
+
+void qoi_gpu_plan_destroy(qoi_gpu_plan *p) {
+	if (!p) return;
+	cudaSetDevice(p->ctx->device);
+	cudaFree(p->d_metas);
+	cudaFree(p->d_state);
+	cudaFree(p->d_pixels);
+	cudaFree(p->d_streams);
+	cudaFree(p->d_decoded);
+	cudaFree(p->d_lens);
+	if (p->h_lens_pinned) cudaFreeHost(p->h_lens_pinned);
+	delete p;
+}
+
+uint64_t qoi_gpu_plan_pixels(const qoi_gpu_plan *p) { return p ? p->geom.total_px : 0; }
+uint32_t qoi_gpu_plan_tiles(const qoi_gpu_plan *p) { return p ? p->geom.n_tiles : 0; }
+
+int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32_t *d_lens, void *cuda_stream) {
+	if (!p || !d_pixels || !d_streams || !d_lens) return QOI_GPU_E_ARG;
+	qoi_gpu_ctx *ctx = p->ctx;
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	CK(ctx, cudaSetDevice(ctx->device));
+	if (++p->epoch >= (1u << 30) - 1u) { /* status words carry a 30-bit epoch */
+		CK(ctx, cudaMemsetAsync(p->d_state, 0, p->layout.total, s));
+		p->epoch = 1;
+	}
+	QoiEncParams P;
+	memset(&P, 0, sizeof P);
+	P.pixels = (const uint8_t *)d_pixels;
+	P.streams = (uint8_t *)d_streams;
+	P.lens = d_lens;
+	P.imgs = p->d_metas;
+	P.n_images = (uint32_t)p->geom.metas.size();
+	P.n_tiles = p->geom.n_tiles;
+	P.epoch = p->epoch;
+	P.st = p->st;
+	const bool zero_copy = p->geom.channels == 4 && p->pix_off_aligned16 && (((uintptr_t)d_pixels & 15u) == 0);
+	const int variant = p->geom.channels == 3 ? 2 : (zero_copy ? 0 : 1);
+	uint32_t grid = (uint32_t)(ctx->sm_count * ctx->enc_blocks_per_sm[variant]);
+	if (grid > P.n_tiles) grid = P.n_tiles;
+	if (variant == 0) qoienc::qoi_encode_kernel<4, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
+	else if (variant == 1) qoienc::qoi_encode_kernel<4, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
+	else qoienc::qoi_encode_kernel<3, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
+	g_launches++;
+	CK(ctx, cudaGetLastError());
+	return QOI_GPU_OK;
+}
+
+int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens, void *d_decoded, int use_index,
+                   int32_t *d_status, void *cuda_stream) {
+	if (!p || !d_streams || !d_lens || !d_decoded) return QOI_GPU_E_ARG;
+	if (use_index && p->epoch == 0) return QOI_GPU_E_ARG; /* no encode has written the index yet */
+	qoi_gpu_ctx *ctx = p->ctx;
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	CK(ctx, cudaSetDevice(ctx->device));
+	QoiDecParams D;
+	memset(&D, 0, sizeof D);
+	D.streams = (const uint8_t *)d_streams;
+	D.lens = d_lens;
+	D.out = (uint8_t *)d_decoded;
+	D.status = d_status;
+	D.imgs = p->d_metas;
+	D.n_images = (uint32_t)p->geom.metas.size();
+	D.n_jobs = use_index ? p->geom.n_tiles : D.n_images;
+	D.out_channels = p->geom.dec_channels;
+	D.use_index = use_index ? 1 : 0;
+	D.st = p->st;
+	/* few segments: narrow blocks so that they spread over the SMs */
+	const bool narrow = D.n_jobs < (uint32_t)ctx->sm_count * 128u * 2u;
+	if (D.out_channels == 4) {
+		if (narrow) launch_decode<4, 32>(D, s);
+		else launch_decode<4, 128>(D, s);
+	} else {
+		if (narrow) launch_decode<3, 32>(D, s);
+		else launch_decode<3, 128>(D, s);
+	}
+	g_launches++;
+	CK(ctx, cudaGetLastError());
+	return QOI_GPU_OK;
+}
+
+/* ------------------------------------------------------------------ host-buffer forms */
+static int plan_mirrors(qoi_gpu_plan *p) {
+	qoi_gpu_ctx *ctx = p->ctx;
+	if (!p->d_pixels) CK(ctx, cudaMalloc(&p->d_pixels, p->geom.pixel_bytes + 16));
+	if (!p->d_streams) CK(ctx, cudaMalloc(&p->d_streams, p->geom.stream_bytes + 16));
+	if (!p->d_decoded) CK(ctx, cudaMalloc(&p->d_decoded, p->geom.decoded_bytes + 16));
+	if (!p->d_lens) CK(ctx, cudaMalloc(&p->d_lens, sizeof(int32_t) * p->geom.metas.size()));
+	if (!p->h_lens_pinned) CK(ctx, cudaMallocHost(&p->h_lens_pinned, sizeof(int32_t) * p->geom.metas.size()));
+	return QOI_GPU_OK;
+}
+
+int qoi_gpu_encode_host(qoi_gpu_plan *p, const void *h_pixels, void *h_streams, int32_t *h_lens) {
+	if (!p || !h_pixels || !h_streams || !h_lens) return QOI_GPU_E_ARG;
+	qoi_gpu_ctx *ctx = p->ctx;
+	CK(ctx, cudaSetDevice(ctx->device));
+	int rc = plan_mirrors(p);
+	if (rc) return rc;
+	cudaStream_t s = ctx->stream;
+	const size_t n = p->geom.metas.size();
+	CK(ctx, cudaMemcpyAsync(p->d_pixels, h_pixels, p->geom.pixel_bytes, cudaMemcpyHostToDevice, s));
+	rc = qoi_gpu_encode(p, p->d_pixels, p->d_streams, p->d_lens, s);
+	if (rc) return rc;
+	CK(ctx, cudaMemcpyAsync(p->h_lens_pinned, p->d_lens, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+	CK(ctx, cudaStreamSynchronize(s));
+	for (size_t i = 0; i < n; i++) {
+		const QoiImgMeta &m = p->geom.metas[i];
+		h_lens[i] = p->h_lens_pinned[i];
+		CK(ctx, cudaMemcpyAsync((unsigned char *)h_streams + m.stream_off, p->d_streams + m.stream_off, (size_t)h_lens[i],
+		                        cudaMemcpyDeviceToHost, s));
+	}
+	CK(ctx, cudaStreamSynchronize(s));
+	return QOI_GPU_OK;
+}
+
+int qoi_gpu_decode_host(qoi_gpu_plan *p, const void *h_streams, const int32_t *h_lens, void *h_decoded, int use_index) {
+	if (!p || !h_streams || !h_lens || !h_decoded) return QOI_GPU_E_ARG;
+	qoi_gpu_ctx *ctx = p->ctx;
+	CK(ctx, cudaSetDevice(ctx->device));
+	int rc = plan_mirrors(p);
+	if (rc) return rc;
+	cudaStream_t s = ctx->stream;
+	const size_t n = p->geom.metas.size();
+	for (size_t i = 0; i < n; i++) {
+		const QoiImgMeta &m = p->geom.metas[i];
+		QoiDescPOD d = {m.width, m.height, m.channels, m.colorspace};
+		if (h_lens[i] < QOI_HEADER_BYTES + QOI_END_BYTES || (size_t)h_lens[i] > qoi_max_foreign_stream(d)) return QOI_GPU_E_ARG;
+		p->h_lens_pinned[i] = h_lens[i];
+		CK(ctx, cudaMemcpyAsync(p->d_streams + m.stream_off, (const unsigned char *)h_streams + m.stream_off, (size_t)h_lens[i],
+		                        cudaMemcpyHostToDevice, s));
+	}
+	CK(ctx, cudaMemcpyAsync(p->d_lens, p->h_lens_pinned, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+	rc = qoi_gpu_decode(p, p->d_streams, p->d_lens, p->d_decoded, use_index, nullptr, s);
+	if (rc) return rc;
+	CK(ctx, cudaMemcpyAsync(h_decoded, p->d_decoded, p->geom.decoded_bytes, cudaMemcpyDeviceToHost, s));
+	CK(ctx, cudaStreamSynchronize(s));
+	return QOI_GPU_OK;
+}
+
+void *qoi_gpu_host_alloc(size_t bytes) {
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+	return p;
+}
+void qoi_gpu_host_free(void *p) {
+	if (p) cudaFreeHost(p);
+}
+
+/* ------------------------------------------------------------------ the reference's own entry points */
+static std::mutex g_mu;
+static qoi_gpu_ctx *g_ctx = nullptr;
+static bool g_ctx_failed = false;
+static qoi_gpu_plan *g_plan = nullptr;
+static qoi_desc g_plan_desc;
+static int g_plan_dec_ch = 0;
+
+static qoi_gpu_ctx *global_ctx() {
+	if (!g_ctx && !g_ctx_failed) {
+		int dev = 0;
+		const char *e = getenv("QOI_GPU_DEVICE");
+		if (e) dev = atoi(e);
+		if (qoi_gpu_ctx_create(&g_ctx, dev) != QOI_GPU_OK) {
+			g_ctx_failed = true;
+			fprintf(stderr, "qoi_gpu: no usable CUDA device -- qoi_encode/qoi_decode have no CPU path and will return NULL\n");
+		}
+	}
+	return g_ctx;
+}
+
+static qoi_gpu_plan *global_plan(qoi_gpu_ctx *ctx, const qoi_desc *d, int dec_ch) {
+	if (g_plan && memcmp(&g_plan_desc, d, sizeof *d) == 0 && g_plan_dec_ch == dec_ch) return g_plan;
+	qoi_gpu_plan_destroy(g_plan);
+	g_plan = nullptr;
+	const uint64_t zero = 0;
+	if (qoi_gpu_plan_create(ctx, &g_plan, 1, d, &zero, &zero, &zero, dec_ch) != QOI_GPU_OK) return nullptr;
+	memset(&g_plan_desc, 0, sizeof g_plan_desc);
+	g_plan_desc = *d;
+	g_plan_dec_ch = dec_ch;
+	return g_plan;
+}
+
+/* reference qoi.h:356-486 */
+void *qoi_encode(const void *data, const qoi_desc *desc, int *out_len) {
+	if (!data || !out_len || !desc) return NULL;
+	QoiDescPOD pod = {desc->width, desc->height, desc->channels, desc->colorspace};
+	if (!qoi_geometry_ok(pod)) return NULL; /* qoi.h:364-372 */
+	qoi_desc d;
+	memset(&d, 0, sizeof d);
+	d.width = desc->width; d.height = desc->height; d.channels = desc->channels; d.colorspace = desc->colorspace;
+	std::lock_guard<std::mutex> lock(g_mu);
+	qoi_gpu_ctx *ctx = global_ctx();
+	if (!ctx) return NULL;
+	qoi_gpu_plan *p = global_plan(ctx, &d, d.channels);
+	if (!p || plan_mirrors(p)) return NULL;
+	cudaStream_t s = ctx->stream;
+	const size_t nbytes = (size_t)d.width * d.height * d.channels;
+	if (cudaMemcpyAsync(p->d_pixels, data, nbytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return NULL;
+	if (qoi_gpu_encode(p, p->d_pixels, p->d_streams, p->d_lens, s) != QOI_GPU_OK) return NULL;
+	if (cudaMemcpyAsync(p->h_lens_pinned, p->d_lens, sizeof(int32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess) return NULL;
+	if (cudaStreamSynchronize(s) != cudaSuccess) return NULL;
+	const int len = p->h_lens_pinned[0];
+	void *out = malloc((size_t)len);
+	if (!out) return NULL;
+	if (cudaMemcpyAsync(out, p->d_streams, (size_t)len, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+		free(out);
+		return NULL;
+	}
+	*out_len = len; /* written only on success, qoi.h:484 */
+	return out;
+}
+
+/* reference qoi.h:488-590 */
+void *qoi_decode(const void *data, int size, qoi_desc *desc, int channels) {
+	if (!data || !desc || (channels != 0 && channels != 3 && channels != 4) || size < QOI_HEADER_BYTES + QOI_END_BYTES) return NULL; /* qoi.h:497-503 */
+	const unsigned char *b = (const unsigned char *)data;
+	const unsigned magic = ((unsigned)b[0] << 24) | ((unsigned)b[1] << 16) | ((unsigned)b[2] << 8) | b[3];
+	desc->width = ((unsigned)b[4] << 24) | ((unsigned)b[5] << 16) | ((unsigned)b[6] << 8) | b[7]; /* filled before validation, qoi.h:508-511 */
+	desc->height = ((unsigned)b[8] << 24) | ((unsigned)b[9] << 16) | ((unsigned)b[10] << 8) | b[11];
+	desc->channels = b[12];
+	desc->colorspace = b[13];
+	QoiDescPOD pod = {desc->width, desc->height, desc->channels, desc->colorspace};
+	if (magic != 0x716F6966u || !qoi_geometry_ok(pod)) return NULL; /* qoi.h:513-521 */
+	const int out_ch = channels ? channels : desc->channels;
+	qoi_desc d;
+	memset(&d, 0, sizeof d);
+	d.width = desc->width; d.height = desc->height; d.channels = desc->channels; d.colorspace = desc->colorspace;
+	std::lock_guard<std::mutex> lock(g_mu);
+	qoi_gpu_ctx *ctx = global_ctx();
+	if (!ctx) return NULL;
+	qoi_gpu_plan *p = global_plan(ctx, &d, out_ch);
+	if (!p || plan_mirrors(p)) return NULL;
+	cudaStream_t s = ctx->stream;
+	/* a stream longer than the worst case only carries bytes no op can consume before the image is full */
+	size_t up = (size_t)size;
+	const size_t cap = qoi_max_foreign_stream(pod);
+	int eff_size = size;
+	if (up > cap) { up = cap; eff_size = (int)cap; }
+	const size_t out_bytes = (size_t)d.width * d.height * (size_t)out_ch;
+	void *out = malloc(out_bytes);
+	if (!out) return NULL;
+	p->h_lens_pinned[0] = eff_size;
+	bool ok = cudaMemcpyAsync(p->d_streams, data, up, cudaMemcpyHostToDevice, s) == cudaSuccess &&
+	          cudaMemcpyAsync(p->d_lens, p->h_lens_pinned, sizeof(int32_t), cudaMemcpyHostToDevice, s) == cudaSuccess &&
+	          qoi_gpu_decode(p, p->d_streams, p->d_lens, p->d_decoded, 0, nullptr, s) == QOI_GPU_OK &&
+	          cudaMemcpyAsync(out, p->d_decoded, out_bytes, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+	          cudaStreamSynchronize(s) == cudaSuccess;
+	if (!ok) {
+		free(out);
+		return NULL;
+	}
+	return out;
+}
+
+} /* extern "C" */

@@ -1,0 +1,335 @@
+/*
+ * cuda_emu.h -- a small CPU emulation of the CUDA subset used by cuda/*.cuh.
+ *
+ * TEST INFRASTRUCTURE ONLY.  The build container has no GPU; this header lets
+ * tests/emu/emu_main.cpp compile the *same kernel source* (cuda/qoi_enc.cuh,
+ * cuda/qoi_dec.cuh) with g++ and run it thread-by-thread on the CPU, so that
+ * indexing, scan and decoupled-look-back logic (and deadlocks) can be debugged
+ * before a GPU run.  It is never linked into libqoi_gpu.so and the product has
+ * no CPU path: qoi_b200 / the C ABI fail if the CUDA library or device is missing.
+ *
+ * Model: every CUDA thread is a ucontext fiber on ONE OS thread.  Fibers switch
+ * only at collectives (__syncthreads, warp-wide intrinsics) and in spin waits
+ * (__nanosleep, mbarrier waits), in a seeded random order, so a missing barrier
+ * or a reader running before its writer shows up as a wrong result, and a wait
+ * that can never be satisfied is reported as a deadlock instead of hanging.
+ * Restrictions (the kernels respect them): warp intrinsics are called with the
+ * full mask by all 32 lanes; block size is a multiple of 32; threads do not exit
+ * before their block's last barrier.
+ */
+#pragma once
+#include <ucontext.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __restrict__
+#define __align__(n) __attribute__((aligned(n)))
+
+struct uint2 { uint32_t x, y; };
+struct __attribute__((aligned(16))) uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = {x, y, z, w}; return r; }
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = {x, y}; return r; }
+
+namespace qemu {
+
+struct Idx { unsigned x, y, z; };
+
+struct Warp {
+	uint64_t slot[32];
+	uint64_t result[32];
+	uint32_t arrived = 0;
+	uint32_t gen = 0;
+};
+
+struct Block {
+	std::vector<unsigned char> smem_store;
+	unsigned char *smem = nullptr;
+	unsigned nthreads = 0;
+	unsigned bar_count = 0;
+	unsigned bar_gen = 0;
+	std::vector<Warp> warps;
+	Idx bidx{0, 0, 0};
+};
+
+struct Fiber {
+	ucontext_t ctx;
+	void *stack = nullptr;
+	bool done = false;
+	Block *blk = nullptr;
+	unsigned tid = 0;
+	Idx tidx{0, 0, 0};
+	const char *waiting = "";
+};
+
+inline Fiber *cur = nullptr;
+inline ucontext_t sched_ctx;
+inline Idx g_blockdim{1, 1, 1}, g_griddim{1, 1, 1};
+inline uint64_t progress = 0;
+inline const std::function<void()> *g_body = nullptr;
+inline uint64_t g_switches = 0;
+
+inline void yield(const char *why) {
+	cur->waiting = why;
+	g_switches++;
+	swapcontext(&cur->ctx, &sched_ctx);
+	cur->waiting = "";
+}
+
+inline void trampoline() {
+	(*g_body)();
+	cur->done = true;
+	progress++;
+	swapcontext(&cur->ctx, &sched_ctx);
+}
+
+inline const uint64_t *collect(unsigned mask, uint64_t v, const char *why) {
+	Fiber *f = cur;
+	Warp &w = f->blk->warps[f->tid / 32];
+	unsigned lane = f->tid % 32;
+	if (mask != 0xFFFFFFFFu) {
+		fprintf(stderr, "cuda_emu: warp collective '%s' with partial mask %08x is not supported\n", why, mask);
+		abort();
+	}
+	w.slot[lane] = v;
+	w.arrived |= 1u << lane;
+	if (w.arrived == mask) {
+		memcpy(w.result, w.slot, sizeof w.slot);
+		w.arrived = 0;
+		w.gen++;
+		progress++;
+	} else {
+		unsigned g = w.gen;
+		while (w.gen == g) yield(why);
+	}
+	return w.result;
+}
+
+inline void block_barrier() {
+	Block *b = cur->blk;
+	b->bar_count++;
+	if (b->bar_count == b->nthreads) {
+		b->bar_count = 0;
+		b->bar_gen++;
+		progress++;
+	} else {
+		unsigned g = b->bar_gen;
+		while (b->bar_gen == g) yield("__syncthreads");
+	}
+}
+
+struct LaunchStats { uint64_t switches; };
+
+/* run `body` as a grid of `grid` blocks x `block` threads with `smem_bytes` dynamic shared memory each */
+inline LaunchStats launch(unsigned grid, unsigned block, size_t smem_bytes, const std::function<void()> &body,
+                          unsigned seed = 1) {
+	if (block % 32) { fprintf(stderr, "cuda_emu: block size must be a multiple of 32\n"); abort(); }
+	const size_t STACK = 96 * 1024;
+	std::vector<Block> blocks(grid);
+	std::vector<Fiber> fibers((size_t)grid * block);
+	g_blockdim = {block, 1, 1};
+	g_griddim = {grid, 1, 1};
+	g_body = &body;
+	g_switches = 0;
+	for (unsigned b = 0; b < grid; b++) {
+		blocks[b].smem_store.assign(smem_bytes + 1024, 0xCD); /* poison: uninitialised shared memory is not zero */
+		uintptr_t p = (uintptr_t)blocks[b].smem_store.data();
+		blocks[b].smem = (unsigned char *)((p + 1023) & ~(uintptr_t)1023);
+		blocks[b].nthreads = block;
+		blocks[b].warps.resize(block / 32);
+		blocks[b].bidx = {b, 0, 0};
+		for (unsigned t = 0; t < block; t++) {
+			Fiber &f = fibers[(size_t)b * block + t];
+			f.blk = &blocks[b];
+			f.tid = t;
+			f.tidx = {t, 0, 0};
+			f.stack = malloc(STACK);
+			getcontext(&f.ctx);
+			f.ctx.uc_stack.ss_sp = f.stack;
+			f.ctx.uc_stack.ss_size = STACK;
+			f.ctx.uc_link = nullptr;
+			makecontext(&f.ctx, (void (*)())trampoline, 0);
+		}
+	}
+	std::vector<size_t> order(fibers.size());
+	for (size_t i = 0; i < order.size(); i++) order[i] = i;
+	uint32_t rs = seed * 2654435761u + 12345u;
+	size_t live = fibers.size();
+	int idle_rounds = 0;
+	while (live) {
+		/* new random order each round (seed 0: plain order, useful for reproducing) */
+		if (seed) {
+			for (size_t i = order.size() - 1; i > 0; i--) {
+				rs ^= rs << 13; rs ^= rs >> 17; rs ^= rs << 5;
+				size_t j = rs % (i + 1);
+				std::swap(order[i], order[j]);
+			}
+		}
+		uint64_t before = progress;
+		for (size_t k = 0; k < order.size(); k++) {
+			Fiber &f = fibers[order[k]];
+			if (f.done) continue;
+			cur = &f;
+			swapcontext(&sched_ctx, &f.ctx);
+			if (f.done) live--;
+		}
+		if (progress == before) {
+			if (++idle_rounds >= 4) {
+				fprintf(stderr, "cuda_emu: DEADLOCK -- no thread made progress. Waiting threads:\n");
+				int shown = 0;
+				for (auto &f : fibers)
+					if (!f.done && shown++ < 24)
+						fprintf(stderr, "  block %u thread %u waits in %s\n", f.blk->bidx.x, f.tid, f.waiting);
+				abort();
+			}
+		} else {
+			idle_rounds = 0;
+		}
+	}
+	for (auto &f : fibers) free(f.stack);
+	cur = nullptr;
+	return LaunchStats{g_switches};
+}
+
+}  // namespace qemu
+
+#define threadIdx (qemu::cur->tidx)
+#define blockIdx (qemu::cur->blk->bidx)
+#define blockDim (qemu::g_blockdim)
+#define gridDim (qemu::g_griddim)
+
+/* ---- barriers and warp-wide intrinsics ---- */
+static inline void __syncthreads() { qemu::block_barrier(); }
+static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) { qemu::collect(mask, 0, "__syncwarp"); }
+
+template <class T> static inline T __shfl_sync(unsigned mask, T v, int src) {
+	static_assert(sizeof(T) <= 8, "");
+	uint64_t raw = 0;
+	memcpy(&raw, &v, sizeof(T));
+	const uint64_t *all = qemu::collect(mask, raw, "__shfl_sync");
+	T out;
+	memcpy(&out, &all[src & 31], sizeof(T));
+	return out;
+}
+template <class T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
+	uint64_t raw = 0;
+	memcpy(&raw, &v, sizeof(T));
+	const uint64_t *all = qemu::collect(mask, raw, "__shfl_up_sync");
+	unsigned lane = qemu::cur->tid % 32;
+	T out = v;
+	if (lane >= delta) memcpy(&out, &all[lane - delta], sizeof(T));
+	return out;
+}
+template <class T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta) {
+	uint64_t raw = 0;
+	memcpy(&raw, &v, sizeof(T));
+	const uint64_t *all = qemu::collect(mask, raw, "__shfl_down_sync");
+	unsigned lane = qemu::cur->tid % 32;
+	T out = v;
+	if (lane + delta < 32) memcpy(&out, &all[lane + delta], sizeof(T));
+	return out;
+}
+template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int x) {
+	uint64_t raw = 0;
+	memcpy(&raw, &v, sizeof(T));
+	const uint64_t *all = qemu::collect(mask, raw, "__shfl_xor_sync");
+	unsigned lane = qemu::cur->tid % 32;
+	T out;
+	memcpy(&out, &all[(lane ^ x) & 31], sizeof(T));
+	return out;
+}
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
+	const uint64_t *all = qemu::collect(mask, pred ? 1 : 0, "__ballot_sync");
+	unsigned r = 0;
+	for (int i = 0; i < 32; i++) r |= (unsigned)(all[i] & 1) << i;
+	return r;
+}
+static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
+	const uint64_t *all = qemu::collect(mask, v, "__match_any_sync");
+	unsigned r = 0;
+	for (int i = 0; i < 32; i++) r |= (unsigned)((uint32_t)all[i] == v) << i;
+	return r;
+}
+static inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
+	const uint64_t *all = qemu::collect(mask, v, "__reduce_or_sync");
+	unsigned r = 0;
+	for (int i = 0; i < 32; i++) r |= (unsigned)all[i];
+	return r;
+}
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+	const uint64_t *all = qemu::collect(mask, v, "__reduce_add_sync");
+	unsigned r = 0;
+	for (int i = 0; i < 32; i++) r += (unsigned)all[i];
+	return r;
+}
+static inline int __reduce_max_sync(unsigned mask, int v) {
+	const uint64_t *all = qemu::collect(mask, (uint64_t)(uint32_t)v, "__reduce_max_sync");
+	int r = (int)(uint32_t)all[0];
+	for (int i = 1; i < 32; i++) r = (int)(uint32_t)all[i] > r ? (int)(uint32_t)all[i] : r;
+	return r;
+}
+static inline int __reduce_min_sync(unsigned mask, int v) {
+	const uint64_t *all = qemu::collect(mask, (uint64_t)(uint32_t)v, "__reduce_min_sync");
+	int r = (int)(uint32_t)all[0];
+	for (int i = 1; i < 32; i++) r = (int)(uint32_t)all[i] < r ? (int)(uint32_t)all[i] : r;
+	return r;
+}
+
+/* ---- scalar intrinsics ---- */
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
+	uint64_t both = ((uint64_t)b << 32) | a;
+	unsigned r = 0;
+	for (int i = 0; i < 4; i++) {
+		unsigned sel = (s >> (4 * i)) & 0xF;
+		unsigned byte = (unsigned)(both >> (8 * (sel & 7))) & 0xFF;
+		if (sel & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+		r |= byte << (8 * i);
+	}
+	return r;
+}
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
+	uint64_t both = ((uint64_t)hi << 32) | lo;
+	return (unsigned)(both >> (sh & 31));
+}
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+	for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xFF) * ((b >> (8 * i)) & 0xFF);
+	return c;
+}
+static inline unsigned __vsub4(unsigned a, unsigned b) {
+	unsigned r = 0;
+	for (int i = 0; i < 4; i++) r |= ((((a >> (8 * i)) & 0xFF) - ((b >> (8 * i)) & 0xFF)) & 0xFF) << (8 * i);
+	return r;
+}
+static inline unsigned __vadd4(unsigned a, unsigned b) {
+	unsigned r = 0;
+	for (int i = 0; i < 4; i++) r |= ((((a >> (8 * i)) & 0xFF) + ((b >> (8 * i)) & 0xFF)) & 0xFF) << (8 * i);
+	return r;
+}
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+
+/* ---- memory ---- */
+template <class T> static inline T __ldcg(const T *p) { return *p; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
+template <class T> static inline void __stcg(T *p, T v) { *p = v; qemu::progress++; }
+static inline void __threadfence() {}
+static inline void __threadfence_block() {}
+static inline void __nanosleep(unsigned) { qemu::yield("spin wait"); }
+
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; qemu::progress++; return o; }
+static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; qemu::progress++; return o; }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; qemu::progress++; return o; }
+static inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; qemu::progress++; return o; }
+static inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; qemu::progress++; return o; }

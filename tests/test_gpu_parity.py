@@ -1,0 +1,307 @@
+"""Parity of the CUDA path against the oracle -- runs on the B200 box (pytest -m gpu).
+
+Everything goes through the C ABI (include/qoi.h, include/qoi_gpu.h) via qoi_b200's ctypes binding.
+The checker is the compiled reference (oracle/_ref/libqoi_ref.so) when present, else the restatement
+(oracle/liboracle.so); both are pinned by tests/test_oracle.py.  Bit exact or fail.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import qoi_testlib as q
+
+pytestmark = pytest.mark.gpu
+
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+
+    import qoi_b200
+
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    assert os.path.exists(qoi_b200.library_path()), "libqoi_gpu.so missing: build() was not run"
+    assert qoi_b200.device_count() >= 1
+    ctx = qoi_b200.Context(0)
+    yield qoi_b200, torch, ctx
+    ctx.close()
+
+
+def dev_u8(torch, arr):
+    return torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+
+
+# ------------------------------------------------------------------ reference API (qoi_encode / qoi_decode)
+def test_kat_through_c_api(gpu):
+    qb, _, _ = gpu
+    for case in KAT["encode"]:
+        px = np.array(case["pixels"], dtype=np.uint8)
+        s = qb.encode(px, qb.Desc(case["width"], case["height"], case["channels"], 0))
+        assert s is not None and s.hex() == case["stream"], case["name"]
+    for case in KAT["decode"]:
+        px, d = qb.decode(bytes.fromhex(case["stream"]), case["channels_arg"])
+        assert px is not None and px.tolist() == case["pixels"], case["name"]
+        assert [d.width, d.height, d.channels, d.colorspace] == case["desc"], case["name"]
+
+
+def test_reject_parity(gpu):
+    qb, _, _ = gpu
+    L = qb.lib()
+    for case in KAT["reject"]:
+        if case["kind"] == "encode":
+            d = qb.Desc(case["w"], case["h"], case["ch"], case["cs"])
+            n = C.c_int(-7)
+            one = (C.c_ubyte * 16)()
+            p = L.qoi_encode(one, C.byref(d), C.byref(n))
+            assert (not bool(p)) == case["null"], case
+            if not p:
+                assert n.value == -7
+        else:
+            px, d = qb.decode(bytes.fromhex(case["stream"]), case["channels_arg"])
+            assert (px is None) == case["null"], case["name"]
+            assert [d.width, d.height, d.channels, d.colorspace] == case["desc"], case["name"]
+    d = qb.Desc(1, 1, 4, 0)
+    n = C.c_int(0)
+    one = (C.c_ubyte * 32)()
+    assert not L.qoi_encode(None, C.byref(d), C.byref(n))
+    assert not L.qoi_encode(one, None, C.byref(n))
+    assert not L.qoi_encode(one, C.byref(d), None)
+    assert not L.qoi_decode(None, 30, C.byref(d), 0)
+    assert not L.qoi_decode(one, 30, None, 0)
+
+
+def test_stress_images_c_api(gpu, cpu):
+    qb, _, _ = gpu
+    chk = cpu.best()
+    rng = np.random.default_rng(2024)
+    for it in range(120):
+        w = int(rng.integers(1, 400))
+        h = int(rng.integers(1, 120))
+        ch = int(rng.integers(3, 5))
+        img = q.stress_image(rng, w * h, ch, it % 6)
+        want = chk.encode(img, w, h, ch, it & 1)
+        got = qb.encode(img, qb.Desc(w, h, ch, it & 1))
+        assert got == want, (it, w, h, ch)
+        for c in (0, 3, 4):
+            pa, _ = chk.decode(want, c)
+            pb, d = qb.decode(want, c)
+            assert pb is not None and (pa == pb).all(), (it, c)
+            assert (d.width, d.height, d.channels, d.colorspace) == (w, h, ch, it & 1)
+
+
+def test_tiny_images(gpu, cpu):
+    qb, _, _ = gpu
+    chk = cpu.best()
+    rng = np.random.default_rng(5)
+    for (w, h) in [(1, 1), (2, 1), (1, 3), (61, 1), (62, 1), (63, 1), (64, 64), (4095, 1), (4096, 1), (4097, 1), (8193, 1)]:
+        for ch in (3, 4):
+            for kind in (1, 4):
+                img = q.stress_image(rng, w * h, ch, kind)
+                assert qb.encode(img, qb.Desc(w, h, ch, 0)) == chk.encode(img, w, h, ch)
+
+
+def test_distributions_c_api(gpu, cpu):
+    qb, _, _ = gpu
+    chk = cpu.best()
+    for dist in range(8):
+        for ch in (3, 4):
+            img = cpu.image(640, 360, ch, dist, 3)
+            want = chk.encode(img, 640, 360, ch)
+            assert qb.encode(img, qb.Desc(640, 360, ch, 0)) == want, (dist, ch)
+            pa, _ = chk.decode(want, 4)
+            pb, _ = qb.decode(want, 4)
+            assert (pa == pb).all()
+
+
+def test_foreign_streams(gpu, cpu):
+    qb, _, _ = gpu
+    chk = cpu.best()
+    rng = np.random.default_rng(77)
+    for it in range(150):
+        n = int(rng.integers(1, 3000))
+        s = q.foreign_stream(rng, n, int(rng.integers(3, 5)), truncate=(it % 5 == 0))
+        for c in (0, 3, 4):
+            pa, da = chk.decode(s, c)
+            pb, db = qb.decode(s, c)
+            assert pb is not None and (pa == pb).all() and bytes(da) == bytes(db), (it, c)
+    # arbitrary bytes after a valid header never crash and match the reference (the qoifuzz.c contract)
+    for it in range(60):
+        body = bytes(rng.integers(0, 256, size=int(rng.integers(9, 400)), dtype=np.uint8))
+        s = q.header(int(rng.integers(1, 40)), int(rng.integers(1, 40)), int(rng.integers(3, 5))) + body
+        pa, _ = chk.decode(s, 4)
+        pb, _ = qb.decode(s, 4)
+        assert (pa is None) == (pb is None)
+        if pa is not None:
+            assert (pa == pb).all(), it
+
+
+def test_config1_4096_rgba_bit_exact(gpu, cpu):
+    """BASELINE.json configs[1]: single 4096x4096 RGBA encode, stream bit exact vs qoi.h."""
+    qb, _, _ = gpu
+    chk = cpu.best()
+    for dist in (4, 0, 7):
+        img = cpu.image(4096, 4096, 4, dist)
+        want = chk.encode(img, 4096, 4096, 4)
+        got = qb.encode(img, qb.Desc(4096, 4096, 4, 0))
+        assert got == want, dist
+        px, _ = qb.decode(got, 4)
+        assert (px == img).all()
+
+
+# ------------------------------------------------------------------ batch / device API
+def run_batch(gpu, cpu, descs_whc, dist_or_imgs, mis=0, dec_ch=4, odd_slots=False, repeat=1):
+    qb, torch, ctx = gpu
+    chk = cpu.best()
+    descs = [qb.Desc(w, h, c, i & 1) for i, (w, h, c) in enumerate(descs_whc)]
+    sizes = [w * h * c for (w, h, c) in descs_whc]
+    poff = mis + np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    if odd_slots:
+        slot = [((qb.max_stream_size(w, h, c) + 41) | 1) for (w, h, c) in descs_whc]
+        soff = 5 + np.concatenate([[0], np.cumsum(slot)[:-1]])
+    else:
+        soff = None
+    plan = qb.Plan(ctx, descs, pixel_off=poff, stream_off=soff, decoded_channels=dec_ch)
+    host = np.zeros(plan.pixel_bytes, dtype=np.uint8)
+    imgs = []
+    for i, (w, h, c) in enumerate(descs_whc):
+        img = dist_or_imgs[i] if isinstance(dist_or_imgs, list) else cpu.image(w, h, c, dist_or_imgs, i)
+        imgs.append(img)
+        host[int(poff[i]):int(poff[i]) + sizes[i]] = img
+    d_pix = dev_u8(torch, host)
+    d_streams = torch.full((plan.stream_bytes + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+    d_lens = torch.full((plan.n,), -1, dtype=torch.int32, device="cuda")
+    d_dec = torch.full((plan.decoded_bytes + 16,), 0xAB, dtype=torch.uint8, device="cuda")
+    d_status = torch.full((plan.n,), -1, dtype=torch.int32, device="cuda")
+    for _ in range(repeat):
+        d_streams.fill_(0xEE)
+        plan.encode(d_pix.data_ptr(), d_streams.data_ptr(), d_lens.data_ptr())
+        torch.cuda.synchronize()
+        lens = d_lens.cpu().numpy()
+        streams = d_streams.cpu().numpy()
+        for i, (w, h, c) in enumerate(descs_whc):
+            want = chk.encode(imgs[i], w, h, c, i & 1)
+            o = int(plan.stream_off[i])
+            assert lens[i] == len(want), (i, lens[i], len(want))
+            assert streams[o:o + lens[i]].tobytes() == want, i
+            assert streams[o + lens[i]] == 0xEE and (o == 0 or streams[o - 1] == 0xEE), "wrote outside the stream"
+        for use_index in (True, False):
+            d_dec.fill_(0xAB)
+            plan.decode(d_streams.data_ptr(), d_lens.data_ptr(), d_dec.data_ptr(), use_index=use_index, d_status=d_status.data_ptr())
+            torch.cuda.synchronize()
+            assert (d_status.cpu().numpy() == 0).all()
+            dec = d_dec.cpu().numpy()
+            assert dec[plan.decoded_bytes] == 0xAB
+            for i, (w, h, c) in enumerate(descs_whc):
+                want_px, _ = chk.decode(streams[int(plan.stream_off[i]):int(plan.stream_off[i]) + lens[i]].tobytes(), dec_ch)
+                o = int(plan._dec_off_eff[i])
+                assert (dec[o:o + w * h * dec_ch] == want_px).all(), (i, use_index)
+    plan.close()
+
+
+def test_batch_rgba_aligned(gpu, cpu):
+    run_batch(gpu, cpu, [(512, 256, 4)] * 6, 4, repeat=3)
+
+
+def test_batch_all_distributions(gpu, cpu):
+    for dist in range(8):
+        run_batch(gpu, cpu, [(300, 200, 4)] * 3, dist)
+        run_batch(gpu, cpu, [(300, 200, 3)] * 3, dist, dec_ch=4)
+
+
+def test_batch_misaligned_and_mixed_sizes(gpu, cpu):
+    run_batch(gpu, cpu, [(97, 23, 4), (1, 1, 4), (211, 87, 4), (64, 64, 4), (4096, 2, 4)], 3, mis=4, odd_slots=True)
+    run_batch(gpu, cpu, [(97, 23, 4), (33, 5, 4)], 6, mis=7, odd_slots=True, dec_ch=3)
+    run_batch(gpu, cpu, [(97, 23, 3), (1, 1, 3), (211, 87, 3), (64, 64, 3), (4097, 3, 3)], 4, mis=1, odd_slots=True, dec_ch=3)
+    run_batch(gpu, cpu, [(129, 77, 3)] * 4, 2, mis=0, dec_ch=4)
+
+
+def test_batch_stress_content(gpu, cpu):
+    rng = np.random.default_rng(31337)
+    for kind in range(6):
+        for ch in (3, 4):
+            whc = [(int(rng.integers(50, 500)), int(rng.integers(20, 200)), ch) for _ in range(4)]
+            imgs = [q.stress_image(rng, w * h, ch, kind) for (w, h, _) in whc]
+            run_batch(gpu, cpu, whc, imgs, dec_ch=4 if kind % 2 else ch)
+
+
+def test_long_runs_across_many_tiles(gpu, cpu):
+    """runs spanning dozens of tiles, the start-colour run, and the all-zero image (INDEX into an untouched slot)."""
+    n = 300 * 1000
+    a = np.zeros((n, 4), dtype=np.uint8); a[:, 3] = 255                      # start colour only
+    b = np.zeros((n, 4), dtype=np.uint8)                                      # {0,0,0,0}
+    c = np.zeros((n, 4), dtype=np.uint8); c[:, 3] = 255; c[n // 2:] = (9, 9, 9, 255); c[-5:] = (0, 0, 0, 255)
+    d = np.full((n, 4), 200, dtype=np.uint8); d[100000] = (1, 2, 3, 4)
+    run_batch(gpu, cpu, [(1000, 300, 4)] * 4, [a.reshape(-1), b.reshape(-1), c.reshape(-1), d.reshape(-1)])
+
+
+def test_config2_small_batch_1080p_rgb(gpu, cpu):
+    """BASELINE.json configs[2] shape (1920x1080 RGB, decode to 4 channels) at a batch the CPU checker finishes quickly."""
+    run_batch(gpu, cpu, [(1920, 1080, 3)] * 8, 4, dec_ch=4)
+
+
+def test_roundtrip_8192_device_resident(gpu, cpu):
+    """BASELINE.json configs[3] image size: 8192x8192 RGBA, checked by the size-independent property
+    decode(encode(x)) == x on the device, plus out_len against the CPU for one image."""
+    qb, torch, ctx = gpu
+    w = h = 8192
+    n = 2
+    plan = qb.Plan(ctx, [qb.Desc(w, h, 4, 0)] * n, decoded_channels=4)
+    host = cpu.batch(n, w, h, 4, 4, first=11)
+    d_pix = dev_u8(torch, host)
+    d_streams = torch.empty(plan.stream_bytes, dtype=torch.uint8, device="cuda")
+    d_lens = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_dec = torch.zeros(plan.decoded_bytes, dtype=torch.uint8, device="cuda")
+    plan.encode(d_pix.data_ptr(), d_streams.data_ptr(), d_lens.data_ptr())
+    for use_index in (True, False):
+        d_dec.zero_()
+        plan.decode(d_streams.data_ptr(), d_lens.data_ptr(), d_dec.data_ptr(), use_index=use_index)
+        torch.cuda.synchronize()
+        assert torch.equal(d_dec, d_pix), use_index
+    want = cpu.best().encode(host[: w * h * 4], w, h, 4)
+    assert int(d_lens[0]) == len(want)
+    o = int(plan.stream_off[0])
+    assert d_streams[o:o + len(want)].cpu().numpy().tobytes() == want
+    plan.close()
+
+
+def test_host_buffer_api(gpu, cpu):
+    qb, _, ctx = gpu
+    chk = cpu.best()
+    whc = [(320, 240, 4)] * 5
+    descs = [qb.Desc(w, h, c, 0) for (w, h, c) in whc]
+    plan = qb.Plan(ctx, descs, decoded_channels=4)
+    host = cpu.batch(5, 320, 240, 4, 4)
+    streams = np.zeros(plan.stream_bytes, dtype=np.uint8)
+    lens = np.zeros(5, dtype=np.int32)
+    plan.encode_host(host, streams, lens)
+    for i in range(5):
+        want = chk.encode(host[i * 320 * 240 * 4:(i + 1) * 320 * 240 * 4], 320, 240, 4)
+        o = int(plan.stream_off[i])
+        assert streams[o:o + lens[i]].tobytes() == want
+    for use_index in (True, False):
+        dec = np.zeros(plan.decoded_bytes, dtype=np.uint8)
+        plan.decode_host(streams, lens, dec, use_index=use_index)
+        assert (dec == host).all()
+    plan.close()
+
+
+def test_header_mismatch_is_reported(gpu, cpu):
+    qb, torch, ctx = gpu
+    plan = qb.Plan(ctx, [qb.Desc(64, 64, 4, 0)] * 2, decoded_channels=4)
+    img = cpu.batch(2, 64, 64, 4, 4)
+    d_pix = dev_u8(torch, img)
+    d_streams = torch.zeros(plan.stream_bytes, dtype=torch.uint8, device="cuda")
+    d_lens = torch.zeros(2, dtype=torch.int32, device="cuda")
+    d_dec = torch.zeros(plan.decoded_bytes, dtype=torch.uint8, device="cuda")
+    d_status = torch.zeros(2, dtype=torch.int32, device="cuda")
+    plan.encode(d_pix.data_ptr(), d_streams.data_ptr(), d_lens.data_ptr())
+    d_streams[int(plan.stream_off[1]) + 7] = 65  # corrupt the width of image 1
+    plan.decode(d_streams.data_ptr(), d_lens.data_ptr(), d_dec.data_ptr(), use_index=False, d_status=d_status.data_ptr())
+    torch.cuda.synchronize()
+    assert d_status.cpu().tolist() == [0, 4]
+    plan.close()

@@ -1,0 +1,31 @@
+#!/bin/bash
+# One GPU-box session: smoke -> gpu tests -> bench -> ncu launch list -> ncu full capture.
+# Everything is bounded by `timeout`; all logs go to gpurun_out/.  Usage: tools/gpu_round.sh [quick|full|prof]
+MODE=${1:-full}
+mkdir -p gpurun_out
+exec > >(tee gpurun_out/round.log) 2>&1
+set -x
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.max.mem --format=csv
+nproc; free -g | head -2
+export PYTHONUNBUFFERED=1
+timeout 300 python __graft_entry__.py smoke; echo "SMOKE_RC=$?"
+if [ "$MODE" != "prof" ]; then
+  timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -40; echo "PYTEST_RC=${PIPESTATUS[0]}"
+fi
+if [ "$MODE" = "quick" ]; then exit 0; fi
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "BENCH_RC=$?"
+cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+for d in 0 7 2 6; do
+  timeout 600 python bench.py --steps 5 --warmup 3 --dist $d --no-cpu --e2e-steps 1 > gpurun_out/bench_dist$d.json 2>> gpurun_out/bench.err; echo "BENCH_DIST${d}_RC=$?"
+  cat gpurun_out/bench_dist$d.json
+done
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; echo "REF_RC=$?"
+cat gpurun_out/bench_ref.json
+# launch list (cold-cache, serialised: shares only)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 3 --batch 8 --no-cpu --e2e-steps 1 > gpurun_out/ncu_bench.log 2>&1; echo "NCU_LIST_RC=$?"
+grep -c qoi gpurun_out/launches.csv
+# full capture of the two kernels (3 launches each, after warm-up)
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:qoi_ -s 6 -c 4 -o gpurun_out/prof -f \
+    python bench.py --steps 2 --warmup 3 --batch 8 --no-cpu --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1; echo "NCU_FULL_RC=$?"
+ls -la gpurun_out
