@@ -5,9 +5,10 @@
 #include <stdint.h>
 
 #define QOI_TILE_PX 4096        /* pixels per encoder tile (== QOI_GPU_TILE_PX) */
-#define QOI_ENC_THREADS 256
-#define QOI_ENC_WARPS 8
-#define QOI_PX_PER_THREAD 16    /* QOI_TILE_PX / QOI_ENC_THREADS */
+#define QOI_ENC_THREADS 288      /* 8 compute warps + 1 scout warp */
+#define QOI_ENC_COMPUTE 256
+#define QOI_ENC_WARPS 8         /* compute warps */
+#define QOI_PX_PER_THREAD 16    /* QOI_TILE_PX / QOI_ENC_COMPUTE */
 #define QOI_WARP_PX 512         /* pixels per warp chunk */
 #define QOI_WARP_STEPS 16       /* 32-pixel steps per warp chunk */
 #define QOI_HEADER_BYTES 14
@@ -25,25 +26,35 @@ struct QoiImgMeta {
 	uint8_t channels, colorspace, pad[6];
 };
 
-/* look-back status word: (epoch << 2) | state */
+/*
+ * Look-back records are self-validating 64-bit words: every word carries the epoch of the launch that
+ * wrote it, so a reader needs no fence and no ordering between words -- it just re-reads a word until
+ * the epoch matches (relaxed gpu-scope loads/stores, L2 coherent).
+ *
+ *   table entry   [63:32] pixel value     [31:1] epoch  [0] slot written
+ *   summary word  [63:32] payload         [31:0] epoch           (payload: valid-mask half / last non-run index)
+ *   byte state    [63:34] epoch  [33:32] state  [31:0] bytes
+ */
 #define QOI_ST_NONE 0u
 #define QOI_ST_AGG 1u  /* the tile's own aggregate is published */
 #define QOI_ST_INC 2u  /* the inclusive prefix (everything up to and including this tile) is published */
 
+#define QOI_SUM_VALID_LO 0
+#define QOI_SUM_VALID_HI 1
+#define QOI_SUM_LNR 2
+#define QOI_SUM_WORDS 4 /* stride per tile (32 bytes) */
+
 /*
  * Per-tile chained-scan state; after an encode it doubles as the decoder's restart index:
- * the state a decoder needs at the start of tile t is inc_* of tile t-1 plus rs_* of tile t.
+ * the state a decoder needs at the start of tile t is inc_ent of tile t-1 plus rs_* of tile t.
  */
 struct QoiTileState {
 	uint32_t *ticket;      /* [2]: next tile to hand out, number of CTAs that finished */
-	uint32_t *tab_status;  /* [tiles] table/run look-back status */
-	uint32_t *agg_tab;     /* [tiles][64] last non-run pixel value per hash slot inside the tile */
-	uint64_t *agg_valid;   /* [tiles] bit s: slot s written inside the tile */
-	int32_t *agg_lnr;      /* [tiles] image pixel index of the tile's last non-run pixel, or QOI_LNR_NONE */
-	uint32_t *inc_tab;     /* [tiles][64] table after the tile (what qoi.h's index[] holds there) */
-	uint64_t *inc_valid;   /* [tiles] */
-	int32_t *inc_lnr;      /* [tiles] last non-run pixel index up to the tile's end, -1 if none yet */
-	uint64_t *byte_state;  /* [tiles] (epoch<<34)|(state<<32)|bytes : output-offset look-back */
+	uint64_t *agg_ent;     /* [tiles][64] last non-run pixel per hash slot INSIDE the tile */
+	uint64_t *agg_sum;     /* [tiles][4]  valid mask halves, last non-run pixel index (QOI_LNR_NONE: none) */
+	uint64_t *inc_ent;     /* [tiles][64] table after the tile == what qoi.h's index[] holds there */
+	uint64_t *inc_sum;     /* [tiles][4]  same, inclusive (last non-run index: -1 if none yet) */
+	uint64_t *byte_state;  /* [tiles] output-offset look-back */
 	int32_t *rs_px;        /* [tiles] first pixel of the tile at which an op starts (-1: none) */
 	int32_t *rs_byte;      /* [tiles] stream offset of that op */
 	uint32_t *rs_prev;     /* [tiles] value of the pixel before it */

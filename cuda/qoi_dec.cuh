@@ -10,15 +10,17 @@
  *       reference's initial state (qoi.h:533-537);
  *   stream written by qoi_encode_kernel (use_index = 1): one segment per
  *       encoder tile.  The chained scan already materialised the state at every
- *       tile boundary: index[] after tile t-1 is inc_tab[t-1], and rs_px /
+ *       tile boundary: index[] after tile t-1 is inc_ent[t-1], and rs_px /
  *       rs_byte / rs_prev give the first op that starts inside tile t, where it
  *       lies in the stream and the pixel before it.  The index is a side table
  *       in HBM; the stream itself carries nothing extra and stays bit exact.
  *
  * One LANE per segment (not one warp): each lane runs the scalar state machine
  * with its 64-entry table in shared memory, laid out [slot][thread] so that any
- * slot pattern across the lanes is bank-conflict free.  All lanes produce one
- * pixel per loop trip, so pixel stores stay converged.
+ * slot pattern across the lanes is bank-conflict free.  Stream bytes come through
+ * a per-lane 64-bit window refilled with aligned 32-bit loads (never past the
+ * stream's last byte); all lanes produce one pixel per loop trip, so pixels leave
+ * in groups of four with one 16-byte store per lane.
  */
 #pragma once
 #include "qoi_common.h"
@@ -32,6 +34,18 @@ using namespace qoidev;
 __device__ __forceinline__ uint32_t be32(const uint8_t *p) {
 	return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
 }
+
+/* per-byte add mod 256 of two packed words (no carries between bytes) */
+__device__ __forceinline__ uint32_t add_bytes(uint32_t a, uint32_t b) {
+	return ((a & 0x7F7F7F7Fu) + (b & 0x7F7F7F7Fu)) ^ ((a ^ b) & 0x80808080u);
+}
+
+struct Reader {
+	const uint32_t *wp; /* next aligned word to load */
+	uint64_t buf;       /* the next `avail` stream bytes, lowest byte first */
+	uint32_t avail;
+	int32_t p;          /* stream offset of buf's first byte */
+};
 
 template <int OUT_CH, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P) {
@@ -68,13 +82,13 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 	if (!ok) return;
 
 	uint32_t px_begin = 0, px_end = m.npx;
-	int32_t p = QOI_HEADER_BYTES;
+	int32_t p0 = QOI_HEADER_BYTES;
 	uint32_t px = 0xFF000000u; /* {0,0,0,255}, qoi.h:534-537 */
 	if (P.use_index) {
 		const int32_t b = P.st.rs_px[job];
 		if (b < 0) return; /* the image ends before an op starts in this tile */
 		px_begin = (uint32_t)b;
-		p = P.st.rs_byte[job];
+		p0 = P.st.rs_byte[job];
 		px = P.st.rs_prev[job];
 		const uint32_t tiles = (m.npx + QOI_TILE_PX - 1) / QOI_TILE_PX;
 		if (job + 1 < m.first_tile + tiles) {
@@ -87,54 +101,125 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 #pragma unroll 8
 		for (int k = 0; k < 64; k++) tab[k * BLOCK] = 0;
 	} else {
-		const uint64_t valid = P.st.inc_valid[job - 1];
-		const uint32_t *src = P.st.inc_tab + (size_t)(job - 1) * 64;
+		const uint64_t *src = P.st.inc_ent + (size_t)(job - 1) * 64; /* [63:32] value, bit 0: slot written */
 #pragma unroll 8
-		for (int k = 0; k < 64; k++) tab[k * BLOCK] = ((valid >> k) & 1ull) ? src[k] : 0u;
+		for (int k = 0; k < 64; k++) {
+			const uint64_t e = src[k];
+			tab[k * BLOCK] = (e & 1ull) ? (uint32_t)(e >> 32) : 0u;
+		}
 		/* the reference DEcoder also stores the current colour after a RUN op (qoi.h:577); the ENcoder's
 		   table does not see the leading run of the start colour.  Only slot 53 can differ, and only
 		   until a pixel hashing to 53 is coded. */
 		const uint32_t op0 = s[QOI_HEADER_BYTES];
-		if (!((valid >> 53) & 1ull) && (op0 & 0xC0u) == 0xC0u && op0 < 0xFEu) tab[53 * BLOCK] = 0xFF000000u;
+		if (!(src[53] & 1ull) && (op0 & 0xC0u) == 0xC0u && op0 < 0xFEu) tab[53 * BLOCK] = 0xFF000000u;
 	}
 
 	const int32_t stop = size - QOI_END_BYTES; /* qoi.h:539 */
-	uint8_t *out = P.out + m.dec_off + (uint64_t)px_begin * OUT_CH;
+	Reader rd;
+	{
+		const uintptr_t a = (uintptr_t)(s + p0);
+		rd.wp = (const uint32_t *)(a & ~(uintptr_t)3);
+		rd.p = p0;
+		rd.buf = 0;
+		rd.avail = 0;
+		if (p0 < stop) { /* the word holding byte p0 lies inside the stream */
+			const uint32_t mis = (uint32_t)(a & 3u);
+			rd.buf = (uint64_t)(__ldg(rd.wp++) >> (8u * mis));
+			rd.avail = 4u - mis;
+		}
+	}
 	uint32_t run = 0;
-	for (uint32_t i = px_begin; i < px_end; i++) {
+
+	/* one pixel: qoi.h:541-578 */
+	auto step = [&]() -> uint32_t {
 		if (run > 0) {
 			run--;
-		} else if (p < stop) {
-			const uint32_t b1 = s[p++];
-			if (b1 == 0xFEu) { /* qoi.h:547-551 */
-				px = (px & 0xFF000000u) | (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16);
-				p += 3;
-			} else if (b1 == 0xFFu) { /* qoi.h:552-557 */
-				px = (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
-				p += 4;
-			} else if ((b1 & 0xC0u) == 0x00u) { /* qoi.h:558-560 */
-				px = tab[b1 * BLOCK];
-			} else if ((b1 & 0xC0u) == 0x40u) { /* qoi.h:561-565: +(-2..1) per channel, wrapping */
-				const uint32_t add = ((((b1 >> 4) & 3u) + 254u) & 0xFFu) | (((((b1 >> 2) & 3u) + 254u) & 0xFFu) << 8) | ((((b1 & 3u) + 254u) & 0xFFu) << 16);
-				px = __vadd4(px, add);
-			} else if ((b1 & 0xC0u) == 0x80u) { /* qoi.h:566-572 */
-				const uint32_t b2 = s[p++];
-				const uint32_t vg = (b1 & 0x3Fu) + 224u; /* -32 mod 256 */
-				const uint32_t add = ((vg + 248u + ((b2 >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((vg + 248u + (b2 & 0xFu)) & 0xFFu) << 16);
-				px = __vadd4(px, add);
-			} else { /* qoi.h:573-575 */
-				run = b1 & 0x3Fu;
+		} else if (rd.p < stop) {
+			/* an op needs at most 5 bytes; a refill word starts at or before byte p+4 <= size-5, so no load crosses `size` */
+			if (rd.avail < 5u) {
+				rd.buf |= (uint64_t)__ldg(rd.wp++) << (8u * rd.avail);
+				rd.avail += 4u;
+				if (rd.avail < 5u) {
+					rd.buf |= (uint64_t)__ldg(rd.wp++) << (8u * rd.avail);
+					rd.avail += 4u;
+				}
 			}
+			const uint32_t tag = (uint32_t)rd.buf & 0xFFu;
+			const uint32_t pay = (uint32_t)(rd.buf >> 8); /* the four bytes after the tag */
+			uint32_t len = 1;
+			if (tag >= 0xFEu) {
+				if (tag == 0xFEu) { /* qoi.h:547-551 */
+					px = (px & 0xFF000000u) | (pay & 0x00FFFFFFu);
+					len = 4;
+				} else { /* qoi.h:552-557 */
+					px = pay;
+					len = 5;
+				}
+			} else {
+				const uint32_t top = tag >> 6;
+				if (top == 0u) { /* qoi.h:558-560 */
+					px = tab[tag * BLOCK];
+				} else if (top == 1u) { /* qoi.h:561-565: each channel += field - 2, wrapping */
+					const uint32_t sel = ((tag >> 4) & 3u) | (((tag >> 2) & 3u) << 4) | ((tag & 3u) << 8) | 0x4000u;
+					px = add_bytes(px, __byte_perm(0x0100FFFEu, 0u, sel)); /* LUT: 0,1,2,3 -> -2,-1,0,+1 */
+				} else if (top == 2u) { /* qoi.h:566-572 */
+					const uint32_t vg = (tag & 0x3Fu) + 224u; /* -32 mod 256 */
+					const uint32_t rb = vg + 248u;            /* vg - 8 */
+					const uint32_t add = ((rb + ((pay >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((rb + (pay & 0xFu)) & 0xFFu) << 16);
+					px = add_bytes(px, add);
+					len = 2;
+				} else { /* qoi.h:573-575 */
+					run = tag & 0x3Fu;
+				}
+			}
+			rd.buf >>= 8u * len;
+			rd.avail -= len;
+			rd.p += (int32_t)len;
 			tab[qoi_slot(px) * BLOCK] = px; /* qoi.h:577 */
 		}
-		if (OUT_CH == 4) {
-			*(uint32_t *)out = px;
-		} else {
-			out[0] = (uint8_t)px;
-			out[1] = (uint8_t)(px >> 8);
-			out[2] = (uint8_t)(px >> 16);
+		return px;
+	};
+
+	uint8_t *obase = P.out + m.dec_off;
+	uint32_t i = px_begin;
+	if (OUT_CH == 4) {
+		uint32_t *o32 = (uint32_t *)obase;
+		const bool vec_ok = ((uintptr_t)obase & 15u) == 0;
+		while (i < px_end && (!vec_ok || (i & 3u))) { /* head (or everything, if the destination is not 16-byte aligned) */
+			o32[i] = step();
+			i++;
 		}
-		out += OUT_CH;
+		while (i + 4 <= px_end) {
+			const uint32_t a = step(), b = step(), c = step(), d = step();
+			*(uint4 *)(o32 + i) = make_uint4(a, b, c, d);
+			i += 4;
+		}
+		while (i < px_end) {
+			o32[i] = step();
+			i++;
+		}
+	} else {
+		const bool vec_ok = ((uintptr_t)obase & 3u) == 0;
+		while (i < px_end && (!vec_ok || (i & 3u))) {
+			const uint32_t a = step();
+			uint8_t *o = obase + (size_t)i * 3;
+			o[0] = (uint8_t)a; o[1] = (uint8_t)(a >> 8); o[2] = (uint8_t)(a >> 16);
+			i++;
+		}
+		while (i + 4 <= px_end) { /* 4 pixels = 12 bytes = three aligned words */
+			const uint32_t a = step(), b = step(), c = step(), d = step();
+			uint32_t *o = (uint32_t *)(obase + (size_t)i * 3);
+			o[0] = (a & 0x00FFFFFFu) | (b << 24);
+			o[1] = ((b >> 8) & 0x0000FFFFu) | (c << 16);
+			o[2] = ((c >> 16) & 0x000000FFu) | (d << 8);
+			i += 4;
+		}
+		while (i < px_end) {
+			const uint32_t a = step();
+			uint8_t *o = obase + (size_t)i * 3;
+			o[0] = (uint8_t)a; o[1] = (uint8_t)(a >> 8); o[2] = (uint8_t)(a >> 16);
+			i++;
+		}
 	}
 }
 

@@ -85,6 +85,23 @@ __device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p) {
 __device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v) {
 	asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
+	uint64_t v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+/* named barriers: producer/consumer hand-off between the scout warp and the compute warps.  The non-.aligned
+   forms are used because lanes of a warp may reach them along different paths (deferred / patched pixels). */
+__device__ __forceinline__ void bar_sync(uint32_t id, uint32_t nthreads) {
+	asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t nthreads) {
+	__threadfence_block();
+	asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void spin_pause() { __nanosleep(32); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -158,6 +175,10 @@ static inline uint32_t ld_acquire_u32(const uint32_t *p) { return *p; }
 static inline void st_release_u32(uint32_t *p, uint32_t v) { *p = v; qemu::progress++; }
 static inline uint64_t ld_acquire_u64(const uint64_t *p) { return *p; }
 static inline void st_release_u64(uint64_t *p, uint64_t v) { *p = v; qemu::progress++; }
+static inline uint64_t ld_relaxed_u64(const uint64_t *p) { return *p; }
+static inline void st_relaxed_u64(uint64_t *p, uint64_t v) { *p = v; qemu::progress++; }
+static inline void bar_sync(uint32_t id, uint32_t nthreads) { qemu::named_barrier(id, nthreads, true); }
+static inline void bar_arrive(uint32_t id, uint32_t nthreads) { qemu::named_barrier(id, nthreads, false); }
 static inline void spin_pause() { qemu::yield("spin wait"); }
 static inline uint32_t lane_id() { return threadIdx.x & 31u; }
 static inline uint32_t lanemask_lt() { return (1u << lane_id()) - 1u; }

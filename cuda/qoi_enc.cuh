@@ -6,33 +6,45 @@
  * by px_prev, a run counter, index[64] and the output cursor p; here each of
  * these becomes a scan over 4096-pixel tiles (order-free form):
  *
- *   run position      k(i) = i - (last non-run pixel before i)         max-scan
+ *   run position      k(i) = i - (last non-run pixel before i)              max-scan
  *   INDEX hit         value of the previous NON-RUN pixel with the same
- *                     hash slot equals this pixel (64 "last writer" lanes) 64-wide last-writer scan
- *   output offset     exclusive prefix sum of the bytes each pixel emits  +-scan
+ *                     hash slot equals this pixel                           64-wide last-writer scan
+ *   output offset     exclusive prefix sum of the bytes each pixel emits    +-scan
  *
  * Persistent CTAs take tiles from an atomic ticket (so every predecessor of a
  * running tile is itself running or finished) and publish / look back through
- * per-tile records in HBM (decoupled look-back).  Pixels are read ONCE: a 1-D
- * TMA bulk copy (cp.async.bulk, SASS UBLKCP) brings the next tile into shared
- * memory while the current one is processed; op bytes are assembled in a shared
- * staging buffer whose alignment is congruent to the destination, and leave
- * with one TMA bulk store plus <16-byte edges.
+ * per-tile records in HBM (decoupled look-back, fence-free: every 64-bit record
+ * word carries its launch epoch).  Pixels are read ONCE: a 1-D TMA bulk copy
+ * (cp.async.bulk, SASS UBLKCP) brings the next tile into shared memory while the
+ * current one is processed; op bytes are assembled in a shared staging buffer
+ * whose alignment is congruent to the destination and leave with one TMA bulk
+ * store plus <16-byte edges.
  *
- * Phases per tile (256 threads, 8 warps, 512 px per warp, 16 px per thread):
- *   E  (EXPAND only) raw RGB / unaligned RGBA bytes -> aligned RGBA words
- *   I  "index pass", striped: 32 consecutive pixels per step across the lanes;
- *      __match_any_sync on the hash slot finds the in-step predecessor, a
- *      per-warp 64-entry table carries across steps; first occurrences of a
- *      slot in the warp chunk are deferred (at most 64 per warp)
- *   T  warp 0: tile aggregate (last writer per slot, last non-run index) is
- *      published, predecessors are looked back, inclusive record published
- *   R  deferred first occurrences are resolved against earlier warps / T_in
- *   C  "classify pass", blocked: each thread walks its 16 consecutive pixels,
- *      decides RUN / INDEX / DIFF / LUMA / RGB / RGBA exactly like qoi.h:415-474,
- *      block-scans the byte counts
- *   B  warp 0: byte-offset look-back (32 predecessors per probe)
- *   W  bytes -> staging -> global; header / end marker / length / restart entry
+ * CTA = 8 compute warps (512 px each, 16 px per thread) + 1 scout warp.
+ *
+ *   compute warps                                   scout warp
+ *   -------------                                   ----------
+ *   wait tile bytes (mbarrier)                      ticket + TMA for the NEXT tile
+ *   E  (EXPAND only) raw bytes -> RGBA words
+ *   I  index pass, striped: 32 consecutive px per
+ *      step; same-slot lanes from 6 ballots of the
+ *      hash bits, per-warp 64-entry table across
+ *      steps; first occurrences of a slot in the
+ *      warp chunk are deferred (<= 64 per warp)
+ *        ---- I_DONE ---->                          T  tile aggregate published; 32-tile window
+ *   C0 classify pass, blocked, with provisional        look-back for the incoming table + last
+ *      hit bits: RUN / INDEX / DIFF / LUMA / RGB /      non-run index; inclusive record published
+ *      RGBA exactly like qoi.h:415-474
+ *        <--- T_READY ----
+ *   R  resolve deferred occurrences (T_in, earlier warps)
+ *   C1 patch pixels whose hit bit changed; threads that
+ *      start inside a run carried from before redo C0
+ *      block scan of byte counts
+ *        ---- C_DONE ---->                          B  output-offset look-back (32 tiles/probe)
+ *        <--- B_READY ----
+ *   W  op bytes -> staging; restart entry
+ *        ---- W_DONE ---->                          staging -> global (TMA store + edges), header,
+ *                                                   end marker, length
  */
 #pragma once
 #include <limits.h>
@@ -58,6 +70,8 @@ struct TileInfo {
 	uint32_t pad[3];
 };
 
+enum { BAR_COMPUTE = 1, BAR_I_DONE = 2, BAR_T_READY = 3, BAR_C_DONE = 4, BAR_B_READY = 5, BAR_W_DONE = 6 };
+
 template <int CH, bool EXPAND>
 struct Layout {
 	static constexpr int RAW_STRIDE = 16 + 16 + QOI_TILE_PX * CH + 16;
@@ -66,14 +80,13 @@ struct Layout {
 	static constexpr int PXBUF_BYTES = EXPAND ? (16 + QOI_TILE_PX * 4 + 16) : 0;
 	static constexpr int OFF_STAGE = OFF_PXBUF + PXBUF_BYTES;
 	static constexpr int STAGE_BYTES = 16 + QOI_TILE_PX * (CH + 1) + 16;
-	static constexpr int OFF_LVAL = OFF_STAGE + STAGE_BYTES;          /* u32 [8][64] */
-	static constexpr int OFF_TINVAL = OFF_LVAL + 8 * 64 * 4;          /* u32 [64] */
+	static constexpr int OFF_LENT = OFF_STAGE + STAGE_BYTES;          /* uint2 [8][64]: {value, written} */
+	static constexpr int OFF_TINVAL = OFF_LENT + 8 * 64 * 8;          /* u32 [64] */
 	static constexpr int OFF_HITW = OFF_TINVAL + 64 * 4;              /* u32 [128] */
 	static constexpr int OFF_NRW = OFF_HITW + 128 * 4;                /* u32 [128] */
 	static constexpr int OFF_LNRS = OFF_NRW + 128 * 4;                /* i32 [128] */
 	static constexpr int OFF_FPOS = OFF_LNRS + 128 * 4;               /* u16 [8][64] */
-	static constexpr int OFF_LFLAG = OFF_FPOS + 8 * 64 * 2;           /* u8 [8][64] */
-	static constexpr int OFF_TINFLAG = OFF_LFLAG + 8 * 64;            /* u8 [64] */
+	static constexpr int OFF_TINFLAG = OFF_FPOS + 8 * 64 * 2;         /* u8 [64] */
 	static constexpr int OFF_MBAR = OFF_TINFLAG + 64;                 /* u64 [2] */
 	static constexpr int OFF_INFO = OFF_MBAR + 16;                    /* TileInfo [2] */
 	static constexpr int OFF_NBR = OFF_INFO + 2 * (int)sizeof(TileInfo); /* u32 [2][2] */
@@ -83,7 +96,7 @@ struct Layout {
 	static constexpr int OFF_MISC = OFF_WLNRIN + 32;                  /* u32 [8] */
 	static constexpr int TOTAL = OFF_MISC + 32;
 	static_assert(sizeof(TileInfo) % 16 == 0, "TileInfo must keep 16-byte alignment of what follows");
-	static_assert(OFF_STAGE % 16 == 0 && OFF_LVAL % 16 == 0 && OFF_MBAR % 8 == 0, "alignment");
+	static_assert(OFF_STAGE % 16 == 0 && OFF_LENT % 16 == 0 && OFF_MBAR % 8 == 0, "alignment");
 };
 
 /* misc[] slots */
@@ -92,8 +105,12 @@ enum { MISC_TILE_BASE = 0, MISC_RS_CAND = 1, MISC_TILE_TOTAL = 2 };
 __device__ __forceinline__ uint64_t pack_bytes(uint32_t epoch, uint32_t state, uint32_t v) {
 	return ((uint64_t)epoch << 34) | ((uint64_t)state << 32) | v;
 }
+__device__ __forceinline__ uint64_t pack_ent(uint32_t epoch, uint32_t value, bool written) {
+	return ((uint64_t)value << 32) | (uint64_t)((epoch << 1) | (written ? 1u : 0u));
+}
+__device__ __forceinline__ uint64_t pack_sum(uint32_t epoch, uint32_t payload) { return ((uint64_t)payload << 32) | epoch; }
 
-/* ---------------------------------------------------------------- tile fetch (warp 0) */
+/* ---------------------------------------------------------------- tile fetch (scout warp) */
 template <int CH, bool EXPAND>
 __device__ __forceinline__ void fetch_tile(const QoiEncParams &P, unsigned char *smem, int b) {
 	using L = Layout<CH, EXPAND>;
@@ -143,12 +160,12 @@ __device__ __forceinline__ void fetch_tile(const QoiEncParams &P, unsigned char 
 		if (t_in == 0) nb = 0xFF000000u;
 		else {
 			const uint8_t *q = gsrc - CH;
-			nb = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | (CH == 4 ? ((uint32_t)q[3] << 24) : 0xFF000000u);
+			nb = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | (CH == 4 ? ((uint32_t)q[CH - 1] << 24) : 0xFF000000u);
 		}
 	} else if (lane == 1) {
 		if (px0 + n_valid < m.npx) {
 			const uint8_t *q = gsrc + nbytes;
-			nb = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | (CH == 4 ? ((uint32_t)q[3] << 24) : 0xFF000000u);
+			nb = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | (CH == 4 ? ((uint32_t)q[CH - 1] << 24) : 0xFF000000u);
 		}
 	}
 	if (lane < 2) {
@@ -190,16 +207,111 @@ __device__ __forceinline__ uint32_t classify(uint32_t v, uint32_t p) {
 	return 5u | (0xFFu << 8) | ((v & 0xFFu) << 16);                       /* qoi.h:468-473 */
 }
 
+/* ---------------------------------------------------------------- scout: table / run look-back over a 32-tile window */
+struct LookBack {
+	uint32_t in_val[2];
+	bool in_ok[2];
+	int32_t lnr_in;
+};
+
+__device__ __forceinline__ void table_lookback(const QoiEncParams &P, uint32_t t, uint32_t first_tile, uint32_t epoch, LookBack &R) {
+	const uint32_t lane = lane_id();
+	uint32_t need_lo = 0xFFFFFFFFu, need_hi = 0xFFFFFFFFu; /* slots still unresolved (uniform) */
+	bool need_lnr = true;
+	uint32_t found_tile[2] = {0, 0};
+	bool found_inc[2] = {false, false};
+	R.in_ok[0] = R.in_ok[1] = false;
+	R.in_val[0] = R.in_val[1] = 0;
+	R.lnr_in = -1;
+	int64_t base = (int64_t)t - 1;
+	while (true) {
+		const int64_t tp = base - lane;
+		uint32_t state, vlo = 0, vhi = 0;
+		int32_t lnr = -1;
+		if (tp < (int64_t)first_tile) {
+			state = QOI_ST_INC; /* before the image: nothing written, no non-run pixel yet */
+		} else {
+			const uint64_t *is = P.st.inc_sum + (size_t)tp * QOI_SUM_WORDS;
+			const uint64_t *as = P.st.agg_sum + (size_t)tp * QOI_SUM_WORDS;
+			while (true) {
+				uint64_t w0 = ld_relaxed_u64(is + 0), w1 = ld_relaxed_u64(is + 1), w2 = ld_relaxed_u64(is + 2);
+				if ((uint32_t)w0 == epoch && (uint32_t)w1 == epoch && (uint32_t)w2 == epoch) {
+					state = QOI_ST_INC;
+					vlo = (uint32_t)(w0 >> 32); vhi = (uint32_t)(w1 >> 32); lnr = (int32_t)(uint32_t)(w2 >> 32);
+					break;
+				}
+				w0 = ld_relaxed_u64(as + 0); w1 = ld_relaxed_u64(as + 1); w2 = ld_relaxed_u64(as + 2);
+				if ((uint32_t)w0 == epoch && (uint32_t)w1 == epoch && (uint32_t)w2 == epoch) {
+					state = QOI_ST_AGG;
+					vlo = (uint32_t)(w0 >> 32); vhi = (uint32_t)(w1 >> 32); lnr = (int32_t)(uint32_t)(w2 >> 32);
+					break;
+				}
+				spin_pause();
+			}
+		}
+		const uint32_t incm = __ballot_sync(QOI_FULL_MASK, state == QOI_ST_INC);
+		const uint32_t first_inc = incm ? (uint32_t)__ffs((int)incm) - 1u : 32u;
+		if (lane > first_inc) { /* tiles older than the nearest inclusive record are irrelevant */
+			vlo = vhi = 0;
+			lnr = QOI_LNR_NONE;
+		}
+		if (need_lnr) {
+			const bool has = (lane <= first_inc) && (state == QOI_ST_INC || lnr != QOI_LNR_NONE);
+			const uint32_t hb = __ballot_sync(QOI_FULL_MASK, has);
+			if (hb) {
+				R.lnr_in = __shfl_sync(QOI_FULL_MASK, lnr, __ffs((int)hb) - 1);
+				need_lnr = false;
+			}
+		}
+#pragma unroll
+		for (int half = 0; half < 2; half++) {
+			const uint32_t need = half ? need_hi : need_lo;
+			const uint32_t vm = half ? vhi : vlo;
+			const uint32_t any = __reduce_or_sync(QOI_FULL_MASK, vm) & need;
+			uint32_t todo = any;
+			while (todo) {
+				const uint32_t sb = (uint32_t)__ffs((int)todo) - 1u;
+				todo &= todo - 1u;
+				const uint32_t b = __ballot_sync(QOI_FULL_MASK, (vm >> sb) & 1u);
+				const uint32_t src = (uint32_t)__ffs((int)b) - 1u; /* nearest tile that wrote the slot */
+				if (lane == sb) {
+					found_tile[half] = (uint32_t)(base - src);
+					found_inc[half] = (src == first_inc);
+					R.in_ok[half] = true;
+				}
+			}
+			if (half) need_hi &= ~any;
+			else need_lo &= ~any;
+		}
+		if (incm) break; /* whatever is still unresolved was never written before this tile */
+		base -= 32;
+	}
+	/* the values themselves */
+#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		if (R.in_ok[q]) {
+			const uint64_t *src = (found_inc[q] ? P.st.inc_ent : P.st.agg_ent) + (size_t)found_tile[q] * 64 + lane + 32u * q;
+			uint64_t e;
+			while (true) {
+				e = ld_relaxed_u64(src);
+				if (((uint32_t)e >> 1) == epoch) break;
+				spin_pause();
+			}
+			R.in_val[q] = (uint32_t)(e >> 32);
+		}
+	}
+}
+
 /* ---------------------------------------------------------------- the kernel */
 template <int CH, bool EXPAND>
 __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const QoiEncParams P) {
 	using L = Layout<CH, EXPAND>;
 	QOI_DYNAMIC_SMEM(smem);
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const bool scout = warp == QOI_ENC_WARPS;
 	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR);
 	TileInfo *infos = (TileInfo *)(smem + L::OFF_INFO);
-	uint32_t *Lval_all = (uint32_t *)(smem + L::OFF_LVAL);
-	uint8_t *Lflag_all = (uint8_t *)(smem + L::OFF_LFLAG);
+	uint2 *Lent_all = (uint2 *)(smem + L::OFF_LENT);
 	uint16_t *Fpos_all = (uint16_t *)(smem + L::OFF_FPOS);
 	uint32_t *Tin_val = (uint32_t *)(smem + L::OFF_TINVAL);
 	uint8_t *Tin_flag = (uint8_t *)(smem + L::OFF_TINFLAG);
@@ -216,9 +328,10 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 		mbar_init(&mbar[0], 1);
 		mbar_init(&mbar[1], 1);
 		mbar_fence_init();
+		misc[MISC_RS_CAND] = (uint32_t)INT_MAX;
 	}
 	__syncthreads();
-	if (warp == 0) fetch_tile<CH, EXPAND>(P, smem, 0);
+	if (scout) fetch_tile<CH, EXPAND>(P, smem, 0);
 	__syncthreads();
 
 	int cur = 0;
@@ -229,109 +342,15 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 		const TileInfo ti = infos[cur];
 		if (ti.tile < 0) break;
 		const uint32_t t = (uint32_t)ti.tile;
-		if (warp == 0) fetch_tile<CH, EXPAND>(P, smem, cur ^ 1); /* prefetch: overlaps everything below */
-
-		/* wait for this tile's bulk copy */
-		if (cur == 0) { mbar_wait(&mbar[0], parity0); parity0 ^= 1u; }
-		else { mbar_wait(&mbar[1], parity1); parity1 ^= 1u; }
-
 		unsigned char *data = smem + L::OFF_RAW + cur * L::RAW_STRIDE + 16;
-		uint32_t *pxv; /* pxv[-1] = pixel before the tile, pxv[0..4095], pxv[4096] = pixel after */
-		if (EXPAND) {
-			/* ---- phase E: 16 pixels per thread, raw bytes at data[sh + CH*i] -> RGBA words ---- */
-			pxv = (uint32_t *)(smem + L::OFF_PXBUF + 16);
-			const uint32_t b0 = ti.sh + tid * (16u * CH);
-			const uint32_t *wsrc = (const uint32_t *)data + (b0 >> 2);
-			const uint32_t shf = (b0 & 3u) * 8u;
-			uint32_t out[16];
-			if (CH == 4) {
-				uint32_t w[17];
-#pragma unroll
-				for (int j = 0; j < 17; j++) w[j] = wsrc[j];
-#pragma unroll
-				for (int j = 0; j < 16; j++) out[j] = __funnelshift_r(w[j], w[j + 1], shf);
-			} else {
-				uint32_t w[13];
-#pragma unroll
-				for (int j = 0; j < 13; j++) w[j] = wsrc[j];
-				uint32_t s[12];
-#pragma unroll
-				for (int j = 0; j < 12; j++) s[j] = __funnelshift_r(w[j], w[j + 1], shf);
-#pragma unroll
-				for (int g = 0; g < 4; g++) {
-					const uint32_t s0 = s[3 * g], s1 = s[3 * g + 1], s2 = s[3 * g + 2];
-					out[4 * g + 0] = (s0 & 0x00FFFFFFu) | 0xFF000000u;
-					out[4 * g + 1] = (s0 >> 24) | ((s1 & 0x0000FFFFu) << 8) | 0xFF000000u;
-					out[4 * g + 2] = (s1 >> 16) | ((s2 & 0x000000FFu) << 16) | 0xFF000000u;
-					out[4 * g + 3] = (s2 >> 8) | 0xFF000000u;
-				}
-			}
-			uint4 *dst = (uint4 *)(pxv + tid * 16u);
-			dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
-			dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
-			dst[2] = make_uint4(out[8], out[9], out[10], out[11]);
-			dst[3] = make_uint4(out[12], out[13], out[14], out[15]);
-			if (tid == 0) {
-				const uint32_t *nbr = (const uint32_t *)(smem + L::OFF_NBR) + cur * 2;
-				pxv[-1] = nbr[0];
-				pxv[QOI_TILE_PX] = nbr[1];
-			}
-			__syncthreads();
-		} else {
-			pxv = (uint32_t *)data;
-		}
+		uint8_t *gstream = P.streams + ti.stream_off;
 
-		/* ---- phase I: striped index pass, one warp per 512-pixel chunk ---- */
-		{
-			uint32_t *Lval = Lval_all + warp * 64;
-			uint8_t *Lflag = Lflag_all + warp * 64;
-			uint16_t *Fpos = Fpos_all + warp * 64;
-			Lflag[lane] = 0;
-			Lflag[lane + 32] = 0;
-			Fpos[lane] = 0xFFFFu;
-			Fpos[lane + 32] = 0xFFFFu;
-			if (tid == 0) misc[MISC_RS_CAND] = (uint32_t)INT_MAX;
-			__syncwarp();
-			int32_t last_nr = -1; /* tile-local index of the last non-run pixel seen so far in this chunk */
-			const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
-#pragma unroll 1
-			for (int s = 0; s < QOI_WARP_STEPS; s++) {
-				const uint32_t i = warp * QOI_WARP_PX + s * 32 + lane;
-				const uint32_t v = pxv[i];
-				const uint32_t p = pxv[(int)i - 1];
-				const bool nonrun = (i < ti.n_valid) && (v != p);
-				const uint32_t h = qoi_slot(v);
-				const uint32_t m = __match_any_sync(QOI_FULL_MASK, nonrun ? h : (64u + lane));
-				const uint32_t nr = __ballot_sync(QOI_FULL_MASK, nonrun);
-				const uint32_t lower = m & lt;
-				const int src = lower ? (31 - __clz((int)lower)) : (int)lane;
-				const uint32_t pv = __shfl_sync(QOI_FULL_MASK, v, src);
-				bool hit = false;
-				if (nonrun) {
-					if (lower) hit = (pv == v);             /* predecessor with the same slot inside this step */
-					else if (Lflag[h]) hit = (Lval[h] == v); /* ... inside this warp chunk */
-					else Fpos[h] = (uint16_t)i;             /* first occurrence in the chunk: resolved in phase R */
-				}
-				const uint32_t hb = __ballot_sync(QOI_FULL_MASK, hit);
-				__syncwarp();
-				if (nonrun && (m & gt) == 0u) { /* last pixel of its slot in this step becomes the table entry */
-					Lval[h] = v;
-					Lflag[h] = 1;
-				}
-				if (lane == 0) {
-					hitw[warp * QOI_WARP_STEPS + s] = hb;
-					nrw[warp * QOI_WARP_STEPS + s] = nr;
-					lnrs[warp * QOI_WARP_STEPS + s] = last_nr;
-				}
-				if (nr) last_nr = (int32_t)(warp * QOI_WARP_PX + s * 32 + 31 - __clz((int)nr));
-				__syncwarp();
-			}
-			if (lane == 0) wlnr[warp] = last_nr;
-		}
-		__syncthreads();
+		if (scout) {
+			/* =============================== scout warp =============================== */
+			fetch_tile<CH, EXPAND>(P, smem, cur ^ 1); /* prefetch: overlaps the whole tile */
 
-		/* ---- phase T: tile aggregate, look-back, inclusive record (warp 0; lane handles slots lane, lane+32) ---- */
-		if (warp == 0) {
+			bar_sync(BAR_I_DONE, QOI_ENC_THREADS); /* per-warp tables of this tile are complete */
+			/* ---- phase T: tile aggregate (lane handles slots lane, lane+32) ---- */
 			uint32_t own_val[2];
 			bool own_ok[2];
 #pragma unroll
@@ -340,8 +359,9 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				own_ok[q] = false;
 				own_val[q] = 0;
 				for (int w = QOI_ENC_WARPS - 1; w >= 0; w--) {
-					if (Lflag_all[w * 64 + s]) {
-						own_val[q] = Lval_all[w * 64 + s];
+					const uint2 e = Lent_all[w * 64 + s];
+					if (e.y) {
+						own_val[q] = e.x;
 						own_ok[q] = true;
 						break;
 					}
@@ -356,195 +376,51 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 			}
 			const uint32_t own_lo = __ballot_sync(QOI_FULL_MASK, own_ok[0]);
 			const uint32_t own_hi = __ballot_sync(QOI_FULL_MASK, own_ok[1]);
-			uint32_t in_val[2] = {0, 0};
-			bool in_ok[2] = {false, false};
-			int32_t lnr_in = -1;
+			LookBack lb;
+			lb.in_ok[0] = lb.in_ok[1] = false;
+			lb.in_val[0] = lb.in_val[1] = 0;
+			lb.lnr_in = -1;
 			if (t != ti.first_tile) {
-				P.st.agg_tab[(size_t)t * 64 + lane] = own_val[0];
-				P.st.agg_tab[(size_t)t * 64 + lane + 32] = own_val[1];
-				if (lane == 0) {
-					P.st.agg_valid[t] = (uint64_t)own_lo | ((uint64_t)own_hi << 32);
-					P.st.agg_lnr[t] = own_lnr;
+				st_relaxed_u64(&P.st.agg_ent[(size_t)t * 64 + lane], pack_ent(epoch, own_val[0], own_ok[0]));
+				st_relaxed_u64(&P.st.agg_ent[(size_t)t * 64 + lane + 32], pack_ent(epoch, own_val[1], own_ok[1]));
+				if (lane < 3) {
+					const uint32_t payload = lane == 0 ? own_lo : (lane == 1 ? own_hi : (uint32_t)own_lnr);
+					st_relaxed_u64(&P.st.agg_sum[(size_t)t * QOI_SUM_WORDS + lane], pack_sum(epoch, payload));
 				}
-				__syncwarp();
-				if (lane == 0) {
-					__threadfence();
-					st_release_u32(&P.st.tab_status[t], (epoch << 2) | QOI_ST_AGG);
-				}
-				/* look back: nearest predecessor that wrote the slot, or the first inclusive record */
-#pragma unroll
-				for (int q = 0; q < 2; q++) {
-					const uint32_t s = lane + 32u * q;
-					uint32_t tp = t - 1;
-					while (true) {
-						const uint32_t st = ld_acquire_u32(&P.st.tab_status[tp]);
-						if ((st >> 2) != epoch || (st & 3u) == QOI_ST_NONE) {
-							spin_pause();
-							continue;
-						}
-						if ((st & 3u) == QOI_ST_INC) {
-							in_ok[q] = (__ldcg(&P.st.inc_valid[tp]) >> s) & 1ull;
-							in_val[q] = __ldcg(&P.st.inc_tab[(size_t)tp * 64 + s]);
-							break;
-						}
-						if ((__ldcg(&P.st.agg_valid[tp]) >> s) & 1ull) {
-							in_ok[q] = true;
-							in_val[q] = __ldcg(&P.st.agg_tab[(size_t)tp * 64 + s]);
-							break;
-						}
-						tp--;
-					}
-				}
-				if (lane == 0) {
-					uint32_t tp = t - 1;
-					while (true) {
-						const uint32_t st = ld_acquire_u32(&P.st.tab_status[tp]);
-						if ((st >> 2) != epoch || (st & 3u) == QOI_ST_NONE) {
-							spin_pause();
-							continue;
-						}
-						if ((st & 3u) == QOI_ST_INC) {
-							lnr_in = __ldcg(&P.st.inc_lnr[tp]);
-							break;
-						}
-						const int32_t a = __ldcg(&P.st.agg_lnr[tp]);
-						if (a != QOI_LNR_NONE) {
-							lnr_in = a;
-							break;
-						}
-						tp--;
-					}
-				}
+				table_lookback(P, t, ti.first_tile, epoch, lb);
 			}
-			Tin_val[lane] = in_val[0];
-			Tin_val[lane + 32] = in_val[1];
-			Tin_flag[lane] = in_ok[0] ? 1 : 0;
-			Tin_flag[lane + 32] = in_ok[1] ? 1 : 0;
+			Tin_val[lane] = lb.in_val[0];
+			Tin_val[lane + 32] = lb.in_val[1];
+			Tin_flag[lane] = lb.in_ok[0] ? 1 : 0;
+			Tin_flag[lane + 32] = lb.in_ok[1] ? 1 : 0;
 			/* inclusive record = what qoi.h's index[] / run bookkeeping hold after this tile */
-			const uint32_t inc_lo = __ballot_sync(QOI_FULL_MASK, own_ok[0] || in_ok[0]);
-			const uint32_t inc_hi = __ballot_sync(QOI_FULL_MASK, own_ok[1] || in_ok[1]);
-			P.st.inc_tab[(size_t)t * 64 + lane] = own_ok[0] ? own_val[0] : in_val[0];
-			P.st.inc_tab[(size_t)t * 64 + lane + 32] = own_ok[1] ? own_val[1] : in_val[1];
-			if (lane == 0) {
-				P.st.inc_valid[t] = (uint64_t)inc_lo | ((uint64_t)inc_hi << 32);
-				P.st.inc_lnr[t] = (own_lnr != QOI_LNR_NONE) ? own_lnr : lnr_in;
-				/* last non-run pixel index before each warp chunk (image coordinates) */
-				int32_t run = lnr_in;
+			const uint32_t inc_lo = __ballot_sync(QOI_FULL_MASK, own_ok[0] || lb.in_ok[0]);
+			const uint32_t inc_hi = __ballot_sync(QOI_FULL_MASK, own_ok[1] || lb.in_ok[1]);
+			st_relaxed_u64(&P.st.inc_ent[(size_t)t * 64 + lane], pack_ent(epoch, own_ok[0] ? own_val[0] : lb.in_val[0], own_ok[0] || lb.in_ok[0]));
+			st_relaxed_u64(&P.st.inc_ent[(size_t)t * 64 + lane + 32], pack_ent(epoch, own_ok[1] ? own_val[1] : lb.in_val[1], own_ok[1] || lb.in_ok[1]));
+			if (lane < 3) {
+				const int32_t inc_lnr = (own_lnr != QOI_LNR_NONE) ? own_lnr : lb.lnr_in;
+				const uint32_t payload = lane == 0 ? inc_lo : (lane == 1 ? inc_hi : (uint32_t)inc_lnr);
+				st_relaxed_u64(&P.st.inc_sum[(size_t)t * QOI_SUM_WORDS + lane], pack_sum(epoch, payload));
+			}
+			if (lane == 0) { /* last non-run pixel index before each warp chunk (image coordinates) */
+				int32_t run = lb.lnr_in;
 				for (int w = 0; w < QOI_ENC_WARPS; w++) {
 					wlnr_in[w] = run;
 					if (wlnr[w] >= 0) run = (int32_t)ti.px0 + wlnr[w];
 				}
 			}
 			__syncwarp();
-			if (lane == 0) {
-				__threadfence();
-				st_release_u32(&P.st.tab_status[t], (epoch << 2) | QOI_ST_INC);
-			}
-		}
-		__syncthreads();
+			bar_arrive(BAR_T_READY, QOI_ENC_THREADS);
 
-		/* ---- phase R: resolve the deferred first occurrences (<= 64 per warp chunk) ---- */
-#pragma unroll
-		for (int j = 0; j < 2; j++) {
-			const uint32_t q = tid * 2 + j;
-			const int w = (int)(q >> 6);
-			const uint32_t s = q & 63u;
-			const uint32_t pos = Fpos_all[w * 64 + s];
-			if (pos != 0xFFFFu) {
-				const uint32_t v = pxv[pos];
-				bool found = false;
-				uint32_t val = 0;
-				for (int w2 = w - 1; w2 >= 0; w2--) {
-					if (Lflag_all[w2 * 64 + s]) {
-						val = Lval_all[w2 * 64 + s];
-						found = true;
-						break;
-					}
-				}
-				if (!found && Tin_flag[s]) {
-					val = Tin_val[s];
-					found = true;
-				}
-				/* an untouched index[] slot holds 0 (qoi.h:393): only the all-zero pixel can hit it */
-				const bool hit = found ? (val == v) : (v == 0u);
-				if (hit) atomicOr(&hitw[pos >> 5], 1u << (pos & 31u));
-			}
-		}
-		__syncthreads();
-
-		/* ---- phase C: blocked classify pass, 16 consecutive pixels per thread ---- */
-		uint32_t v[16];
-		uint32_t code[16];
-		uint32_t ttotal = 0;
-		const uint32_t i0 = tid * 16u;
-		uint32_t pprev;
-		{
-			const uint4 *src = (const uint4 *)(pxv + i0);
-			const uint4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
-			v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
-			v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
-			v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w;
-			v[12] = q3.x; v[13] = q3.y; v[14] = q3.z; v[15] = q3.w;
-			pprev = pxv[(int)i0 - 1];
-			const uint32_t pnext = pxv[i0 + 16];
-			const uint32_t wi = i0 >> 5, bo = i0 & 31u;
-			const uint32_t hitbits = (hitw[wi] >> bo) & 0xFFFFu;
-			const uint32_t nrword = nrw[wi];
-			const uint32_t nrbits = (nrword >> bo) & 0xFFFFu;
-			/* run position of the pixel before my first one */
-			const uint32_t below = nrword & ((1u << bo) - 1u);
-			int32_t lnr_glob;
-			if (below) lnr_glob = (int32_t)(ti.px0 + (i0 & ~31u) + 31u - (uint32_t)__clz((int)below));
-			else {
-				const int32_t l = lnrs[wi];
-				lnr_glob = (l >= 0) ? (int32_t)ti.px0 + l : wlnr_in[warp];
-			}
-			const uint32_t c = (uint32_t)((int32_t)(ti.px0 + i0) - 1 - lnr_glob); /* run pixels between them */
-			int32_t r = (c == 0u) ? -1 : (int32_t)((c - 1u) % 62u);               /* (k-1) % 62 of the previous pixel */
-			int32_t cand = INT_MAX;
-			uint32_t before = pprev;
-#pragma unroll
-			for (int j = 0; j < 16; j++) {
-				const uint32_t gi = ti.px0 + i0 + j;
-				uint32_t cd = 0;
-				if (i0 + j < ti.n_valid) {
-					if ((nrbits >> j) & 1u) {
-						r = -1;
-						if (cand == INT_MAX) cand = (int32_t)(i0 + j);
-						if ((hitbits >> j) & 1u) cd = 1u | (qoi_slot(v[j]) << 8); /* qoi.h:432-434 */
-						else cd = classify(v[j], before);
-					} else {
-						/* run pixel (qoi.h:415-421): a byte leaves at run length 62, at the image end, or when the run ends */
-						r = (r == 61) ? 0 : r + 1;
-						if (r == 0 && cand == INT_MAX) cand = (int32_t)(i0 + j);
-						const uint32_t nx = (j == 15) ? pnext : v[j < 15 ? j + 1 : 15];
-						if (r == 61 || gi == ti.npx - 1u || nx != v[j]) cd = 1u | ((0xC0u | (uint32_t)r) << 8);
-					}
-				}
-				code[j] = cd;
-				ttotal += cd & 7u;
-				before = v[j];
-			}
-			if (tid < 4 && cand != INT_MAX) atomicMin((int *)&misc[MISC_RS_CAND], cand);
-		}
-		/* block scan of the per-thread byte counts */
-		uint32_t incl = ttotal;
-#pragma unroll
-		for (int dlt = 1; dlt < 32; dlt <<= 1) {
-			const uint32_t o = __shfl_up_sync(QOI_FULL_MASK, incl, dlt);
-			if (lane >= (uint32_t)dlt) incl += o;
-		}
-		if (lane == 31) wtot[warp] = incl;
-		__syncthreads();
-
-		/* ---- phase B: output offset look-back (warp 0) ---- */
-		if (warp == 0) {
+			bar_sync(BAR_C_DONE, QOI_ENC_THREADS); /* byte counts of the compute warps are in wtot[] */
+			/* ---- phase B: output offset look-back, 32 predecessors per probe ---- */
 			uint32_t total = 0;
 #pragma unroll
 			for (int w = 0; w < QOI_ENC_WARPS; w++) total += wtot[w];
 			uint32_t excl = QOI_HEADER_BYTES;
 			if (t != ti.first_tile) {
-				if (lane == 0) st_release_u64(&P.st.byte_state[t], pack_bytes(epoch, QOI_ST_AGG, total));
+				if (lane == 0) st_relaxed_u64(&P.st.byte_state[t], pack_bytes(epoch, QOI_ST_AGG, total));
 				uint32_t sum = 0;
 				int64_t base = (int64_t)t - 1;
 				while (true) {
@@ -552,7 +428,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 					uint32_t state = QOI_ST_AGG, val = 0;
 					if (tp >= (int64_t)ti.first_tile) {
 						while (true) {
-							const uint64_t st = ld_acquire_u64(&P.st.byte_state[tp]);
+							const uint64_t st = ld_relaxed_u64(&P.st.byte_state[tp]);
 							if ((uint32_t)(st >> 34) == epoch && ((st >> 32) & 3u) != QOI_ST_NONE) {
 								state = (uint32_t)(st >> 32) & 3u;
 								val = (uint32_t)st;
@@ -573,73 +449,35 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				excl = sum;
 			}
 			if (lane == 0) {
-				st_release_u64(&P.st.byte_state[t], pack_bytes(epoch, QOI_ST_INC, excl + total));
+				st_relaxed_u64(&P.st.byte_state[t], pack_bytes(epoch, QOI_ST_INC, excl + total));
 				misc[MISC_TILE_BASE] = excl;
 				misc[MISC_TILE_TOTAL] = total;
 				tma_store_wait_read(); /* the previous tile's bulk store has finished reading the staging buffer */
 			}
-		}
-		__syncthreads();
+			__syncwarp();
+			bar_arrive(BAR_B_READY, QOI_ENC_THREADS);
 
-		/* ---- phase W: op bytes -> staging (alignment congruent to the destination) ---- */
-		const uint32_t tile_base = misc[MISC_TILE_BASE];
-		const uint32_t tile_total = misc[MISC_TILE_TOTAL];
-		const int32_t rs_cand = (int32_t)misc[MISC_RS_CAND];
-		uint8_t *gstream = P.streams + ti.stream_off;
-		uint8_t *gdst = gstream + tile_base;
-		const uint32_t padb = (uint32_t)((uintptr_t)gdst & 15u);
-		{
-			uint32_t woff = incl - ttotal; /* exclusive inside the warp */
-			for (uint32_t w = 0; w < warp; w++) woff += wtot[w];
-			unsigned char *o = stage + padb + woff;
-			uint32_t before = pprev;
-#pragma unroll
-			for (int j = 0; j < 16; j++) {
-				const uint32_t cd = code[j];
-				const uint32_t sz = cd & 7u;
-				if ((int32_t)(i0 + j) == rs_cand) { /* decoder restart point of this tile */
-					P.st.rs_px[t] = (int32_t)(ti.px0 + i0 + j);
-					P.st.rs_byte[t] = (int32_t)(tile_base + (uint32_t)(o - (stage + padb)));
-					P.st.rs_prev[t] = before;
+			bar_sync(BAR_W_DONE, QOI_ENC_THREADS); /* staging is complete, everybody has read this tile's misc[] */
+			if (lane == 0) misc[MISC_RS_CAND] = (uint32_t)INT_MAX; /* for the next tile (used after its T_READY) */
+			/* ---- staging -> global: one bulk store for the 16-byte aligned interior, byte stores for the edges ---- */
+			{
+				uint8_t *gdst = gstream + excl;
+				const uint32_t padb = (uint32_t)((uintptr_t)gdst & 15u);
+				const uint32_t lo_off = (padb + 15u) & ~15u;
+				const uint32_t end = padb + total;
+				const uint32_t hi_off = end & ~15u;
+				const bool bulk = hi_off > lo_off;
+				if (lane == 0 && bulk) {
+					fence_proxy_async_smem();
+					tma_store_1d(gdst + (lo_off - padb), stage + lo_off, hi_off - lo_off);
+					tma_store_commit();
 				}
-				if (sz) {
-					o[0] = (uint8_t)(cd >> 8);
-					if (sz >= 2) {
-						o[1] = (uint8_t)(cd >> 16);
-						if (sz >= 4) {
-							o[2] = (uint8_t)(v[j] >> 8);
-							o[3] = (uint8_t)(v[j] >> 16);
-							if (sz == 5) o[4] = (uint8_t)(v[j] >> 24);
-						}
-					}
-					o += sz;
-				}
-				before = v[j];
-			}
-			if (tid == 0 && rs_cand == INT_MAX) P.st.rs_px[t] = -1;
-		}
-		__syncthreads();
-
-		/* ---- staging -> global: one bulk store for the 16-byte aligned interior, byte stores for the edges ---- */
-		{
-			const uint32_t lo_off = (padb + 15u) & ~15u;
-			const uint32_t end = padb + tile_total;
-			const uint32_t hi_off = end & ~15u;
-			const bool bulk = hi_off > lo_off;
-			if (tid == 0 && bulk) {
-				fence_proxy_async_smem();
-				tma_store_1d(gdst + (lo_off - padb), stage + lo_off, hi_off - lo_off);
-				tma_store_commit();
-			}
-			const uint32_t a_hi = bulk ? lo_off : end;          /* [padb, a_hi) */
-			const uint32_t b_lo = bulk ? hi_off : end;          /* [b_lo, end)  */
-			if (tid >= 32 && tid < 64) {
-				for (uint32_t o = padb + (tid - 32); o < a_hi; o += 32) gdst[o - padb] = stage[o];
-			} else if (tid >= 64 && tid < 96) {
-				for (uint32_t o = b_lo + (tid - 64); o < end; o += 32) gdst[o - padb] = stage[o];
-			} else if (tid >= 96 && tid < 96 + QOI_HEADER_BYTES) {
-				if (t == ti.first_tile) { /* header, qoi.h:384-388 */
-					const uint32_t k = tid - 96;
+				const uint32_t a_hi = bulk ? lo_off : end; /* [padb, a_hi) */
+				const uint32_t b_lo = bulk ? hi_off : end; /* [b_lo, end)  */
+				for (uint32_t o = padb + lane; o < a_hi; o += 32) gdst[o - padb] = stage[o];
+				for (uint32_t o = b_lo + lane; o < end; o += 32) gdst[o - padb] = stage[o];
+				if (t == ti.first_tile && lane < QOI_HEADER_BYTES) { /* header, qoi.h:384-388 */
+					const uint32_t k = lane;
 					uint8_t b;
 					if (k < 4) b = (uint8_t)("qoif"[k]);
 					else if (k < 8) b = (uint8_t)(ti.width >> (8 * (7 - k)));
@@ -648,22 +486,282 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 					else b = (uint8_t)(ti.chan_cs >> 8);
 					gstream[k] = b;
 				}
-			} else if (tid >= 128 && tid < 128 + QOI_END_BYTES + 1) {
-				if (ti.px0 + ti.n_valid == ti.npx) { /* end marker and length, qoi.h:480-484 */
-					const uint32_t k = tid - 128;
-					const uint32_t fin = tile_base + tile_total;
+				if (ti.px0 + ti.n_valid == ti.npx && lane >= 16 && lane < 16 + QOI_END_BYTES + 1) { /* end marker, length: qoi.h:480-484 */
+					const uint32_t k = lane - 16;
+					const uint32_t fin = excl + total;
 					if (k < QOI_END_BYTES) gstream[fin + k] = (k == QOI_END_BYTES - 1) ? 1 : 0;
 					else P.lens[ti.img] = (int32_t)(fin + QOI_END_BYTES);
 				}
 			}
+		} else {
+			/* =============================== compute warps =============================== */
+			if (cur == 0) { mbar_wait(&mbar[0], parity0); parity0 ^= 1u; }
+			else { mbar_wait(&mbar[1], parity1); parity1 ^= 1u; }
+
+			uint32_t *pxv; /* pxv[-1] = pixel before the tile, pxv[0..4095], pxv[4096] = pixel after */
+			if (EXPAND) {
+				/* ---- phase E: 16 pixels per thread, raw bytes at data[sh + CH*i] -> RGBA words ---- */
+				pxv = (uint32_t *)(smem + L::OFF_PXBUF + 16);
+				const uint32_t b0 = ti.sh + tid * (16u * CH);
+				const uint32_t *wsrc = (const uint32_t *)data + (b0 >> 2);
+				const uint32_t shf = (b0 & 3u) * 8u;
+				uint32_t out[16];
+				if (CH == 4) {
+					uint32_t w[17];
+#pragma unroll
+					for (int j = 0; j < 17; j++) w[j] = wsrc[j];
+#pragma unroll
+					for (int j = 0; j < 16; j++) out[j] = __funnelshift_r(w[j], w[j + 1], shf);
+				} else {
+					uint32_t w[13];
+#pragma unroll
+					for (int j = 0; j < 13; j++) w[j] = wsrc[j];
+					uint32_t s[12];
+#pragma unroll
+					for (int j = 0; j < 12; j++) s[j] = __funnelshift_r(w[j], w[j + 1], shf);
+#pragma unroll
+					for (int g = 0; g < 4; g++) {
+						const uint32_t s0 = s[3 * g], s1 = s[3 * g + 1], s2 = s[3 * g + 2];
+						out[4 * g + 0] = (s0 & 0x00FFFFFFu) | 0xFF000000u;
+						out[4 * g + 1] = (s0 >> 24) | ((s1 & 0x0000FFFFu) << 8) | 0xFF000000u;
+						out[4 * g + 2] = (s1 >> 16) | ((s2 & 0x000000FFu) << 16) | 0xFF000000u;
+						out[4 * g + 3] = (s2 >> 8) | 0xFF000000u;
+					}
+				}
+				uint4 *dst = (uint4 *)(pxv + tid * 16u);
+				dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+				dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+				dst[2] = make_uint4(out[8], out[9], out[10], out[11]);
+				dst[3] = make_uint4(out[12], out[13], out[14], out[15]);
+				if (tid == 0) {
+					const uint32_t *nbr = (const uint32_t *)(smem + L::OFF_NBR) + cur * 2;
+					pxv[-1] = nbr[0];
+					pxv[QOI_TILE_PX] = nbr[1];
+				}
+				bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
+			} else {
+				pxv = (uint32_t *)data;
+			}
+
+			/* ---- phase I: striped index pass, one warp per 512-pixel chunk ---- */
+			{
+				uint2 *Lent = Lent_all + warp * 64;
+				uint16_t *Fpos = Fpos_all + warp * 64;
+				Lent[lane] = make_uint2(0u, 0u);
+				Lent[lane + 32] = make_uint2(0u, 0u);
+				Fpos[lane] = 0xFFFFu;
+				Fpos[lane + 32] = 0xFFFFu;
+				__syncwarp();
+				int32_t last_nr = -1; /* tile-local index of the last non-run pixel seen so far in this chunk */
+				const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
+#pragma unroll 1
+				for (int s = 0; s < QOI_WARP_STEPS; s++) {
+					const uint32_t i = warp * QOI_WARP_PX + s * 32 + lane;
+					const uint32_t v = pxv[i];
+					const uint32_t p = pxv[(int)i - 1];
+					const bool nonrun = (i < ti.n_valid) && (v != p);
+					const uint32_t h = qoi_slot(v);
+					const uint32_t nr = __ballot_sync(QOI_FULL_MASK, nonrun);
+					/* lanes whose (non-run) pixel has the same slot: intersect the six hash-bit planes */
+					uint32_t m = nr;
+#pragma unroll
+					for (int b = 0; b < 6; b++) {
+						const bool bit = (h >> b) & 1u;
+						const uint32_t plane = __ballot_sync(QOI_FULL_MASK, nonrun && bit);
+						m &= bit ? plane : ~plane;
+					}
+					const uint32_t lower = m & lt;
+					const int src = lower ? (31 - __clz((int)lower)) : (int)lane;
+					const uint32_t pv = __shfl_sync(QOI_FULL_MASK, v, src);
+					const uint2 ent = Lent[h];
+					bool hit = false;
+					if (nonrun) {
+						if (lower) hit = (pv == v);           /* predecessor with the same slot inside this step */
+						else if (ent.y) hit = (ent.x == v);   /* ... inside this warp chunk */
+						else Fpos[h] = (uint16_t)i;           /* first occurrence in the chunk: resolved in phase R */
+					}
+					const uint32_t hb = __ballot_sync(QOI_FULL_MASK, hit);
+					__syncwarp();
+					if (nonrun && (m & gt) == 0u) Lent[h] = make_uint2(v, 1u); /* last pixel of its slot in this step */
+					if (lane == 0) {
+						hitw[warp * QOI_WARP_STEPS + s] = hb;
+						nrw[warp * QOI_WARP_STEPS + s] = nr;
+						lnrs[warp * QOI_WARP_STEPS + s] = last_nr;
+					}
+					if (nr) last_nr = (int32_t)(warp * QOI_WARP_PX + s * 32 + 31 - __clz((int)nr));
+					__syncwarp();
+				}
+				if (lane == 0) wlnr[warp] = last_nr;
+			}
+			__syncwarp();
+			bar_arrive(BAR_I_DONE, QOI_ENC_THREADS);
+
+			/* ---- phase C: blocked classify pass, 16 consecutive pixels per thread ---- */
+			uint32_t v[16];
+			uint32_t code[16];
+			uint32_t ttotal = 0;
+			const uint32_t i0 = tid * 16u;
+			const uint32_t wi = i0 >> 5, bo = i0 & 31u;
+			uint32_t pprev, pnext;
+			{
+				const uint4 *src = (const uint4 *)(pxv + i0);
+				const uint4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+				v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
+				v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+				v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w;
+				v[12] = q3.x; v[13] = q3.y; v[14] = q3.z; v[15] = q3.w;
+				pprev = pxv[(int)i0 - 1];
+				pnext = pxv[i0 + 16];
+			}
+			const uint32_t nrword = nrw[wi];
+			const uint32_t nrbits = (nrword >> bo) & 0xFFFFu;
+			const uint32_t below = nrword & ((1u << bo) - 1u);
+			/* Does this thread start inside a run whose start lies outside what this warp has seen?  Only then
+			   does it need the carry from earlier warps / tiles, and it waits for it (pass 1). */
+			int32_t lnr_local = -1; /* tile-local index of the last non-run pixel before my first one, if known locally */
+			if (below) lnr_local = (int32_t)((i0 & ~31u) + 31u - (uint32_t)__clz((int)below));
+			else lnr_local = lnrs[wi];
+			const bool first_is_run = (i0 < ti.n_valid) && !(nrbits & 1u);
+			const bool defer = first_is_run && lnr_local < 0;
+			uint32_t hitbits = (hitw[wi] >> bo) & 0xFFFFu;
+			int32_t cand = INT_MAX;
+#pragma unroll 1
+			for (int pass = 0; pass < 2; pass++) {
+				int32_t lnr_glob = (lnr_local >= 0) ? (int32_t)ti.px0 + lnr_local : 0;
+				if (pass == 1) {
+					bar_sync(BAR_T_READY, QOI_ENC_THREADS); /* T_in and the run carry are in shared memory */
+					/* ---- phase R: resolve the deferred first occurrences (<= 64 per warp chunk) ---- */
+#pragma unroll
+					for (int j = 0; j < 2; j++) {
+						const uint32_t q = tid * 2 + j;
+						const int w = (int)(q >> 6);
+						const uint32_t s = q & 63u;
+						const uint32_t pos = Fpos_all[w * 64 + s];
+						if (pos != 0xFFFFu) {
+							const uint32_t pvv = pxv[pos];
+							bool found = false;
+							uint32_t val = 0;
+							for (int w2 = w - 1; w2 >= 0; w2--) {
+								const uint2 e = Lent_all[w2 * 64 + s];
+								if (e.y) {
+									val = e.x;
+									found = true;
+									break;
+								}
+							}
+							if (!found && Tin_flag[s]) {
+								val = Tin_val[s];
+								found = true;
+							}
+							/* an untouched index[] slot holds 0 (qoi.h:393): only the all-zero pixel can hit it */
+							const bool hit = found ? (val == pvv) : (pvv == 0u);
+							if (hit) atomicOr(&hitw[pos >> 5], 1u << (pos & 31u));
+						}
+					}
+					bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
+					const uint32_t hb1 = (hitw[wi] >> bo) & 0xFFFFu;
+					const uint32_t changed = hb1 ^ hitbits; /* bits can only turn on */
+					hitbits = hb1;
+					if (!defer) {
+						/* patch the pixels that turned into INDEX ops (qoi.h:432-434) */
+#pragma unroll
+						for (int j = 0; j < 16; j++) {
+							if ((changed >> j) & 1u) {
+								ttotal -= (code[j] & 7u) - 1u;
+								code[j] = 1u | (qoi_slot(v[j]) << 8);
+							}
+						}
+						break;
+					}
+					lnr_glob = (lnr_local >= 0) ? (int32_t)ti.px0 + lnr_local : wlnr_in[warp];
+				} else if (defer) {
+					continue;
+				}
+				/* run pixels between the last non-run pixel and my first pixel */
+				const uint32_t c = (uint32_t)((int32_t)(ti.px0 + i0) - 1 - lnr_glob);
+				int32_t r = (c == 0u) ? -1 : (int32_t)((c - 1u) % 62u); /* (k-1) % 62 of the previous pixel */
+				uint32_t before = pprev;
+				ttotal = 0;
+				cand = INT_MAX;
+#pragma unroll
+				for (int j = 0; j < 16; j++) {
+					const uint32_t gi = ti.px0 + i0 + j;
+					uint32_t cd = 0;
+					if (i0 + j < ti.n_valid) {
+						if ((nrbits >> j) & 1u) {
+							r = -1;
+							if (cand == INT_MAX) cand = (int32_t)(i0 + j);
+							if ((hitbits >> j) & 1u) cd = 1u | (qoi_slot(v[j]) << 8); /* qoi.h:432-434 */
+							else cd = classify(v[j], before);
+						} else {
+							/* run pixel (qoi.h:415-421): a byte leaves at run length 62, at the image end, or when the run ends */
+							r = (r == 61) ? 0 : r + 1;
+							if (r == 0 && cand == INT_MAX) cand = (int32_t)(i0 + j);
+							const uint32_t nx = (j == 15) ? pnext : v[j < 15 ? j + 1 : 15];
+							if (r == 61 || gi == ti.npx - 1u || nx != v[j]) cd = 1u | ((0xC0u | (uint32_t)r) << 8);
+						}
+					}
+					code[j] = cd;
+					ttotal += cd & 7u;
+					before = v[j];
+				}
+			}
+			if (tid < 4 && cand != INT_MAX) atomicMin((int *)&misc[MISC_RS_CAND], cand);
+			/* block scan of the per-thread byte counts */
+			uint32_t incl = ttotal;
+#pragma unroll
+			for (int dlt = 1; dlt < 32; dlt <<= 1) {
+				const uint32_t o = __shfl_up_sync(QOI_FULL_MASK, incl, dlt);
+				if (lane >= (uint32_t)dlt) incl += o;
+			}
+			if (lane == 31) wtot[warp] = incl;
+			__syncwarp();
+			bar_arrive(BAR_C_DONE, QOI_ENC_THREADS);
+
+			bar_sync(BAR_B_READY, QOI_ENC_THREADS);
+			/* ---- phase W: op bytes -> staging (alignment congruent to the destination) ---- */
+			const uint32_t tile_base = misc[MISC_TILE_BASE];
+			const int32_t rs_cand = (int32_t)misc[MISC_RS_CAND];
+			const uint32_t padb = (uint32_t)((uintptr_t)(gstream + tile_base) & 15u);
+			{
+				uint32_t woff = incl - ttotal; /* exclusive inside the warp */
+				for (uint32_t w = 0; w < warp; w++) woff += wtot[w];
+				unsigned char *o = stage + padb + woff;
+				uint32_t before = pprev;
+#pragma unroll
+				for (int j = 0; j < 16; j++) {
+					const uint32_t cd = code[j];
+					const uint32_t sz = cd & 7u;
+					if ((int32_t)(i0 + j) == rs_cand) { /* decoder restart point of this tile */
+						P.st.rs_px[t] = (int32_t)(ti.px0 + i0 + j);
+						P.st.rs_byte[t] = (int32_t)(tile_base + (uint32_t)(o - (stage + padb)));
+						P.st.rs_prev[t] = before;
+					}
+					if (sz) {
+						o[0] = (uint8_t)(cd >> 8);
+						if (sz >= 2) {
+							o[1] = (uint8_t)(cd >> 16);
+							if (sz >= 4) {
+								o[2] = (uint8_t)(v[j] >> 8);
+								o[3] = (uint8_t)(v[j] >> 16);
+								if (sz == 5) o[4] = (uint8_t)(v[j] >> 24);
+							}
+						}
+						o += sz;
+					}
+					before = v[j];
+				}
+				if (tid == 0 && rs_cand == INT_MAX) P.st.rs_px[t] = -1;
+			}
+			__syncwarp();
+			bar_arrive(BAR_W_DONE, QOI_ENC_THREADS);
 		}
-		__syncthreads();
 		cur ^= 1;
 	}
 
 	/* the last CTA to finish rearms the ticket for the next launch */
 	__syncthreads();
-	if (tid == 0) {
+	if (tid == QOI_ENC_COMPUTE) { /* scout lane 0 issued the bulk stores */
 		tma_store_wait_all();
 		const uint32_t done = atomicAdd(&P.st.ticket[1], 1u);
 		if (done == gridDim.x - 1u) {

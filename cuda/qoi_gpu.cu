@@ -410,4 +410,43 @@ void *qoi_decode(const void *data, int size, qoi_desc *desc, int channels) {
 	return out;
 }
 
+/* the two stdio conveniences, so that the library alone offers all four reference entry points
+   (a program that defines QOI_IMPLEMENTATION gets its own copies from include/qoi.h; reference qoi.h:595-646) */
+int qoi_write(const char *filename, const void *data, const qoi_desc *desc) {
+	FILE *fp = fopen(filename, "wb");
+	if (!fp) return 0;
+	int n = 0;
+	void *stream = qoi_encode(data, desc, &n);
+	if (!stream) {
+		fclose(fp);
+		return 0;
+	}
+	fwrite(stream, 1, (size_t)n, fp);
+	fflush(fp);
+	const int bad = ferror(fp);
+	fclose(fp);
+	free(stream);
+	return bad ? 0 : n;
+}
+
+void *qoi_read(const char *filename, qoi_desc *desc, int channels) {
+	FILE *fp = fopen(filename, "rb");
+	if (!fp) return NULL;
+	long len;
+	if (fseek(fp, 0, SEEK_END) != 0 || (len = ftell(fp)) <= 0 || fseek(fp, 0, SEEK_SET) != 0) {
+		fclose(fp);
+		return NULL;
+	}
+	void *stream = malloc((size_t)len);
+	if (!stream) {
+		fclose(fp);
+		return NULL;
+	}
+	const size_t got = fread(stream, 1, (size_t)len, fp);
+	fclose(fp);
+	void *px = (got == (size_t)len) ? qoi_decode(stream, (int)len, desc, channels) : NULL;
+	free(stream);
+	return px;
+}
+
 } /* extern "C" */

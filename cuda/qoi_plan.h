@@ -81,7 +81,7 @@ static inline int qoi_plan_geometry(QoiPlanGeom &g, int n, const QoiDescPOD *des
 }
 
 struct QoiStateLayout {
-	size_t off[12];
+	size_t off[9];
 	size_t total;
 };
 
@@ -89,8 +89,8 @@ static inline QoiStateLayout qoi_state_layout(uint32_t n_tiles) {
 	QoiStateLayout L;
 	size_t o = 0;
 	const size_t T = n_tiles;
-	const size_t sizes[12] = {16, T * 4, T * 256, T * 8, T * 4, T * 256, T * 8, T * 4, T * 8, T * 4, T * 4, T * 4};
-	for (int i = 0; i < 12; i++) {
+	const size_t sizes[9] = {16, T * 512, T * 32, T * 512, T * 32, T * 8, T * 4, T * 4, T * 4};
+	for (int i = 0; i < 9; i++) {
 		L.off[i] = o;
 		o += (sizes[i] + 255) & ~(size_t)255;
 	}
@@ -100,15 +100,12 @@ static inline QoiStateLayout qoi_state_layout(uint32_t n_tiles) {
 
 static inline void qoi_state_bind(QoiTileState &st, unsigned char *base, const QoiStateLayout &L) {
 	st.ticket = (uint32_t *)(base + L.off[0]);
-	st.tab_status = (uint32_t *)(base + L.off[1]);
-	st.agg_tab = (uint32_t *)(base + L.off[2]);
-	st.agg_valid = (uint64_t *)(base + L.off[3]);
-	st.agg_lnr = (int32_t *)(base + L.off[4]);
-	st.inc_tab = (uint32_t *)(base + L.off[5]);
-	st.inc_valid = (uint64_t *)(base + L.off[6]);
-	st.inc_lnr = (int32_t *)(base + L.off[7]);
-	st.byte_state = (uint64_t *)(base + L.off[8]);
-	st.rs_px = (int32_t *)(base + L.off[9]);
-	st.rs_byte = (int32_t *)(base + L.off[10]);
-	st.rs_prev = (uint32_t *)(base + L.off[11]);
+	st.agg_ent = (uint64_t *)(base + L.off[1]);
+	st.agg_sum = (uint64_t *)(base + L.off[2]);
+	st.inc_ent = (uint64_t *)(base + L.off[3]);
+	st.inc_sum = (uint64_t *)(base + L.off[4]);
+	st.byte_state = (uint64_t *)(base + L.off[5]);
+	st.rs_px = (int32_t *)(base + L.off[6]);
+	st.rs_byte = (int32_t *)(base + L.off[7]);
+	st.rs_prev = (uint32_t *)(base + L.off[8]);
 }

@@ -59,6 +59,8 @@ struct Block {
 	unsigned bar_gen = 0;
 	std::vector<Warp> warps;
 	Idx bidx{0, 0, 0};
+	unsigned nb_count[16] = {0};
+	unsigned nb_gen[16] = {0};
 };
 
 struct Fiber {
@@ -125,6 +127,23 @@ inline void block_barrier() {
 		unsigned g = b->bar_gen;
 		while (b->bar_gen == g) yield("__syncthreads");
 	}
+}
+
+/* bar.sync / bar.arrive on barrier `id` with `nthreads` participants per phase */
+inline void named_barrier(unsigned id, unsigned nthreads, bool wait) {
+	Block *b = cur->blk;
+	if (id >= 16) { fprintf(stderr, "cuda_emu: barrier id %u out of range\n", id); abort(); }
+	unsigned g = b->nb_gen[id];
+	b->nb_count[id]++;
+	if (b->nb_count[id] > nthreads) { fprintf(stderr, "cuda_emu: barrier %u over-subscribed (%u > %u)\n", id, b->nb_count[id], nthreads); abort(); }
+	if (b->nb_count[id] == nthreads) {
+		b->nb_count[id] = 0;
+		b->nb_gen[id]++;
+		progress++;
+		return;
+	}
+	if (wait)
+		while (b->nb_gen[id] == g) yield("named barrier");
 }
 
 struct LaunchStats { uint64_t switches; };

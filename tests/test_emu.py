@@ -1,0 +1,70 @@
+"""Runs the real kernel source on the CPU emulator (tests/emu) against the oracle -- CPU only.
+
+This exercises the chained-scan / look-back logic of cuda/qoi_enc.cuh and the segment decoder of
+cuda/qoi_dec.cuh on tile, warp-chunk and image boundaries with several CTAs interleaved in random
+order.  It is a debugging aid for a container without a GPU, not a product path (see cuda_emu.h).
+"""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import qoi_testlib as q
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu", "emu_main")
+
+
+@pytest.fixture(scope="module")
+def emu(cpu):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+    return EMU
+
+
+def run_enc(emu, img, w, h, ch, n, grid, seed, mis):
+    with tempfile.NamedTemporaryFile(suffix=".raw") as f:
+        f.write(np.ascontiguousarray(img, dtype=np.uint8).tobytes())
+        f.flush()
+        r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
+                           capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("PASS"), r.stdout + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dist", range(8))
+def test_emulated_distributions(emu, cpu, dist):
+    run_enc(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0)
+    run_enc(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist)
+
+
+def test_emulated_stress(emu, cpu):
+    rng = np.random.default_rng(7)
+    for it in range(18):
+        w = int(rng.integers(60, 300)); h = int(rng.integers(20, 120)); ch = int(rng.integers(3, 5)); n = int(rng.integers(1, 4))
+        img = np.concatenate([q.stress_image(rng, w * h, ch, it % 6) for _ in range(n)])
+        run_enc(emu, img, w, h, ch, n, int(rng.integers(1, 5)), it + 1, int(rng.integers(0, 17)) if it % 2 else 0)
+
+
+def test_emulated_long_runs(emu, cpu):
+    n = 40000
+    a = np.zeros((n, 4), dtype=np.uint8); a[:, 3] = 255
+    b = np.zeros((n, 4), dtype=np.uint8)
+    c = np.zeros((n, 4), dtype=np.uint8); c[:, 3] = 255; c[n // 2:] = (9, 9, 9, 255); c[-5:] = (0, 0, 0, 255)
+    d = np.full((n, 4), 200, dtype=np.uint8); d[12345] = (1, 2, 3, 4)
+    for img in (a, b, c, d):
+        run_enc(emu, img.reshape(-1), 400, 100, 4, 1, 4, 3, 0)
+        run_enc(emu, np.ascontiguousarray(img[:, :3]).reshape(-1), 400, 100, 3, 1, 3, 4, 5)
+
+
+def test_emulated_foreign_decode(emu, cpu):
+    rng = np.random.default_rng(3)
+    recs = bytearray()
+    n = 40
+    for i in range(n):
+        s = q.foreign_stream(rng, 900, 4, w=30, h=30, truncate=(i % 4 == 0))
+        recs += len(s).to_bytes(4, "little") + s
+    with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+        f.write(bytes(recs)); f.flush()
+        r = subprocess.run([emu, "dec", "30", "30", "4", str(n), "5", f.name], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("PASS"), r.stdout + r.stderr[-2000:]
