@@ -5,7 +5,7 @@
 #include <stdint.h>
 
 #define QOI_TILE_PX 4096        /* pixels per encoder tile (== QOI_GPU_TILE_PX) */
-#define QOI_ENC_THREADS 288      /* 8 compute warps + 1 scout warp */
+#define QOI_ENC_THREADS 320      /* 8 compute warps + scout warp + loader warp */
 #define QOI_ENC_COMPUTE 256
 #define QOI_ENC_WARPS 8         /* compute warps */
 #define QOI_PX_PER_THREAD 16    /* QOI_TILE_PX / QOI_ENC_COMPUTE */
@@ -65,6 +65,7 @@ struct QoiEncParams {
 	uint8_t *streams;
 	int32_t *lens;
 	const QoiImgMeta *imgs;
+	const uint32_t *tile_img; /* [n_tiles] image that owns each tile */
 	uint32_t n_images;
 	uint32_t n_tiles;
 	uint32_t epoch; /* 1 .. 2^30-1, different for every launch that shares the state arrays */
@@ -77,6 +78,7 @@ struct QoiDecParams {
 	uint8_t *out;
 	int32_t *status; /* may be NULL */
 	const QoiImgMeta *imgs;
+	const uint32_t *tile_img; /* [tiles] image that owns each tile (indexed decode) */
 	uint32_t n_images;
 	uint32_t n_jobs;  /* tiles if use_index, else images */
 	int32_t out_channels;

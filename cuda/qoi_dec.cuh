@@ -55,18 +55,7 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 	if (job >= P.n_jobs) return;
 
 	/* ---- which image, which pixels ---- */
-	uint32_t img;
-	if (P.use_index) {
-		uint32_t lo = 0, hi = P.n_images - 1;
-		while (lo < hi) {
-			const uint32_t mid = (lo + hi + 1) >> 1;
-			if (P.imgs[mid].first_tile <= job) lo = mid;
-			else hi = mid - 1;
-		}
-		img = lo;
-	} else {
-		img = job;
-	}
+	const uint32_t img = P.use_index ? P.tile_img[job] : job;
 	const QoiImgMeta m = P.imgs[img];
 	const uint8_t *s = P.streams + m.stream_off;
 	const int32_t size = P.lens[img];

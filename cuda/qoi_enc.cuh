@@ -20,31 +20,36 @@
  * whose alignment is congruent to the destination and leave with one TMA bulk
  * store plus <16-byte edges.
  *
- * CTA = 8 compute warps (512 px each, 16 px per thread) + 1 scout warp.
+ * Inside a tile the "previous pixel with my hash slot" is found through a
+ * slot x position BIT MATRIX in shared memory (64 rows of 4096 bits): every
+ * non-run pixel sets its bit, then looks backwards along its row for the nearest
+ * set bit.  The gaps along one row sum to at most the tile length, so a tile
+ * costs O(pixels + 64 * words) word reads however the slots are distributed.
  *
- *   compute warps                                   scout warp
- *   -------------                                   ----------
- *   wait tile bytes (mbarrier)                      ticket + TMA for the NEXT tile
- *   E  (EXPAND only) raw bytes -> RGBA words
- *   I  index pass, striped: 32 consecutive px per
- *      step; same-slot lanes from 6 ballots of the
- *      hash bits, per-warp 64-entry table across
- *      steps; first occurrences of a slot in the
- *      warp chunk are deferred (<= 64 per warp)
- *        ---- I_DONE ---->                          T  tile aggregate published; 32-tile window
- *   C0 classify pass, blocked, with provisional        look-back for the incoming table + last
- *      hit bits: RUN / INDEX / DIFF / LUMA / RGB /      non-run index; inclusive record published
- *      RGBA exactly like qoi.h:415-474
- *        <--- T_READY ----
- *   R  resolve deferred occurrences (T_in, earlier warps)
- *   C1 patch pixels whose hit bit changed; threads that
- *      start inside a run carried from before redo C0
- *      block scan of byte counts
- *        ---- C_DONE ---->                          B  output-offset look-back (32 tiles/probe)
- *        <--- B_READY ----
+ * CTA = 8 compute warps (16 consecutive px per thread) + scout warp + loader warp.
+ *
+ *   compute warps                              scout warp               loader warp
+ *   -------------                              ----------               -----------
+ *   wait tile bytes (mbarrier)                                          ticket, TMA for the NEXT tile
+ *   E  (EXPAND) raw bytes -> RGBA words
+ *   A  hash + non-run flag per pixel, set bits
+ *      in the slot x position matrix
+ *        ------- I_DONE ------->               T  tile aggregate (last
+ *   C0 per pixel: nearest earlier bit in its      writer per slot) published;
+ *      row -> INDEX hit or not; RUN / DIFF /      32-tile window look-back for
+ *      LUMA / RGB / RGBA exactly like              the incoming table and the last
+ *      qoi.h:415-474.  A slot's first pixel        non-run index; inclusive record
+ *      in the tile is deferred (<= 64)             published
+ *        <------ T_READY -------
+ *   R  deferred pixels against T_in
+ *   C1 patch pixels that became hits; threads
+ *      inside a run carried into the tile redo
+ *      their 16 pixels; block scan of sizes
+ *        ------- C_DONE ------->               B  output-offset look-back
+ *        <------ B_READY -------                  (32 tiles per probe)
  *   W  op bytes -> staging; restart entry
- *        ---- W_DONE ---->                          staging -> global (TMA store + edges), header,
- *                                                   end marker, length
+ *        ------- W_DONE ----------------------------------------------> staging -> global (TMA store
+ *        <------ STAGE_FREE -------------------------------------------  + edges), header, end marker
  */
 #pragma once
 #include <limits.h>
@@ -70,23 +75,35 @@ struct TileInfo {
 	uint32_t pad[3];
 };
 
-enum { BAR_COMPUTE = 1, BAR_I_DONE = 2, BAR_T_READY = 3, BAR_C_DONE = 4, BAR_B_READY = 5, BAR_W_DONE = 6 };
+enum {
+	BAR_COMPUTE = 1,    /* the 256 compute threads */
+	BAR_I_DONE = 2,     /* compute -> scout */
+	BAR_T_READY = 3,    /* scout -> compute */
+	BAR_C_DONE = 4,     /* compute -> scout */
+	BAR_B_READY = 5,    /* scout -> compute */
+	BAR_W_DONE = 6,     /* compute -> loader */
+	BAR_STAGE_FREE = 7, /* loader -> compute + scout: next tile's info is in shared memory, staging is free */
+	BAR_E_DONE = 8      /* compute -> loader (EXPAND): the raw buffer has been consumed */
+};
+#define QOI_N_CS (QOI_ENC_COMPUTE + 32)      /* compute + one helper warp */
+#define QOI_N_ALL QOI_ENC_THREADS
+
+#define QOI_CELL_ROW 520 /* bytes per slot row: 4096 bits + 8 bytes of padding (spreads rows over the banks) */
 
 template <int CH, bool EXPAND>
 struct Layout {
+	static constexpr int NBUF = EXPAND ? 1 : 2; /* EXPAND frees the raw buffer right after phase E */
 	static constexpr int RAW_STRIDE = 16 + 16 + QOI_TILE_PX * CH + 16;
 	static constexpr int OFF_RAW = 0;
-	static constexpr int OFF_PXBUF = 2 * RAW_STRIDE;
+	static constexpr int OFF_PXBUF = NBUF * RAW_STRIDE;
 	static constexpr int PXBUF_BYTES = EXPAND ? (16 + QOI_TILE_PX * 4 + 16) : 0;
-	static constexpr int OFF_STAGE = OFF_PXBUF + PXBUF_BYTES;
+	static constexpr int OFF_CELLS = OFF_PXBUF + PXBUF_BYTES;         /* bit matrix; the staging buffer aliases it */
+	static constexpr int CELLS_BYTES = 64 * QOI_CELL_ROW;
 	static constexpr int STAGE_BYTES = 16 + QOI_TILE_PX * (CH + 1) + 16;
-	static constexpr int OFF_LENT = OFF_STAGE + STAGE_BYTES;          /* uint2 [8][64]: {value, written} */
-	static constexpr int OFF_TINVAL = OFF_LENT + 8 * 64 * 8;          /* u32 [64] */
+	static constexpr int OFF_TINVAL = OFF_CELLS + CELLS_BYTES;        /* u32 [64] */
 	static constexpr int OFF_HITW = OFF_TINVAL + 64 * 4;              /* u32 [128] */
-	static constexpr int OFF_NRW = OFF_HITW + 128 * 4;                /* u32 [128] */
-	static constexpr int OFF_LNRS = OFF_NRW + 128 * 4;                /* i32 [128] */
-	static constexpr int OFF_FPOS = OFF_LNRS + 128 * 4;               /* u16 [8][64] */
-	static constexpr int OFF_TINFLAG = OFF_FPOS + 8 * 64 * 2;         /* u8 [64] */
+	static constexpr int OFF_FPOS = OFF_HITW + 128 * 4;               /* u16 [64] */
+	static constexpr int OFF_TINFLAG = OFF_FPOS + 64 * 2;             /* u8 [64] */
 	static constexpr int OFF_MBAR = OFF_TINFLAG + 64;                 /* u64 [2] */
 	static constexpr int OFF_INFO = OFF_MBAR + 16;                    /* TileInfo [2] */
 	static constexpr int OFF_NBR = OFF_INFO + 2 * (int)sizeof(TileInfo); /* u32 [2][2] */
@@ -95,8 +112,9 @@ struct Layout {
 	static constexpr int OFF_WLNRIN = OFF_WLNR + 32;                  /* i32 [8] */
 	static constexpr int OFF_MISC = OFF_WLNRIN + 32;                  /* u32 [8] */
 	static constexpr int TOTAL = OFF_MISC + 32;
+	static_assert(STAGE_BYTES <= CELLS_BYTES, "staging must fit into the bit matrix it aliases");
 	static_assert(sizeof(TileInfo) % 16 == 0, "TileInfo must keep 16-byte alignment of what follows");
-	static_assert(OFF_STAGE % 16 == 0 && OFF_LENT % 16 == 0 && OFF_MBAR % 8 == 0, "alignment");
+	static_assert(OFF_CELLS % 16 == 0 && OFF_TINVAL % 16 == 0 && OFF_MBAR % 8 == 0, "alignment");
 };
 
 /* misc[] slots */
@@ -109,36 +127,52 @@ __device__ __forceinline__ uint64_t pack_ent(uint32_t epoch, uint32_t value, boo
 	return ((uint64_t)value << 32) | (uint64_t)((epoch << 1) | (written ? 1u : 0u));
 }
 __device__ __forceinline__ uint64_t pack_sum(uint32_t epoch, uint32_t payload) { return ((uint64_t)payload << 32) | epoch; }
+__device__ __forceinline__ int hi_bit64(uint64_t w) { /* index of the highest set bit, w != 0 */
+	const uint32_t hi = (uint32_t)(w >> 32);
+	return hi ? 63 - __clz((int)hi) : 31 - __clz((int)(uint32_t)w);
+}
 
-/* ---------------------------------------------------------------- tile fetch (scout warp) */
-template <int CH, bool EXPAND>
-__device__ __forceinline__ void fetch_tile(const QoiEncParams &P, unsigned char *smem, int b) {
-	using L = Layout<CH, EXPAND>;
+/* ---------------------------------------------------------------- tile fetch (loader warp) */
+struct Fetch {
+	uint32_t tile;
+	bool any;
+	QoiImgMeta m;
+	uint32_t img;
+};
+
+/* step 1: take a ticket and read the image record (touches no shared memory) */
+__device__ __forceinline__ void fetch_ticket(const QoiEncParams &P, Fetch &F) {
 	const uint32_t lane = lane_id();
-	TileInfo *info = (TileInfo *)(smem + L::OFF_INFO) + b;
-	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR) + b;
 	uint32_t tile = 0;
 	if (lane == 0) tile = atomicAdd(&P.st.ticket[0], 1u);
 	tile = __shfl_sync(QOI_FULL_MASK, tile, 0);
-	if (tile >= P.n_tiles) {
+	F.tile = tile;
+	F.any = tile < P.n_tiles;
+	if (F.any) {
+		F.img = P.tile_img[tile];
+		F.m = P.imgs[F.img];
+	}
+}
+
+/* step 2: start the bulk copy into raw buffer `rb`, fill fragments / neighbours, publish the info record `ib` */
+template <int CH, bool EXPAND>
+__device__ __forceinline__ void fetch_issue(const QoiEncParams &P, unsigned char *smem, const Fetch &F, int rb, int ib) {
+	using L = Layout<CH, EXPAND>;
+	const uint32_t lane = lane_id();
+	TileInfo *info = (TileInfo *)(smem + L::OFF_INFO) + ib;
+	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR) + rb;
+	if (!F.any) {
 		if (lane == 0) info->tile = -1;
 		return;
 	}
-	/* image that owns the tile: largest i with first_tile[i] <= tile */
-	uint32_t lo = 0, hi = P.n_images - 1;
-	while (lo < hi) {
-		uint32_t mid = (lo + hi + 1) >> 1;
-		if (P.imgs[mid].first_tile <= tile) lo = mid;
-		else hi = mid - 1;
-	}
-	const QoiImgMeta m = P.imgs[lo];
-	const uint32_t t_in = tile - m.first_tile;
+	const QoiImgMeta &m = F.m;
+	const uint32_t t_in = F.tile - m.first_tile;
 	const uint32_t px0 = t_in * QOI_TILE_PX;
 	const uint32_t n_valid = (m.npx - px0) < (uint32_t)QOI_TILE_PX ? (m.npx - px0) : (uint32_t)QOI_TILE_PX;
 	const uint8_t *gsrc = P.pixels + m.pix_off + (uint64_t)px0 * CH;
 	const uint32_t nbytes = n_valid * CH;
 	const uint32_t sh = EXPAND ? (uint32_t)((uintptr_t)gsrc & 15u) : 0u;
-	unsigned char *data = smem + L::OFF_RAW + b * L::RAW_STRIDE + 16; /* data[sh + k] = gsrc[k] */
+	unsigned char *data = smem + L::OFF_RAW + rb * L::RAW_STRIDE + 16; /* data[sh + k] = gsrc[k] */
 	const uint32_t lo_off = (sh + 15u) & ~15u;
 	const uint32_t hi_off = (sh + nbytes) & ~15u;
 	const uint32_t tma_bytes = hi_off > lo_off ? hi_off - lo_off : 0u;
@@ -169,12 +203,12 @@ __device__ __forceinline__ void fetch_tile(const QoiEncParams &P, unsigned char 
 		}
 	}
 	if (lane < 2) {
-		if (EXPAND) ((uint32_t *)(smem + L::OFF_NBR))[b * 2 + lane] = nb;
+		if (EXPAND) ((uint32_t *)(smem + L::OFF_NBR))[ib * 2 + lane] = nb;
 		else ((uint32_t *)data)[lane == 0 ? -1 : QOI_TILE_PX] = nb;
 	}
 	if (lane == 0) {
-		info->tile = (int32_t)tile;
-		info->img = lo;
+		info->tile = (int32_t)F.tile;
+		info->img = F.img;
 		info->t_in_img = t_in;
 		info->n_valid = n_valid;
 		info->px0 = px0;
@@ -309,20 +343,19 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 	QOI_DYNAMIC_SMEM(smem);
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const bool scout = warp == QOI_ENC_WARPS;
+	const bool loader = warp == QOI_ENC_WARPS + 1;
 	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR);
 	TileInfo *infos = (TileInfo *)(smem + L::OFF_INFO);
-	uint2 *Lent_all = (uint2 *)(smem + L::OFF_LENT);
-	uint16_t *Fpos_all = (uint16_t *)(smem + L::OFF_FPOS);
+	unsigned char *cells = smem + L::OFF_CELLS;
+	unsigned char *stage = cells; /* alias: the matrix is dead once phase R is over */
+	uint16_t *Fpos = (uint16_t *)(smem + L::OFF_FPOS);
 	uint32_t *Tin_val = (uint32_t *)(smem + L::OFF_TINVAL);
 	uint8_t *Tin_flag = (uint8_t *)(smem + L::OFF_TINFLAG);
 	uint32_t *hitw = (uint32_t *)(smem + L::OFF_HITW);
-	uint32_t *nrw = (uint32_t *)(smem + L::OFF_NRW);
-	int32_t *lnrs = (int32_t *)(smem + L::OFF_LNRS);
 	uint32_t *wtot = (uint32_t *)(smem + L::OFF_WTOT);
 	int32_t *wlnr = (int32_t *)(smem + L::OFF_WLNR);
 	int32_t *wlnr_in = (int32_t *)(smem + L::OFF_WLNRIN);
 	uint32_t *misc = (uint32_t *)(smem + L::OFF_MISC);
-	unsigned char *stage = smem + L::OFF_STAGE;
 
 	if (tid == 0) {
 		mbar_init(&mbar[0], 1);
@@ -331,37 +364,91 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 		misc[MISC_RS_CAND] = (uint32_t)INT_MAX;
 	}
 	__syncthreads();
-	if (scout) fetch_tile<CH, EXPAND>(P, smem, 0);
-	__syncthreads();
+	if (loader) {
+		Fetch F;
+		fetch_ticket(P, F);
+		fetch_issue<CH, EXPAND>(P, smem, F, 0, 0);
+		__syncwarp();
+		bar_arrive(BAR_STAGE_FREE, QOI_N_ALL);
+	}
 
 	int cur = 0;
 	uint32_t parity0 = 0, parity1 = 0;
 	const uint32_t epoch = P.epoch;
 
 	while (true) {
+		if (!loader) bar_sync(BAR_STAGE_FREE, QOI_N_ALL); /* infos[cur] is published, staging / matrix memory is free */
 		const TileInfo ti = infos[cur];
 		if (ti.tile < 0) break;
 		const uint32_t t = (uint32_t)ti.tile;
-		unsigned char *data = smem + L::OFF_RAW + cur * L::RAW_STRIDE + 16;
+		const int rb = EXPAND ? 0 : cur;
+		unsigned char *data = smem + L::OFF_RAW + rb * L::RAW_STRIDE + 16;
+		uint32_t *pxv = EXPAND ? (uint32_t *)(smem + L::OFF_PXBUF + 16) : (uint32_t *)data; /* pxv[-1 .. 4096] */
 		uint8_t *gstream = P.streams + ti.stream_off;
 
-		if (scout) {
-			/* =============================== scout warp =============================== */
-			fetch_tile<CH, EXPAND>(P, smem, cur ^ 1); /* prefetch: overlaps the whole tile */
+		if (loader) {
+			/* =============================== loader warp =============================== */
+			Fetch F;
+			fetch_ticket(P, F);
+			if (EXPAND) bar_sync(BAR_E_DONE, QOI_N_CS); /* single raw buffer: wait until phase E has drained it */
+			fetch_issue<CH, EXPAND>(P, smem, F, EXPAND ? 0 : (cur ^ 1), cur ^ 1);
 
-			bar_sync(BAR_I_DONE, QOI_ENC_THREADS); /* per-warp tables of this tile are complete */
-			/* ---- phase T: tile aggregate (lane handles slots lane, lane+32) ---- */
+			bar_sync(BAR_W_DONE, QOI_N_CS); /* staging is complete */
+			{
+				const uint32_t excl = misc[MISC_TILE_BASE], total = misc[MISC_TILE_TOTAL];
+				uint8_t *gdst = gstream + excl;
+				const uint32_t padb = (uint32_t)((uintptr_t)gdst & 15u);
+				const uint32_t lo_off = (padb + 15u) & ~15u;
+				const uint32_t end = padb + total;
+				const uint32_t hi_off = end & ~15u;
+				const bool bulk = hi_off > lo_off;
+				if (lane == 0 && bulk) {
+					fence_proxy_async_smem();
+					tma_store_1d(gdst + (lo_off - padb), stage + lo_off, hi_off - lo_off);
+					tma_store_commit();
+				}
+				const uint32_t a_hi = bulk ? lo_off : end; /* [padb, a_hi) */
+				const uint32_t b_lo = bulk ? hi_off : end; /* [b_lo, end)  */
+				for (uint32_t o = padb + lane; o < a_hi; o += 32) gdst[o - padb] = stage[o];
+				for (uint32_t o = b_lo + lane; o < end; o += 32) gdst[o - padb] = stage[o];
+				if (t == ti.first_tile && lane < QOI_HEADER_BYTES) { /* header, qoi.h:384-388 */
+					const uint32_t k = lane;
+					uint8_t b;
+					if (k < 4) b = (uint8_t)("qoif"[k]);
+					else if (k < 8) b = (uint8_t)(ti.width >> (8 * (7 - k)));
+					else if (k < 12) b = (uint8_t)(ti.height >> (8 * (11 - k)));
+					else if (k == 12) b = (uint8_t)(ti.chan_cs & 0xFFu);
+					else b = (uint8_t)(ti.chan_cs >> 8);
+					gstream[k] = b;
+				}
+				if (ti.px0 + ti.n_valid == ti.npx && lane >= 16 && lane < 16 + QOI_END_BYTES + 1) { /* end marker, length: qoi.h:480-484 */
+					const uint32_t k = lane - 16;
+					const uint32_t fin = excl + total;
+					if (k < QOI_END_BYTES) gstream[fin + k] = (k == QOI_END_BYTES - 1) ? 1 : 0;
+					else P.lens[ti.img] = (int32_t)(fin + QOI_END_BYTES);
+				}
+				if (lane == 0) {
+					misc[MISC_RS_CAND] = (uint32_t)INT_MAX; /* for the next tile */
+					tma_store_wait_read();                  /* the bulk store has finished reading the staging buffer */
+				}
+			}
+			__syncwarp();
+			bar_arrive(BAR_STAGE_FREE, QOI_N_ALL);
+		} else if (scout) {
+			/* =============================== scout warp =============================== */
+			bar_sync(BAR_I_DONE, QOI_N_CS); /* the bit matrix and wlnr[] of this tile are complete */
+			/* ---- phase T: tile aggregate = last set bit of each slot row (lane handles slots lane, lane+32) ---- */
 			uint32_t own_val[2];
 			bool own_ok[2];
 #pragma unroll
 			for (int q = 0; q < 2; q++) {
-				const uint32_t s = lane + 32u * q;
+				const uint64_t *row = (const uint64_t *)(cells + (lane + 32u * q) * QOI_CELL_ROW);
 				own_ok[q] = false;
 				own_val[q] = 0;
-				for (int w = QOI_ENC_WARPS - 1; w >= 0; w--) {
-					const uint2 e = Lent_all[w * 64 + s];
-					if (e.y) {
-						own_val[q] = e.x;
+				for (int g = 63; g >= 0; g--) {
+					const uint64_t w = row[g];
+					if (w) {
+						own_val[q] = pxv[g * 64 + hi_bit64(w)];
 						own_ok[q] = true;
 						break;
 					}
@@ -403,17 +490,11 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				const uint32_t payload = lane == 0 ? inc_lo : (lane == 1 ? inc_hi : (uint32_t)inc_lnr);
 				st_relaxed_u64(&P.st.inc_sum[(size_t)t * QOI_SUM_WORDS + lane], pack_sum(epoch, payload));
 			}
-			if (lane == 0) { /* last non-run pixel index before each warp chunk (image coordinates) */
-				int32_t run = lb.lnr_in;
-				for (int w = 0; w < QOI_ENC_WARPS; w++) {
-					wlnr_in[w] = run;
-					if (wlnr[w] >= 0) run = (int32_t)ti.px0 + wlnr[w];
-				}
-			}
+			if (lane == 0) wlnr_in[0] = lb.lnr_in; /* last non-run pixel index before the tile (image coordinates) */
 			__syncwarp();
-			bar_arrive(BAR_T_READY, QOI_ENC_THREADS);
+			bar_arrive(BAR_T_READY, QOI_N_CS);
 
-			bar_sync(BAR_C_DONE, QOI_ENC_THREADS); /* byte counts of the compute warps are in wtot[] */
+			bar_sync(BAR_C_DONE, QOI_N_CS); /* byte counts of the compute warps are in wtot[] */
 			/* ---- phase B: output offset look-back, 32 predecessors per probe ---- */
 			uint32_t total = 0;
 #pragma unroll
@@ -452,56 +533,20 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				st_relaxed_u64(&P.st.byte_state[t], pack_bytes(epoch, QOI_ST_INC, excl + total));
 				misc[MISC_TILE_BASE] = excl;
 				misc[MISC_TILE_TOTAL] = total;
-				tma_store_wait_read(); /* the previous tile's bulk store has finished reading the staging buffer */
 			}
 			__syncwarp();
-			bar_arrive(BAR_B_READY, QOI_ENC_THREADS);
-
-			bar_sync(BAR_W_DONE, QOI_ENC_THREADS); /* staging is complete, everybody has read this tile's misc[] */
-			if (lane == 0) misc[MISC_RS_CAND] = (uint32_t)INT_MAX; /* for the next tile (used after its T_READY) */
-			/* ---- staging -> global: one bulk store for the 16-byte aligned interior, byte stores for the edges ---- */
-			{
-				uint8_t *gdst = gstream + excl;
-				const uint32_t padb = (uint32_t)((uintptr_t)gdst & 15u);
-				const uint32_t lo_off = (padb + 15u) & ~15u;
-				const uint32_t end = padb + total;
-				const uint32_t hi_off = end & ~15u;
-				const bool bulk = hi_off > lo_off;
-				if (lane == 0 && bulk) {
-					fence_proxy_async_smem();
-					tma_store_1d(gdst + (lo_off - padb), stage + lo_off, hi_off - lo_off);
-					tma_store_commit();
-				}
-				const uint32_t a_hi = bulk ? lo_off : end; /* [padb, a_hi) */
-				const uint32_t b_lo = bulk ? hi_off : end; /* [b_lo, end)  */
-				for (uint32_t o = padb + lane; o < a_hi; o += 32) gdst[o - padb] = stage[o];
-				for (uint32_t o = b_lo + lane; o < end; o += 32) gdst[o - padb] = stage[o];
-				if (t == ti.first_tile && lane < QOI_HEADER_BYTES) { /* header, qoi.h:384-388 */
-					const uint32_t k = lane;
-					uint8_t b;
-					if (k < 4) b = (uint8_t)("qoif"[k]);
-					else if (k < 8) b = (uint8_t)(ti.width >> (8 * (7 - k)));
-					else if (k < 12) b = (uint8_t)(ti.height >> (8 * (11 - k)));
-					else if (k == 12) b = (uint8_t)(ti.chan_cs & 0xFFu);
-					else b = (uint8_t)(ti.chan_cs >> 8);
-					gstream[k] = b;
-				}
-				if (ti.px0 + ti.n_valid == ti.npx && lane >= 16 && lane < 16 + QOI_END_BYTES + 1) { /* end marker, length: qoi.h:480-484 */
-					const uint32_t k = lane - 16;
-					const uint32_t fin = excl + total;
-					if (k < QOI_END_BYTES) gstream[fin + k] = (k == QOI_END_BYTES - 1) ? 1 : 0;
-					else P.lens[ti.img] = (int32_t)(fin + QOI_END_BYTES);
-				}
-			}
+			bar_arrive(BAR_B_READY, QOI_N_CS);
 		} else {
 			/* =============================== compute warps =============================== */
-			if (cur == 0) { mbar_wait(&mbar[0], parity0); parity0 ^= 1u; }
+			if (rb == 0) { mbar_wait(&mbar[0], parity0); parity0 ^= 1u; }
 			else { mbar_wait(&mbar[1], parity1); parity1 ^= 1u; }
 
-			uint32_t *pxv; /* pxv[-1] = pixel before the tile, pxv[0..4095], pxv[4096] = pixel after */
+			/* clear the bit matrix (it aliases the staging buffer of the previous tile) and the per-tile side tables */
+			for (uint32_t k = tid; k < (uint32_t)(L::CELLS_BYTES / 16); k += QOI_ENC_COMPUTE) ((uint4 *)cells)[k] = make_uint4(0u, 0u, 0u, 0u);
+			if (tid < 128) hitw[tid] = 0u;
+			if (tid < 64) Fpos[tid] = 0xFFFFu;
 			if (EXPAND) {
 				/* ---- phase E: 16 pixels per thread, raw bytes at data[sh + CH*i] -> RGBA words ---- */
-				pxv = (uint32_t *)(smem + L::OFF_PXBUF + 16);
 				const uint32_t b0 = ti.sh + tid * (16u * CH);
 				const uint32_t *wsrc = (const uint32_t *)data + (b0 >> 2);
 				const uint32_t shf = (b0 & 3u) * 8u;
@@ -538,70 +583,15 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 					pxv[-1] = nbr[0];
 					pxv[QOI_TILE_PX] = nbr[1];
 				}
-				bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
-			} else {
-				pxv = (uint32_t *)data;
 			}
+			bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
+			if (EXPAND) bar_arrive(BAR_E_DONE, QOI_N_CS); /* the raw buffer may be refilled */
 
-			/* ---- phase I: striped index pass, one warp per 512-pixel chunk ---- */
-			{
-				uint2 *Lent = Lent_all + warp * 64;
-				uint16_t *Fpos = Fpos_all + warp * 64;
-				Lent[lane] = make_uint2(0u, 0u);
-				Lent[lane + 32] = make_uint2(0u, 0u);
-				Fpos[lane] = 0xFFFFu;
-				Fpos[lane + 32] = 0xFFFFu;
-				__syncwarp();
-				int32_t last_nr = -1; /* tile-local index of the last non-run pixel seen so far in this chunk */
-				const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
-#pragma unroll 1
-				for (int s = 0; s < QOI_WARP_STEPS; s++) {
-					const uint32_t i = warp * QOI_WARP_PX + s * 32 + lane;
-					const uint32_t v = pxv[i];
-					const uint32_t p = pxv[(int)i - 1];
-					const bool nonrun = (i < ti.n_valid) && (v != p);
-					const uint32_t h = qoi_slot(v);
-					const uint32_t nr = __ballot_sync(QOI_FULL_MASK, nonrun);
-					/* lanes whose (non-run) pixel has the same slot: intersect the six hash-bit planes */
-					uint32_t m = nr;
-#pragma unroll
-					for (int b = 0; b < 6; b++) {
-						const bool bit = (h >> b) & 1u;
-						const uint32_t plane = __ballot_sync(QOI_FULL_MASK, nonrun && bit);
-						m &= bit ? plane : ~plane;
-					}
-					const uint32_t lower = m & lt;
-					const int src = lower ? (31 - __clz((int)lower)) : (int)lane;
-					const uint32_t pv = __shfl_sync(QOI_FULL_MASK, v, src);
-					const uint2 ent = Lent[h];
-					bool hit = false;
-					if (nonrun) {
-						if (lower) hit = (pv == v);           /* predecessor with the same slot inside this step */
-						else if (ent.y) hit = (ent.x == v);   /* ... inside this warp chunk */
-						else Fpos[h] = (uint16_t)i;           /* first occurrence in the chunk: resolved in phase R */
-					}
-					const uint32_t hb = __ballot_sync(QOI_FULL_MASK, hit);
-					__syncwarp();
-					if (nonrun && (m & gt) == 0u) Lent[h] = make_uint2(v, 1u); /* last pixel of its slot in this step */
-					if (lane == 0) {
-						hitw[warp * QOI_WARP_STEPS + s] = hb;
-						nrw[warp * QOI_WARP_STEPS + s] = nr;
-						lnrs[warp * QOI_WARP_STEPS + s] = last_nr;
-					}
-					if (nr) last_nr = (int32_t)(warp * QOI_WARP_PX + s * 32 + 31 - __clz((int)nr));
-					__syncwarp();
-				}
-				if (lane == 0) wlnr[warp] = last_nr;
-			}
-			__syncwarp();
-			bar_arrive(BAR_I_DONE, QOI_ENC_THREADS);
-
-			/* ---- phase C: blocked classify pass, 16 consecutive pixels per thread ---- */
+			/* ---- phase A: my 16 consecutive pixels: non-run flags, bits into the slot x position matrix ---- */
 			uint32_t v[16];
 			uint32_t code[16];
 			uint32_t ttotal = 0;
 			const uint32_t i0 = tid * 16u;
-			const uint32_t wi = i0 >> 5, bo = i0 & 31u;
 			uint32_t pprev, pnext;
 			{
 				const uint4 *src = (const uint4 *)(pxv + i0);
@@ -613,55 +603,68 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				pprev = pxv[(int)i0 - 1];
 				pnext = pxv[i0 + 16];
 			}
-			const uint32_t nrword = nrw[wi];
-			const uint32_t nrbits = (nrword >> bo) & 0xFFFFu;
-			const uint32_t below = nrword & ((1u << bo) - 1u);
-			/* Does this thread start inside a run whose start lies outside what this warp has seen?  Only then
-			   does it need the carry from earlier warps / tiles, and it waits for it (pass 1). */
-			int32_t lnr_local = -1; /* tile-local index of the last non-run pixel before my first one, if known locally */
-			if (below) lnr_local = (int32_t)((i0 & ~31u) + 31u - (uint32_t)__clz((int)below));
-			else lnr_local = lnrs[wi];
-			const bool first_is_run = (i0 < ti.n_valid) && !(nrbits & 1u);
-			const bool defer = first_is_run && lnr_local < 0;
-			uint32_t hitbits = (hitw[wi] >> bo) & 0xFFFFu;
+			uint32_t nrbits = 0;
+			{
+				uint32_t before = pprev;
+#pragma unroll
+				for (int j = 0; j < 16; j++) {
+					if (i0 + j < ti.n_valid && v[j] != before) {
+						uint16_t *cell = (uint16_t *)(cells + qoi_slot(v[j]) * QOI_CELL_ROW) + tid;
+						*cell = (uint16_t)(*cell | (1u << j));
+						nrbits |= 1u << j;
+					}
+					before = v[j];
+				}
+			}
+			/* last non-run pixel (tile coordinates) before my first pixel: warp max-scan + per-warp totals */
+			int32_t lnr_local;
+			{
+				const int32_t mine = nrbits ? (int32_t)(i0 + 31u - (uint32_t)__clz((int)nrbits)) : -1;
+				int32_t incl = mine;
+#pragma unroll
+				for (int dlt = 1; dlt < 32; dlt <<= 1) {
+					const int32_t o = __shfl_up_sync(QOI_FULL_MASK, incl, dlt);
+					if (lane >= (uint32_t)dlt && o > incl) incl = o;
+				}
+				lnr_local = __shfl_up_sync(QOI_FULL_MASK, incl, 1);
+				if (lane == 0) lnr_local = -1;
+				if (lane == 31) wlnr[warp] = incl;
+			}
+			bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE); /* matrix and wlnr[] complete */
+			bar_arrive(BAR_I_DONE, QOI_N_CS);
+			if (lnr_local < 0) {
+				for (int w = (int)warp - 1; w >= 0; w--) {
+					if (wlnr[w] >= 0) {
+						lnr_local = wlnr[w];
+						break;
+					}
+				}
+			}
+			/* a thread that starts inside a run which began before this tile needs the carry from the look-back */
+			const bool defer = (i0 < ti.n_valid) && !(nrbits & 1u) && lnr_local < 0;
+			uint32_t hitbits = 0;
 			int32_t cand = INT_MAX;
+			const uint32_t grp = tid >> 2, bitbase = (tid & 3u) * 16u;
+
+			/* ---- phase C: classify pass; pass 0 with what the tile knows, pass 1 after the look-back ---- */
 #pragma unroll 1
 			for (int pass = 0; pass < 2; pass++) {
-				int32_t lnr_glob = (lnr_local >= 0) ? (int32_t)ti.px0 + lnr_local : 0;
+				int32_t lnr_glob = (lnr_local >= 0) ? (int32_t)ti.px0 + lnr_local : (int32_t)(ti.px0 + i0) - 1;
 				if (pass == 1) {
-					bar_sync(BAR_T_READY, QOI_ENC_THREADS); /* T_in and the run carry are in shared memory */
-					/* ---- phase R: resolve the deferred first occurrences (<= 64 per warp chunk) ---- */
-#pragma unroll
-					for (int j = 0; j < 2; j++) {
-						const uint32_t q = tid * 2 + j;
-						const int w = (int)(q >> 6);
-						const uint32_t s = q & 63u;
-						const uint32_t pos = Fpos_all[w * 64 + s];
+					bar_sync(BAR_T_READY, QOI_N_CS); /* T_in and the run carry are in shared memory */
+					/* ---- phase R: a slot's first pixel in the tile against the incoming table ---- */
+					if (tid < 64) {
+						const uint32_t pos = Fpos[tid];
 						if (pos != 0xFFFFu) {
 							const uint32_t pvv = pxv[pos];
-							bool found = false;
-							uint32_t val = 0;
-							for (int w2 = w - 1; w2 >= 0; w2--) {
-								const uint2 e = Lent_all[w2 * 64 + s];
-								if (e.y) {
-									val = e.x;
-									found = true;
-									break;
-								}
-							}
-							if (!found && Tin_flag[s]) {
-								val = Tin_val[s];
-								found = true;
-							}
 							/* an untouched index[] slot holds 0 (qoi.h:393): only the all-zero pixel can hit it */
-							const bool hit = found ? (val == pvv) : (pvv == 0u);
+							const bool hit = Tin_flag[tid] ? (Tin_val[tid] == pvv) : (pvv == 0u);
 							if (hit) atomicOr(&hitw[pos >> 5], 1u << (pos & 31u));
 						}
 					}
 					bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
-					const uint32_t hb1 = (hitw[wi] >> bo) & 0xFFFFu;
-					const uint32_t changed = hb1 ^ hitbits; /* bits can only turn on */
-					hitbits = hb1;
+					const uint32_t changed = (hitw[i0 >> 5] >> (i0 & 31u)) & 0xFFFFu; /* pixels that turned into hits */
+					hitbits |= changed;
 					if (!defer) {
 						/* patch the pixels that turned into INDEX ops (qoi.h:432-434) */
 #pragma unroll
@@ -673,9 +676,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 						}
 						break;
 					}
-					lnr_glob = (lnr_local >= 0) ? (int32_t)ti.px0 + lnr_local : wlnr_in[warp];
-				} else if (defer) {
-					continue;
+					lnr_glob = wlnr_in[0];
 				}
 				/* run pixels between the last non-run pixel and my first pixel */
 				const uint32_t c = (uint32_t)((int32_t)(ti.px0 + i0) - 1 - lnr_glob);
@@ -691,7 +692,28 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 						if ((nrbits >> j) & 1u) {
 							r = -1;
 							if (cand == INT_MAX) cand = (int32_t)(i0 + j);
-							if ((hitbits >> j) & 1u) cd = 1u | (qoi_slot(v[j]) << 8); /* qoi.h:432-434 */
+							const uint32_t h = qoi_slot(v[j]);
+							bool hit;
+							if (pass == 0) {
+								/* nearest earlier non-run pixel with my slot: walk back along row h of the bit matrix */
+								const uint64_t *row = (const uint64_t *)(cells + h * QOI_CELL_ROW);
+								int g = (int)grp;
+								uint64_t w = row[g] & ((1ull << (bitbase + j)) - 1ull);
+								while (w == 0ull && g > 0) {
+									g--;
+									w = row[g];
+								}
+								if (w) {
+									hit = pxv[g * 64 + hi_bit64(w)] == v[j];
+								} else {
+									Fpos[h] = (uint16_t)(i0 + j); /* first pixel of this slot in the tile: phase R decides */
+									hit = false;
+								}
+								hitbits |= (hit ? 1u : 0u) << j;
+							} else {
+								hit = (hitbits >> j) & 1u;
+							}
+							if (hit) cd = 1u | (h << 8); /* qoi.h:432-434 */
 							else cd = classify(v[j], before);
 						} else {
 							/* run pixel (qoi.h:415-421): a byte leaves at run length 62, at the image end, or when the run ends */
@@ -716,9 +738,9 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 			}
 			if (lane == 31) wtot[warp] = incl;
 			__syncwarp();
-			bar_arrive(BAR_C_DONE, QOI_ENC_THREADS);
+			bar_arrive(BAR_C_DONE, QOI_N_CS);
 
-			bar_sync(BAR_B_READY, QOI_ENC_THREADS);
+			bar_sync(BAR_B_READY, QOI_N_CS);
 			/* ---- phase W: op bytes -> staging (alignment congruent to the destination) ---- */
 			const uint32_t tile_base = misc[MISC_TILE_BASE];
 			const int32_t rs_cand = (int32_t)misc[MISC_RS_CAND];
@@ -754,14 +776,14 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				if (tid == 0 && rs_cand == INT_MAX) P.st.rs_px[t] = -1;
 			}
 			__syncwarp();
-			bar_arrive(BAR_W_DONE, QOI_ENC_THREADS);
+			bar_arrive(BAR_W_DONE, QOI_N_CS);
 		}
 		cur ^= 1;
 	}
 
 	/* the last CTA to finish rearms the ticket for the next launch */
 	__syncthreads();
-	if (tid == QOI_ENC_COMPUTE) { /* scout lane 0 issued the bulk stores */
+	if (loader && lane == 0) { /* this thread issued the bulk stores */
 		tma_store_wait_all();
 		const uint32_t done = atomicAdd(&P.st.ticket[1], 1u);
 		if (done == gridDim.x - 1u) {

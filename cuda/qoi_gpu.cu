@@ -41,6 +41,7 @@ struct qoi_gpu_plan {
 	QoiPlanGeom geom;
 	QoiStateLayout layout;
 	QoiImgMeta *d_metas = nullptr;
+	uint32_t *d_tile_img = nullptr;
 	unsigned char *d_state = nullptr;
 	QoiTileState st;
 	uint32_t epoch = 0;
@@ -145,6 +146,8 @@ int qoi_gpu_plan_create(qoi_gpu_ctx *ctx, qoi_gpu_plan **out, int n, const qoi_d
 	p->layout = qoi_state_layout(p->geom.n_tiles);
 	cudaError_t e = cudaSetDevice(ctx->device);
 	if (e == cudaSuccess) e = cudaMalloc(&p->d_metas, sizeof(QoiImgMeta) * (size_t)n);
+	if (e == cudaSuccess) e = cudaMalloc(&p->d_tile_img, sizeof(uint32_t) * (size_t)p->geom.n_tiles);
+	if (e == cudaSuccess) e = cudaMemcpy(p->d_tile_img, p->geom.tile_img.data(), sizeof(uint32_t) * (size_t)p->geom.n_tiles, cudaMemcpyHostToDevice);
 	if (e == cudaSuccess) e = cudaMalloc(&p->d_state, p->layout.total);
 	if (e == cudaSuccess) e = cudaMemset(p->d_state, 0, p->layout.total);
 	if (e == cudaSuccess) e = cudaMemcpy(p->d_metas, p->geom.metas.data(), sizeof(QoiImgMeta) * (size_t)n, cudaMemcpyHostToDevice);
@@ -162,6 +165,7 @@ void qoi_gpu_plan_destroy(qoi_gpu_plan *p) {
 	if (!p) return;
 	cudaSetDevice(p->ctx->device);
 	cudaFree(p->d_metas);
+	cudaFree(p->d_tile_img);
 	cudaFree(p->d_state);
 	cudaFree(p->d_pixels);
 	cudaFree(p->d_streams);
@@ -189,6 +193,7 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	P.streams = (uint8_t *)d_streams;
 	P.lens = d_lens;
 	P.imgs = p->d_metas;
+	P.tile_img = p->d_tile_img;
 	P.n_images = (uint32_t)p->geom.metas.size();
 	P.n_tiles = p->geom.n_tiles;
 	P.epoch = p->epoch;
@@ -219,6 +224,7 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 	D.out = (uint8_t *)d_decoded;
 	D.status = d_status;
 	D.imgs = p->d_metas;
+	D.tile_img = p->d_tile_img;
 	D.n_images = (uint32_t)p->geom.metas.size();
 	D.n_jobs = use_index ? p->geom.n_tiles : D.n_images;
 	D.out_channels = p->geom.dec_channels;

@@ -36,6 +36,7 @@ static inline size_t qoi_max_foreign_stream(const QoiDescPOD &d) {
 
 struct QoiPlanGeom {
 	std::vector<QoiImgMeta> metas;
+	std::vector<uint32_t> tile_img; /* image index of every tile */
 	uint32_t n_tiles = 0;
 	uint64_t total_px = 0;
 	int channels = 0;
@@ -77,6 +78,12 @@ static inline int qoi_plan_geometry(QoiPlanGeom &g, int n, const QoiDescPOD *des
 		e = m.dec_off + (uint64_t)m.npx * g.dec_channels; if (e > g.decoded_bytes) g.decoded_bytes = e;
 	}
 	g.n_tiles = (uint32_t)tiles;
+	g.tile_img.resize(g.n_tiles);
+	for (int i = 0; i < n; i++) {
+		const QoiImgMeta &m = g.metas[(size_t)i];
+		const uint32_t nt = (m.npx + QOI_TILE_PX - 1) / QOI_TILE_PX;
+		for (uint32_t k = 0; k < nt; k++) g.tile_img[m.first_tile + k] = (uint32_t)i;
+	}
 	return 0;
 }
 

@@ -99,6 +99,7 @@ int main(int argc, char **argv) {
 			P.streams = streams.data();
 			P.lens = lens.data();
 			P.imgs = g.metas.data();
+			P.tile_img = g.tile_img.data();
 			P.n_images = (uint32_t)n;
 			P.n_tiles = g.n_tiles;
 			qoi_state_bind(P.st, sbase, SL);
@@ -139,6 +140,7 @@ int main(int argc, char **argv) {
 				D.out = out.data();
 				D.status = status.data();
 				D.imgs = g.metas.data();
+				D.tile_img = g.tile_img.data();
 				D.n_images = (uint32_t)n;
 				D.n_jobs = use_index ? g.n_tiles : (uint32_t)n;
 				D.out_channels = dec_ch;
@@ -189,6 +191,7 @@ int main(int argc, char **argv) {
 			D.out = out.data();
 			D.status = status.data();
 			D.imgs = g.metas.data();
+			D.tile_img = g.tile_img.data();
 			D.n_images = (uint32_t)n;
 			D.n_jobs = (uint32_t)n;
 			D.out_channels = dec_ch;

@@ -25,7 +25,9 @@ cat gpurun_out/bench_ref.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --batch 8 --no-cpu --e2e-steps 1 > gpurun_out/ncu_bench.log 2>&1; echo "NCU_LIST_RC=$?"
 grep -c qoi gpurun_out/launches.csv
-# full capture of the two kernels (3 launches each, after warm-up)
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:qoi_ -s 6 -c 4 -o gpurun_out/prof -f \
-    python bench.py --steps 2 --warmup 3 --batch 8 --no-cpu --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1; echo "NCU_FULL_RC=$?"
+# full capture: encoder at batch 8, decoder at the bench batch (its occupancy depends on the segment count)
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:qoi_encode -s 3 -c 2 -o gpurun_out/prof_enc -f \
+    python bench.py --steps 2 --warmup 3 --batch 8 --no-cpu --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1; echo "NCU_ENC_RC=$?"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:qoi_decode -s 3 -c 2 -o gpurun_out/prof_dec -f \
+    python bench.py --steps 2 --warmup 3 --batch 32 --no-cpu --e2e-steps 1 >> gpurun_out/ncu_full.log 2>&1; echo "NCU_DEC_RC=$?"
 ls -la gpurun_out
