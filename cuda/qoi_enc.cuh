@@ -82,8 +82,9 @@ enum {
 	BAR_C_DONE = 4,     /* compute -> scout */
 	BAR_B_READY = 5,    /* scout -> compute */
 	BAR_W_DONE = 6,     /* compute -> loader */
-	BAR_STAGE_FREE = 7, /* loader -> compute + scout: next tile's info is in shared memory, staging is free */
-	BAR_E_DONE = 8      /* compute -> loader (EXPAND): the raw buffer has been consumed */
+	BAR_STAGE_FREE = 7, /* loader -> compute: the bulk store has drained the staging buffer (== bit matrix memory) */
+	BAR_E_DONE = 8,     /* compute -> loader (EXPAND): the raw buffer has been consumed */
+	BAR_INFO_READY = 9  /* loader -> compute + scout: the next tile's info record is in shared memory */
 };
 #define QOI_N_CS (QOI_ENC_COMPUTE + 32)      /* compute + one helper warp */
 #define QOI_N_ALL QOI_ENC_THREADS
@@ -146,10 +147,11 @@ __device__ __forceinline__ void fetch_ticket(const QoiEncParams &P, Fetch &F) {
 	uint32_t tile = 0;
 	if (lane == 0) tile = atomicAdd(&P.st.ticket[0], 1u);
 	tile = __shfl_sync(QOI_FULL_MASK, tile, 0);
-	F.tile = tile;
 	F.any = tile < P.n_tiles;
+	F.tile = 0;
 	if (F.any) {
-		F.img = P.tile_img[tile];
+		F.tile = P.tile_order[tile]; /* ascending inside every image, images interleaved */
+		F.img = P.tile_img[F.tile];
 		F.m = P.imgs[F.img];
 	}
 }
@@ -260,37 +262,37 @@ __device__ __forceinline__ void table_lookback(const QoiEncParams &P, uint32_t t
 	int64_t base = (int64_t)t - 1;
 	while (true) {
 		const int64_t tp = base - lane;
-		uint32_t state, vlo = 0, vhi = 0;
+		uint32_t state = QOI_ST_NONE, vlo = 0, vhi = 0;
 		int32_t lnr = -1;
 		if (tp < (int64_t)first_tile) {
 			state = QOI_ST_INC; /* before the image: nothing written, no non-run pixel yet */
-		} else {
+		} else { /* one look, no waiting: an unpublished tile only matters if nothing nearer resolves the slot */
 			const uint64_t *is = P.st.inc_sum + (size_t)tp * QOI_SUM_WORDS;
 			const uint64_t *as = P.st.agg_sum + (size_t)tp * QOI_SUM_WORDS;
-			while (true) {
-				uint64_t w0 = ld_relaxed_u64(is + 0), w1 = ld_relaxed_u64(is + 1), w2 = ld_relaxed_u64(is + 2);
-				if ((uint32_t)w0 == epoch && (uint32_t)w1 == epoch && (uint32_t)w2 == epoch) {
-					state = QOI_ST_INC;
-					vlo = (uint32_t)(w0 >> 32); vhi = (uint32_t)(w1 >> 32); lnr = (int32_t)(uint32_t)(w2 >> 32);
-					break;
-				}
+			uint64_t w0 = ld_relaxed_u64(is + 0), w1 = ld_relaxed_u64(is + 1), w2 = ld_relaxed_u64(is + 2);
+			if ((uint32_t)w0 == epoch && (uint32_t)w1 == epoch && (uint32_t)w2 == epoch) {
+				state = QOI_ST_INC;
+			} else {
 				w0 = ld_relaxed_u64(as + 0); w1 = ld_relaxed_u64(as + 1); w2 = ld_relaxed_u64(as + 2);
-				if ((uint32_t)w0 == epoch && (uint32_t)w1 == epoch && (uint32_t)w2 == epoch) {
-					state = QOI_ST_AGG;
-					vlo = (uint32_t)(w0 >> 32); vhi = (uint32_t)(w1 >> 32); lnr = (int32_t)(uint32_t)(w2 >> 32);
-					break;
-				}
-				spin_pause();
+				if ((uint32_t)w0 == epoch && (uint32_t)w1 == epoch && (uint32_t)w2 == epoch) state = QOI_ST_AGG;
+			}
+			if (state != QOI_ST_NONE) {
+				vlo = (uint32_t)(w0 >> 32); vhi = (uint32_t)(w1 >> 32); lnr = (int32_t)(uint32_t)(w2 >> 32);
 			}
 		}
-		const uint32_t incm = __ballot_sync(QOI_FULL_MASK, state == QOI_ST_INC);
+		/* lanes [0, usable) hold published tiles; only they (up to the nearest inclusive record) may answer */
+		const uint32_t known = __ballot_sync(QOI_FULL_MASK, state != QOI_ST_NONE);
+		const uint32_t usable = (known == 0xFFFFFFFFu) ? 32u : (uint32_t)__ffs((int)~known) - 1u;
+		const uint32_t umask = (usable == 32u) ? 0xFFFFFFFFu : ((1u << usable) - 1u);
+		const uint32_t incm = __ballot_sync(QOI_FULL_MASK, state == QOI_ST_INC) & umask;
 		const uint32_t first_inc = incm ? (uint32_t)__ffs((int)incm) - 1u : 32u;
-		if (lane > first_inc) { /* tiles older than the nearest inclusive record are irrelevant */
+		const bool part = lane < usable && lane <= first_inc;
+		if (!part) {
 			vlo = vhi = 0;
 			lnr = QOI_LNR_NONE;
 		}
 		if (need_lnr) {
-			const bool has = (lane <= first_inc) && (state == QOI_ST_INC || lnr != QOI_LNR_NONE);
+			const bool has = part && (state == QOI_ST_INC || lnr != QOI_LNR_NONE);
 			const uint32_t hb = __ballot_sync(QOI_FULL_MASK, has);
 			if (hb) {
 				R.lnr_in = __shfl_sync(QOI_FULL_MASK, lnr, __ffs((int)hb) - 1);
@@ -317,8 +319,10 @@ __device__ __forceinline__ void table_lookback(const QoiEncParams &P, uint32_t t
 			if (half) need_hi &= ~any;
 			else need_lo &= ~any;
 		}
-		if (incm) break; /* whatever is still unresolved was never written before this tile */
-		base -= 32;
+		if (incm) break;                                  /* whatever is still unresolved was never written before this tile */
+		if (!need_lnr && !(need_lo | need_hi)) break;     /* everything answered by nearer tiles */
+		if (usable == 0u) spin_pause();                   /* the nearest undecided tile has not published yet */
+		base -= usable;
 	}
 	/* the values themselves */
 #pragma unroll
@@ -369,7 +373,8 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 		fetch_ticket(P, F);
 		fetch_issue<CH, EXPAND>(P, smem, F, 0, 0);
 		__syncwarp();
-		bar_arrive(BAR_STAGE_FREE, QOI_N_ALL);
+		bar_arrive(BAR_INFO_READY, QOI_N_ALL);
+		bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
 	}
 
 	int cur = 0;
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 	const uint32_t epoch = P.epoch;
 
 	while (true) {
-		if (!loader) bar_sync(BAR_STAGE_FREE, QOI_N_ALL); /* infos[cur] is published, staging / matrix memory is free */
+		if (!loader) bar_sync(BAR_INFO_READY, QOI_N_ALL); /* infos[cur] is published */
 		const TileInfo ti = infos[cur];
 		if (ti.tile < 0) break;
 		const uint32_t t = (uint32_t)ti.tile;
@@ -392,6 +397,8 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 			fetch_ticket(P, F);
 			if (EXPAND) bar_sync(BAR_E_DONE, QOI_N_CS); /* single raw buffer: wait until phase E has drained it */
 			fetch_issue<CH, EXPAND>(P, smem, F, EXPAND ? 0 : (cur ^ 1), cur ^ 1);
+			__syncwarp();
+			bar_arrive(BAR_INFO_READY, QOI_N_ALL); /* consumed at the top of the next iteration */
 
 			bar_sync(BAR_W_DONE, QOI_N_CS); /* staging is complete */
 			{
@@ -433,7 +440,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				}
 			}
 			__syncwarp();
-			bar_arrive(BAR_STAGE_FREE, QOI_N_ALL);
+			bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
 		} else if (scout) {
 			/* =============================== scout warp =============================== */
 			bar_sync(BAR_I_DONE, QOI_N_CS); /* the bit matrix and wlnr[] of this tile are complete */
@@ -542,6 +549,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 			else { mbar_wait(&mbar[1], parity1); parity1 ^= 1u; }
 
 			/* clear the bit matrix (it aliases the staging buffer of the previous tile) and the per-tile side tables */
+			bar_sync(BAR_STAGE_FREE, QOI_N_CS);
 			for (uint32_t k = tid; k < (uint32_t)(L::CELLS_BYTES / 16); k += QOI_ENC_COMPUTE) ((uint4 *)cells)[k] = make_uint4(0u, 0u, 0u, 0u);
 			if (tid < 128) hitw[tid] = 0u;
 			if (tid < 64) Fpos[tid] = 0xFFFFu;

@@ -42,6 +42,7 @@ struct qoi_gpu_plan {
 	QoiStateLayout layout;
 	QoiImgMeta *d_metas = nullptr;
 	uint32_t *d_tile_img = nullptr;
+	uint32_t *d_tile_order = nullptr;
 	unsigned char *d_state = nullptr;
 	QoiTileState st;
 	uint32_t epoch = 0;
@@ -148,6 +149,8 @@ int qoi_gpu_plan_create(qoi_gpu_ctx *ctx, qoi_gpu_plan **out, int n, const qoi_d
 	if (e == cudaSuccess) e = cudaMalloc(&p->d_metas, sizeof(QoiImgMeta) * (size_t)n);
 	if (e == cudaSuccess) e = cudaMalloc(&p->d_tile_img, sizeof(uint32_t) * (size_t)p->geom.n_tiles);
 	if (e == cudaSuccess) e = cudaMemcpy(p->d_tile_img, p->geom.tile_img.data(), sizeof(uint32_t) * (size_t)p->geom.n_tiles, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMalloc(&p->d_tile_order, sizeof(uint32_t) * (size_t)p->geom.n_tiles);
+	if (e == cudaSuccess) e = cudaMemcpy(p->d_tile_order, p->geom.tile_order.data(), sizeof(uint32_t) * (size_t)p->geom.n_tiles, cudaMemcpyHostToDevice);
 	if (e == cudaSuccess) e = cudaMalloc(&p->d_state, p->layout.total);
 	if (e == cudaSuccess) e = cudaMemset(p->d_state, 0, p->layout.total);
 	if (e == cudaSuccess) e = cudaMemcpy(p->d_metas, p->geom.metas.data(), sizeof(QoiImgMeta) * (size_t)n, cudaMemcpyHostToDevice);
@@ -166,6 +169,7 @@ void qoi_gpu_plan_destroy(qoi_gpu_plan *p) {
 	cudaSetDevice(p->ctx->device);
 	cudaFree(p->d_metas);
 	cudaFree(p->d_tile_img);
+	cudaFree(p->d_tile_order);
 	cudaFree(p->d_state);
 	cudaFree(p->d_pixels);
 	cudaFree(p->d_streams);
@@ -194,6 +198,7 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	P.lens = d_lens;
 	P.imgs = p->d_metas;
 	P.tile_img = p->d_tile_img;
+	P.tile_order = p->d_tile_order;
 	P.n_images = (uint32_t)p->geom.metas.size();
 	P.n_tiles = p->geom.n_tiles;
 	P.epoch = p->epoch;

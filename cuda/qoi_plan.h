@@ -37,6 +37,7 @@ static inline size_t qoi_max_foreign_stream(const QoiDescPOD &d) {
 struct QoiPlanGeom {
 	std::vector<QoiImgMeta> metas;
 	std::vector<uint32_t> tile_img; /* image index of every tile */
+	std::vector<uint32_t> tile_order; /* ticket -> tile (round robin over the images, ascending inside an image) */
 	uint32_t n_tiles = 0;
 	uint64_t total_px = 0;
 	int channels = 0;
@@ -83,6 +84,22 @@ static inline int qoi_plan_geometry(QoiPlanGeom &g, int n, const QoiDescPOD *des
 		const QoiImgMeta &m = g.metas[(size_t)i];
 		const uint32_t nt = (m.npx + QOI_TILE_PX - 1) / QOI_TILE_PX;
 		for (uint32_t k = 0; k < nt; k++) g.tile_img[m.first_tile + k] = (uint32_t)i;
+	}
+	/* Ticket order.  A tile only ever waits for EARLIER tiles of its own image, so any order that is ascending
+	   inside each image is safe; interleaving the images keeps the look-back chains short (the ~450 tiles in
+	   flight then belong to many images instead of one). */
+	g.tile_order.clear();
+	g.tile_order.reserve(g.n_tiles);
+	{
+		uint32_t max_tiles = 0;
+		std::vector<uint32_t> nts((size_t)n);
+		for (int i = 0; i < n; i++) {
+			nts[(size_t)i] = (g.metas[(size_t)i].npx + QOI_TILE_PX - 1) / QOI_TILE_PX;
+			if (nts[(size_t)i] > max_tiles) max_tiles = nts[(size_t)i];
+		}
+		for (uint32_t k = 0; k < max_tiles; k++)
+			for (int i = 0; i < n; i++)
+				if (k < nts[(size_t)i]) g.tile_order.push_back(g.metas[(size_t)i].first_tile + k);
 	}
 	return 0;
 }

@@ -100,6 +100,7 @@ int main(int argc, char **argv) {
 			P.lens = lens.data();
 			P.imgs = g.metas.data();
 			P.tile_img = g.tile_img.data();
+			P.tile_order = g.tile_order.data();
 			P.n_images = (uint32_t)n;
 			P.n_tiles = g.n_tiles;
 			qoi_state_bind(P.st, sbase, SL);
