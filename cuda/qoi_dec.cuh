@@ -17,10 +17,13 @@
  *
  * One LANE per segment (not one warp): each lane runs the scalar state machine
  * with its 64-entry table in shared memory, laid out [slot][thread] so that any
- * slot pattern across the lanes is bank-conflict free.  Stream bytes come through
- * a per-lane 64-bit window refilled with aligned 32-bit loads (never past the
- * stream's last byte); all lanes produce one pixel per loop trip, so pixels leave
- * in groups of four with one 16-byte store per lane.
+ * slot pattern across the lanes is bank-conflict free.  Stream bytes are fetched
+ * 32 bytes (one full sector) at a time per lane with two 16-byte loads that are
+ * issued one chunk ahead and parked in registers, then dropped into a small
+ * per-lane ring in shared memory; the op parser reads a 64-bit window refilled
+ * from that ring.  No load touches a byte outside the stream's own words.  All
+ * lanes produce one pixel per loop trip, so pixels leave in groups of four with
+ * one 16-byte store per lane.
  */
 #pragma once
 #include "qoi_common.h"
@@ -40,17 +43,43 @@ __device__ __forceinline__ uint32_t add_bytes(uint32_t a, uint32_t b) {
 	return ((a & 0x7F7F7F7Fu) + (b & 0x7F7F7F7Fu)) ^ ((a ^ b) & 0x80808080u);
 }
 
+#define QOI_DEC_RING_WORDS 16 /* two 32-byte chunks per lane */
+#define QOI_DEC_SMEM_WORDS (64 + QOI_DEC_RING_WORDS)
+
 struct Reader {
-	const uint32_t *wp; /* next aligned word to load */
 	uint64_t buf;       /* the next `avail` stream bytes, lowest byte first */
 	uint32_t avail;
 	int32_t p;          /* stream offset of buf's first byte */
+	uint32_t wi;        /* ring word the window is refilled from next */
+	const uint4 *gp;    /* next 32-byte chunk to fetch (32-byte aligned address) */
+	uintptr_t lo, hi;   /* the stream's own words: [lo, hi), 4-byte aligned */
+	uint4 pa, pb;       /* the chunk that is in flight / parked until its ring half is free */
 };
+
+/* 32 bytes at gp; words outside [lo, hi) read as zero and are never touched */
+__device__ __forceinline__ void load_chunk(Reader &rd) {
+	const uintptr_t a = (uintptr_t)rd.gp;
+	if (a >= rd.lo && a + 32 <= rd.hi) {
+		rd.pa = __ldg(rd.gp);
+		rd.pb = __ldg(rd.gp + 1);
+	} else {
+		uint32_t w[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			const uintptr_t wa = a + 4u * k;
+			w[k] = (wa >= rd.lo && wa + 4 <= rd.hi) ? __ldg((const uint32_t *)wa) : 0u;
+		}
+		rd.pa = make_uint4(w[0], w[1], w[2], w[3]);
+		rd.pb = make_uint4(w[4], w[5], w[6], w[7]);
+	}
+	rd.gp += 2;
+}
 
 template <int OUT_CH, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P) {
 	QOI_DYNAMIC_SMEM(smem);
-	uint32_t *tab = (uint32_t *)smem + threadIdx.x; /* tab[slot * BLOCK] */
+	uint32_t *tab = (uint32_t *)smem + threadIdx.x;  /* tab[slot * BLOCK] */
+	uint32_t *ring = tab + 64 * BLOCK;               /* ring[word * BLOCK] */
 	const uint32_t job = blockIdx.x * BLOCK + threadIdx.x;
 	if (job >= P.n_jobs) return;
 
@@ -107,15 +136,39 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 	Reader rd;
 	{
 		const uintptr_t a = (uintptr_t)(s + p0);
-		rd.wp = (const uint32_t *)(a & ~(uintptr_t)3);
+		rd.lo = (uintptr_t)s & ~(uintptr_t)3;
+		rd.hi = ((uintptr_t)s + (uintptr_t)size + 3u) & ~(uintptr_t)3;
+		rd.gp = (const uint4 *)(a & ~(uintptr_t)31);
 		rd.p = p0;
+		/* the first two chunks go straight into the ring, the third is put in flight */
+#pragma unroll
+		for (int half = 0; half < 2; half++) {
+			load_chunk(rd);
+			uint32_t *r = ring + half * 8 * BLOCK;
+			r[0 * BLOCK] = rd.pa.x; r[1 * BLOCK] = rd.pa.y; r[2 * BLOCK] = rd.pa.z; r[3 * BLOCK] = rd.pa.w;
+			r[4 * BLOCK] = rd.pb.x; r[5 * BLOCK] = rd.pb.y; r[6 * BLOCK] = rd.pb.z; r[7 * BLOCK] = rd.pb.w;
+		}
+		load_chunk(rd);
+		rd.wi = (uint32_t)((a & 31u) >> 2);
 		rd.buf = 0;
 		rd.avail = 0;
-		if (p0 < stop) { /* the word holding byte p0 lies inside the stream */
-			const uint32_t mis = (uint32_t)(a & 3u);
-			rd.buf = (uint64_t)(__ldg(rd.wp++) >> (8u * mis));
-			rd.avail = 4u - mis;
+	}
+	/* next 4 stream bytes from the ring; when a ring half has been used up, park the in-flight chunk there and fetch the next */
+	auto next_word = [&]() -> uint32_t {
+		const uint32_t w = ring[(rd.wi & (QOI_DEC_RING_WORDS - 1)) * BLOCK];
+		rd.wi++;
+		if ((rd.wi & 7u) == 0u) {
+			uint32_t *r = ring + ((rd.wi - 8u) & (QOI_DEC_RING_WORDS - 1)) * BLOCK;
+			r[0 * BLOCK] = rd.pa.x; r[1 * BLOCK] = rd.pa.y; r[2 * BLOCK] = rd.pa.z; r[3 * BLOCK] = rd.pa.w;
+			r[4 * BLOCK] = rd.pb.x; r[5 * BLOCK] = rd.pb.y; r[6 * BLOCK] = rd.pb.z; r[7 * BLOCK] = rd.pb.w;
+			load_chunk(rd);
 		}
+		return w;
+	};
+	{ /* prime the window with the word that holds byte p0 */
+		const uint32_t mis = (uint32_t)((uintptr_t)(s + p0) & 3u);
+		rd.buf = (uint64_t)(next_word() >> (8u * mis));
+		rd.avail = 4u - mis;
 	}
 	uint32_t run = 0;
 
@@ -124,12 +177,12 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 		if (run > 0) {
 			run--;
 		} else if (rd.p < stop) {
-			/* an op needs at most 5 bytes; a refill word starts at or before byte p+4 <= size-5, so no load crosses `size` */
+			/* an op needs at most 5 bytes */
 			if (rd.avail < 5u) {
-				rd.buf |= (uint64_t)__ldg(rd.wp++) << (8u * rd.avail);
+				rd.buf |= (uint64_t)next_word() << (8u * rd.avail);
 				rd.avail += 4u;
 				if (rd.avail < 5u) {
-					rd.buf |= (uint64_t)__ldg(rd.wp++) << (8u * rd.avail);
+					rd.buf |= (uint64_t)next_word() << (8u * rd.avail);
 					rd.avail += 4u;
 				}
 			}

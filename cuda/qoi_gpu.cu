@@ -75,7 +75,7 @@ static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
 template <int OUT_CH, int BLOCK>
 static void launch_decode(const QoiDecParams &D, cudaStream_t s) {
 	const uint32_t grid = (D.n_jobs + BLOCK - 1) / BLOCK;
-	qoidec::qoi_decode_kernel<OUT_CH, BLOCK><<<grid, BLOCK, 64 * BLOCK * 4, s>>>(D);
+	qoidec::qoi_decode_kernel<OUT_CH, BLOCK><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
 }
 
 extern "C" {

@@ -48,7 +48,7 @@ static void run_encode(const QoiEncParams &P, unsigned grid, unsigned seed) {
 
 static void run_decode(const QoiDecParams &P, unsigned seed) {
 	unsigned grid = (P.n_jobs + QOI_DEC_THREADS - 1) / QOI_DEC_THREADS;
-	size_t smem = 64 * QOI_DEC_THREADS * 4;
+	size_t smem = QOI_DEC_SMEM_WORDS * QOI_DEC_THREADS * 4;
 	if (P.out_channels == 4) qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS>(P); }, seed);
 	else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS>(P); }, seed);
 }
