@@ -31,7 +31,8 @@ static std::atomic<uint64_t> g_launches{0};
 struct qoi_gpu_ctx {
 	int device = 0;
 	int sm_count = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr;                 /* kernels of the host-buffer entry points */
+	cudaStream_t s_h2d = nullptr, s_d2h = nullptr; /* one stream per copy direction: PCIe is full duplex */
 	char err[256] = {0};
 	int enc_blocks_per_sm[3] = {0, 0, 0}; /* <4,false>, <4,true>, <3,true> */
 };
@@ -51,6 +52,12 @@ struct qoi_gpu_plan {
 	unsigned char *d_pixels = nullptr, *d_streams = nullptr, *d_decoded = nullptr;
 	int32_t *d_lens = nullptr;
 	int32_t *h_lens_pinned = nullptr;
+	/* the host-buffer entry points cut the batch into chunks (sub-plans over the same buffers) and pipeline
+	   H2D copy / kernel / D2H copy of successive chunks */
+	std::vector<qoi_gpu_plan *> chunks;
+	std::vector<int> chunk_first;
+	std::vector<cudaEvent_t> ev_in, ev_k;
+	int index_owner = 0; /* who holds the restart index of the last encode: 0 nobody, 1 this plan, 2 the chunks */
 };
 
 #define CK(ctx, call)                                                                         \
@@ -99,6 +106,8 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 	cudaError_t e = cudaSetDevice(device);
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
 	if (e != cudaSuccess) {
 		delete c;
 		return QOI_GPU_E_CUDA;
@@ -120,6 +129,8 @@ void qoi_gpu_ctx_destroy(qoi_gpu_ctx *c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+	if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
 	delete c;
 }
 
@@ -176,6 +187,9 @@ void qoi_gpu_plan_destroy(qoi_gpu_plan *p) {
 	cudaFree(p->d_decoded);
 	cudaFree(p->d_lens);
 	if (p->h_lens_pinned) cudaFreeHost(p->h_lens_pinned);
+	for (qoi_gpu_plan *c : p->chunks) qoi_gpu_plan_destroy(c);
+	for (cudaEvent_t e : p->ev_in) cudaEventDestroy(e);
+	for (cudaEvent_t e : p->ev_k) cudaEventDestroy(e);
 	delete p;
 }
 
@@ -212,6 +226,7 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	else qoienc::qoi_encode_kernel<3, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
 	g_launches++;
 	CK(ctx, cudaGetLastError());
+	p->index_owner = 1;
 	return QOI_GPU_OK;
 }
 
@@ -260,50 +275,128 @@ static int plan_mirrors(qoi_gpu_plan *p) {
 	return QOI_GPU_OK;
 }
 
+#define QOI_HOST_CHUNKS 8
+
+/* sub-plans over the same buffers, one per chunk of consecutive images */
+static int plan_chunks(qoi_gpu_plan *p) {
+	if (!p->chunks.empty()) return QOI_GPU_OK;
+	qoi_gpu_ctx *ctx = p->ctx;
+	const int n = (int)p->geom.metas.size();
+	const int k = n < QOI_HOST_CHUNKS ? n : QOI_HOST_CHUNKS;
+	std::vector<qoi_desc> descs((size_t)n);
+	std::vector<uint64_t> po((size_t)n), so((size_t)n), dof((size_t)n);
+	for (int i = 0; i < n; i++) {
+		const QoiImgMeta &m = p->geom.metas[(size_t)i];
+		memset(&descs[(size_t)i], 0, sizeof(qoi_desc));
+		descs[(size_t)i].width = m.width; descs[(size_t)i].height = m.height;
+		descs[(size_t)i].channels = m.channels; descs[(size_t)i].colorspace = m.colorspace;
+		po[(size_t)i] = m.pix_off; so[(size_t)i] = m.stream_off; dof[(size_t)i] = m.dec_off;
+	}
+	for (int c = 0; c < k; c++) {
+		const int first = (int)((int64_t)n * c / k), last = (int)((int64_t)n * (c + 1) / k);
+		qoi_gpu_plan *sub = nullptr;
+		int rc = qoi_gpu_plan_create(ctx, &sub, last - first, descs.data() + first, po.data() + first, so.data() + first, dof.data() + first,
+		                             p->geom.dec_channels);
+		if (rc) return rc;
+		p->chunks.push_back(sub);
+		p->chunk_first.push_back(first);
+		cudaEvent_t e1, e2;
+		CK(ctx, cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+		CK(ctx, cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+		p->ev_in.push_back(e1);
+		p->ev_k.push_back(e2);
+	}
+	p->chunk_first.push_back(n);
+	return QOI_GPU_OK;
+}
+
 int qoi_gpu_encode_host(qoi_gpu_plan *p, const void *h_pixels, void *h_streams, int32_t *h_lens) {
 	if (!p || !h_pixels || !h_streams || !h_lens) return QOI_GPU_E_ARG;
 	qoi_gpu_ctx *ctx = p->ctx;
 	CK(ctx, cudaSetDevice(ctx->device));
 	int rc = plan_mirrors(p);
+	if (!rc) rc = plan_chunks(p);
 	if (rc) return rc;
-	cudaStream_t s = ctx->stream;
-	const size_t n = p->geom.metas.size();
-	CK(ctx, cudaMemcpyAsync(p->d_pixels, h_pixels, p->geom.pixel_bytes, cudaMemcpyHostToDevice, s));
-	rc = qoi_gpu_encode(p, p->d_pixels, p->d_streams, p->d_lens, s);
-	if (rc) return rc;
-	CK(ctx, cudaMemcpyAsync(p->h_lens_pinned, p->d_lens, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
-	CK(ctx, cudaStreamSynchronize(s));
-	for (size_t i = 0; i < n; i++) {
-		const QoiImgMeta &m = p->geom.metas[i];
-		h_lens[i] = p->h_lens_pinned[i];
-		CK(ctx, cudaMemcpyAsync((unsigned char *)h_streams + m.stream_off, p->d_streams + m.stream_off, (size_t)h_lens[i],
-		                        cudaMemcpyDeviceToHost, s));
+	const size_t nc = p->chunks.size();
+	/* queue everything that does not need the lengths: copy in, encode, lengths out -- chunk after chunk */
+	for (size_t c = 0; c < nc; c++) {
+		const int first = p->chunk_first[c], last = p->chunk_first[c + 1];
+		uint64_t lo = ~0ull, hi = 0;
+		for (int i = first; i < last; i++) {
+			const QoiImgMeta &m = p->geom.metas[(size_t)i];
+			const uint64_t e = m.pix_off + (uint64_t)m.npx * m.channels;
+			if (m.pix_off < lo) lo = m.pix_off;
+			if (e > hi) hi = e;
+		}
+		CK(ctx, cudaMemcpyAsync(p->d_pixels + lo, (const unsigned char *)h_pixels + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, ctx->s_h2d));
+		CK(ctx, cudaEventRecord(p->ev_in[c], ctx->s_h2d));
+		CK(ctx, cudaStreamWaitEvent(ctx->stream, p->ev_in[c], 0));
+		rc = qoi_gpu_encode(p->chunks[c], p->d_pixels, p->d_streams, p->d_lens + first, ctx->stream);
+		if (rc) return rc;
+		CK(ctx, cudaMemcpyAsync(p->h_lens_pinned + first, p->d_lens + first, sizeof(int32_t) * (size_t)(last - first), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaEventRecord(p->ev_k[c], ctx->stream));
 	}
-	CK(ctx, cudaStreamSynchronize(s));
+	/* streams out as soon as a chunk's lengths are known; these copies overlap the uploads and kernels of later chunks */
+	for (size_t c = 0; c < nc; c++) {
+		CK(ctx, cudaEventSynchronize(p->ev_k[c]));
+		for (int i = p->chunk_first[c]; i < p->chunk_first[c + 1]; i++) {
+			const QoiImgMeta &m = p->geom.metas[(size_t)i];
+			h_lens[i] = p->h_lens_pinned[i];
+			CK(ctx, cudaMemcpyAsync((unsigned char *)h_streams + m.stream_off, p->d_streams + m.stream_off, (size_t)h_lens[i],
+			                        cudaMemcpyDeviceToHost, ctx->s_d2h));
+		}
+	}
+	CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+	p->index_owner = 2;
 	return QOI_GPU_OK;
 }
 
 int qoi_gpu_decode_host(qoi_gpu_plan *p, const void *h_streams, const int32_t *h_lens, void *h_decoded, int use_index) {
 	if (!p || !h_streams || !h_lens || !h_decoded) return QOI_GPU_E_ARG;
+	if (use_index && p->index_owner == 0) return QOI_GPU_E_ARG;
 	qoi_gpu_ctx *ctx = p->ctx;
 	CK(ctx, cudaSetDevice(ctx->device));
 	int rc = plan_mirrors(p);
+	if (!rc) rc = plan_chunks(p);
 	if (rc) return rc;
-	cudaStream_t s = ctx->stream;
 	const size_t n = p->geom.metas.size();
 	for (size_t i = 0; i < n; i++) {
 		const QoiImgMeta &m = p->geom.metas[i];
 		QoiDescPOD d = {m.width, m.height, m.channels, m.colorspace};
 		if (h_lens[i] < QOI_HEADER_BYTES + QOI_END_BYTES || (size_t)h_lens[i] > qoi_max_foreign_stream(d)) return QOI_GPU_E_ARG;
 		p->h_lens_pinned[i] = h_lens[i];
-		CK(ctx, cudaMemcpyAsync(p->d_streams + m.stream_off, (const unsigned char *)h_streams + m.stream_off, (size_t)h_lens[i],
-		                        cudaMemcpyHostToDevice, s));
 	}
-	CK(ctx, cudaMemcpyAsync(p->d_lens, p->h_lens_pinned, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
-	rc = qoi_gpu_decode(p, p->d_streams, p->d_lens, p->d_decoded, use_index, nullptr, s);
-	if (rc) return rc;
-	CK(ctx, cudaMemcpyAsync(h_decoded, p->d_decoded, p->geom.decoded_bytes, cudaMemcpyDeviceToHost, s));
-	CK(ctx, cudaStreamSynchronize(s));
+	CK(ctx, cudaMemcpyAsync(p->d_lens, p->h_lens_pinned, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->s_h2d));
+	const bool whole = use_index && p->index_owner == 1; /* the index lives in this plan: one launch over the batch */
+	const size_t nc = p->chunks.size();
+	for (size_t c = 0; c < nc; c++) {
+		const int first = p->chunk_first[c], last = p->chunk_first[c + 1];
+		uint64_t lo = ~0ull, hi = 0;
+		for (int i = first; i < last; i++) {
+			const QoiImgMeta &m = p->geom.metas[(size_t)i];
+			CK(ctx, cudaMemcpyAsync(p->d_streams + m.stream_off, (const unsigned char *)h_streams + m.stream_off, (size_t)h_lens[i],
+			                        cudaMemcpyHostToDevice, ctx->s_h2d));
+			const uint64_t e = m.dec_off + (uint64_t)m.npx * p->geom.dec_channels;
+			if (m.dec_off < lo) lo = m.dec_off;
+			if (e > hi) hi = e;
+		}
+		CK(ctx, cudaEventRecord(p->ev_in[c], ctx->s_h2d));
+		CK(ctx, cudaStreamWaitEvent(ctx->stream, p->ev_in[c], 0));
+		if (whole) {
+			if (c + 1 < nc) continue; /* all streams first, then the single launch */
+			rc = qoi_gpu_decode(p, p->d_streams, p->d_lens, p->d_decoded, 1, nullptr, ctx->stream);
+			if (rc) return rc;
+			CK(ctx, cudaMemcpyAsync(h_decoded, p->d_decoded, p->geom.decoded_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(ctx, cudaStreamSynchronize(ctx->stream));
+			return QOI_GPU_OK;
+		}
+		rc = qoi_gpu_decode(p->chunks[c], p->d_streams, p->d_lens + first, p->d_decoded, use_index, nullptr, ctx->stream);
+		if (rc) return rc;
+		CK(ctx, cudaEventRecord(p->ev_k[c], ctx->stream));
+		CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, p->ev_k[c], 0));
+		CK(ctx, cudaMemcpyAsync((unsigned char *)h_decoded + lo, p->d_decoded + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, ctx->s_d2h));
+	}
+	CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
 	return QOI_GPU_OK;
 }
 
