@@ -69,9 +69,12 @@ def load_cpu_codec():
     db = getattr(lib, prefix + "decode_batch")
     db.restype = C.c_double
     db.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
-    ht = getattr(lib, prefix + "host_threads")
-    ht.restype = C.c_int
-    return kind, eb, db, ht()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU legs pass an explicit thread count (num_threads clause) instead
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    return kind, eb, db, max(1, threads)
 
 
 class DescC(C.Structure):

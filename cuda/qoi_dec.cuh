@@ -172,52 +172,46 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 	}
 	uint32_t run = 0;
 
-	/* one pixel: qoi.h:541-578 */
+	/* one pixel: qoi.h:541-578.  Lanes of a warp sit in different op types all the time, so the op itself is
+	   evaluated branch-free (every candidate result is computed, selects pick one); only the refill branches. */
 	auto step = [&]() -> uint32_t {
-		if (run > 0) {
-			run--;
-		} else if (rd.p < stop) {
-			/* an op needs at most 5 bytes */
+		const bool parse = (run == 0u) && (rd.p < stop);
+		if (parse && rd.avail < 5u) { /* an op needs at most 5 bytes */
+			rd.buf |= (uint64_t)next_word() << (8u * rd.avail);
+			rd.avail += 4u;
 			if (rd.avail < 5u) {
 				rd.buf |= (uint64_t)next_word() << (8u * rd.avail);
 				rd.avail += 4u;
-				if (rd.avail < 5u) {
-					rd.buf |= (uint64_t)next_word() << (8u * rd.avail);
-					rd.avail += 4u;
-				}
 			}
-			const uint32_t tag = (uint32_t)rd.buf & 0xFFu;
-			const uint32_t pay = (uint32_t)(rd.buf >> 8); /* the four bytes after the tag */
-			uint32_t len = 1;
-			if (tag >= 0xFEu) {
-				if (tag == 0xFEu) { /* qoi.h:547-551 */
-					px = (px & 0xFF000000u) | (pay & 0x00FFFFFFu);
-					len = 4;
-				} else { /* qoi.h:552-557 */
-					px = pay;
-					len = 5;
-				}
-			} else {
-				const uint32_t top = tag >> 6;
-				if (top == 0u) { /* qoi.h:558-560 */
-					px = tab[tag * BLOCK];
-				} else if (top == 1u) { /* qoi.h:561-565: each channel += field - 2, wrapping */
-					const uint32_t sel = ((tag >> 4) & 3u) | (((tag >> 2) & 3u) << 4) | ((tag & 3u) << 8) | 0x4000u;
-					px = add_bytes(px, __byte_perm(0x0100FFFEu, 0u, sel)); /* LUT: 0,1,2,3 -> -2,-1,0,+1 */
-				} else if (top == 2u) { /* qoi.h:566-572 */
-					const uint32_t vg = (tag & 0x3Fu) + 224u; /* -32 mod 256 */
-					const uint32_t rb = vg + 248u;            /* vg - 8 */
-					const uint32_t add = ((rb + ((pay >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((rb + (pay & 0xFu)) & 0xFFu) << 16);
-					px = add_bytes(px, add);
-					len = 2;
-				} else { /* qoi.h:573-575 */
-					run = tag & 0x3Fu;
-				}
-			}
+		}
+		const uint32_t tag = (uint32_t)rd.buf & 0xFFu;
+		const uint32_t pay = (uint32_t)(rd.buf >> 8); /* the four bytes after the tag */
+		const uint32_t top = tag >> 6;
+		const bool is_rgb = tag == 0xFEu, is_rgba = tag == 0xFFu; /* qoi.h:547-557 are tested before the 2-bit tags */
+		const uint32_t idxv = tab[(tag & 63u) * BLOCK];           /* qoi.h:558-560 */
+		/* qoi.h:561-565: each channel += field - 2, wrapping (LUT 0,1,2,3 -> -2,-1,0,+1) */
+		const uint32_t sel = ((tag >> 4) & 3u) | (((tag >> 2) & 3u) << 4) | ((tag & 3u) << 8) | 0x4000u;
+		const uint32_t dadd = __byte_perm(0x0100FFFEu, 0u, sel);
+		/* qoi.h:566-572 */
+		const uint32_t vg = (tag & 0x3Fu) + 224u; /* -32 mod 256 */
+		const uint32_t rb = vg + 248u;            /* vg - 8 */
+		const uint32_t ladd = ((rb + ((pay >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((rb + (pay & 0xFu)) & 0xFFu) << 16);
+		const uint32_t rel = add_bytes(px, top == 1u ? dadd : ladd);
+		uint32_t npx = top == 0u ? idxv : rel;
+		npx = top == 3u ? px : npx;                                            /* RUN keeps the colour (qoi.h:573-575) */
+		npx = is_rgb ? ((px & 0xFF000000u) | (pay & 0x00FFFFFFu)) : npx;
+		npx = is_rgba ? pay : npx;
+		const uint32_t len = is_rgba ? 5u : (is_rgb ? 4u : (top == 2u ? 2u : 1u));
+		const uint32_t nrun = (top == 3u && tag < 0xFEu) ? (tag & 0x3Fu) : 0u;
+		if (parse) {
+			px = npx;
 			rd.buf >>= 8u * len;
 			rd.avail -= len;
 			rd.p += (int32_t)len;
 			tab[qoi_slot(px) * BLOCK] = px; /* qoi.h:577 */
+			run = nrun;
+		} else if (run > 0u) {
+			run--;
 		}
 		return px;
 	};

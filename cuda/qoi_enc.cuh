@@ -101,7 +101,8 @@ struct Layout {
 	static constexpr int OFF_CELLS = OFF_PXBUF + PXBUF_BYTES;         /* bit matrix; the staging buffer aliases it */
 	static constexpr int CELLS_BYTES = 64 * QOI_CELL_ROW;
 	static constexpr int STAGE_BYTES = 16 + QOI_TILE_PX * (CH + 1) + 16;
-	static constexpr int OFF_TINVAL = OFF_CELLS + CELLS_BYTES;        /* u32 [64] */
+	static constexpr int OFF_SUMMARY = OFF_CELLS + CELLS_BYTES;       /* u64 [64]: bit g of row h = word g of the row is non-zero */
+	static constexpr int OFF_TINVAL = OFF_SUMMARY + 64 * 8;           /* u32 [64] */
 	static constexpr int OFF_HITW = OFF_TINVAL + 64 * 4;              /* u32 [128] */
 	static constexpr int OFF_FPOS = OFF_HITW + 128 * 4;               /* u16 [64] */
 	static constexpr int OFF_TINFLAG = OFF_FPOS + 64 * 2;             /* u8 [64] */
@@ -115,7 +116,7 @@ struct Layout {
 	static constexpr int TOTAL = OFF_MISC + 32;
 	static_assert(STAGE_BYTES <= CELLS_BYTES, "staging must fit into the bit matrix it aliases");
 	static_assert(sizeof(TileInfo) % 16 == 0, "TileInfo must keep 16-byte alignment of what follows");
-	static_assert(OFF_CELLS % 16 == 0 && OFF_TINVAL % 16 == 0 && OFF_MBAR % 8 == 0, "alignment");
+	static_assert(OFF_CELLS % 16 == 0 && OFF_SUMMARY % 8 == 0 && OFF_TINVAL % 16 == 0 && OFF_MBAR % 8 == 0, "alignment");
 };
 
 /* misc[] slots */
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR);
 	TileInfo *infos = (TileInfo *)(smem + L::OFF_INFO);
 	unsigned char *cells = smem + L::OFF_CELLS;
+	uint64_t *summary = (uint64_t *)(smem + L::OFF_SUMMARY);
 	unsigned char *stage = cells; /* alias: the matrix is dead once phase R is over */
 	uint16_t *Fpos = (uint16_t *)(smem + L::OFF_FPOS);
 	uint32_t *Tin_val = (uint32_t *)(smem + L::OFF_TINVAL);
@@ -449,16 +451,14 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 			bool own_ok[2];
 #pragma unroll
 			for (int q = 0; q < 2; q++) {
-				const uint64_t *row = (const uint64_t *)(cells + (lane + 32u * q) * QOI_CELL_ROW);
-				own_ok[q] = false;
+				const uint32_t sl = lane + 32u * q;
+				const uint64_t *row = (const uint64_t *)(cells + sl * QOI_CELL_ROW);
+				const uint64_t sm = summary[sl];
+				own_ok[q] = sm != 0ull;
 				own_val[q] = 0;
-				for (int g = 63; g >= 0; g--) {
-					const uint64_t w = row[g];
-					if (w) {
-						own_val[q] = pxv[g * 64 + hi_bit64(w)];
-						own_ok[q] = true;
-						break;
-					}
+				if (own_ok[q]) {
+					const int g = hi_bit64(sm);
+					own_val[q] = pxv[g * 64 + hi_bit64(row[g])];
 				}
 			}
 			int32_t own_lnr = QOI_LNR_NONE;
@@ -611,12 +611,15 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				pprev = pxv[(int)i0 - 1];
 				pnext = pxv[i0 + 16];
 			}
+			const bool full = ti.n_valid == (uint32_t)QOI_TILE_PX; /* uniform: only an image's last tile can be partial */
+			const bool last_tile = ti.px0 + ti.n_valid == ti.npx;
+			const bool track_cand = tid < 4;                        /* the restart point lies in the first 62 pixels */
 			uint32_t nrbits = 0;
 			{
 				uint32_t before = pprev;
 #pragma unroll
 				for (int j = 0; j < 16; j++) {
-					if (i0 + j < ti.n_valid && v[j] != before) {
+					if ((full || i0 + j < ti.n_valid) && v[j] != before) {
 						uint16_t *cell = (uint16_t *)(cells + qoi_slot(v[j]) * QOI_CELL_ROW) + tid;
 						*cell = (uint16_t)(*cell | (1u << j));
 						nrbits |= 1u << j;
@@ -639,6 +642,15 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				if (lane == 31) wlnr[warp] = incl;
 			}
 			bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE); /* matrix and wlnr[] complete */
+			/* second level: one bit per 64-pixel word of every row, so that a look-up never has to walk */
+#pragma unroll
+			for (int r = 0; r < 8; r++) {
+				const uint64_t *row = (const uint64_t *)(cells + (warp * 8u + r) * QOI_CELL_ROW);
+				const uint32_t b0 = __ballot_sync(QOI_FULL_MASK, row[lane] != 0ull);
+				const uint32_t b1 = __ballot_sync(QOI_FULL_MASK, row[lane + 32] != 0ull);
+				if (lane == 0) summary[warp * 8u + r] = (uint64_t)b0 | ((uint64_t)b1 << 32);
+			}
+			bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
 			bar_arrive(BAR_I_DONE, QOI_N_CS);
 			if (lnr_local < 0) {
 				for (int w = (int)warp - 1; w >= 0; w--) {
@@ -649,7 +661,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				}
 			}
 			/* a thread that starts inside a run which began before this tile needs the carry from the look-back */
-			const bool defer = (i0 < ti.n_valid) && !(nrbits & 1u) && lnr_local < 0;
+			const bool defer = (full || i0 < ti.n_valid) && !(nrbits & 1u) && lnr_local < 0;
 			uint32_t hitbits = 0;
 			int32_t cand = INT_MAX;
 			const uint32_t grp = tid >> 2, bitbase = (tid & 3u) * 16u;
@@ -696,20 +708,24 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				for (int j = 0; j < 16; j++) {
 					const uint32_t gi = ti.px0 + i0 + j;
 					uint32_t cd = 0;
-					if (i0 + j < ti.n_valid) {
+					if (full || i0 + j < ti.n_valid) {
 						if ((nrbits >> j) & 1u) {
 							r = -1;
-							if (cand == INT_MAX) cand = (int32_t)(i0 + j);
+							if (track_cand && cand == INT_MAX) cand = (int32_t)(i0 + j);
 							const uint32_t h = qoi_slot(v[j]);
 							bool hit;
 							if (pass == 0) {
-								/* nearest earlier non-run pixel with my slot: walk back along row h of the bit matrix */
+								/* nearest earlier non-run pixel with my slot: my own 64-pixel word first, else the nearest
+								   earlier non-empty word of row h (second-level bits) */
 								const uint64_t *row = (const uint64_t *)(cells + h * QOI_CELL_ROW);
 								int g = (int)grp;
 								uint64_t w = row[g] & ((1ull << (bitbase + j)) - 1ull);
-								while (w == 0ull && g > 0) {
-									g--;
-									w = row[g];
+								if (w == 0ull) {
+									const uint64_t sm = summary[h] & ((1ull << grp) - 1ull);
+									if (sm) {
+										g = hi_bit64(sm);
+										w = row[g];
+									}
 								}
 								if (w) {
 									hit = pxv[g * 64 + hi_bit64(w)] == v[j];
@@ -726,9 +742,9 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 						} else {
 							/* run pixel (qoi.h:415-421): a byte leaves at run length 62, at the image end, or when the run ends */
 							r = (r == 61) ? 0 : r + 1;
-							if (r == 0 && cand == INT_MAX) cand = (int32_t)(i0 + j);
+							if (track_cand && r == 0 && cand == INT_MAX) cand = (int32_t)(i0 + j);
 							const uint32_t nx = (j == 15) ? pnext : v[j < 15 ? j + 1 : 15];
-							if (r == 61 || gi == ti.npx - 1u || nx != v[j]) cd = 1u | ((0xC0u | (uint32_t)r) << 8);
+							if (r == 61 || (last_tile && gi == ti.npx - 1u) || nx != v[j]) cd = 1u | ((0xC0u | (uint32_t)r) << 8);
 						}
 					}
 					code[j] = cd;
@@ -736,7 +752,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 					before = v[j];
 				}
 			}
-			if (tid < 4 && cand != INT_MAX) atomicMin((int *)&misc[MISC_RS_CAND], cand);
+			if (track_cand && cand != INT_MAX) atomicMin((int *)&misc[MISC_RS_CAND], cand);
 			/* block scan of the per-thread byte counts */
 			uint32_t incl = ttotal;
 #pragma unroll
@@ -757,16 +773,27 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				uint32_t woff = incl - ttotal; /* exclusive inside the warp */
 				for (uint32_t w = 0; w < warp; w++) woff += wtot[w];
 				unsigned char *o = stage + padb + woff;
-				uint32_t before = pprev;
+				if (track_cand) { /* decoder restart point of this tile: the owner of pixel rs_cand records where its op starts */
+					const int32_t jr = rs_cand - (int32_t)i0;
+					if (jr >= 0 && jr < 16) {
+						uint32_t off = woff, before = pprev;
+#pragma unroll
+						for (int j = 0; j < 16; j++) {
+							if (j < jr) {
+								off += code[j] & 7u;
+								before = v[j];
+							}
+						}
+						P.st.rs_px[t] = (int32_t)(ti.px0 + (uint32_t)rs_cand);
+						P.st.rs_byte[t] = (int32_t)(tile_base + off);
+						P.st.rs_prev[t] = before;
+					}
+					if (tid == 0 && rs_cand == INT_MAX) P.st.rs_px[t] = -1;
+				}
 #pragma unroll
 				for (int j = 0; j < 16; j++) {
 					const uint32_t cd = code[j];
 					const uint32_t sz = cd & 7u;
-					if ((int32_t)(i0 + j) == rs_cand) { /* decoder restart point of this tile */
-						P.st.rs_px[t] = (int32_t)(ti.px0 + i0 + j);
-						P.st.rs_byte[t] = (int32_t)(tile_base + (uint32_t)(o - (stage + padb)));
-						P.st.rs_prev[t] = before;
-					}
 					if (sz) {
 						o[0] = (uint8_t)(cd >> 8);
 						if (sz >= 2) {
@@ -779,9 +806,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 						}
 						o += sz;
 					}
-					before = v[j];
 				}
-				if (tid == 0 && rs_cand == INT_MAX) P.st.rs_px[t] = -1;
 			}
 			__syncwarp();
 			bar_arrive(BAR_W_DONE, QOI_N_CS);

@@ -305,3 +305,32 @@ def test_header_mismatch_is_reported(gpu, cpu):
     torch.cuda.synchronize()
     assert d_status.cpu().tolist() == [0, 4]
     plan.close()
+
+
+def test_size_sweep_config4(gpu, cpu):
+    """BASELINE.json configs[4]: sizes 64x64 .. 16384x16384, channels 3 and 4.  Small sizes are compared byte for
+    byte with the CPU; the largest ones through decode(encode(x)) == x on the device plus one full byte comparison."""
+    qb, torch, ctx = gpu
+    chk = cpu.best()
+    for sz in (64, 128, 256, 512, 1024, 2048):
+        for ch in (3, 4):
+            run_batch(gpu, cpu, [(sz, sz, ch)] * 2, 4, dec_ch=4)
+    for sz, ch, full in ((8192, 3, False), (16384, 4, True), (16384, 3, False)):
+        plan = qb.Plan(ctx, [qb.Desc(sz, sz, ch, 0)], decoded_channels=ch)
+        host = cpu.image(sz, sz, ch, 4, 5)
+        d_pix = dev_u8(torch, host)
+        d_streams = torch.empty(plan.stream_bytes, dtype=torch.uint8, device="cuda")
+        d_lens = torch.zeros(1, dtype=torch.int32, device="cuda")
+        d_dec = torch.zeros(plan.decoded_bytes, dtype=torch.uint8, device="cuda")
+        plan.encode(d_pix.data_ptr(), d_streams.data_ptr(), d_lens.data_ptr())
+        plan.decode(d_streams.data_ptr(), d_lens.data_ptr(), d_dec.data_ptr(), use_index=True)
+        torch.cuda.synchronize()
+        assert torch.equal(d_dec, d_pix), (sz, ch)
+        if full:
+            want = chk.encode(host, sz, sz, ch)
+            n = int(d_lens[0])
+            assert n == len(want)
+            assert d_streams[:n].cpu().numpy().tobytes() == want
+        plan.close()
+        del d_pix, d_streams, d_dec
+        torch.cuda.empty_cache()

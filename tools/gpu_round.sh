@@ -10,7 +10,7 @@ nproc; free -g | head -2
 export PYTHONUNBUFFERED=1
 timeout 300 python __graft_entry__.py smoke; echo "SMOKE_RC=$?"
 if [ "$MODE" != "prof" ]; then
-  timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -40; echo "PYTEST_RC=${PIPESTATUS[0]}"
+  timeout 1500 python -m pytest tests -m gpu -x -v --timeout=240 --durations=8 2>&1 | tail -60; echo "PYTEST_RC=${PIPESTATUS[0]}"
 fi
 if [ "$MODE" = "quick" ]; then exit 0; fi
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "BENCH_RC=$?"
