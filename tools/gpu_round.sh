@@ -10,7 +10,13 @@ nproc; free -g | head -2
 export PYTHONUNBUFFERED=1
 timeout 300 python __graft_entry__.py smoke; echo "SMOKE_RC=$?"
 if [ "$MODE" != "prof" ]; then
-  timeout 1500 python -m pytest tests -m gpu -x -v --timeout=240 --durations=8 2>&1 | tail -60; echo "PYTEST_RC=${PIPESTATUS[0]}"
+  # one process per test with its own wall-clock limit: a hung kernel costs minutes, not the session, and is named
+  PYTEST_RC=0
+  for t in $(python -m pytest tests -m gpu --collect-only -q 2>/dev/null | grep "::"); do
+    timeout 300 python -m pytest "$t" -x -q --durations=1 2>&1 | tail -4 | grep -E "passed|failed|error|slowest|s call" ; rc=${PIPESTATUS[0]}
+    if [ $rc -ne 0 ]; then echo "TEST_FAILED rc=$rc $t"; PYTEST_RC=1; fi
+  done
+  echo "PYTEST_RC=$PYTEST_RC"
 fi
 if [ "$MODE" = "quick" ]; then exit 0; fi
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "BENCH_RC=$?"
