@@ -10,13 +10,9 @@ nproc; free -g | head -2
 export PYTHONUNBUFFERED=1
 timeout 300 python __graft_entry__.py smoke; echo "SMOKE_RC=$?"
 if [ "$MODE" != "prof" ]; then
-  # one process per test with its own wall-clock limit: a hung kernel costs minutes, not the session, and is named
-  PYTEST_RC=0
-  for t in $(python -m pytest tests -m gpu --collect-only -q 2>/dev/null | grep "::"); do
-    timeout 300 python -m pytest "$t" -x -q --durations=1 2>&1 | tail -4 | grep -E "passed|failed|error|slowest|s call" ; rc=${PIPESTATUS[0]}
-    if [ $rc -ne 0 ]; then echo "TEST_FAILED rc=$rc $t"; PYTEST_RC=1; fi
-  done
-  echo "PYTEST_RC=$PYTEST_RC"
+  # exactly what the driver runs (one process); per-test limit with stack dump so that a hang is named, not silent
+  timeout 1200 python -m pytest tests -x -q -m gpu --timeout=240 --timeout-method=thread --durations=5 > gpurun_out/pytest.log 2>&1; echo "PYTEST_RC=$?"
+  tail -25 gpurun_out/pytest.log
 fi
 if [ "$MODE" = "quick" ]; then exit 0; fi
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "BENCH_RC=$?"
@@ -31,9 +27,9 @@ cat gpurun_out/bench_ref.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --batch 8 --no-cpu --e2e-steps 1 > gpurun_out/ncu_bench.log 2>&1; echo "NCU_LIST_RC=$?"
 grep -c qoi gpurun_out/launches.csv
-# full capture: encoder at batch 8, decoder at the bench batch (its occupancy depends on the segment count)
+# full capture of both kernels at the bench batch (same command as the bench line, fewer steps)
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:qoi_encode -s 3 -c 2 -o gpurun_out/prof_enc -f \
-    python bench.py --steps 2 --warmup 3 --batch 8 --no-cpu --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1; echo "NCU_ENC_RC=$?"
+    python bench.py --steps 2 --warmup 3 --batch 32 --no-cpu --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1; echo "NCU_ENC_RC=$?"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:qoi_decode -s 3 -c 2 -o gpurun_out/prof_dec -f \
     python bench.py --steps 2 --warmup 3 --batch 32 --no-cpu --e2e-steps 1 >> gpurun_out/ncu_full.log 2>&1; echo "NCU_DEC_RC=$?"
 ls -la gpurun_out
