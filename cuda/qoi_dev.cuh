@@ -102,7 +102,7 @@ __device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t nthreads) {
 	__threadfence_block();
 	asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void spin_pause() { __nanosleep(200); }
+__device__ __forceinline__ void spin_pause() { __nanosleep(64); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ uint32_t lanemask_lt() {
 	uint32_t m;

@@ -399,10 +399,14 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 			fetch_ticket(P, F);
 			if (EXPAND) bar_sync(BAR_E_DONE, QOI_N_CS); /* single raw buffer: wait until phase E has drained it */
 			fetch_issue<CH, EXPAND>(P, smem, F, EXPAND ? 0 : (cur ^ 1), cur ^ 1);
-			__syncwarp();
-			bar_arrive(BAR_INFO_READY, QOI_N_ALL); /* consumed at the top of the next iteration */
 
 			bar_sync(BAR_W_DONE, QOI_N_CS); /* staging is complete */
+			/* Only now may INFO_READY be signalled again: a compute thread arrives at W_DONE, and the scout at the
+			   B_READY before it, only after passing this iteration's INFO_READY, so the barrier's previous phase is
+			   over.  (Signalling right after fetch_issue could overtake a warp that had not reached its
+			   bar.sync yet and complete that phase early.) */
+			__syncwarp();
+			bar_arrive(BAR_INFO_READY, QOI_N_ALL); /* consumed at the top of the next iteration */
 			{
 				const uint32_t excl = misc[MISC_TILE_BASE], total = misc[MISC_TILE_TOTAL];
 				uint8_t *gdst = gstream + excl;
@@ -666,46 +670,6 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 			int32_t cand = INT_MAX;
 			const uint32_t grp = tid >> 2, bitbase = (tid & 3u) * 16u;
 
-			/* ---- phase H: INDEX hits.  For every non-run pixel the nearest earlier non-run pixel with the same slot:
-			   its own 64-pixel word of row h first, else the nearest earlier non-empty word (second-level bits).
-			   Four pixels at a time, loads first, so that their shared-memory latencies overlap. ---- */
-			{
-				const uint64_t gmask = (1ull << grp) - 1ull;
-#pragma unroll
-				for (int q = 0; q < 4; q++) {
-					uint32_t hh[4];
-					uint64_t ww[4], ss[4];
-					int gg[4];
-					uint32_t pv[4];
-#pragma unroll
-					for (int k = 0; k < 4; k++) {
-						const int j = 4 * q + k;
-						hh[k] = qoi_slot(v[j]);
-						const uint64_t *row = (const uint64_t *)(cells + hh[k] * QOI_CELL_ROW);
-						ww[k] = row[grp] & ((1ull << (bitbase + j)) - 1ull);
-						ss[k] = summary[hh[k]] & gmask;
-						gg[k] = (int)grp;
-					}
-#pragma unroll
-					for (int k = 0; k < 4; k++) {
-						if (ww[k] == 0ull && ss[k] != 0ull) {
-							gg[k] = hi_bit64(ss[k]);
-							ww[k] = ((const uint64_t *)(cells + hh[k] * QOI_CELL_ROW))[gg[k]];
-						}
-					}
-#pragma unroll
-					for (int k = 0; k < 4; k++) pv[k] = ww[k] ? pxv[gg[k] * 64 + hi_bit64(ww[k])] : 0u;
-#pragma unroll
-					for (int k = 0; k < 4; k++) {
-						const int j = 4 * q + k;
-						if ((nrbits >> j) & 1u) {
-							if (ww[k]) hitbits |= (pv[k] == v[j] ? 1u : 0u) << j;
-							else Fpos[hh[k]] = (uint16_t)(i0 + j); /* first pixel of this slot in the tile: phase R decides */
-						}
-					}
-				}
-			}
-
 			/* ---- phase C: classify pass; pass 0 with what the tile knows, pass 1 after the look-back ---- */
 #pragma unroll 1
 			for (int pass = 0; pass < 2; pass++) {
@@ -752,8 +716,31 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 						if ((nrbits >> j) & 1u) {
 							r = -1;
 							if (track_cand && cand == INT_MAX) cand = (int32_t)(i0 + j);
-							const bool hit = (hitbits >> j) & 1u;
 							const uint32_t h = qoi_slot(v[j]);
+							bool hit;
+							if (pass == 0) {
+								/* nearest earlier non-run pixel with my slot: my own 64-pixel word first, else the nearest
+								   earlier non-empty word of row h (second-level bits) */
+								const uint64_t *row = (const uint64_t *)(cells + h * QOI_CELL_ROW);
+								int g = (int)grp;
+								uint64_t w = row[g] & ((1ull << (bitbase + j)) - 1ull);
+								if (w == 0ull) {
+									const uint64_t sm = summary[h] & ((1ull << grp) - 1ull);
+									if (sm) {
+										g = hi_bit64(sm);
+										w = row[g];
+									}
+								}
+								if (w) {
+									hit = pxv[g * 64 + hi_bit64(w)] == v[j];
+								} else {
+									Fpos[h] = (uint16_t)(i0 + j); /* first pixel of this slot in the tile: phase R decides */
+									hit = false;
+								}
+								hitbits |= (hit ? 1u : 0u) << j;
+							} else {
+								hit = (hitbits >> j) & 1u;
+							}
 							if (hit) cd = 1u | (h << 8); /* qoi.h:432-434 */
 							else cd = classify(v[j], before);
 						} else {

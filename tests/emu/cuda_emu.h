@@ -71,6 +71,8 @@ struct Fiber {
 	unsigned tid = 0;
 	Idx tidx{0, 0, 0};
 	const char *waiting = "";
+	unsigned nb_phase[16] = {0}; /* how often this thread has arrived at each named barrier */
+	unsigned nap = 0;            /* scheduler rounds this thread still sits out (models a warp that is not scheduled for a while) */
 };
 
 inline Fiber *cur = nullptr;
@@ -134,6 +136,14 @@ inline void named_barrier(unsigned id, unsigned nthreads, bool wait) {
 	Block *b = cur->blk;
 	if (id >= 16) { fprintf(stderr, "cuda_emu: barrier id %u out of range\n", id); abort(); }
 	unsigned g = b->nb_gen[id];
+	/* a thread may only arrive for phase k once phase k-1 has completed: otherwise its arrival is counted towards the
+	   unfinished phase and releases it early (a real hardware hazard, found the hard way) */
+	if (cur->nb_phase[id] != g) {
+		fprintf(stderr, "cuda_emu: BARRIER PHASE RACE on barrier %u: block %u thread %u arrives for phase %u while phase %u is still open\n",
+		        id, b->bidx.x, cur->tid, cur->nb_phase[id], g);
+		abort();
+	}
+	cur->nb_phase[id]++;
 	b->nb_count[id]++;
 	if (b->nb_count[id] > nthreads) { fprintf(stderr, "cuda_emu: barrier %u over-subscribed (%u > %u)\n", id, b->nb_count[id], nthreads); abort(); }
 	if (b->nb_count[id] == nthreads) {
@@ -194,15 +204,27 @@ inline LaunchStats launch(unsigned grid, unsigned block, size_t smem_bytes, cons
 			}
 		}
 		uint64_t before = progress;
+		bool napping = false;
 		for (size_t k = 0; k < order.size(); k++) {
 			Fiber &f = fibers[order[k]];
 			if (f.done) continue;
+			if (f.nap) { /* arbitrary skew between threads: protocols must not rely on "everybody runs soon" */
+				f.nap--;
+				napping = true;
+				continue;
+			}
 			cur = &f;
 			swapcontext(&sched_ctx, &f.ctx);
 			if (f.done) live--;
+			else if (seed) {
+				rs ^= rs << 13; rs ^= rs >> 17; rs ^= rs << 5;
+				if ((rs & 127u) == 0u) f.nap = 1 + (rs >> 8) % 48;
+			}
 		}
 		if (progress == before) {
-			if (++idle_rounds >= 4) {
+			if (napping) {
+				for (auto &f : fibers) f.nap = 0; /* nothing moved: wake everybody before calling it a deadlock */
+			} else if (++idle_rounds >= 4) {
 				fprintf(stderr, "cuda_emu: DEADLOCK -- no thread made progress. Waiting threads:\n");
 				int shown = 0;
 				for (auto &f : fibers)
