@@ -61,6 +61,32 @@ __device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_sme
 	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes)
 	             : "memory");
 }
+/* L2 eviction policy for data that is touched exactly once (pixels in, streams out): keeps the look-back records,
+   the restart index and the instruction stream resident in L2 while gigabytes stream through */
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_addr(dst_smem)),
+	             "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
+	             : "memory");
+}
+__device__ __forceinline__ void tma_store_1d_hint(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t pol) {
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes),
+	             "l"(pol)
+	             : "memory");
+}
+/* streaming (evict-first) 16-byte global accesses for the decoder */
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
+	uint4 v;
+	asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ void st_stream_u4(uint4 *p, uint4 v) {
+	asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 /* wait until all committed bulk stores of this thread have finished READING shared memory */
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -167,6 +193,11 @@ static inline void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t b
 	memcpy(dst_gmem, src_smem, bytes);
 	qemu::progress++;
 }
+static inline uint64_t l2_evict_first_policy() { return 0; }
+static inline void tma_load_1d_hint(void *d, const void *s_, uint32_t n, uint64_t *bar, uint64_t) { tma_load_1d(d, s_, n, bar); }
+static inline void tma_store_1d_hint(void *d, const void *s_, uint32_t n, uint64_t) { tma_store_1d(d, s_, n); }
+static inline uint4 ld_stream_u4(const uint4 *p) { return *p; }
+static inline void st_stream_u4(uint4 *p, uint4 v) { *p = v; }
 static inline void tma_store_commit() {}
 static inline void tma_store_wait_read() {}
 static inline void tma_store_wait_all() {}

@@ -181,7 +181,7 @@ __device__ __forceinline__ void fetch_issue(const QoiEncParams &P, unsigned char
 	const uint32_t tma_bytes = hi_off > lo_off ? hi_off - lo_off : 0u;
 	if (lane == 0) {
 		mbar_arrive_expect_tx(mbar, tma_bytes);
-		if (tma_bytes) tma_load_1d(data + lo_off, gsrc + (lo_off - sh), tma_bytes, mbar);
+		if (tma_bytes) tma_load_1d_hint(data + lo_off, gsrc + (lo_off - sh), tma_bytes, mbar, l2_evict_first_policy());
 	}
 	/* the <16-byte fragments on either side of the 16-byte aligned interior */
 	uint32_t a_lo = sh, a_hi = tma_bytes ? lo_off : sh + nbytes;
@@ -342,7 +342,8 @@ __device__ __forceinline__ void table_lookback(const QoiEncParams &P, uint32_t t
 }
 
 /* ---------------------------------------------------------------- the kernel */
-template <int CH, bool EXPAND>
+/* WALK: look-ups walk back along the slot row word by word instead of using the second-level bits (A/B switch) */
+template <int CH, bool EXPAND, bool WALK>
 __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const QoiEncParams P) {
 	using L = Layout<CH, EXPAND>;
 	QOI_DYNAMIC_SMEM(smem);
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 				const bool bulk = hi_off > lo_off;
 				if (lane == 0 && bulk) {
 					fence_proxy_async_smem();
-					tma_store_1d(gdst + (lo_off - padb), stage + lo_off, hi_off - lo_off);
+					tma_store_1d_hint(gdst + (lo_off - padb), stage + lo_off, hi_off - lo_off, l2_evict_first_policy());
 					tma_store_commit();
 				}
 				const uint32_t a_hi = bulk ? lo_off : end; /* [padb, a_hi) */
@@ -457,12 +458,24 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 			for (int q = 0; q < 2; q++) {
 				const uint32_t sl = lane + 32u * q;
 				const uint64_t *row = (const uint64_t *)(cells + sl * QOI_CELL_ROW);
-				const uint64_t sm = summary[sl];
-				own_ok[q] = sm != 0ull;
+				own_ok[q] = false;
 				own_val[q] = 0;
-				if (own_ok[q]) {
-					const int g = hi_bit64(sm);
-					own_val[q] = pxv[g * 64 + hi_bit64(row[g])];
+				if (WALK) {
+					for (int g = 63; g >= 0; g--) {
+						const uint64_t w = row[g];
+						if (w) {
+							own_val[q] = pxv[g * 64 + hi_bit64(w)];
+							own_ok[q] = true;
+							break;
+						}
+					}
+				} else {
+					const uint64_t sm = summary[sl];
+					if (sm) {
+						const int g = hi_bit64(sm);
+						own_val[q] = pxv[g * 64 + hi_bit64(row[g])];
+						own_ok[q] = true;
+					}
 				}
 			}
 			int32_t own_lnr = QOI_LNR_NONE;
@@ -648,13 +661,13 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 			bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE); /* matrix and wlnr[] complete */
 			/* second level: one bit per 64-pixel word of every row, so that a look-up never has to walk */
 #pragma unroll
-			for (int r = 0; r < 8; r++) {
+			for (int r = 0; r < (WALK ? 0 : 8); r++) {
 				const uint64_t *row = (const uint64_t *)(cells + (warp * 8u + r) * QOI_CELL_ROW);
 				const uint32_t b0 = __ballot_sync(QOI_FULL_MASK, row[lane] != 0ull);
 				const uint32_t b1 = __ballot_sync(QOI_FULL_MASK, row[lane + 32] != 0ull);
 				if (lane == 0) summary[warp * 8u + r] = (uint64_t)b0 | ((uint64_t)b1 << 32);
 			}
-			bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
+			if (!WALK) bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
 			bar_arrive(BAR_I_DONE, QOI_N_CS);
 			if (lnr_local < 0) {
 				for (int w = (int)warp - 1; w >= 0; w--) {
@@ -724,7 +737,12 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 								const uint64_t *row = (const uint64_t *)(cells + h * QOI_CELL_ROW);
 								int g = (int)grp;
 								uint64_t w = row[g] & ((1ull << (bitbase + j)) - 1ull);
-								if (w == 0ull) {
+								if (WALK) {
+									while (w == 0ull && g > 0) {
+										g--;
+										w = row[g];
+									}
+								} else if (w == 0ull) {
 									const uint64_t sm = summary[h] & ((1ull << grp) - 1ull);
 									if (sm) {
 										g = hi_bit64(sm);

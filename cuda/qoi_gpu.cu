@@ -35,6 +35,7 @@ struct qoi_gpu_ctx {
 	cudaStream_t s_h2d = nullptr, s_d2h = nullptr; /* one stream per copy direction: PCIe is full duplex */
 	char err[256] = {0};
 	int enc_blocks_per_sm[3] = {0, 0, 0}; /* <4,false>, <4,true>, <3,true> */
+	bool walk = false;                    /* QOI_GPU_WALK=1: word-walking look-up variant (A/B switch for profiling) */
 };
 
 struct qoi_gpu_plan {
@@ -72,9 +73,10 @@ struct qoi_gpu_plan {
 template <int CH, bool EXPAND>
 static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
 	using L = qoienc::Layout<CH, EXPAND>;
-	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
 	int nb = 0;
-	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qoienc::qoi_encode_kernel<CH, EXPAND>, QOI_ENC_THREADS, L::TOTAL));
+	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qoienc::qoi_encode_kernel<CH, EXPAND, false>, QOI_ENC_THREADS, L::TOTAL));
 	*out = nb > 0 ? nb : 1;
 	return QOI_GPU_OK;
 }
@@ -111,6 +113,10 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 	if (e != cudaSuccess) {
 		delete c;
 		return QOI_GPU_E_CUDA;
+	}
+	{
+		const char *w = getenv("QOI_GPU_WALK");
+		c->walk = w && atoi(w) != 0;
 	}
 	int rc = enc_occupancy<4, false>(c, &c->enc_blocks_per_sm[0]);
 	if (!rc) rc = enc_occupancy<4, true>(c, &c->enc_blocks_per_sm[1]);
@@ -221,9 +227,15 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	const int variant = p->geom.channels == 3 ? 2 : (zero_copy ? 0 : 1);
 	uint32_t grid = (uint32_t)(ctx->sm_count * ctx->enc_blocks_per_sm[variant]);
 	if (grid > P.n_tiles) grid = P.n_tiles;
-	if (variant == 0) qoienc::qoi_encode_kernel<4, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-	else if (variant == 1) qoienc::qoi_encode_kernel<4, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-	else qoienc::qoi_encode_kernel<3, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
+	if (ctx->walk) {
+		if (variant == 0) qoienc::qoi_encode_kernel<4, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
+		else if (variant == 1) qoienc::qoi_encode_kernel<4, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
+		else qoienc::qoi_encode_kernel<3, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
+	} else {
+		if (variant == 0) qoienc::qoi_encode_kernel<4, false, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
+		else if (variant == 1) qoienc::qoi_encode_kernel<4, true, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
+		else qoienc::qoi_encode_kernel<3, true, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
+	}
 	g_launches++;
 	CK(ctx, cudaGetLastError());
 	p->index_owner = 1;
