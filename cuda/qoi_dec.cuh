@@ -60,8 +60,8 @@ struct Reader {
 __device__ __forceinline__ void load_chunk(Reader &rd) {
 	const uintptr_t a = (uintptr_t)rd.gp;
 	if (a >= rd.lo && a + 32 <= rd.hi) {
-		rd.pa = ld_stream_u4(rd.gp);
-		rd.pb = ld_stream_u4(rd.gp + 1);
+		rd.pa = __ldg(rd.gp);
+		rd.pb = __ldg(rd.gp + 1);
 	} else {
 		uint32_t w[8];
 #pragma unroll
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 		}
 		while (i + 4 <= px_end) {
 			const uint32_t a = step(), b = step(), c = step(), d = step();
-			st_stream_u4((uint4 *)(o32 + i), make_uint4(a, b, c, d));
+			*(uint4 *)(o32 + i) = make_uint4(a, b, c, d);
 			i += 4;
 		}
 		while (i < px_end) {

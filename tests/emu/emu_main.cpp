@@ -43,7 +43,7 @@ static std::vector<unsigned char> read_file(const char *path) {
 template <int CH, bool EXPAND>
 static void run_encode(const QoiEncParams &P, unsigned grid, unsigned seed) {
 	using L = qoienc::Layout<CH, EXPAND>;
-	qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { if (getenv("QOI_GPU_WALK")) qoienc::qoi_encode_kernel<CH, EXPAND, true>(P); else qoienc::qoi_encode_kernel<CH, EXPAND, false>(P); }, seed);
+	qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { if (getenv("QOI_GPU_LOOKUP") && !strcmp(getenv("QOI_GPU_LOOKUP"), "summary")) qoienc::qoi_encode_kernel<CH, EXPAND, false>(P); else qoienc::qoi_encode_kernel<CH, EXPAND, true>(P); }, seed);
 }
 
 static void run_decode(const QoiDecParams &P, unsigned seed) {

@@ -27,9 +27,11 @@ def run_enc(emu, img, w, h, ch, n, grid, seed, mis):
     with tempfile.NamedTemporaryFile(suffix=".raw") as f:
         f.write(np.ascontiguousarray(img, dtype=np.uint8).tobytes())
         f.flush()
-        r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
-                           capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and r.stdout.startswith("PASS"), r.stdout + r.stderr[-2000:]
+        for lookup in ("walk", "summary"):  # both look-up variants of the encoder (QOI_GPU_LOOKUP)
+            env = dict(os.environ, QOI_GPU_LOOKUP=lookup)
+            r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
+                               capture_output=True, text=True, timeout=300, env=env)
+            assert r.returncode == 0 and r.stdout.startswith("PASS"), lookup + ": " + r.stdout + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("dist", range(8))

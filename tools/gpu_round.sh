@@ -17,7 +17,7 @@ fi
 if [ "$MODE" = "quick" ]; then exit 0; fi
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "BENCH_RC=$?"
 cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-for d in 0 7 2 6; do
+for d in 0 7 2 6; do  # worst case, best case, run-heavy, index-heavy
   timeout 600 python bench.py --steps 5 --warmup 3 --dist $d --no-cpu --e2e-steps 1 > gpurun_out/bench_dist$d.json 2>> gpurun_out/bench.err; echo "BENCH_DIST${d}_RC=$?"
   cat gpurun_out/bench_dist$d.json
 done
