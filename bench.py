@@ -312,7 +312,7 @@ def main():
     h2d = plan.pixel_bytes + enc_bytes + 4 * n
     d2h = enc_bytes + plan.decoded_bytes + 4 * n
 
-    # ---- foreign-stream decode (no restart index): reported beside the headline, not part of it
+    # ---- foreign-stream decode (no restart index, the path qoi_decode of the C API takes): reported beside the headline, not part of it
     fe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     plan.decode(d_streams.data_ptr(), d_lens.data_ptr(), d_dec.data_ptr(), False, None, stream)
     fe[0].record()
@@ -381,7 +381,7 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "extra": {"decode_foreign_stream_gpx_per_s": px_rank / (foreign_ms * 1e-3) / 1e9,
-                      "decode_foreign_note": "same streams decoded WITHOUT the restart index: one lane per image (qoi.h's loop is sequential per stream)",
+                      "decode_foreign_note": "same streams decoded WITHOUT the restart index (any-stream path: parse scan + speculative segments + exact fix-up, cuda/qoi_fdec.cuh)",
                       "encoded_bytes_all_ranks": enc_bytes_all},
         }
         print(json.dumps(line), flush=True)

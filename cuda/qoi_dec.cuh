@@ -6,8 +6,10 @@
  * unit of parallelism is a *segment*: a position in the stream at which the
  * complete decoder state is known.
  *
- *   foreign stream (use_index = 0): one segment = the whole image, state = the
- *       reference's initial state (qoi.h:533-537);
+ *   foreign stream: no state is known inside the stream; those go through the
+ *       speculative decoder of qoi_fdec.cuh.  (use_index = 0 in THIS kernel means one
+ *       segment = the whole image from the reference's initial state, qoi.h:533-537;
+ *       it is kept as the simplest exact form and is not launched by the C ABI.)
  *   stream written by qoi_encode_kernel (use_index = 1): one segment per
  *       encoder tile.  The chained scan already materialised the state at every
  *       tile boundary: index[] after tile t-1 is inc_ent[t-1], and rs_px /

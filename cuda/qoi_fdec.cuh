@@ -1,0 +1,454 @@
+/*
+ * qoi_fdec.cuh -- parallel decode of ARBITRARY ("foreign") QOI streams on sm_100a.
+ *
+ * The reference decoder (qoi.h:540-587) chains four things through the stream: the read cursor p, the
+ * current colour px, the run counter and index[64].  For a stream we did not write there is no restart
+ * index, so the state at any cut has to be *found*:
+ *
+ *   1. parse (exact, parallel).  The stream is cut into segments of QOI_FSEG_BYTES bytes.  An op's
+ *      length depends on its first byte only (0xFE:4, 0xFF:5, 10xxxxxx:2, else 1; qoi.h:547-575), so for
+ *      each of the 5 possible distances from the segment start to its first op the segment maps
+ *      "entry skip -> (exit skip, pixels produced)".  fparse_kernel tabulates that map; fchain_kernel
+ *      composes the maps along each stream and leaves every segment's true first op and first pixel.
+ *   2. speculate (parallel).  fdecode_kernel decodes every segment from a GUESSED state (px, index[])
+ *      and records what the result actually depended on: which index[] slots were read before the
+ *      segment itself wrote them, and whether the incoming colour / alpha was used before being replaced.
+ *   3. verify (sequential per stream, cheap: no pixels, 64 lanes' worth of state).  fverify_kernel walks
+ *      the segments in order with the EXACT state.  A segment whose guesses agree with the exact state on
+ *      everything it depended on is final, and its writes advance the exact state.  At the first
+ *      disagreement that segment gets the exact state as its new guess; behind it the chain continues in
+ *      "guess mode" so that later segments get better guesses (a purely relative segment's output colour
+ *      is re-based: out = new_in + (old_out - old_in)).  Only segments whose guess changed on something
+ *      they depend on are decoded again.
+ *   4. fix up (exact).  After QOI_FDEC_ROUNDS speculative launches ffix_kernel makes the same in-order walk
+ *      once more, but decodes the segments whose guess still does not hold on the spot (one lane, the
+ *      reference loop), so the chain state stays exact to the end of the stream.  The result is therefore
+ *      exact for every input; the sequential work is proportional to what speculation could not settle
+ *      (streams whose colours are almost all INDEX / relative ops degrade to the sequential decoder).
+ *
+ * Every kernel cites the reference rule it restates; nothing here reads outside [stream, stream+size).
+ */
+#pragma once
+#include "qoi_common.h"
+#include "qoi_dev.cuh"
+
+namespace qoifdec {
+using namespace qoidev;
+
+#define QOI_FSEG_BYTES 4096
+#define QOI_FDEC_ROUNDS 3 /* speculative decode launches (with a verify pass between them) before the exact fix-up */
+#define QOI_FDEC_THREADS 128
+
+struct QoiFState {
+	/* geometry (host written) */
+	const uint32_t *seg_base; /* [n_images + 1] first global segment of each image (capacity, not live count) */
+	/* parse */
+	uint32_t *px_cnt;         /* [segs][5] pixels produced when entered with skip s */
+	uint8_t *exit_skip;       /* [segs][8] (5 used) */
+	/* chain result */
+	uint8_t *entry;           /* [segs] distance from the segment start to its first op */
+	uint32_t *px_start;       /* [segs] first pixel of the segment */
+	uint32_t *n_live;         /* [n_images] segments that hold at least one op of a pixel < npx */
+	/* speculation */
+	uint32_t *in_px;          /* [segs] guessed colour before the segment */
+	uint32_t *in_tab;         /* [segs][64] guessed index[] */
+	uint32_t *out_px;         /* [segs] */
+	uint32_t *out_tab;        /* [segs][64] values written by the segment (last writer per slot) */
+	uint64_t *out_written;    /* [segs] */
+	uint64_t *rbw;            /* [segs] slots read before the segment wrote them */
+	uint64_t *out_clean;      /* [segs] written slots whose value does not depend on the guess (came from ops inside the segment) */
+	uint8_t *dep;             /* [segs] bit0: incoming r,g,b used; bit1: incoming alpha used; bit2: no absolute colour op inside;
+	                             bit3: the outgoing r,g,b do not depend on the guess */
+	uint8_t *redo;            /* [segs] decode (again) in the next fdecode launch */
+	/* verification */
+	uint32_t *verified;       /* [n_images] segments [0, verified) are final */
+	uint32_t *ex_px;          /* [n_images] exact colour after the verified prefix */
+	uint32_t *ex_tab;         /* [n_images][64] exact index[] after the verified prefix */
+};
+
+struct QoiFParams {
+	const uint8_t *streams;
+	const int32_t *lens;
+	uint8_t *out;
+	int32_t *status;
+	const QoiImgMeta *imgs;
+	uint32_t n_images;
+	uint32_t n_segs; /* capacity over all images */
+	int32_t out_channels;
+	QoiFState f;
+};
+
+__device__ __forceinline__ uint32_t add_bytes(uint32_t a, uint32_t b) {
+	return ((a & 0x7F7F7F7Fu) + (b & 0x7F7F7F7Fu)) ^ ((a ^ b) & 0x80808080u);
+}
+__device__ __forceinline__ uint32_t sub_bytes(uint32_t a, uint32_t b) {
+	return ((a | 0x80808080u) - (b & 0x7F7F7F7Fu)) ^ ((a ^ ~b) & 0x80808080u);
+}
+__device__ __forceinline__ uint32_t be32(const uint8_t *p) {
+	return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+}
+
+/* which image owns global segment g (binary search in seg_base) */
+__device__ __forceinline__ uint32_t seg_image(const QoiFParams &P, uint32_t g) {
+	uint32_t lo = 0, hi = P.n_images - 1;
+	while (lo < hi) {
+		const uint32_t mid = (lo + hi + 1) >> 1;
+		if (P.f.seg_base[mid] <= g) lo = mid;
+		else hi = mid - 1;
+	}
+	return lo;
+}
+
+/* header against the plan, as qoi_decode_kernel does (qoi.h:513-521 is enforced by the host entry points) */
+__device__ __forceinline__ bool stream_ok(const QoiImgMeta &m, const uint8_t *s, int32_t size) {
+	if (size < QOI_HEADER_BYTES + QOI_END_BYTES) return false;
+	return s[0] == 'q' && s[1] == 'o' && s[2] == 'i' && s[3] == 'f' && be32(s + 4) == m.width && be32(s + 8) == m.height &&
+	       s[12] == m.channels && s[13] == m.colorspace;
+}
+
+/* ------------------------------------------------------------------ 1a. parse: one thread per segment */
+__global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFParams P) {
+	const uint32_t g = blockIdx.x * QOI_FDEC_THREADS + threadIdx.x;
+	if (g >= P.n_segs) return;
+	const uint32_t img = seg_image(P, g);
+	const QoiImgMeta m = P.imgs[img];
+	const uint8_t *s = P.streams + m.stream_off;
+	const int32_t size = P.lens[img];
+	if (!stream_ok(m, s, size)) return;
+	const int32_t stop = size - QOI_END_BYTES; /* qoi.h:539 */
+	const int32_t begin = QOI_HEADER_BYTES + (int32_t)(g - P.f.seg_base[img]) * QOI_FSEG_BYTES;
+	if (begin >= stop) return; /* beyond the stream */
+	const int32_t end = begin + QOI_FSEG_BYTES < stop ? begin + QOI_FSEG_BYTES : stop;
+#pragma unroll 1
+	for (int sk = 0; sk < 5; sk++) {
+		int32_t p = begin + sk;
+		uint32_t cnt = 0;
+		while (p < end) {
+			const uint32_t tag = s[p];
+			const uint32_t top = tag >> 6;
+			/* op length from its first byte (qoi.h:547,552,566; everything else is one byte) */
+			p += (tag == 0xFEu) ? 4 : (tag == 0xFFu) ? 5 : (top == 2u ? 2 : 1);
+			cnt += (top == 3u && tag < 0xFEu) ? (tag & 0x3Fu) + 1u : 1u; /* a RUN op yields run+1 pixels (qoi.h:573-575,541-543) */
+		}
+		P.f.px_cnt[(size_t)g * 5 + sk] = cnt;
+		P.f.exit_skip[(size_t)g * 8 + sk] = (uint8_t)(p >= end ? p - end : 0);
+	}
+}
+
+/* ------------------------------------------------------------------ 1b. chain: one thread per stream */
+__global__ void __launch_bounds__(32) fchain_kernel(const QoiFParams P) {
+	const uint32_t img = blockIdx.x * 32 + threadIdx.x;
+	if (img >= P.n_images) return;
+	const QoiImgMeta m = P.imgs[img];
+	const uint8_t *s = P.streams + m.stream_off;
+	const int32_t size = P.lens[img];
+	const bool ok = stream_ok(m, s, size);
+	if (P.status) P.status[img] = ok ? 0 : 4; /* QOI_GPU_E_STREAM */
+	uint32_t live = 0;
+	if (ok) {
+		const int32_t stop = size - QOI_END_BYTES;
+		const uint32_t base = P.f.seg_base[img];
+		const uint32_t nseg = stop > QOI_HEADER_BYTES ? (uint32_t)((stop - QOI_HEADER_BYTES + QOI_FSEG_BYTES - 1) / QOI_FSEG_BYTES) : 0u;
+		uint32_t skip = 0, px = 0;
+		for (uint32_t j = 0; j < nseg && px < m.npx; j++) {
+			const uint32_t g = base + j;
+			P.f.entry[g] = (uint8_t)skip;
+			P.f.px_start[g] = px;
+			P.f.redo[g] = 1;
+			P.f.in_px[g] = 0xFF000000u; /* round-0 guess: the reference's initial state (qoi.h:533-537) */
+			px += P.f.px_cnt[(size_t)g * 5 + skip];
+			skip = P.f.exit_skip[(size_t)g * 8 + skip];
+			live = j + 1;
+		}
+	}
+	P.f.n_live[img] = live;
+	P.f.verified[img] = 0;
+	P.f.ex_px[img] = 0xFF000000u;
+	for (int k = 0; k < 64; k++) P.f.ex_tab[(size_t)img * 64 + k] = 0u;
+}
+
+/* round-0 guess of index[]: zeros (qoi.h:533) */
+__global__ void __launch_bounds__(QOI_FDEC_THREADS) fzero_kernel(const QoiFParams P) {
+	const uint32_t g = blockIdx.x * QOI_FDEC_THREADS + threadIdx.x;
+	if (g >= P.n_segs) return;
+	const uint32_t img = seg_image(P, g);
+	if (g - P.f.seg_base[img] >= P.f.n_live[img]) return;
+	uint4 *t = (uint4 *)(P.f.in_tab + (size_t)g * 64);
+#pragma unroll
+	for (int k = 0; k < 16; k++) t[k] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+/* ------------------------------------------------------------------ 2. speculative decode: one lane per segment */
+template <int OUT_CH>
+__global__ void __launch_bounds__(QOI_FDEC_THREADS) fdecode_kernel(const QoiFParams P) {
+	QOI_DYNAMIC_SMEM(smem);
+	uint32_t *tab = (uint32_t *)smem + threadIdx.x; /* tab[slot * QOI_FDEC_THREADS] */
+	const uint32_t g = blockIdx.x * QOI_FDEC_THREADS + threadIdx.x;
+	if (g >= P.n_segs) return;
+	const uint32_t img = seg_image(P, g);
+	const uint32_t j = g - P.f.seg_base[img];
+	const uint32_t live = P.f.n_live[img];
+	if (j >= live || j < P.f.verified[img] || !P.f.redo[g]) return;
+	const QoiImgMeta m = P.imgs[img];
+	const uint8_t *s = P.streams + m.stream_off;
+	const int32_t stop = P.lens[img] - QOI_END_BYTES;
+	const int32_t begin = QOI_HEADER_BYTES + (int32_t)j * QOI_FSEG_BYTES;
+	const int32_t end = begin + QOI_FSEG_BYTES < stop ? begin + QOI_FSEG_BYTES : stop;
+	const uint32_t px_begin = P.f.px_start[g];
+	/* the last live segment also owns the pixels a truncated stream leaves over (they repeat the last colour, qoi.h:544) */
+	const uint32_t px_end = (j + 1 < live) ? P.f.px_start[g + 1] : m.npx;
+
+	uint32_t px = P.f.in_px[g];
+	{
+		const uint32_t *src = P.f.in_tab + (size_t)g * 64;
+#pragma unroll 8
+		for (int k = 0; k < 64; k++) tab[k * QOI_FDEC_THREADS] = src[k];
+	}
+	uint64_t written = 0, rbw = 0, cleanw = 0;
+	bool rgb_known = false, a_known = false, dep_rgb = false, dep_a = false, rel_only = true;
+	bool clean = false; /* r,g,b of px derive only from ops inside this segment (heuristic input for the re-guessing chain) */
+	int32_t p = begin + (int32_t)P.f.entry[g];
+	uint32_t run = 0;
+	uint8_t *o = P.out + m.dec_off + (size_t)px_begin * OUT_CH;
+	for (uint32_t i = px_begin; i < px_end; i++) {
+		if (run > 0) {
+			run--;
+		} else if (p < end) {
+			const uint32_t tag = s[p++];
+			if (tag == 0xFEu) { /* qoi.h:547-551: r,g,b replaced, alpha kept */
+				px = (px & 0xFF000000u) | (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16);
+				p += 3;
+				if (!a_known) dep_a = true;
+				rgb_known = true;
+				rel_only = false;
+				clean = true;
+			} else if (tag == 0xFFu) { /* qoi.h:552-557 */
+				px = (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
+				p += 4;
+				rgb_known = a_known = true;
+				rel_only = false;
+				clean = true;
+			} else if ((tag & 0xC0u) == 0x00u) { /* qoi.h:558-560 */
+				if (!((written >> tag) & 1ull)) rbw |= 1ull << tag;
+				clean = (cleanw >> tag) & 1ull; /* a slot not written here has no clean bit */
+				px = tab[tag * QOI_FDEC_THREADS];
+				rgb_known = a_known = true;
+				rel_only = false;
+			} else if ((tag & 0xC0u) == 0x40u) { /* qoi.h:561-565 */
+				const uint32_t sel = ((tag >> 4) & 3u) | (((tag >> 2) & 3u) << 4) | ((tag & 3u) << 8) | 0x4000u;
+				px = add_bytes(px, __byte_perm(0x0100FFFEu, 0u, sel));
+				if (!rgb_known) dep_rgb = true;
+				if (!a_known) dep_a = true;
+			} else if ((tag & 0xC0u) == 0x80u) { /* qoi.h:566-572 */
+				const uint32_t b2 = s[p++];
+				const uint32_t vg = (tag & 0x3Fu) + 224u;
+				const uint32_t rb = vg + 248u;
+				px = add_bytes(px, ((rb + ((b2 >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((rb + (b2 & 0xFu)) & 0xFFu) << 16));
+				if (!rgb_known) dep_rgb = true;
+				if (!a_known) dep_a = true;
+			} else { /* qoi.h:573-575 */
+				run = tag & 0x3Fu;
+				if (!rgb_known) dep_rgb = true;
+				if (!a_known) dep_a = true;
+			}
+			const uint32_t h = qoi_slot(px);
+			tab[h * QOI_FDEC_THREADS] = px; /* qoi.h:577 */
+			written |= 1ull << h;
+			cleanw = clean ? (cleanw | (1ull << h)) : (cleanw & ~(1ull << h));
+		} else { /* stream exhausted: the pixel repeats the current colour */
+			if (!rgb_known) dep_rgb = true;
+			if (!a_known) dep_a = true;
+		}
+		if (OUT_CH == 4) {
+			*(uint32_t *)o = px;
+		} else {
+			o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
+		}
+		o += OUT_CH;
+	}
+	P.f.out_px[g] = px;
+	P.f.out_written[g] = written;
+	P.f.rbw[g] = rbw;
+	P.f.out_clean[g] = cleanw;
+	P.f.dep[g] = (uint8_t)((dep_rgb ? 1 : 0) | (dep_a ? 2 : 0) | (rel_only ? 4 : 0) | (clean ? 8 : 0));
+	P.f.redo[g] = 0;
+	{
+		uint32_t *dst = P.f.out_tab + (size_t)g * 64;
+#pragma unroll 8
+		for (int k = 0; k < 64; k++) dst[k] = tab[k * QOI_FDEC_THREADS];
+	}
+}
+
+/* ------------------------------------------------------------------ 3. verify + re-guess: one warp per stream */
+__global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
+	const uint32_t img = blockIdx.x;
+	const uint32_t lane = threadIdx.x;
+	if (img >= P.n_images) return;
+	const uint32_t live = P.f.n_live[img];
+	uint32_t ver = P.f.verified[img];
+	if (ver >= live) return;
+	const uint32_t base = P.f.seg_base[img];
+	/* chain state: lane holds slots lane and lane+32 */
+	uint32_t t0 = P.f.ex_tab[(size_t)img * 64 + lane], t1 = P.f.ex_tab[(size_t)img * 64 + lane + 32];
+	uint32_t px = P.f.ex_px[img];
+	bool exact = true;
+	for (uint32_t j = ver; j < live; j++) {
+		const uint32_t g = base + j;
+		const uint64_t rbw = P.f.rbw[g], wr = P.f.out_written[g];
+		const uint32_t dep = P.f.dep[g];
+		const uint32_t g_px = P.f.in_px[g];
+		const uint32_t g0 = P.f.in_tab[(size_t)g * 64 + lane], g1 = P.f.in_tab[(size_t)g * 64 + lane + 32];
+		const uint32_t o0 = P.f.out_tab[(size_t)g * 64 + lane], o1 = P.f.out_tab[(size_t)g * 64 + lane + 32];
+		const uint32_t o_px = P.f.out_px[g];
+		/* does the guess this segment was decoded with agree with the chain state on everything it used? */
+		const uint32_t pmask = ((dep & 1u) ? 0x00FFFFFFu : 0u) | ((dep & 2u) ? 0xFF000000u : 0u);
+		bool bad = ((rbw >> lane) & 1ull) && g0 != t0;
+		bad = bad || (((rbw >> (lane + 32)) & 1ull) && g1 != t1);
+		bad = bad || (lane == 0 && ((g_px ^ px) & pmask) != 0u);
+		const bool differs = __ballot_sync(QOI_FULL_MASK, bad) != 0u;
+		uint64_t apply = wr;
+		if (differs) {
+			/* new guess for this segment = the chain state (the exact state while `exact` still holds) */
+			P.f.in_tab[(size_t)g * 64 + lane] = t0;
+			P.f.in_tab[(size_t)g * 64 + lane + 32] = t1;
+			if (lane == 0) {
+				P.f.in_px[g] = px;
+				P.f.redo[g] = 1;
+			}
+			if (exact) {
+				exact = false;
+				ver = j; /* everything before j is final */
+			}
+			/* Keep chaining for the segments behind it.  Its stale writes are only trusted where the value did not
+			   depend on the guess; the other slots keep the older value (right when the table is stable, e.g. a
+			   palette).  A purely relative segment's colour is re-based, a guess-independent one taken as is. */
+			apply = wr & P.f.out_clean[g];
+			if (dep & 4u) px = add_bytes(px, sub_bytes(o_px, g_px));
+			else if (dep & 8u) px = (o_px & 0x00FFFFFFu) | (((dep & 2u) ? px : o_px) & 0xFF000000u);
+			/* else: unknown; the incoming colour is as good a guess as any */
+		} else {
+			if (exact) ver = j + 1;
+			/* the colour leaving the segment: channels that did not depend on the incoming colour come from the decode */
+			if (dep & 4u) px = add_bytes(px, sub_bytes(o_px, g_px));
+			else px = o_px;
+		}
+		if ((apply >> lane) & 1ull) t0 = o0;
+		if ((apply >> (lane + 32)) & 1ull) t1 = o1;
+		if (exact) { /* remember the exact state after the verified prefix (the tail kernel and the next round start here) */
+			P.f.ex_tab[(size_t)img * 64 + lane] = t0;
+			P.f.ex_tab[(size_t)img * 64 + lane + 32] = t1;
+			if (lane == 0) P.f.ex_px[img] = px;
+		}
+	}
+	if (lane == 0) P.f.verified[img] = ver;
+}
+
+/* ------------------------------------------------------------------ 4. exact fix-up: one warp per stream */
+/* Walks the not yet verified segments in order with the exact state, like fverify_kernel, but a segment whose guess
+   does not hold is decoded right here (lane 0, the reference loop qoi.h:540-587) so the state stays exact.  Valid
+   segments cost a 64-entry compare and merge; the sequential work is proportional to the segments that speculation
+   could not settle.  After this kernel every pixel is final. */
+template <int OUT_CH>
+__global__ void __launch_bounds__(32) ffix_kernel(const QoiFParams P) {
+	QOI_DYNAMIC_SMEM(smem);
+	uint32_t *tab = (uint32_t *)smem; /* exact index[] */
+	const uint32_t img = blockIdx.x;
+	const uint32_t lane = threadIdx.x;
+	if (img >= P.n_images) return;
+	const uint32_t live = P.f.n_live[img];
+	const uint32_t ver = P.f.verified[img];
+	if (ver >= live) return; /* everything verified (also: rejected or empty stream) */
+	const QoiImgMeta m = P.imgs[img];
+	const uint8_t *s = P.streams + m.stream_off;
+	const int32_t stop = P.lens[img] - QOI_END_BYTES;
+	const uint32_t base = P.f.seg_base[img];
+	tab[lane] = P.f.ex_tab[(size_t)img * 64 + lane];
+	tab[lane + 32] = P.f.ex_tab[(size_t)img * 64 + lane + 32];
+	uint32_t px = P.f.ex_px[img];
+	__syncwarp();
+	for (uint32_t j = ver; j < live; j++) {
+		const uint32_t g = base + j;
+		const uint64_t rbw = P.f.rbw[g], wr = P.f.out_written[g];
+		const uint32_t dep = P.f.dep[g];
+		const uint32_t g_px = P.f.in_px[g];
+		const uint32_t pmask = ((dep & 1u) ? 0x00FFFFFFu : 0u) | ((dep & 2u) ? 0xFF000000u : 0u);
+		bool bad = ((rbw >> lane) & 1ull) && P.f.in_tab[(size_t)g * 64 + lane] != tab[lane];
+		bad = bad || (((rbw >> (lane + 32)) & 1ull) && P.f.in_tab[(size_t)g * 64 + lane + 32] != tab[lane + 32]);
+		bad = bad || (lane == 0 && ((g_px ^ px) & pmask) != 0u);
+		bad = bad || P.f.redo[g] != 0; /* a new guess was issued but never decoded */
+		if (__ballot_sync(QOI_FULL_MASK, bad) == 0u) {
+			const uint32_t o_px = P.f.out_px[g];
+			px = (dep & 4u) ? add_bytes(px, sub_bytes(o_px, g_px)) : o_px;
+			if ((wr >> lane) & 1ull) tab[lane] = P.f.out_tab[(size_t)g * 64 + lane];
+			if ((wr >> (lane + 32)) & 1ull) tab[lane + 32] = P.f.out_tab[(size_t)g * 64 + lane + 32];
+		} else if (lane == 0) {
+			const int32_t begin = QOI_HEADER_BYTES + (int32_t)j * QOI_FSEG_BYTES;
+			const int32_t end = begin + QOI_FSEG_BYTES < stop ? begin + QOI_FSEG_BYTES : stop;
+			const uint32_t px_begin = P.f.px_start[g];
+			const uint32_t px_end = (j + 1 < live) ? P.f.px_start[g + 1] : m.npx;
+			int32_t p = begin + (int32_t)P.f.entry[g];
+			uint32_t run = 0;
+			uint8_t *o = P.out + m.dec_off + (size_t)px_begin * OUT_CH;
+			for (uint32_t i = px_begin; i < px_end; i++) {
+				if (run > 0) {
+					run--;
+				} else if (p < end) {
+					const uint32_t tag = s[p++];
+					if (tag == 0xFEu) {
+						px = (px & 0xFF000000u) | (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16);
+						p += 3;
+					} else if (tag == 0xFFu) {
+						px = (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
+						p += 4;
+					} else if ((tag & 0xC0u) == 0x00u) {
+						px = tab[tag];
+					} else if ((tag & 0xC0u) == 0x40u) {
+						const uint32_t sel = ((tag >> 4) & 3u) | (((tag >> 2) & 3u) << 4) | ((tag & 3u) << 8) | 0x4000u;
+						px = add_bytes(px, __byte_perm(0x0100FFFEu, 0u, sel));
+					} else if ((tag & 0xC0u) == 0x80u) {
+						const uint32_t b2 = s[p++];
+						const uint32_t vg = (tag & 0x3Fu) + 224u;
+						const uint32_t rb = vg + 248u;
+						px = add_bytes(px, ((rb + ((b2 >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((rb + (b2 & 0xFu)) & 0xFFu) << 16));
+					} else {
+						run = tag & 0x3Fu;
+					}
+					tab[qoi_slot(px)] = px;
+				}
+				if (OUT_CH == 4) {
+					*(uint32_t *)o = px;
+				} else {
+					o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
+				}
+				o += OUT_CH;
+			}
+		}
+		__syncwarp();
+		px = __shfl_sync(QOI_FULL_MASK, px, 0);
+	}
+	if (lane == 0) P.f.verified[img] = live;
+}
+
+/* binds the arrays of a QoiFState onto one allocation laid out by qoi_fstate_layout() (qoi_plan.h) */
+static inline void fstate_bind(QoiFState &f, unsigned char *base, const size_t *off) {
+	f.seg_base = (const uint32_t *)(base + off[0]);
+	f.px_cnt = (uint32_t *)(base + off[1]);
+	f.exit_skip = (uint8_t *)(base + off[2]);
+	f.entry = (uint8_t *)(base + off[3]);
+	f.px_start = (uint32_t *)(base + off[4]);
+	f.n_live = (uint32_t *)(base + off[5]);
+	f.in_px = (uint32_t *)(base + off[6]);
+	f.in_tab = (uint32_t *)(base + off[7]);
+	f.out_px = (uint32_t *)(base + off[8]);
+	f.out_tab = (uint32_t *)(base + off[9]);
+	f.out_written = (uint64_t *)(base + off[10]);
+	f.rbw = (uint64_t *)(base + off[11]);
+	f.out_clean = (uint64_t *)(base + off[17]);
+	f.dep = (uint8_t *)(base + off[12]);
+	f.redo = (uint8_t *)(base + off[13]);
+	f.verified = (uint32_t *)(base + off[14]);
+	f.ex_px = (uint32_t *)(base + off[15]);
+	f.ex_tab = (uint32_t *)(base + off[16]);
+}
+
+}  // namespace qoifdec

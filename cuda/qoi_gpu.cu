@@ -21,6 +21,7 @@
 #include "../include/qoi_gpu.h"
 #include "qoi_dec.cuh"
 #include "qoi_enc.cuh"
+#include "qoi_fdec.cuh"
 #include "qoi_plan.h"
 
 static_assert(sizeof(qoi_desc) == sizeof(QoiDescPOD), "qoi_desc layout");
@@ -60,6 +61,9 @@ struct qoi_gpu_plan {
 	std::vector<int> chunk_first;
 	std::vector<cudaEvent_t> ev_in, ev_k;
 	int index_owner = 0; /* who holds the restart index of the last encode: 0 nobody, 1 this plan, 2 the chunks */
+	/* scratch of the foreign-stream decoder (qoi_fdec.cuh), allocated on first use */
+	unsigned char *d_fstate = nullptr;
+	QoiFLayout flayout;
 };
 
 #define CK(ctx, call)                                                                         \
@@ -187,6 +191,7 @@ void qoi_gpu_plan_destroy(qoi_gpu_plan *p) {
 	cudaSetDevice(p->ctx->device);
 	cudaFree(p->d_metas);
 	cudaFree(p->d_tile_img);
+	cudaFree(p->d_fstate);
 	cudaFree(p->d_tile_order);
 	cudaFree(p->d_state);
 	cudaFree(p->d_pixels);
@@ -250,6 +255,41 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 	qoi_gpu_ctx *ctx = p->ctx;
 	cudaStream_t s = (cudaStream_t)cuda_stream;
 	CK(ctx, cudaSetDevice(ctx->device));
+	if (!use_index) {
+		/* any stream: exact parse scan, speculative segment decode, verification, exact fix-up (qoi_fdec.cuh) */
+		static_assert(QOI_FSEG_BYTES_HOST == QOI_FSEG_BYTES, "segment size");
+		if (!p->d_fstate) {
+			p->flayout = qoi_fstate_layout(p->geom);
+			CK(ctx, cudaMalloc(&p->d_fstate, p->flayout.total));
+			CK(ctx, cudaMemcpy(p->d_fstate + p->flayout.off[0], p->flayout.seg_base.data(), p->flayout.seg_base.size() * sizeof(uint32_t),
+			                   cudaMemcpyHostToDevice));
+		}
+		qoifdec::QoiFParams F;
+		memset(&F, 0, sizeof F);
+		F.streams = (const uint8_t *)d_streams;
+		F.lens = d_lens;
+		F.out = (uint8_t *)d_decoded;
+		F.status = d_status;
+		F.imgs = p->d_metas;
+		F.n_images = (uint32_t)p->geom.metas.size();
+		F.n_segs = p->flayout.n_segs;
+		F.out_channels = p->geom.dec_channels;
+		qoifdec::fstate_bind(F.f, p->d_fstate, p->flayout.off);
+		const uint32_t gs = (F.n_segs + QOI_FDEC_THREADS - 1) / QOI_FDEC_THREADS, gi = (F.n_images + 31) / 32;
+		qoifdec::fparse_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
+		qoifdec::fchain_kernel<<<gi, 32, 0, s>>>(F);
+		qoifdec::fzero_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
+		for (int r = 0; r < QOI_FDEC_ROUNDS; r++) {
+			if (F.out_channels == 4) qoifdec::fdecode_kernel<4><<<gs, QOI_FDEC_THREADS, 64 * QOI_FDEC_THREADS * 4, s>>>(F);
+			else qoifdec::fdecode_kernel<3><<<gs, QOI_FDEC_THREADS, 64 * QOI_FDEC_THREADS * 4, s>>>(F);
+			if (r + 1 < QOI_FDEC_ROUNDS) qoifdec::fverify_kernel<<<F.n_images, 32, 0, s>>>(F);
+		}
+		if (F.out_channels == 4) qoifdec::ffix_kernel<4><<<F.n_images, 32, 64 * 4, s>>>(F);
+		else qoifdec::ffix_kernel<3><<<F.n_images, 32, 64 * 4, s>>>(F);
+		g_launches += 3 + 2 * QOI_FDEC_ROUNDS;
+		CK(ctx, cudaGetLastError());
+		return QOI_GPU_OK;
+	}
 	QoiDecParams D;
 	memset(&D, 0, sizeof D);
 	D.streams = (const uint8_t *)d_streams;
@@ -259,9 +299,9 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 	D.imgs = p->d_metas;
 	D.tile_img = p->d_tile_img;
 	D.n_images = (uint32_t)p->geom.metas.size();
-	D.n_jobs = use_index ? p->geom.n_tiles : D.n_images;
+	D.n_jobs = p->geom.n_tiles;
 	D.out_channels = p->geom.dec_channels;
-	D.use_index = use_index ? 1 : 0;
+	D.use_index = 1;
 	D.st = p->st;
 	/* few segments: narrow blocks so that they spread over the SMs */
 	const bool narrow = D.n_jobs < (uint32_t)ctx->sm_count * 128u * 2u;

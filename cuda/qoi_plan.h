@@ -133,3 +133,36 @@ static inline void qoi_state_bind(QoiTileState &st, unsigned char *base, const Q
 	st.rs_byte = (int32_t *)(base + L.off[7]);
 	st.rs_prev = (uint32_t *)(base + L.off[8]);
 }
+
+/* ------------------------------------------------------------------ foreign-stream decoder scratch (qoi_fdec.cuh) */
+#define QOI_FSEG_BYTES_HOST 4096 /* must equal QOI_FSEG_BYTES */
+
+struct QoiFLayout {
+	std::vector<uint32_t> seg_base; /* [n + 1] */
+	uint32_t n_segs = 0;
+	size_t off[18];
+	size_t total = 0;
+};
+
+static inline QoiFLayout qoi_fstate_layout(const QoiPlanGeom &g) {
+	QoiFLayout L;
+	const size_t n = g.metas.size();
+	L.seg_base.resize(n + 1);
+	uint64_t segs = 0;
+	for (size_t i = 0; i < n; i++) {
+		L.seg_base[i] = (uint32_t)segs;
+		const uint64_t worst = (uint64_t)g.metas[i].npx * 5u; /* longest chunk area a decoder can consume */
+		segs += (worst + QOI_FSEG_BYTES_HOST - 1) / QOI_FSEG_BYTES_HOST + 1;
+	}
+	L.seg_base[n] = (uint32_t)segs;
+	L.n_segs = (uint32_t)segs;
+	const size_t S = segs, N = n;
+	const size_t sizes[18] = {(N + 1) * 4, S * 20, S * 8, S, S * 4, N * 4, S * 4, S * 256, S * 4, S * 256, S * 8, S * 8, S, S, N * 4, N * 4, N * 256, S * 8};
+	size_t o = 0;
+	for (int k = 0; k < 18; k++) {
+		L.off[k] = o;
+		o += (sizes[k] + 255) & ~(size_t)255;
+	}
+	L.total = o;
+	return L;
+}

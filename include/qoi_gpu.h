@@ -18,7 +18,9 @@
  *     at the encoder's tile boundaries using the restart index the encoder
  *     leaves in the plan (px, previous pixel, byte offset, 64-entry table per
  *     tile) -- the index lives OUTSIDE the .qoi stream, which stays bit exact.
- *     Any other stream ("foreign") is one segment per image.
+ *     Any other stream ("foreign") goes through a parse scan + speculative segment decode +
+ *     verification + exact fix-up (cuda/qoi_fdec.cuh): exact for every input, parallel inside
+ *     one stream as far as its content allows.
  *
  * All functions return QOI_GPU_OK (0) or a QOI_GPU_E_* code; none of them
  * falls back to the CPU.
@@ -88,7 +90,7 @@ int qoi_gpu_encode(qoi_gpu_plan *plan, const void *d_pixels, void *d_streams, in
  * d_lens: device int32[n_images] stream sizes (as qoi_decode's `size`).
  * use_index != 0: the streams are the ones the last qoi_gpu_encode on this plan wrote; decode them
  *                 segment-parallel with the plan's restart index.
- * use_index == 0: treat every stream as foreign -- one segment per image, no index needed.
+ * use_index == 0: treat every stream as foreign -- no index needed (what qoi_decode of the C API uses).
  * d_status (may be NULL): device int32[n_images], set to 0 or QOI_GPU_E_STREAM per image when the
  *                 header in the stream disagrees with the plan (magic, size, channels, colorspace).
  */

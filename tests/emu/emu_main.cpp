@@ -21,6 +21,7 @@
 #define QOI_EMU 1
 #include "qoi_dec.cuh"
 #include "qoi_enc.cuh"
+#include "qoi_fdec.cuh"
 #include "qoi_plan.h"
 
 extern "C" {
@@ -51,6 +52,46 @@ static void run_decode(const QoiDecParams &P, unsigned seed) {
 	size_t smem = QOI_DEC_SMEM_WORDS * QOI_DEC_THREADS * 4;
 	if (P.out_channels == 4) qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS>(P); }, seed);
 	else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS>(P); }, seed);
+}
+
+/* the foreign-stream pipeline exactly as qoi_gpu_decode enqueues it */
+static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned seed, int rounds = QOI_FDEC_ROUNDS) {
+	static_assert(QOI_FSEG_BYTES_HOST == QOI_FSEG_BYTES, "segment size");
+	QoiFLayout FL = qoi_fstate_layout(g);
+	std::vector<unsigned char> store(FL.total + 256, 0x5A);
+	unsigned char *base = (unsigned char *)(((uintptr_t)store.data() + 255) & ~(uintptr_t)255);
+	memcpy(base + FL.off[0], FL.seg_base.data(), FL.seg_base.size() * 4);
+	qoifdec::QoiFParams F;
+	memset(&F, 0, sizeof F);
+	F.streams = D.streams; F.lens = D.lens; F.out = D.out; F.status = D.status; F.imgs = D.imgs;
+	F.n_images = D.n_images; F.n_segs = FL.n_segs; F.out_channels = D.out_channels;
+	qoifdec::fstate_bind(F.f, base, FL.off);
+	const unsigned gs = (FL.n_segs + QOI_FDEC_THREADS - 1) / QOI_FDEC_THREADS, gi = (D.n_images + 31) / 32;
+	qemu::launch(gs, QOI_FDEC_THREADS, 0, [&]() { qoifdec::fparse_kernel(F); }, seed);
+	qemu::launch(gi, 32, 0, [&]() { qoifdec::fchain_kernel(F); }, seed);
+	qemu::launch(gs, QOI_FDEC_THREADS, 0, [&]() { qoifdec::fzero_kernel(F); }, seed);
+	for (int r = 0; r < rounds; r++) {
+		if (D.out_channels == 4) qemu::launch(gs, QOI_FDEC_THREADS, 64 * QOI_FDEC_THREADS * 4, [&]() { qoifdec::fdecode_kernel<4>(F); }, seed);
+		else qemu::launch(gs, QOI_FDEC_THREADS, 64 * QOI_FDEC_THREADS * 4, [&]() { qoifdec::fdecode_kernel<3>(F); }, seed);
+		if (r + 1 < rounds) qemu::launch(D.n_images, 32, 0, [&]() { qoifdec::fverify_kernel(F); }, seed);
+		if (getenv("QOI_EMU_FTRACE")) {
+			for (uint32_t i = 0; i < D.n_images; i++) {
+				fprintf(stderr, "round %d image %u verified %u/%u redo:", r, i, F.f.verified[i], F.f.n_live[i]);
+				for (uint32_t j = 0; j < F.f.n_live[i]; j++) if (F.f.redo[F.f.seg_base[i] + j]) fprintf(stderr, " %u", j);
+				fprintf(stderr, "\n");
+			}
+		}
+	}
+	if (getenv("QOI_EMU_FSTATS")) { /* how much is left for the sequential fix-up (an extra verify pass only marks; ffix stays exact) */
+		qemu::launch(D.n_images, 32, 0, [&]() { qoifdec::fverify_kernel(F); }, seed);
+		for (uint32_t i = 0; i < D.n_images; i++) {
+			uint32_t bad = 0;
+			for (uint32_t j = 0; j < F.f.n_live[i]; j++) bad += F.f.redo[F.f.seg_base[i] + j] ? 1 : 0;
+			fprintf(stderr, "image %u: %u live segments, verified prefix %u, %u segments left to the fix-up after %d rounds\n", i, F.f.n_live[i], F.f.verified[i], bad, rounds);
+		}
+	}
+	if (D.out_channels == 4) qemu::launch(D.n_images, 32, 64 * 4, [&]() { qoifdec::ffix_kernel<4>(F); }, seed);
+	else qemu::launch(D.n_images, 32, 64 * 4, [&]() { qoifdec::ffix_kernel<3>(F); }, seed);
 }
 
 static int first_diff(const unsigned char *a, const unsigned char *b, size_t n) {
@@ -147,7 +188,8 @@ int main(int argc, char **argv) {
 				D.out_channels = dec_ch;
 				D.use_index = use_index;
 				D.st = P.st;
-				run_decode(D, seed);
+				if (use_index) run_decode(D, seed);
+				else run_foreign(D, g, seed, getenv("QOI_EMU_FROUNDS") ? atoi(getenv("QOI_EMU_FROUNDS")) : QOI_FDEC_ROUNDS);
 				for (int i = 0; i < n; i++) {
 					QoiDescPOD dd;
 					unsigned char *ref = (unsigned char *)ora_decode(streams.data() + soff[i], lens[i], &dd, dec_ch);
@@ -197,7 +239,7 @@ int main(int argc, char **argv) {
 			D.n_jobs = (uint32_t)n;
 			D.out_channels = dec_ch;
 			D.use_index = 0;
-			run_decode(D, seed);
+			run_foreign(D, g, seed, getenv("QOI_EMU_FROUNDS") ? atoi(getenv("QOI_EMU_FROUNDS")) : QOI_FDEC_ROUNDS);
 			for (int i = 0; i < n; i++) {
 				QoiDescPOD dd;
 				unsigned char *ref = (unsigned char *)ora_decode(file.data() + soff[i], lens[i], &dd, dec_ch);
