@@ -36,8 +36,9 @@ namespace qoifdec {
 using namespace qoidev;
 
 #define QOI_FSEG_BYTES 4096
-#define QOI_FDEC_ROUNDS 3 /* speculative decode launches (with a verify pass between them) before the exact fix-up */
+#define QOI_FDEC_ROUNDS 4 /* speculative decode launches (with a verify pass between them) before the exact fix-up */
 #define QOI_FDEC_THREADS 128
+#define QOI_FCHAIN_SMEM ((32 * 5 + 32 * 2 + 32 + 32 + 4) * 4)
 
 struct QoiFState {
 	/* geometry (host written) */
@@ -135,36 +136,70 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 	}
 }
 
-/* ------------------------------------------------------------------ 1b. chain: one thread per stream */
+/* ------------------------------------------------------------------ 1b. chain: one warp per stream */
+/* The composition itself is sequential (skip -> exit skip), but it only touches two small words per segment: the
+   lanes fetch the maps of 32 segments at a time into shared memory, lane 0 composes them there, the lanes write the
+   results back coalesced. */
 __global__ void __launch_bounds__(32) fchain_kernel(const QoiFParams P) {
-	const uint32_t img = blockIdx.x * 32 + threadIdx.x;
+	QOI_DYNAMIC_SMEM(smem); /* (32*5 + 32*2 + 32 + 32 + 4) words */
+	uint32_t *s_cnt = (uint32_t *)smem, *s_exit = s_cnt + 32 * 5, *s_entry = s_exit + 32 * 2, *s_px = s_entry + 32;
+	uint32_t *s_state = s_px + 32; /* skip, px, live */
+	const uint32_t img = blockIdx.x;
+	const uint32_t lane = threadIdx.x;
 	if (img >= P.n_images) return;
 	const QoiImgMeta m = P.imgs[img];
 	const uint8_t *s = P.streams + m.stream_off;
 	const int32_t size = P.lens[img];
 	const bool ok = stream_ok(m, s, size);
-	if (P.status) P.status[img] = ok ? 0 : 4; /* QOI_GPU_E_STREAM */
-	uint32_t live = 0;
+	if (lane == 0 && P.status) P.status[img] = ok ? 0 : 4; /* QOI_GPU_E_STREAM */
+	if (lane == 0) { s_state[0] = 0; s_state[1] = 0; s_state[2] = 0; }
+	__syncwarp();
 	if (ok) {
 		const int32_t stop = size - QOI_END_BYTES;
 		const uint32_t base = P.f.seg_base[img];
 		const uint32_t nseg = stop > QOI_HEADER_BYTES ? (uint32_t)((stop - QOI_HEADER_BYTES + QOI_FSEG_BYTES - 1) / QOI_FSEG_BYTES) : 0u;
-		uint32_t skip = 0, px = 0;
-		for (uint32_t j = 0; j < nseg && px < m.npx; j++) {
-			const uint32_t g = base + j;
-			P.f.entry[g] = (uint8_t)skip;
-			P.f.px_start[g] = px;
-			P.f.redo[g] = 1;
-			P.f.in_px[g] = 0xFF000000u; /* round-0 guess: the reference's initial state (qoi.h:533-537) */
-			px += P.f.px_cnt[(size_t)g * 5 + skip];
-			skip = P.f.exit_skip[(size_t)g * 8 + skip];
-			live = j + 1;
+		for (uint32_t j0 = 0; j0 < nseg; j0 += 32) {
+			const uint32_t nb = nseg - j0 < 32u ? nseg - j0 : 32u;
+			if (lane < nb) {
+				const uint32_t g = base + j0 + lane;
+#pragma unroll
+				for (int k = 0; k < 5; k++) s_cnt[lane * 5 + k] = P.f.px_cnt[(size_t)g * 5 + k];
+				const uint2 e = *(const uint2 *)(P.f.exit_skip + (size_t)g * 8);
+				s_exit[lane * 2] = e.x;
+				s_exit[lane * 2 + 1] = e.y;
+			}
+			__syncwarp();
+			if (lane == 0) {
+				uint32_t skip = s_state[0], px = s_state[1], live = s_state[2];
+				for (uint32_t k = 0; k < nb; k++) {
+					if (px >= m.npx) { s_entry[k] = 0xFFu; continue; } /* all pixels already produced: dead segment */
+					s_entry[k] = skip;
+					s_px[k] = px;
+					px += s_cnt[k * 5 + skip];
+					skip = (skip < 4 ? (s_exit[k * 2] >> (8 * skip)) : s_exit[k * 2 + 1]) & 0xFFu;
+					live = j0 + k + 1;
+				}
+				s_state[0] = skip; s_state[1] = px; s_state[2] = live;
+			}
+			__syncwarp();
+			if (lane < nb && s_entry[lane] != 0xFFu) {
+				const uint32_t g = base + j0 + lane;
+				P.f.entry[g] = (uint8_t)s_entry[lane];
+				P.f.px_start[g] = s_px[lane];
+				P.f.redo[g] = 1;
+				P.f.in_px[g] = 0xFF000000u; /* round-0 guess: the reference's initial state (qoi.h:533-537) */
+			}
+			__syncwarp();
+			if (s_state[1] >= m.npx) break;
 		}
 	}
-	P.f.n_live[img] = live;
-	P.f.verified[img] = 0;
-	P.f.ex_px[img] = 0xFF000000u;
-	for (int k = 0; k < 64; k++) P.f.ex_tab[(size_t)img * 64 + k] = 0u;
+	if (lane == 0) {
+		P.f.n_live[img] = s_state[2];
+		P.f.verified[img] = 0;
+		P.f.ex_px[img] = 0xFF000000u;
+	}
+	P.f.ex_tab[(size_t)img * 64 + lane] = 0u;
+	P.f.ex_tab[(size_t)img * 64 + lane + 32] = 0u;
 }
 
 /* round-0 guess of index[]: zeros (qoi.h:533) */
@@ -279,6 +314,27 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fdecode_kernel(const QoiFPar
 	}
 }
 
+/* what the in-order walks (fverify_kernel, ffix_kernel) need to know about one segment; loaded a few segments ahead of
+   use because none of it depends on the chain state -- the walk itself is then shared-memory / register work only */
+struct SegRec {
+	uint64_t rbw, wr, clean;
+	uint32_t dep, g_px, o_px, g0, g1, o0, o1, redo;
+};
+#define QOI_FWALK_BATCH 4
+__device__ __forceinline__ void load_rec(const QoiFParams &P, uint32_t g, uint32_t lane, SegRec &r) {
+	r.rbw = P.f.rbw[g];
+	r.wr = P.f.out_written[g];
+	r.clean = P.f.out_clean[g];
+	r.dep = P.f.dep[g];
+	r.redo = P.f.redo[g];
+	r.g_px = P.f.in_px[g];
+	r.o_px = P.f.out_px[g];
+	r.g0 = P.f.in_tab[(size_t)g * 64 + lane];
+	r.g1 = P.f.in_tab[(size_t)g * 64 + lane + 32];
+	r.o0 = P.f.out_tab[(size_t)g * 64 + lane];
+	r.o1 = P.f.out_tab[(size_t)g * 64 + lane + 32];
+}
+
 /* ------------------------------------------------------------------ 3. verify + re-guess: one warp per stream */
 __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
 	const uint32_t img = blockIdx.x;
@@ -292,52 +348,57 @@ __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
 	uint32_t t0 = P.f.ex_tab[(size_t)img * 64 + lane], t1 = P.f.ex_tab[(size_t)img * 64 + lane + 32];
 	uint32_t px = P.f.ex_px[img];
 	bool exact = true;
-	for (uint32_t j = ver; j < live; j++) {
-		const uint32_t g = base + j;
-		const uint64_t rbw = P.f.rbw[g], wr = P.f.out_written[g];
-		const uint32_t dep = P.f.dep[g];
-		const uint32_t g_px = P.f.in_px[g];
-		const uint32_t g0 = P.f.in_tab[(size_t)g * 64 + lane], g1 = P.f.in_tab[(size_t)g * 64 + lane + 32];
-		const uint32_t o0 = P.f.out_tab[(size_t)g * 64 + lane], o1 = P.f.out_tab[(size_t)g * 64 + lane + 32];
-		const uint32_t o_px = P.f.out_px[g];
-		/* does the guess this segment was decoded with agree with the chain state on everything it used? */
-		const uint32_t pmask = ((dep & 1u) ? 0x00FFFFFFu : 0u) | ((dep & 2u) ? 0xFF000000u : 0u);
-		bool bad = ((rbw >> lane) & 1ull) && g0 != t0;
-		bad = bad || (((rbw >> (lane + 32)) & 1ull) && g1 != t1);
-		bad = bad || (lane == 0 && ((g_px ^ px) & pmask) != 0u);
-		const bool differs = __ballot_sync(QOI_FULL_MASK, bad) != 0u;
-		uint64_t apply = wr;
-		if (differs) {
-			/* new guess for this segment = the chain state (the exact state while `exact` still holds) */
-			P.f.in_tab[(size_t)g * 64 + lane] = t0;
-			P.f.in_tab[(size_t)g * 64 + lane + 32] = t1;
-			if (lane == 0) {
-				P.f.in_px[g] = px;
-				P.f.redo[g] = 1;
+	for (uint32_t j0 = ver; j0 < live; j0 += QOI_FWALK_BATCH) {
+		SegRec recs[QOI_FWALK_BATCH];
+#pragma unroll
+		for (int b = 0; b < QOI_FWALK_BATCH; b++)
+			if (j0 + b < live) load_rec(P, base + j0 + b, lane, recs[b]);
+#pragma unroll
+		for (int b = 0; b < QOI_FWALK_BATCH; b++) {
+			const uint32_t j = j0 + b;
+			if (j >= live) break;
+			const uint32_t g = base + j;
+			const SegRec &r = recs[b];
+			const uint32_t dep = r.dep, g_px = r.g_px, o_px = r.o_px;
+			/* does the guess this segment was decoded with agree with the chain state on everything it used? */
+			const uint32_t pmask = ((dep & 1u) ? 0x00FFFFFFu : 0u) | ((dep & 2u) ? 0xFF000000u : 0u);
+			bool bad = ((r.rbw >> lane) & 1ull) && r.g0 != t0;
+			bad = bad || (((r.rbw >> (lane + 32)) & 1ull) && r.g1 != t1);
+			bad = bad || (lane == 0 && ((g_px ^ px) & pmask) != 0u);
+			const bool differs = __ballot_sync(QOI_FULL_MASK, bad) != 0u;
+			uint64_t apply = r.wr;
+			if (differs) {
+				/* new guess for this segment = the chain state (the exact state while `exact` still holds) */
+				P.f.in_tab[(size_t)g * 64 + lane] = t0;
+				P.f.in_tab[(size_t)g * 64 + lane + 32] = t1;
+				if (lane == 0) {
+					P.f.in_px[g] = px;
+					P.f.redo[g] = 1;
+				}
+				if (exact) {
+					exact = false;
+					ver = j; /* everything before j is final */
+				}
+				/* Keep chaining for the segments behind it.  Its stale writes are only trusted where the value did not
+				   depend on the guess; the other slots keep the older value (right when the table is stable, e.g. a
+				   palette).  A purely relative segment's colour is re-based, a guess-independent one taken as is. */
+				apply = r.wr & r.clean;
+				if (dep & 4u) px = add_bytes(px, sub_bytes(o_px, g_px));
+				else if (dep & 8u) px = (o_px & 0x00FFFFFFu) | (((dep & 2u) ? px : o_px) & 0xFF000000u);
+				/* else: unknown; the incoming colour is as good a guess as any */
+			} else {
+				if (exact) ver = j + 1;
+				/* the colour leaving the segment: channels that did not depend on the incoming colour come from the decode */
+				if (dep & 4u) px = add_bytes(px, sub_bytes(o_px, g_px));
+				else px = o_px;
 			}
-			if (exact) {
-				exact = false;
-				ver = j; /* everything before j is final */
+			if ((apply >> lane) & 1ull) t0 = r.o0;
+			if ((apply >> (lane + 32)) & 1ull) t1 = r.o1;
+			if (exact) { /* remember the exact state after the verified prefix (the fix-up and the next round start here) */
+				P.f.ex_tab[(size_t)img * 64 + lane] = t0;
+				P.f.ex_tab[(size_t)img * 64 + lane + 32] = t1;
+				if (lane == 0) P.f.ex_px[img] = px;
 			}
-			/* Keep chaining for the segments behind it.  Its stale writes are only trusted where the value did not
-			   depend on the guess; the other slots keep the older value (right when the table is stable, e.g. a
-			   palette).  A purely relative segment's colour is re-based, a guess-independent one taken as is. */
-			apply = wr & P.f.out_clean[g];
-			if (dep & 4u) px = add_bytes(px, sub_bytes(o_px, g_px));
-			else if (dep & 8u) px = (o_px & 0x00FFFFFFu) | (((dep & 2u) ? px : o_px) & 0xFF000000u);
-			/* else: unknown; the incoming colour is as good a guess as any */
-		} else {
-			if (exact) ver = j + 1;
-			/* the colour leaving the segment: channels that did not depend on the incoming colour come from the decode */
-			if (dep & 4u) px = add_bytes(px, sub_bytes(o_px, g_px));
-			else px = o_px;
-		}
-		if ((apply >> lane) & 1ull) t0 = o0;
-		if ((apply >> (lane + 32)) & 1ull) t1 = o1;
-		if (exact) { /* remember the exact state after the verified prefix (the tail kernel and the next round start here) */
-			P.f.ex_tab[(size_t)img * 64 + lane] = t0;
-			P.f.ex_tab[(size_t)img * 64 + lane + 32] = t1;
-			if (lane == 0) P.f.ex_px[img] = px;
 		}
 	}
 	if (lane == 0) P.f.verified[img] = ver;
@@ -366,21 +427,28 @@ __global__ void __launch_bounds__(32) ffix_kernel(const QoiFParams P) {
 	tab[lane + 32] = P.f.ex_tab[(size_t)img * 64 + lane + 32];
 	uint32_t px = P.f.ex_px[img];
 	__syncwarp();
-	for (uint32_t j = ver; j < live; j++) {
+	for (uint32_t j0 = ver; j0 < live; j0 += QOI_FWALK_BATCH) {
+	SegRec recs[QOI_FWALK_BATCH];
+#pragma unroll
+	for (int b = 0; b < QOI_FWALK_BATCH; b++)
+		if (j0 + b < live) load_rec(P, base + j0 + b, lane, recs[b]);
+#pragma unroll
+	for (int b = 0; b < QOI_FWALK_BATCH; b++) {
+		const uint32_t j = j0 + b;
+		if (j >= live) break;
 		const uint32_t g = base + j;
-		const uint64_t rbw = P.f.rbw[g], wr = P.f.out_written[g];
-		const uint32_t dep = P.f.dep[g];
-		const uint32_t g_px = P.f.in_px[g];
+		const SegRec &r = recs[b];
+		const uint32_t dep = r.dep, g_px = r.g_px;
 		const uint32_t pmask = ((dep & 1u) ? 0x00FFFFFFu : 0u) | ((dep & 2u) ? 0xFF000000u : 0u);
-		bool bad = ((rbw >> lane) & 1ull) && P.f.in_tab[(size_t)g * 64 + lane] != tab[lane];
-		bad = bad || (((rbw >> (lane + 32)) & 1ull) && P.f.in_tab[(size_t)g * 64 + lane + 32] != tab[lane + 32]);
+		bool bad = ((r.rbw >> lane) & 1ull) && r.g0 != tab[lane];
+		bad = bad || (((r.rbw >> (lane + 32)) & 1ull) && r.g1 != tab[lane + 32]);
 		bad = bad || (lane == 0 && ((g_px ^ px) & pmask) != 0u);
-		bad = bad || P.f.redo[g] != 0; /* a new guess was issued but never decoded */
+		bad = bad || r.redo != 0; /* a new guess was issued but never decoded */
 		if (__ballot_sync(QOI_FULL_MASK, bad) == 0u) {
-			const uint32_t o_px = P.f.out_px[g];
+			const uint32_t o_px = r.o_px;
 			px = (dep & 4u) ? add_bytes(px, sub_bytes(o_px, g_px)) : o_px;
-			if ((wr >> lane) & 1ull) tab[lane] = P.f.out_tab[(size_t)g * 64 + lane];
-			if ((wr >> (lane + 32)) & 1ull) tab[lane + 32] = P.f.out_tab[(size_t)g * 64 + lane + 32];
+			if ((r.wr >> lane) & 1ull) tab[lane] = r.o0;
+			if ((r.wr >> (lane + 32)) & 1ull) tab[lane + 32] = r.o1;
 		} else if (lane == 0) {
 			const int32_t begin = QOI_HEADER_BYTES + (int32_t)j * QOI_FSEG_BYTES;
 			const int32_t end = begin + QOI_FSEG_BYTES < stop ? begin + QOI_FSEG_BYTES : stop;
@@ -425,6 +493,7 @@ __global__ void __launch_bounds__(32) ffix_kernel(const QoiFParams P) {
 		}
 		__syncwarp();
 		px = __shfl_sync(QOI_FULL_MASK, px, 0);
+	}
 	}
 	if (lane == 0) P.f.verified[img] = live;
 }

@@ -275,9 +275,9 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 		F.n_segs = p->flayout.n_segs;
 		F.out_channels = p->geom.dec_channels;
 		qoifdec::fstate_bind(F.f, p->d_fstate, p->flayout.off);
-		const uint32_t gs = (F.n_segs + QOI_FDEC_THREADS - 1) / QOI_FDEC_THREADS, gi = (F.n_images + 31) / 32;
+		const uint32_t gs = (F.n_segs + QOI_FDEC_THREADS - 1) / QOI_FDEC_THREADS;
 		qoifdec::fparse_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
-		qoifdec::fchain_kernel<<<gi, 32, 0, s>>>(F);
+		qoifdec::fchain_kernel<<<F.n_images, 32, QOI_FCHAIN_SMEM, s>>>(F);
 		qoifdec::fzero_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
 		for (int r = 0; r < QOI_FDEC_ROUNDS; r++) {
 			if (F.out_channels == 4) qoifdec::fdecode_kernel<4><<<gs, QOI_FDEC_THREADS, 64 * QOI_FDEC_THREADS * 4, s>>>(F);

@@ -68,7 +68,7 @@ static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned se
 	qoifdec::fstate_bind(F.f, base, FL.off);
 	const unsigned gs = (FL.n_segs + QOI_FDEC_THREADS - 1) / QOI_FDEC_THREADS, gi = (D.n_images + 31) / 32;
 	qemu::launch(gs, QOI_FDEC_THREADS, 0, [&]() { qoifdec::fparse_kernel(F); }, seed);
-	qemu::launch(gi, 32, 0, [&]() { qoifdec::fchain_kernel(F); }, seed);
+	qemu::launch(D.n_images, 32, QOI_FCHAIN_SMEM, [&]() { qoifdec::fchain_kernel(F); }, seed);
 	qemu::launch(gs, QOI_FDEC_THREADS, 0, [&]() { qoifdec::fzero_kernel(F); }, seed);
 	for (int r = 0; r < rounds; r++) {
 		if (D.out_channels == 4) qemu::launch(gs, QOI_FDEC_THREADS, 64 * QOI_FDEC_THREADS * 4, [&]() { qoifdec::fdecode_kernel<4>(F); }, seed);
