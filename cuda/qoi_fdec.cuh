@@ -36,9 +36,15 @@ namespace qoifdec {
 using namespace qoidev;
 
 #define QOI_FSEG_BYTES 4096
-#define QOI_FDEC_ROUNDS 4 /* speculative decode launches (with a verify pass between them) before the exact fix-up */
+#define QOI_FDEC_ROUNDS 6 /* speculative decode launches (with a verify pass between them) before the exact fix-up */
 #define QOI_FDEC_THREADS 128
 #define QOI_FCHAIN_SMEM ((32 * 5 + 32 * 2 + 32 + 32 + 4) * 4)
+#define QOI_FDEC_SMEM ((64 + 32) * QOI_FDEC_THREADS * 4) /* per lane: index[64] + 64 source half-words */
+/* Where a channel group (r,g,b or alpha) of a colour came from, as tracked by the speculative decode: values 0..63 = slot
+   of the guessed index[] that was read before the segment wrote it (r,g,b possibly plus DIFF/LUMA deltas) */
+#define QOI_SRC_IN 64u    /* the colour that entered the segment (r,g,b possibly plus deltas) */
+#define QOI_SRC_OWN 65u   /* bytes of the segment itself: independent of every guess */
+#define QOI_SRC_NONE 0xFFu
 
 struct QoiFState {
 	/* geometry (host written) */
@@ -57,9 +63,11 @@ struct QoiFState {
 	uint32_t *out_tab;        /* [segs][64] values written by the segment (last writer per slot) */
 	uint64_t *out_written;    /* [segs] */
 	uint64_t *rbw;            /* [segs] slots read before the segment wrote them */
-	uint64_t *out_clean;      /* [segs] written slots whose value does not depend on the guess (came from ops inside the segment) */
-	uint8_t *dep;             /* [segs] bit0: incoming r,g,b used; bit1: incoming alpha used; bit2: no absolute colour op inside;
-	                             bit3: the outgoing r,g,b do not depend on the guess */
+	uint16_t *out_src;        /* [segs][64] where the value a slot holds after the segment came from: low byte r,g,b, high byte
+	                             alpha (QOI_SRC_*: a slot of the GUESSED index[], the incoming colour, or the segment's own
+	                             bytes); 0xFFFF = slot not written */
+	uint32_t *dep;            /* [segs] bit0: a pixel used the incoming r,g,b; bit1: ... the incoming alpha;
+	                             bits 8-15 / 16-23: QOI_SRC_* of the outgoing colour's r,g,b / alpha */
 	uint8_t *redo;            /* [segs] decode (again) in the next fdecode launch */
 	/* verification */
 	uint32_t *verified;       /* [n_images] segments [0, verified) are final */
@@ -107,6 +115,11 @@ __device__ __forceinline__ bool stream_ok(const QoiImgMeta &m, const uint8_t *s,
 	       s[12] == m.channels && s[13] == m.colorspace;
 }
 
+/* op length from its first byte (qoi.h:547,552,566; everything else is one byte) and the pixels it yields (a RUN op
+   yields run+1, qoi.h:573-575,541-543) */
+__device__ __forceinline__ int32_t op_len(uint32_t tag) { return (tag == 0xFEu) ? 4 : (tag == 0xFFu) ? 5 : ((tag >> 6) == 2u ? 2 : 1); }
+__device__ __forceinline__ uint32_t op_px(uint32_t tag) { return ((tag >> 6) == 3u && tag < 0xFEu) ? (tag & 0x3Fu) + 1u : 1u; }
+
 /* ------------------------------------------------------------------ 1a. parse: one thread per segment */
 __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFParams P) {
 	const uint32_t g = blockIdx.x * QOI_FDEC_THREADS + threadIdx.x;
@@ -120,19 +133,60 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 	const int32_t begin = QOI_HEADER_BYTES + (int32_t)(g - P.f.seg_base[img]) * QOI_FSEG_BYTES;
 	if (begin >= stop) return; /* beyond the stream */
 	const int32_t end = begin + QOI_FSEG_BYTES < stop ? begin + QOI_FSEG_BYTES : stop;
+	/* Walk 0 is made in full.  Walks 1..4 usually fall onto an op boundary of walk 0 within a few ops and are the same
+	   from there on: walk 0 remembers its op starts inside the first 128 bytes (bitmap), the others stop as soon as they
+	   land on one and take walk 0's tail.  A walk that stays out of phase (e.g. a stream of two-byte ops entered at
+	   odd and even offsets) is simply made in full as well. */
+	const int32_t near = begin + 128 < end ? begin + 128 : end;
+	uint64_t seen_lo = 0, seen_hi = 0;
+	uint32_t total0 = 0;
+	int32_t p0 = begin;
+	while (p0 < end) {
+		if (p0 < near) {
+			const uint32_t off = (uint32_t)(p0 - begin);
+			if (off < 64u) seen_lo |= 1ull << off;
+			else seen_hi |= 1ull << (off - 64u);
+		}
+		const uint32_t tag = s[p0];
+		p0 += op_len(tag);
+		total0 += op_px(tag);
+	}
+	const uint32_t exit0 = (uint32_t)(p0 - end);
+	P.f.px_cnt[(size_t)g * 5] = total0;
+	P.f.exit_skip[(size_t)g * 8] = (uint8_t)exit0;
 #pragma unroll 1
-	for (int sk = 0; sk < 5; sk++) {
+	for (int sk = 1; sk < 5; sk++) {
 		int32_t p = begin + sk;
 		uint32_t cnt = 0;
-		while (p < end) {
+		bool merged = false;
+		while (p < near) {
+			const uint32_t off = (uint32_t)(p - begin);
+			if (((off < 64u ? seen_lo : seen_hi) >> (off & 63u)) & 1ull) { merged = true; break; }
 			const uint32_t tag = s[p];
-			const uint32_t top = tag >> 6;
-			/* op length from its first byte (qoi.h:547,552,566; everything else is one byte) */
-			p += (tag == 0xFEu) ? 4 : (tag == 0xFFu) ? 5 : (top == 2u ? 2 : 1);
-			cnt += (top == 3u && tag < 0xFEu) ? (tag & 0x3Fu) + 1u : 1u; /* a RUN op yields run+1 pixels (qoi.h:573-575,541-543) */
+			p += op_len(tag);
+			cnt += op_px(tag);
+		}
+		uint32_t ex;
+		if (merged) {
+			/* pixels walk 0 produced before the meeting point */
+			uint32_t before = 0;
+			for (int32_t q = begin; q < p;) {
+				const uint32_t tag = s[q];
+				q += op_len(tag);
+				before += op_px(tag);
+			}
+			cnt += total0 - before;
+			ex = exit0;
+		} else {
+			while (p < end) {
+				const uint32_t tag = s[p];
+				p += op_len(tag);
+				cnt += op_px(tag);
+			}
+			ex = p >= end ? (uint32_t)(p - end) : 0u; /* an entry skip beyond a very short last segment */
 		}
 		P.f.px_cnt[(size_t)g * 5 + sk] = cnt;
-		P.f.exit_skip[(size_t)g * 8 + sk] = (uint8_t)(p >= end ? p - end : 0);
+		P.f.exit_skip[(size_t)g * 8 + sk] = (uint8_t)ex;
 	}
 }
 
@@ -239,9 +293,15 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fdecode_kernel(const QoiFPar
 #pragma unroll 8
 		for (int k = 0; k < 64; k++) tab[k * QOI_FDEC_THREADS] = src[k];
 	}
-	uint64_t written = 0, rbw = 0, cleanw = 0;
-	bool rgb_known = false, a_known = false, dep_rgb = false, dep_a = false, rel_only = true;
-	bool clean = false; /* r,g,b of px derive only from ops inside this segment (heuristic input for the re-guessing chain) */
+	/* Per slot: where the value it holds now came from (QOI_SRC_*; r,g,b in the low byte, alpha in the high byte,
+	   0xFFFF = not written by this segment); two slots to a word, words interleaved over the threads (conflict free).
+	   `src` is the same for the current colour. */
+	uint16_t *sst = (uint16_t *)((uint32_t *)smem + 64 * QOI_FDEC_THREADS + threadIdx.x); /* sst[(slot >> 1) * 2 * THREADS + (slot & 1)] */
+#pragma unroll
+	for (int k = 0; k < 32; k++) *(uint32_t *)(sst + k * 2 * QOI_FDEC_THREADS) = 0xFFFFFFFFu;
+	uint64_t rbw = 0;
+	uint32_t src = QOI_SRC_IN | (QOI_SRC_IN << 8);
+	bool dep_rgb = false, dep_a = false;
 	int32_t p = begin + (int32_t)P.f.entry[g];
 	uint32_t run = 0;
 	uint8_t *o = P.out + m.dec_off + (size_t)px_begin * OUT_CH;
@@ -253,46 +313,39 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fdecode_kernel(const QoiFPar
 			if (tag == 0xFEu) { /* qoi.h:547-551: r,g,b replaced, alpha kept */
 				px = (px & 0xFF000000u) | (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16);
 				p += 3;
-				if (!a_known) dep_a = true;
-				rgb_known = true;
-				rel_only = false;
-				clean = true;
+				src = (src & 0xFF00u) | QOI_SRC_OWN;
 			} else if (tag == 0xFFu) { /* qoi.h:552-557 */
 				px = (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
 				p += 4;
-				rgb_known = a_known = true;
-				rel_only = false;
-				clean = true;
+				src = QOI_SRC_OWN | (QOI_SRC_OWN << 8);
 			} else if ((tag & 0xC0u) == 0x00u) { /* qoi.h:558-560 */
-				if (!((written >> tag) & 1ull)) rbw |= 1ull << tag;
-				clean = (cleanw >> tag) & 1ull; /* a slot not written here has no clean bit */
+				const uint32_t st = sst[(tag >> 1) * 2 * QOI_FDEC_THREADS + (tag & 1u)];
+				if (st == 0xFFFFu) {
+					rbw |= 1ull << tag;
+					src = tag | (tag << 8);
+				} else {
+					src = st;
+				}
 				px = tab[tag * QOI_FDEC_THREADS];
-				rgb_known = a_known = true;
-				rel_only = false;
 			} else if ((tag & 0xC0u) == 0x40u) { /* qoi.h:561-565 */
 				const uint32_t sel = ((tag >> 4) & 3u) | (((tag >> 2) & 3u) << 4) | ((tag & 3u) << 8) | 0x4000u;
 				px = add_bytes(px, __byte_perm(0x0100FFFEu, 0u, sel));
-				if (!rgb_known) dep_rgb = true;
-				if (!a_known) dep_a = true;
 			} else if ((tag & 0xC0u) == 0x80u) { /* qoi.h:566-572 */
 				const uint32_t b2 = s[p++];
 				const uint32_t vg = (tag & 0x3Fu) + 224u;
 				const uint32_t rb = vg + 248u;
 				px = add_bytes(px, ((rb + ((b2 >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((rb + (b2 & 0xFu)) & 0xFFu) << 16));
-				if (!rgb_known) dep_rgb = true;
-				if (!a_known) dep_a = true;
 			} else { /* qoi.h:573-575 */
 				run = tag & 0x3Fu;
-				if (!rgb_known) dep_rgb = true;
-				if (!a_known) dep_a = true;
 			}
+			dep_rgb = dep_rgb || (src & 0xFFu) == QOI_SRC_IN;
+			dep_a = dep_a || (src >> 8) == QOI_SRC_IN;
 			const uint32_t h = qoi_slot(px);
 			tab[h * QOI_FDEC_THREADS] = px; /* qoi.h:577 */
-			written |= 1ull << h;
-			cleanw = clean ? (cleanw | (1ull << h)) : (cleanw & ~(1ull << h));
+			sst[(h >> 1) * 2 * QOI_FDEC_THREADS + (h & 1u)] = (uint16_t)src;
 		} else { /* stream exhausted: the pixel repeats the current colour */
-			if (!rgb_known) dep_rgb = true;
-			if (!a_known) dep_a = true;
+			dep_rgb = dep_rgb || (src & 0xFFu) == QOI_SRC_IN;
+			dep_a = dep_a || (src >> 8) == QOI_SRC_IN;
 		}
 		if (OUT_CH == 4) {
 			*(uint32_t *)o = px;
@@ -301,11 +354,21 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fdecode_kernel(const QoiFPar
 		}
 		o += OUT_CH;
 	}
+	uint64_t written = 0;
+	{
+		uint32_t *dsrc = (uint32_t *)(P.f.out_src + (size_t)g * 64);
+#pragma unroll 4
+		for (int k = 0; k < 32; k++) {
+			const uint32_t wv = *(const uint32_t *)(sst + k * 2 * QOI_FDEC_THREADS);
+			if ((wv & 0xFFFFu) != 0xFFFFu) written |= 1ull << (2 * k);
+			if ((wv >> 16) != 0xFFFFu) written |= 2ull << (2 * k);
+			dsrc[k] = wv;
+		}
+	}
 	P.f.out_px[g] = px;
 	P.f.out_written[g] = written;
 	P.f.rbw[g] = rbw;
-	P.f.out_clean[g] = cleanw;
-	P.f.dep[g] = (uint8_t)((dep_rgb ? 1 : 0) | (dep_a ? 2 : 0) | (rel_only ? 4 : 0) | (clean ? 8 : 0));
+	P.f.dep[g] = (dep_rgb ? 1u : 0u) | (dep_a ? 2u : 0u) | (src << 8);
 	P.f.redo[g] = 0;
 	{
 		uint32_t *dst = P.f.out_tab + (size_t)g * 64;
@@ -317,14 +380,16 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fdecode_kernel(const QoiFPar
 /* what the in-order walks (fverify_kernel, ffix_kernel) need to know about one segment; loaded a few segments ahead of
    use because none of it depends on the chain state -- the walk itself is then shared-memory / register work only */
 struct SegRec {
-	uint64_t rbw, wr, clean;
+	uint64_t rbw, wr;
+	uint32_t s0, s1; /* QOI_SRC_* pairs of slots lane and lane + 32 */
 	uint32_t dep, g_px, o_px, g0, g1, o0, o1, redo;
 };
 #define QOI_FWALK_BATCH 4
 __device__ __forceinline__ void load_rec(const QoiFParams &P, uint32_t g, uint32_t lane, SegRec &r) {
 	r.rbw = P.f.rbw[g];
 	r.wr = P.f.out_written[g];
-	r.clean = P.f.out_clean[g];
+	r.s0 = P.f.out_src[(size_t)g * 64 + lane];
+	r.s1 = P.f.out_src[(size_t)g * 64 + lane + 32];
 	r.dep = P.f.dep[g];
 	r.redo = P.f.redo[g];
 	r.g_px = P.f.in_px[g];
@@ -348,11 +413,14 @@ __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
 	uint32_t t0 = P.f.ex_tab[(size_t)img * 64 + lane], t1 = P.f.ex_tab[(size_t)img * 64 + lane + 32];
 	uint32_t px = P.f.ex_px[img];
 	bool exact = true;
+	SegRec recs[QOI_FWALK_BATCH], ahead[QOI_FWALK_BATCH]; /* the batch being walked, the batch in flight */
+#pragma unroll
+	for (int b = 0; b < QOI_FWALK_BATCH; b++)
+		if (ver + b < live) load_rec(P, base + ver + b, lane, recs[b]);
 	for (uint32_t j0 = ver; j0 < live; j0 += QOI_FWALK_BATCH) {
-		SegRec recs[QOI_FWALK_BATCH];
 #pragma unroll
 		for (int b = 0; b < QOI_FWALK_BATCH; b++)
-			if (j0 + b < live) load_rec(P, base + j0 + b, lane, recs[b]);
+			if (j0 + QOI_FWALK_BATCH + b < live) load_rec(P, base + j0 + QOI_FWALK_BATCH + b, lane, ahead[b]);
 #pragma unroll
 		for (int b = 0; b < QOI_FWALK_BATCH; b++) {
 			const uint32_t j = j0 + b;
@@ -362,10 +430,9 @@ __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
 			const uint32_t dep = r.dep, g_px = r.g_px, o_px = r.o_px;
 			/* does the guess this segment was decoded with agree with the chain state on everything it used? */
 			const uint32_t pmask = ((dep & 1u) ? 0x00FFFFFFu : 0u) | ((dep & 2u) ? 0xFF000000u : 0u);
-			bool bad = ((r.rbw >> lane) & 1ull) && r.g0 != t0;
-			bad = bad || (((r.rbw >> (lane + 32)) & 1ull) && r.g1 != t1);
-			bad = bad || (lane == 0 && ((g_px ^ px) & pmask) != 0u);
-			const bool differs = __ballot_sync(QOI_FULL_MASK, bad) != 0u;
+			/* which slots of the guess equal the chain state */
+			const uint64_t agree = (uint64_t)__ballot_sync(QOI_FULL_MASK, r.g0 == t0) | ((uint64_t)__ballot_sync(QOI_FULL_MASK, r.g1 == t1) << 32);
+			const bool differs = (r.rbw & ~agree) != 0ull || ((g_px ^ px) & pmask) != 0u;
 			uint64_t apply = r.wr;
 			if (differs) {
 				/* new guess for this segment = the chain state (the exact state while `exact` still holds) */
@@ -379,18 +446,37 @@ __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
 					exact = false;
 					ver = j; /* everything before j is final */
 				}
-				/* Keep chaining for the segments behind it.  Its stale writes are only trusted where the value did not
-				   depend on the guess; the other slots keep the older value (right when the table is stable, e.g. a
-				   palette).  A purely relative segment's colour is re-based, a guess-independent one taken as is. */
-				apply = r.wr & r.clean;
-				if (dep & 4u) px = add_bytes(px, sub_bytes(o_px, g_px));
-				else if (dep & 8u) px = (o_px & 0x00FFFFFFu) | (((dep & 2u) ? px : o_px) & 0xFF000000u);
-				/* else: unknown; the incoming colour is as good a guess as any */
+				/* Keep chaining for the segments behind it.  Of its stale writes only those are trusted whose source was
+				   guessed right (a slot that agrees, the incoming colour if it agrees, or the segment's own bytes); the other
+				   slots keep the older value (right when the table is stable, e.g. a palette).  The outgoing colour: a
+				   channel whose source was wrong is re-based on the chain's value of that source (r,g,b are source + deltas,
+				   alpha is the source's alpha). */
+				const bool in_rgb_ok = ((g_px ^ px) & 0x00FFFFFFu) == 0u, in_a_ok = ((g_px ^ px) & 0xFF000000u) == 0u;
+				const uint32_t lo = 1u << lane;
+				uint64_t ap = 0;
+				{
+					const uint32_t c0 = r.s0 & 0xFFu, a0 = r.s0 >> 8, c1 = r.s1 & 0xFFu, a1 = r.s1 >> 8;
+					const bool ok0 = r.s0 != 0xFFFFu && (c0 == QOI_SRC_OWN || (c0 == QOI_SRC_IN ? in_rgb_ok : ((agree >> c0) & 1ull) != 0ull)) &&
+					                 (a0 == QOI_SRC_OWN || (a0 == QOI_SRC_IN ? in_a_ok : ((agree >> a0) & 1ull) != 0ull));
+					const bool ok1 = r.s1 != 0xFFFFu && (c1 == QOI_SRC_OWN || (c1 == QOI_SRC_IN ? in_rgb_ok : ((agree >> c1) & 1ull) != 0ull)) &&
+					                 (a1 == QOI_SRC_OWN || (a1 == QOI_SRC_IN ? in_a_ok : ((agree >> a1) & 1ull) != 0ull));
+					ap = (ok0 ? (uint64_t)lo : 0ull) | (ok1 ? (uint64_t)lo << 32 : 0ull);
+				}
+				apply = ap;
+				const uint32_t sc = (dep >> 8) & 0xFFu, sa = (dep >> 16) & 0xFFu;
+				/* the guessed and the chain value of the source slots (held by lane slot & 31) */
+				const uint32_t gc0 = __shfl_sync(QOI_FULL_MASK, r.g0, sc & 31u), gc1 = __shfl_sync(QOI_FULL_MASK, r.g1, sc & 31u);
+				const uint32_t tc0 = __shfl_sync(QOI_FULL_MASK, t0, sc & 31u), tc1 = __shfl_sync(QOI_FULL_MASK, t1, sc & 31u);
+				const uint32_t ta0 = __shfl_sync(QOI_FULL_MASK, t0, sa & 31u), ta1 = __shfl_sync(QOI_FULL_MASK, t1, sa & 31u);
+				uint32_t rgb = o_px, al = o_px;
+				if (sc == QOI_SRC_IN) rgb = add_bytes(px, sub_bytes(o_px, g_px));
+				else if (sc < 64u) rgb = add_bytes((sc & 32u) ? tc1 : tc0, sub_bytes(o_px, (sc & 32u) ? gc1 : gc0));
+				if (sa == QOI_SRC_IN) al = px;
+				else if (sa < 64u) al = (sa & 32u) ? ta1 : ta0;
+				px = (rgb & 0x00FFFFFFu) | (al & 0xFF000000u);
 			} else {
 				if (exact) ver = j + 1;
-				/* the colour leaving the segment: channels that did not depend on the incoming colour come from the decode */
-				if (dep & 4u) px = add_bytes(px, sub_bytes(o_px, g_px));
-				else px = o_px;
+				px = o_px; /* agreed on everything it used: the decode is what the chain state produces */
 			}
 			if ((apply >> lane) & 1ull) t0 = r.o0;
 			if ((apply >> (lane + 32)) & 1ull) t1 = r.o1;
@@ -400,6 +486,8 @@ __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
 				if (lane == 0) P.f.ex_px[img] = px;
 			}
 		}
+#pragma unroll
+		for (int b = 0; b < QOI_FWALK_BATCH; b++) recs[b] = ahead[b];
 	}
 	if (lane == 0) P.f.verified[img] = ver;
 }
@@ -427,11 +515,14 @@ __global__ void __launch_bounds__(32) ffix_kernel(const QoiFParams P) {
 	tab[lane + 32] = P.f.ex_tab[(size_t)img * 64 + lane + 32];
 	uint32_t px = P.f.ex_px[img];
 	__syncwarp();
-	for (uint32_t j0 = ver; j0 < live; j0 += QOI_FWALK_BATCH) {
-	SegRec recs[QOI_FWALK_BATCH];
+	SegRec recs[QOI_FWALK_BATCH], ahead[QOI_FWALK_BATCH];
 #pragma unroll
 	for (int b = 0; b < QOI_FWALK_BATCH; b++)
-		if (j0 + b < live) load_rec(P, base + j0 + b, lane, recs[b]);
+		if (ver + b < live) load_rec(P, base + ver + b, lane, recs[b]);
+	for (uint32_t j0 = ver; j0 < live; j0 += QOI_FWALK_BATCH) {
+#pragma unroll
+	for (int b = 0; b < QOI_FWALK_BATCH; b++)
+		if (j0 + QOI_FWALK_BATCH + b < live) load_rec(P, base + j0 + QOI_FWALK_BATCH + b, lane, ahead[b]);
 #pragma unroll
 	for (int b = 0; b < QOI_FWALK_BATCH; b++) {
 		const uint32_t j = j0 + b;
@@ -445,8 +536,7 @@ __global__ void __launch_bounds__(32) ffix_kernel(const QoiFParams P) {
 		bad = bad || (lane == 0 && ((g_px ^ px) & pmask) != 0u);
 		bad = bad || r.redo != 0; /* a new guess was issued but never decoded */
 		if (__ballot_sync(QOI_FULL_MASK, bad) == 0u) {
-			const uint32_t o_px = r.o_px;
-			px = (dep & 4u) ? add_bytes(px, sub_bytes(o_px, g_px)) : o_px;
+			px = r.o_px;
 			if ((r.wr >> lane) & 1ull) tab[lane] = r.o0;
 			if ((r.wr >> (lane + 32)) & 1ull) tab[lane + 32] = r.o1;
 		} else if (lane == 0) {
@@ -494,6 +584,8 @@ __global__ void __launch_bounds__(32) ffix_kernel(const QoiFParams P) {
 		__syncwarp();
 		px = __shfl_sync(QOI_FULL_MASK, px, 0);
 	}
+#pragma unroll
+	for (int b = 0; b < QOI_FWALK_BATCH; b++) recs[b] = ahead[b];
 	}
 	if (lane == 0) P.f.verified[img] = live;
 }
@@ -512,8 +604,8 @@ static inline void fstate_bind(QoiFState &f, unsigned char *base, const size_t *
 	f.out_tab = (uint32_t *)(base + off[9]);
 	f.out_written = (uint64_t *)(base + off[10]);
 	f.rbw = (uint64_t *)(base + off[11]);
-	f.out_clean = (uint64_t *)(base + off[17]);
-	f.dep = (uint8_t *)(base + off[12]);
+	f.out_src = (uint16_t *)(base + off[17]);
+	f.dep = (uint32_t *)(base + off[12]);
 	f.redo = (uint8_t *)(base + off[13]);
 	f.verified = (uint32_t *)(base + off[14]);
 	f.ex_px = (uint32_t *)(base + off[15]);

@@ -280,8 +280,8 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 		qoifdec::fchain_kernel<<<F.n_images, 32, QOI_FCHAIN_SMEM, s>>>(F);
 		qoifdec::fzero_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
 		for (int r = 0; r < QOI_FDEC_ROUNDS; r++) {
-			if (F.out_channels == 4) qoifdec::fdecode_kernel<4><<<gs, QOI_FDEC_THREADS, 64 * QOI_FDEC_THREADS * 4, s>>>(F);
-			else qoifdec::fdecode_kernel<3><<<gs, QOI_FDEC_THREADS, 64 * QOI_FDEC_THREADS * 4, s>>>(F);
+			if (F.out_channels == 4) qoifdec::fdecode_kernel<4><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
+			else qoifdec::fdecode_kernel<3><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
 			if (r + 1 < QOI_FDEC_ROUNDS) qoifdec::fverify_kernel<<<F.n_images, 32, 0, s>>>(F);
 		}
 		if (F.out_channels == 4) qoifdec::ffix_kernel<4><<<F.n_images, 32, 64 * 4, s>>>(F);

@@ -157,7 +157,7 @@ static inline QoiFLayout qoi_fstate_layout(const QoiPlanGeom &g) {
 	L.seg_base[n] = (uint32_t)segs;
 	L.n_segs = (uint32_t)segs;
 	const size_t S = segs, N = n;
-	const size_t sizes[18] = {(N + 1) * 4, S * 20, S * 8, S, S * 4, N * 4, S * 4, S * 256, S * 4, S * 256, S * 8, S * 8, S, S, N * 4, N * 4, N * 256, S * 8};
+	const size_t sizes[18] = {(N + 1) * 4, S * 20, S * 8, S, S * 4, N * 4, S * 4, S * 256, S * 4, S * 256, S * 8, S * 8, S * 4, S, N * 4, N * 4, N * 256, S * 128};
 	size_t o = 0;
 	for (int k = 0; k < 18; k++) {
 		L.off[k] = o;

@@ -71,8 +71,8 @@ static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned se
 	qemu::launch(D.n_images, 32, QOI_FCHAIN_SMEM, [&]() { qoifdec::fchain_kernel(F); }, seed);
 	qemu::launch(gs, QOI_FDEC_THREADS, 0, [&]() { qoifdec::fzero_kernel(F); }, seed);
 	for (int r = 0; r < rounds; r++) {
-		if (D.out_channels == 4) qemu::launch(gs, QOI_FDEC_THREADS, 64 * QOI_FDEC_THREADS * 4, [&]() { qoifdec::fdecode_kernel<4>(F); }, seed);
-		else qemu::launch(gs, QOI_FDEC_THREADS, 64 * QOI_FDEC_THREADS * 4, [&]() { qoifdec::fdecode_kernel<3>(F); }, seed);
+		if (D.out_channels == 4) qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { qoifdec::fdecode_kernel<4>(F); }, seed);
+		else qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { qoifdec::fdecode_kernel<3>(F); }, seed);
 		if (r + 1 < rounds) qemu::launch(D.n_images, 32, 0, [&]() { qoifdec::fverify_kernel(F); }, seed);
 		if (getenv("QOI_EMU_FTRACE")) {
 			for (uint32_t i = 0; i < D.n_images; i++) {
