@@ -31,15 +31,17 @@
 #pragma once
 #include "qoi_common.h"
 #include "qoi_dev.cuh"
+#include "qoi_dec.cuh" /* the chunked stream reader (qoidec::Reader) */
 
 namespace qoifdec {
 using namespace qoidev;
 
 #define QOI_FSEG_BYTES 4096
-#define QOI_FDEC_ROUNDS 6 /* speculative decode launches (with a verify pass between them) before the exact fix-up */
+#define QOI_FDEC_ROUNDS 10 /* speculative decode launches (with a verify pass between them) before the exact fix-up */
 #define QOI_FDEC_THREADS 128
+#define QOI_FFIX_SMEM ((64 + QOI_FSEG_BYTES / 4 + 8) * 4) /* index[], one staged segment */
 #define QOI_FCHAIN_SMEM ((32 * 5 + 32 * 2 + 32 + 32 + 4) * 4)
-#define QOI_FDEC_SMEM ((64 + 32) * QOI_FDEC_THREADS * 4) /* per lane: index[64] + 64 source half-words */
+#define QOI_FDEC_SMEM ((64 + 32 + QOI_DEC_RING_WORDS) * QOI_FDEC_THREADS * 4) /* per lane: index[64], 64 source half-words, stream ring */
 /* Where a channel group (r,g,b or alpha) of a colour came from, as tracked by the speculative decode: values 0..63 = slot
    of the guessed index[] that was read before the segment wrote it (r,g,b possibly plus DIFF/LUMA deltas) */
 #define QOI_SRC_IN 64u    /* the colour that entered the segment (r,g,b possibly plus deltas) */
@@ -70,9 +72,13 @@ struct QoiFState {
 	                             bits 8-15 / 16-23: QOI_SRC_* of the outgoing colour's r,g,b / alpha */
 	uint8_t *redo;            /* [segs] decode (again) in the next fdecode launch */
 	/* verification */
-	uint32_t *verified;       /* [n_images] segments [0, verified) are final */
-	uint32_t *ex_px;          /* [n_images] exact colour after the verified prefix */
-	uint32_t *ex_tab;         /* [n_images][64] exact index[] after the verified prefix */
+	uint32_t *redo_list;      /* [segs] the segments to decode in the next fdecode launch (rounds >= 1), in no particular order */
+	uint32_t *n_redo;         /* [64] length of that list per round */
+	/* double buffered by pass parity: a launch reads [fsel_rd], the verify pass writes [fsel_wr] */
+	uint32_t *verified;       /* [2][n_images] segments [0, verified) are final */
+	uint32_t *ex_px;          /* [2][n_images] exact colour after the verified prefix */
+	uint32_t *ex_tab;         /* [2][n_images][64] exact index[] after the verified prefix */
+	uint32_t *bstate;         /* [2][n_images][QOI_FVER_CHUNKS][65] chain state at the start of each verify range */
 };
 
 struct QoiFParams {
@@ -84,8 +90,21 @@ struct QoiFParams {
 	uint32_t n_images;
 	uint32_t n_segs; /* capacity over all images */
 	int32_t out_channels;
+	uint32_t round; /* speculative round of this launch (0 = every live segment, from the reference's initial state) */
 	QoiFState f;
 };
+
+#define QOI_FVER_CHUNKS 8  /* verify warps (ranges) per stream */
+#define QOI_FVER_BWORDS 65 /* index[64] + colour */
+#ifdef QOI_EMU /* tests/emu: small streams must be able to exercise the multi-range path */
+static inline uint32_t qoi_fver_min_range() { const char *e = getenv("QOI_EMU_FVER_MIN_RANGE"); return e ? (uint32_t)atoi(e) : 1024u; }
+#define QOI_FVER_MIN_RANGE qoi_fver_min_range()
+#else
+#define QOI_FVER_MIN_RANGE 1024u /* segments per range at least */
+#endif
+/* which copy of the pass-buffered state (verified, ex_px, ex_tab, bstate) a launch reads / the verify pass writes */
+__device__ __forceinline__ uint32_t fsel_rd(const QoiFParams &P) { return (P.round + 1u) & 1u; }
+__device__ __forceinline__ uint32_t fsel_wr(const QoiFParams &P) { return P.round & 1u; }
 
 __device__ __forceinline__ uint32_t add_bytes(uint32_t a, uint32_t b) {
 	return ((a & 0x7F7F7F7Fu) + (b & 0x7F7F7F7Fu)) ^ ((a ^ b) & 0x80808080u);
@@ -249,16 +268,19 @@ __global__ void __launch_bounds__(32) fchain_kernel(const QoiFParams P) {
 	}
 	if (lane == 0) {
 		P.f.n_live[img] = s_state[2];
-		P.f.verified[img] = 0;
-		P.f.ex_px[img] = 0xFF000000u;
+		P.f.verified[img] = P.f.verified[P.n_images + img] = 0; /* both parities of the pass-buffered state */
+		P.f.ex_px[img] = P.f.ex_px[P.n_images + img] = 0xFF000000u;
 	}
 	P.f.ex_tab[(size_t)img * 64 + lane] = 0u;
 	P.f.ex_tab[(size_t)img * 64 + lane + 32] = 0u;
+	P.f.ex_tab[((size_t)P.n_images + img) * 64 + lane] = 0u;
+	P.f.ex_tab[((size_t)P.n_images + img) * 64 + lane + 32] = 0u;
 }
 
 /* round-0 guess of index[]: zeros (qoi.h:533) */
 __global__ void __launch_bounds__(QOI_FDEC_THREADS) fzero_kernel(const QoiFParams P) {
 	const uint32_t g = blockIdx.x * QOI_FDEC_THREADS + threadIdx.x;
+	if (g < 64u) P.f.n_redo[g] = 0u;
 	if (g >= P.n_segs) return;
 	const uint32_t img = seg_image(P, g);
 	if (g - P.f.seg_base[img] >= P.f.n_live[img]) return;
@@ -272,12 +294,18 @@ template <int OUT_CH>
 __global__ void __launch_bounds__(QOI_FDEC_THREADS) fdecode_kernel(const QoiFParams P) {
 	QOI_DYNAMIC_SMEM(smem);
 	uint32_t *tab = (uint32_t *)smem + threadIdx.x; /* tab[slot * QOI_FDEC_THREADS] */
-	const uint32_t g = blockIdx.x * QOI_FDEC_THREADS + threadIdx.x;
+	/* round 0: lane k takes segment k; later rounds: the k-th entry of the list the last verify pass left, so that the
+	   few segments that are decoded again fill whole warps */
+	uint32_t g = blockIdx.x * QOI_FDEC_THREADS + threadIdx.x;
+	if (P.round > 0u) {
+		if (g >= P.f.n_redo[P.round]) return;
+		g = P.f.redo_list[g];
+	}
 	if (g >= P.n_segs) return;
 	const uint32_t img = seg_image(P, g);
 	const uint32_t j = g - P.f.seg_base[img];
 	const uint32_t live = P.f.n_live[img];
-	if (j >= live || j < P.f.verified[img] || !P.f.redo[g]) return;
+	if (j >= live || j < P.f.verified[fsel_rd(P) * P.n_images + img] || !P.f.redo[g]) return;
 	const QoiImgMeta m = P.imgs[img];
 	const uint8_t *s = P.streams + m.stream_off;
 	const int32_t stop = P.lens[img] - QOI_END_BYTES;
@@ -296,63 +324,136 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fdecode_kernel(const QoiFPar
 	/* Per slot: where the value it holds now came from (QOI_SRC_*; r,g,b in the low byte, alpha in the high byte,
 	   0xFFFF = not written by this segment); two slots to a word, words interleaved over the threads (conflict free).
 	   `src` is the same for the current colour. */
-	uint16_t *sst = (uint16_t *)((uint32_t *)smem + 64 * QOI_FDEC_THREADS + threadIdx.x); /* sst[(slot >> 1) * 2 * THREADS + (slot & 1)] */
+	constexpr int B = QOI_FDEC_THREADS;
+	uint16_t *sst = (uint16_t *)((uint32_t *)smem + 64 * B + threadIdx.x); /* sst[(slot >> 1) * 2 * B + (slot & 1)] */
+	uint32_t *ring = (uint32_t *)smem + (64 + 32) * B + threadIdx.x;        /* ring[word * B] */
 #pragma unroll
-	for (int k = 0; k < 32; k++) *(uint32_t *)(sst + k * 2 * QOI_FDEC_THREADS) = 0xFFFFFFFFu;
+	for (int k = 0; k < 32; k++) *(uint32_t *)(sst + k * 2 * B) = 0xFFFFFFFFu;
 	uint64_t rbw = 0;
 	uint32_t src = QOI_SRC_IN | (QOI_SRC_IN << 8);
 	bool dep_rgb = false, dep_a = false;
-	int32_t p = begin + (int32_t)P.f.entry[g];
+	const int32_t p0 = begin + (int32_t)P.f.entry[g];
 	uint32_t run = 0;
-	uint8_t *o = P.out + m.dec_off + (size_t)px_begin * OUT_CH;
-	for (uint32_t i = px_begin; i < px_end; i++) {
-		if (run > 0) {
-			run--;
-		} else if (p < end) {
-			const uint32_t tag = s[p++];
-			if (tag == 0xFEu) { /* qoi.h:547-551: r,g,b replaced, alpha kept */
-				px = (px & 0xFF000000u) | (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16);
-				p += 3;
-				src = (src & 0xFF00u) | QOI_SRC_OWN;
-			} else if (tag == 0xFFu) { /* qoi.h:552-557 */
-				px = (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
-				p += 4;
-				src = QOI_SRC_OWN | (QOI_SRC_OWN << 8);
-			} else if ((tag & 0xC0u) == 0x00u) { /* qoi.h:558-560 */
-				const uint32_t st = sst[(tag >> 1) * 2 * QOI_FDEC_THREADS + (tag & 1u)];
-				if (st == 0xFFFFu) {
-					rbw |= 1ull << tag;
-					src = tag | (tag << 8);
-				} else {
-					src = st;
-				}
-				px = tab[tag * QOI_FDEC_THREADS];
-			} else if ((tag & 0xC0u) == 0x40u) { /* qoi.h:561-565 */
-				const uint32_t sel = ((tag >> 4) & 3u) | (((tag >> 2) & 3u) << 4) | ((tag & 3u) << 8) | 0x4000u;
-				px = add_bytes(px, __byte_perm(0x0100FFFEu, 0u, sel));
-			} else if ((tag & 0xC0u) == 0x80u) { /* qoi.h:566-572 */
-				const uint32_t b2 = s[p++];
-				const uint32_t vg = (tag & 0x3Fu) + 224u;
-				const uint32_t rb = vg + 248u;
-				px = add_bytes(px, ((rb + ((b2 >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((rb + (b2 & 0xFu)) & 0xFFu) << 16));
-			} else { /* qoi.h:573-575 */
-				run = tag & 0x3Fu;
+
+	/* stream bytes: the reader of the indexed decoder (qoi_dec.cuh) -- 32-byte chunks one ahead, a per-lane ring in
+	   shared memory, a 64-bit window; an op that straddles `end` is read to its last byte (it lies inside the stream:
+	   the end marker follows `stop`), words outside the stream read as zero and are never touched */
+	qoidec::Reader rd;
+	{
+		const uintptr_t a = (uintptr_t)(s + p0);
+		rd.lo = (uintptr_t)s & ~(uintptr_t)3;
+		rd.hi = ((uintptr_t)s + (uintptr_t)P.lens[img] + 3u) & ~(uintptr_t)3;
+		rd.gp = (const uint4 *)(a & ~(uintptr_t)31);
+		rd.p = p0;
+#pragma unroll
+		for (int half = 0; half < 2; half++) {
+			qoidec::load_chunk(rd);
+			uint32_t *r = ring + half * 8 * B;
+			r[0 * B] = rd.pa.x; r[1 * B] = rd.pa.y; r[2 * B] = rd.pa.z; r[3 * B] = rd.pa.w;
+			r[4 * B] = rd.pb.x; r[5 * B] = rd.pb.y; r[6 * B] = rd.pb.z; r[7 * B] = rd.pb.w;
+		}
+		qoidec::load_chunk(rd);
+		rd.wi = (uint32_t)((a & 31u) >> 2);
+		rd.buf = 0;
+		rd.avail = 0;
+	}
+	auto next_word = [&]() -> uint32_t {
+		const uint32_t w = ring[(rd.wi & (QOI_DEC_RING_WORDS - 1)) * B];
+		rd.wi++;
+		if ((rd.wi & 7u) == 0u) {
+			uint32_t *r = ring + ((rd.wi - 8u) & (QOI_DEC_RING_WORDS - 1)) * B;
+			r[0 * B] = rd.pa.x; r[1 * B] = rd.pa.y; r[2 * B] = rd.pa.z; r[3 * B] = rd.pa.w;
+			r[4 * B] = rd.pb.x; r[5 * B] = rd.pb.y; r[6 * B] = rd.pb.z; r[7 * B] = rd.pb.w;
+			qoidec::load_chunk(rd);
+		}
+		return w;
+	};
+	{
+		const uint32_t mis = (uint32_t)((uintptr_t)(s + p0) & 3u);
+		rd.buf = (uint64_t)(next_word() >> (8u * mis));
+		rd.avail = 4u - mis;
+	}
+
+	/* one pixel (qoi.h:541-578), evaluated branch-free like qoi_decode_kernel, plus the bookkeeping of where the
+	   colour came from */
+	auto step = [&]() -> uint32_t {
+		const bool parse = (run == 0u) && (rd.p < end);
+		if (parse && rd.avail < 5u) {
+			rd.buf |= (uint64_t)next_word() << (8u * rd.avail);
+			rd.avail += 4u;
+			if (rd.avail < 5u) {
+				rd.buf |= (uint64_t)next_word() << (8u * rd.avail);
+				rd.avail += 4u;
 			}
-			dep_rgb = dep_rgb || (src & 0xFFu) == QOI_SRC_IN;
-			dep_a = dep_a || (src >> 8) == QOI_SRC_IN;
+		}
+		const uint32_t tag = (uint32_t)rd.buf & 0xFFu;
+		const uint32_t pay = (uint32_t)(rd.buf >> 8);
+		const uint32_t top = tag >> 6, t6 = tag & 63u;
+		const bool is_rgb = tag == 0xFEu, is_rgba = tag == 0xFFu;               /* qoi.h:547-557 */
+		const uint32_t idxv = tab[t6 * B];                                       /* qoi.h:558-560 */
+		const uint32_t ist = sst[(t6 >> 1) * 2 * B + (t6 & 1u)];                 /* ... and where that slot's value came from */
+		const uint32_t sel = ((tag >> 4) & 3u) | (((tag >> 2) & 3u) << 4) | ((tag & 3u) << 8) | 0x4000u;
+		const uint32_t dadd = __byte_perm(0x0100FFFEu, 0u, sel);                 /* qoi.h:561-565 */
+		const uint32_t vg = t6 + 224u;
+		const uint32_t rb = vg + 248u;
+		const uint32_t ladd = ((rb + ((pay >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((rb + (pay & 0xFu)) & 0xFFu) << 16); /* qoi.h:566-572 */
+		const uint32_t rel = add_bytes(px, top == 1u ? dadd : ladd);
+		uint32_t npx = top == 0u ? idxv : rel;
+		npx = top == 3u ? px : npx;                                              /* qoi.h:573-575 */
+		npx = is_rgb ? ((px & 0xFF000000u) | (pay & 0x00FFFFFFu)) : npx;
+		npx = is_rgba ? pay : npx;
+		const bool fresh = top == 0u && ist == 0xFFFFu; /* INDEX of a slot this segment has not written: the guess is used */
+		uint32_t nsrc = top == 0u ? (fresh ? (t6 | (t6 << 8)) : ist) : src;
+		nsrc = is_rgb ? ((src & 0xFF00u) | QOI_SRC_OWN) : nsrc; /* r,g,b replaced, alpha kept */
+		nsrc = is_rgba ? (QOI_SRC_OWN | (QOI_SRC_OWN << 8)) : nsrc;
+		const uint32_t len = is_rgba ? 5u : (is_rgb ? 4u : (top == 2u ? 2u : 1u));
+		const uint32_t nrun = (top == 3u && tag < 0xFEu) ? t6 : 0u;
+		if (parse) {
+			px = npx;
+			src = nsrc;
+			if (fresh) rbw |= 1ull << t6;
+			rd.buf >>= 8u * len;
+			rd.avail -= len;
+			rd.p += (int32_t)len;
 			const uint32_t h = qoi_slot(px);
-			tab[h * QOI_FDEC_THREADS] = px; /* qoi.h:577 */
-			sst[(h >> 1) * 2 * QOI_FDEC_THREADS + (h & 1u)] = (uint16_t)src;
-		} else { /* stream exhausted: the pixel repeats the current colour */
-			dep_rgb = dep_rgb || (src & 0xFFu) == QOI_SRC_IN;
-			dep_a = dep_a || (src >> 8) == QOI_SRC_IN;
+			tab[h * B] = px; /* qoi.h:577 */
+			sst[(h >> 1) * 2 * B + (h & 1u)] = (uint16_t)src;
+			run = nrun;
+		} else if (run > 0u) {
+			run--;
 		}
-		if (OUT_CH == 4) {
-			*(uint32_t *)o = px;
-		} else {
-			o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
+		/* every pixel that leaves while a channel still is the incoming one makes the segment depend on it (also the
+		   pixels a truncated stream leaves over, qoi.h:544) */
+		dep_rgb = dep_rgb || (src & 0xFFu) == QOI_SRC_IN;
+		dep_a = dep_a || (src >> 8) == QOI_SRC_IN;
+		return px;
+	};
+
+	uint8_t *obase = P.out + m.dec_off;
+	uint32_t i = px_begin;
+	if (OUT_CH == 4) {
+		uint32_t *o32 = (uint32_t *)obase;
+		const bool vec_ok = ((uintptr_t)obase & 15u) == 0;
+		while (i < px_end && (!vec_ok || (i & 3u))) {
+			o32[i] = step();
+			i++;
 		}
-		o += OUT_CH;
+		while (i + 4 <= px_end) {
+			const uint32_t a = step(), b = step(), c = step(), d = step();
+			*(uint4 *)(o32 + i) = make_uint4(a, b, c, d);
+			i += 4;
+		}
+		while (i < px_end) {
+			o32[i] = step();
+			i++;
+		}
+	} else {
+		while (i < px_end) {
+			const uint32_t a = step();
+			uint8_t *o = obase + (size_t)i * 3;
+			o[0] = (uint8_t)a; o[1] = (uint8_t)(a >> 8); o[2] = (uint8_t)(a >> 16);
+			i++;
+		}
 	}
 	uint64_t written = 0;
 	{
@@ -377,8 +478,9 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fdecode_kernel(const QoiFPar
 	}
 }
 
-/* what the in-order walks (fverify_kernel, ffix_kernel) need to know about one segment; loaded a few segments ahead of
-   use because none of it depends on the chain state -- the walk itself is then shared-memory / register work only */
+/* What the in-order walks (fverify_kernel, ffix_kernel) need to know about one segment.  None of it depends on the
+   chain state, so the records are streamed QOI_FWALK_RING segments ahead of the walk into a ring in shared memory
+   with per-thread asynchronous copies; the walk itself is then shared-memory / register work only. */
 struct SegRec {
 	uint64_t rbw, wr;
 	uint32_t s0, s1; /* QOI_SRC_* pairs of slots lane and lane + 32 */
@@ -400,39 +502,108 @@ __device__ __forceinline__ void load_rec(const QoiFParams &P, uint32_t g, uint32
 	r.o1 = P.f.out_tab[(size_t)g * 64 + lane + 32];
 }
 
-/* ------------------------------------------------------------------ 3. verify + re-guess: one warp per stream */
+/* Calls body(j, record of segment j) for j = first .. last-1 in order.  Two register batches: while one is walked the
+   other is in flight (no copies between them: a register move would wait for its load).  Measured alternatives
+   (round 1, B200): records packed to six words per lane and eight segments per batch, and a 16-entry cp.async ring in
+   shared memory, were 3-5x SLOWER than this plain form -- see DESIGN.md section 7. */
+template <typename Body>
+__device__ __forceinline__ void walk_records(const QoiFParams &P, uint32_t base, uint32_t first, uint32_t last, uint32_t lane, Body body) {
+	constexpr uint32_t B = QOI_FWALK_BATCH;
+	SegRec ra[B], rb[B];
+#pragma unroll
+	for (uint32_t b = 0; b < B; b++)
+		if (first + b < last) load_rec(P, base + first + b, lane, ra[b]);
+	uint32_t j0 = first;
+	while (j0 < last) {
+#pragma unroll
+		for (uint32_t b = 0; b < B; b++)
+			if (j0 + B + b < last) load_rec(P, base + j0 + B + b, lane, rb[b]);
+#pragma unroll
+		for (uint32_t b = 0; b < B; b++)
+			if (j0 + b < last) body(j0 + b, ra[b]);
+		j0 += B;
+		if (j0 >= last) break;
+#pragma unroll
+		for (uint32_t b = 0; b < B; b++)
+			if (j0 + B + b < last) load_rec(P, base + j0 + B + b, lane, ra[b]);
+#pragma unroll
+		for (uint32_t b = 0; b < B; b++)
+			if (j0 + b < last) body(j0 + b, rb[b]);
+		j0 += B;
+	}
+}
+
+/* ------------------------------------------------------------------ 3. verify + re-guess: QOI_FVER_CHUNKS warps per stream */
+/* The live segments of a stream are cut into QOI_FVER_CHUNKS equal ranges, one warp each.  The warp whose range holds
+   the first unverified segment starts there with the EXACT state and is the only one that can verify; the warps of
+   the ranges behind it start at their range with the chain state the previous pass had at that point (bstate) and only
+   produce guesses.  A range start is therefore one pass stale -- just another guess error; exactness never depends on
+   it (the prefix logic and the fix-up do not use it).  All cross-pass state is double buffered by pass parity (a pass
+   reads what the pass before wrote), so no warp reads something another warp of the same launch writes. */
+
 __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
-	const uint32_t img = blockIdx.x;
+	const uint32_t img = blockIdx.x / QOI_FVER_CHUNKS, chunk = blockIdx.x % QOI_FVER_CHUNKS;
 	const uint32_t lane = threadIdx.x;
 	if (img >= P.n_images) return;
+	const uint32_t rd = fsel_rd(P) * P.n_images + img, wr = fsel_wr(P) * P.n_images + img;
 	const uint32_t live = P.f.n_live[img];
-	uint32_t ver = P.f.verified[img];
-	if (ver >= live) return;
+	uint32_t ver = P.f.verified[rd];
+	/* ranges only where the walk is long: content whose index[] is stable (UI graphics: few, long segments) converges
+	   best with one in-order walk, and there it is short anyway */
+	const uint32_t nch = live / QOI_FVER_MIN_RANGE < 1u ? 1u : (live / QOI_FVER_MIN_RANGE > QOI_FVER_CHUNKS ? QOI_FVER_CHUNKS : live / QOI_FVER_MIN_RANGE);
+	if (chunk >= nch) return;
+	const uint32_t lo = (uint32_t)(((uint64_t)live * chunk) / nch), hi = (uint32_t)(((uint64_t)live * (chunk + 1u)) / nch);
+	const bool owner = ver < live ? (ver >= lo && ver < hi) : (chunk == 0u); /* of the exact state */
+	if (owner && ver >= live) { /* nothing left: carry the state over to this pass's buffer */
+		P.f.ex_tab[(size_t)wr * 64 + lane] = P.f.ex_tab[(size_t)rd * 64 + lane];
+		P.f.ex_tab[(size_t)wr * 64 + lane + 32] = P.f.ex_tab[(size_t)rd * 64 + lane + 32];
+		if (lane == 0) { P.f.ex_px[wr] = P.f.ex_px[rd]; P.f.verified[wr] = ver; }
+		return;
+	}
+	if (ver >= live || hi <= ver || lo >= hi) return; /* verified range, or empty range */
 	const uint32_t base = P.f.seg_base[img];
 	/* chain state: lane holds slots lane and lane+32 */
-	uint32_t t0 = P.f.ex_tab[(size_t)img * 64 + lane], t1 = P.f.ex_tab[(size_t)img * 64 + lane + 32];
-	uint32_t px = P.f.ex_px[img];
-	bool exact = true;
-	SegRec recs[QOI_FWALK_BATCH], ahead[QOI_FWALK_BATCH]; /* the batch being walked, the batch in flight */
-#pragma unroll
-	for (int b = 0; b < QOI_FWALK_BATCH; b++)
-		if (ver + b < live) load_rec(P, base + ver + b, lane, recs[b]);
-	for (uint32_t j0 = ver; j0 < live; j0 += QOI_FWALK_BATCH) {
-#pragma unroll
-		for (int b = 0; b < QOI_FWALK_BATCH; b++)
-			if (j0 + QOI_FWALK_BATCH + b < live) load_rec(P, base + j0 + QOI_FWALK_BATCH + b, lane, ahead[b]);
-#pragma unroll
-		for (int b = 0; b < QOI_FWALK_BATCH; b++) {
-			const uint32_t j = j0 + b;
-			if (j >= live) break;
+	uint32_t t0, t1, px;
+	bool exact = owner;
+	uint32_t first;
+	if (owner) {
+		first = ver;
+		t0 = P.f.ex_tab[(size_t)rd * 64 + lane];
+		t1 = P.f.ex_tab[(size_t)rd * 64 + lane + 32];
+		px = P.f.ex_px[rd];
+		P.f.ex_tab[(size_t)wr * 64 + lane] = t0; /* stays the exact state if nothing more can be verified */
+		P.f.ex_tab[(size_t)wr * 64 + lane + 32] = t1;
+		if (lane == 0) P.f.ex_px[wr] = px;
+	} else {
+		first = lo;
+		if (P.round == 0u) {
+			/* No earlier pass.  The state must not AGREE with the round-0 guess (zeros, opaque black) by accident, or the
+			   garbage a segment decoded from that guess would be trusted -- e.g. alpha 0 from an INDEX of an empty slot,
+			   which nothing in an opaque image ever replaces.  0xFFFFFFFF cannot be the content of any slot but 38 (a
+			   value sits in the slot it hashes to); opaque alpha is the prior that survives. */
+			t0 = t1 = 0xFFFFFFFFu;
+			px = 0xFF7F7F7Fu;
+		} else {
+			const uint32_t *bs = P.f.bstate + ((size_t)rd * QOI_FVER_CHUNKS + chunk) * QOI_FVER_BWORDS;
+			t0 = bs[lane];
+			t1 = bs[lane + 32];
+			px = bs[64];
+		}
+	}
+	{
+		auto body = [&](uint32_t j, const SegRec &r) {
 			const uint32_t g = base + j;
-			const SegRec &r = recs[b];
 			const uint32_t dep = r.dep, g_px = r.g_px, o_px = r.o_px;
 			/* does the guess this segment was decoded with agree with the chain state on everything it used? */
 			const uint32_t pmask = ((dep & 1u) ? 0x00FFFFFFu : 0u) | ((dep & 2u) ? 0xFF000000u : 0u);
 			/* which slots of the guess equal the chain state */
 			const uint64_t agree = (uint64_t)__ballot_sync(QOI_FULL_MASK, r.g0 == t0) | ((uint64_t)__ballot_sync(QOI_FULL_MASK, r.g1 == t1) << 32);
 			const bool differs = (r.rbw & ~agree) != 0ull || ((g_px ^ px) & pmask) != 0u;
+#ifdef QOI_EMU_FDEBUG /* tests/emu only: why a segment's guess was rejected */
+			if (lane == 0 && getenv("QOI_EMU_FDEBUG"))
+				fprintf(stderr, "  pass %u chunk %u seg %u %s differs=%d px %08x guess %08x pmask %08x badslots %016llx\n", P.round, chunk, j,
+				        exact ? "EXACT" : "guess", (int)differs, px, g_px, pmask, (unsigned long long)(r.rbw & ~agree));
+#endif
 			uint64_t apply = r.wr;
 			if (differs) {
 				/* new guess for this segment = the chain state (the exact state while `exact` still holds) */
@@ -441,6 +612,7 @@ __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
 				if (lane == 0) {
 					P.f.in_px[g] = px;
 					P.f.redo[g] = 1;
+					P.f.redo_list[atomicAdd(&P.f.n_redo[P.round + 1u], 1u)] = g;
 				}
 				if (exact) {
 					exact = false;
@@ -481,15 +653,20 @@ __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
 			if ((apply >> lane) & 1ull) t0 = r.o0;
 			if ((apply >> (lane + 32)) & 1ull) t1 = r.o1;
 			if (exact) { /* remember the exact state after the verified prefix (the fix-up and the next round start here) */
-				P.f.ex_tab[(size_t)img * 64 + lane] = t0;
-				P.f.ex_tab[(size_t)img * 64 + lane + 32] = t1;
-				if (lane == 0) P.f.ex_px[img] = px;
+				P.f.ex_tab[(size_t)wr * 64 + lane] = t0;
+				P.f.ex_tab[(size_t)wr * 64 + lane + 32] = t1;
+				if (lane == 0) P.f.ex_px[wr] = px;
 			}
-		}
-#pragma unroll
-		for (int b = 0; b < QOI_FWALK_BATCH; b++) recs[b] = ahead[b];
+		};
+		walk_records(P, base, first, hi, lane, body);
 	}
-	if (lane == 0) P.f.verified[img] = ver;
+	if (owner && lane == 0) P.f.verified[wr] = ver;
+	if (chunk + 1u < nch) { /* where the next range starts in the next pass */
+		uint32_t *bs = P.f.bstate + ((size_t)wr * QOI_FVER_CHUNKS + chunk + 1u) * QOI_FVER_BWORDS;
+		bs[lane] = t0;
+		bs[lane + 32] = t1;
+		if (lane == 0) bs[64] = px;
+	}
 }
 
 /* ------------------------------------------------------------------ 4. exact fix-up: one warp per stream */
@@ -501,34 +678,26 @@ template <int OUT_CH>
 __global__ void __launch_bounds__(32) ffix_kernel(const QoiFParams P) {
 	QOI_DYNAMIC_SMEM(smem);
 	uint32_t *tab = (uint32_t *)smem; /* exact index[] */
+	uint32_t *stage = tab + 64;       /* one segment of stream words (QOI_FFIX_SMEM) */
 	const uint32_t img = blockIdx.x;
 	const uint32_t lane = threadIdx.x;
 	if (img >= P.n_images) return;
 	const uint32_t live = P.f.n_live[img];
-	const uint32_t ver = P.f.verified[img];
+	const uint32_t rd = fsel_rd(P) * P.n_images + img;
+	const uint32_t ver = P.f.verified[rd];
 	if (ver >= live) return; /* everything verified (also: rejected or empty stream) */
 	const QoiImgMeta m = P.imgs[img];
 	const uint8_t *s = P.streams + m.stream_off;
 	const int32_t stop = P.lens[img] - QOI_END_BYTES;
+	const uintptr_t s_lo = (uintptr_t)s & ~(uintptr_t)3, s_hi = ((uintptr_t)s + (uintptr_t)P.lens[img] + 3u) & ~(uintptr_t)3;
 	const uint32_t base = P.f.seg_base[img];
-	tab[lane] = P.f.ex_tab[(size_t)img * 64 + lane];
-	tab[lane + 32] = P.f.ex_tab[(size_t)img * 64 + lane + 32];
-	uint32_t px = P.f.ex_px[img];
+	tab[lane] = P.f.ex_tab[(size_t)rd * 64 + lane];
+	tab[lane + 32] = P.f.ex_tab[(size_t)rd * 64 + lane + 32];
+	uint32_t px = P.f.ex_px[rd];
 	__syncwarp();
-	SegRec recs[QOI_FWALK_BATCH], ahead[QOI_FWALK_BATCH];
-#pragma unroll
-	for (int b = 0; b < QOI_FWALK_BATCH; b++)
-		if (ver + b < live) load_rec(P, base + ver + b, lane, recs[b]);
-	for (uint32_t j0 = ver; j0 < live; j0 += QOI_FWALK_BATCH) {
-#pragma unroll
-	for (int b = 0; b < QOI_FWALK_BATCH; b++)
-		if (j0 + QOI_FWALK_BATCH + b < live) load_rec(P, base + j0 + QOI_FWALK_BATCH + b, lane, ahead[b]);
-#pragma unroll
-	for (int b = 0; b < QOI_FWALK_BATCH; b++) {
-		const uint32_t j = j0 + b;
-		if (j >= live) break;
+	{
+	auto body = [&](uint32_t j, const SegRec &r) {
 		const uint32_t g = base + j;
-		const SegRec &r = recs[b];
 		const uint32_t dep = r.dep, g_px = r.g_px;
 		const uint32_t pmask = ((dep & 1u) ? 0x00FFFFFFu : 0u) | ((dep & 2u) ? 0xFF000000u : 0u);
 		bool bad = ((r.rbw >> lane) & 1ull) && r.g0 != tab[lane];
@@ -539,55 +708,67 @@ __global__ void __launch_bounds__(32) ffix_kernel(const QoiFParams P) {
 			px = r.o_px;
 			if ((r.wr >> lane) & 1ull) tab[lane] = r.o0;
 			if ((r.wr >> (lane + 32)) & 1ull) tab[lane + 32] = r.o1;
-		} else if (lane == 0) {
+		} else {
 			const int32_t begin = QOI_HEADER_BYTES + (int32_t)j * QOI_FSEG_BYTES;
 			const int32_t end = begin + QOI_FSEG_BYTES < stop ? begin + QOI_FSEG_BYTES : stop;
-			const uint32_t px_begin = P.f.px_start[g];
-			const uint32_t px_end = (j + 1 < live) ? P.f.px_start[g + 1] : m.npx;
-			int32_t p = begin + (int32_t)P.f.entry[g];
-			uint32_t run = 0;
-			uint8_t *o = P.out + m.dec_off + (size_t)px_begin * OUT_CH;
-			for (uint32_t i = px_begin; i < px_end; i++) {
-				if (run > 0) {
-					run--;
-				} else if (p < end) {
-					const uint32_t tag = s[p++];
-					if (tag == 0xFEu) {
-						px = (px & 0xFF000000u) | (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16);
-						p += 3;
-					} else if (tag == 0xFFu) {
-						px = (uint32_t)s[p] | ((uint32_t)s[p + 1] << 8) | ((uint32_t)s[p + 2] << 16) | ((uint32_t)s[p + 3] << 24);
-						p += 4;
-					} else if ((tag & 0xC0u) == 0x00u) {
-						px = tab[tag];
-					} else if ((tag & 0xC0u) == 0x40u) {
-						const uint32_t sel = ((tag >> 4) & 3u) | (((tag >> 2) & 3u) << 4) | ((tag & 3u) << 8) | 0x4000u;
-						px = add_bytes(px, __byte_perm(0x0100FFFEu, 0u, sel));
-					} else if ((tag & 0xC0u) == 0x80u) {
-						const uint32_t b2 = s[p++];
-						const uint32_t vg = (tag & 0x3Fu) + 224u;
-						const uint32_t rb = vg + 248u;
-						px = add_bytes(px, ((rb + ((b2 >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((rb + (b2 & 0xFu)) & 0xFFu) << 16));
-					} else {
-						run = tag & 0x3Fu;
+			/* all lanes copy the segment's words (and the few bytes an op may reach past `end`) into shared memory,
+			   then lane 0 runs the reference loop on them; words outside the stream are never touched */
+			const uintptr_t w0 = (uintptr_t)(s + begin) & ~(uintptr_t)3;
+			const uintptr_t w1 = ((uintptr_t)(s + end) + 8u + 3u) & ~(uintptr_t)3;
+			const uint32_t nw = (uint32_t)((w1 - w0) >> 2);
+			for (uint32_t k = lane; k < nw; k += 32) {
+				const uintptr_t wa = w0 + 4u * k;
+				stage[k] = (wa >= s_lo && wa + 4 <= s_hi) ? __ldg((const uint32_t *)wa) : 0u;
+			}
+			__syncwarp();
+			if (lane == 0) {
+				const uint8_t *stage_b = (const uint8_t *)stage;
+				const int32_t d = (int32_t)((intptr_t)(uintptr_t)s - (intptr_t)w0); /* stream byte q sits at stage_b[q + d] */
+				const uint32_t px_begin = P.f.px_start[g];
+				const uint32_t px_end = (j + 1 < live) ? P.f.px_start[g + 1] : m.npx;
+				int32_t p = begin + (int32_t)P.f.entry[g];
+				uint32_t run = 0;
+				uint8_t *o = P.out + m.dec_off + (size_t)px_begin * OUT_CH;
+				for (uint32_t i = px_begin; i < px_end; i++) {
+					if (run > 0) {
+						run--;
+					} else if (p < end) {
+						const uint32_t tag = stage_b[(p++) + d];
+						if (tag == 0xFEu) {
+							px = (px & 0xFF000000u) | (uint32_t)stage_b[p + d] | ((uint32_t)stage_b[p + 1 + d] << 8) | ((uint32_t)stage_b[p + 2 + d] << 16);
+							p += 3;
+						} else if (tag == 0xFFu) {
+							px = (uint32_t)stage_b[p + d] | ((uint32_t)stage_b[p + 1 + d] << 8) | ((uint32_t)stage_b[p + 2 + d] << 16) | ((uint32_t)stage_b[p + 3 + d] << 24);
+							p += 4;
+						} else if ((tag & 0xC0u) == 0x00u) {
+							px = tab[tag];
+						} else if ((tag & 0xC0u) == 0x40u) {
+							const uint32_t sel = ((tag >> 4) & 3u) | (((tag >> 2) & 3u) << 4) | ((tag & 3u) << 8) | 0x4000u;
+							px = add_bytes(px, __byte_perm(0x0100FFFEu, 0u, sel));
+						} else if ((tag & 0xC0u) == 0x80u) {
+							const uint32_t b2 = stage_b[(p++) + d];
+							const uint32_t vg = (tag & 0x3Fu) + 224u;
+							const uint32_t rb = vg + 248u;
+							px = add_bytes(px, ((rb + ((b2 >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((rb + (b2 & 0xFu)) & 0xFFu) << 16));
+						} else {
+							run = tag & 0x3Fu;
+						}
+						tab[qoi_slot(px)] = px;
 					}
-					tab[qoi_slot(px)] = px;
+					if (OUT_CH == 4) {
+						*(uint32_t *)o = px;
+					} else {
+						o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
+					}
+					o += OUT_CH;
 				}
-				if (OUT_CH == 4) {
-					*(uint32_t *)o = px;
-				} else {
-					o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
-				}
-				o += OUT_CH;
 			}
 		}
 		__syncwarp();
 		px = __shfl_sync(QOI_FULL_MASK, px, 0);
+	};
+	walk_records(P, base, ver, live, lane, body);
 	}
-#pragma unroll
-	for (int b = 0; b < QOI_FWALK_BATCH; b++) recs[b] = ahead[b];
-	}
-	if (lane == 0) P.f.verified[img] = live;
 }
 
 /* binds the arrays of a QoiFState onto one allocation laid out by qoi_fstate_layout() (qoi_plan.h) */
@@ -607,9 +788,12 @@ static inline void fstate_bind(QoiFState &f, unsigned char *base, const size_t *
 	f.out_src = (uint16_t *)(base + off[17]);
 	f.dep = (uint32_t *)(base + off[12]);
 	f.redo = (uint8_t *)(base + off[13]);
+	f.redo_list = (uint32_t *)(base + off[18]);
+	f.n_redo = (uint32_t *)(base + off[19]);
 	f.verified = (uint32_t *)(base + off[14]);
 	f.ex_px = (uint32_t *)(base + off[15]);
 	f.ex_tab = (uint32_t *)(base + off[16]);
+	f.bstate = (uint32_t *)(base + off[20]);
 }
 
 }  // namespace qoifdec

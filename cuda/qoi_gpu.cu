@@ -75,6 +75,14 @@ struct qoi_gpu_plan {
 		}                                                                                     \
 	} while (0)
 
+static_assert(QOI_FFIX_SMEM <= 48 * 1024 && QOI_FCHAIN_SMEM <= 48 * 1024 && QOI_FVER_CHUNKS_HOST == QOI_FVER_CHUNKS && QOI_FDEC_ROUNDS < 60, "these kernels are launched without a shared-memory opt-in");
+/* the speculative decoder's blocks need more than the default 48 KB of dynamic shared memory */
+static int fdec_setup(qoi_gpu_ctx *ctx) {
+	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
+	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
+	return QOI_GPU_OK;
+}
+
 template <int CH, bool EXPAND>
 static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
 	using L = qoienc::Layout<CH, EXPAND>;
@@ -126,6 +134,7 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 	int rc = enc_occupancy<4, false>(c, &c->enc_blocks_per_sm[0]);
 	if (!rc) rc = enc_occupancy<4, true>(c, &c->enc_blocks_per_sm[1]);
 	if (!rc) rc = enc_occupancy<3, true>(c, &c->enc_blocks_per_sm[2]);
+	if (!rc) rc = fdec_setup(c);
 	if (rc) {
 		fprintf(stderr, "qoi_gpu: kernel setup failed: %s\n", c->err);
 		cudaStreamDestroy(c->stream);
@@ -261,6 +270,7 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 		if (!p->d_fstate) {
 			p->flayout = qoi_fstate_layout(p->geom);
 			CK(ctx, cudaMalloc(&p->d_fstate, p->flayout.total));
+			CK(ctx, cudaMemset(p->d_fstate, 0, p->flayout.total));
 			CK(ctx, cudaMemcpy(p->d_fstate + p->flayout.off[0], p->flayout.seg_base.data(), p->flayout.seg_base.size() * sizeof(uint32_t),
 			                   cudaMemcpyHostToDevice));
 		}
@@ -280,12 +290,14 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 		qoifdec::fchain_kernel<<<F.n_images, 32, QOI_FCHAIN_SMEM, s>>>(F);
 		qoifdec::fzero_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
 		for (int r = 0; r < QOI_FDEC_ROUNDS; r++) {
+			F.round = (uint32_t)r;
 			if (F.out_channels == 4) qoifdec::fdecode_kernel<4><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
 			else qoifdec::fdecode_kernel<3><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
-			if (r + 1 < QOI_FDEC_ROUNDS) qoifdec::fverify_kernel<<<F.n_images, 32, 0, s>>>(F);
+			if (r + 1 < QOI_FDEC_ROUNDS) qoifdec::fverify_kernel<<<F.n_images * QOI_FVER_CHUNKS, 32, 0, s>>>(F);
 		}
-		if (F.out_channels == 4) qoifdec::ffix_kernel<4><<<F.n_images, 32, 64 * 4, s>>>(F);
-		else qoifdec::ffix_kernel<3><<<F.n_images, 32, 64 * 4, s>>>(F);
+		F.round = QOI_FDEC_ROUNDS - 1; /* reads what the last verify pass wrote */
+		if (F.out_channels == 4) qoifdec::ffix_kernel<4><<<F.n_images, 32, QOI_FFIX_SMEM, s>>>(F);
+		else qoifdec::ffix_kernel<3><<<F.n_images, 32, QOI_FFIX_SMEM, s>>>(F);
 		g_launches += 3 + 2 * QOI_FDEC_ROUNDS;
 		CK(ctx, cudaGetLastError());
 		return QOI_GPU_OK;

@@ -136,11 +136,12 @@ static inline void qoi_state_bind(QoiTileState &st, unsigned char *base, const Q
 
 /* ------------------------------------------------------------------ foreign-stream decoder scratch (qoi_fdec.cuh) */
 #define QOI_FSEG_BYTES_HOST 4096 /* must equal QOI_FSEG_BYTES */
+#define QOI_FVER_CHUNKS_HOST 8 /* must equal QOI_FVER_CHUNKS */
 
 struct QoiFLayout {
 	std::vector<uint32_t> seg_base; /* [n + 1] */
 	uint32_t n_segs = 0;
-	size_t off[18];
+	size_t off[21];
 	size_t total = 0;
 };
 
@@ -157,9 +158,9 @@ static inline QoiFLayout qoi_fstate_layout(const QoiPlanGeom &g) {
 	L.seg_base[n] = (uint32_t)segs;
 	L.n_segs = (uint32_t)segs;
 	const size_t S = segs, N = n;
-	const size_t sizes[18] = {(N + 1) * 4, S * 20, S * 8, S, S * 4, N * 4, S * 4, S * 256, S * 4, S * 256, S * 8, S * 8, S * 4, S, N * 4, N * 4, N * 256, S * 128};
+	const size_t sizes[21] = {(N + 1) * 4, S * 20, S * 8, S, S * 4, N * 4, S * 4, S * 256, S * 4, S * 256, S * 8, S * 8, S * 4, S, N * 8, N * 8, N * 512, S * 128, S * 4, 256, N * 2 * QOI_FVER_CHUNKS_HOST * 65 * 4};
 	size_t o = 0;
-	for (int k = 0; k < 18; k++) {
+	for (int k = 0; k < 21; k++) {
 		L.off[k] = o;
 		o += (sizes[k] + 255) & ~(size_t)255;
 	}

@@ -70,28 +70,34 @@ static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned se
 	qemu::launch(gs, QOI_FDEC_THREADS, 0, [&]() { qoifdec::fparse_kernel(F); }, seed);
 	qemu::launch(D.n_images, 32, QOI_FCHAIN_SMEM, [&]() { qoifdec::fchain_kernel(F); }, seed);
 	qemu::launch(gs, QOI_FDEC_THREADS, 0, [&]() { qoifdec::fzero_kernel(F); }, seed);
+	int extra = 0;
 	for (int r = 0; r < rounds; r++) {
+		F.round = (uint32_t)r;
 		if (D.out_channels == 4) qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { qoifdec::fdecode_kernel<4>(F); }, seed);
 		else qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { qoifdec::fdecode_kernel<3>(F); }, seed);
-		if (r + 1 < rounds) qemu::launch(D.n_images, 32, 0, [&]() { qoifdec::fverify_kernel(F); }, seed);
+		if (r + 1 < rounds) qemu::launch(D.n_images * QOI_FVER_CHUNKS, 32, 0, [&]() { qoifdec::fverify_kernel(F); }, seed);
 		if (getenv("QOI_EMU_FTRACE")) {
 			for (uint32_t i = 0; i < D.n_images; i++) {
-				fprintf(stderr, "round %d image %u verified %u/%u redo:", r, i, F.f.verified[i], F.f.n_live[i]);
+				fprintf(stderr, "round %d image %u verified %u/%u redo:", r, i, F.f.verified[((uint32_t)r & 1u) * D.n_images + i], F.f.n_live[i]);
 				for (uint32_t j = 0; j < F.f.n_live[i]; j++) if (F.f.redo[F.f.seg_base[i] + j]) fprintf(stderr, " %u", j);
 				fprintf(stderr, "\n");
 			}
 		}
 	}
 	if (getenv("QOI_EMU_FSTATS")) { /* how much is left for the sequential fix-up (an extra verify pass only marks; ffix stays exact) */
-		qemu::launch(D.n_images, 32, 0, [&]() { qoifdec::fverify_kernel(F); }, seed);
+		F.round = (uint32_t)(rounds - 1);
+		qemu::launch(D.n_images * QOI_FVER_CHUNKS, 32, 0, [&]() { qoifdec::fverify_kernel(F); }, seed);
+		extra = 1;
+		const uint32_t sel = (uint32_t)(rounds - 1) & 1u;
 		for (uint32_t i = 0; i < D.n_images; i++) {
 			uint32_t bad = 0;
 			for (uint32_t j = 0; j < F.f.n_live[i]; j++) bad += F.f.redo[F.f.seg_base[i] + j] ? 1 : 0;
-			fprintf(stderr, "image %u: %u live segments, verified prefix %u, %u segments left to the fix-up after %d rounds\n", i, F.f.n_live[i], F.f.verified[i], bad, rounds);
+			fprintf(stderr, "image %u: %u live segments, verified prefix %u, %u segments left to the fix-up after %d rounds\n", i, F.f.n_live[i], F.f.verified[sel * D.n_images + i], bad, rounds);
 		}
 	}
-	if (D.out_channels == 4) qemu::launch(D.n_images, 32, 64 * 4, [&]() { qoifdec::ffix_kernel<4>(F); }, seed);
-	else qemu::launch(D.n_images, 32, 64 * 4, [&]() { qoifdec::ffix_kernel<3>(F); }, seed);
+	F.round = (uint32_t)(rounds - 1 + extra); /* reads what the last verify pass wrote */
+	if (D.out_channels == 4) qemu::launch(D.n_images, 32, QOI_FFIX_SMEM, [&]() { qoifdec::ffix_kernel<4>(F); }, seed);
+	else qemu::launch(D.n_images, 32, QOI_FFIX_SMEM, [&]() { qoifdec::ffix_kernel<3>(F); }, seed);
 }
 
 static int first_diff(const unsigned char *a, const unsigned char *b, size_t n) {

@@ -28,7 +28,8 @@ def run_enc(emu, img, w, h, ch, n, grid, seed, mis):
         f.write(np.ascontiguousarray(img, dtype=np.uint8).tobytes())
         f.flush()
         for lookup in ("walk", "summary"):  # both look-up variants of the encoder (QOI_GPU_LOOKUP)
-            env = dict(os.environ, QOI_GPU_LOOKUP=lookup)
+            # ... and the foreign decoder's verify pass with one range per stream / with several
+            env = dict(os.environ, QOI_GPU_LOOKUP=lookup, QOI_EMU_FVER_MIN_RANGE="1024" if lookup == "walk" else "3")
             r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
                                capture_output=True, text=True, timeout=300, env=env)
             assert r.returncode == 0 and r.stdout.startswith("PASS"), lookup + ": " + r.stdout + r.stderr[-2000:]
@@ -61,12 +62,22 @@ def test_emulated_long_runs(emu, cpu):
 
 def test_emulated_foreign_decode(emu, cpu):
     rng = np.random.default_rng(3)
-    recs = bytearray()
-    n = 40
-    for i in range(n):
-        s = q.foreign_stream(rng, 900, 4, w=30, h=30, truncate=(i % 4 == 0))
-        recs += len(s).to_bytes(4, "little") + s
-    with tempfile.NamedTemporaryFile(suffix=".bin") as f:
-        f.write(bytes(recs)); f.flush()
-        r = subprocess.run([emu, "dec", "30", "30", "4", str(n), "5", f.name], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and r.stdout.startswith("PASS"), r.stdout + r.stderr[-2000:]
+
+    def run(streams, w, h, env_extra):
+        recs = bytearray()
+        for st in streams:
+            recs += len(st).to_bytes(4, "little") + st
+        with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+            f.write(bytes(recs)); f.flush()
+            r = subprocess.run([emu, "dec", str(w), str(h), "4", str(len(streams)), "5", f.name], capture_output=True, text=True,
+                               timeout=300, env=dict(os.environ, **env_extra))
+        assert r.returncode == 0 and r.stdout.startswith("PASS"), str(env_extra) + r.stdout + r.stderr[-2000:]
+
+    small = [q.foreign_stream(rng, 900, 4, w=30, h=30, truncate=(i % 4 == 0)) for i in range(40)]
+    run(small, 30, 30, {})
+    # streams of many segments (random op soup: the speculation rarely holds, the fix-up does the work), with
+    # different numbers of speculative rounds (both parities of the pass-buffered state)
+    big = [q.foreign_stream(rng, 40000, 4, w=200, h=200, truncate=(i == 2)) for i in range(4)]
+    for rounds in ("1", "2", "3", "6", "9"):
+        run(big, 200, 200, {"QOI_EMU_FROUNDS": rounds})
+        run(big, 200, 200, {"QOI_EMU_FROUNDS": rounds, "QOI_EMU_FVER_MIN_RANGE": "2"})  # several verify ranges per stream
