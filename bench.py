@@ -194,6 +194,61 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def c_api_single_image(h_pix, args):
+    """extra.c_api_single_image: the four-function drop-in itself, one image per call (see the note in the result)."""
+    # the four-function drop-in itself, called the way qoibench.c calls qoi.h: one image per call, pageable
+    # host memory, malloc'ed results (qoi_decode decodes a stream as ANY stream: no restart index)
+    import qoi_b200
+    from qoi_b200 import api as _api
+    one = np.ascontiguousarray(h_pix[:W * H * CH])
+    d1 = qoi_b200.Desc(W, H, CH, 0)
+    L = _api.lib()
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    nbytes, d2 = C.c_int(0), qoi_b200.Desc(0, 0, 0, 0)
+
+    def c_encode():
+        p_ = L.qoi_encode(one.ctypes.data, C.byref(d1), C.byref(nbytes))
+        if not p_:
+            raise RuntimeError("qoi_encode returned NULL")
+        return p_
+
+    def c_decode(stream_ptr):
+        q_ = L.qoi_decode(stream_ptr, nbytes.value, C.byref(d2), 4)
+        if not q_:
+            raise RuntimeError("qoi_decode returned NULL")
+        return q_
+
+    sp = c_encode()                          # first calls build the cached plan and its scratch (untimed)
+    libc.free(c_decode(sp))
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        libc.free(sp)
+        sp = c_encode()
+    t1 = time.perf_counter()
+    for _ in range(reps):
+        q = c_decode(sp)
+        if _ + 1 < reps:
+            libc.free(q)
+    t2 = time.perf_counter()
+    back = np.frombuffer(C.string_at(q, W * H * 4), dtype=np.uint8)
+    libc.free(q)
+    libc.free(sp)
+    if not np.array_equal(back, one):
+        raise RuntimeError("C API round trip mismatch")
+    kind1, eb1, db1, _t = load_cpu_codec()
+    k1 = np.empty(W * H * (CH + 1) + 22, dtype=np.uint8)
+    l1 = np.zeros(1, dtype=np.int32)
+    cpu_round_trip(eb1, db1, 1, one, 1, k1, l1, k1.size)
+    te1, td1 = cpu_round_trip(eb1, db1, 1, one, 1, k1, l1, k1.size)
+    c_api = {"image": f"{W}x{H} RGBA {DIST_NAMES[args.dist]}", "qoi_encode_ms": 1e3 * (t1 - t0) / reps,
+             "qoi_decode_ms": 1e3 * (t2 - t1) / reps, "cpu_kind": kind1, "cpu_qoi_encode_ms": 1e3 * te1,
+             "cpu_qoi_decode_ms": 1e3 * td1,
+             "note": "single calls of the reference API, host pointers in and out, copies and the any-stream decoder inside"}
+    return c_api
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -365,57 +420,10 @@ def main():
             cpu_baseline = {"value": px_rank / (te + td) / 1e9, "unit": "Gpx/s", "cores": min(threads, n), "kind": kind,
                             "sample": f"{n} x {W}x{H} RGBA images, one encode+decode pass, OpenMP over images; GPU streams verified identical",
                             "encode_gpx": px_rank / te / 1e9, "decode_gpx": px_rank / td / 1e9}
-        c_api = None
-        if world == 1 and not args.no_cpu:
-            # the four-function drop-in itself, called the way qoibench.c calls qoi.h: one image per call, pageable
-            # host memory, malloc'ed results (qoi_decode decodes a stream as ANY stream: no restart index)
-            one = np.ascontiguousarray(h_pix[:W * H * CH])
-            d1 = qoi_b200.Desc(W, H, CH, 0)
-            from qoi_b200 import api as _api
-            L = _api.lib()
-            libc = C.CDLL(None)
-            libc.free.argtypes = [C.c_void_p]
-            nbytes, d2 = C.c_int(0), qoi_b200.Desc(0, 0, 0, 0)
-
-            def c_encode():
-                p_ = L.qoi_encode(one.ctypes.data, C.byref(d1), C.byref(nbytes))
-                if not p_:
-                    raise SystemExit("qoi_encode returned NULL")
-                return p_
-
-            def c_decode(stream_ptr):
-                q_ = L.qoi_decode(stream_ptr, nbytes.value, C.byref(d2), 4)
-                if not q_:
-                    raise SystemExit("qoi_decode returned NULL")
-                return q_
-
-            sp = c_encode()                          # first calls build the cached plan and its scratch (untimed)
-            libc.free(c_decode(sp))
-            reps = 3
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                libc.free(sp)
-                sp = c_encode()
-            t1 = time.perf_counter()
-            for _ in range(reps):
-                q = c_decode(sp)
-                if _ + 1 < reps:
-                    libc.free(q)
-            t2 = time.perf_counter()
-            back = np.frombuffer(C.string_at(q, W * H * 4), dtype=np.uint8)
-            libc.free(q)
-            libc.free(sp)
-            if not np.array_equal(back, one):
-                raise SystemExit("C API round trip mismatch")
-            kind1, eb1, db1, _t = load_cpu_codec()
-            k1 = np.empty(W * H * (CH + 1) + 22, dtype=np.uint8)
-            l1 = np.zeros(1, dtype=np.int32)
-            cpu_round_trip(eb1, db1, 1, one, 1, k1, l1, k1.size)
-            te1, td1 = cpu_round_trip(eb1, db1, 1, one, 1, k1, l1, k1.size)
-            c_api = {"image": f"{W}x{H} RGBA {DIST_NAMES[args.dist]}", "qoi_encode_ms": 1e3 * (t1 - t0) / reps,
-                     "qoi_decode_ms": 1e3 * (t2 - t1) / reps, "cpu_kind": kind1, "cpu_qoi_encode_ms": 1e3 * te1,
-                     "cpu_qoi_decode_ms": 1e3 * td1,
-                     "note": "single calls of the reference API, host pointers in and out, copies and the any-stream decoder inside"}
+        try:
+            c_api = c_api_single_image(h_pix, args) if (world == 1 and not args.no_cpu) else None
+        except Exception as e:  # the headline line must not depend on this extra
+            c_api = {"error": repr(e)}
         line = {
             "metric": METRIC, "value": value, "unit": "Gpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

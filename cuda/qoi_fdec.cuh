@@ -79,6 +79,8 @@ struct QoiFState {
 	uint32_t *ex_px;          /* [2][n_images] exact colour after the verified prefix */
 	uint32_t *ex_tab;         /* [2][n_images][64] exact index[] after the verified prefix */
 	uint32_t *bstate;         /* [2][n_images][QOI_FVER_CHUNKS][65] chain state at the start of each verify range */
+	uint32_t *vcount;         /* [3][n_images] per verify pass (mod 3): rejected guesses + ranges whose start state was not the
+	                             state their predecessor ended with; 0 = the pass found the whole stream consistent */
 };
 
 struct QoiFParams {
@@ -269,6 +271,7 @@ __global__ void __launch_bounds__(32) fchain_kernel(const QoiFParams P) {
 	if (lane == 0) {
 		P.f.n_live[img] = s_state[2];
 		P.f.verified[img] = P.f.verified[P.n_images + img] = 0; /* both parities of the pass-buffered state */
+		P.f.vcount[img] = P.f.vcount[P.n_images + img] = P.f.vcount[2u * P.n_images + img] = 0;
 		P.f.ex_px[img] = P.f.ex_px[P.n_images + img] = 0xFF000000u;
 	}
 	P.f.ex_tab[(size_t)img * 64 + lane] = 0u;
@@ -560,8 +563,17 @@ __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
 		if (lane == 0) { P.f.ex_px[wr] = P.f.ex_px[rd]; P.f.verified[wr] = ver; }
 		return;
 	}
+	/* Fixed point: the previous pass rejected no guess and every range started with the state its predecessor ended
+	   with, so all its walks together were one exact walk from the verified prefix to the end: everything is final.
+	   (The counter was completed by the previous launch; nothing read here is written by this one.) */
+	if (P.round >= 1u && ver < live && P.f.vcount[((P.round + 2u) % 3u) * P.n_images + img] == 0u) {
+		if (chunk == 0u && lane == 0) P.f.verified[wr] = live;
+		return;
+	}
+	if (chunk == 0u && lane == 0) P.f.vcount[((P.round + 1u) % 3u) * P.n_images + img] = 0u; /* the next pass's counter */
 	if (ver >= live || hi <= ver || lo >= hi) return; /* verified range, or empty range */
 	const uint32_t base = P.f.seg_base[img];
+	uint32_t nbad = 0;
 	/* chain state: lane holds slots lane and lane+32 */
 	uint32_t t0, t1, px;
 	bool exact = owner;
@@ -605,6 +617,7 @@ __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
 				        exact ? "EXACT" : "guess", (int)differs, px, g_px, pmask, (unsigned long long)(r.rbw & ~agree));
 #endif
 			uint64_t apply = r.wr;
+			nbad += differs ? 1u : 0u;
 			if (differs) {
 				/* new guess for this segment = the chain state (the exact state while `exact` still holds) */
 				P.f.in_tab[(size_t)g * 64 + lane] = t0;
@@ -661,12 +674,18 @@ __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
 		walk_records(P, base, first, hi, lane, body);
 	}
 	if (owner && lane == 0) P.f.verified[wr] = ver;
-	if (chunk + 1u < nch) { /* where the next range starts in the next pass */
+	if (chunk + 1u < nch) {
+		/* did the next range start (in this pass) with the state this one ends with? */
+		const uint32_t *bo = P.f.bstate + ((size_t)rd * QOI_FVER_CHUNKS + chunk + 1u) * QOI_FVER_BWORDS;
+		const bool same = P.round >= 1u && bo[lane] == t0 && bo[lane + 32] == t1 && bo[64] == px;
+		if (__ballot_sync(QOI_FULL_MASK, same) != QOI_FULL_MASK) nbad++;
+		/* where the next range starts in the next pass */
 		uint32_t *bs = P.f.bstate + ((size_t)wr * QOI_FVER_CHUNKS + chunk + 1u) * QOI_FVER_BWORDS;
 		bs[lane] = t0;
 		bs[lane + 32] = t1;
 		if (lane == 0) bs[64] = px;
 	}
+	if (lane == 0 && nbad) atomicAdd(&P.f.vcount[(P.round % 3u) * P.n_images + img], nbad);
 }
 
 /* ------------------------------------------------------------------ 4. exact fix-up: one warp per stream */
@@ -794,6 +813,7 @@ static inline void fstate_bind(QoiFState &f, unsigned char *base, const size_t *
 	f.ex_px = (uint32_t *)(base + off[15]);
 	f.ex_tab = (uint32_t *)(base + off[16]);
 	f.bstate = (uint32_t *)(base + off[20]);
+	f.vcount = (uint32_t *)(base + off[21]);
 }
 
 }  // namespace qoifdec

@@ -141,7 +141,7 @@ static inline void qoi_state_bind(QoiTileState &st, unsigned char *base, const Q
 struct QoiFLayout {
 	std::vector<uint32_t> seg_base; /* [n + 1] */
 	uint32_t n_segs = 0;
-	size_t off[21];
+	size_t off[22];
 	size_t total = 0;
 };
 
@@ -158,9 +158,9 @@ static inline QoiFLayout qoi_fstate_layout(const QoiPlanGeom &g) {
 	L.seg_base[n] = (uint32_t)segs;
 	L.n_segs = (uint32_t)segs;
 	const size_t S = segs, N = n;
-	const size_t sizes[21] = {(N + 1) * 4, S * 20, S * 8, S, S * 4, N * 4, S * 4, S * 256, S * 4, S * 256, S * 8, S * 8, S * 4, S, N * 8, N * 8, N * 512, S * 128, S * 4, 256, N * 2 * QOI_FVER_CHUNKS_HOST * 65 * 4};
+	const size_t sizes[22] = {(N + 1) * 4, S * 20, S * 8, S, S * 4, N * 4, S * 4, S * 256, S * 4, S * 256, S * 8, S * 8, S * 4, S, N * 8, N * 8, N * 512, S * 128, S * 4, 256, N * 2 * QOI_FVER_CHUNKS_HOST * 65 * 4, N * 12};
 	size_t o = 0;
-	for (int k = 0; k < 21; k++) {
+	for (int k = 0; k < 22; k++) {
 		L.off[k] = o;
 		o += (sizes[k] + 255) & ~(size_t)255;
 	}

@@ -32,4 +32,8 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:qoi
     python bench.py --steps 2 --warmup 3 --batch 32 --no-cpu --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1; echo "NCU_ENC_RC=$?"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:qoi_decode -s 3 -c 2 -o gpurun_out/prof_dec -f \
     python bench.py --steps 2 --warmup 3 --batch 32 --no-cpu --e2e-steps 1 >> gpurun_out/ncu_full.log 2>&1; echo "NCU_DEC_RC=$?"
+# foreign-stream (any-stream) decoder: per-kernel launch list on the headline content and batch throughput per distribution
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^f' -c 80 --csv --log-file gpurun_out/foreign_launches_d4.csv python tools/foreign_prof.py 4 8 1 > gpurun_out/foreign_prof_d4.log 2>&1; echo "FPROF_RC=$?"
+for d in 4 0 6 2 3 7; do timeout 200 python tools/foreign_prof.py $d 32 3 2>&1 | tail -1; done | tee gpurun_out/foreign_batch32.txt
+timeout 200 python tools/foreign_prof.py 4 1 3 2>&1 | tail -1 | tee -a gpurun_out/foreign_batch32.txt
 ls -la gpurun_out
