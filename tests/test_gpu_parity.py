@@ -153,6 +153,49 @@ def test_config1_4096_rgba_bit_exact(gpu, cpu):
         assert (px == img).all()
 
 
+def test_foreign_large_streams(gpu, cpu):
+    """Streams of many 4096-byte segments that the reference ENCODER would never write (op soup, INDEX into any slot,
+    RGBA ops with changing alpha, truncation): the speculative decoder rarely settles these, the exact fix-up must."""
+    qb, _, _ = gpu
+    chk = cpu.best()
+    rng = np.random.default_rng(2024)
+    for it, (w, h) in enumerate([(640, 480), (1000, 333), (512, 512), (2048, 150)]):
+        s = q.foreign_stream(rng, w * h, 4 if it % 2 == 0 else 3, w=w, h=h, truncate=(it == 1))
+        for c in (4, 3):
+            pa, da = chk.decode(s, c)
+            pb, db = qb.decode(s, c)
+            assert pb is not None and (pa == pb).all() and bytes(da) == bytes(db), (it, c)
+
+
+def test_foreign_real_photographs(gpu, cpu):
+    """Real photographic content (JPEG-decoded photographs that ship with scikit-learn, tiled 2x2), encoded by the CPU
+    checker and decoded as foreign streams: INDEX ~10 %, RUN ~10 %, the op mix synthetic data does not have."""
+    PIL = pytest.importorskip("PIL.Image")
+    qb, _, _ = gpu
+    chk = cpu.best()
+    try:
+        import sklearn.datasets
+        base = os.path.join(os.path.dirname(sklearn.datasets.__file__), "images")
+    except Exception:
+        pytest.skip("scikit-learn not present")
+    found = 0
+    for name in ("china.jpg", "flower.jpg"):
+        path = os.path.join(base, name)
+        if not os.path.exists(path):
+            continue
+        found += 1
+        for mode, ch in (("RGBA", 4), ("RGB", 3)):
+            a = np.asarray(PIL.open(path).convert(mode))
+            a = np.ascontiguousarray(np.tile(a, (2, 2, 1)))
+            h, w = a.shape[:2]
+            stream = chk.encode(a.reshape(-1), w, h, ch)
+            px, d = qb.decode(stream, ch)
+            assert px is not None and (px == a.reshape(-1)).all(), (name, mode)
+            assert qb.encode(a.reshape(-1), qb.Desc(w, h, ch, 0)) == stream, (name, mode)
+    if not found:
+        pytest.skip("sample photographs not present")
+
+
 # ------------------------------------------------------------------ batch / device API
 def run_batch(gpu, cpu, descs_whc, dist_or_imgs, mis=0, dec_ch=4, odd_slots=False, repeat=1):
     qb, torch, ctx = gpu
