@@ -92,20 +92,24 @@ def cpu_round_trip(eb, db, threads, pixels, n, keep_streams, keep_lens, slot):
 
 
 class ClockSampler:
+    """nvidia-smi polled every 20 ms in the background.  It is started before the warm-up (the tool needs a few hundred
+    ms to come up) and the samples are cut to the wall-clock window of the timed region afterwards."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, device_index):
         self.file = tempfile.NamedTemporaryFile(prefix="qoi_clocks_", suffix=".csv", delete=False)
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device_index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=self.file, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """t_begin / t_end: time.time() around the timed region; samples outside are dropped (all kept if none falls inside)."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -115,6 +119,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         self.file.close()
+        rows = []
         sm, mx, reasons = [], [], set()
         try:
             for line in open(self.file.name):
@@ -122,11 +127,24 @@ class ClockSampler:
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
+                    rec = (float(f[1]), float(f[2]), [v.lower().startswith("active") for v in f[5:9]])
                 except ValueError:
                     continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if val.lower().startswith("active"):
+                ts = None
+                if len(f) >= 10:
+                    try:
+                        ts = datetime.datetime.strptime(f[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    except ValueError:
+                        ts = None
+                rows.append((ts, rec))
+            inside = [r for ts, r in rows if ts is not None and t_begin is not None and t_begin - 0.02 <= ts <= t_end + 0.02]
+            use = inside if inside else [r for _, r in rows]
+            out["window"] = "timed region" if inside else "whole run (no sample fell inside the timed region)"
+            sm, mx, reasons = [], [], set()
+            for a, b, flags in use:
+                sm.append(a); mx.append(b)
+                for name, on in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
+                    if on:
                         reasons.add(name)
         finally:
             os.unlink(self.file.name)
@@ -317,6 +335,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # started early, cut to the timed window later
     # ---- warm-up + correctness of the round trip (untimed)
     for _ in range(args.warmup):
         step()
@@ -329,19 +348,20 @@ def main():
     e_bpp = enc_bytes / px_rank
 
     # ---- timed region: exactly K steps, events on the launching stream, clocks sampled meanwhile
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     launches0 = qoi_b200.launch_count()
     barrier()
     t_start = torch.cuda.Event(enable_timing=True)
     t_stop = torch.cuda.Event(enable_timing=True)
+    wall_begin = time.time()
     t_start.record()
     for k in range(args.steps):
         step(evs[k])
     t_stop.record()
     barrier()
     launches = qoi_b200.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
+    wall_end = time.time()
+    clocks = sampler.stop(wall_begin, wall_end) if sampler else None
     total_ms = t_start.elapsed_time(t_stop)
     enc_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     dec_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps

@@ -54,6 +54,16 @@ for rep, kern, fn in (("prof_enc.ncu-rep", "qoi_encode_kernel", "encode_lines.tx
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), tmp, kern, "30"], capture_output=True, text=True).stdout
     open(os.path.join(out, fn), "w").write("per source line: share of executed warp instructions (i) and of warp stall samples (s)\n" + res)
     os.unlink(tmp)
+# the foreign-stream (any-stream) decoder: launch list of its pipeline + batch throughput per distribution
+fl = os.path.join(ROOT, "gpurun_out", "foreign_launches_d4.csv")
+if os.path.exists(fl):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "foreign_launches.py"), fl], capture_output=True, text=True).stdout
+    extra = ""
+    fb = os.path.join(ROOT, "gpurun_out", "foreign_batch32.txt")
+    if os.path.exists(fb):
+        extra = "\nCUDA-event times of qoi_gpu_decode(use_index=0), not under ncu (tools/foreign_prof.py <dist> <batch> 3):\n" + open(fb).read()
+    open(os.path.join(out, "foreign_pipeline.txt"), "w").write(
+        "per-kernel times (ncu launch list, cold-cache and serialised) of one foreign decode of 8 x 4096^2 RGBA photo streams\n" + res + extra)
 for f in ("launches.csv", "bench.json", "bench_ref.json", "bench_dist0.json", "bench_dist2.json", "bench_dist6.json", "bench_dist7.json"):
     p = os.path.join(ROOT, "gpurun_out", f)
     if os.path.exists(p) and os.path.getsize(p):
