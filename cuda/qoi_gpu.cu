@@ -36,6 +36,7 @@ struct qoi_gpu_ctx {
 	cudaStream_t s_h2d = nullptr, s_d2h = nullptr; /* one stream per copy direction: PCIe is full duplex */
 	char err[256] = {0};
 	int enc_blocks_per_sm[3] = {0, 0, 0}; /* <4,false>, <4,true>, <3,true> */
+	bool refill_uni = true;               /* decoders' stream reader: warp-uniform refill (default) or lane-driven (QOI_GPU_REFILL=lane) */
 	bool walk = true;                     /* look-up variant: word walk (default; 8% faster on photo content) or second-level
 	                                         bits (QOI_GPU_LOOKUP=summary; 20% faster on run-dominated content) */
 };
@@ -78,8 +79,10 @@ struct qoi_gpu_plan {
 static_assert(QOI_FFIX_SMEM <= 48 * 1024 && QOI_FCHAIN_SMEM <= 48 * 1024 && QOI_FVER_CHUNKS_HOST == QOI_FVER_CHUNKS && QOI_FDEC_ROUNDS < 60, "these kernels are launched without a shared-memory opt-in");
 /* the speculative decoder's blocks need more than the default 48 KB of dynamic shared memory */
 static int fdec_setup(qoi_gpu_ctx *ctx) {
-	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
-	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
+	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
+	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
+	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
+	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
 	return QOI_GPU_OK;
 }
 
@@ -95,9 +98,10 @@ static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
 }
 
 template <int OUT_CH, int BLOCK>
-static void launch_decode(const QoiDecParams &D, cudaStream_t s) {
+static void launch_decode(const QoiDecParams &D, cudaStream_t s, bool uni) {
 	const uint32_t grid = (D.n_jobs + BLOCK - 1) / BLOCK;
-	qoidec::qoi_decode_kernel<OUT_CH, BLOCK><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
+	if (uni) qoidec::qoi_decode_kernel<OUT_CH, BLOCK, true><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
+	else qoidec::qoi_decode_kernel<OUT_CH, BLOCK, false><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
 }
 
 extern "C" {
@@ -130,6 +134,8 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 	{
 		const char *w = getenv("QOI_GPU_LOOKUP");
 		if (w && !strcmp(w, "summary")) c->walk = false;
+		const char *rf = getenv("QOI_GPU_REFILL");
+		if (rf && !strcmp(rf, "lane")) c->refill_uni = false;
 	}
 	int rc = enc_occupancy<4, false>(c, &c->enc_blocks_per_sm[0]);
 	if (!rc) rc = enc_occupancy<4, true>(c, &c->enc_blocks_per_sm[1]);
@@ -291,8 +297,13 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 		qoifdec::fzero_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
 		for (int r = 0; r < QOI_FDEC_ROUNDS; r++) {
 			F.round = (uint32_t)r;
-			if (F.out_channels == 4) qoifdec::fdecode_kernel<4><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
-			else qoifdec::fdecode_kernel<3><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
+			if (F.out_channels == 4) {
+				if (ctx->refill_uni) qoifdec::fdecode_kernel<4, true><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
+				else qoifdec::fdecode_kernel<4, false><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
+			} else {
+				if (ctx->refill_uni) qoifdec::fdecode_kernel<3, true><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
+				else qoifdec::fdecode_kernel<3, false><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
+			}
 			if (r + 1 < QOI_FDEC_ROUNDS) qoifdec::fverify_kernel<<<F.n_images * QOI_FVER_CHUNKS, 32, 0, s>>>(F);
 		}
 		F.round = QOI_FDEC_ROUNDS - 1; /* reads what the last verify pass wrote */
@@ -318,11 +329,11 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 	/* few segments: narrow blocks so that they spread over the SMs */
 	const bool narrow = D.n_jobs < (uint32_t)ctx->sm_count * 128u * 2u;
 	if (D.out_channels == 4) {
-		if (narrow) launch_decode<4, 32>(D, s);
-		else launch_decode<4, 128>(D, s);
+		if (narrow) launch_decode<4, 32>(D, s, ctx->refill_uni);
+		else launch_decode<4, 128>(D, s, ctx->refill_uni);
 	} else {
-		if (narrow) launch_decode<3, 32>(D, s);
-		else launch_decode<3, 128>(D, s);
+		if (narrow) launch_decode<3, 32>(D, s, ctx->refill_uni);
+		else launch_decode<3, 128>(D, s, ctx->refill_uni);
 	}
 	g_launches++;
 	CK(ctx, cudaGetLastError());

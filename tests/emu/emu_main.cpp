@@ -29,6 +29,9 @@ void *ora_encode(const void *data, const QoiDescPOD *desc, int *out_len);
 void *ora_decode(const void *data, int size, QoiDescPOD *desc, int channels);
 }
 
+/* which stream-reader refill the decoders use (QOI_EMU_REFILL=lane selects the lane-driven one) */
+static bool emu_uni() { const char *e = getenv("QOI_EMU_REFILL"); return !(e && !strcmp(e, "lane")); }
+
 static std::vector<unsigned char> read_file(const char *path) {
 	FILE *f = fopen(path, "rb");
 	if (!f) { fprintf(stderr, "cannot open %s\n", path); exit(2); }
@@ -50,8 +53,8 @@ static void run_encode(const QoiEncParams &P, unsigned grid, unsigned seed) {
 static void run_decode(const QoiDecParams &P, unsigned seed) {
 	unsigned grid = (P.n_jobs + QOI_DEC_THREADS - 1) / QOI_DEC_THREADS;
 	size_t smem = QOI_DEC_SMEM_WORDS * QOI_DEC_THREADS * 4;
-	if (P.out_channels == 4) qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS>(P); }, seed);
-	else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS>(P); }, seed);
+	if (P.out_channels == 4) qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_uni()) qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, true>(P); else qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, false>(P); }, seed);
+	else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_uni()) qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true>(P); else qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, false>(P); }, seed);
 }
 
 /* the foreign-stream pipeline exactly as qoi_gpu_decode enqueues it */
@@ -73,8 +76,8 @@ static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned se
 	int extra = 0;
 	for (int r = 0; r < rounds; r++) {
 		F.round = (uint32_t)r;
-		if (D.out_channels == 4) qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { qoifdec::fdecode_kernel<4>(F); }, seed);
-		else qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { qoifdec::fdecode_kernel<3>(F); }, seed);
+		if (D.out_channels == 4) qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { if (emu_uni()) qoifdec::fdecode_kernel<4, true>(F); else qoifdec::fdecode_kernel<4, false>(F); }, seed);
+		else qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { if (emu_uni()) qoifdec::fdecode_kernel<3, true>(F); else qoifdec::fdecode_kernel<3, false>(F); }, seed);
 		if (r + 1 < rounds) qemu::launch(D.n_images * QOI_FVER_CHUNKS, 32, 0, [&]() { qoifdec::fverify_kernel(F); }, seed);
 		if (getenv("QOI_EMU_FTRACE")) {
 			for (uint32_t i = 0; i < D.n_images; i++) {

@@ -29,7 +29,9 @@ def run_enc(emu, img, w, h, ch, n, grid, seed, mis):
         f.flush()
         for lookup in ("walk", "summary"):  # both look-up variants of the encoder (QOI_GPU_LOOKUP)
             # ... and the foreign decoder's verify pass with one range per stream / with several
-            env = dict(os.environ, QOI_GPU_LOOKUP=lookup, QOI_EMU_FVER_MIN_RANGE="1024" if lookup == "walk" else "3")
+            # ... and the decoders' stream reader with warp-uniform / lane-driven refill
+            env = dict(os.environ, QOI_GPU_LOOKUP=lookup, QOI_EMU_FVER_MIN_RANGE="1024" if lookup == "walk" else "3",
+                       QOI_EMU_REFILL="uniform" if lookup == "walk" else "lane")
             r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
                                capture_output=True, text=True, timeout=300, env=env)
             assert r.returncode == 0 and r.stdout.startswith("PASS"), lookup + ": " + r.stdout + r.stderr[-2000:]
@@ -75,6 +77,7 @@ def test_emulated_foreign_decode(emu, cpu):
 
     small = [q.foreign_stream(rng, 900, 4, w=30, h=30, truncate=(i % 4 == 0)) for i in range(40)]
     run(small, 30, 30, {})
+    run(small, 30, 30, {"QOI_EMU_REFILL": "lane"})
     # streams of many segments (random op soup: the speculation rarely holds, the fix-up does the work), with
     # different numbers of speculative rounds (both parities of the pass-buffered state)
     big = [q.foreign_stream(rng, 40000, 4, w=200, h=200, truncate=(i == 2)) for i in range(4)]
