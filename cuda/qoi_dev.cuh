@@ -56,19 +56,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 	             "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
 	             : "memory");
 }
-/* per-thread asynchronous global -> shared copies (LDGSTS), 4 / 8 / 16 bytes, naturally aligned on both sides */
-__device__ __forceinline__ void cp_async_4(void *dst_smem, const void *src_gmem) {
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_8(void *dst_smem, const void *src_gmem) {
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src_gmem) {
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 /* shared -> global bulk copy; same alignment rules; completion tracked by the bulk group */
 __device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {
 	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes)
@@ -206,12 +193,6 @@ static inline void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t b
 	memcpy(dst_gmem, src_smem, bytes);
 	qemu::progress++;
 }
-static inline void cp_async_4(void *d, const void *s_) { memcpy(d, s_, 4); }
-static inline void cp_async_8(void *d, const void *s_) { memcpy(d, s_, 8); }
-static inline void cp_async_16(void *d, const void *s_) { memcpy(d, s_, 16); }
-static inline void cp_async_commit() {}
-template <int N>
-static inline void cp_async_wait() {}
 static inline uint64_t l2_evict_first_policy() { return 0; }
 static inline void tma_load_1d_hint(void *d, const void *s_, uint32_t n, uint64_t *bar, uint64_t) { tma_load_1d(d, s_, n, bar); }
 static inline void tma_store_1d_hint(void *d, const void *s_, uint32_t n, uint64_t) { tma_store_1d(d, s_, n); }

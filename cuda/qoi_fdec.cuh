@@ -629,7 +629,8 @@ __global__ void __launch_bounds__(32) fverify_kernel(const QoiFParams P) {
 			const uint32_t pmask = ((dep & 1u) ? 0x00FFFFFFu : 0u) | ((dep & 2u) ? 0xFF000000u : 0u);
 			/* which slots of the guess equal the chain state */
 			const uint64_t agree = (uint64_t)__ballot_sync(QOI_FULL_MASK, r.g0 == t0) | ((uint64_t)__ballot_sync(QOI_FULL_MASK, r.g1 == t1) << 32);
-			const bool differs = (r.rbw & ~agree) != 0ull || ((g_px ^ px) & pmask) != 0u;
+			/* (a guess that was issued but never decoded -- redo still set -- is never accepted: its record is the old decode's) */
+			const bool differs = (r.rbw & ~agree) != 0ull || ((g_px ^ px) & pmask) != 0u || r.redo != 0u;
 #ifdef QOI_EMU_FDEBUG /* tests/emu only: why a segment's guess was rejected */
 			if (lane == 0 && getenv("QOI_EMU_FDEBUG"))
 				fprintf(stderr, "  pass %u chunk %u seg %u %s differs=%d px %08x guess %08x pmask %08x badslots %016llx\n", P.round, chunk, j,

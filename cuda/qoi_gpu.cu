@@ -358,7 +358,12 @@ static int plan_chunks(qoi_gpu_plan *p) {
 	if (!p->chunks.empty()) return QOI_GPU_OK;
 	qoi_gpu_ctx *ctx = p->ctx;
 	const int n = (int)p->geom.metas.size();
-	const int k = n < QOI_HOST_CHUNKS ? n : QOI_HOST_CHUNKS;
+	int want = QOI_HOST_CHUNKS;
+	{
+		const char *e = getenv("QOI_GPU_HOST_CHUNKS"); /* A/B knob: more chunks = shorter pipeline fill and drain, smaller launches */
+		if (e && atoi(e) > 0 && atoi(e) <= 64) want = atoi(e);
+	}
+	const int k = n < want ? n : want;
 	std::vector<qoi_desc> descs((size_t)n);
 	std::vector<uint64_t> po((size_t)n), so((size_t)n), dof((size_t)n);
 	for (int i = 0; i < n; i++) {

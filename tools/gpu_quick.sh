@@ -14,10 +14,8 @@ for d in 0 6; do
 done
 # per-kernel times of the foreign-stream pipeline (launch list; numbers under ncu are not bench values)
 for d in 4 6; do
-  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^f' -c 60 --csv --log-file gpurun_out/foreign_launches_d$d.csv python tools/foreign_prof.py $d 8 1 > gpurun_out/foreign_prof_d$d.log 2>&1; echo "FPROF${d}_RC=$?"
+  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^f' -c 80 --csv --log-file gpurun_out/foreign_launches_d$d.csv python tools/foreign_prof.py $d 8 1 > gpurun_out/foreign_prof_d$d.log 2>&1; echo "FPROF${d}_RC=$?"
 done
-QOI_GPU_FWALK=async timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^f' -c 60 --csv --log-file gpurun_out/foreign_launches_d4_async.csv python tools/foreign_prof.py 4 8 1 > gpurun_out/foreign_prof_d4_async.log 2>&1; echo "FPROF4A_RC=$?"
 for d in 4 0 6; do
   timeout 200 python tools/foreign_prof.py $d 32 3 2>&1 | tail -1
 done
-QOI_GPU_FWALK=async timeout 200 python tools/foreign_prof.py 4 32 3 2>&1 | tail -1

@@ -36,4 +36,8 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:qoi
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^f' -c 80 --csv --log-file gpurun_out/foreign_launches_d4.csv python tools/foreign_prof.py 4 8 1 > gpurun_out/foreign_prof_d4.log 2>&1; echo "FPROF_RC=$?"
 for d in 4 0 6 2 3 7; do timeout 200 python tools/foreign_prof.py $d 32 3 2>&1 | tail -1; done | tee gpurun_out/foreign_batch32.txt
 timeout 200 python tools/foreign_prof.py 4 1 3 2>&1 | tail -1 | tee -a gpurun_out/foreign_batch32.txt
+# A/B: chunks of the pipelined host path (e2e only)
+for k in 8 16 32; do
+  QOI_GPU_HOST_CHUNKS=$k timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu --e2e-steps 4 2>> gpurun_out/bench.err | python -c "import json,sys; j=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('host chunks $k: e2e', j['e2e'])"
+done | tee gpurun_out/host_chunks.txt
 ls -la gpurun_out
