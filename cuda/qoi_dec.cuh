@@ -77,7 +77,7 @@ __device__ __forceinline__ void load_chunk(Reader &rd) {
 	rd.gp += 2;
 }
 
-template <int OUT_CH, int BLOCK, bool UNI>
+template <int OUT_CH, int BLOCK, bool UNI, bool PRE>
 __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P) {
 	QOI_DYNAMIC_SMEM(smem);
 	uint32_t *tab = (uint32_t *)smem + threadIdx.x;  /* tab[slot * BLOCK] */
@@ -156,9 +156,14 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 		rd.avail = 0;
 	}
 	/* next 4 stream bytes from the ring; when a ring half has been used up, park the in-flight chunk there and fetch the next */
+	/* PRE (experimental, needs UNI; off by default, not yet measured): the ring word is read one call ahead, so that the
+	   shared-memory latency is off the parse chain.  The word after the current one is always in the ring: the chunk
+	   behind the reader's is parked by the refill() of the trip in which the reader entered its chunk. */
+	uint32_t ahead = 0;
 	auto next_word = [&]() -> uint32_t {
-		const uint32_t w = ring[(rd.wi & (QOI_DEC_RING_WORDS - 1)) * BLOCK];
+		const uint32_t w = PRE ? ahead : ring[(rd.wi & (QOI_DEC_RING_WORDS - 1)) * BLOCK];
 		rd.wi++;
+		if (PRE) ahead = ring[(rd.wi & (QOI_DEC_RING_WORDS - 1)) * BLOCK];
 		if (!UNI && (rd.wi & 7u) == 0u) { /* lane-driven refill: the half just read is free */
 			uint32_t *r = ring + ((rd.wi - 8u) & (QOI_DEC_RING_WORDS - 1)) * BLOCK;
 			r[0 * BLOCK] = rd.pa.x; r[1 * BLOCK] = rd.pa.y; r[2 * BLOCK] = rd.pa.z; r[3 * BLOCK] = rd.pa.w;
@@ -183,6 +188,7 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 		}
 	};
 	{ /* prime the window with the word that holds byte p0 */
+		if (PRE) ahead = ring[(rd.wi & (QOI_DEC_RING_WORDS - 1)) * BLOCK];
 		const uint32_t mis = (uint32_t)((uintptr_t)(s + p0) & 3u);
 		rd.buf = (uint64_t)(next_word() >> (8u * mis));
 		rd.avail = 4u - mis;

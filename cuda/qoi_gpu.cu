@@ -36,6 +36,7 @@ struct qoi_gpu_ctx {
 	cudaStream_t s_h2d = nullptr, s_d2h = nullptr; /* one stream per copy direction: PCIe is full duplex */
 	char err[256] = {0};
 	int enc_blocks_per_sm[3] = {0, 0, 0}; /* <4,false>, <4,true>, <3,true> */
+	bool read_ahead = false;              /* experimental: ring word read one call ahead (QOI_GPU_REFILL=ahead); indexed decoder only */
 	bool refill_uni = true;               /* decoders' stream reader: warp-uniform refill (default) or lane-driven (QOI_GPU_REFILL=lane) */
 	bool walk = true;                     /* look-up variant: word walk (default; 8% faster on photo content) or second-level
 	                                         bits (QOI_GPU_LOOKUP=summary; 20% faster on run-dominated content) */
@@ -98,10 +99,11 @@ static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
 }
 
 template <int OUT_CH, int BLOCK>
-static void launch_decode(const QoiDecParams &D, cudaStream_t s, bool uni) {
+static void launch_decode(const QoiDecParams &D, cudaStream_t s, int uni) { /* 0 lane-driven refill, 1 warp-uniform, 2 + word read ahead */
 	const uint32_t grid = (D.n_jobs + BLOCK - 1) / BLOCK;
-	if (uni) qoidec::qoi_decode_kernel<OUT_CH, BLOCK, true><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
-	else qoidec::qoi_decode_kernel<OUT_CH, BLOCK, false><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
+	if (uni == 2) qoidec::qoi_decode_kernel<OUT_CH, BLOCK, true, true><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
+	else if (uni) qoidec::qoi_decode_kernel<OUT_CH, BLOCK, true, false><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
+	else qoidec::qoi_decode_kernel<OUT_CH, BLOCK, false, false><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
 }
 
 extern "C" {
@@ -136,6 +138,7 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 		if (w && !strcmp(w, "summary")) c->walk = false;
 		const char *rf = getenv("QOI_GPU_REFILL");
 		if (rf && !strcmp(rf, "lane")) c->refill_uni = false;
+		if (rf && !strcmp(rf, "ahead")) c->read_ahead = true;
 	}
 	int rc = enc_occupancy<4, false>(c, &c->enc_blocks_per_sm[0]);
 	if (!rc) rc = enc_occupancy<4, true>(c, &c->enc_blocks_per_sm[1]);
@@ -329,11 +332,11 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 	/* few segments: narrow blocks so that they spread over the SMs */
 	const bool narrow = D.n_jobs < (uint32_t)ctx->sm_count * 128u * 2u;
 	if (D.out_channels == 4) {
-		if (narrow) launch_decode<4, 32>(D, s, ctx->refill_uni);
-		else launch_decode<4, 128>(D, s, ctx->refill_uni);
+		if (narrow) launch_decode<4, 32>(D, s, ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
+		else launch_decode<4, 128>(D, s, ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
 	} else {
-		if (narrow) launch_decode<3, 32>(D, s, ctx->refill_uni);
-		else launch_decode<3, 128>(D, s, ctx->refill_uni);
+		if (narrow) launch_decode<3, 32>(D, s, ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
+		else launch_decode<3, 128>(D, s, ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
 	}
 	g_launches++;
 	CK(ctx, cudaGetLastError());

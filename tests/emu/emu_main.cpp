@@ -30,6 +30,7 @@ void *ora_decode(const void *data, int size, QoiDescPOD *desc, int channels);
 }
 
 /* which stream-reader refill the decoders use (QOI_EMU_REFILL=lane selects the lane-driven one) */
+static bool emu_ahead() { const char *e = getenv("QOI_EMU_REFILL"); return e && !strcmp(e, "ahead"); }
 static bool emu_uni() { const char *e = getenv("QOI_EMU_REFILL"); return !(e && !strcmp(e, "lane")); }
 
 static std::vector<unsigned char> read_file(const char *path) {
@@ -53,8 +54,8 @@ static void run_encode(const QoiEncParams &P, unsigned grid, unsigned seed) {
 static void run_decode(const QoiDecParams &P, unsigned seed) {
 	unsigned grid = (P.n_jobs + QOI_DEC_THREADS - 1) / QOI_DEC_THREADS;
 	size_t smem = QOI_DEC_SMEM_WORDS * QOI_DEC_THREADS * 4;
-	if (P.out_channels == 4) qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_uni()) qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, true>(P); else qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, false>(P); }, seed);
-	else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_uni()) qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true>(P); else qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, false>(P); }, seed);
+	if (P.out_channels == 4) qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_ahead()) qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, true, true>(P); else if (emu_uni()) qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, true, false>(P); else qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, false, false>(P); }, seed);
+	else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_ahead()) qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true, true>(P); else if (emu_uni()) qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true, false>(P); else qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, false, false>(P); }, seed);
 }
 
 /* the foreign-stream pipeline exactly as qoi_gpu_decode enqueues it */

@@ -23,7 +23,7 @@ def emu(cpu):
     return EMU
 
 
-def run_enc(emu, img, w, h, ch, n, grid, seed, mis):
+def run_enc(emu, img, w, h, ch, n, grid, seed, mis, extra_variants=()):
     with tempfile.NamedTemporaryFile(suffix=".raw") as f:
         f.write(np.ascontiguousarray(img, dtype=np.uint8).tobytes())
         f.flush()
@@ -35,12 +35,17 @@ def run_enc(emu, img, w, h, ch, n, grid, seed, mis):
             r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
                                capture_output=True, text=True, timeout=300, env=env)
             assert r.returncode == 0 and r.stdout.startswith("PASS"), lookup + ": " + r.stdout + r.stderr[-2000:]
+        for extra in extra_variants:  # experimental kernel variants that are off by default
+            r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
+                               capture_output=True, text=True, timeout=300, env=dict(os.environ, **extra))
+            assert r.returncode == 0 and r.stdout.startswith("PASS"), str(extra) + ": " + r.stdout + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("dist", range(8))
 def test_emulated_distributions(emu, cpu, dist):
-    run_enc(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0)
-    run_enc(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist)
+    ahead = ({"QOI_EMU_REFILL": "ahead"},)  # indexed decoder reading its ring one word ahead (QOI_GPU_REFILL=ahead)
+    run_enc(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0, ahead)
+    run_enc(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist, ahead)
 
 
 def test_emulated_stress(emu, cpu):
