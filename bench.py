@@ -444,6 +444,7 @@ def main():
             c_api = c_api_single_image(h_pix, args) if (world == 1 and not args.no_cpu) else None
         except Exception as e:  # the headline line must not depend on this extra
             c_api = {"error": repr(e)}
+        knobs = {k: v for k, v in os.environ.items() if k.startswith("QOI_GPU_")}  # A/B switches in effect (none by default)
         line = {
             "metric": METRIC, "value": value, "unit": "Gpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -461,7 +462,8 @@ def main():
             "clocks": clocks,
             "extra": {"decode_foreign_stream_gpx_per_s": px_rank / (foreign_ms * 1e-3) / 1e9,
                       "decode_foreign_note": "same streams decoded WITHOUT the restart index (any-stream path: parse scan + speculative segments + exact fix-up, cuda/qoi_fdec.cuh)",
-                      "encoded_bytes_all_ranks": enc_bytes_all, "c_api_single_image": c_api},
+                      "encoded_bytes_all_ranks": enc_bytes_all, "c_api_single_image": c_api,
+                      "library": os.path.basename(qoi_b200.library_path()), "knobs": knobs},
         }
         print(json.dumps(line), flush=True)
     if dist_on:

@@ -1,0 +1,531 @@
+/*
+ * qoi_enc4.cuh -- EXPERIMENTAL "striped" variant of the chained-scan encoder (QOI_GPU_ENC=striped | striped-match).
+ * OFF BY DEFAULT.  Checked bit-exact on the CPU emulator (tests/test_emu.py), NOT YET RUN ON A GPU: the round's
+ * GPU minutes were spent when it was written.  The shipped encoder is qoi_enc.cuh; this file only adds kernels.
+ *
+ * Same CTA skeleton, look-back records, loader and scout protocol as qoi_enc.cuh (reference loop: qoi.h:406-478);
+ * what changes is how the 8 compute warps walk a tile.  There a THREAD owns 16 consecutive pixels and finds the
+ * previous pixel of its hash slot through a slot x position bit matrix (divergent walks, byte-wise stores, ~9 warp
+ * instructions per pixel, profiles/r1_final/encode_lines.txt).  Here a WARP owns 512 consecutive pixels and walks them
+ * as 16 rows of 32, lane = pixel, so every step of qoi.h's state machine is a warp-wide operation:
+ *
+ *   px == px_prev (qoi.h:415)      one compare against the left neighbour (shared memory), ballot = non-run mask
+ *   index[hash] == px (qoi.h:432)  lanes with my hash slot from six ballots of the hash bits (or match.any); the
+ *                                  nearest lower one is my predecessor (shuffle); none in the row -> the warp's own
+ *                                  64-entry table of the rows before; none there -> deferred to phase R (<= 64 per warp)
+ *   run counter (qoi.h:416-421)    distance to the last non-run pixel: clz of the ballot, else the warp's carry
+ *   op selection (qoi.h:438-474)   branch-free classify on the packed pixel
+ *   output cursor p                packed shuffle scan over four rows at a time, warp totals, tile look-back (scout)
+ *
+ * The bit matrix is gone (its shared memory holds the staging buffer, the per-warp tables and the patch words).
+ */
+#pragma once
+#include "qoi_enc.cuh"
+
+namespace qoienc4 {
+using namespace qoidev;
+using namespace qoienc;
+
+/* what lives in the former bit-matrix area of Layout<CH, EXPAND> */
+template <int CH, bool EXPAND>
+struct Sub {
+	using L = Layout<CH, EXPAND>;
+	static constexpr int OFF_STAGE = L::OFF_CELLS;
+	static constexpr int OFF_LENT = OFF_STAGE + ((L::STAGE_BYTES + 15) & ~15); /* uint2 [8][64]: last non-run pixel per slot in the warp's chunk */
+	static constexpr int OFF_FPOS = OFF_LENT + QOI_ENC_WARPS * 64 * 8;          /* u16 [8][64]: first pixel of a slot in the warp's chunk */
+	static constexpr int OFF_PATCH = OFF_FPOS + QOI_ENC_WARPS * 64 * 2;         /* u32 [8][16]: pixels that phase R turned into INDEX hits */
+	static constexpr int END = OFF_PATCH + QOI_ENC_WARPS * 16 * 4;
+	static_assert(END <= L::OFF_CELLS + L::CELLS_BYTES, "the striped variant must fit into the bit-matrix area");
+	static_assert(OFF_LENT % 8 == 0, "alignment");
+};
+
+/* qoi.h:438-474 for a non-run pixel that is not an INDEX hit; same result as qoienc::classify, no branches */
+__device__ __forceinline__ uint32_t classify_bf(uint32_t v, uint32_t p) {
+	const uint32_t d = __vsub4(v, p);           /* per-channel difference mod 256 (qoi.h:439-441) */
+	const uint32_t t = __vadd4(d, 0x00020202u); /* dr+2, dg+2, db+2, da */
+	const bool is_diff = (t & 0xFFFCFCFCu) == 0u; /* qoi.h:446-451 */
+	const uint32_t diff_cd = 1u | ((0x40u | ((t & 3u) << 4) | (((t >> 8) & 3u) << 2) | ((t >> 16) & 3u)) << 8);
+	const uint32_t dg = (d >> 8) & 0xFFu;
+	const uint32_t e = __vsub4(d, dg * 0x00010101u); /* dr-dg, 0, db-dg, da-dg (qoi.h:443-444) */
+	const uint32_t t2 = __vadd4(e, 0x00080008u);
+	const uint32_t g32 = (dg + 32u) & 0xFFu;
+	const bool a_eq = (d >> 24) == 0u;
+	const bool is_luma = a_eq && (t2 & 0x00F000F0u) == 0u && (g32 & 0xC0u) == 0u; /* qoi.h:453-459 */
+	const uint32_t luma_cd = 2u | ((0x80u | g32) << 8) | ((((t2 & 0xFu) << 4) | ((t2 >> 16) & 0xFu)) << 16);
+	const uint32_t abs_cd = (a_eq ? (4u | (0xFEu << 8)) : (5u | (0xFFu << 8))) | ((v & 0xFFu) << 16); /* qoi.h:461-473 */
+	return is_diff ? diff_cd : (is_luma ? luma_cd : abs_cd);
+}
+
+/* op of a run pixel (qoi.h:415-421): k = its position in the run (1-based).  The run byte 0xC0 | (k-1)%62 is kept in
+   bits 8..15 even when nothing is emitted, so that "an op starts here" ((k-1)%62 == 0) can be read back later */
+__device__ __forceinline__ uint32_t run_code(uint32_t k, bool ends) {
+	const uint32_t r = (k - 1u) % 62u;
+	return ((r == 61u || ends) ? 1u : 0u) | ((0xC0u | r) << 8);
+}
+
+/* plane = ballot(x != 0), mine = x != 0 ? ~0 : 0, off one predicate (the compiler's own form recomputes the bit three times) */
+__device__ __forceinline__ void ballot_and_mask(uint32_t x, uint32_t &plane, uint32_t &mine) {
+#ifdef QOI_EMU
+	plane = __ballot_sync(QOI_FULL_MASK, x != 0u);
+	mine = x != 0u ? 0xFFFFFFFFu : 0u;
+#else
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "setp.ne.u32 p, %2, 0;\n\t"
+	    "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+	    "selp.u32 %1, 0xffffffff, 0, p;\n\t}"
+	    : "=r"(plane), "=r"(mine)
+	    : "r"(x));
+#endif
+}
+
+/* MATCH: same-slot lanes from match.any instead of six ballots (A/B switch) */
+template <int CH, bool EXPAND, bool MATCH>
+__global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(const QoiEncParams P) {
+	using L = Layout<CH, EXPAND>;
+	using S = Sub<CH, EXPAND>;
+	QOI_DYNAMIC_SMEM(smem);
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const bool scout = warp == QOI_ENC_WARPS;
+	const bool loader = warp == QOI_ENC_WARPS + 1;
+	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR);
+	TileInfo *infos = (TileInfo *)(smem + L::OFF_INFO);
+	unsigned char *stage = smem + S::OFF_STAGE;
+	uint2 *Lent_all = (uint2 *)(smem + S::OFF_LENT);
+	uint16_t *Fpos_all = (uint16_t *)(smem + S::OFF_FPOS);
+	uint32_t *patch_all = (uint32_t *)(smem + S::OFF_PATCH);
+	uint32_t *Tin_val = (uint32_t *)(smem + L::OFF_TINVAL);
+	uint8_t *Tin_flag = (uint8_t *)(smem + L::OFF_TINFLAG);
+	uint32_t *wtot = (uint32_t *)(smem + L::OFF_WTOT);
+	int32_t *wlnr = (int32_t *)(smem + L::OFF_WLNR);
+	int32_t *wlnr_in = (int32_t *)(smem + L::OFF_WLNRIN);
+	uint32_t *misc = (uint32_t *)(smem + L::OFF_MISC);
+
+	if (tid == 0) {
+		mbar_init(&mbar[0], 1);
+		mbar_init(&mbar[1], 1);
+		mbar_fence_init();
+	}
+	__syncthreads();
+	if (loader) {
+		Fetch F;
+		fetch_ticket(P, F);
+		fetch_issue<CH, EXPAND>(P, smem, F, 0, 0);
+		__syncwarp();
+		bar_arrive(BAR_INFO_READY, QOI_N_ALL);
+		bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
+	}
+
+	int cur = 0;
+	uint32_t parity0 = 0, parity1 = 0;
+	const uint32_t epoch = P.epoch;
+
+	while (true) {
+		if (!loader) bar_sync(BAR_INFO_READY, QOI_N_ALL); /* infos[cur] is published */
+		const TileInfo ti = infos[cur];
+		if (ti.tile < 0) break;
+		const uint32_t t = (uint32_t)ti.tile;
+		const int rb = EXPAND ? 0 : cur;
+		unsigned char *data = smem + L::OFF_RAW + rb * L::RAW_STRIDE + 16;
+		uint32_t *pxv = EXPAND ? (uint32_t *)(smem + L::OFF_PXBUF + 16) : (uint32_t *)data; /* pxv[-1 .. 4096] */
+		uint8_t *gstream = P.streams + ti.stream_off;
+
+		if (loader) {
+			/* =============================== loader warp (as in qoi_enc.cuh) =============================== */
+			Fetch F;
+			fetch_ticket(P, F);
+			if (EXPAND) bar_sync(BAR_E_DONE, QOI_N_CS);
+			fetch_issue<CH, EXPAND>(P, smem, F, EXPAND ? 0 : (cur ^ 1), cur ^ 1);
+
+			bar_sync(BAR_W_DONE, QOI_N_CS); /* staging is complete */
+			__syncwarp();
+			bar_arrive(BAR_INFO_READY, QOI_N_ALL); /* only now: see the note in qoi_enc.cuh */
+			{
+				const uint32_t excl = misc[MISC_TILE_BASE], total = misc[MISC_TILE_TOTAL];
+				uint8_t *gdst = gstream + excl;
+				const uint32_t padb = (uint32_t)((uintptr_t)gdst & 15u);
+				const uint32_t lo_off = (padb + 15u) & ~15u;
+				const uint32_t end = padb + total;
+				const uint32_t hi_off = end & ~15u;
+				const bool bulk = hi_off > lo_off;
+				if (lane == 0 && bulk) {
+					fence_proxy_async_smem();
+					tma_store_1d_hint(gdst + (lo_off - padb), stage + lo_off, hi_off - lo_off, l2_evict_first_policy());
+					tma_store_commit();
+				}
+				const uint32_t a_hi = bulk ? lo_off : end;
+				const uint32_t b_lo = bulk ? hi_off : end;
+				for (uint32_t o = padb + lane; o < a_hi; o += 32) gdst[o - padb] = stage[o];
+				for (uint32_t o = b_lo + lane; o < end; o += 32) gdst[o - padb] = stage[o];
+				if (t == ti.first_tile && lane < QOI_HEADER_BYTES) { /* header, qoi.h:384-388 */
+					const uint32_t k = lane;
+					uint8_t b;
+					if (k < 4) b = (uint8_t)("qoif"[k]);
+					else if (k < 8) b = (uint8_t)(ti.width >> (8 * (7 - k)));
+					else if (k < 12) b = (uint8_t)(ti.height >> (8 * (11 - k)));
+					else if (k == 12) b = (uint8_t)(ti.chan_cs & 0xFFu);
+					else b = (uint8_t)(ti.chan_cs >> 8);
+					gstream[k] = b;
+				}
+				if (ti.px0 + ti.n_valid == ti.npx && lane >= 16 && lane < 16 + QOI_END_BYTES + 1) { /* end marker, length: qoi.h:480-484 */
+					const uint32_t k = lane - 16;
+					const uint32_t fin = excl + total;
+					if (k < QOI_END_BYTES) gstream[fin + k] = (k == QOI_END_BYTES - 1) ? 1 : 0;
+					else P.lens[ti.img] = (int32_t)(fin + QOI_END_BYTES);
+				}
+				if (lane == 0) tma_store_wait_read(); /* the bulk store has finished reading the staging buffer */
+			}
+			__syncwarp();
+			bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
+		} else if (scout) {
+			/* =============================== scout warp =============================== */
+			bar_sync(BAR_I_DONE, QOI_N_CS); /* the per-warp tables and wlnr[] of this tile are complete */
+			/* ---- phase T: tile aggregate = the last warp that wrote each slot (lane handles slots lane, lane+32) ---- */
+			uint32_t own_val[2];
+			bool own_ok[2];
+#pragma unroll
+			for (int q = 0; q < 2; q++) {
+				const uint32_t sl = lane + 32u * q;
+				own_ok[q] = false;
+				own_val[q] = 0;
+				for (int w = QOI_ENC_WARPS - 1; w >= 0; w--) {
+					const uint2 e = Lent_all[w * 64 + sl];
+					if (e.y) {
+						own_val[q] = e.x;
+						own_ok[q] = true;
+						break;
+					}
+				}
+			}
+			int32_t own_lnr = QOI_LNR_NONE;
+			for (int w = QOI_ENC_WARPS - 1; w >= 0; w--) {
+				if (wlnr[w] >= 0) {
+					own_lnr = (int32_t)ti.px0 + wlnr[w];
+					break;
+				}
+			}
+			const uint32_t own_lo = __ballot_sync(QOI_FULL_MASK, own_ok[0]);
+			const uint32_t own_hi = __ballot_sync(QOI_FULL_MASK, own_ok[1]);
+			LookBack lb;
+			lb.in_ok[0] = lb.in_ok[1] = false;
+			lb.in_val[0] = lb.in_val[1] = 0;
+			lb.lnr_in = -1;
+			if (t != ti.first_tile) {
+				st_relaxed_u64(&P.st.agg_ent[(size_t)t * 64 + lane], pack_ent(epoch, own_val[0], own_ok[0]));
+				st_relaxed_u64(&P.st.agg_ent[(size_t)t * 64 + lane + 32], pack_ent(epoch, own_val[1], own_ok[1]));
+				if (lane < 3) {
+					const uint32_t payload = lane == 0 ? own_lo : (lane == 1 ? own_hi : (uint32_t)own_lnr);
+					st_relaxed_u64(&P.st.agg_sum[(size_t)t * QOI_SUM_WORDS + lane], pack_sum(epoch, payload));
+				}
+				table_lookback(P, t, ti.first_tile, epoch, lb);
+			}
+			Tin_val[lane] = lb.in_val[0];
+			Tin_val[lane + 32] = lb.in_val[1];
+			Tin_flag[lane] = lb.in_ok[0] ? 1 : 0;
+			Tin_flag[lane + 32] = lb.in_ok[1] ? 1 : 0;
+			const uint32_t inc_lo = __ballot_sync(QOI_FULL_MASK, own_ok[0] || lb.in_ok[0]);
+			const uint32_t inc_hi = __ballot_sync(QOI_FULL_MASK, own_ok[1] || lb.in_ok[1]);
+			st_relaxed_u64(&P.st.inc_ent[(size_t)t * 64 + lane], pack_ent(epoch, own_ok[0] ? own_val[0] : lb.in_val[0], own_ok[0] || lb.in_ok[0]));
+			st_relaxed_u64(&P.st.inc_ent[(size_t)t * 64 + lane + 32], pack_ent(epoch, own_ok[1] ? own_val[1] : lb.in_val[1], own_ok[1] || lb.in_ok[1]));
+			if (lane < 3) {
+				const int32_t inc_lnr = (own_lnr != QOI_LNR_NONE) ? own_lnr : lb.lnr_in;
+				const uint32_t payload = lane == 0 ? inc_lo : (lane == 1 ? inc_hi : (uint32_t)inc_lnr);
+				st_relaxed_u64(&P.st.inc_sum[(size_t)t * QOI_SUM_WORDS + lane], pack_sum(epoch, payload));
+			}
+			if (lane == 0) wlnr_in[0] = lb.lnr_in; /* last non-run pixel index before the tile (image coordinates) */
+			__syncwarp();
+			bar_arrive(BAR_T_READY, QOI_N_CS);
+
+			bar_sync(BAR_C_DONE, QOI_N_CS); /* byte counts of the compute warps are in wtot[] */
+			/* ---- phase B: output offset look-back, 32 predecessors per probe (as in qoi_enc.cuh) ---- */
+			uint32_t total = 0;
+#pragma unroll
+			for (int w = 0; w < QOI_ENC_WARPS; w++) total += wtot[w];
+			uint32_t excl = QOI_HEADER_BYTES;
+			if (t != ti.first_tile) {
+				if (lane == 0) st_relaxed_u64(&P.st.byte_state[t], pack_bytes(epoch, QOI_ST_AGG, total));
+				uint32_t sum = 0;
+				int64_t base = (int64_t)t - 1;
+				while (true) {
+					const int64_t tp = base - lane;
+					uint32_t state = QOI_ST_AGG, val = 0;
+					if (tp >= (int64_t)ti.first_tile) {
+						while (true) {
+							const uint64_t st = ld_relaxed_u64(&P.st.byte_state[tp]);
+							if ((uint32_t)(st >> 34) == epoch && ((st >> 32) & 3u) != QOI_ST_NONE) {
+								state = (uint32_t)(st >> 32) & 3u;
+								val = (uint32_t)st;
+								break;
+							}
+							spin_pause();
+						}
+					}
+					const uint32_t incm = __ballot_sync(QOI_FULL_MASK, state == QOI_ST_INC);
+					if (incm) {
+						const uint32_t first = (uint32_t)__ffs((int)incm) - 1u;
+						sum += __reduce_add_sync(QOI_FULL_MASK, lane <= first ? val : 0u);
+						break;
+					}
+					sum += __reduce_add_sync(QOI_FULL_MASK, val);
+					base -= 32;
+				}
+				excl = sum;
+			}
+			if (lane == 0) {
+				st_relaxed_u64(&P.st.byte_state[t], pack_bytes(epoch, QOI_ST_INC, excl + total));
+				misc[MISC_TILE_BASE] = excl;
+				misc[MISC_TILE_TOTAL] = total;
+			}
+			__syncwarp();
+			bar_arrive(BAR_B_READY, QOI_N_CS);
+		} else {
+			/* =============================== compute warps =============================== */
+			if (rb == 0) { mbar_wait(&mbar[0], parity0); parity0 ^= 1u; }
+			else { mbar_wait(&mbar[1], parity1); parity1 ^= 1u; }
+
+			uint2 *Lent = Lent_all + warp * 64;
+			uint16_t *Fpos = Fpos_all + warp * 64;
+			uint32_t *patchw = patch_all + warp * 16;
+			Lent[lane] = make_uint2(0u, 0u);
+			Lent[lane + 32] = make_uint2(0u, 0u);
+			Fpos[lane] = 0xFFFFu;
+			Fpos[lane + 32] = 0xFFFFu;
+			if (lane < 16) patchw[lane] = 0u;
+			if (EXPAND) {
+				/* ---- phase E: 16 pixels per thread, raw bytes at data[sh + CH*i] -> RGBA words (as in qoi_enc.cuh) ---- */
+				const uint32_t b0 = ti.sh + tid * (16u * CH);
+				const uint32_t *wsrc = (const uint32_t *)data + (b0 >> 2);
+				const uint32_t shf = (b0 & 3u) * 8u;
+				uint32_t out[16];
+				if (CH == 4) {
+					uint32_t w[17];
+#pragma unroll
+					for (int j = 0; j < 17; j++) w[j] = wsrc[j];
+#pragma unroll
+					for (int j = 0; j < 16; j++) out[j] = __funnelshift_r(w[j], w[j + 1], shf);
+				} else {
+					uint32_t w[13];
+#pragma unroll
+					for (int j = 0; j < 13; j++) w[j] = wsrc[j];
+					uint32_t s[12];
+#pragma unroll
+					for (int j = 0; j < 12; j++) s[j] = __funnelshift_r(w[j], w[j + 1], shf);
+#pragma unroll
+					for (int g = 0; g < 4; g++) {
+						const uint32_t s0 = s[3 * g], s1 = s[3 * g + 1], s2 = s[3 * g + 2];
+						out[4 * g + 0] = (s0 & 0x00FFFFFFu) | 0xFF000000u;
+						out[4 * g + 1] = (s0 >> 24) | ((s1 & 0x0000FFFFu) << 8) | 0xFF000000u;
+						out[4 * g + 2] = (s1 >> 16) | ((s2 & 0x000000FFu) << 16) | 0xFF000000u;
+						out[4 * g + 3] = (s2 >> 8) | 0xFF000000u;
+					}
+				}
+				uint4 *dst = (uint4 *)(pxv + tid * 16u);
+				dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+				dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+				dst[2] = make_uint4(out[8], out[9], out[10], out[11]);
+				dst[3] = make_uint4(out[12], out[13], out[14], out[15]);
+				if (tid == 0) {
+					const uint32_t *nbr = (const uint32_t *)(smem + L::OFF_NBR) + cur * 2;
+					pxv[-1] = nbr[0];
+					pxv[QOI_TILE_PX] = nbr[1];
+				}
+				bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
+				bar_arrive(BAR_E_DONE, QOI_N_CS); /* the raw buffer may be refilled */
+			}
+			__syncwarp();
+
+			const uint32_t nv = ti.n_valid; /* <= 4096; only an image's last tile can be partial */
+			const bool last_tile = ti.px0 + ti.n_valid == ti.npx;
+			const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
+			const uint32_t wbase = warp * (uint32_t)QOI_WARP_PX;
+
+			/* ---- pass 0: 16 rows of 32 pixels, lane = pixel.  code[s] = size | b0 << 8 | b1 << 16 of my pixel in row s ---- */
+			uint32_t code[QOI_WARP_STEPS];
+			uint32_t nrmask = 0; /* bit s: my pixel of row s is a non-run pixel */
+			uint32_t pend = 0;   /* bit s: my pixel of row s is a run pixel whose run started before this warp's chunk */
+			int32_t last_nr = -1; /* tile-local index of the last non-run pixel of this chunk so far (uniform) */
+#pragma unroll
+			for (int s = 0; s < QOI_WARP_STEPS; s++) {
+				const uint32_t rb0 = wbase + (uint32_t)s * 32u;
+				uint32_t cd = 0;
+				if (rb0 < nv) { /* uniform */
+					const uint32_t il = rb0 + lane;
+					const uint32_t v = pxv[il], p = pxv[(int)il - 1], nx = pxv[il + 1];
+					const bool valid = il < nv;
+					const bool nonrun = valid && v != p; /* qoi.h:415 */
+					const uint32_t nr = __ballot_sync(QOI_FULL_MASK, nonrun);
+					const uint32_t h = qoi_slot(v);
+					uint32_t m; /* the non-run lanes of this row with my slot */
+					if (MATCH) {
+						m = __match_any_sync(QOI_FULL_MASK, nonrun ? h : 64u + lane);
+					} else {
+						uint32_t differ = 0; /* lanes whose slot differs from mine in some bit */
+#pragma unroll
+						for (int b = 0; b < 6; b++) {
+							uint32_t plane, mine;
+							ballot_and_mask(h & (1u << b), plane, mine);
+							differ |= plane ^ mine;
+						}
+						m = nr & ~differ;
+					}
+					const uint32_t lower = m & lt;
+					const int src = lower ? (31 - __clz((int)lower)) : (int)lane;
+					const uint32_t pv = __shfl_sync(QOI_FULL_MASK, v, src);
+					const uint2 ent = Lent[h];
+					bool hit = false;
+					if (nonrun) {
+						if (lower) hit = (pv == v);          /* predecessor with my slot inside this row */
+						else if (ent.y) hit = (ent.x == v);  /* ... in an earlier row of this chunk */
+						else Fpos[h] = (uint16_t)il;         /* first pixel of the slot in the chunk: phase R decides */
+					}
+					__syncwarp();
+					if (nonrun && (m & gt) == 0u) Lent[h] = make_uint2(v, 1u); /* last pixel of its slot in this row */
+					if (nonrun) {
+						cd = hit ? (1u | (h << 8)) : classify_bf(v, p); /* qoi.h:432-434 / 438-474 */
+						nrmask |= 1u << s;
+					} else if (valid) {
+						const uint32_t below = nr & lt;
+						const int32_t lnr_l = below ? (int32_t)(rb0 + 31u - (uint32_t)__clz((int)below)) : last_nr;
+						if (lnr_l >= 0) cd = run_code(il - (uint32_t)lnr_l, (last_tile && ti.px0 + il == ti.npx - 1u) || nx != v);
+						else pend |= 1u << s;
+					}
+					if (nr) last_nr = (int32_t)(rb0 + 31u - (uint32_t)__clz((int)nr));
+					__syncwarp();
+				}
+				code[s] = cd;
+			}
+			if (lane == 0) wlnr[warp] = last_nr;
+			__syncwarp();
+			bar_arrive(BAR_I_DONE, QOI_N_CS);
+
+			bar_sync(BAR_T_READY, QOI_N_CS); /* every warp's table is final; T_in and the run carry are in shared memory */
+			/* ---- phase R: my chunk's deferred pixels against the earlier warps' tables, then the incoming table ---- */
+#pragma unroll
+			for (int q = 0; q < 2; q++) {
+				const uint32_t sl = lane + 32u * q;
+				const uint32_t pos = Fpos[sl];
+				if (pos != 0xFFFFu) {
+					const uint32_t pvv = pxv[pos];
+					bool found = false;
+					uint32_t val = 0;
+					for (int w2 = (int)warp - 1; w2 >= 0; w2--) {
+						const uint2 e = Lent_all[w2 * 64 + sl];
+						if (e.y) {
+							val = e.x;
+							found = true;
+							break;
+						}
+					}
+					if (!found && Tin_flag[sl]) {
+						val = Tin_val[sl];
+						found = true;
+					}
+					/* an untouched index[] slot holds 0 (qoi.h:393): only the all-zero pixel can hit it */
+					const bool hit = found ? (val == pvv) : (pvv == 0u);
+					if (hit) atomicOr(&patchw[(pos >> 5) & 15u], 1u << (pos & 31u));
+				}
+			}
+			__syncwarp();
+			/* ---- patch the pixels that turned into INDEX ops; finish the runs that were carried into the chunk ---- */
+			int32_t lnr_carry = wlnr_in[0]; /* image coordinates; -1: no non-run pixel since the image start */
+			for (int w2 = (int)warp - 1; w2 >= 0; w2--) {
+				if (wlnr[w2] >= 0) {
+					lnr_carry = (int32_t)ti.px0 + wlnr[w2];
+					break;
+				}
+			}
+			const bool any_pend = __ballot_sync(QOI_FULL_MASK, pend != 0u) != 0u;
+#pragma unroll
+			for (int s = 0; s < QOI_WARP_STEPS; s++) {
+				const uint32_t il = wbase + (uint32_t)s * 32u + lane;
+				if ((patchw[s] >> lane) & 1u) code[s] = 1u | (qoi_slot(pxv[il]) << 8);
+				if (any_pend && ((pend >> s) & 1u)) {
+					const uint32_t gi = ti.px0 + il;
+					code[s] = run_code(gi - (uint32_t)lnr_carry, (last_tile && gi == ti.npx - 1u) || pxv[il + 1] != pxv[il]);
+				}
+			}
+			/* decoder restart point of the tile: the first pixel at which an op starts (within the first 62 pixels) */
+			int32_t cand = INT_MAX;
+			if (warp == 0) {
+#pragma unroll
+				for (int s = 0; s < 2; s++) {
+					const uint32_t il = (uint32_t)s * 32u + lane;
+					const bool valid = il < nv;
+					const bool starts = valid && (((nrmask >> s) & 1u) || ((code[s] >> 8) & 0x3Fu) == 0u);
+					const uint32_t b = __ballot_sync(QOI_FULL_MASK, starts);
+					if (b && cand == INT_MAX) cand = (int32_t)((uint32_t)s * 32u + (uint32_t)__ffs((int)b) - 1u);
+				}
+			}
+			/* ---- byte offsets: packed inclusive scan over the sizes of four rows at a time (a row holds <= 160 bytes) ---- */
+			uint32_t ex4[4], tot4[4];
+			uint32_t wsum = 0;
+#pragma unroll
+			for (int g = 0; g < 4; g++) {
+				const uint32_t pk = (code[4 * g] & 7u) | ((code[4 * g + 1] & 7u) << 8) | ((code[4 * g + 2] & 7u) << 16) | ((code[4 * g + 3] & 7u) << 24);
+				uint32_t incl = pk;
+#pragma unroll
+				for (int dlt = 1; dlt < 32; dlt <<= 1) {
+					const uint32_t o = __shfl_up_sync(QOI_FULL_MASK, incl, dlt);
+					if (lane >= (uint32_t)dlt) incl += o;
+				}
+				ex4[g] = incl - pk;
+				tot4[g] = __shfl_sync(QOI_FULL_MASK, incl, 31);
+				wsum = __dp4a(tot4[g], 0x01010101u, wsum);
+			}
+			if (lane == 0) wtot[warp] = wsum;
+			__syncwarp();
+			bar_arrive(BAR_C_DONE, QOI_N_CS);
+
+			bar_sync(BAR_B_READY, QOI_N_CS);
+			bar_sync(BAR_STAGE_FREE, QOI_N_CS); /* the previous tile's bulk store has drained the staging buffer */
+			/* ---- phase W: op bytes -> staging (alignment congruent to the destination) ---- */
+			const uint32_t tile_base = misc[MISC_TILE_BASE];
+			const uint32_t padb = (uint32_t)((uintptr_t)(gstream + tile_base) & 15u);
+			uint32_t rowbase = 0;
+			for (uint32_t w = 0; w < warp; w++) rowbase += wtot[w];
+#pragma unroll
+			for (int s = 0; s < QOI_WARP_STEPS; s++) {
+				const uint32_t il = wbase + (uint32_t)s * 32u + lane;
+				const uint32_t off = rowbase + ((ex4[s >> 2] >> (8 * (s & 3))) & 0xFFu);
+				const uint32_t cd = code[s];
+				const uint32_t sz = cd & 7u;
+				unsigned char *o = stage + padb + off;
+				if (s < 2 && warp == 0 && (int32_t)il == cand) { /* the owner of the restart pixel records where its op starts */
+					P.st.rs_px[t] = (int32_t)(ti.px0 + il);
+					P.st.rs_byte[t] = (int32_t)(tile_base + off);
+					P.st.rs_prev[t] = pxv[(int)il - 1];
+				}
+				if (sz) {
+					o[0] = (uint8_t)(cd >> 8);
+					if (sz >= 2) {
+						o[1] = (uint8_t)(cd >> 16);
+						if (sz >= 4) {
+							const uint32_t v = pxv[il];
+							o[2] = (uint8_t)(v >> 8);
+							o[3] = (uint8_t)(v >> 16);
+							if (sz == 5) o[4] = (uint8_t)(v >> 24);
+						}
+					}
+				}
+				rowbase += (tot4[s >> 2] >> (8 * (s & 3))) & 0xFFu;
+			}
+			if (tid == 0 && cand == INT_MAX) P.st.rs_px[t] = -1;
+			__syncwarp();
+			bar_arrive(BAR_W_DONE, QOI_N_CS);
+		}
+		cur ^= 1;
+	}
+
+	/* the last CTA to finish rearms the ticket for the next launch */
+	__syncthreads();
+	if (loader && lane == 0) { /* this thread issued the bulk stores */
+		tma_store_wait_all();
+		const uint32_t done = atomicAdd(&P.st.ticket[1], 1u);
+		if (done == gridDim.x - 1u) {
+			P.st.ticket[0] = 0;
+			P.st.ticket[1] = 0;
+		}
+	}
+}
+
+}  // namespace qoienc4

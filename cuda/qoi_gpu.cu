@@ -21,6 +21,7 @@
 #include "../include/qoi_gpu.h"
 #include "qoi_dec.cuh"
 #include "qoi_enc.cuh"
+#include "qoi_enc4.cuh"
 #include "qoi_fdec.cuh"
 #include "qoi_plan.h"
 
@@ -36,6 +37,8 @@ struct qoi_gpu_ctx {
 	cudaStream_t s_h2d = nullptr, s_d2h = nullptr; /* one stream per copy direction: PCIe is full duplex */
 	char err[256] = {0};
 	int enc_blocks_per_sm[3] = {0, 0, 0}; /* <4,false>, <4,true>, <3,true> */
+	int enc_striped = 0;                  /* experimental encoder of qoi_enc4.cuh (QOI_GPU_ENC=striped: 1, striped-match: 2); emulator-tested,
+	                                         off by default */
 	bool read_ahead = false;              /* experimental: ring word read one call ahead (QOI_GPU_REFILL=ahead); indexed decoder only */
 	bool refill_uni = true;               /* decoders' stream reader: warp-uniform refill (default) or lane-driven (QOI_GPU_REFILL=lane) */
 	bool walk = true;                     /* look-up variant: word walk (default; 8% faster on photo content) or second-level
@@ -98,6 +101,22 @@ static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
 	return QOI_GPU_OK;
 }
 
+/* experimental striped encoder (qoi_enc4.cuh): same shared-memory layout and grid as the shipped kernels */
+static int enc_striped_setup(qoi_gpu_ctx *ctx) {
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
+	int nb[3] = {0, 0, 0};
+	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[0], qoienc4::qoi_encode_striped_kernel<4, false, false>, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL));
+	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[1], qoienc4::qoi_encode_striped_kernel<4, true, false>, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL));
+	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[2], qoienc4::qoi_encode_striped_kernel<3, true, false>, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL));
+	for (int i = 0; i < 3; i++) ctx->enc_blocks_per_sm[i] = nb[i] > 0 ? nb[i] : 1; /* the grid must not exceed what is co-resident (look-back) */
+	return QOI_GPU_OK;
+}
+
 template <int OUT_CH, int BLOCK>
 static void launch_decode(const QoiDecParams &D, cudaStream_t s, int uni) { /* 0 lane-driven refill, 1 warp-uniform, 2 + word read ahead */
 	const uint32_t grid = (D.n_jobs + BLOCK - 1) / BLOCK;
@@ -139,11 +158,15 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 		const char *rf = getenv("QOI_GPU_REFILL");
 		if (rf && !strcmp(rf, "lane")) c->refill_uni = false;
 		if (rf && !strcmp(rf, "ahead")) c->read_ahead = true;
+		const char *ev = getenv("QOI_GPU_ENC");
+		if (ev && !strcmp(ev, "striped")) c->enc_striped = 1;
+		if (ev && !strcmp(ev, "striped-match")) c->enc_striped = 2;
 	}
 	int rc = enc_occupancy<4, false>(c, &c->enc_blocks_per_sm[0]);
 	if (!rc) rc = enc_occupancy<4, true>(c, &c->enc_blocks_per_sm[1]);
 	if (!rc) rc = enc_occupancy<3, true>(c, &c->enc_blocks_per_sm[2]);
 	if (!rc) rc = fdec_setup(c);
+	if (!rc && c->enc_striped) rc = enc_striped_setup(c);
 	if (rc) {
 		fprintf(stderr, "qoi_gpu: kernel setup failed: %s\n", c->err);
 		cudaStreamDestroy(c->stream);
@@ -251,7 +274,19 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	const int variant = p->geom.channels == 3 ? 2 : (zero_copy ? 0 : 1);
 	uint32_t grid = (uint32_t)(ctx->sm_count * ctx->enc_blocks_per_sm[variant]);
 	if (grid > P.n_tiles) grid = P.n_tiles;
-	if (ctx->walk) {
+	if (ctx->enc_striped) { /* experimental, QOI_GPU_ENC=striped | striped-match */
+		const bool mt = ctx->enc_striped == 2;
+		if (variant == 0) {
+			if (mt) qoienc4::qoi_encode_striped_kernel<4, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
+			else qoienc4::qoi_encode_striped_kernel<4, false, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
+		} else if (variant == 1) {
+			if (mt) qoienc4::qoi_encode_striped_kernel<4, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
+			else qoienc4::qoi_encode_striped_kernel<4, true, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
+		} else {
+			if (mt) qoienc4::qoi_encode_striped_kernel<3, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
+			else qoienc4::qoi_encode_striped_kernel<3, true, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
+		}
+	} else if (ctx->walk) {
 		if (variant == 0) qoienc::qoi_encode_kernel<4, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
 		else if (variant == 1) qoienc::qoi_encode_kernel<4, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
 		else qoienc::qoi_encode_kernel<3, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);

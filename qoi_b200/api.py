@@ -9,7 +9,9 @@ QOI_LINEAR = 1
 TILE_PX = 4096
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libqoi_gpu.so")
+# QOI_GPU_LIB selects another build of the same C ABI (experiments/build_exp.py writes libqoi_gpu_exp.so for A/B runs);
+# it is still a CUDA library with no CPU path, and bench.py records the override in its JSON line.
+_LIB_PATH = os.environ.get("QOI_GPU_LIB") or os.path.join(_HERE, "libqoi_gpu.so")
 _lib = None
 
 _ERRORS = {1: "QOI_GPU_E_ARG", 2: "QOI_GPU_E_CUDA", 3: "QOI_GPU_E_NOMEM", 4: "QOI_GPU_E_STREAM"}

@@ -21,6 +21,7 @@
 #define QOI_EMU 1
 #include "qoi_dec.cuh"
 #include "qoi_enc.cuh"
+#include "qoi_enc4.cuh"
 #include "qoi_fdec.cuh"
 #include "qoi_plan.h"
 
@@ -48,6 +49,9 @@ static std::vector<unsigned char> read_file(const char *path) {
 template <int CH, bool EXPAND>
 static void run_encode(const QoiEncParams &P, unsigned grid, unsigned seed) {
 	using L = qoienc::Layout<CH, EXPAND>;
+	const char *ev = getenv("QOI_EMU_ENC"); /* experimental striped encoder (cuda/qoi_enc4.cuh): striped | striped-match */
+	if (ev && !strcmp(ev, "striped")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, false>(P); }, seed); return; }
+	if (ev && !strcmp(ev, "striped-match")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true>(P); }, seed); return; }
 	qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { if (getenv("QOI_GPU_LOOKUP") && !strcmp(getenv("QOI_GPU_LOOKUP"), "summary")) qoienc::qoi_encode_kernel<CH, EXPAND, false>(P); else qoienc::qoi_encode_kernel<CH, EXPAND, true>(P); }, seed);
 }
 
@@ -182,7 +186,7 @@ int main(int argc, char **argv) {
 				}
 			}
 			/* decode what we wrote: with the restart index, then as a foreign stream */
-			for (int use_index = 1; use_index >= 0; use_index--) {
+			for (int use_index = 1; use_index >= (getenv("QOI_EMU_SKIP_FOREIGN") ? 1 : 0); use_index--) { /* encoder-variant runs skip the any-stream decoder */
 				std::vector<unsigned char> out(g.decoded_bytes + 16, 0xAB);
 				std::vector<int32_t> status(n, -1);
 				QoiDecParams D;

@@ -48,6 +48,45 @@ def test_emulated_distributions(emu, cpu, dist):
     run_enc(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist, ahead)
 
 
+STRIPED = ({"QOI_EMU_ENC": "striped"}, {"QOI_EMU_ENC": "striped-match"})  # cuda/qoi_enc4.cuh (QOI_GPU_ENC=striped | striped-match)
+
+
+def run_variants(emu, img, w, h, ch, n, grid, seed, mis, variants):
+    """Only the experimental variants (the default kernels are covered by run_enc)."""
+    with tempfile.NamedTemporaryFile(suffix=".raw") as f:
+        f.write(np.ascontiguousarray(img, dtype=np.uint8).tobytes())
+        f.flush()
+        for extra in variants:
+            r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
+                               capture_output=True, text=True, timeout=300, env=dict(os.environ, QOI_EMU_SKIP_FOREIGN="1", **extra))
+            assert r.returncode == 0 and r.stdout.startswith("PASS"), str(extra) + ": " + r.stdout + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dist", range(8))
+def test_emulated_striped_encoder_distributions(emu, cpu, dist):
+    """The experimental lane-per-pixel encoder: streams bit exact, its restart index decodes, nothing written out of bounds."""
+    run_variants(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0, STRIPED[dist % 2:dist % 2 + 1])
+    run_variants(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist, STRIPED[1 - dist % 2:2 - dist % 2])
+
+
+def test_emulated_striped_encoder_stress_and_runs(emu, cpu):
+    rng = np.random.default_rng(7)
+    for it in range(6):
+        w = int(rng.integers(60, 300)); h = int(rng.integers(20, 120)); ch = int(rng.integers(3, 5)); n = int(rng.integers(1, 4))
+        img = np.concatenate([q.stress_image(rng, w * h, ch, it % 6) for _ in range(n)])
+        run_variants(emu, img, w, h, ch, n, int(rng.integers(1, 5)), it + 1, int(rng.integers(0, 17)) if it % 2 else 0, STRIPED[it % 2:it % 2 + 1])
+    n = 40000  # runs that cross warp chunks, tiles and the 62 boundary; runs from the image start (qoi.h:396-399)
+    a = np.zeros((n, 4), dtype=np.uint8); a[:, 3] = 255
+    b = np.zeros((n, 4), dtype=np.uint8)
+    c = np.zeros((n, 4), dtype=np.uint8); c[:, 3] = 255; c[n // 2:] = (9, 9, 9, 255); c[-5:] = (0, 0, 0, 255)
+    d = np.full((n, 4), 200, dtype=np.uint8); d[12345] = (1, 2, 3, 4)
+    for k, img in enumerate((a, b, c, d)):
+        if k % 2 == 0:
+            run_variants(emu, img.reshape(-1), 400, 100, 4, 1, 4, 3, 0, STRIPED[:1])
+        else:
+            run_variants(emu, np.ascontiguousarray(img[:, :3]).reshape(-1), 400, 100, 3, 1, 3, 4, 5, STRIPED[(k // 2) % 2:(k // 2) % 2 + 1])
+
+
 def test_emulated_stress(emu, cpu):
     rng = np.random.default_rng(7)
     for it in range(18):
