@@ -317,3 +317,51 @@ def test_unchanged_tools_on_gpu(tmp_path, cpu):
         pytest.skip("dropin/qoibench and dropin/qoiconv are built where the reference sources are (build()); not present")
     out = run_tools_and_check(cpu, tmp_path, qoiconv, qoibench)
     assert "decode ms" in out
+
+# ----------------------------------------------------------------------------- qoiconv for directories (batch API)
+def check_dir_tool(cpu, tmp_path, env):
+    """dropin/qoiconv_dir: png -> qoi for a directory in several batches, bit exact; qoi -> png back, pixel exact."""
+    chk = cpu.best()
+    items = png_corpus(cpu, str(tmp_path / "images"))
+    top = {k: v for k, v in items.items() if os.path.dirname(k) == str(tmp_path / "images")}  # the tool does not recurse
+    out, back = tmp_path / "qoi", tmp_path / "back"
+    out.mkdir(); back.mkdir()
+    tool = os.path.join(DROPIN, "qoiconv_dir")
+    r = subprocess.run([tool, str(tmp_path / "images"), str(out), "--budget-mpx", "0.01", "--verify"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"{len(top)} files" in r.stdout and " 0 failed" in r.stdout
+    assert int(r.stdout.split(" files in ")[1].split()[0]) >= 3  # RGB and RGBA batches, split further by the tiny budget
+    for name, (w, h, ch, px) in top.items():
+        q = out / (os.path.basename(name)[:-4] + ".qoi")
+        assert q.read_bytes() == chk.encode(px, w, h, ch), name
+    r = subprocess.run([tool, str(out), str(back)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and " 0 failed" in r.stdout, r.stdout + r.stderr
+    for name, (w, h, ch, px) in top.items():
+        im = PIL.open(back / os.path.basename(name))
+        assert im.size == (w, h) and (np.asarray(im).reshape(-1) == px).all(), name
+    r = subprocess.run([tool, str(tmp_path / "nothing-here"), str(back)], capture_output=True, text=True, env=env)
+    assert r.returncode == 1
+
+
+def test_directory_converter_host_logic_with_cpu_double(tmp_path, cpu):
+    """Batching, pinned-slot layout, file I/O and the reader/GPU/writer ring of dropin/qoiconv_dir.c, with the batch entry
+    points of libqoi_gpu.so replaced (LD_PRELOAD) by a TEST DOUBLE over the CPU checker -- tests/shim/, never shipped."""
+    import __graft_entry__ as g
+
+    g.build()
+    make("qoiconv_dir")
+    double = os.path.join(ROOT, "tests", "shim", "libqoi_gpu_cpu_double.so")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-shared", "-fPIC", os.path.join(ROOT, "tests", "shim", "qoi_gpu_cpu_double.c"),
+                           "-I" + os.path.join(ROOT, "include"), "-o", double, "-L" + os.path.join(ROOT, "oracle"), "-loracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    check_dir_tool(cpu, tmp_path, dict(os.environ, LD_PRELOAD=double, OMP_NUM_THREADS="4"))
+    # without the double (and without a device) the tool refuses: no CPU path
+    r = subprocess.run([os.path.join(DROPIN, "qoiconv_dir"), str(tmp_path / "images"), str(tmp_path / "qoi")], capture_output=True, text=True)
+    assert r.returncode == 2 and "no usable CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_directory_converter_on_gpu(tmp_path, cpu):
+    if not os.path.exists(os.path.join(DROPIN, "qoiconv_dir")):
+        pytest.skip("dropin/qoiconv_dir not built (build() builds it)")
+    check_dir_tool(cpu, tmp_path, dict(os.environ))
