@@ -1,6 +1,6 @@
 /*
  * selftest.c -- drives the three stand-ins of dropin/compat/ the way the reference's tools do and
- * dumps what they produce, so that tests/test_dropin_tools.py can compare it with independently
+ * dumps what they produce, so that tests/test_zz_dropin_tools.py can compare it with independently
  * computed pixels. PNG I/O only; no QOI code is involved.
  *
  *   selftest decode in.png out.raw      -> stbi_info + stbi_load(req = 3 if the file has 3 channels else 4)

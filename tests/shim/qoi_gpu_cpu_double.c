@@ -5,7 +5,7 @@
  * GPU, so its batching, file handling and threading are exercised here by LD_PRELOADing this object in front
  * of libqoi_gpu.so: the handful of include/qoi_gpu.h entry points the tool uses are re-implemented on the CPU
  * checker (oracle/liboracle.so: ora_encode / ora_decode, the restatement of qoi.h).  Only tests/ builds and loads
- * it (tests/test_dropin_tools.py); on the GPU box the same tool runs against the real library.
+ * it (tests/test_zz_dropin_tools.py); on the GPU box the same tool runs against the real library.
  */
 #include <stdint.h>
 #include <stdio.h>

@@ -3,6 +3,9 @@
 qoibench.c / qoiconv.c need <png.h>, stb_image.h and stb_image_write.h for their PNG I/O (qoibench.c:17-25,
 qoiconv.c:23-26); none is in the image, so dropin/compat/ carries zlib-backed stand-ins with the same entry points.
 
+(The file name sorts last on purpose: the GPU tests below drive separate processes and have not run on a box yet, so the
+parity tests of test_gpu_parity.py come first under `pytest -x`.)
+
 CPU part (here): the stand-ins are checked against independently computed pixels (numpy + a tiny PNG writer in this
 file, and Pillow both ways) for every colour type / bit depth / interlace mode, and the two tools are built from the
 byte-identical reference sources against the REFERENCE qoi.h (dropin/_ref/, no GPU code) to show the tool + stand-in
