@@ -79,8 +79,12 @@ __device__ __forceinline__ void ballot_and_mask(uint32_t x, uint32_t &plane, uin
 #endif
 }
 
-/* MATCH: same-slot lanes from match.any instead of six ballots (A/B switch) */
-template <int CH, bool EXPAND, bool MATCH>
+/* MATCH: same-slot lanes from match.any instead of six ballots (A/B switch).
+   EARLYW: phase W does not wait for the tile's output offset -- the op bytes are staged from offset 0 as soon as the warp
+   totals are known, the wait for B_READY comes afterwards (the look-back latency hides behind the emission) and the compute
+   warps copy the staging buffer out themselves with a byte-shifted 16-byte copy, instead of the loader's bulk store (which
+   needs source and destination congruent mod 16).  The STAGE_FREE hand-off is not needed then. */
+template <int CH, bool EXPAND, bool MATCH, bool EARLYW = false>
 __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(const QoiEncParams P) {
 	using L = Layout<CH, EXPAND>;
 	using S = Sub<CH, EXPAND>;
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 		fetch_issue<CH, EXPAND>(P, smem, F, 0, 0);
 		__syncwarp();
 		bar_arrive(BAR_INFO_READY, QOI_N_ALL);
-		bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
+		if (!EARLYW) bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
 	}
 
 	int cur = 0;
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 				const uint32_t lo_off = (padb + 15u) & ~15u;
 				const uint32_t end = padb + total;
 				const uint32_t hi_off = end & ~15u;
-				const bool bulk = hi_off > lo_off;
+				const bool bulk = !EARLYW && hi_off > lo_off;
 				if (lane == 0 && bulk) {
 					fence_proxy_async_smem();
 					tma_store_1d_hint(gdst + (lo_off - padb), stage + lo_off, hi_off - lo_off, l2_evict_first_policy());
@@ -155,8 +159,10 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 				}
 				const uint32_t a_hi = bulk ? lo_off : end;
 				const uint32_t b_lo = bulk ? hi_off : end;
-				for (uint32_t o = padb + lane; o < a_hi; o += 32) gdst[o - padb] = stage[o];
-				for (uint32_t o = b_lo + lane; o < end; o += 32) gdst[o - padb] = stage[o];
+				if (!EARLYW) { /* EARLYW: the compute warps have copied everything out before W_DONE */
+					for (uint32_t o = padb + lane; o < a_hi; o += 32) gdst[o - padb] = stage[o];
+					for (uint32_t o = b_lo + lane; o < end; o += 32) gdst[o - padb] = stage[o];
+				}
 				if (t == ti.first_tile && lane < QOI_HEADER_BYTES) { /* header, qoi.h:384-388 */
 					const uint32_t k = lane;
 					uint8_t b;
@@ -173,10 +179,10 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 					if (k < QOI_END_BYTES) gstream[fin + k] = (k == QOI_END_BYTES - 1) ? 1 : 0;
 					else P.lens[ti.img] = (int32_t)(fin + QOI_END_BYTES);
 				}
-				if (lane == 0) tma_store_wait_read(); /* the bulk store has finished reading the staging buffer */
+				if (!EARLYW && lane == 0) tma_store_wait_read(); /* the bulk store has finished reading the staging buffer */
 			}
 			__syncwarp();
-			bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
+			if (!EARLYW) bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
 		} else if (scout) {
 			/* =============================== scout warp =============================== */
 			bar_sync(BAR_I_DONE, QOI_N_CS); /* the per-warp tables and wlnr[] of this tile are complete */
@@ -476,13 +482,19 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 			__syncwarp();
 			bar_arrive(BAR_C_DONE, QOI_N_CS);
 
-			bar_sync(BAR_B_READY, QOI_N_CS);
-			bar_sync(BAR_STAGE_FREE, QOI_N_CS); /* the previous tile's bulk store has drained the staging buffer */
-			/* ---- phase W: op bytes -> staging (alignment congruent to the destination) ---- */
-			const uint32_t tile_base = misc[MISC_TILE_BASE];
-			const uint32_t padb = (uint32_t)((uintptr_t)(gstream + tile_base) & 15u);
+			uint32_t tile_base = 0, padb = 0;
+			if (EARLYW) {
+				bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE); /* wtot[] of every warp is visible; every warp is past its last use of the staging buffer */
+			} else {
+				bar_sync(BAR_B_READY, QOI_N_CS);
+				bar_sync(BAR_STAGE_FREE, QOI_N_CS); /* the previous tile's bulk store has drained the staging buffer */
+				tile_base = misc[MISC_TILE_BASE];
+				padb = (uint32_t)((uintptr_t)(gstream + tile_base) & 15u); /* staging congruent to the destination */
+			}
+			/* ---- phase W: op bytes -> staging ---- */
 			uint32_t rowbase = 0;
 			for (uint32_t w = 0; w < warp; w++) rowbase += wtot[w];
+			uint32_t rs_off = 0xFFFFFFFFu; /* tile-relative byte offset of the restart op, in the lane that owns the restart pixel */
 #pragma unroll
 			for (int s = 0; s < QOI_WARP_STEPS; s++) {
 				const uint32_t il = wbase + (uint32_t)s * 32u + lane;
@@ -490,11 +502,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 				const uint32_t cd = code[s];
 				const uint32_t sz = cd & 7u;
 				unsigned char *o = stage + padb + off;
-				if (s < 2 && warp == 0 && (int32_t)il == cand) { /* the owner of the restart pixel records where its op starts */
-					P.st.rs_px[t] = (int32_t)(ti.px0 + il);
-					P.st.rs_byte[t] = (int32_t)(tile_base + off);
-					P.st.rs_prev[t] = pxv[(int)il - 1];
-				}
+				if (s < 2 && warp == 0 && (int32_t)il == cand) rs_off = off;
 				if (sz) {
 					o[0] = (uint8_t)(cd >> 8);
 					if (sz >= 2) {
@@ -508,6 +516,38 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 					}
 				}
 				rowbase += (tot4[s >> 2] >> (8 * (s & 3))) & 0xFFu;
+			}
+			if (EARLYW) {
+				bar_sync(BAR_B_READY, QOI_N_CS);
+				tile_base = misc[MISC_TILE_BASE];
+			}
+			if (rs_off != 0xFFFFFFFFu) { /* the owner of the restart pixel records where its op starts */
+				P.st.rs_px[t] = (int32_t)ti.px0 + cand;
+				P.st.rs_byte[t] = (int32_t)(tile_base + rs_off);
+				P.st.rs_prev[t] = pxv[cand - 1];
+			}
+			if (EARLYW) {
+				bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE); /* the staging buffer is complete */
+				const uint32_t total = misc[MISC_TILE_TOTAL];
+				uint8_t *gdst = gstream + tile_base;
+				uint32_t head = (16u - (uint32_t)((uintptr_t)gdst & 15u)) & 15u; /* bytes up to the first aligned 16 */
+				if (head > total) head = total;
+				const uint32_t nvec = (total - head) >> 4;
+				if (tid < head) gdst[tid] = stage[tid];
+				const uint32_t *s32 = (const uint32_t *)stage + (head >> 2);
+				const uint32_t sh = (head & 3u) * 8u;
+				for (uint32_t k = tid; k < nvec; k += QOI_ENC_COMPUTE) {
+					const uint32_t *w = s32 + 4u * k;
+					const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
+					uint4 q;
+					q.x = __funnelshift_r(w0, w1, sh);
+					q.y = __funnelshift_r(w1, w2, sh);
+					q.z = __funnelshift_r(w2, w3, sh);
+					q.w = __funnelshift_r(w3, w4, sh);
+					*(uint4 *)(gdst + head + 16u * k) = q;
+				}
+				const uint32_t tail0 = head + 16u * nvec;
+				if (tail0 + tid < total) gdst[tail0 + tid] = stage[tail0 + tid]; /* fewer than 16 bytes */
 			}
 			if (tid == 0 && cand == INT_MAX) P.st.rs_px[t] = -1;
 			__syncwarp();

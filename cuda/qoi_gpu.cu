@@ -37,7 +37,7 @@ struct qoi_gpu_ctx {
 	cudaStream_t s_h2d = nullptr, s_d2h = nullptr; /* one stream per copy direction: PCIe is full duplex */
 	char err[256] = {0};
 	int enc_blocks_per_sm[3] = {0, 0, 0}; /* <4,false>, <4,true>, <3,true> */
-	int enc_striped = 0;                  /* experimental encoder of qoi_enc4.cuh (QOI_GPU_ENC=striped: 1, striped-match: 2); emulator-tested,
+	int enc_striped = 0;                  /* experimental encoder of qoi_enc4.cuh (QOI_GPU_ENC=striped: 1, striped-match: 2, striped-earlyw: 3); emulator-tested,
 	                                         off by default */
 	bool read_ahead = false;              /* experimental: ring word read one call ahead (QOI_GPU_REFILL=ahead); indexed decoder only */
 	bool refill_uni = true;               /* decoders' stream reader: warp-uniform refill (default) or lane-driven (QOI_GPU_REFILL=lane) */
@@ -106,6 +106,9 @@ static int enc_striped_setup(qoi_gpu_ctx *ctx) {
 	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
 	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
 	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
 	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
 	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
 	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
@@ -161,6 +164,7 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 		const char *ev = getenv("QOI_GPU_ENC");
 		if (ev && !strcmp(ev, "striped")) c->enc_striped = 1;
 		if (ev && !strcmp(ev, "striped-match")) c->enc_striped = 2;
+		if (ev && !strcmp(ev, "striped-earlyw")) c->enc_striped = 3;
 	}
 	int rc = enc_occupancy<4, false>(c, &c->enc_blocks_per_sm[0]);
 	if (!rc) rc = enc_occupancy<4, true>(c, &c->enc_blocks_per_sm[1]);
@@ -275,8 +279,12 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	uint32_t grid = (uint32_t)(ctx->sm_count * ctx->enc_blocks_per_sm[variant]);
 	if (grid > P.n_tiles) grid = P.n_tiles;
 	if (ctx->enc_striped) { /* experimental, QOI_GPU_ENC=striped | striped-match */
-		const bool mt = ctx->enc_striped == 2;
-		if (variant == 0) {
+		const bool mt = ctx->enc_striped == 2, ew = ctx->enc_striped == 3;
+		if (ew) {
+			if (variant == 0) qoienc4::qoi_encode_striped_kernel<4, false, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
+			else if (variant == 1) qoienc4::qoi_encode_striped_kernel<4, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
+			else qoienc4::qoi_encode_striped_kernel<3, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
+		} else if (variant == 0) {
 			if (mt) qoienc4::qoi_encode_striped_kernel<4, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
 			else qoienc4::qoi_encode_striped_kernel<4, false, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
 		} else if (variant == 1) {

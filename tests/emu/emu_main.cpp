@@ -51,6 +51,7 @@ static void run_encode(const QoiEncParams &P, unsigned grid, unsigned seed) {
 	using L = qoienc::Layout<CH, EXPAND>;
 	const char *ev = getenv("QOI_EMU_ENC"); /* experimental striped encoder (cuda/qoi_enc4.cuh): striped | striped-match */
 	if (ev && !strcmp(ev, "striped")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, false>(P); }, seed); return; }
+	if (ev && !strcmp(ev, "striped-earlyw")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, false, true>(P); }, seed); return; }
 	if (ev && !strcmp(ev, "striped-match")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true>(P); }, seed); return; }
 	qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { if (getenv("QOI_GPU_LOOKUP") && !strcmp(getenv("QOI_GPU_LOOKUP"), "summary")) qoienc::qoi_encode_kernel<CH, EXPAND, false>(P); else qoienc::qoi_encode_kernel<CH, EXPAND, true>(P); }, seed);
 }

@@ -48,7 +48,9 @@ def test_emulated_distributions(emu, cpu, dist):
     run_enc(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist, ahead)
 
 
-STRIPED = ({"QOI_EMU_ENC": "striped"}, {"QOI_EMU_ENC": "striped-match"})  # cuda/qoi_enc4.cuh (QOI_GPU_ENC=striped | striped-match)
+# cuda/qoi_enc4.cuh (QOI_GPU_ENC=striped | striped-match | striped-earlyw); the tests below alternate between the first two ...
+STRIPED = ({"QOI_EMU_ENC": "striped"}, {"QOI_EMU_ENC": "striped-match"})
+STRIPED_EARLYW = ({"QOI_EMU_ENC": "striped-earlyw"},)  # ... and run this one on a subset
 
 
 def run_variants(emu, img, w, h, ch, n, grid, seed, mis, variants):
@@ -67,6 +69,9 @@ def test_emulated_striped_encoder_distributions(emu, cpu, dist):
     """The experimental lane-per-pixel encoder: streams bit exact, its restart index decodes, nothing written out of bounds."""
     run_variants(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0, STRIPED[dist % 2:dist % 2 + 1])
     run_variants(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist, STRIPED[1 - dist % 2:2 - dist % 2])
+    if dist in (3, 4, 7):
+        run_variants(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 30 + dist, 0, STRIPED_EARLYW)
+        run_variants(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 40 + dist, dist, STRIPED_EARLYW)
 
 
 def test_emulated_striped_encoder_stress_and_runs(emu, cpu):

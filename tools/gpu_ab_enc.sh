@@ -24,6 +24,7 @@ run_variant() {  # name, env assignments...
 run_variant default QOI_GPU_NOP=1
 run_variant striped QOI_GPU_ENC=striped
 run_variant stripedmatch QOI_GPU_ENC=striped-match
+run_variant stripedearlyw QOI_GPU_ENC=striped-earlyw
 if [ -f "$EXP" ]; then run_variant earlyw QOI_GPU_LIB=$EXP QOI_GPU_ENC=earlyw; fi
 python tools/bench_summary.py gpurun_out/ab_enc_*_d*.json
 # one ncu capture of the striped kernel for the line profile (tools/ncu_lines.py reads it here)
