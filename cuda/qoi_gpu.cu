@@ -37,6 +37,9 @@ struct qoi_gpu_ctx {
 	cudaStream_t s_h2d = nullptr, s_d2h = nullptr; /* one stream per copy direction: PCIe is full duplex */
 	char err[256] = {0};
 	int enc_blocks_per_sm[3] = {0, 0, 0}; /* <4,false>, <4,true>, <3,true> */
+#ifdef QOI_EXP_EARLYW
+	bool enc_earlyw = false;              /* experimental build only (experiments/encoder_earlyw.patch): QOI_GPU_ENC=earlyw */
+#endif
 	int enc_striped = 0;                  /* experimental encoder of qoi_enc4.cuh (QOI_GPU_ENC=striped: 1, striped-match: 2, striped-earlyw: 3); emulator-tested,
 	                                         off by default */
 	bool read_ahead = false;              /* experimental: ring word read one call ahead (QOI_GPU_REFILL=ahead); indexed decoder only */
@@ -95,6 +98,9 @@ static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
 	using L = qoienc::Layout<CH, EXPAND>;
 	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
 	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+#ifdef QOI_EXP_EARLYW
+	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+#endif
 	int nb = 0;
 	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qoienc::qoi_encode_kernel<CH, EXPAND, false>, QOI_ENC_THREADS, L::TOTAL));
 	*out = nb > 0 ? nb : 1;
@@ -162,6 +168,9 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 		if (rf && !strcmp(rf, "lane")) c->refill_uni = false;
 		if (rf && !strcmp(rf, "ahead")) c->read_ahead = true;
 		const char *ev = getenv("QOI_GPU_ENC");
+#ifdef QOI_EXP_EARLYW
+		if (ev && !strcmp(ev, "earlyw")) c->enc_earlyw = true;
+#endif
 		if (ev && !strcmp(ev, "striped")) c->enc_striped = 1;
 		if (ev && !strcmp(ev, "striped-match")) c->enc_striped = 2;
 		if (ev && !strcmp(ev, "striped-earlyw")) c->enc_striped = 3;
@@ -294,6 +303,12 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 			if (mt) qoienc4::qoi_encode_striped_kernel<3, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
 			else qoienc4::qoi_encode_striped_kernel<3, true, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
 		}
+#ifdef QOI_EXP_EARLYW
+	} else if (ctx->enc_earlyw) { /* experimental build only, QOI_GPU_ENC=earlyw */
+		if (variant == 0) qoienc::qoi_encode_kernel<4, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
+		else if (variant == 1) qoienc::qoi_encode_kernel<4, true, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
+		else qoienc::qoi_encode_kernel<3, true, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
+#endif
 	} else if (ctx->walk) {
 		if (variant == 0) qoienc::qoi_encode_kernel<4, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
 		else if (variant == 1) qoienc::qoi_encode_kernel<4, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);

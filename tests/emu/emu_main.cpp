@@ -50,6 +50,9 @@ template <int CH, bool EXPAND>
 static void run_encode(const QoiEncParams &P, unsigned grid, unsigned seed) {
 	using L = qoienc::Layout<CH, EXPAND>;
 	const char *ev = getenv("QOI_EMU_ENC"); /* experimental striped encoder (cuda/qoi_enc4.cuh): striped | striped-match */
+#ifdef QOI_EXP_EARLYW /* experimental build only (experiments/encoder_earlyw.patch) */
+	if (ev && !strcmp(ev, "earlyw")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc::qoi_encode_kernel<CH, EXPAND, true, true>(P); }, seed); return; }
+#endif
 	if (ev && !strcmp(ev, "striped")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, false>(P); }, seed); return; }
 	if (ev && !strcmp(ev, "striped-earlyw")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, false, true>(P); }, seed); return; }
 	if (ev && !strcmp(ev, "striped-match")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true>(P); }, seed); return; }
