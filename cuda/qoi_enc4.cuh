@@ -1,7 +1,8 @@
 /*
  * qoi_enc4.cuh -- EXPERIMENTAL "striped" variant of the chained-scan encoder (QOI_GPU_ENC=striped | striped-match).
- * OFF BY DEFAULT.  Checked bit-exact on the CPU emulator (tests/test_emu.py), NOT YET RUN ON A GPU: the round's
- * GPU minutes were spent when it was written.  The shipped encoder is qoi_enc.cuh; this file only adds kernels.
+ * OFF BY DEFAULT.  Checked bit-exact on the CPU emulator (tests/test_emu.py) and, once, on a B200 (tools/striped_smoke.c:
+ * streams byte-identical to the shipped encoder, 8-12 % slower -- profiles/r1_final/striped_smoke.txt; not profiled yet).
+ * The shipped encoder is qoi_enc.cuh; this file only adds kernels.
  *
  * Same CTA skeleton, look-back records, loader and scout protocol as qoi_enc.cuh (reference loop: qoi.h:406-478);
  * what changes is how the 8 compute warps walk a tile.  There a THREAD owns 16 consecutive pixels and finds the
