@@ -80,13 +80,283 @@ __device__ __forceinline__ void ballot_and_mask(uint32_t x, uint32_t &plane, uin
 #endif
 }
 
+
+/* ---------------------------------------------------------------- "slab" mode (QOI_GPU_ENC=slab | slab-match) */
+/*
+ * What the first GPU run of the striped kernel said (profiles/r1_final/striped_smoke.txt): 40 % fewer instructions did not
+ * buy time, so the limiter is dependent latency and (probably) instruction fetch -- the striped main pass is unrolled 16 x
+ * because it keeps one op code per row in registers, ~7 700 SASS instructions of which every warp walks most once per tile.
+ * Slab mode keeps the striped idea and removes both: rolled loops, nothing kept per row in registers.
+ *
+ *   index pass   (before T_READY) the serial part only: non-run mask, same-slot predecessor, per-warp table, deferred
+ *                first occurrences; leaves one non-run word and one hit word per row in shared memory
+ *   phase R      sets the hit bits of the deferred pixels in those words
+ *   emit pass    (after T_READY) rows are independent now: classify, sizes, packed scan over four rows, and the op bytes
+ *                go straight into the warp's own SLAB of the staging area (512 px x 5 bytes) at a running offset
+ *   copy-out     after B_READY every warp copies its slab to tile_base + (bytes of the warps before it) with a
+ *                byte-shifted 16-byte copy -- no second pass over the ops, no staging hand-off, no bulk store
+ */
+template <int CH, bool EXPAND>
+struct SubSlab {
+	using L = Layout<CH, EXPAND>;
+	static constexpr int SLAB_BYTES = QOI_WARP_PX * (CH + 1) + 16; /* worst case of a chunk + room for the shifted copy's last word */
+	static constexpr int OFF_SLAB = L::OFF_CELLS;
+	static constexpr int OFF_LENT = OFF_SLAB + QOI_ENC_WARPS * SLAB_BYTES;
+	static constexpr int OFF_FPOS = OFF_LENT + QOI_ENC_WARPS * 64 * 8;
+	static constexpr int OFF_HITW = OFF_FPOS + QOI_ENC_WARPS * 64 * 2;                   /* u32 [8][16] */
+	static constexpr int OFF_NRW = OFF_HITW + QOI_ENC_WARPS * QOI_WARP_STEPS * 4;        /* u32 [8][16] */
+	static constexpr int END = OFF_NRW + QOI_ENC_WARPS * QOI_WARP_STEPS * 4;
+	static_assert(END <= L::OFF_CELLS + L::CELLS_BYTES, "slab mode must fit into the bit-matrix area");
+	static_assert(SLAB_BYTES % 16 == 0 && OFF_LENT % 8 == 0, "alignment");
+};
+
+template <int CH, bool EXPAND, bool MATCH>
+__device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned char *smem, const TileInfo &ti, const uint32_t *pxv,
+                                             uint8_t *gstream) {
+	using L = Layout<CH, EXPAND>;
+	using S = SubSlab<CH, EXPAND>;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const uint32_t t = (uint32_t)ti.tile;
+	unsigned char *slab = smem + S::OFF_SLAB + warp * S::SLAB_BYTES;
+	uint2 *Lent_all = (uint2 *)(smem + S::OFF_LENT);
+	uint2 *Lent = Lent_all + warp * 64;
+	uint16_t *Fpos = (uint16_t *)(smem + S::OFF_FPOS) + warp * 64;
+	uint32_t *hitw = (uint32_t *)(smem + S::OFF_HITW) + warp * QOI_WARP_STEPS;
+	uint32_t *nrw = (uint32_t *)(smem + S::OFF_NRW) + warp * QOI_WARP_STEPS;
+	const uint32_t *Tin_val = (const uint32_t *)(smem + L::OFF_TINVAL);
+	const uint8_t *Tin_flag = (const uint8_t *)(smem + L::OFF_TINFLAG);
+	uint32_t *wtot = (uint32_t *)(smem + L::OFF_WTOT);
+	int32_t *wlnr = (int32_t *)(smem + L::OFF_WLNR);
+	const int32_t *wlnr_in = (const int32_t *)(smem + L::OFF_WLNRIN);
+	const uint32_t *misc = (const uint32_t *)(smem + L::OFF_MISC);
+
+	Lent[lane] = make_uint2(0u, 0u);
+	Lent[lane + 32] = make_uint2(0u, 0u);
+	Fpos[lane] = 0xFFFFu;
+	Fpos[lane + 32] = 0xFFFFu;
+	if (lane < QOI_WARP_STEPS) {
+		hitw[lane] = 0u;
+		nrw[lane] = 0u;
+	}
+	__syncwarp();
+
+	const uint32_t nv = ti.n_valid; /* <= 4096; only an image's last tile can be partial */
+	const bool last_tile = ti.px0 + ti.n_valid == ti.npx;
+	const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
+	const uint32_t wbase = warp * (uint32_t)QOI_WARP_PX;
+
+	/* ---- index pass: the only part in which a row depends on the row before it (through the warp's table) ---- */
+	{
+		int32_t last_nr = -1; /* tile-local index of the last non-run pixel of this chunk so far (uniform) */
+		uint32_t v = pxv[wbase + lane], p = pxv[(int)(wbase + lane) - 1]; /* row 0; the next row's pixels are loaded a row ahead */
+#pragma unroll 1
+		for (int s = 0; s < QOI_WARP_STEPS; s++) {
+			const uint32_t rb0 = wbase + (uint32_t)s * 32u;
+			if (rb0 >= nv) break; /* uniform */
+			const uint32_t il = rb0 + lane;
+			const uint32_t iln = (s + 1 < QOI_WARP_STEPS) ? il + 32u : il; /* stays inside pxv[-1 .. 4096] */
+			const uint32_t v_next = pxv[iln], p_next = pxv[(int)iln - 1];
+			const bool nonrun = il < nv && v != p; /* qoi.h:415 */
+			const uint32_t nr = __ballot_sync(QOI_FULL_MASK, nonrun);
+			const uint32_t h = qoi_slot(v);
+			uint32_t m; /* the non-run lanes of this row with my slot */
+			if (MATCH) {
+				m = __match_any_sync(QOI_FULL_MASK, nonrun ? h : 64u + lane);
+			} else {
+				uint32_t differ = 0;
+#pragma unroll
+				for (int b = 0; b < 6; b++) {
+					uint32_t plane, mine;
+					ballot_and_mask(h & (1u << b), plane, mine);
+					differ |= plane ^ mine;
+				}
+				m = nr & ~differ;
+			}
+			const uint32_t lower = m & lt;
+			const int src = lower ? (31 - __clz((int)lower)) : (int)lane;
+			const uint32_t pv = __shfl_sync(QOI_FULL_MASK, v, src);
+			const uint2 ent = Lent[h];
+			bool hit = false;
+			if (nonrun) {
+				if (lower) hit = (pv == v);          /* predecessor with my slot inside this row */
+				else if (ent.y) hit = (ent.x == v);  /* ... in an earlier row of this chunk */
+				else Fpos[h] = (uint16_t)il;         /* first pixel of the slot in the chunk: phase R decides */
+			}
+			const uint32_t hb = __ballot_sync(QOI_FULL_MASK, hit);
+			__syncwarp();
+			if (nonrun && (m & gt) == 0u) Lent[h] = make_uint2(v, 1u); /* last pixel of its slot in this row */
+			if (lane == 0) {
+				nrw[s] = nr;
+				hitw[s] = hb;
+			}
+			if (nr) last_nr = (int32_t)(rb0 + 31u - (uint32_t)__clz((int)nr));
+			__syncwarp();
+			v = v_next;
+			p = p_next;
+		}
+		if (lane == 0) wlnr[warp] = last_nr;
+	}
+	__syncwarp();
+	bar_arrive(BAR_I_DONE, QOI_N_CS);
+
+	bar_sync(BAR_T_READY, QOI_N_CS); /* every warp's table is final; T_in and the run carry are in shared memory */
+	/* ---- phase R: my chunk's deferred pixels against the earlier warps' tables, then the incoming table ---- */
+#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		const uint32_t sl = lane + 32u * q;
+		const uint32_t pos = Fpos[sl];
+		if (pos != 0xFFFFu) {
+			const uint32_t pvv = pxv[pos];
+			bool found = false;
+			uint32_t val = 0;
+			for (int w2 = (int)warp - 1; w2 >= 0; w2--) {
+				const uint2 e = Lent_all[w2 * 64 + sl];
+				if (e.y) {
+					val = e.x;
+					found = true;
+					break;
+				}
+			}
+			if (!found && Tin_flag[sl]) {
+				val = Tin_val[sl];
+				found = true;
+			}
+			/* an untouched index[] slot holds 0 (qoi.h:393): only the all-zero pixel can hit it */
+			const bool hit = found ? (val == pvv) : (pvv == 0u);
+			if (hit) atomicOr(&hitw[(pos >> 5) & (QOI_WARP_STEPS - 1)], 1u << (pos & 31u));
+		}
+	}
+	__syncwarp();
+	/* last non-run pixel before the chunk (image coordinates; -1: none since the image start) */
+	int32_t lnr_img = wlnr_in[0];
+	for (int w2 = (int)warp - 1; w2 >= 0; w2--) {
+		if (wlnr[w2] >= 0) {
+			lnr_img = (int32_t)ti.px0 + wlnr[w2];
+			break;
+		}
+	}
+
+	/* ---- emit pass: four independent rows at a time; op bytes go into the warp's slab at a running offset ---- */
+	uint32_t off = 0;                 /* bytes of this chunk so far (uniform) */
+	int32_t cand = INT_MAX;           /* decoder restart point: first pixel of the tile at which an op starts (warp 0) */
+	uint32_t rs_off = 0xFFFFFFFFu;    /* its byte offset, in the lane that owns the pixel */
+#pragma unroll 1
+	for (int g = 0; g < QOI_WARP_STEPS / 4; g++) {
+		if (wbase + (uint32_t)g * 128u >= nv) break; /* uniform */
+		uint32_t cd[4];
+		uint32_t starts = 0; /* warp 0, group 0: bit k = an op starts at my pixel of row k */
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const int s = 4 * g + k;
+			const uint32_t rb0 = wbase + (uint32_t)s * 32u;
+			const uint32_t il = rb0 + lane;
+			const uint32_t nr = nrw[s], hb = hitw[s];
+			uint32_t c = 0;
+			if (rb0 < nv) { /* uniform */
+				const uint32_t v = pxv[il], p = pxv[(int)il - 1];
+				const bool valid = il < nv;
+				const bool nonrun = (nr >> lane) & 1u;
+				if (nonrun) {
+					c = ((hb >> lane) & 1u) ? (1u | (qoi_slot(v) << 8)) : classify_bf(v, p); /* qoi.h:432-434 / 438-474 */
+				} else if (valid) { /* qoi.h:415-421 */
+					const uint32_t below = nr & lt;
+					const int32_t lnr = below ? (int32_t)(ti.px0 + rb0 + 31u - (uint32_t)__clz((int)below)) : lnr_img;
+					const uint32_t gi = ti.px0 + il;
+					c = run_code(gi - (uint32_t)lnr, (last_tile && gi == ti.npx - 1u) || pxv[il + 1] != v);
+				}
+				if (warp == 0 && g == 0 && k < 2 && valid && (nonrun || ((c >> 8) & 0x3Fu) == 0u)) starts |= 1u << k;
+				if (nr) lnr_img = (int32_t)(ti.px0 + rb0 + 31u - (uint32_t)__clz((int)nr));
+			}
+			cd[k] = c;
+		}
+		/* packed inclusive scan of the four rows' sizes (a row holds <= 160 bytes) */
+		const uint32_t pk = (cd[0] & 7u) | ((cd[1] & 7u) << 8) | ((cd[2] & 7u) << 16) | ((cd[3] & 7u) << 24);
+		uint32_t incl = pk;
+#pragma unroll
+		for (int dlt = 1; dlt < 32; dlt <<= 1) {
+			const uint32_t o = __shfl_up_sync(QOI_FULL_MASK, incl, dlt);
+			if (lane >= (uint32_t)dlt) incl += o;
+		}
+		const uint32_t ex = incl - pk, tot = __shfl_sync(QOI_FULL_MASK, incl, 31);
+		if (warp == 0 && g == 0) {
+#pragma unroll
+			for (int k = 0; k < 2; k++) {
+				const uint32_t b = __ballot_sync(QOI_FULL_MASK, (starts >> k) & 1u);
+				if (b && cand == INT_MAX) {
+					cand = (int32_t)((uint32_t)k * 32u + (uint32_t)__ffs((int)b) - 1u);
+					if ((int32_t)((uint32_t)k * 32u + lane) == cand) rs_off = off + (k ? (tot & 0xFFu) : 0u) + ((ex >> (8 * k)) & 0xFFu);
+				}
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const uint32_t c = cd[k], sz = c & 7u;
+			unsigned char *o = slab + off + ((ex >> (8 * k)) & 0xFFu);
+			if (sz) {
+				o[0] = (uint8_t)(c >> 8);
+				if (sz >= 2) {
+					o[1] = (uint8_t)(c >> 16);
+					if (sz >= 4) {
+						const uint32_t v = pxv[wbase + (uint32_t)(4 * g + k) * 32u + lane];
+						o[2] = (uint8_t)(v >> 8);
+						o[3] = (uint8_t)(v >> 16);
+						if (sz == 5) o[4] = (uint8_t)(v >> 24);
+					}
+				}
+			}
+			off += (tot >> (8 * k)) & 0xFFu;
+		}
+	}
+	if (lane == 0) wtot[warp] = off;
+	__syncwarp();
+	bar_arrive(BAR_C_DONE, QOI_N_CS);
+
+	bar_sync(BAR_B_READY, QOI_N_CS);
+	/* ---- copy-out: my slab -> tile_base + bytes of the warps before me ---- */
+	const uint32_t tile_base = misc[MISC_TILE_BASE];
+	uint32_t woff = 0;
+	for (uint32_t w = 0; w < warp; w++) woff += wtot[w];
+	if (rs_off != 0xFFFFFFFFu) { /* warp 0: the owner of the restart pixel records where its op starts */
+		P.st.rs_px[t] = (int32_t)ti.px0 + cand;
+		P.st.rs_byte[t] = (int32_t)(tile_base + rs_off);
+		P.st.rs_prev[t] = pxv[cand - 1];
+	}
+	if (tid == 0 && cand == INT_MAX) P.st.rs_px[t] = -1;
+	{
+		uint8_t *gdst = gstream + tile_base + woff;
+		const uint32_t total = off;
+		uint32_t head = (16u - (uint32_t)((uintptr_t)gdst & 15u)) & 15u; /* bytes up to the first aligned 16 */
+		if (head > total) head = total;
+		const uint32_t nvec = (total - head) >> 4;
+		if (lane < head) gdst[lane] = slab[lane];
+		const uint32_t *s32 = (const uint32_t *)slab + (head >> 2);
+		const uint32_t sh = (head & 3u) * 8u;
+		for (uint32_t k = lane; k < nvec; k += 32u) {
+			const uint32_t *w = s32 + 4u * k;
+			const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
+			uint4 q;
+			q.x = __funnelshift_r(w0, w1, sh);
+			q.y = __funnelshift_r(w1, w2, sh);
+			q.z = __funnelshift_r(w2, w3, sh);
+			q.w = __funnelshift_r(w3, w4, sh);
+			*(uint4 *)(gdst + head + 16u * k) = q;
+		}
+		const uint32_t tail0 = head + 16u * nvec;
+		if (tail0 + lane < total) gdst[tail0 + lane] = slab[tail0 + lane]; /* fewer than 16 bytes */
+	}
+	__syncwarp();
+	bar_arrive(BAR_W_DONE, QOI_N_CS);
+}
+
 /* MATCH: same-slot lanes from match.any instead of six ballots (A/B switch).
    EARLYW: phase W does not wait for the tile's output offset -- the op bytes are staged from offset 0 as soon as the warp
    totals are known, the wait for B_READY comes afterwards (the look-back latency hides behind the emission) and the compute
    warps copy the staging buffer out themselves with a byte-shifted 16-byte copy, instead of the loader's bulk store (which
    needs source and destination congruent mod 16).  The STAGE_FREE hand-off is not needed then. */
-template <int CH, bool EXPAND, bool MATCH, bool EARLYW = false>
+/* SLAB: the compute warps run slab_compute() above (no staging hand-off either, like EARLYW) */
+template <int CH, bool EXPAND, bool MATCH, bool EARLYW = false, bool SLAB = false>
 __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(const QoiEncParams P) {
+	constexpr bool NOSTAGE = EARLYW || SLAB; /* the loader never touches the staging area */
 	using L = Layout<CH, EXPAND>;
 	using S = Sub<CH, EXPAND>;
 	QOI_DYNAMIC_SMEM(smem);
@@ -96,7 +366,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR);
 	TileInfo *infos = (TileInfo *)(smem + L::OFF_INFO);
 	unsigned char *stage = smem + S::OFF_STAGE;
-	uint2 *Lent_all = (uint2 *)(smem + S::OFF_LENT);
+	uint2 *Lent_all = (uint2 *)(smem + (SLAB ? SubSlab<CH, EXPAND>::OFF_LENT : S::OFF_LENT));
 	uint16_t *Fpos_all = (uint16_t *)(smem + S::OFF_FPOS);
 	uint32_t *patch_all = (uint32_t *)(smem + S::OFF_PATCH);
 	uint32_t *Tin_val = (uint32_t *)(smem + L::OFF_TINVAL);
@@ -118,7 +388,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 		fetch_issue<CH, EXPAND>(P, smem, F, 0, 0);
 		__syncwarp();
 		bar_arrive(BAR_INFO_READY, QOI_N_ALL);
-		if (!EARLYW) bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
+		if (!NOSTAGE) bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
 	}
 
 	int cur = 0;
@@ -152,7 +422,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 				const uint32_t lo_off = (padb + 15u) & ~15u;
 				const uint32_t end = padb + total;
 				const uint32_t hi_off = end & ~15u;
-				const bool bulk = !EARLYW && hi_off > lo_off;
+				const bool bulk = !NOSTAGE && hi_off > lo_off;
 				if (lane == 0 && bulk) {
 					fence_proxy_async_smem();
 					tma_store_1d_hint(gdst + (lo_off - padb), stage + lo_off, hi_off - lo_off, l2_evict_first_policy());
@@ -160,7 +430,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 				}
 				const uint32_t a_hi = bulk ? lo_off : end;
 				const uint32_t b_lo = bulk ? hi_off : end;
-				if (!EARLYW) { /* EARLYW: the compute warps have copied everything out before W_DONE */
+				if (!NOSTAGE) { /* EARLYW / SLAB: the compute warps have copied everything out before W_DONE */
 					for (uint32_t o = padb + lane; o < a_hi; o += 32) gdst[o - padb] = stage[o];
 					for (uint32_t o = b_lo + lane; o < end; o += 32) gdst[o - padb] = stage[o];
 				}
@@ -180,10 +450,10 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 					if (k < QOI_END_BYTES) gstream[fin + k] = (k == QOI_END_BYTES - 1) ? 1 : 0;
 					else P.lens[ti.img] = (int32_t)(fin + QOI_END_BYTES);
 				}
-				if (!EARLYW && lane == 0) tma_store_wait_read(); /* the bulk store has finished reading the staging buffer */
+				if (!NOSTAGE && lane == 0) tma_store_wait_read(); /* the bulk store has finished reading the staging buffer */
 			}
 			__syncwarp();
-			if (!EARLYW) bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
+			if (!NOSTAGE) bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
 		} else if (scout) {
 			/* =============================== scout warp =============================== */
 			bar_sync(BAR_I_DONE, QOI_N_CS); /* the per-warp tables and wlnr[] of this tile are complete */
@@ -293,11 +563,11 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 			uint2 *Lent = Lent_all + warp * 64;
 			uint16_t *Fpos = Fpos_all + warp * 64;
 			uint32_t *patchw = patch_all + warp * 16;
-			Lent[lane] = make_uint2(0u, 0u);
-			Lent[lane + 32] = make_uint2(0u, 0u);
-			Fpos[lane] = 0xFFFFu;
-			Fpos[lane + 32] = 0xFFFFu;
-			if (lane < 16) patchw[lane] = 0u;
+			if (!SLAB) Lent[lane] = make_uint2(0u, 0u);
+			if (!SLAB) Lent[lane + 32] = make_uint2(0u, 0u);
+			if (!SLAB) Fpos[lane] = 0xFFFFu;
+			if (!SLAB) Fpos[lane + 32] = 0xFFFFu;
+			if (!SLAB && lane < 16) patchw[lane] = 0u;
 			if (EXPAND) {
 				/* ---- phase E: 16 pixels per thread, raw bytes at data[sh + CH*i] -> RGBA words (as in qoi_enc.cuh) ---- */
 				const uint32_t b0 = ti.sh + tid * (16u * CH);
@@ -341,6 +611,9 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 			}
 			__syncwarp();
 
+			if (SLAB) {
+				slab_compute<CH, EXPAND, MATCH>(P, smem, ti, pxv, gstream);
+			} else {
 			const uint32_t nv = ti.n_valid; /* <= 4096; only an image's last tile can be partial */
 			const bool last_tile = ti.px0 + ti.n_valid == ti.npx;
 			const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
@@ -553,6 +826,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 			if (tid == 0 && cand == INT_MAX) P.st.rs_px[t] = -1;
 			__syncwarp();
 			bar_arrive(BAR_W_DONE, QOI_N_CS);
+			} /* !SLAB */
 		}
 		cur ^= 1;
 	}

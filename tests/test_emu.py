@@ -50,6 +50,7 @@ def test_emulated_distributions(emu, cpu, dist):
 
 # cuda/qoi_enc4.cuh (QOI_GPU_ENC=striped | striped-match | striped-earlyw); the tests below alternate between the first two ...
 STRIPED = ({"QOI_EMU_ENC": "striped"}, {"QOI_EMU_ENC": "striped-match"})
+SLAB = ({"QOI_EMU_ENC": "slab"}, {"QOI_EMU_ENC": "slab-match"})  # the rolled "slab" mode of the same kernel (QOI_GPU_ENC=slab | slab-match)
 STRIPED_EARLYW = ({"QOI_EMU_ENC": "striped-earlyw"},)  # ... and run this one on a subset
 
 
@@ -67,9 +68,10 @@ def run_variants(emu, img, w, h, ch, n, grid, seed, mis, variants):
 @pytest.mark.parametrize("dist", range(8))
 def test_emulated_striped_encoder_distributions(emu, cpu, dist):
     """The experimental lane-per-pixel encoder: streams bit exact, its restart index decodes, nothing written out of bounds."""
-    run_variants(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0, STRIPED[dist % 2:dist % 2 + 1])
-    run_variants(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist, STRIPED[1 - dist % 2:2 - dist % 2])
-    if dist in (3, 4, 7):
+    four = STRIPED + SLAB
+    run_variants(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0, (four[dist % 4],))
+    run_variants(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist, (four[(dist + 2) % 4],))
+    if dist == 4:
         run_variants(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 30 + dist, 0, STRIPED_EARLYW)
         run_variants(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 40 + dist, dist, STRIPED_EARLYW)
 
@@ -79,7 +81,7 @@ def test_emulated_striped_encoder_stress_and_runs(emu, cpu):
     for it in range(6):
         w = int(rng.integers(60, 300)); h = int(rng.integers(20, 120)); ch = int(rng.integers(3, 5)); n = int(rng.integers(1, 4))
         img = np.concatenate([q.stress_image(rng, w * h, ch, it % 6) for _ in range(n)])
-        run_variants(emu, img, w, h, ch, n, int(rng.integers(1, 5)), it + 1, int(rng.integers(0, 17)) if it % 2 else 0, STRIPED[it % 2:it % 2 + 1])
+        run_variants(emu, img, w, h, ch, n, int(rng.integers(1, 5)), it + 1, int(rng.integers(0, 17)) if it % 2 else 0, (STRIPED + SLAB)[it % 4:it % 4 + 1])
     n = 40000  # runs that cross warp chunks, tiles and the 62 boundary; runs from the image start (qoi.h:396-399)
     a = np.zeros((n, 4), dtype=np.uint8); a[:, 3] = 255
     b = np.zeros((n, 4), dtype=np.uint8)
@@ -87,9 +89,9 @@ def test_emulated_striped_encoder_stress_and_runs(emu, cpu):
     d = np.full((n, 4), 200, dtype=np.uint8); d[12345] = (1, 2, 3, 4)
     for k, img in enumerate((a, b, c, d)):
         if k % 2 == 0:
-            run_variants(emu, img.reshape(-1), 400, 100, 4, 1, 4, 3, 0, STRIPED[:1])
+            run_variants(emu, img.reshape(-1), 400, 100, 4, 1, 4, 3, 0, ((STRIPED[0], SLAB[0])[k // 2],))
         else:
-            run_variants(emu, np.ascontiguousarray(img[:, :3]).reshape(-1), 400, 100, 3, 1, 3, 4, 5, STRIPED[(k // 2) % 2:(k // 2) % 2 + 1])
+            run_variants(emu, np.ascontiguousarray(img[:, :3]).reshape(-1), 400, 100, 3, 1, 3, 4, 5, ((SLAB[1], STRIPED[1])[k // 2],))
 
 
 def test_emulated_stress(emu, cpu):

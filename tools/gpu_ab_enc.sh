@@ -3,6 +3,7 @@
 #   default                       the shipped kernels (cuda/qoi_enc.cuh)
 #   QOI_GPU_ENC=striped           lane-per-pixel encoder, six-ballot slot matching (cuda/qoi_enc4.cuh)
 #   QOI_GPU_ENC=striped-match     same with match.any
+#   QOI_GPU_ENC=slab | slab-match rolled loops, op bytes straight into per-warp slabs, copy-out by the compute warps
 #   exp library + QOI_GPU_ENC=earlyw   phase W before the output offset is known (experiments/encoder_earlyw.patch)
 # For every variant: the GPU parity tests that exercise the encoder, then bench lines for photo / noise / palette / const0.
 #   gpurun --timeout 1500 -- 'bash tools/gpu_ab_enc.sh'
@@ -25,9 +26,13 @@ run_variant default QOI_GPU_NOP=1
 run_variant striped QOI_GPU_ENC=striped
 run_variant stripedmatch QOI_GPU_ENC=striped-match
 run_variant stripedearlyw QOI_GPU_ENC=striped-earlyw
+run_variant slab QOI_GPU_ENC=slab
+run_variant slabmatch QOI_GPU_ENC=slab-match
 if [ -f "$EXP" ]; then run_variant earlyw QOI_GPU_LIB=$EXP QOI_GPU_ENC=earlyw; fi
 python tools/bench_summary.py gpurun_out/ab_enc_*_d*.json
 # one ncu capture of the striped kernel for the line profile (tools/ncu_lines.py reads it here)
-QOI_GPU_ENC=striped timeout 600 ncu --set full --import-source on --clock-control none -k regex:striped -c 1 \
-  -o gpurun_out/ncu_striped python bench.py --steps 1 --warmup 1 --no-cpu --e2e-steps 1 --batch 8 > gpurun_out/ncu_striped.log 2>&1
-echo "NCU_RC=$?"
+for v in striped slab; do
+QOI_GPU_ENC=$v timeout 600 ncu --set full --import-source on --clock-control none -k regex:striped -c 1 \
+  -o gpurun_out/ncu_$v python bench.py --steps 1 --warmup 1 --no-cpu --e2e-steps 1 --batch 8 > gpurun_out/ncu_$v.log 2>&1
+echo "NCU_${v}_RC=$?"
+done
