@@ -267,6 +267,36 @@ def c_api_single_image(h_pix, args):
     return c_api
 
 
+
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers it allocates from
+    here on (and the DMA traffic of the e2e leg) stay on the GPU's side of the socket interconnect.  Returns a small
+    dict for the JSON line, or None where the platform does not say (VMs often report numa_node = -1).
+    QOI_BENCH_NUMA=0 switches it off.  The caller restores the original affinity before any CPU-codec leg."""
+    if os.environ.get("QOI_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use or use == allowed:
+            return {"node": node, "cpus": len(use), "bound": False}
+        os.sched_setaffinity(0, use)
+        return {"node": node, "cpus": len(use), "bound": True}
+    except Exception:  # never let a missing sysfs file or attribute stop the benchmark
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -296,6 +326,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
+    full_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank)  # before the context and the pinned buffers exist
     dist_on = world > 1
     if dist_on:
         import torch.distributed as dist
@@ -427,6 +459,7 @@ def main():
                        "gpx_per_s": px_rank / (dec_ms * 1e-3) / 1e9, "traffic": (traffic or {}).get("decode")},
         }
         cpu_baseline = None
+        os.sched_setaffinity(0, full_affinity)  # the CPU codec legs get every host thread again
         if world == 1 and not args.no_cpu:
             kind, eb, db, threads = load_cpu_codec()
             slot = W * H * (CH + 1) + 22
@@ -453,6 +486,7 @@ def main():
                        "global_batch": n * world, "distribution": DIST_NAMES[args.dist], "decode_channels": 4,
                        "encoded_bytes_per_px": e_bpp, "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
                        "l2": f"inputs {plan.pixel_bytes >> 20} MiB per GPU per step, larger than the 126 MB L2 (no flush needed)",
+                       "numa": numa,
                        "decode_path": "segment-parallel with the encoder's restart index (side table, 0.07 B/px, outside the bit-exact stream)"},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
