@@ -459,7 +459,10 @@ def main():
                        "gpx_per_s": px_rank / (dec_ms * 1e-3) / 1e9, "traffic": (traffic or {}).get("decode")},
         }
         cpu_baseline = None
-        os.sched_setaffinity(0, full_affinity)  # the CPU codec legs get every host thread again
+        try:
+            os.sched_setaffinity(0, full_affinity)  # the CPU codec legs get every host thread again
+        except OSError:
+            pass
         if world == 1 and not args.no_cpu:
             kind, eb, db, threads = load_cpu_codec()
             slot = W * H * (CH + 1) + 22
