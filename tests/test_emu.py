@@ -69,29 +69,28 @@ def run_variants(emu, img, w, h, ch, n, grid, seed, mis, variants):
 def test_emulated_striped_encoder_distributions(emu, cpu, dist):
     """The experimental lane-per-pixel encoder: streams bit exact, its restart index decodes, nothing written out of bounds."""
     four = STRIPED + SLAB
-    run_variants(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0, (four[dist % 4],))
-    run_variants(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist, (four[(dist + 2) % 4],))
-    if dist == 4:
+    run_variants(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0, four)
+    run_variants(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist, four)
+    if True:
         run_variants(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 30 + dist, 0, STRIPED_EARLYW)
         run_variants(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 40 + dist, dist, STRIPED_EARLYW)
 
 
 def test_emulated_striped_encoder_stress_and_runs(emu, cpu):
     rng = np.random.default_rng(7)
-    for it in range(6):
+    for it in range(18):
         w = int(rng.integers(60, 300)); h = int(rng.integers(20, 120)); ch = int(rng.integers(3, 5)); n = int(rng.integers(1, 4))
         img = np.concatenate([q.stress_image(rng, w * h, ch, it % 6) for _ in range(n)])
-        run_variants(emu, img, w, h, ch, n, int(rng.integers(1, 5)), it + 1, int(rng.integers(0, 17)) if it % 2 else 0, (STRIPED + SLAB)[it % 4:it % 4 + 1])
+        five = STRIPED + SLAB + STRIPED_EARLYW
+        run_variants(emu, img, w, h, ch, n, int(rng.integers(1, 5)), it + 1, int(rng.integers(0, 17)) if it % 2 else 0, (five[it % 5], five[(it + 2) % 5]))
     n = 40000  # runs that cross warp chunks, tiles and the 62 boundary; runs from the image start (qoi.h:396-399)
     a = np.zeros((n, 4), dtype=np.uint8); a[:, 3] = 255
     b = np.zeros((n, 4), dtype=np.uint8)
     c = np.zeros((n, 4), dtype=np.uint8); c[:, 3] = 255; c[n // 2:] = (9, 9, 9, 255); c[-5:] = (0, 0, 0, 255)
     d = np.full((n, 4), 200, dtype=np.uint8); d[12345] = (1, 2, 3, 4)
     for k, img in enumerate((a, b, c, d)):
-        if k % 2 == 0:
-            run_variants(emu, img.reshape(-1), 400, 100, 4, 1, 4, 3, 0, ((STRIPED[0], SLAB[0])[k // 2],))
-        else:
-            run_variants(emu, np.ascontiguousarray(img[:, :3]).reshape(-1), 400, 100, 3, 1, 3, 4, 5, ((SLAB[1], STRIPED[1])[k // 2],))
+        run_variants(emu, img.reshape(-1), 400, 100, 4, 1, 4, 3, 0, STRIPED + SLAB + STRIPED_EARLYW)
+        run_variants(emu, np.ascontiguousarray(img[:, :3]).reshape(-1), 400, 100, 3, 1, 3, 4, 5, STRIPED + SLAB + STRIPED_EARLYW)
 
 
 def test_emulated_stress(emu, cpu):
@@ -135,3 +134,12 @@ def test_emulated_foreign_decode(emu, cpu):
     for rounds in ("1", "2", "3", "6", "9"):
         run(big, 200, 200, {"QOI_EMU_FROUNDS": rounds})
         run(big, 200, 200, {"QOI_EMU_FROUNDS": rounds, "QOI_EMU_FVER_MIN_RANGE": "2"})  # several verify ranges per stream
+
+
+def test_emulated_many_tiles(emu, cpu):
+    """512 x 512 images (64 tiles each) on 6 CTAs: look-back windows of many in-flight predecessors, for the shipped encoder
+    and every variant."""
+    img = cpu.batch(1, 512, 512, 4, 4)
+    run_variants(emu, img, 512, 512, 4, 1, 6, 7, 0, ({"QOI_GPU_LOOKUP": "walk"}, STRIPED[0], SLAB[1]))
+    pal = cpu.batch(1, 512, 300, 3, 6)
+    run_variants(emu, pal, 512, 300, 3, 1, 5, 9, 3, (STRIPED[1], SLAB[0]))
