@@ -110,9 +110,70 @@ struct SubSlab {
 	static_assert(SLAB_BYTES % 16 == 0 && OFF_LENT % 8 == 0, "alignment");
 };
 
-template <int CH, bool EXPAND, bool MATCH>
+/* what a warp keeps of a tile between its emit pass and its copy-out (PIPE: across the next tile's index pass) */
+struct SlabCarry {
+	bool valid;
+	uint32_t t;          /* tile */
+	uint8_t *gstream;    /* its image's stream */
+	uint32_t bytes;      /* bytes in my slab */
+	int32_t rs_px;       /* restart pixel (image coordinates), INT_MAX: none in this tile (warp 0 only) */
+	uint32_t rs_off;     /* its byte offset inside the tile, 0xFFFFFFFF in lanes that do not own it */
+	uint32_t rs_prev;    /* the pixel before it */
+	uint32_t parity;     /* which copy of the scout's per-tile outputs belongs to the tile (PIPE) */
+};
+
+/* misc[] holds two copies of {tile base, -, tile total} so that the scout can finish tile k+1 while tile k is still copied out */
+__device__ __forceinline__ uint32_t misc_slot(uint32_t parity, uint32_t what) { return parity * 4u + what; }
+
+/* B_READY, restart record, my slab -> tile_base + bytes of the warps before me (byte-shifted 16-byte copy) */
+template <int CH, bool EXPAND, bool PIPE>
+__device__ __forceinline__ void slab_finish(const QoiEncParams &P, unsigned char *smem, const SlabCarry &c) {
+	using L = Layout<CH, EXPAND>;
+	using S = SubSlab<CH, EXPAND>;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const unsigned char *slab = smem + S::OFF_SLAB + warp * S::SLAB_BYTES;
+	const uint32_t *misc = (const uint32_t *)(smem + L::OFF_MISC);
+	const uint32_t *wtot = (const uint32_t *)(smem + L::OFF_WTOT);
+	const uint32_t *wpre = (const uint32_t *)(smem + L::OFF_HITW); /* PIPE: u32 [2][8] exclusive prefix of wtot, written by the scout */
+	bar_sync(BAR_B_READY, QOI_N_CS);
+	const uint32_t tile_base = misc[misc_slot(PIPE ? c.parity : 0u, MISC_TILE_BASE)];
+	uint32_t woff = 0;
+	if (PIPE) woff = wpre[c.parity * QOI_ENC_WARPS + warp];
+	else for (uint32_t w = 0; w < warp; w++) woff += wtot[w];
+	if (c.rs_off != 0xFFFFFFFFu) { /* warp 0: the owner of the restart pixel records where its op starts */
+		P.st.rs_px[c.t] = c.rs_px;
+		P.st.rs_byte[c.t] = (int32_t)(tile_base + c.rs_off);
+		P.st.rs_prev[c.t] = c.rs_prev;
+	}
+	if (tid == 0 && c.rs_px == INT_MAX) P.st.rs_px[c.t] = -1;
+	uint8_t *gdst = c.gstream + tile_base + woff;
+	const uint32_t total = c.bytes;
+	uint32_t head = (16u - (uint32_t)((uintptr_t)gdst & 15u)) & 15u; /* bytes up to the first aligned 16 */
+	if (head > total) head = total;
+	const uint32_t nvec = (total - head) >> 4;
+	if (lane < head) gdst[lane] = slab[lane];
+	const uint32_t *s32 = (const uint32_t *)slab + (head >> 2);
+	const uint32_t sh = (head & 3u) * 8u;
+	for (uint32_t k = lane; k < nvec; k += 32u) {
+		const uint32_t *w = s32 + 4u * k;
+		const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
+		uint4 q;
+		q.x = __funnelshift_r(w0, w1, sh);
+		q.y = __funnelshift_r(w1, w2, sh);
+		q.z = __funnelshift_r(w2, w3, sh);
+		q.w = __funnelshift_r(w3, w4, sh);
+		*(uint4 *)(gdst + head + 16u * k) = q;
+	}
+	const uint32_t tail0 = head + 16u * nvec;
+	if (tail0 + lane < total) gdst[tail0 + lane] = slab[tail0 + lane]; /* fewer than 16 bytes */
+	__syncwarp();
+}
+
+/* PIPE: the copy-out of a tile (and the wait for its output offset) moves behind the NEXT tile's index pass:
+   per iteration  index(k) -> copy-out(k-1) -> emit(k); the pixel buffer is released to the loader after emit(k) already */
+template <int CH, bool EXPAND, bool MATCH, bool PIPE>
 __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned char *smem, const TileInfo &ti, const uint32_t *pxv,
-                                             uint8_t *gstream) {
+                                             uint8_t *gstream, uint32_t parity, SlabCarry &carry) {
 	using L = Layout<CH, EXPAND>;
 	using S = SubSlab<CH, EXPAND>;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -199,6 +260,8 @@ __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned cha
 	__syncwarp();
 	bar_arrive(BAR_I_DONE, QOI_N_CS);
 
+	if (PIPE && carry.valid) slab_finish<CH, EXPAND, true>(P, smem, carry); /* the previous tile leaves while the scout looks back for this one */
+
 	bar_sync(BAR_T_READY, QOI_N_CS); /* every warp's table is final; T_in and the run carry are in shared memory */
 	/* ---- phase R: my chunk's deferred pixels against the earlier warps' tables, then the incoming table ---- */
 #pragma unroll
@@ -235,6 +298,9 @@ __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned cha
 			break;
 		}
 	}
+	/* PIPE: nobody waits for B_READY before the next tile's index pass re-initialises the tables, so everybody must be
+	   done reading the other warps' tables (phase R) and wlnr[] before anybody goes on */
+	if (PIPE) bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
 
 	/* ---- emit pass: four independent rows at a time; op bytes go into the warp's slab at a running offset ---- */
 	uint32_t off = 0;                 /* bytes of this chunk so far (uniform) */
@@ -308,44 +374,22 @@ __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned cha
 		}
 	}
 	if (lane == 0) wtot[warp] = off;
+	carry.valid = true;
+	carry.t = t;
+	carry.gstream = gstream;
+	carry.bytes = off;
+	carry.rs_px = (warp == 0 && cand != INT_MAX) ? (int32_t)ti.px0 + cand : INT_MAX;
+	carry.rs_off = rs_off;
+	carry.rs_prev = (warp == 0 && cand != INT_MAX) ? pxv[cand - 1] : 0u;
+	carry.parity = parity;
 	__syncwarp();
 	bar_arrive(BAR_C_DONE, QOI_N_CS);
-
-	bar_sync(BAR_B_READY, QOI_N_CS);
-	/* ---- copy-out: my slab -> tile_base + bytes of the warps before me ---- */
-	const uint32_t tile_base = misc[MISC_TILE_BASE];
-	uint32_t woff = 0;
-	for (uint32_t w = 0; w < warp; w++) woff += wtot[w];
-	if (rs_off != 0xFFFFFFFFu) { /* warp 0: the owner of the restart pixel records where its op starts */
-		P.st.rs_px[t] = (int32_t)ti.px0 + cand;
-		P.st.rs_byte[t] = (int32_t)(tile_base + rs_off);
-		P.st.rs_prev[t] = pxv[cand - 1];
+	if (PIPE) {
+		bar_arrive(BAR_W_DONE, QOI_N_CS); /* the pixel buffer is free (nothing reads pxv any more): the loader may refill it */
+	} else {
+		slab_finish<CH, EXPAND, false>(P, smem, carry);
+		bar_arrive(BAR_W_DONE, QOI_N_CS);
 	}
-	if (tid == 0 && cand == INT_MAX) P.st.rs_px[t] = -1;
-	{
-		uint8_t *gdst = gstream + tile_base + woff;
-		const uint32_t total = off;
-		uint32_t head = (16u - (uint32_t)((uintptr_t)gdst & 15u)) & 15u; /* bytes up to the first aligned 16 */
-		if (head > total) head = total;
-		const uint32_t nvec = (total - head) >> 4;
-		if (lane < head) gdst[lane] = slab[lane];
-		const uint32_t *s32 = (const uint32_t *)slab + (head >> 2);
-		const uint32_t sh = (head & 3u) * 8u;
-		for (uint32_t k = lane; k < nvec; k += 32u) {
-			const uint32_t *w = s32 + 4u * k;
-			const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
-			uint4 q;
-			q.x = __funnelshift_r(w0, w1, sh);
-			q.y = __funnelshift_r(w1, w2, sh);
-			q.z = __funnelshift_r(w2, w3, sh);
-			q.w = __funnelshift_r(w3, w4, sh);
-			*(uint4 *)(gdst + head + 16u * k) = q;
-		}
-		const uint32_t tail0 = head + 16u * nvec;
-		if (tail0 + lane < total) gdst[tail0 + lane] = slab[tail0 + lane]; /* fewer than 16 bytes */
-	}
-	__syncwarp();
-	bar_arrive(BAR_W_DONE, QOI_N_CS);
 }
 
 /* MATCH: same-slot lanes from match.any instead of six ballots (A/B switch).
@@ -354,7 +398,9 @@ __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned cha
    warps copy the staging buffer out themselves with a byte-shifted 16-byte copy, instead of the loader's bulk store (which
    needs source and destination congruent mod 16).  The STAGE_FREE hand-off is not needed then. */
 /* SLAB: the compute warps run slab_compute() above (no staging hand-off either, like EARLYW) */
-template <int CH, bool EXPAND, bool MATCH, bool EARLYW = false, bool SLAB = false>
+/* PIPE (slab mode only): see slab_compute -- the scout then also writes header, end marker and length (the loader no longer
+   learns when a tile's bytes are out) and publishes the per-warp output offsets in two alternating copies */
+template <int CH, bool EXPAND, bool MATCH, bool EARLYW = false, bool SLAB = false, bool PIPE = false>
 __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(const QoiEncParams P) {
 	constexpr bool NOSTAGE = EARLYW || SLAB; /* the loader never touches the staging area */
 	using L = Layout<CH, EXPAND>;
@@ -394,6 +440,8 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 	int cur = 0;
 	uint32_t parity0 = 0, parity1 = 0;
 	const uint32_t epoch = P.epoch;
+	SlabCarry carry; /* slab mode: a compute warp's tile that is finished but not copied out yet */
+	carry.valid = false;
 
 	while (true) {
 		if (!loader) bar_sync(BAR_INFO_READY, QOI_N_ALL); /* infos[cur] is published */
@@ -434,7 +482,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 					for (uint32_t o = padb + lane; o < a_hi; o += 32) gdst[o - padb] = stage[o];
 					for (uint32_t o = b_lo + lane; o < end; o += 32) gdst[o - padb] = stage[o];
 				}
-				if (t == ti.first_tile && lane < QOI_HEADER_BYTES) { /* header, qoi.h:384-388 */
+				if (!PIPE && t == ti.first_tile && lane < QOI_HEADER_BYTES) { /* header, qoi.h:384-388 (PIPE: the scout writes it) */
 					const uint32_t k = lane;
 					uint8_t b;
 					if (k < 4) b = (uint8_t)("qoif"[k]);
@@ -444,7 +492,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 					else b = (uint8_t)(ti.chan_cs >> 8);
 					gstream[k] = b;
 				}
-				if (ti.px0 + ti.n_valid == ti.npx && lane >= 16 && lane < 16 + QOI_END_BYTES + 1) { /* end marker, length: qoi.h:480-484 */
+				if (!PIPE && ti.px0 + ti.n_valid == ti.npx && lane >= 16 && lane < 16 + QOI_END_BYTES + 1) { /* end marker, length: qoi.h:480-484 */
 					const uint32_t k = lane - 16;
 					const uint32_t fin = excl + total;
 					if (k < QOI_END_BYTES) gstream[fin + k] = (k == QOI_END_BYTES - 1) ? 1 : 0;
@@ -550,8 +598,31 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 			}
 			if (lane == 0) {
 				st_relaxed_u64(&P.st.byte_state[t], pack_bytes(epoch, QOI_ST_INC, excl + total));
-				misc[MISC_TILE_BASE] = excl;
-				misc[MISC_TILE_TOTAL] = total;
+				misc[misc_slot(PIPE ? (uint32_t)cur : 0u, MISC_TILE_BASE)] = excl;
+				misc[misc_slot(PIPE ? (uint32_t)cur : 0u, MISC_TILE_TOTAL)] = total;
+			}
+			if (PIPE) {
+				if (lane < QOI_ENC_WARPS) { /* where each warp's slab goes inside the tile */
+					uint32_t pre = 0;
+					for (uint32_t w = 0; w < lane; w++) pre += wtot[w];
+					((uint32_t *)(smem + L::OFF_HITW))[(uint32_t)cur * QOI_ENC_WARPS + lane] = pre;
+				}
+				if (t == ti.first_tile && lane < QOI_HEADER_BYTES) { /* header, qoi.h:384-388 */
+					const uint32_t k = lane;
+					uint8_t b;
+					if (k < 4) b = (uint8_t)("qoif"[k]);
+					else if (k < 8) b = (uint8_t)(ti.width >> (8 * (7 - k)));
+					else if (k < 12) b = (uint8_t)(ti.height >> (8 * (11 - k)));
+					else if (k == 12) b = (uint8_t)(ti.chan_cs & 0xFFu);
+					else b = (uint8_t)(ti.chan_cs >> 8);
+					gstream[k] = b;
+				}
+				if (ti.px0 + ti.n_valid == ti.npx && lane >= 16 && lane < 16 + QOI_END_BYTES + 1) { /* end marker, length: qoi.h:480-484 */
+					const uint32_t k = lane - 16;
+					const uint32_t fin = excl + total;
+					if (k < QOI_END_BYTES) gstream[fin + k] = (k == QOI_END_BYTES - 1) ? 1 : 0;
+					else P.lens[ti.img] = (int32_t)(fin + QOI_END_BYTES);
+				}
 			}
 			__syncwarp();
 			bar_arrive(BAR_B_READY, QOI_N_CS);
@@ -612,7 +683,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 			__syncwarp();
 
 			if (SLAB) {
-				slab_compute<CH, EXPAND, MATCH>(P, smem, ti, pxv, gstream);
+				slab_compute<CH, EXPAND, MATCH, PIPE>(P, smem, ti, pxv, gstream, (uint32_t)cur, carry);
 			} else {
 			const uint32_t nv = ti.n_valid; /* <= 4096; only an image's last tile can be partial */
 			const bool last_tile = ti.px0 + ti.n_valid == ti.npx;
@@ -831,6 +902,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 		cur ^= 1;
 	}
 
+	if (SLAB && PIPE && !loader && !scout && carry.valid) slab_finish<CH, EXPAND, true>(P, smem, carry); /* the last tile's copy-out */
 	/* the last CTA to finish rearms the ticket for the next launch */
 	__syncthreads();
 	if (loader && lane == 0) { /* this thread issued the bulk stores */

@@ -40,7 +40,7 @@ struct qoi_gpu_ctx {
 #ifdef QOI_EXP_EARLYW
 	bool enc_earlyw = false;              /* experimental build only (experiments/encoder_earlyw.patch): QOI_GPU_ENC=earlyw */
 #endif
-	int enc_striped = 0;                  /* experimental encoder of qoi_enc4.cuh (QOI_GPU_ENC=striped: 1, striped-match: 2, striped-earlyw: 3, slab: 4, slab-match: 5); emulator-tested,
+	int enc_striped = 0;                  /* experimental encoder of qoi_enc4.cuh (QOI_GPU_ENC=striped: 1, striped-match: 2, striped-earlyw: 3, slab: 4, slab-match: 5, slab-pipe: 6, slab-pipe-ballot: 7); emulator-tested,
 	                                         off by default */
 	bool read_ahead = false;              /* experimental: ring word read one call ahead (QOI_GPU_REFILL=ahead); indexed decoder only */
 	bool refill_uni = true;               /* decoders' stream reader: warp-uniform refill (default) or lane-driven (QOI_GPU_REFILL=lane) */
@@ -112,6 +112,12 @@ static int enc_striped_setup(qoi_gpu_ctx *ctx) {
 	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
 	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
 	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
 	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
 	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
 	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
@@ -182,6 +188,8 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 		if (ev && !strcmp(ev, "striped-earlyw")) c->enc_striped = 3;
 		if (ev && !strcmp(ev, "slab")) c->enc_striped = 4;
 		if (ev && !strcmp(ev, "slab-match")) c->enc_striped = 5;
+		if (ev && !strcmp(ev, "slab-pipe")) c->enc_striped = 6;        /* match.any */
+		if (ev && !strcmp(ev, "slab-pipe-ballot")) c->enc_striped = 7;
 	}
 	int rc = enc_occupancy<4, false>(c, &c->enc_blocks_per_sm[0]);
 	if (!rc) rc = enc_occupancy<4, true>(c, &c->enc_blocks_per_sm[1]);
@@ -297,7 +305,19 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	if (grid > P.n_tiles) grid = P.n_tiles;
 	if (ctx->enc_striped) { /* experimental, QOI_GPU_ENC=striped | striped-match */
 		const bool mt = ctx->enc_striped == 2, ew = ctx->enc_striped == 3;
-		if (ctx->enc_striped >= 4) { /* slab mode */
+		if (ctx->enc_striped >= 6) { /* slab mode, copy-out pipelined behind the next tile's index pass */
+			const bool sm = ctx->enc_striped == 6;
+			if (variant == 0) {
+				if (sm) qoienc4::qoi_encode_striped_kernel<4, false, true, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
+				else qoienc4::qoi_encode_striped_kernel<4, false, false, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
+			} else if (variant == 1) {
+				if (sm) qoienc4::qoi_encode_striped_kernel<4, true, true, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
+				else qoienc4::qoi_encode_striped_kernel<4, true, false, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
+			} else {
+				if (sm) qoienc4::qoi_encode_striped_kernel<3, true, true, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
+				else qoienc4::qoi_encode_striped_kernel<3, true, false, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
+			}
+		} else if (ctx->enc_striped >= 4) { /* slab mode */
 			const bool sm = ctx->enc_striped == 5;
 			if (variant == 0) {
 				if (sm) qoienc4::qoi_encode_striped_kernel<4, false, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
