@@ -81,6 +81,115 @@ __device__ __forceinline__ void ballot_and_mask(uint32_t x, uint32_t &plane, uin
 }
 
 
+/* ---------------------------------------------------------------- compact layout (slab mode, QOI_GPU_ENC=slab4 | slab4-pipe) */
+/* bytes of the slab-mode work area: 8 slabs, per-warp tables, first-occurrence positions, hit and non-run words */
+template <int CH>
+struct SlabArea {
+	static constexpr int SLAB_BYTES = QOI_WARP_PX * (CH + 1) + 16;
+	static constexpr int BYTES = QOI_ENC_WARPS * SLAB_BYTES + QOI_ENC_WARPS * 64 * 8 + QOI_ENC_WARPS * 64 * 2 + 2 * QOI_ENC_WARPS * QOI_WARP_STEPS * 4;
+};
+/*
+ * The kernel is bound by dependent latency (profiles/r1_final/striped_smoke.txt), so the obvious lever is more resident
+ * warps.  Slab mode needs 48 registers with 8 bytes of spill and, with ONE pixel buffer instead of two and the work area
+ * cut to what slab mode uses, 45 KB of shared memory (RGBA zero-copy): 4 CTAs (40 warps) per SM instead of 3 (30).  The
+ * price: the next tile's bulk copy can only start when the compute warps are done with the current pixels, so its latency
+ * is covered by the other CTAs of the SM instead of by this CTA's own work.
+ */
+template <int CH, bool EXPAND>
+struct LayoutC {
+	static constexpr int NBUF = 1;
+	static constexpr int RAW_STRIDE = 16 + 16 + QOI_TILE_PX * CH + 16;
+	static constexpr int OFF_RAW = 0;
+	static constexpr int OFF_PXBUF = NBUF * RAW_STRIDE;
+	static constexpr int PXBUF_BYTES = EXPAND ? (16 + QOI_TILE_PX * 4 + 16) : 0;
+	static constexpr int OFF_CELLS = OFF_PXBUF + PXBUF_BYTES;
+	static constexpr int CELLS_BYTES = (SlabArea<CH>::BYTES + 15) & ~15;
+	static constexpr int OFF_TINVAL = OFF_CELLS + CELLS_BYTES;        /* u32 [64] */
+	static constexpr int OFF_HITW = OFF_TINVAL + 64 * 4;              /* u32 [16]: the scout's per-warp output offsets, two copies */
+	static constexpr int OFF_TINFLAG = OFF_HITW + 16 * 4;             /* u8 [64] */
+	static constexpr int OFF_MBAR = OFF_TINFLAG + 64;                 /* u64 [2] */
+	static constexpr int OFF_INFO = OFF_MBAR + 16;                    /* TileInfo [2] */
+	static constexpr int OFF_NBR = OFF_INFO + 2 * (int)sizeof(TileInfo);
+	static constexpr int OFF_WTOT = OFF_NBR + 16;
+	static constexpr int OFF_WLNR = OFF_WTOT + 32;
+	static constexpr int OFF_WLNRIN = OFF_WLNR + 32;
+	static constexpr int OFF_MISC = OFF_WLNRIN + 32;
+	static constexpr int TOTAL = OFF_MISC + 32;
+	static_assert(OFF_CELLS % 16 == 0 && OFF_TINVAL % 16 == 0 && OFF_MBAR % 8 == 0 && OFF_INFO % 16 == 0, "alignment");
+};
+template <int CH, bool EXPAND, bool COMPACT>
+struct PickLayout { using type = Layout<CH, EXPAND>; };
+template <int CH, bool EXPAND>
+struct PickLayout<CH, EXPAND, true> { using type = LayoutC<CH, EXPAND>; };
+
+/* qoienc::fetch_issue for any layout type L (same code; the shipped function is tied to Layout<CH, EXPAND>).
+   step 2: start the bulk copy into raw buffer `rb`, fill fragments / neighbours, publish the info record `ib` */
+template <class L, int CH, bool EXPAND>
+__device__ __forceinline__ void fetch_issue_l(const QoiEncParams &P, unsigned char *smem, const Fetch &F, int rb, int ib) {
+	const uint32_t lane = lane_id();
+	TileInfo *info = (TileInfo *)(smem + L::OFF_INFO) + ib;
+	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR) + rb;
+	if (!F.any) {
+		if (lane == 0) info->tile = -1;
+		return;
+	}
+	const QoiImgMeta &m = F.m;
+	const uint32_t t_in = F.tile - m.first_tile;
+	const uint32_t px0 = t_in * QOI_TILE_PX;
+	const uint32_t n_valid = (m.npx - px0) < (uint32_t)QOI_TILE_PX ? (m.npx - px0) : (uint32_t)QOI_TILE_PX;
+	const uint8_t *gsrc = P.pixels + m.pix_off + (uint64_t)px0 * CH;
+	const uint32_t nbytes = n_valid * CH;
+	const uint32_t sh = EXPAND ? (uint32_t)((uintptr_t)gsrc & 15u) : 0u;
+	unsigned char *data = smem + L::OFF_RAW + rb * L::RAW_STRIDE + 16; /* data[sh + k] = gsrc[k] */
+	const uint32_t lo_off = (sh + 15u) & ~15u;
+	const uint32_t hi_off = (sh + nbytes) & ~15u;
+	const uint32_t tma_bytes = hi_off > lo_off ? hi_off - lo_off : 0u;
+	if (lane == 0) {
+		mbar_arrive_expect_tx(mbar, tma_bytes);
+		if (tma_bytes) tma_load_1d_hint(data + lo_off, gsrc + (lo_off - sh), tma_bytes, mbar, l2_evict_first_policy());
+	}
+	/* the <16-byte fragments on either side of the 16-byte aligned interior */
+	uint32_t a_lo = sh, a_hi = tma_bytes ? lo_off : sh + nbytes;
+	uint32_t b_lo = tma_bytes ? hi_off : 0u, b_hi = tma_bytes ? sh + nbytes : 0u;
+	uint32_t o = a_lo + lane;
+	if (o < a_hi) data[o] = gsrc[o - sh];
+	o = b_lo + lane;
+	if (o < b_hi) data[o] = gsrc[o - sh];
+	/* neighbours: the pixel before the tile (start colour {0,0,0,255} at the image start, qoi.h:396-399)
+	   and the pixel after it (needed to know whether a run ends on the tile's last pixel) */
+	uint32_t nb = 0;
+	if (lane == 0) {
+		if (t_in == 0) nb = 0xFF000000u;
+		else {
+			const uint8_t *q = gsrc - CH;
+			nb = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | (CH == 4 ? ((uint32_t)q[CH - 1] << 24) : 0xFF000000u);
+		}
+	} else if (lane == 1) {
+		if (px0 + n_valid < m.npx) {
+			const uint8_t *q = gsrc + nbytes;
+			nb = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | (CH == 4 ? ((uint32_t)q[CH - 1] << 24) : 0xFF000000u);
+		}
+	}
+	if (lane < 2) {
+		if (EXPAND) ((uint32_t *)(smem + L::OFF_NBR))[ib * 2 + lane] = nb;
+		else ((uint32_t *)data)[lane == 0 ? -1 : QOI_TILE_PX] = nb;
+	}
+	if (lane == 0) {
+		info->tile = (int32_t)F.tile;
+		info->img = F.img;
+		info->t_in_img = t_in;
+		info->n_valid = n_valid;
+		info->px0 = px0;
+		info->npx = m.npx;
+		info->first_tile = m.first_tile;
+		info->sh = sh;
+		info->stream_off = m.stream_off;
+		info->width = m.width;
+		info->height = m.height;
+		info->chan_cs = (uint32_t)m.channels | ((uint32_t)m.colorspace << 8);
+	}
+}
+
 /* ---------------------------------------------------------------- "slab" mode (QOI_GPU_ENC=slab | slab-match) */
 /*
  * What the first GPU run of the striped kernel said (profiles/r1_final/striped_smoke.txt): 40 % fewer instructions did not
@@ -96,10 +205,9 @@ __device__ __forceinline__ void ballot_and_mask(uint32_t x, uint32_t &plane, uin
  *   copy-out     after B_READY every warp copies its slab to tile_base + (bytes of the warps before it) with a
  *                byte-shifted 16-byte copy -- no second pass over the ops, no staging hand-off, no bulk store
  */
-template <int CH, bool EXPAND>
+template <class L, int CH>
 struct SubSlab {
-	using L = Layout<CH, EXPAND>;
-	static constexpr int SLAB_BYTES = QOI_WARP_PX * (CH + 1) + 16; /* worst case of a chunk + room for the shifted copy's last word */
+	static constexpr int SLAB_BYTES = SlabArea<CH>::SLAB_BYTES; /* worst case of a chunk + room for the shifted copy's last word */
 	static constexpr int OFF_SLAB = L::OFF_CELLS;
 	static constexpr int OFF_LENT = OFF_SLAB + QOI_ENC_WARPS * SLAB_BYTES;
 	static constexpr int OFF_FPOS = OFF_LENT + QOI_ENC_WARPS * 64 * 8;
@@ -126,10 +234,10 @@ struct SlabCarry {
 __device__ __forceinline__ uint32_t misc_slot(uint32_t parity, uint32_t what) { return parity * 4u + what; }
 
 /* B_READY, restart record, my slab -> tile_base + bytes of the warps before me (byte-shifted 16-byte copy) */
-template <int CH, bool EXPAND, bool PIPE>
+template <int CH, bool EXPAND, bool PIPE, bool COMPACT>
 __device__ __forceinline__ void slab_finish(const QoiEncParams &P, unsigned char *smem, const SlabCarry &c) {
-	using L = Layout<CH, EXPAND>;
-	using S = SubSlab<CH, EXPAND>;
+	using L = typename PickLayout<CH, EXPAND, COMPACT>::type;
+	using S = SubSlab<L, CH>;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const unsigned char *slab = smem + S::OFF_SLAB + warp * S::SLAB_BYTES;
 	const uint32_t *misc = (const uint32_t *)(smem + L::OFF_MISC);
@@ -171,11 +279,11 @@ __device__ __forceinline__ void slab_finish(const QoiEncParams &P, unsigned char
 
 /* PIPE: the copy-out of a tile (and the wait for its output offset) moves behind the NEXT tile's index pass:
    per iteration  index(k) -> copy-out(k-1) -> emit(k); the pixel buffer is released to the loader after emit(k) already */
-template <int CH, bool EXPAND, bool MATCH, bool PIPE>
+template <int CH, bool EXPAND, bool MATCH, bool PIPE, bool COMPACT>
 __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned char *smem, const TileInfo &ti, const uint32_t *pxv,
                                              uint8_t *gstream, uint32_t parity, SlabCarry &carry) {
-	using L = Layout<CH, EXPAND>;
-	using S = SubSlab<CH, EXPAND>;
+	using L = typename PickLayout<CH, EXPAND, COMPACT>::type;
+	using S = SubSlab<L, CH>;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const uint32_t t = (uint32_t)ti.tile;
 	unsigned char *slab = smem + S::OFF_SLAB + warp * S::SLAB_BYTES;
@@ -260,7 +368,7 @@ __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned cha
 	__syncwarp();
 	bar_arrive(BAR_I_DONE, QOI_N_CS);
 
-	if (PIPE && carry.valid) slab_finish<CH, EXPAND, true>(P, smem, carry); /* the previous tile leaves while the scout looks back for this one */
+	if (PIPE && carry.valid) slab_finish<CH, EXPAND, true, COMPACT>(P, smem, carry); /* the previous tile leaves while the scout looks back for this one */
 
 	bar_sync(BAR_T_READY, QOI_N_CS); /* every warp's table is final; T_in and the run carry are in shared memory */
 	/* ---- phase R: my chunk's deferred pixels against the earlier warps' tables, then the incoming table ---- */
@@ -387,7 +495,7 @@ __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned cha
 	if (PIPE) {
 		bar_arrive(BAR_W_DONE, QOI_N_CS); /* the pixel buffer is free (nothing reads pxv any more): the loader may refill it */
 	} else {
-		slab_finish<CH, EXPAND, false>(P, smem, carry);
+		slab_finish<CH, EXPAND, false, COMPACT>(P, smem, carry);
 		bar_arrive(BAR_W_DONE, QOI_N_CS);
 	}
 }
@@ -400,11 +508,13 @@ __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned cha
 /* SLAB: the compute warps run slab_compute() above (no staging hand-off either, like EARLYW) */
 /* PIPE (slab mode only): see slab_compute -- the scout then also writes header, end marker and length (the loader no longer
    learns when a tile's bytes are out) and publishes the per-warp output offsets in two alternating copies */
-template <int CH, bool EXPAND, bool MATCH, bool EARLYW = false, bool SLAB = false, bool PIPE = false>
-__global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(const QoiEncParams P) {
+/* COMPACT (slab mode only): LayoutC above -- one pixel buffer, 4 CTAs per SM */
+template <int CH, bool EXPAND, bool MATCH, bool EARLYW = false, bool SLAB = false, bool PIPE = false, bool COMPACT = false>
+__global__ void __launch_bounds__(QOI_ENC_THREADS, COMPACT ? 4 : 3) qoi_encode_striped_kernel(const QoiEncParams P) {
+	static_assert(!COMPACT || SLAB, "the compact layout only holds what slab mode needs");
 	constexpr bool NOSTAGE = EARLYW || SLAB; /* the loader never touches the staging area */
-	using L = Layout<CH, EXPAND>;
-	using S = Sub<CH, EXPAND>;
+	using L = typename PickLayout<CH, EXPAND, COMPACT>::type;
+	using S = Sub<CH, EXPAND>; /* striped (non-slab) work area; only meaningful with Layout<CH, EXPAND> */
 	QOI_DYNAMIC_SMEM(smem);
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	const bool scout = warp == QOI_ENC_WARPS;
@@ -412,7 +522,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR);
 	TileInfo *infos = (TileInfo *)(smem + L::OFF_INFO);
 	unsigned char *stage = smem + S::OFF_STAGE;
-	uint2 *Lent_all = (uint2 *)(smem + (SLAB ? SubSlab<CH, EXPAND>::OFF_LENT : S::OFF_LENT));
+	uint2 *Lent_all = (uint2 *)(smem + (SLAB ? SubSlab<L, CH>::OFF_LENT : S::OFF_LENT));
 	uint16_t *Fpos_all = (uint16_t *)(smem + S::OFF_FPOS);
 	uint32_t *patch_all = (uint32_t *)(smem + S::OFF_PATCH);
 	uint32_t *Tin_val = (uint32_t *)(smem + L::OFF_TINVAL);
@@ -431,7 +541,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 	if (loader) {
 		Fetch F;
 		fetch_ticket(P, F);
-		fetch_issue<CH, EXPAND>(P, smem, F, 0, 0);
+		fetch_issue_l<L, CH, EXPAND>(P, smem, F, 0, 0);
 		__syncwarp();
 		bar_arrive(BAR_INFO_READY, QOI_N_ALL);
 		if (!NOSTAGE) bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
@@ -448,7 +558,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 		const TileInfo ti = infos[cur];
 		if (ti.tile < 0) break;
 		const uint32_t t = (uint32_t)ti.tile;
-		const int rb = EXPAND ? 0 : cur;
+		const int rb = (EXPAND || COMPACT) ? 0 : cur;
 		unsigned char *data = smem + L::OFF_RAW + rb * L::RAW_STRIDE + 16;
 		uint32_t *pxv = EXPAND ? (uint32_t *)(smem + L::OFF_PXBUF + 16) : (uint32_t *)data; /* pxv[-1 .. 4096] */
 		uint8_t *gstream = P.streams + ti.stream_off;
@@ -458,9 +568,10 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 			Fetch F;
 			fetch_ticket(P, F);
 			if (EXPAND) bar_sync(BAR_E_DONE, QOI_N_CS);
-			fetch_issue<CH, EXPAND>(P, smem, F, EXPAND ? 0 : (cur ^ 1), cur ^ 1);
+			if (COMPACT && !EXPAND) bar_sync(BAR_W_DONE, QOI_N_CS); /* one pixel buffer: the compute warps must be done with it */
+			fetch_issue_l<L, CH, EXPAND>(P, smem, F, (EXPAND || COMPACT) ? 0 : (cur ^ 1), cur ^ 1);
 
-			bar_sync(BAR_W_DONE, QOI_N_CS); /* staging is complete */
+			if (!(COMPACT && !EXPAND)) bar_sync(BAR_W_DONE, QOI_N_CS); /* staging is complete (COMPACT: waited for above) */
 			__syncwarp();
 			bar_arrive(BAR_INFO_READY, QOI_N_ALL); /* only now: see the note in qoi_enc.cuh */
 			{
@@ -683,7 +794,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 			__syncwarp();
 
 			if (SLAB) {
-				slab_compute<CH, EXPAND, MATCH, PIPE>(P, smem, ti, pxv, gstream, (uint32_t)cur, carry);
+				slab_compute<CH, EXPAND, MATCH, PIPE, COMPACT>(P, smem, ti, pxv, gstream, (uint32_t)cur, carry);
 			} else {
 			const uint32_t nv = ti.n_valid; /* <= 4096; only an image's last tile can be partial */
 			const bool last_tile = ti.px0 + ti.n_valid == ti.npx;
@@ -902,7 +1013,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_striped_kernel(
 		cur ^= 1;
 	}
 
-	if (SLAB && PIPE && !loader && !scout && carry.valid) slab_finish<CH, EXPAND, true>(P, smem, carry); /* the last tile's copy-out */
+	if (SLAB && PIPE && !loader && !scout && carry.valid) slab_finish<CH, EXPAND, true, COMPACT>(P, smem, carry); /* the last tile's copy-out */
 	/* the last CTA to finish rearms the ticket for the next launch */
 	__syncthreads();
 	if (loader && lane == 0) { /* this thread issued the bulk stores */

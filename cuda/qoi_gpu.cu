@@ -40,8 +40,8 @@ struct qoi_gpu_ctx {
 #ifdef QOI_EXP_EARLYW
 	bool enc_earlyw = false;              /* experimental build only (experiments/encoder_earlyw.patch): QOI_GPU_ENC=earlyw */
 #endif
-	int enc_striped = 0;                  /* experimental encoder of qoi_enc4.cuh (QOI_GPU_ENC=striped: 1, striped-match: 2, striped-earlyw: 3, slab: 4, slab-match: 5, slab-pipe: 6, slab-pipe-ballot: 7); emulator-tested,
-	                                         off by default */
+	int enc_striped = 0;                  /* experimental encoder of qoi_enc4.cuh: 1 + index into g_enc4[] (QOI_GPU_ENC=striped | slab | ...);
+	                                         emulator-tested, off by default */
 	bool read_ahead = false;              /* experimental: ring word read one call ahead (QOI_GPU_REFILL=ahead); indexed decoder only */
 	bool refill_uni = true;               /* decoders' stream reader: warp-uniform refill (default) or lane-driven (QOI_GPU_REFILL=lane) */
 	bool walk = true;                     /* look-up variant: word walk (default; 8% faster on photo content) or second-level
@@ -107,34 +107,41 @@ static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
 	return QOI_GPU_OK;
 }
 
-/* experimental striped encoder (qoi_enc4.cuh): same shared-memory layout and grid as the shipped kernels */
+/* experimental encoders of qoi_enc4.cuh, one row per QOI_GPU_ENC value; fn[variant]: 0 = <4, zero-copy>, 1 = <4, EXPAND>, 2 = <3, EXPAND> */
+typedef void (*Enc4Kernel)(const QoiEncParams);
+struct Enc4Mode {
+	const char *name;
+	Enc4Kernel fn[3];
+	int smem[3];
+};
+#define ENC4_ROW(name, MATCH, EARLYW, SLAB, PIPE, COMPACT)                                                                \
+	{name,                                                                                                                \
+	 {qoienc4::qoi_encode_striped_kernel<4, false, MATCH, EARLYW, SLAB, PIPE, COMPACT>,                                     \
+	  qoienc4::qoi_encode_striped_kernel<4, true, MATCH, EARLYW, SLAB, PIPE, COMPACT>,                                      \
+	  qoienc4::qoi_encode_striped_kernel<3, true, MATCH, EARLYW, SLAB, PIPE, COMPACT>},                                     \
+	 {qoienc4::PickLayout<4, false, COMPACT>::type::TOTAL, qoienc4::PickLayout<4, true, COMPACT>::type::TOTAL,              \
+	  qoienc4::PickLayout<3, true, COMPACT>::type::TOTAL}}
+static const Enc4Mode g_enc4[] = {
+    ENC4_ROW("striped", false, false, false, false, false),        /* lane-per-pixel rows, six-ballot slot matching */
+    ENC4_ROW("striped-match", true, false, false, false, false),   /* ... match.any */
+    ENC4_ROW("striped-earlyw", false, true, false, false, false),  /* ... phase W before the output offset is known */
+    ENC4_ROW("slab", false, false, true, false, false),            /* rolled loops, op bytes into per-warp slabs */
+    ENC4_ROW("slab-match", true, false, true, false, false),
+    ENC4_ROW("slab-pipe", true, false, true, true, false),         /* ... copy-out behind the next tile's index pass */
+    ENC4_ROW("slab-pipe-ballot", false, false, true, true, false),
+    ENC4_ROW("slab4", true, false, true, false, true),             /* ... compact layout: one pixel buffer, 4 CTAs per SM */
+    ENC4_ROW("slab4-pipe", true, false, true, true, true),
+};
+#undef ENC4_ROW
+
 static int enc_striped_setup(qoi_gpu_ctx *ctx) {
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, false>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<4, true>::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc4::qoi_encode_striped_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, qoienc::Layout<3, true>::TOTAL));
-	int nb[3] = {0, 0, 0};
-	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[0], qoienc4::qoi_encode_striped_kernel<4, false, false>, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL));
-	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[1], qoienc4::qoi_encode_striped_kernel<4, true, false>, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL));
-	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[2], qoienc4::qoi_encode_striped_kernel<3, true, false>, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL));
-	for (int i = 0; i < 3; i++) ctx->enc_blocks_per_sm[i] = nb[i] > 0 ? nb[i] : 1; /* the grid must not exceed what is co-resident (look-back) */
+	const Enc4Mode &m = g_enc4[ctx->enc_striped - 1];
+	for (int v = 0; v < 3; v++) {
+		CK(ctx, cudaFuncSetAttribute((const void *)m.fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem[v]));
+		int nb = 0;
+		CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)m.fn[v], QOI_ENC_THREADS, (size_t)m.smem[v]));
+		ctx->enc_blocks_per_sm[v] = nb > 0 ? nb : 1; /* the grid must not exceed what is co-resident (look-back) */
+	}
 	return QOI_GPU_OK;
 }
 
@@ -183,13 +190,8 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 #ifdef QOI_EXP_EARLYW
 		if (ev && !strcmp(ev, "earlyw")) c->enc_earlyw = true;
 #endif
-		if (ev && !strcmp(ev, "striped")) c->enc_striped = 1;
-		if (ev && !strcmp(ev, "striped-match")) c->enc_striped = 2;
-		if (ev && !strcmp(ev, "striped-earlyw")) c->enc_striped = 3;
-		if (ev && !strcmp(ev, "slab")) c->enc_striped = 4;
-		if (ev && !strcmp(ev, "slab-match")) c->enc_striped = 5;
-		if (ev && !strcmp(ev, "slab-pipe")) c->enc_striped = 6;        /* match.any */
-		if (ev && !strcmp(ev, "slab-pipe-ballot")) c->enc_striped = 7;
+		for (size_t k = 0; ev && k < sizeof g_enc4 / sizeof g_enc4[0]; k++)
+			if (!strcmp(ev, g_enc4[k].name)) c->enc_striped = (int)k + 1;
 	}
 	int rc = enc_occupancy<4, false>(c, &c->enc_blocks_per_sm[0]);
 	if (!rc) rc = enc_occupancy<4, true>(c, &c->enc_blocks_per_sm[1]);
@@ -303,46 +305,9 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	const int variant = p->geom.channels == 3 ? 2 : (zero_copy ? 0 : 1);
 	uint32_t grid = (uint32_t)(ctx->sm_count * ctx->enc_blocks_per_sm[variant]);
 	if (grid > P.n_tiles) grid = P.n_tiles;
-	if (ctx->enc_striped) { /* experimental, QOI_GPU_ENC=striped | striped-match */
-		const bool mt = ctx->enc_striped == 2, ew = ctx->enc_striped == 3;
-		if (ctx->enc_striped >= 6) { /* slab mode, copy-out pipelined behind the next tile's index pass */
-			const bool sm = ctx->enc_striped == 6;
-			if (variant == 0) {
-				if (sm) qoienc4::qoi_encode_striped_kernel<4, false, true, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-				else qoienc4::qoi_encode_striped_kernel<4, false, false, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-			} else if (variant == 1) {
-				if (sm) qoienc4::qoi_encode_striped_kernel<4, true, true, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-				else qoienc4::qoi_encode_striped_kernel<4, true, false, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-			} else {
-				if (sm) qoienc4::qoi_encode_striped_kernel<3, true, true, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
-				else qoienc4::qoi_encode_striped_kernel<3, true, false, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
-			}
-		} else if (ctx->enc_striped >= 4) { /* slab mode */
-			const bool sm = ctx->enc_striped == 5;
-			if (variant == 0) {
-				if (sm) qoienc4::qoi_encode_striped_kernel<4, false, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-				else qoienc4::qoi_encode_striped_kernel<4, false, false, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-			} else if (variant == 1) {
-				if (sm) qoienc4::qoi_encode_striped_kernel<4, true, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-				else qoienc4::qoi_encode_striped_kernel<4, true, false, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-			} else {
-				if (sm) qoienc4::qoi_encode_striped_kernel<3, true, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
-				else qoienc4::qoi_encode_striped_kernel<3, true, false, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
-			}
-		} else if (ew) {
-			if (variant == 0) qoienc4::qoi_encode_striped_kernel<4, false, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-			else if (variant == 1) qoienc4::qoi_encode_striped_kernel<4, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-			else qoienc4::qoi_encode_striped_kernel<3, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
-		} else if (variant == 0) {
-			if (mt) qoienc4::qoi_encode_striped_kernel<4, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-			else qoienc4::qoi_encode_striped_kernel<4, false, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-		} else if (variant == 1) {
-			if (mt) qoienc4::qoi_encode_striped_kernel<4, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-			else qoienc4::qoi_encode_striped_kernel<4, true, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-		} else {
-			if (mt) qoienc4::qoi_encode_striped_kernel<3, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
-			else qoienc4::qoi_encode_striped_kernel<3, true, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
-		}
+	if (ctx->enc_striped) { /* experimental, QOI_GPU_ENC=<a name of g_enc4[]> */
+		const Enc4Mode &m = g_enc4[ctx->enc_striped - 1];
+		m.fn[variant]<<<grid, QOI_ENC_THREADS, (size_t)m.smem[variant], s>>>(P);
 #ifdef QOI_EXP_EARLYW
 	} else if (ctx->enc_earlyw) { /* experimental build only, QOI_GPU_ENC=earlyw */
 		if (variant == 0) qoienc::qoi_encode_kernel<4, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);

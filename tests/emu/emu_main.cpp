@@ -57,6 +57,8 @@ static void run_encode(const QoiEncParams &P, unsigned grid, unsigned seed) {
 	if (ev && !strcmp(ev, "striped-earlyw")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, false, true>(P); }, seed); return; }
 	if (ev && !strcmp(ev, "slab")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, false, false, true>(P); }, seed); return; }
 	if (ev && !strcmp(ev, "slab-pipe")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true, false, true, true>(P); }, seed); return; }
+	if (ev && !strcmp(ev, "slab4")) { using LC = qoienc4::LayoutC<CH, EXPAND>; qemu::launch(grid, QOI_ENC_THREADS, (size_t)LC::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true, false, true, false, true>(P); }, seed); return; }
+	if (ev && !strcmp(ev, "slab4-pipe")) { using LC = qoienc4::LayoutC<CH, EXPAND>; qemu::launch(grid, QOI_ENC_THREADS, (size_t)LC::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true, false, true, true, true>(P); }, seed); return; }
 	if (ev && !strcmp(ev, "slab-pipe-ballot")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, false, false, true, true>(P); }, seed); return; }
 	if (ev && !strcmp(ev, "slab-match")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true, false, true>(P); }, seed); return; }
 	if (ev && !strcmp(ev, "striped-match")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true>(P); }, seed); return; }

@@ -51,6 +51,7 @@ def test_emulated_distributions(emu, cpu, dist):
 # cuda/qoi_enc4.cuh (QOI_GPU_ENC=striped | striped-match | striped-earlyw); the tests below alternate between the first two ...
 STRIPED = ({"QOI_EMU_ENC": "striped"}, {"QOI_EMU_ENC": "striped-match"})
 PIPE = ({"QOI_EMU_ENC": "slab-pipe"}, {"QOI_EMU_ENC": "slab-pipe-ballot"})  # slab mode with the copy-out behind the next tile's index pass
+COMPACT = ({"QOI_EMU_ENC": "slab4"}, {"QOI_EMU_ENC": "slab4-pipe"})  # slab mode in the compact layout (one pixel buffer, 4 CTAs per SM)
 SLAB = ({"QOI_EMU_ENC": "slab"}, {"QOI_EMU_ENC": "slab-match"})  # the rolled "slab" mode of the same kernel (QOI_GPU_ENC=slab | slab-match)
 STRIPED_EARLYW = ({"QOI_EMU_ENC": "striped-earlyw"},)  # ... and run this one on a subset
 
@@ -69,7 +70,7 @@ def run_variants(emu, img, w, h, ch, n, grid, seed, mis, variants):
 @pytest.mark.parametrize("dist", range(8))
 def test_emulated_striped_encoder_distributions(emu, cpu, dist):
     """The experimental lane-per-pixel encoder: streams bit exact, its restart index decodes, nothing written out of bounds."""
-    four = STRIPED + SLAB + PIPE
+    four = STRIPED + SLAB + PIPE + COMPACT
     run_variants(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0, four)
     run_variants(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist, four)
     if True:
@@ -82,16 +83,16 @@ def test_emulated_striped_encoder_stress_and_runs(emu, cpu):
     for it in range(18):
         w = int(rng.integers(60, 300)); h = int(rng.integers(20, 120)); ch = int(rng.integers(3, 5)); n = int(rng.integers(1, 4))
         img = np.concatenate([q.stress_image(rng, w * h, ch, it % 6) for _ in range(n)])
-        seven = STRIPED + SLAB + STRIPED_EARLYW + PIPE
-        run_variants(emu, img, w, h, ch, n, int(rng.integers(1, 5)), it + 1, int(rng.integers(0, 17)) if it % 2 else 0, (seven[it % 7], seven[(it + 3) % 7], PIPE[it % 2]))
+        nine = STRIPED + SLAB + STRIPED_EARLYW + PIPE + COMPACT
+        run_variants(emu, img, w, h, ch, n, int(rng.integers(1, 5)), it + 1, int(rng.integers(0, 17)) if it % 2 else 0, (nine[it % 9], nine[(it + 4) % 9], COMPACT[it % 2]))
     n = 40000  # runs that cross warp chunks, tiles and the 62 boundary; runs from the image start (qoi.h:396-399)
     a = np.zeros((n, 4), dtype=np.uint8); a[:, 3] = 255
     b = np.zeros((n, 4), dtype=np.uint8)
     c = np.zeros((n, 4), dtype=np.uint8); c[:, 3] = 255; c[n // 2:] = (9, 9, 9, 255); c[-5:] = (0, 0, 0, 255)
     d = np.full((n, 4), 200, dtype=np.uint8); d[12345] = (1, 2, 3, 4)
     for k, img in enumerate((a, b, c, d)):
-        run_variants(emu, img.reshape(-1), 400, 100, 4, 1, 4, 3, 0, STRIPED + SLAB + STRIPED_EARLYW + PIPE)
-        run_variants(emu, np.ascontiguousarray(img[:, :3]).reshape(-1), 400, 100, 3, 1, 3, 4, 5, STRIPED + SLAB + STRIPED_EARLYW + PIPE)
+        run_variants(emu, img.reshape(-1), 400, 100, 4, 1, 4, 3, 0, STRIPED + SLAB + STRIPED_EARLYW + PIPE + COMPACT)
+        run_variants(emu, np.ascontiguousarray(img[:, :3]).reshape(-1), 400, 100, 3, 1, 3, 4, 5, STRIPED + SLAB + STRIPED_EARLYW + PIPE + COMPACT)
 
 
 def test_emulated_stress(emu, cpu):
@@ -141,8 +142,8 @@ def test_emulated_many_tiles(emu, cpu):
     """512 x 512 images (64 tiles each) on 6 CTAs: look-back windows of many in-flight predecessors, for the shipped encoder
     and every variant."""
     img = cpu.batch(1, 512, 512, 4, 4)
-    run_variants(emu, img, 512, 512, 4, 1, 6, 7, 0, ({"QOI_GPU_LOOKUP": "walk"}, STRIPED[0], SLAB[1], PIPE[0]))
+    run_variants(emu, img, 512, 512, 4, 1, 6, 7, 0, ({"QOI_GPU_LOOKUP": "walk"}, STRIPED[0], SLAB[1], PIPE[0], COMPACT[1]))
     pal = cpu.batch(1, 512, 300, 3, 6)
-    run_variants(emu, pal, 512, 300, 3, 1, 5, 9, 3, (STRIPED[1], SLAB[0], PIPE[1]))
+    run_variants(emu, pal, 512, 300, 3, 1, 5, 9, 3, (STRIPED[1], SLAB[0], PIPE[1], COMPACT[0]))
     for grid in (1, 2, 7):  # the pipelined hand-offs with one CTA, with fewer CTAs than images, with more CTAs than tiles in flight
-        run_variants(emu, cpu.batch(5, 256, 64, 4, 6), 256, 64, 4, 5, grid, 3 + grid, 5, PIPE[:1])
+        run_variants(emu, cpu.batch(5, 256, 64, 4, 6), 256, 64, 4, 5, grid, 3 + grid, 5, PIPE[:1] + COMPACT)

@@ -19,7 +19,7 @@ void qoi_synth_batch(uint8_t *dst, size_t stride, int n, uint32_t w, uint32_t h,
 
 int main(int argc, char **argv) {
 	const int n = argc > 1 ? atoi(argv[1]) : 8, W = 4096, H = 4096, CH = 4, runs = 5;
-	const char *variants[] = {"", "striped", "striped-earlyw", "striped-match", "slab", "slab-match", "slab-pipe", "slab-pipe-ballot"};
+	const char *variants[] = {"", "striped", "striped-earlyw", "striped-match", "slab", "slab-match", "slab-pipe", "slab-pipe-ballot", "slab4", "slab4-pipe"};
 	const size_t img = (size_t)W * H * CH;
 	qoi_desc *descs = (qoi_desc *)calloc((size_t)n, sizeof(qoi_desc));
 	uint64_t *poff = (uint64_t *)calloc((size_t)n, 8), *soff = (uint64_t *)calloc((size_t)n, 8);
