@@ -58,6 +58,12 @@ struct QoiTileState {
 	int32_t *rs_px;        /* [tiles] first pixel of the tile at which an op starts (-1: none) */
 	int32_t *rs_byte;      /* [tiles] stream offset of that op */
 	uint32_t *rs_prev;     /* [tiles] value of the pixel before it */
+	/* a second restart point per tile, at its first op start at or after pixel QOI_TILE_PX / 2 -- written only by the
+	   slab-mode encoders of qoi_enc4.cuh (experimental); it lets the indexed decoder run two lanes per tile */
+	uint64_t *mid_ent;     /* [tiles][64] table before that op: [63:32] value, bit 0 slot written */
+	int32_t *mid_px;       /* [tiles] its pixel (-1: none) */
+	int32_t *mid_byte;     /* [tiles] stream offset of the op */
+	uint32_t *mid_prev;    /* [tiles] value of the pixel before it */
 };
 
 struct QoiEncParams {

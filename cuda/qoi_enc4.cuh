@@ -248,12 +248,16 @@ __device__ __forceinline__ void slab_finish(const QoiEncParams &P, unsigned char
 	uint32_t woff = 0;
 	if (PIPE) woff = wpre[c.parity * QOI_ENC_WARPS + warp];
 	else for (uint32_t w = 0; w < warp; w++) woff += wtot[w];
-	if (c.rs_off != 0xFFFFFFFFu) { /* warp 0: the owner of the restart pixel records where its op starts */
-		P.st.rs_px[c.t] = c.rs_px;
-		P.st.rs_byte[c.t] = (int32_t)(tile_base + c.rs_off);
-		P.st.rs_prev[c.t] = c.rs_prev;
+	if (warp == 0 || warp == QOI_ENC_WARPS / 2) { /* restart records: tile start (warp 0), second half (warp 4) */
+		int32_t *o_px = warp ? P.st.mid_px : P.st.rs_px, *o_byte = warp ? P.st.mid_byte : P.st.rs_byte;
+		uint32_t *o_prev = warp ? P.st.mid_prev : P.st.rs_prev;
+		if (c.rs_off != 0xFFFFFFFFu) { /* the lane that owns the restart pixel records where its op starts */
+			o_px[c.t] = c.rs_px;
+			o_byte[c.t] = (int32_t)(tile_base + woff + c.rs_off);
+			o_prev[c.t] = c.rs_prev;
+		}
+		if (lane == 0 && c.rs_px == INT_MAX) o_px[c.t] = -1;
 	}
-	if (tid == 0 && c.rs_px == INT_MAX) P.st.rs_px[c.t] = -1;
 	uint8_t *gdst = c.gstream + tile_base + woff;
 	const uint32_t total = c.bytes;
 	uint32_t head = (16u - (uint32_t)((uintptr_t)gdst & 15u)) & 15u; /* bytes up to the first aligned 16 */
@@ -406,13 +410,39 @@ __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned cha
 			break;
 		}
 	}
+	/* table at the tile's mid point = what qoi.h's index[] holds before the first pixel of warp 4's chunk: the nearest of the
+	   first four warps' tables, else the incoming table (the same walk phase R does); pixels between the mid point and the
+	   restart op are run pixels and write nothing.  Read by the decoder when it runs two lanes per tile. */
+	if (warp == QOI_ENC_WARPS / 2) {
+#pragma unroll
+		for (int q = 0; q < 2; q++) {
+			const uint32_t sl = lane + 32u * q;
+			bool found = false;
+			uint32_t val = 0;
+			for (int w2 = (int)warp - 1; w2 >= 0; w2--) {
+				const uint2 e = Lent_all[w2 * 64 + sl];
+				if (e.y) {
+					val = e.x;
+					found = true;
+					break;
+				}
+			}
+			if (!found && Tin_flag[sl]) {
+				val = Tin_val[sl];
+				found = true;
+			}
+			P.st.mid_ent[(size_t)t * 64 + sl] = ((uint64_t)val << 32) | (found ? 1ull : 0ull);
+		}
+	}
 	/* PIPE: nobody waits for B_READY before the next tile's index pass re-initialises the tables, so everybody must be
 	   done reading the other warps' tables (phase R) and wlnr[] before anybody goes on */
 	if (PIPE) bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
 
 	/* ---- emit pass: four independent rows at a time; op bytes go into the warp's slab at a running offset ---- */
 	uint32_t off = 0;                 /* bytes of this chunk so far (uniform) */
-	int32_t cand = INT_MAX;           /* decoder restart point: first pixel of the tile at which an op starts (warp 0) */
+	/* decoder restart points: the first pixel at which an op starts in the tile (warp 0) and in its second half (warp 4) */
+	const bool rs_owner = warp == 0 || warp == QOI_ENC_WARPS / 2;
+	int32_t cand = INT_MAX;
 	uint32_t rs_off = 0xFFFFFFFFu;    /* its byte offset, in the lane that owns the pixel */
 #pragma unroll 1
 	for (int g = 0; g < QOI_WARP_STEPS / 4; g++) {
@@ -438,7 +468,7 @@ __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned cha
 					const uint32_t gi = ti.px0 + il;
 					c = run_code(gi - (uint32_t)lnr, (last_tile && gi == ti.npx - 1u) || pxv[il + 1] != v);
 				}
-				if (warp == 0 && g == 0 && k < 2 && valid && (nonrun || ((c >> 8) & 0x3Fu) == 0u)) starts |= 1u << k;
+				if (rs_owner && g == 0 && k < 2 && valid && (nonrun || ((c >> 8) & 0x3Fu) == 0u)) starts |= 1u << k;
 				if (nr) lnr_img = (int32_t)(ti.px0 + rb0 + 31u - (uint32_t)__clz((int)nr));
 			}
 			cd[k] = c;
@@ -452,13 +482,13 @@ __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned cha
 			if (lane >= (uint32_t)dlt) incl += o;
 		}
 		const uint32_t ex = incl - pk, tot = __shfl_sync(QOI_FULL_MASK, incl, 31);
-		if (warp == 0 && g == 0) {
+		if (rs_owner && g == 0) {
 #pragma unroll
 			for (int k = 0; k < 2; k++) {
 				const uint32_t b = __ballot_sync(QOI_FULL_MASK, (starts >> k) & 1u);
 				if (b && cand == INT_MAX) {
-					cand = (int32_t)((uint32_t)k * 32u + (uint32_t)__ffs((int)b) - 1u);
-					if ((int32_t)((uint32_t)k * 32u + lane) == cand) rs_off = off + (k ? (tot & 0xFFu) : 0u) + ((ex >> (8 * k)) & 0xFFu);
+					cand = (int32_t)(wbase + (uint32_t)k * 32u + (uint32_t)__ffs((int)b) - 1u);
+					if ((int32_t)(wbase + (uint32_t)k * 32u + lane) == cand) rs_off = off + (k ? (tot & 0xFFu) : 0u) + ((ex >> (8 * k)) & 0xFFu);
 				}
 			}
 		}
@@ -486,9 +516,9 @@ __device__ __forceinline__ void slab_compute(const QoiEncParams &P, unsigned cha
 	carry.t = t;
 	carry.gstream = gstream;
 	carry.bytes = off;
-	carry.rs_px = (warp == 0 && cand != INT_MAX) ? (int32_t)ti.px0 + cand : INT_MAX;
+	carry.rs_px = (rs_owner && cand != INT_MAX) ? (int32_t)ti.px0 + cand : INT_MAX;
 	carry.rs_off = rs_off;
-	carry.rs_prev = (warp == 0 && cand != INT_MAX) ? pxv[cand - 1] : 0u;
+	carry.rs_prev = (rs_owner && cand != INT_MAX) ? pxv[cand - 1] : 0u;
 	carry.parity = parity;
 	__syncwarp();
 	bar_arrive(BAR_C_DONE, QOI_N_CS);

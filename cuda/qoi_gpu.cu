@@ -40,6 +40,8 @@ struct qoi_gpu_ctx {
 #ifdef QOI_EXP_EARLYW
 	bool enc_earlyw = false;              /* experimental build only (experiments/encoder_earlyw.patch): QOI_GPU_ENC=earlyw */
 #endif
+	bool dec_half = false;                /* experimental: indexed decode with two lanes per tile (QOI_GPU_DEC=half); only used when the
+	                                         index was written by a slab-mode encoder */
 	int enc_striped = 0;                  /* experimental encoder of qoi_enc4.cuh: 1 + index into g_enc4[] (QOI_GPU_ENC=striped | slab | ...);
 	                                         emulator-tested, off by default */
 	bool read_ahead = false;              /* experimental: ring word read one call ahead (QOI_GPU_REFILL=ahead); indexed decoder only */
@@ -68,6 +70,7 @@ struct qoi_gpu_plan {
 	std::vector<qoi_gpu_plan *> chunks;
 	std::vector<int> chunk_first;
 	std::vector<cudaEvent_t> ev_in, ev_k;
+	bool index_has_mid = false; /* the last encode on this plan also wrote the mid-tile restart records */
 	int index_owner = 0; /* who holds the restart index of the last encode: 0 nobody, 1 this plan, 2 the chunks */
 	/* scratch of the foreign-stream decoder (qoi_fdec.cuh), allocated on first use */
 	unsigned char *d_fstate = nullptr;
@@ -111,11 +114,12 @@ static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
 typedef void (*Enc4Kernel)(const QoiEncParams);
 struct Enc4Mode {
 	const char *name;
+	bool slab; /* writes the mid-tile restart records (QoiTileState::mid_*) */
 	Enc4Kernel fn[3];
 	int smem[3];
 };
 #define ENC4_ROW(name, MATCH, EARLYW, SLAB, PIPE, COMPACT)                                                                \
-	{name,                                                                                                                \
+	{name, SLAB,                                                                                                          \
 	 {qoienc4::qoi_encode_striped_kernel<4, false, MATCH, EARLYW, SLAB, PIPE, COMPACT>,                                     \
 	  qoienc4::qoi_encode_striped_kernel<4, true, MATCH, EARLYW, SLAB, PIPE, COMPACT>,                                      \
 	  qoienc4::qoi_encode_striped_kernel<3, true, MATCH, EARLYW, SLAB, PIPE, COMPACT>},                                     \
@@ -146,8 +150,12 @@ static int enc_striped_setup(qoi_gpu_ctx *ctx) {
 }
 
 template <int OUT_CH, int BLOCK>
-static void launch_decode(const QoiDecParams &D, cudaStream_t s, int uni) { /* 0 lane-driven refill, 1 warp-uniform, 2 + word read ahead */
+static void launch_decode(const QoiDecParams &D, cudaStream_t s, int uni) { /* 0 lane-driven refill, 1 warp-uniform, 2 + word read ahead, 3 two lanes per tile */
 	const uint32_t grid = (D.n_jobs + BLOCK - 1) / BLOCK;
+	if (uni == 3) {
+		qoidec::qoi_decode_kernel<OUT_CH, BLOCK, true, false, true><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
+		return;
+	}
 	if (uni == 2) qoidec::qoi_decode_kernel<OUT_CH, BLOCK, true, true><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
 	else if (uni) qoidec::qoi_decode_kernel<OUT_CH, BLOCK, true, false><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
 	else qoidec::qoi_decode_kernel<OUT_CH, BLOCK, false, false><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
@@ -190,6 +198,8 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 #ifdef QOI_EXP_EARLYW
 		if (ev && !strcmp(ev, "earlyw")) c->enc_earlyw = true;
 #endif
+		const char *dv = getenv("QOI_GPU_DEC");
+		if (dv && !strcmp(dv, "half")) c->dec_half = true;
 		for (size_t k = 0; ev && k < sizeof g_enc4 / sizeof g_enc4[0]; k++)
 			if (!strcmp(ev, g_enc4[k].name)) c->enc_striped = (int)k + 1;
 	}
@@ -326,6 +336,7 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	g_launches++;
 	CK(ctx, cudaGetLastError());
 	p->index_owner = 1;
+	p->index_has_mid = ctx->enc_striped && g_enc4[ctx->enc_striped - 1].slab;
 	return QOI_GPU_OK;
 }
 
@@ -393,13 +404,15 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 	D.use_index = 1;
 	D.st = p->st;
 	/* few segments: narrow blocks so that they spread over the SMs */
+	const bool half = ctx->dec_half && p->index_has_mid; /* experimental: job = 2 * tile + half */
+	if (half) D.n_jobs *= 2;
 	const bool narrow = D.n_jobs < (uint32_t)ctx->sm_count * 128u * 2u;
 	if (D.out_channels == 4) {
-		if (narrow) launch_decode<4, 32>(D, s, ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
-		else launch_decode<4, 128>(D, s, ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
+		if (narrow) launch_decode<4, 32>(D, s, half ? 3 : ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
+		else launch_decode<4, 128>(D, s, half ? 3 : ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
 	} else {
-		if (narrow) launch_decode<3, 32>(D, s, ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
-		else launch_decode<3, 128>(D, s, ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
+		if (narrow) launch_decode<3, 32>(D, s, half ? 3 : ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
+		else launch_decode<3, 128>(D, s, half ? 3 : ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
 	}
 	g_launches++;
 	CK(ctx, cudaGetLastError());

@@ -105,7 +105,7 @@ static inline int qoi_plan_geometry(QoiPlanGeom &g, int n, const QoiDescPOD *des
 }
 
 struct QoiStateLayout {
-	size_t off[9];
+	size_t off[13];
 	size_t total;
 };
 
@@ -113,8 +113,8 @@ static inline QoiStateLayout qoi_state_layout(uint32_t n_tiles) {
 	QoiStateLayout L;
 	size_t o = 0;
 	const size_t T = n_tiles;
-	const size_t sizes[9] = {16, T * 512, T * 32, T * 512, T * 32, T * 8, T * 4, T * 4, T * 4};
-	for (int i = 0; i < 9; i++) {
+	const size_t sizes[13] = {16, T * 512, T * 32, T * 512, T * 32, T * 8, T * 4, T * 4, T * 4, T * 512, T * 4, T * 4, T * 4};
+	for (int i = 0; i < 13; i++) {
 		L.off[i] = o;
 		o += (sizes[i] + 255) & ~(size_t)255;
 	}
@@ -132,6 +132,10 @@ static inline void qoi_state_bind(QoiTileState &st, unsigned char *base, const Q
 	st.rs_px = (int32_t *)(base + L.off[6]);
 	st.rs_byte = (int32_t *)(base + L.off[7]);
 	st.rs_prev = (uint32_t *)(base + L.off[8]);
+	st.mid_ent = (uint64_t *)(base + L.off[9]);
+	st.mid_px = (int32_t *)(base + L.off[10]);
+	st.mid_byte = (int32_t *)(base + L.off[11]);
+	st.mid_prev = (uint32_t *)(base + L.off[12]);
 }
 
 /* ------------------------------------------------------------------ foreign-stream decoder scratch (qoi_fdec.cuh) */

@@ -68,6 +68,14 @@ static void run_encode(const QoiEncParams &P, unsigned grid, unsigned seed) {
 static void run_decode(const QoiDecParams &P, unsigned seed) {
 	unsigned grid = (P.n_jobs + QOI_DEC_THREADS - 1) / QOI_DEC_THREADS;
 	size_t smem = QOI_DEC_SMEM_WORDS * QOI_DEC_THREADS * 4;
+	if (getenv("QOI_EMU_DEC") && !strcmp(getenv("QOI_EMU_DEC"), "half") && P.use_index) { /* two lanes per tile; needs a slab-mode encoder's index */
+		QoiDecParams H = P;
+		H.n_jobs = 2 * P.n_jobs;
+		grid = (H.n_jobs + QOI_DEC_THREADS - 1) / QOI_DEC_THREADS;
+		if (P.out_channels == 4) qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, true, false, true>(H); }, seed);
+		else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true, false, true>(H); }, seed);
+		return;
+	}
 	if (P.out_channels == 4) qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_ahead()) qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, true, true>(P); else if (emu_uni()) qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, true, false>(P); else qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, false, false>(P); }, seed);
 	else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_ahead()) qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true, true>(P); else if (emu_uni()) qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true, false>(P); else qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, false, false>(P); }, seed);
 }
@@ -194,6 +202,11 @@ int main(int argc, char **argv) {
 					if (got[olen] != 0xEE || (soff[i] && got[-1] != 0xEE)) { printf("FAIL encode image %d: wrote outside its stream\n", i); return 1; }
 					free(ref);
 				}
+			}
+			if (getenv("QOI_EMU_HALFSTAT")) { /* how many tiles carry a second restart point (slab-mode encoders only) */
+				unsigned have = 0;
+				for (uint32_t tt = 0; tt < g.n_tiles; tt++) have += P.st.mid_px[tt] >= 0;
+				fprintf(stderr, "mid restart points: %u of %u tiles\n", have, g.n_tiles);
 			}
 			/* decode what we wrote: with the restart index, then as a foreign stream */
 			for (int use_index = 1; use_index >= (getenv("QOI_EMU_SKIP_FOREIGN") ? 1 : 0); use_index--) { /* encoder-variant runs skip the any-stream decoder */

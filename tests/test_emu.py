@@ -147,3 +147,15 @@ def test_emulated_many_tiles(emu, cpu):
     run_variants(emu, pal, 512, 300, 3, 1, 5, 9, 3, (STRIPED[1], SLAB[0], PIPE[1], COMPACT[0]))
     for grid in (1, 2, 7):  # the pipelined hand-offs with one CTA, with fewer CTAs than images, with more CTAs than tiles in flight
         run_variants(emu, cpu.batch(5, 256, 64, 4, 6), 256, 64, 4, 5, grid, 3 + grid, 5, PIPE[:1] + COMPACT)
+
+
+def test_emulated_two_lanes_per_tile_decode(emu, cpu):
+    """QOI_GPU_DEC=half: the slab-mode encoders also leave a restart point at every tile's mid point (table = merge of the first
+    four warps' tables with the incoming one); the indexed decoder then runs job = 2 * tile + half.  Shapes around the mid
+    point, runs crossing it, partial tiles."""
+    half = lambda v: dict(v, QOI_EMU_DEC="half")
+    for k, (w, h, ch, n, dist) in enumerate([(160, 130, 4, 2, 4), (131, 97, 3, 2, 3), (400, 100, 4, 1, 7), (2048, 1, 4, 3, 4), (2049, 1, 4, 3, 4),
+                                             (2110, 1, 3, 2, 7), (2047, 3, 4, 2, 2), (512, 512, 4, 1, 0), (256, 64, 4, 5, 6), (300, 200, 3, 2, 5)]):
+        img = cpu.batch(n, w, h, ch, dist)
+        variants = (SLAB + PIPE + COMPACT)
+        run_variants(emu, img, w, h, ch, n, 1 + k % 4, k + 1, (0, 5, 3)[k % 3] if ch == 4 else 1 + k % 3, (half(variants[k % 6]), half(variants[(k + 3) % 6])))

@@ -4,6 +4,7 @@
 #   stage 2 (per variant named on the command line; default: none) GPU parity tests that exercise the encoder, bench lines for
 #                       photo / noise / palette / const0, one ncu --set full capture
 #   gpurun --timeout 1500 -- 'bash tools/gpu_ab_enc.sh slab-match striped-match'
+# QOI_GPU_DEC=half (two decode lanes per tile, needs a slab* encoder) can be exported around the call; stage 1 times it as *+half
 # Variants: striped | striped-match | striped-earlyw | slab | slab-match | slab-pipe | slab-pipe-ballot | slab4 | slab4-pipe   (QOI_GPU_ENC), earlyw (needs qoi_b200/libqoi_gpu_exp.so)
 mkdir -p gpurun_out
 exec > >(tee gpurun_out/ab_enc.log) 2>&1

@@ -19,7 +19,9 @@ void qoi_synth_batch(uint8_t *dst, size_t stride, int n, uint32_t w, uint32_t h,
 
 int main(int argc, char **argv) {
 	const int n = argc > 1 ? atoi(argv[1]) : 8, W = 4096, H = 4096, CH = 4, runs = 5;
-	const char *variants[] = {"", "striped", "striped-earlyw", "striped-match", "slab", "slab-match", "slab-pipe", "slab-pipe-ballot", "slab4", "slab4-pipe"};
+	/* QOI_GPU_ENC value, optionally "+half": the same encoder with QOI_GPU_DEC=half (indexed decode with two lanes per tile) */
+	const char *variants[] = {"", "striped", "striped-earlyw", "striped-match", "slab", "slab-match", "slab-pipe", "slab-pipe-ballot", "slab4", "slab4-pipe",
+	                          "slab-match+half", "slab4-pipe+half"};
 	const size_t img = (size_t)W * H * CH;
 	qoi_desc *descs = (qoi_desc *)calloc((size_t)n, sizeof(qoi_desc));
 	uint64_t *poff = (uint64_t *)calloc((size_t)n, 8), *soff = (uint64_t *)calloc((size_t)n, 8);
@@ -46,7 +48,12 @@ int main(int argc, char **argv) {
 	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
 	int bad = 0;
 	for (int v = 0; v < (int)(sizeof variants / sizeof variants[0]); v++) {
-		setenv("QOI_GPU_ENC", variants[v], 1); /* read by qoi_gpu_ctx_create */
+		char encname[64];
+		snprintf(encname, sizeof encname, "%s", variants[v]);
+		char *plus = strchr(encname, 0x2B);
+		if (plus) *plus = 0;
+		setenv("QOI_GPU_ENC", encname, 1); /* both read by qoi_gpu_ctx_create */
+		setenv("QOI_GPU_DEC", plus ? plus + 1 : "", 1);
 		qoi_gpu_ctx *ctx = NULL;
 		qoi_gpu_plan *plan = NULL;
 		if (qoi_gpu_ctx_create(&ctx, 0) != QOI_GPU_OK || qoi_gpu_plan_create(ctx, &plan, n, descs, poff, soff, NULL, 4) != QOI_GPU_OK) { printf("setup failed\n"); return 2; }
@@ -73,7 +80,7 @@ int main(int argc, char **argv) {
 		if (v) {
 			for (int i = 0; i < n && same; i++) same = l_got[i] == l_ref[i] && memcmp(h_got + soff[i], h_ref + soff[i], (size_t)l_ref[i]) == 0;
 		}
-		printf("%-15s encode %7.3f ms (%6.1f Gpx/s)  indexed decode %7.3f ms   streams %s   round trip %s\n", v ? variants[v] : "shipped", enc / runs,
+		printf("%-17s encode %7.3f ms (%6.1f Gpx/s)  indexed decode %7.3f ms   streams %s   round trip %s\n", v ? variants[v] : "shipped", enc / runs,
 		       (double)W * H * n / (enc / runs * 1e6), dec / runs, v ? (same ? "IDENTICAL to shipped" : "*** DIFFER ***") : "(reference for the others)",
 		       rt ? "ok" : "*** MISMATCH ***");
 		fflush(stdout);
