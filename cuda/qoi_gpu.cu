@@ -38,7 +38,10 @@ struct qoi_gpu_ctx {
 	char err[256] = {0};
 	int enc_blocks_per_sm[3] = {0, 0, 0}; /* <4,false>, <4,true>, <3,true> */
 #ifdef QOI_EXP_EARLYW
-	bool enc_earlyw = false;              /* experimental build only (experiments/encoder_earlyw.patch): QOI_GPU_ENC=earlyw */
+	bool enc_earlyw = false;              /* experimental build only (experiments/encoder_earlyw.patch): QOI_GPU_ENC=earlyw | earlyw-mid */
+#endif
+#ifdef QOI_EXP_MID
+	bool enc_mid = false;                 /* experimental build only (experiments/encoder_mid.patch): QOI_GPU_ENC=mid | earlyw-mid */
 #endif
 	bool dec_half = false;                /* experimental: indexed decode with two lanes per tile (QOI_GPU_DEC=half); only used when the
 	                                         index was written by a slab-mode encoder */
@@ -103,6 +106,10 @@ static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
 	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
 #ifdef QOI_EXP_EARLYW
 	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+#endif
+#ifdef QOI_EXP_MID
+	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
 #endif
 	int nb = 0;
 	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qoienc::qoi_encode_kernel<CH, EXPAND, false>, QOI_ENC_THREADS, L::TOTAL));
@@ -196,7 +203,10 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 		if (rf && !strcmp(rf, "ahead")) c->read_ahead = true;
 		const char *ev = getenv("QOI_GPU_ENC");
 #ifdef QOI_EXP_EARLYW
-		if (ev && !strcmp(ev, "earlyw")) c->enc_earlyw = true;
+		if (ev && (!strcmp(ev, "earlyw") || !strcmp(ev, "earlyw-mid"))) c->enc_earlyw = true;
+#endif
+#ifdef QOI_EXP_MID
+		if (ev && (!strcmp(ev, "mid") || !strcmp(ev, "earlyw-mid"))) c->enc_mid = true;
 #endif
 		const char *dv = getenv("QOI_GPU_DEC");
 		if (dv && !strcmp(dv, "half")) c->dec_half = true;
@@ -318,6 +328,18 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	if (ctx->enc_striped) { /* experimental, QOI_GPU_ENC=<a name of g_enc4[]> */
 		const Enc4Mode &m = g_enc4[ctx->enc_striped - 1];
 		m.fn[variant]<<<grid, QOI_ENC_THREADS, (size_t)m.smem[variant], s>>>(P);
+#ifdef QOI_EXP_MID
+	} else if (ctx->enc_mid) { /* experimental build only, QOI_GPU_ENC=mid | earlyw-mid: the shipped encoder + mid-tile restart records */
+		if (ctx->enc_earlyw) {
+			if (variant == 0) qoienc::qoi_encode_kernel<4, false, true, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
+			else if (variant == 1) qoienc::qoi_encode_kernel<4, true, true, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
+			else qoienc::qoi_encode_kernel<3, true, true, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
+		} else {
+			if (variant == 0) qoienc::qoi_encode_kernel<4, false, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
+			else if (variant == 1) qoienc::qoi_encode_kernel<4, true, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
+			else qoienc::qoi_encode_kernel<3, true, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
+		}
+#endif
 #ifdef QOI_EXP_EARLYW
 	} else if (ctx->enc_earlyw) { /* experimental build only, QOI_GPU_ENC=earlyw */
 		if (variant == 0) qoienc::qoi_encode_kernel<4, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
@@ -337,6 +359,9 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	CK(ctx, cudaGetLastError());
 	p->index_owner = 1;
 	p->index_has_mid = ctx->enc_striped && g_enc4[ctx->enc_striped - 1].slab;
+#ifdef QOI_EXP_MID
+	if (ctx->enc_mid && !ctx->enc_striped) p->index_has_mid = true;
+#endif
 	return QOI_GPU_OK;
 }
 

@@ -56,7 +56,7 @@ def build_emulator():
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
     cmd = [gxx, "-std=c++17", "-O2", "-g", "-Wall", "-Wno-unknown-pragmas", "-Wno-comment", "-Wno-unused-variable", "-Wno-unused-function",
-           "-DQOI_EMU", "-DQOI_EXP_EARLYW", "-I" + os.path.join(EXP, "cuda"), "-I" + os.path.join(EXP, "tests", "emu"),
+           "-DQOI_EMU", "-DQOI_EXP_EARLYW", "-DQOI_EXP_MID", "-I" + os.path.join(EXP, "cuda"), "-I" + os.path.join(EXP, "tests", "emu"),
            os.path.join(EXP, "tests", "emu", "emu_main.cpp"), "-o", EMU,
            "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")]
     subprocess.check_call(cmd)
@@ -68,7 +68,7 @@ def build_library():
     from qoi_b200.build import NVCC_FLAGS, find_nvcc
 
     cmd = [find_nvcc()] + (["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []) + NVCC_FLAGS + \
-          ["-DQOI_EXP_EARLYW", "-I" + os.path.join(EXP, "include"), "-o", LIB, os.path.join(EXP, "cuda", "qoi_gpu.cu")]
+          ["-DQOI_EXP_EARLYW", "-DQOI_EXP_MID", "-I" + os.path.join(EXP, "include"), "-o", LIB, os.path.join(EXP, "cuda", "qoi_gpu.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -50,6 +50,10 @@ template <int CH, bool EXPAND>
 static void run_encode(const QoiEncParams &P, unsigned grid, unsigned seed) {
 	using L = qoienc::Layout<CH, EXPAND>;
 	const char *ev = getenv("QOI_EMU_ENC"); /* experimental striped encoder (cuda/qoi_enc4.cuh): striped | striped-match */
+#ifdef QOI_EXP_MID /* experimental build only (experiments/encoder_mid.patch, on top of earlyw) */
+	if (ev && !strcmp(ev, "mid")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc::qoi_encode_kernel<CH, EXPAND, true, false, true>(P); }, seed); return; }
+	if (ev && !strcmp(ev, "earlyw-mid")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc::qoi_encode_kernel<CH, EXPAND, true, true, true>(P); }, seed); return; }
+#endif
 #ifdef QOI_EXP_EARLYW /* experimental build only (experiments/encoder_earlyw.patch) */
 	if (ev && !strcmp(ev, "earlyw")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc::qoi_encode_kernel<CH, EXPAND, true, true>(P); }, seed); return; }
 #endif

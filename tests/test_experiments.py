@@ -16,18 +16,21 @@ def test_patch_series_applies_and_passes_the_emulator(cpu):
 
     build_exp.prepare()  # raises if a patch of experiments/series no longer applies
     emu = build_exp.build_emulator()
-    variants = {"encoder_earlyw.patch": "earlyw"}
+    variants = {"encoder_earlyw.patch": [{"QOI_EMU_ENC": "earlyw"}],
+                # the shipped encoder with mid-tile restart records, decoded with two lanes per tile
+                "encoder_mid.patch": [{"QOI_EMU_ENC": "mid", "QOI_EMU_DEC": "half"}, {"QOI_EMU_ENC": "earlyw-mid", "QOI_EMU_DEC": "half"}]}
     assert set(build_exp.series()) == set(variants), "a patch in experiments/series has no emulator check here"
     for name in build_exp.series():
-        for (w, h, ch, n, grid, seed, mis, dist) in [(160, 130, 4, 2, 3, 11, 0, 4), (131, 97, 3, 2, 2, 23, 3, 3), (400, 100, 4, 1, 4, 3, 0, 7)]:
-            img = cpu.batch(n, w, h, ch, dist)
-            with tempfile.NamedTemporaryFile(suffix=".raw") as f:
-                f.write(np.ascontiguousarray(img).tobytes())
-                f.flush()
-                r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
-                                   capture_output=True, text=True, timeout=300,
-                                   env=dict(os.environ, QOI_EMU_ENC=variants[name], QOI_EMU_SKIP_FOREIGN="1"))
-            assert r.returncode == 0 and r.stdout.startswith("PASS"), name + ": " + r.stdout + r.stderr[-2000:]
+        for extra in variants[name]:
+            for (w, h, ch, n, grid, seed, mis, dist) in [(160, 130, 4, 2, 3, 11, 0, 4), (131, 97, 3, 2, 2, 23, 3, 3), (400, 100, 4, 1, 4, 3, 0, 7),
+                                                         (2049, 1, 4, 3, 2, 5, 0, 4), (2047, 3, 4, 2, 3, 6, 5, 2)]:
+                img = cpu.batch(n, w, h, ch, dist)
+                with tempfile.NamedTemporaryFile(suffix=".raw") as f:
+                    f.write(np.ascontiguousarray(img).tobytes())
+                    f.flush()
+                    r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
+                                       capture_output=True, text=True, timeout=300, env=dict(os.environ, QOI_EMU_SKIP_FOREIGN="1", **extra))
+                assert r.returncode == 0 and r.stdout.startswith("PASS"), name + str(extra) + ": " + r.stdout + r.stderr[-2000:]
 
 
 def test_library_override_is_explicit():

@@ -13,6 +13,10 @@ EXP=$PWD/qoi_b200/libqoi_gpu_exp.so
 echo "=== stage 1: striped_smoke"
 timeout 120 bench/striped_smoke 32 | tee gpurun_out/striped_smoke.txt
 echo "SMOKE_RC=$?"
+if [ -f "$EXP" ]; then  # the patched shipped encoder (experiments/series), same tool with the experimental library in front
+  LD_PRELOAD=$EXP timeout 120 bench/striped_smoke 32 earlyw mid+half earlyw-mid+half | tee gpurun_out/striped_smoke_exp.txt
+  echo "SMOKE_EXP_RC=$?"
+fi
 run_variant() {  # name, env assignments...
   local name=$1; shift
   echo "=== $name"

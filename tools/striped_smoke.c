@@ -19,9 +19,16 @@ void qoi_synth_batch(uint8_t *dst, size_t stride, int n, uint32_t w, uint32_t h,
 
 int main(int argc, char **argv) {
 	const int n = argc > 1 ? atoi(argv[1]) : 8, W = 4096, H = 4096, CH = 4, runs = 5;
-	/* QOI_GPU_ENC value, optionally "+half": the same encoder with QOI_GPU_DEC=half (indexed decode with two lanes per tile) */
-	const char *variants[] = {"", "striped", "striped-earlyw", "striped-match", "slab", "slab-match", "slab-pipe", "slab-pipe-ballot", "slab4", "slab4-pipe",
-	                          "slab-match+half", "slab4-pipe+half"};
+	/* QOI_GPU_ENC value, optionally "+half": the same encoder with QOI_GPU_DEC=half (indexed decode with two lanes per tile).
+	   Names given on the command line replace the built-in list -- e.g. for the experimental library:
+	   LD_PRELOAD=qoi_b200/libqoi_gpu_exp.so bench/striped_smoke 32 earlyw mid+half earlyw-mid+half */
+	static const char *builtin[] = {"", "striped", "striped-earlyw", "striped-match", "slab", "slab-match", "slab-pipe", "slab-pipe-ballot", "slab4", "slab4-pipe",
+	                                "slab-match+half", "slab4-pipe+half"};
+	const char *variants[64];
+	int nvar = 0;
+	variants[nvar++] = "";
+	if (argc > 2) for (int i = 2; i < argc && nvar < 64; i++) variants[nvar++] = argv[i];
+	else for (size_t i = 1; i < sizeof builtin / sizeof builtin[0]; i++) variants[nvar++] = builtin[i];
 	const size_t img = (size_t)W * H * CH;
 	qoi_desc *descs = (qoi_desc *)calloc((size_t)n, sizeof(qoi_desc));
 	uint64_t *poff = (uint64_t *)calloc((size_t)n, 8), *soff = (uint64_t *)calloc((size_t)n, 8);
@@ -47,7 +54,7 @@ int main(int argc, char **argv) {
 	CK(cudaStreamCreate(&st));
 	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
 	int bad = 0;
-	for (int v = 0; v < (int)(sizeof variants / sizeof variants[0]); v++) {
+	for (int v = 0; v < nvar; v++) {
 		char encname[64];
 		snprintf(encname, sizeof encname, "%s", variants[v]);
 		char *plus = strchr(encname, 0x2B);
