@@ -20,7 +20,7 @@ fi
 run_variant() {  # name, env assignments...
   local name=$1; shift
   echo "=== $name"
-  env "$@" timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu --timeout=300 --timeout-method=thread \
+  env "$@" QOI_TEST_VARIANTS=1 timeout 900 python -m pytest tests/test_zz_variants.py tests/test_gpu_parity.py -x -q -m gpu --timeout=300 --timeout-method=thread \
       -k "not foreign and not photograph" > gpurun_out/ab_enc_pytest_$name.log 2>&1
   echo "PYTEST_${name}_RC=$?"; tail -2 gpurun_out/ab_enc_pytest_$name.log
   for d in 4 0 6 7; do
