@@ -17,10 +17,12 @@ if [ -f "$EXP" ]; then  # the patched shipped encoder (experiments/series), same
   LD_PRELOAD=$EXP timeout 120 bench/striped_smoke 32 earlyw mid+half earlyw-mid+half | tee gpurun_out/striped_smoke_exp.txt
   echo "SMOKE_EXP_RC=$?"
 fi
+echo "=== stage 1b: parity of every off-by-default variant (mixed batches, RGB/RGBA, misaligned, partial tiles), one process per case"
+QOI_TEST_VARIANTS=1 timeout 1200 python -m pytest tests/test_zz_variants.py -q -m gpu 2>&1 | tail -5
 run_variant() {  # name, env assignments...
   local name=$1; shift
   echo "=== $name"
-  env "$@" QOI_TEST_VARIANTS=1 timeout 900 python -m pytest tests/test_zz_variants.py tests/test_gpu_parity.py -x -q -m gpu --timeout=300 --timeout-method=thread \
+  env "$@" timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu --timeout=300 --timeout-method=thread \
       -k "not foreign and not photograph" > gpurun_out/ab_enc_pytest_$name.log 2>&1
   echo "PYTEST_${name}_RC=$?"; tail -2 gpurun_out/ab_enc_pytest_$name.log
   for d in 4 0 6 7; do
