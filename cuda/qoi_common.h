@@ -4,13 +4,12 @@
 #pragma once
 #include <stdint.h>
 
-#define QOI_TILE_PX 4096        /* pixels per encoder tile (== QOI_GPU_TILE_PX) */
-#define QOI_ENC_THREADS 320      /* 8 compute warps + scout warp + loader warp */
-#define QOI_ENC_COMPUTE 256
-#define QOI_ENC_WARPS 8         /* compute warps */
-#define QOI_PX_PER_THREAD 16    /* QOI_TILE_PX / QOI_ENC_COMPUTE */
-#define QOI_WARP_PX 512         /* pixels per warp chunk */
-#define QOI_WARP_STEPS 16       /* 32-pixel steps per warp chunk */
+#define QOI_TILE_PX 2048        /* pixels per encoder tile == pixels per decoder segment (== QOI_GPU_TILE_PX) */
+#define QOI_ENC_WARPS 4         /* compute warps per CTA */
+#define QOI_ENC_COMPUTE (QOI_ENC_WARPS * 32)
+#define QOI_ENC_THREADS (QOI_ENC_COMPUTE + 32) /* + one service warp: tickets, bulk loads, look-backs */
+#define QOI_WARP_PX (QOI_TILE_PX / QOI_ENC_WARPS) /* pixels per warp chunk */
+#define QOI_WARP_ROWS (QOI_WARP_PX / 32)          /* 32-pixel rows per warp chunk (lane = pixel) */
 #define QOI_HEADER_BYTES 14
 #define QOI_END_BYTES 8
 #define QOI_LNR_NONE INT32_MIN  /* "no non-run pixel in this tile" in an aggregate record */
@@ -31,39 +30,37 @@ struct QoiImgMeta {
  * wrote it, so a reader needs no fence and no ordering between words -- it just re-reads a word until
  * the epoch matches (relaxed gpu-scope loads/stores, L2 coherent).
  *
- *   table entry   [63:32] pixel value     [31:1] epoch  [0] slot written
- *   summary word  [63:32] payload         [31:0] epoch           (payload: valid-mask half / last non-run index)
+ *   table entry   [63:32] pixel value     [31:1] epoch  [0] 1
+ *   summary word  [63:32] payload         [31:0] epoch
  *   byte state    [63:34] epoch  [33:32] state  [31:0] bytes
+ *
+ * One table record per tile, ent[t][64].  A tile publishes the slots it wrote itself as soon as its own pixels are
+ * hashed (they are final: nothing before the tile can change them), and the slots it did not write once its look-back
+ * has found their value (0 for a slot no pixel of the image has touched yet: qoi.h:393 zero-fills index[]).  After the
+ * launch ent[t] is exactly what qoi.h's index[] holds behind the last pixel of tile t.
  */
 #define QOI_ST_NONE 0u
 #define QOI_ST_AGG 1u  /* the tile's own aggregate is published */
 #define QOI_ST_INC 2u  /* the inclusive prefix (everything up to and including this tile) is published */
 
-#define QOI_SUM_VALID_LO 0
-#define QOI_SUM_VALID_HI 1
-#define QOI_SUM_LNR 2
-#define QOI_SUM_WORDS 4 /* stride per tile (32 bytes) */
+#define QOI_SUM_OWN_LO 0   /* slots 0..31 written by the tile itself */
+#define QOI_SUM_OWN_HI 1   /* slots 32..63 */
+#define QOI_SUM_OWN_LNR 2  /* image index of the tile's last non-run pixel (QOI_LNR_NONE: it has none) */
+#define QOI_SUM_INC_LNR 3  /* published with the inclusive record: last non-run pixel up to the tile's end (-1: none yet) */
+#define QOI_SUM_WORDS 4    /* stride per tile (32 bytes) */
 
 /*
  * Per-tile chained-scan state; after an encode it doubles as the decoder's restart index:
- * the state a decoder needs at the start of tile t is inc_ent of tile t-1 plus rs_* of tile t.
+ * the state a decoder needs at the start of tile t is ent of tile t-1 plus rs_* of tile t.
  */
 struct QoiTileState {
 	uint32_t *ticket;      /* [2]: next tile to hand out, number of CTAs that finished */
-	uint64_t *agg_ent;     /* [tiles][64] last non-run pixel per hash slot INSIDE the tile */
-	uint64_t *agg_sum;     /* [tiles][4]  valid mask halves, last non-run pixel index (QOI_LNR_NONE: none) */
-	uint64_t *inc_ent;     /* [tiles][64] table after the tile == what qoi.h's index[] holds there */
-	uint64_t *inc_sum;     /* [tiles][4]  same, inclusive (last non-run index: -1 if none yet) */
+	uint64_t *ent;         /* [tiles][64] index[] behind the tile's last pixel (see above) */
+	uint64_t *sum;         /* [tiles][4]  summary words of the look-back */
 	uint64_t *byte_state;  /* [tiles] output-offset look-back */
 	int32_t *rs_px;        /* [tiles] first pixel of the tile at which an op starts (-1: none) */
 	int32_t *rs_byte;      /* [tiles] stream offset of that op */
 	uint32_t *rs_prev;     /* [tiles] value of the pixel before it */
-	/* a second restart point per tile, at its first op start at or after pixel QOI_TILE_PX / 2 -- written only by the
-	   slab-mode encoders of qoi_enc4.cuh (experimental); it lets the indexed decoder run two lanes per tile */
-	uint64_t *mid_ent;     /* [tiles][64] table before that op: [63:32] value, bit 0 slot written */
-	int32_t *mid_px;       /* [tiles] its pixel (-1: none) */
-	int32_t *mid_byte;     /* [tiles] stream offset of the op */
-	uint32_t *mid_prev;    /* [tiles] value of the pixel before it */
 };
 
 struct QoiEncParams {

@@ -12,7 +12,7 @@
  *       it is kept as the simplest exact form and is not launched by the C ABI.)
  *   stream written by qoi_encode_kernel (use_index = 1): one segment per
  *       encoder tile.  The chained scan already materialised the state at every
- *       tile boundary: index[] after tile t-1 is inc_ent[t-1], and rs_px /
+ *       tile boundary: index[] after tile t-1 is ent[t-1], and rs_px /
  *       rs_byte / rs_prev give the first op that starts inside tile t, where it
  *       lies in the stream and the pixel before it.  The index is a side table
  *       in HBM; the stream itself carries nothing extra and stays bit exact.
@@ -77,24 +77,21 @@ __device__ __forceinline__ void load_chunk(Reader &rd) {
 	rd.gp += 2;
 }
 
-/* HALF (experimental, off by default; needs an index written by a slab-mode encoder of qoi_enc4.cuh): two lanes per tile,
-   job = 2 * tile + half, the second one starting at the tile's mid restart point (QoiTileState::mid_*) */
-template <int OUT_CH, int BLOCK, bool UNI, bool PRE, bool HALF = false>
+template <int OUT_CH, int BLOCK, bool UNI, bool PRE>
 __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P) {
 	QOI_DYNAMIC_SMEM(smem);
 	uint32_t *tab = (uint32_t *)smem + threadIdx.x;  /* tab[slot * BLOCK] */
 	uint32_t *ring = tab + 64 * BLOCK;               /* ring[word * BLOCK] */
 	const uint32_t job_id = blockIdx.x * BLOCK + threadIdx.x;
 	if (job_id >= P.n_jobs) return;
-	const uint32_t job = HALF ? job_id >> 1 : job_id; /* the tile (indexed decode) or the image */
-	const bool second = HALF && (job_id & 1u);
+	const uint32_t job = job_id; /* the tile (indexed decode) or the image */
 
 	/* ---- which image, which pixels ---- */
 	const uint32_t img = P.use_index ? P.tile_img[job] : job;
 	const QoiImgMeta m = P.imgs[img];
 	const uint8_t *s = P.streams + m.stream_off;
 	const int32_t size = P.lens[img];
-	const bool first_seg = !P.use_index || (job == m.first_tile && !second);
+	const bool first_seg = !P.use_index || job == m.first_tile;
 
 	/* header against the plan (the host entry points reject bad headers before any launch, qoi.h:513-521) */
 	bool ok = size >= QOI_HEADER_BYTES + QOI_END_BYTES;
@@ -109,16 +106,13 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 	int32_t p0 = QOI_HEADER_BYTES;
 	uint32_t px = 0xFF000000u; /* {0,0,0,255}, qoi.h:534-537 */
 	if (P.use_index) {
-		const int32_t b = second ? P.st.mid_px[job] : P.st.rs_px[job];
-		if (b < 0) return; /* the image ends before an op starts in this tile (or in its second half) */
+		const int32_t b = P.st.rs_px[job];
+		if (b < 0) return; /* the image ends before an op starts in this tile */
 		px_begin = (uint32_t)b;
-		p0 = second ? P.st.mid_byte[job] : P.st.rs_byte[job];
-		px = second ? P.st.mid_prev[job] : P.st.rs_prev[job];
+		p0 = P.st.rs_byte[job];
+		px = P.st.rs_prev[job];
 		const uint32_t tiles = (m.npx + QOI_TILE_PX - 1) / QOI_TILE_PX;
-		const int32_t mid = (HALF && !second) ? P.st.mid_px[job] : -1;
-		if (mid >= 0) {
-			px_end = (uint32_t)mid; /* the other lane of this tile takes over there */
-		} else if (job + 1 < m.first_tile + tiles) {
+		if (job + 1 < m.first_tile + tiles) {
 			const int32_t e = P.st.rs_px[job + 1];
 			if (e >= 0) px_end = (uint32_t)e;
 		}
@@ -128,17 +122,14 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 #pragma unroll 8
 		for (int k = 0; k < 64; k++) tab[k * BLOCK] = 0;
 	} else {
-		const uint64_t *src = second ? P.st.mid_ent + (size_t)job * 64 : P.st.inc_ent + (size_t)(job - 1) * 64; /* [63:32] value, bit 0: slot written */
+		const uint64_t *src = P.st.ent + (size_t)(job - 1) * 64; /* [63:32] value; 0 in a slot nothing has been stored to yet */
 #pragma unroll 8
-		for (int k = 0; k < 64; k++) {
-			const uint64_t e = src[k];
-			tab[k * BLOCK] = (e & 1ull) ? (uint32_t)(e >> 32) : 0u;
-		}
+		for (int k = 0; k < 64; k++) tab[k * BLOCK] = (uint32_t)(src[k] >> 32);
 		/* the reference DEcoder also stores the current colour after a RUN op (qoi.h:577); the ENcoder's
 		   table does not see the leading run of the start colour.  Only slot 53 can differ, and only
 		   until a pixel hashing to 53 is coded. */
 		const uint32_t op0 = s[QOI_HEADER_BYTES];
-		if (!(src[53] & 1ull) && (op0 & 0xC0u) == 0xC0u && op0 < 0xFEu) tab[53 * BLOCK] = 0xFF000000u;
+		if ((uint32_t)(src[53] >> 32) == 0u && (op0 & 0xC0u) == 0xC0u && op0 < 0xFEu) tab[53 * BLOCK] = 0xFF000000u; /* no colour of slot 53 is 0 */
 	}
 
 	const int32_t stop = size - QOI_END_BYTES; /* qoi.h:539 */

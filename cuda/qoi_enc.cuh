@@ -1,55 +1,52 @@
 /*
- * qoi_enc.cuh -- single-pass chained-scan QOI encoder for sm_100a.
+ * qoi_enc.cuh -- single-pass chained-scan QOI encoder for sm_100a (round-2 rewrite).
  *
- * Replaces the sequential loop of the reference encoder (qoi.h:406-478) for a
- * whole batch of images in one launch.  The per-pixel state machine is carried
- * by px_prev, a run counter, index[64] and the output cursor p; here each of
- * these becomes a scan over 4096-pixel tiles (order-free form):
+ * Replaces the sequential loop of the reference encoder (qoi.h:406-478) for a whole batch of images in one launch.
+ * The reference carries px_prev, a run counter, index[64] and the output cursor p from pixel to pixel; in the
+ * order-free form each of them is a scan over 2048-pixel tiles:
  *
- *   run position      k(i) = i - (last non-run pixel before i)              max-scan
- *   INDEX hit         value of the previous NON-RUN pixel with the same
- *                     hash slot equals this pixel                           64-wide last-writer scan
- *   output offset     exclusive prefix sum of the bytes each pixel emits    +-scan
+ *   run position      k(i) = i - (last non-run pixel before i)                      max-scan
+ *   INDEX hit         the previous NON-RUN pixel with the same hash slot has the
+ *                     same value (no such pixel: only the all-zero pixel hits)     64-wide last-writer scan
+ *   output offset     exclusive prefix sum of the bytes each pixel emits            +-scan
  *
- * Persistent CTAs take tiles from an atomic ticket (so every predecessor of a
- * running tile is itself running or finished) and publish / look back through
- * per-tile records in HBM (decoupled look-back, fence-free: every 64-bit record
- * word carries its launch epoch).  Pixels are read ONCE: a 1-D TMA bulk copy
- * (cp.async.bulk, SASS UBLKCP) brings the next tile into shared memory while the
- * current one is processed; op bytes are assembled in a shared staging buffer
- * whose alignment is congruent to the destination and leave with one TMA bulk
- * store plus <16-byte edges.
+ * Persistent CTAs take tiles from an atomic ticket (every predecessor of a running tile is itself running or
+ * finished, so look-back cannot deadlock) and publish / look back through per-tile records in HBM (decoupled
+ * look-back, fence-free: every 64-bit record word carries its launch epoch).  Pixels are read ONCE: a 1-D TMA bulk
+ * copy (cp.async.bulk, SASS UBLKCP) brings a tile into shared memory.
  *
- * Inside a tile the "previous pixel with my hash slot" is found through a
- * slot x position BIT MATRIX in shared memory (64 rows of 4096 bits): every
- * non-run pixel sets its bit, then looks backwards along its row for the nearest
- * set bit.  The gaps along one row sum to at most the tile length, so a tile
- * costs O(pixels + 64 * words) word reads however the slots are distributed.
+ * What round 1 taught (profiles/r1_final, profiles/r2_ab): nine variants of a 4096-pixel, 10-warp CTA all took 7-8 ms
+ * for 32 x 4096^2 whatever their instruction count -- three or four CTAs per SM, each spending most of a tile waiting
+ * at hand-off barriers, leave the schedulers without ready warps.  This kernel is built the other way round:
  *
- * CTA = 8 compute warps (16 consecutive px per thread) + scout warp + loader warp.
+ *   - small CTAs (4 compute warps + 1 service warp, ~22 KB of shared memory, <= 40 registers): ~10 CTAs = 10 tiles
+ *     in flight per SM, so one CTA's look-back wait is another CTA's compute time;
+ *   - lane = pixel.  A warp owns 512 consecutive pixels and walks them as 16 rows of 32; every step of qoi.h's state
+ *     machine is a warp-wide operation (ballot = non-run mask, match.any = lanes with my hash slot, shuffle = the
+ *     same-slot predecessor inside the row, one shared-memory word per slot for the rows before);
+ *   - two light passes instead of defer-and-patch.  Pass A only finds the last writer of every slot in each warp's
+ *     chunk (no look-ups); the tile aggregate is published, the service warp looks back for the incoming table, and
+ *     pass B runs with an EXACT table from its first pixel: look-up, op selection, sizes (three ballots + popc, no
+ *     shuffle scan) and the op bytes straight into the warp's own slab of shared memory at a running offset;
+ *   - the slab leaves with a byte-shifted 16-byte copy as soon as the tile's output offset is known.
  *
- *   compute warps                              scout warp               loader warp
- *   -------------                              ----------               -----------
- *   wait tile bytes (mbarrier)                                          ticket, TMA for the NEXT tile
+ *   compute warps (4)                                     service warp
+ *   -----------------                                     ------------
+ *   wait tile (mbarrier: info record + pixels)            ticket for the NEXT tile (atomic + two dependent loads)
  *   E  (EXPAND) raw bytes -> RGBA words
- *   A  hash + non-run flag per pixel, set bits
- *      in the slot x position matrix
- *        ------- I_DONE ------->               T  tile aggregate (last
- *   C0 per pixel: nearest earlier bit in its      writer per slot) published;
- *      row -> INDEX hit or not; RUN / DIFF /      32-tile window look-back for
- *      LUMA / RGB / RGBA exactly like              the incoming table and the last
- *      qoi.h:415-474.  A slot's first pixel        non-run index; inclusive record
- *      in the tile is deferred (<= 64)             published
- *        <------ T_READY -------
- *   R  deferred pixels against T_in
- *   C1 patch pixels that became hits; threads
- *      inside a run carried into the tile redo
- *      their 16 pixels; block scan of sizes
- *        ------- C_DONE ------->               B  output-offset look-back
- *        <------ B_READY -------                  (32 tiles per probe)
- *   W  op bytes -> staging; restart entry
- *        ------- W_DONE ----------------------------------------------> staging -> global (TMA store
- *        <------ STAGE_FREE -------------------------------------------  + edges), header, end marker
+ *   A  per row: non-run mask, slot, last writer
+ *      of each slot -> the warp's table
+ *        ------- A_DONE ------->                          T  tile aggregate published; 32-tile window look-back for
+ *                                                            the incoming table and the last non-run index;
+ *        <------ T_READY -------                             inclusive record published
+ *   M  my chunk's incoming table = nearest earlier
+ *      warp that wrote the slot, else the tile's
+ *   B  per row: INDEX / RUN / DIFF / LUMA / RGB / RGBA
+ *      exactly like qoi.h:415-474, bytes -> slab
+ *        ------- B_DONE ------->                          bulk copy of the NEXT tile's pixels; output-offset
+ *        <------ B_READY -------                          look-back (32 tiles per probe); header / end marker / length
+ *   C  slab -> stream (shifted 16-byte copy),
+ *      restart record of the tile
  */
 #pragma once
 #include <limits.h>
@@ -63,129 +60,110 @@ using namespace qoidev;
 struct TileInfo {
 	int32_t tile; /* -1: no more work */
 	uint32_t img;
-	uint32_t t_in_img;
 	uint32_t n_valid;   /* pixels of this tile that exist */
 	uint32_t px0;       /* image pixel index of the tile's first pixel */
 	uint32_t npx;       /* pixels in the image */
 	uint32_t first_tile;
 	uint32_t sh;        /* (global source address) & 15, 0 on the zero-copy path */
+	uint32_t chan_cs;   /* channels | colorspace << 8 */
 	uint64_t stream_off;
 	uint32_t width, height;
-	uint32_t chan_cs;   /* channels | colorspace << 8 */
-	uint32_t pad[3];
+	uint32_t nbr_prev, nbr_next; /* the pixels either side of the tile (EXPAND; the zero-copy path puts them next to the pixels) */
+	uint32_t pad[2];
 };
+static_assert(sizeof(TileInfo) == 64, "TileInfo layout");
 
 enum {
-	BAR_COMPUTE = 1,    /* the 256 compute threads */
-	BAR_I_DONE = 2,     /* compute -> scout */
-	BAR_T_READY = 3,    /* scout -> compute */
-	BAR_C_DONE = 4,     /* compute -> scout */
-	BAR_B_READY = 5,    /* scout -> compute */
-	BAR_W_DONE = 6,     /* compute -> loader */
-	BAR_STAGE_FREE = 7, /* loader -> compute: the bulk store has drained the staging buffer (== bit matrix memory) */
-	BAR_E_DONE = 8,     /* compute -> loader (EXPAND): the raw buffer has been consumed */
-	BAR_INFO_READY = 9  /* loader -> compute + scout: the next tile's info record is in shared memory */
+	BAR_COMPUTE = 1, /* the compute threads among themselves */
+	BAR_A_DONE = 2,  /* compute -> service: per-warp tables of this tile are complete */
+	BAR_T_READY = 3, /* service -> compute: incoming table and run carry are in shared memory */
+	BAR_B_DONE = 4,  /* compute -> service: op bytes are in the slabs, the pixel buffer is free */
+	BAR_B_READY = 5  /* service -> compute: the tile's output offset is known */
 };
-#define QOI_N_CS (QOI_ENC_COMPUTE + 32)      /* compute + one helper warp */
-#define QOI_N_ALL QOI_ENC_THREADS
-
-#define QOI_CELL_ROW 520 /* bytes per slot row: 4096 bits + 8 bytes of padding (spreads rows over the banks) */
+#define QOI_N_CS QOI_ENC_THREADS /* compute warps + service warp */
 
 template <int CH, bool EXPAND>
 struct Layout {
-	static constexpr int NBUF = EXPAND ? 1 : 2; /* EXPAND frees the raw buffer right after phase E */
-	static constexpr int RAW_STRIDE = 16 + 16 + QOI_TILE_PX * CH + 16;
-	static constexpr int OFF_RAW = 0;
-	static constexpr int OFF_PXBUF = NBUF * RAW_STRIDE;
-	static constexpr int PXBUF_BYTES = EXPAND ? (16 + QOI_TILE_PX * 4 + 16) : 0;
-	static constexpr int OFF_CELLS = OFF_PXBUF + PXBUF_BYTES;         /* bit matrix; the staging buffer aliases it */
-	static constexpr int CELLS_BYTES = 64 * QOI_CELL_ROW;
-	static constexpr int STAGE_BYTES = 16 + QOI_TILE_PX * (CH + 1) + 16;
-	static constexpr int OFF_SUMMARY = OFF_CELLS + CELLS_BYTES;       /* u64 [64]: bit g of row h = word g of the row is non-zero */
-	static constexpr int OFF_TINVAL = OFF_SUMMARY + 64 * 8;           /* u32 [64] */
-	static constexpr int OFF_HITW = OFF_TINVAL + 64 * 4;              /* u32 [128] */
-	static constexpr int OFF_FPOS = OFF_HITW + 128 * 4;               /* u16 [64] */
-	static constexpr int OFF_TINFLAG = OFF_FPOS + 64 * 2;             /* u8 [64] */
-	static constexpr int OFF_MBAR = OFF_TINFLAG + 64;                 /* u64 [2] */
-	static constexpr int OFF_INFO = OFF_MBAR + 16;                    /* TileInfo [2] */
-	static constexpr int OFF_NBR = OFF_INFO + 2 * (int)sizeof(TileInfo); /* u32 [2][2] */
-	static constexpr int OFF_WTOT = OFF_NBR + 16;                     /* u32 [8] */
-	static constexpr int OFF_WLNR = OFF_WTOT + 32;                    /* i32 [8] */
-	static constexpr int OFF_WLNRIN = OFF_WLNR + 32;                  /* i32 [8] */
-	static constexpr int OFF_MISC = OFF_WLNRIN + 32;                  /* u32 [8] */
-	static constexpr int TOTAL = OFF_MISC + 32;
-	static_assert(STAGE_BYTES <= CELLS_BYTES, "staging must fit into the bit matrix it aliases");
-	static_assert(sizeof(TileInfo) % 16 == 0, "TileInfo must keep 16-byte alignment of what follows");
-	static_assert(OFF_CELLS % 16 == 0 && OFF_SUMMARY % 8 == 0 && OFF_TINVAL % 16 == 0 && OFF_MBAR % 8 == 0, "alignment");
+	/* RGBA words pix[-1 .. QOI_TILE_PX]; on the zero-copy path this is the bulk copy's destination */
+	static constexpr int OFF_PIX = 0;
+	static constexpr int PIX_BYTES = 16 + QOI_TILE_PX * 4 + 16;
+	/* EXPAND: raw[sh + k] = source byte k (sh = source address & 15), one spare word behind the end */
+	static constexpr int OFF_RAW = OFF_PIX + PIX_BYTES;
+	static constexpr int RAW_BYTES = EXPAND ? ((16 + QOI_TILE_PX * CH + 16 + 15) & ~15) : 0;
+	/* one slab of op bytes per compute warp: worst case of its chunk + room for the shifted copy's last word */
+	static constexpr int OFF_SLAB = OFF_RAW + RAW_BYTES;
+	static constexpr int SLAB_BYTES = QOI_WARP_PX * (CH + 1) + 32;
+	static constexpr int OFF_WTAB = OFF_SLAB + QOI_ENC_WARPS * SLAB_BYTES; /* uint2 [warps][64]: last non-run pixel per slot in the warp's chunk {value, written} */
+	static constexpr int OFF_TIN = OFF_WTAB + QOI_ENC_WARPS * 64 * 8;      /* u32 [warps][64]: the warp's running index[] in pass B */
+	static constexpr int OFF_TINS = OFF_TIN + QOI_ENC_WARPS * 64 * 4;      /* u32 [64]: index[] before the tile (service warp) */
+	static constexpr int OFF_MBAR = OFF_TINS + 64 * 4;                     /* u64 */
+	static constexpr int OFF_INFO = OFF_MBAR + 16;                         /* TileInfo [2] */
+	static constexpr int OFF_WTOT = OFF_INFO + 2 * (int)sizeof(TileInfo);  /* u32 [warps] bytes per slab */
+	static constexpr int OFF_WLNR = OFF_WTOT + QOI_ENC_WARPS * 4;          /* i32 [warps] last non-run pixel of the chunk (tile coordinates, -1: none) */
+	static constexpr int OFF_MISC = OFF_WLNR + QOI_ENC_WARPS * 4;          /* u32 [4] */
+	static constexpr int TOTAL = OFF_MISC + 16;
+	static_assert(SLAB_BYTES % 16 == 0 && OFF_SLAB % 16 == 0 && OFF_WTAB % 8 == 0 && OFF_MBAR % 8 == 0 && OFF_INFO % 16 == 0, "alignment");
 };
 
 /* misc[] slots */
-enum { MISC_TILE_BASE = 0, MISC_RS_CAND = 1, MISC_TILE_TOTAL = 2 };
+enum { MISC_TILE_BASE = 0, MISC_LNR_IN = 1 };
 
 __device__ __forceinline__ uint64_t pack_bytes(uint32_t epoch, uint32_t state, uint32_t v) {
 	return ((uint64_t)epoch << 34) | ((uint64_t)state << 32) | v;
 }
-__device__ __forceinline__ uint64_t pack_ent(uint32_t epoch, uint32_t value, bool written) {
-	return ((uint64_t)value << 32) | (uint64_t)((epoch << 1) | (written ? 1u : 0u));
-}
+__device__ __forceinline__ uint64_t pack_ent(uint32_t epoch, uint32_t value) { return ((uint64_t)value << 32) | (uint64_t)((epoch << 1) | 1u); }
 __device__ __forceinline__ uint64_t pack_sum(uint32_t epoch, uint32_t payload) { return ((uint64_t)payload << 32) | epoch; }
-__device__ __forceinline__ int hi_bit64(uint64_t w) { /* index of the highest set bit, w != 0 */
-	const uint32_t hi = (uint32_t)(w >> 32);
-	return hi ? 63 - __clz((int)hi) : 31 - __clz((int)(uint32_t)w);
-}
 
-/* ---------------------------------------------------------------- tile fetch (loader warp) */
+/* ---------------------------------------------------------------- tile fetch (service warp) */
 struct Fetch {
-	uint32_t tile;
+	uint32_t tile, img;
 	bool any;
-	QoiImgMeta m;
-	uint32_t img;
 };
 
-/* step 1: take a ticket and read the image record (touches no shared memory) */
+/* step 1: take a ticket; which tile, which image (touches no shared memory, so it can run a whole tile ahead) */
 __device__ __forceinline__ void fetch_ticket(const QoiEncParams &P, Fetch &F) {
 	const uint32_t lane = lane_id();
-	uint32_t tile = 0;
-	if (lane == 0) tile = atomicAdd(&P.st.ticket[0], 1u);
-	tile = __shfl_sync(QOI_FULL_MASK, tile, 0);
-	F.any = tile < P.n_tiles;
+	uint32_t tk = 0;
+	if (lane == 0) tk = atomicAdd(&P.st.ticket[0], 1u);
+	tk = __shfl_sync(QOI_FULL_MASK, tk, 0);
+	F.any = tk < P.n_tiles;
 	F.tile = 0;
+	F.img = 0;
 	if (F.any) {
-		F.tile = P.tile_order[tile]; /* ascending inside every image, images interleaved */
+		F.tile = P.tile_order[tk]; /* ascending inside every image, images interleaved */
 		F.img = P.tile_img[F.tile];
-		F.m = P.imgs[F.img];
 	}
 }
 
-/* step 2: start the bulk copy into raw buffer `rb`, fill fragments / neighbours, publish the info record `ib` */
+/* step 2: publish the info record `ib`, fill fragments / neighbours, start the bulk copy.  The mbarrier's phase
+   completes when the copy has landed; its arrive (release) also makes the info record visible to the waiters. */
 template <int CH, bool EXPAND>
-__device__ __forceinline__ void fetch_issue(const QoiEncParams &P, unsigned char *smem, const Fetch &F, int rb, int ib) {
+__device__ __forceinline__ void fetch_issue(const QoiEncParams &P, unsigned char *smem, const Fetch &F, int ib) {
 	using L = Layout<CH, EXPAND>;
 	const uint32_t lane = lane_id();
 	TileInfo *info = (TileInfo *)(smem + L::OFF_INFO) + ib;
-	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR) + rb;
+	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR);
 	if (!F.any) {
-		if (lane == 0) info->tile = -1;
+		if (lane == 0) {
+			info->tile = -1;
+			mbar_arrive_expect_tx(mbar, 0u);
+		}
 		return;
 	}
-	const QoiImgMeta &m = F.m;
+	const QoiImgMeta m = P.imgs[F.img];
 	const uint32_t t_in = F.tile - m.first_tile;
 	const uint32_t px0 = t_in * QOI_TILE_PX;
 	const uint32_t n_valid = (m.npx - px0) < (uint32_t)QOI_TILE_PX ? (m.npx - px0) : (uint32_t)QOI_TILE_PX;
 	const uint8_t *gsrc = P.pixels + m.pix_off + (uint64_t)px0 * CH;
 	const uint32_t nbytes = n_valid * CH;
 	const uint32_t sh = EXPAND ? (uint32_t)((uintptr_t)gsrc & 15u) : 0u;
-	unsigned char *data = smem + L::OFF_RAW + rb * L::RAW_STRIDE + 16; /* data[sh + k] = gsrc[k] */
+	unsigned char *data = EXPAND ? smem + L::OFF_RAW : smem + L::OFF_PIX + 16; /* data[sh + k] = gsrc[k] */
 	const uint32_t lo_off = (sh + 15u) & ~15u;
 	const uint32_t hi_off = (sh + nbytes) & ~15u;
 	const uint32_t tma_bytes = hi_off > lo_off ? hi_off - lo_off : 0u;
-	if (lane == 0) {
-		mbar_arrive_expect_tx(mbar, tma_bytes);
-		if (tma_bytes) tma_load_1d_hint(data + lo_off, gsrc + (lo_off - sh), tma_bytes, mbar, l2_evict_first_policy());
-	}
 	/* the <16-byte fragments on either side of the 16-byte aligned interior */
-	uint32_t a_lo = sh, a_hi = tma_bytes ? lo_off : sh + nbytes;
-	uint32_t b_lo = tma_bytes ? hi_off : 0u, b_hi = tma_bytes ? sh + nbytes : 0u;
+	const uint32_t a_lo = sh, a_hi = tma_bytes ? lo_off : sh + nbytes;
+	const uint32_t b_lo = tma_bytes ? hi_off : 0u, b_hi = tma_bytes ? sh + nbytes : 0u;
 	uint32_t o = a_lo + lane;
 	if (o < a_hi) data[o] = gsrc[o - sh];
 	o = b_lo + lane;
@@ -206,13 +184,12 @@ __device__ __forceinline__ void fetch_issue(const QoiEncParams &P, unsigned char
 		}
 	}
 	if (lane < 2) {
-		if (EXPAND) ((uint32_t *)(smem + L::OFF_NBR))[ib * 2 + lane] = nb;
+		if (EXPAND) (lane == 0 ? info->nbr_prev : info->nbr_next) = nb;
 		else ((uint32_t *)data)[lane == 0 ? -1 : QOI_TILE_PX] = nb;
 	}
 	if (lane == 0) {
 		info->tile = (int32_t)F.tile;
 		info->img = F.img;
-		info->t_in_img = t_in;
 		info->n_valid = n_valid;
 		info->px0 = px0;
 		info->npx = m.npx;
@@ -223,42 +200,47 @@ __device__ __forceinline__ void fetch_issue(const QoiEncParams &P, unsigned char
 		info->height = m.height;
 		info->chan_cs = (uint32_t)m.channels | ((uint32_t)m.colorspace << 8);
 	}
+	__syncwarp(); /* lanes 0/1 and the fragment lanes wrote shared memory that lane 0's arrive releases */
+	if (lane == 0) {
+		mbar_arrive_expect_tx(mbar, tma_bytes);
+		if (tma_bytes) tma_load_1d_hint(data + lo_off, gsrc + (lo_off - sh), tma_bytes, mbar, l2_evict_first_policy());
+	}
 }
 
-/* ---------------------------------------------------------------- op classification of one non-run, non-hit pixel */
-/* returns size | b0 << 8 | b1 << 16 ; reference qoi.h:438-474 */
-__device__ __forceinline__ uint32_t classify(uint32_t v, uint32_t p) {
-	const uint32_t d = __vsub4(v, p);                 /* per-channel difference mod 256 (qoi.h:439-441) */
-	const uint32_t t = __vadd4(d, 0x00020202u);       /* dr+2, dg+2, db+2, da */
-	if ((t & 0xFFFCFCFCu) == 0u) {                    /* alpha equal and all three in [-2,1] (qoi.h:446-451) */
-		return 1u | ((0x40u | ((t & 3u) << 4) | (((t >> 8) & 3u) << 2) | ((t >> 16) & 3u)) << 8);
-	}
+/* ---------------------------------------------------------------- op of one non-run pixel that is not an INDEX hit */
+/* qoi.h:438-474, branch free, on packed r | g<<8 | b<<16 | a<<24 words.  size 1 DIFF, 2 LUMA, 4 RGB, 5 RGBA;
+   b0 = first byte, b1 = second byte (LUMA's second byte, or r for RGB / RGBA whose g, b, a follow from v). */
+__device__ __forceinline__ void classify(uint32_t v, uint32_t p, uint32_t &size, uint32_t &b0, uint32_t &b1) {
+	/* per-channel difference mod 256 (qoi.h:439-441), no borrows between bytes */
+	const uint32_t d = ((v | 0x80808080u) - (p & 0x7F7F7F7Fu)) ^ ((v ^ ~p) & 0x80808080u);
+	const bool a_eq = d < 0x01000000u; /* alpha unchanged (qoi.h:438) */
+	/* DIFF (qoi.h:446-451): dr+2, dg+2, db+2 all in 0..3 */
+	const uint32_t t = ((d & 0x7F7F7F7Fu) + 0x00020202u) ^ (d & 0x80808080u);
+	const bool is_diff = (t & 0xFFFCFCFCu) == 0u;
+	const uint32_t diff_b = 0x40u | ((t << 4) & 0x30u) | ((t >> 6) & 0x0Cu) | ((t >> 16) & 0x03u);
+	/* LUMA (qoi.h:443-444, 453-459): vg in -32..31, vr-vg and vb-vg in -8..7, all as wrapped signed bytes */
 	const uint32_t dg = (d >> 8) & 0xFFu;
-	const uint32_t e = __vsub4(d, dg * 0x00010101u);  /* dr-dg, 0, db-dg, da-dg (qoi.h:443-444) */
-	const uint32_t t2 = __vadd4(e, 0x00080008u);      /* dr-dg+8, ., db-dg+8, . */
 	const uint32_t g32 = (dg + 32u) & 0xFFu;
-	if ((d >> 24) == 0u && (t2 & 0x00F000F0u) == 0u && (g32 & 0xC0u) == 0u) { /* qoi.h:453-459 */
-		return 2u | ((0x80u | g32) << 8) | ((((t2 & 0xFu) << 4) | ((t2 >> 16) & 0xFu)) << 16);
-	}
-	if ((d >> 24) == 0u) return 4u | (0xFEu << 8) | ((v & 0xFFu) << 16); /* qoi.h:461-465 */
-	return 5u | (0xFFu << 8) | ((v & 0xFFu) << 16);                       /* qoi.h:468-473 */
+	/* two 16-bit lanes: 0x108 + d_c - dg never borrows; the low byte of each lane is (d_c - dg + 8) mod 256 */
+	const uint32_t t2 = (((d & 0x00FF00FFu) | 0x01000100u) + 0x00080008u - dg * 0x00010001u) & 0x00FF00FFu;
+	const bool is_luma = a_eq && g32 < 64u && (t2 & 0x00F000F0u) == 0u;
+	const uint32_t luma_b1 = ((t2 & 0xFu) << 4) | (t2 >> 16);
+	size = is_diff ? 1u : (is_luma ? 2u : (a_eq ? 4u : 5u));
+	b0 = is_diff ? diff_b : (is_luma ? (0x80u | g32) : (a_eq ? 0xFEu : 0xFFu)); /* qoi.h:461-473 */
+	b1 = is_luma ? luma_b1 : (v & 0xFFu);
 }
 
-/* ---------------------------------------------------------------- scout: table / run look-back over a 32-tile window */
+/* ---------------------------------------------------------------- service warp: table / run look-back over a 32-tile window */
 struct LookBack {
-	uint32_t in_val[2];
-	bool in_ok[2];
-	int32_t lnr_in;
+	uint32_t val[2]; /* index[] before the tile, slots lane and lane + 32 */
+	int32_t lnr_in;  /* last non-run pixel before the tile (image coordinates), -1: none yet */
 };
 
 __device__ __forceinline__ void table_lookback(const QoiEncParams &P, uint32_t t, uint32_t first_tile, uint32_t epoch, LookBack &R) {
 	const uint32_t lane = lane_id();
-	uint32_t need_lo = 0xFFFFFFFFu, need_hi = 0xFFFFFFFFu; /* slots still unresolved (uniform) */
-	bool need_lnr = true;
-	uint32_t found_tile[2] = {0, 0};
-	bool found_inc[2] = {false, false};
-	R.in_ok[0] = R.in_ok[1] = false;
-	R.in_val[0] = R.in_val[1] = 0;
+	bool need0 = true, need1 = true; /* my two slots */
+	bool need_lnr = true;            /* uniform */
+	int64_t found0 = -1, found1 = -1; /* tile whose record holds the slot's value; -1: never written (value 0) */
 	R.lnr_in = -1;
 	int64_t base = (int64_t)t - 1;
 	while (true) {
@@ -268,270 +250,166 @@ __device__ __forceinline__ void table_lookback(const QoiEncParams &P, uint32_t t
 		if (tp < (int64_t)first_tile) {
 			state = QOI_ST_INC; /* before the image: nothing written, no non-run pixel yet */
 		} else { /* one look, no waiting: an unpublished tile only matters if nothing nearer resolves the slot */
-			const uint64_t *is = P.st.inc_sum + (size_t)tp * QOI_SUM_WORDS;
-			const uint64_t *as = P.st.agg_sum + (size_t)tp * QOI_SUM_WORDS;
-			uint64_t w0 = ld_relaxed_u64(is + 0), w1 = ld_relaxed_u64(is + 1), w2 = ld_relaxed_u64(is + 2);
-			if ((uint32_t)w0 == epoch && (uint32_t)w1 == epoch && (uint32_t)w2 == epoch) {
+			const uint64_t *sw = P.st.sum + (size_t)tp * QOI_SUM_WORDS;
+			const uint64_t w3 = ld_relaxed_u64(sw + QOI_SUM_INC_LNR);
+			if ((uint32_t)w3 == epoch) {
 				state = QOI_ST_INC;
+				lnr = (int32_t)(uint32_t)(w3 >> 32);
 			} else {
-				w0 = ld_relaxed_u64(as + 0); w1 = ld_relaxed_u64(as + 1); w2 = ld_relaxed_u64(as + 2);
-				if ((uint32_t)w0 == epoch && (uint32_t)w1 == epoch && (uint32_t)w2 == epoch) state = QOI_ST_AGG;
-			}
-			if (state != QOI_ST_NONE) {
-				vlo = (uint32_t)(w0 >> 32); vhi = (uint32_t)(w1 >> 32); lnr = (int32_t)(uint32_t)(w2 >> 32);
-			}
-		}
-		/* lanes [0, usable) hold published tiles; only they (up to the nearest inclusive record) may answer */
-		const uint32_t known = __ballot_sync(QOI_FULL_MASK, state != QOI_ST_NONE);
-		const uint32_t usable = (known == 0xFFFFFFFFu) ? 32u : (uint32_t)__ffs((int)~known) - 1u;
-		const uint32_t umask = (usable == 32u) ? 0xFFFFFFFFu : ((1u << usable) - 1u);
-		const uint32_t incm = __ballot_sync(QOI_FULL_MASK, state == QOI_ST_INC) & umask;
-		const uint32_t first_inc = incm ? (uint32_t)__ffs((int)incm) - 1u : 32u;
-		const bool part = lane < usable && lane <= first_inc;
-		if (!part) {
-			vlo = vhi = 0;
-			lnr = QOI_LNR_NONE;
-		}
-		if (need_lnr) {
-			const bool has = part && (state == QOI_ST_INC || lnr != QOI_LNR_NONE);
-			const uint32_t hb = __ballot_sync(QOI_FULL_MASK, has);
-			if (hb) {
-				R.lnr_in = __shfl_sync(QOI_FULL_MASK, lnr, __ffs((int)hb) - 1);
-				need_lnr = false;
-			}
-		}
-#pragma unroll
-		for (int half = 0; half < 2; half++) {
-			const uint32_t need = half ? need_hi : need_lo;
-			const uint32_t vm = half ? vhi : vlo;
-			const uint32_t any = __reduce_or_sync(QOI_FULL_MASK, vm) & need;
-			uint32_t todo = any;
-			while (todo) {
-				const uint32_t sb = (uint32_t)__ffs((int)todo) - 1u;
-				todo &= todo - 1u;
-				const uint32_t b = __ballot_sync(QOI_FULL_MASK, (vm >> sb) & 1u);
-				const uint32_t src = (uint32_t)__ffs((int)b) - 1u; /* nearest tile that wrote the slot */
-				if (lane == sb) {
-					found_tile[half] = (uint32_t)(base - src);
-					found_inc[half] = (src == first_inc);
-					R.in_ok[half] = true;
+				const uint64_t w0 = ld_relaxed_u64(sw + QOI_SUM_OWN_LO), w1 = ld_relaxed_u64(sw + QOI_SUM_OWN_HI), w2 = ld_relaxed_u64(sw + QOI_SUM_OWN_LNR);
+				if ((uint32_t)w0 == epoch && (uint32_t)w1 == epoch && (uint32_t)w2 == epoch) {
+					state = QOI_ST_AGG;
+					vlo = (uint32_t)(w0 >> 32);
+					vhi = (uint32_t)(w1 >> 32);
+					lnr = (int32_t)(uint32_t)(w2 >> 32);
 				}
 			}
-			if (half) need_hi &= ~any;
-			else need_lo &= ~any;
 		}
-		if (incm) break;                                  /* whatever is still unresolved was never written before this tile */
-		if (!need_lnr && !(need_lo | need_hi)) break;     /* everything answered by nearer tiles */
-		if (usable == 0u) spin_pause();                   /* the nearest undecided tile has not published yet */
+		/* lanes [0, usable) hold published tiles; they answer in order, up to the nearest inclusive record */
+		const uint32_t known = __ballot_sync(QOI_FULL_MASK, state != QOI_ST_NONE);
+		const uint32_t usable = (known == 0xFFFFFFFFu) ? 32u : (uint32_t)__ffs((int)~known) - 1u;
+		bool done = false;
+		for (uint32_t src = 0; src < usable; src++) { /* uniform */
+			const uint32_t st = __shfl_sync(QOI_FULL_MASK, state, (int)src);
+			const uint32_t mlo = __shfl_sync(QOI_FULL_MASK, vlo, (int)src);
+			const uint32_t mhi = __shfl_sync(QOI_FULL_MASK, vhi, (int)src);
+			const int32_t ll = __shfl_sync(QOI_FULL_MASK, lnr, (int)src);
+			const int64_t tile = base - (int64_t)src;
+			const bool inc = st == QOI_ST_INC;
+			const int64_t holder = tile >= (int64_t)first_tile ? tile : -1;
+			if (need0 && (inc || ((mlo >> lane) & 1u))) { need0 = false; found0 = holder; }
+			if (need1 && (inc || ((mhi >> lane) & 1u))) { need1 = false; found1 = holder; }
+			if (need_lnr && (inc || ll != QOI_LNR_NONE)) { need_lnr = false; R.lnr_in = ll; }
+			if (inc || (!need_lnr && !__ballot_sync(QOI_FULL_MASK, need0 || need1))) { /* an inclusive record answers everything */
+				done = true;
+				break;
+			}
+		}
+		if (done) break;
+		if (usable == 0u) spin_pause(); /* the nearest undecided tile has not published yet */
 		base -= usable;
 	}
-	/* the values themselves */
+	/* the values themselves (a slot a tile did not write itself appears with its inclusive record) */
+	R.val[0] = R.val[1] = 0u;
 #pragma unroll
 	for (int q = 0; q < 2; q++) {
-		if (R.in_ok[q]) {
-			const uint64_t *src = (found_inc[q] ? P.st.inc_ent : P.st.agg_ent) + (size_t)found_tile[q] * 64 + lane + 32u * q;
+		const int64_t f = q ? found1 : found0;
+		if (f >= 0) {
+			const uint64_t *src = P.st.ent + (size_t)f * 64 + lane + 32u * q;
 			uint64_t e;
 			while (true) {
 				e = ld_relaxed_u64(src);
 				if (((uint32_t)e >> 1) == epoch) break;
 				spin_pause();
 			}
-			R.in_val[q] = (uint32_t)(e >> 32);
+			R.val[q] = (uint32_t)(e >> 32);
 		}
 	}
 }
 
 /* ---------------------------------------------------------------- the kernel */
-/* WALK: look-ups walk back along the slot row word by word instead of using the second-level bits (A/B switch) */
-template <int CH, bool EXPAND, bool WALK>
-__global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const QoiEncParams P) {
+#ifndef QOI_ENC_MIN_BLOCKS
+#define QOI_ENC_MIN_BLOCKS 9 /* register budget: 40 (45 warps fit in 64 K registers) */
+#endif
+
+template <int CH, bool EXPAND>
+__global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encode_kernel(const QoiEncParams P) {
 	using L = Layout<CH, EXPAND>;
 	QOI_DYNAMIC_SMEM(smem);
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-	const bool scout = warp == QOI_ENC_WARPS;
-	const bool loader = warp == QOI_ENC_WARPS + 1;
+	const bool service = warp == QOI_ENC_WARPS;
 	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR);
 	TileInfo *infos = (TileInfo *)(smem + L::OFF_INFO);
-	unsigned char *cells = smem + L::OFF_CELLS;
-	uint64_t *summary = (uint64_t *)(smem + L::OFF_SUMMARY);
-	unsigned char *stage = cells; /* alias: the matrix is dead once phase R is over */
-	uint16_t *Fpos = (uint16_t *)(smem + L::OFF_FPOS);
-	uint32_t *Tin_val = (uint32_t *)(smem + L::OFF_TINVAL);
-	uint8_t *Tin_flag = (uint8_t *)(smem + L::OFF_TINFLAG);
-	uint32_t *hitw = (uint32_t *)(smem + L::OFF_HITW);
+	uint32_t *pix = (uint32_t *)(smem + L::OFF_PIX + 16); /* pix[-1 .. QOI_TILE_PX] */
+	uint2 *wtab_all = (uint2 *)(smem + L::OFF_WTAB);
+	uint32_t *Tins = (uint32_t *)(smem + L::OFF_TINS);
 	uint32_t *wtot = (uint32_t *)(smem + L::OFF_WTOT);
 	int32_t *wlnr = (int32_t *)(smem + L::OFF_WLNR);
-	int32_t *wlnr_in = (int32_t *)(smem + L::OFF_WLNRIN);
 	uint32_t *misc = (uint32_t *)(smem + L::OFF_MISC);
-
-	if (tid == 0) {
-		mbar_init(&mbar[0], 1);
-		mbar_init(&mbar[1], 1);
-		mbar_fence_init();
-		misc[MISC_RS_CAND] = (uint32_t)INT_MAX;
-	}
-	__syncthreads();
-	if (loader) {
-		Fetch F;
-		fetch_ticket(P, F);
-		fetch_issue<CH, EXPAND>(P, smem, F, 0, 0);
-		__syncwarp();
-		bar_arrive(BAR_INFO_READY, QOI_N_ALL);
-		bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
-	}
-
-	int cur = 0;
-	uint32_t parity0 = 0, parity1 = 0;
 	const uint32_t epoch = P.epoch;
 
-	while (true) {
-		if (!loader) bar_sync(BAR_INFO_READY, QOI_N_ALL); /* infos[cur] is published */
-		const TileInfo ti = infos[cur];
-		if (ti.tile < 0) break;
-		const uint32_t t = (uint32_t)ti.tile;
-		const int rb = EXPAND ? 0 : cur;
-		unsigned char *data = smem + L::OFF_RAW + rb * L::RAW_STRIDE + 16;
-		uint32_t *pxv = EXPAND ? (uint32_t *)(smem + L::OFF_PXBUF + 16) : (uint32_t *)data; /* pxv[-1 .. 4096] */
-		uint8_t *gstream = P.streams + ti.stream_off;
+	if (tid == 0) {
+		mbar_init(mbar, 1);
+		mbar_fence_init();
+	}
+	__syncthreads();
 
-		if (loader) {
-			/* =============================== loader warp =============================== */
-			Fetch F;
-			fetch_ticket(P, F);
-			if (EXPAND) bar_sync(BAR_E_DONE, QOI_N_CS); /* single raw buffer: wait until phase E has drained it */
-			fetch_issue<CH, EXPAND>(P, smem, F, EXPAND ? 0 : (cur ^ 1), cur ^ 1);
+	if (service) {
+		/* =============================== service warp =============================== */
+		Fetch F;
+		fetch_ticket(P, F);
+		fetch_issue<CH, EXPAND>(P, smem, F, 0);
+		int cur = 0;
+		while (F.any) {
+			const TileInfo *ti = infos + cur;
+			const uint32_t t = F.tile;
+			Fetch Fn;
+			fetch_ticket(P, Fn); /* a whole tile ahead: its three dependent round trips hide behind pass A */
+			const uint32_t first_tile = ti->first_tile, px0 = ti->px0;
 
-			bar_sync(BAR_W_DONE, QOI_N_CS); /* staging is complete */
-			/* Only now may INFO_READY be signalled again: a compute thread arrives at W_DONE, and the scout at the
-			   B_READY before it, only after passing this iteration's INFO_READY, so the barrier's previous phase is
-			   over.  (Signalling right after fetch_issue could overtake a warp that had not reached its
-			   bar.sync yet and complete that phase early.) */
-			__syncwarp();
-			bar_arrive(BAR_INFO_READY, QOI_N_ALL); /* consumed at the top of the next iteration */
-			{
-				const uint32_t excl = misc[MISC_TILE_BASE], total = misc[MISC_TILE_TOTAL];
-				uint8_t *gdst = gstream + excl;
-				const uint32_t padb = (uint32_t)((uintptr_t)gdst & 15u);
-				const uint32_t lo_off = (padb + 15u) & ~15u;
-				const uint32_t end = padb + total;
-				const uint32_t hi_off = end & ~15u;
-				const bool bulk = hi_off > lo_off;
-				if (lane == 0 && bulk) {
-					fence_proxy_async_smem();
-					tma_store_1d_hint(gdst + (lo_off - padb), stage + lo_off, hi_off - lo_off, l2_evict_first_policy());
-					tma_store_commit();
-				}
-				const uint32_t a_hi = bulk ? lo_off : end; /* [padb, a_hi) */
-				const uint32_t b_lo = bulk ? hi_off : end; /* [b_lo, end)  */
-				for (uint32_t o = padb + lane; o < a_hi; o += 32) gdst[o - padb] = stage[o];
-				for (uint32_t o = b_lo + lane; o < end; o += 32) gdst[o - padb] = stage[o];
-				if (t == ti.first_tile && lane < QOI_HEADER_BYTES) { /* header, qoi.h:384-388 */
-					const uint32_t k = lane;
-					uint8_t b;
-					if (k < 4) b = (uint8_t)("qoif"[k]);
-					else if (k < 8) b = (uint8_t)(ti.width >> (8 * (7 - k)));
-					else if (k < 12) b = (uint8_t)(ti.height >> (8 * (11 - k)));
-					else if (k == 12) b = (uint8_t)(ti.chan_cs & 0xFFu);
-					else b = (uint8_t)(ti.chan_cs >> 8);
-					gstream[k] = b;
-				}
-				if (ti.px0 + ti.n_valid == ti.npx && lane >= 16 && lane < 16 + QOI_END_BYTES + 1) { /* end marker, length: qoi.h:480-484 */
-					const uint32_t k = lane - 16;
-					const uint32_t fin = excl + total;
-					if (k < QOI_END_BYTES) gstream[fin + k] = (k == QOI_END_BYTES - 1) ? 1 : 0;
-					else P.lens[ti.img] = (int32_t)(fin + QOI_END_BYTES);
-				}
-				if (lane == 0) {
-					misc[MISC_RS_CAND] = (uint32_t)INT_MAX; /* for the next tile */
-					tma_store_wait_read();                  /* the bulk store has finished reading the staging buffer */
-				}
-			}
-			__syncwarp();
-			bar_arrive(BAR_STAGE_FREE, QOI_N_CS);
-		} else if (scout) {
-			/* =============================== scout warp =============================== */
-			bar_sync(BAR_I_DONE, QOI_N_CS); /* the bit matrix and wlnr[] of this tile are complete */
-			/* ---- phase T: tile aggregate = last set bit of each slot row (lane handles slots lane, lane+32) ---- */
+			bar_sync(BAR_A_DONE, QOI_N_CS); /* the per-warp tables and wlnr[] of this tile are complete */
+			/* ---- phase T: tile aggregate = the last warp that wrote each slot (lane handles slots lane, lane + 32) ---- */
 			uint32_t own_val[2];
 			bool own_ok[2];
 #pragma unroll
 			for (int q = 0; q < 2; q++) {
-				const uint32_t sl = lane + 32u * q;
-				const uint64_t *row = (const uint64_t *)(cells + sl * QOI_CELL_ROW);
 				own_ok[q] = false;
 				own_val[q] = 0;
-				if (WALK) {
-					for (int g = 63; g >= 0; g--) {
-						const uint64_t w = row[g];
-						if (w) {
-							own_val[q] = pxv[g * 64 + hi_bit64(w)];
-							own_ok[q] = true;
-							break;
-						}
-					}
-				} else {
-					const uint64_t sm = summary[sl];
-					if (sm) {
-						const int g = hi_bit64(sm);
-						own_val[q] = pxv[g * 64 + hi_bit64(row[g])];
+#pragma unroll
+				for (int w = 0; w < QOI_ENC_WARPS; w++) {
+					const uint2 e = wtab_all[w * 64 + lane + 32 * q];
+					if (e.y) {
+						own_val[q] = e.x;
 						own_ok[q] = true;
 					}
 				}
 			}
 			int32_t own_lnr = QOI_LNR_NONE;
-			for (int w = QOI_ENC_WARPS - 1; w >= 0; w--) {
-				if (wlnr[w] >= 0) {
-					own_lnr = (int32_t)ti.px0 + wlnr[w];
-					break;
-				}
-			}
-			const uint32_t own_lo = __ballot_sync(QOI_FULL_MASK, own_ok[0]);
-			const uint32_t own_hi = __ballot_sync(QOI_FULL_MASK, own_ok[1]);
+#pragma unroll
+			for (int w = 0; w < QOI_ENC_WARPS; w++)
+				if (wlnr[w] >= 0) own_lnr = (int32_t)px0 + wlnr[w];
 			LookBack lb;
-			lb.in_ok[0] = lb.in_ok[1] = false;
-			lb.in_val[0] = lb.in_val[1] = 0;
+			lb.val[0] = lb.val[1] = 0u;
 			lb.lnr_in = -1;
-			if (t != ti.first_tile) {
-				st_relaxed_u64(&P.st.agg_ent[(size_t)t * 64 + lane], pack_ent(epoch, own_val[0], own_ok[0]));
-				st_relaxed_u64(&P.st.agg_ent[(size_t)t * 64 + lane + 32], pack_ent(epoch, own_val[1], own_ok[1]));
+			if (t != first_tile) {
+				const uint32_t own_lo = __ballot_sync(QOI_FULL_MASK, own_ok[0]);
+				const uint32_t own_hi = __ballot_sync(QOI_FULL_MASK, own_ok[1]);
+				if (own_ok[0]) st_relaxed_u64(&P.st.ent[(size_t)t * 64 + lane], pack_ent(epoch, own_val[0]));
+				if (own_ok[1]) st_relaxed_u64(&P.st.ent[(size_t)t * 64 + lane + 32], pack_ent(epoch, own_val[1]));
 				if (lane < 3) {
 					const uint32_t payload = lane == 0 ? own_lo : (lane == 1 ? own_hi : (uint32_t)own_lnr);
-					st_relaxed_u64(&P.st.agg_sum[(size_t)t * QOI_SUM_WORDS + lane], pack_sum(epoch, payload));
+					st_relaxed_u64(&P.st.sum[(size_t)t * QOI_SUM_WORDS + lane], pack_sum(epoch, payload));
 				}
-				table_lookback(P, t, ti.first_tile, epoch, lb);
+				table_lookback(P, t, first_tile, epoch, lb);
 			}
-			Tin_val[lane] = lb.in_val[0];
-			Tin_val[lane + 32] = lb.in_val[1];
-			Tin_flag[lane] = lb.in_ok[0] ? 1 : 0;
-			Tin_flag[lane + 32] = lb.in_ok[1] ? 1 : 0;
-			/* inclusive record = what qoi.h's index[] / run bookkeeping hold after this tile */
-			const uint32_t inc_lo = __ballot_sync(QOI_FULL_MASK, own_ok[0] || lb.in_ok[0]);
-			const uint32_t inc_hi = __ballot_sync(QOI_FULL_MASK, own_ok[1] || lb.in_ok[1]);
-			st_relaxed_u64(&P.st.inc_ent[(size_t)t * 64 + lane], pack_ent(epoch, own_ok[0] ? own_val[0] : lb.in_val[0], own_ok[0] || lb.in_ok[0]));
-			st_relaxed_u64(&P.st.inc_ent[(size_t)t * 64 + lane + 32], pack_ent(epoch, own_ok[1] ? own_val[1] : lb.in_val[1], own_ok[1] || lb.in_ok[1]));
-			if (lane < 3) {
-				const int32_t inc_lnr = (own_lnr != QOI_LNR_NONE) ? own_lnr : lb.lnr_in;
-				const uint32_t payload = lane == 0 ? inc_lo : (lane == 1 ? inc_hi : (uint32_t)inc_lnr);
-				st_relaxed_u64(&P.st.inc_sum[(size_t)t * QOI_SUM_WORDS + lane], pack_sum(epoch, payload));
-			}
-			if (lane == 0) wlnr_in[0] = lb.lnr_in; /* last non-run pixel index before the tile (image coordinates) */
+			Tins[lane] = lb.val[0];
+			Tins[lane + 32] = lb.val[1];
+			if (lane == 0) misc[MISC_LNR_IN] = (uint32_t)lb.lnr_in;
 			__syncwarp();
 			bar_arrive(BAR_T_READY, QOI_N_CS);
+			/* inclusive record = what qoi.h's index[] / run bookkeeping hold after this tile */
+			if (t == first_tile || !own_ok[0]) st_relaxed_u64(&P.st.ent[(size_t)t * 64 + lane], pack_ent(epoch, own_ok[0] ? own_val[0] : lb.val[0]));
+			if (t == first_tile || !own_ok[1]) st_relaxed_u64(&P.st.ent[(size_t)t * 64 + lane + 32], pack_ent(epoch, own_ok[1] ? own_val[1] : lb.val[1]));
+			if (lane == 0) {
+				const int32_t inc_lnr = (own_lnr != QOI_LNR_NONE) ? own_lnr : lb.lnr_in;
+				st_relaxed_u64(&P.st.sum[(size_t)t * QOI_SUM_WORDS + QOI_SUM_INC_LNR], pack_sum(epoch, (uint32_t)inc_lnr));
+			}
 
-			bar_sync(BAR_C_DONE, QOI_N_CS); /* byte counts of the compute warps are in wtot[] */
+			bar_sync(BAR_B_DONE, QOI_N_CS); /* slab sizes are in wtot[]; nobody reads the pixel buffer any more */
+			fetch_issue<CH, EXPAND>(P, smem, Fn, cur ^ 1);
 			/* ---- phase B: output offset look-back, 32 predecessors per probe ---- */
 			uint32_t total = 0;
 #pragma unroll
 			for (int w = 0; w < QOI_ENC_WARPS; w++) total += wtot[w];
 			uint32_t excl = QOI_HEADER_BYTES;
-			if (t != ti.first_tile) {
+			if (t != first_tile) {
 				if (lane == 0) st_relaxed_u64(&P.st.byte_state[t], pack_bytes(epoch, QOI_ST_AGG, total));
 				uint32_t sum = 0;
 				int64_t base = (int64_t)t - 1;
 				while (true) {
 					const int64_t tp = base - lane;
 					uint32_t state = QOI_ST_AGG, val = 0;
-					if (tp >= (int64_t)ti.first_tile) {
+					if (tp >= (int64_t)first_tile) {
 						while (true) {
 							const uint64_t st = ld_relaxed_u64(&P.st.byte_state[tp]);
 							if ((uint32_t)(st >> 34) == epoch && ((st >> 32) & 3u) != QOI_ST_NONE) {
@@ -541,7 +419,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 							}
 							spin_pause();
 						}
-					}
+					} /* tiles before the image count as empty aggregates; the image's first tile always publishes an inclusive record */
 					const uint32_t incm = __ballot_sync(QOI_FULL_MASK, state == QOI_ST_INC);
 					if (incm) {
 						const uint32_t first = (uint32_t)__ffs((int)incm) - 1u;
@@ -556,295 +434,243 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, 3) qoi_encode_kernel(const Qo
 			if (lane == 0) {
 				st_relaxed_u64(&P.st.byte_state[t], pack_bytes(epoch, QOI_ST_INC, excl + total));
 				misc[MISC_TILE_BASE] = excl;
-				misc[MISC_TILE_TOTAL] = total;
 			}
 			__syncwarp();
 			bar_arrive(BAR_B_READY, QOI_N_CS);
-		} else {
-			/* =============================== compute warps =============================== */
-			if (rb == 0) { mbar_wait(&mbar[0], parity0); parity0 ^= 1u; }
-			else { mbar_wait(&mbar[1], parity1); parity1 ^= 1u; }
-
-			/* clear the bit matrix (it aliases the staging buffer of the previous tile) and the per-tile side tables */
-			bar_sync(BAR_STAGE_FREE, QOI_N_CS);
-			for (uint32_t k = tid; k < (uint32_t)(L::CELLS_BYTES / 16); k += QOI_ENC_COMPUTE) ((uint4 *)cells)[k] = make_uint4(0u, 0u, 0u, 0u);
-			if (tid < 128) hitw[tid] = 0u;
-			if (tid < 64) Fpos[tid] = 0xFFFFu;
-			if (EXPAND) {
-				/* ---- phase E: 16 pixels per thread, raw bytes at data[sh + CH*i] -> RGBA words ---- */
-				const uint32_t b0 = ti.sh + tid * (16u * CH);
-				const uint32_t *wsrc = (const uint32_t *)data + (b0 >> 2);
-				const uint32_t shf = (b0 & 3u) * 8u;
-				uint32_t out[16];
-				if (CH == 4) {
-					uint32_t w[17];
-#pragma unroll
-					for (int j = 0; j < 17; j++) w[j] = wsrc[j];
-#pragma unroll
-					for (int j = 0; j < 16; j++) out[j] = __funnelshift_r(w[j], w[j + 1], shf);
-				} else {
-					uint32_t w[13];
-#pragma unroll
-					for (int j = 0; j < 13; j++) w[j] = wsrc[j];
-					uint32_t s[12];
-#pragma unroll
-					for (int j = 0; j < 12; j++) s[j] = __funnelshift_r(w[j], w[j + 1], shf);
-#pragma unroll
-					for (int g = 0; g < 4; g++) {
-						const uint32_t s0 = s[3 * g], s1 = s[3 * g + 1], s2 = s[3 * g + 2];
-						out[4 * g + 0] = (s0 & 0x00FFFFFFu) | 0xFF000000u;
-						out[4 * g + 1] = (s0 >> 24) | ((s1 & 0x0000FFFFu) << 8) | 0xFF000000u;
-						out[4 * g + 2] = (s1 >> 16) | ((s2 & 0x000000FFu) << 16) | 0xFF000000u;
-						out[4 * g + 3] = (s2 >> 8) | 0xFF000000u;
-					}
-				}
-				uint4 *dst = (uint4 *)(pxv + tid * 16u);
-				dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
-				dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
-				dst[2] = make_uint4(out[8], out[9], out[10], out[11]);
-				dst[3] = make_uint4(out[12], out[13], out[14], out[15]);
-				if (tid == 0) {
-					const uint32_t *nbr = (const uint32_t *)(smem + L::OFF_NBR) + cur * 2;
-					pxv[-1] = nbr[0];
-					pxv[QOI_TILE_PX] = nbr[1];
-				}
-			}
-			bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
-			if (EXPAND) bar_arrive(BAR_E_DONE, QOI_N_CS); /* the raw buffer may be refilled */
-
-			/* ---- phase A: my 16 consecutive pixels: non-run flags, bits into the slot x position matrix ---- */
-			uint32_t v[16];
-			uint32_t code[16];
-			uint32_t ttotal = 0;
-			const uint32_t i0 = tid * 16u;
-			uint32_t pprev, pnext;
 			{
-				const uint4 *src = (const uint4 *)(pxv + i0);
-				const uint4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
-				v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
-				v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
-				v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w;
-				v[12] = q3.x; v[13] = q3.y; v[14] = q3.z; v[15] = q3.w;
-				pprev = pxv[(int)i0 - 1];
-				pnext = pxv[i0 + 16];
-			}
-			const bool full = ti.n_valid == (uint32_t)QOI_TILE_PX; /* uniform: only an image's last tile can be partial */
-			const bool last_tile = ti.px0 + ti.n_valid == ti.npx;
-			const bool track_cand = tid < 4;                        /* the restart point lies in the first 62 pixels */
-			uint32_t nrbits = 0;
-			{
-				uint32_t before = pprev;
-#pragma unroll
-				for (int j = 0; j < 16; j++) {
-					if ((full || i0 + j < ti.n_valid) && v[j] != before) {
-						uint16_t *cell = (uint16_t *)(cells + qoi_slot(v[j]) * QOI_CELL_ROW) + tid;
-						*cell = (uint16_t)(*cell | (1u << j));
-						nrbits |= 1u << j;
-					}
-					before = v[j];
+				uint8_t *gstream = P.streams + ti->stream_off;
+				if (t == first_tile && lane < QOI_HEADER_BYTES) { /* header, qoi.h:384-388 */
+					const uint32_t k = lane;
+					uint8_t b;
+					if (k < 4) b = (uint8_t)("qoif"[k]);
+					else if (k < 8) b = (uint8_t)(ti->width >> (8 * (7 - k)));
+					else if (k < 12) b = (uint8_t)(ti->height >> (8 * (11 - k)));
+					else if (k == 12) b = (uint8_t)(ti->chan_cs & 0xFFu);
+					else b = (uint8_t)(ti->chan_cs >> 8);
+					gstream[k] = b;
+				}
+				if (ti->px0 + ti->n_valid == ti->npx && lane >= 16 && lane < 16 + QOI_END_BYTES + 1) { /* end marker, length: qoi.h:480-484 */
+					const uint32_t k = lane - 16;
+					const uint32_t fin = excl + total;
+					if (k < QOI_END_BYTES) gstream[fin + k] = (k == QOI_END_BYTES - 1) ? 1 : 0;
+					else P.lens[ti->img] = (int32_t)(fin + QOI_END_BYTES);
 				}
 			}
-			/* last non-run pixel (tile coordinates) before my first pixel: warp max-scan + per-warp totals */
-			int32_t lnr_local;
-			{
-				const int32_t mine = nrbits ? (int32_t)(i0 + 31u - (uint32_t)__clz((int)nrbits)) : -1;
-				int32_t incl = mine;
-#pragma unroll
-				for (int dlt = 1; dlt < 32; dlt <<= 1) {
-					const int32_t o = __shfl_up_sync(QOI_FULL_MASK, incl, dlt);
-					if (lane >= (uint32_t)dlt && o > incl) incl = o;
-				}
-				lnr_local = __shfl_up_sync(QOI_FULL_MASK, incl, 1);
-				if (lane == 0) lnr_local = -1;
-				if (lane == 31) wlnr[warp] = incl;
-			}
-			bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE); /* matrix and wlnr[] complete */
-			/* second level: one bit per 64-pixel word of every row, so that a look-up never has to walk */
-#pragma unroll
-			for (int r = 0; r < (WALK ? 0 : 8); r++) {
-				const uint64_t *row = (const uint64_t *)(cells + (warp * 8u + r) * QOI_CELL_ROW);
-				const uint32_t b0 = __ballot_sync(QOI_FULL_MASK, row[lane] != 0ull);
-				const uint32_t b1 = __ballot_sync(QOI_FULL_MASK, row[lane + 32] != 0ull);
-				if (lane == 0) summary[warp * 8u + r] = (uint64_t)b0 | ((uint64_t)b1 << 32);
-			}
-			if (!WALK) bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
-			bar_arrive(BAR_I_DONE, QOI_N_CS);
-			if (lnr_local < 0) {
-				for (int w = (int)warp - 1; w >= 0; w--) {
-					if (wlnr[w] >= 0) {
-						lnr_local = wlnr[w];
-						break;
-					}
-				}
-			}
-			/* a thread that starts inside a run which began before this tile needs the carry from the look-back */
-			const bool defer = (full || i0 < ti.n_valid) && !(nrbits & 1u) && lnr_local < 0;
-			uint32_t hitbits = 0;
-			int32_t cand = INT_MAX;
-			const uint32_t grp = tid >> 2, bitbase = (tid & 3u) * 16u;
-
-			/* ---- phase C: classify pass; pass 0 with what the tile knows, pass 1 after the look-back ---- */
-#pragma unroll 1
-			for (int pass = 0; pass < 2; pass++) {
-				int32_t lnr_glob = (lnr_local >= 0) ? (int32_t)ti.px0 + lnr_local : (int32_t)(ti.px0 + i0) - 1;
-				if (pass == 1) {
-					bar_sync(BAR_T_READY, QOI_N_CS); /* T_in and the run carry are in shared memory */
-					/* ---- phase R: a slot's first pixel in the tile against the incoming table ---- */
-					if (tid < 64) {
-						const uint32_t pos = Fpos[tid];
-						if (pos != 0xFFFFu) {
-							const uint32_t pvv = pxv[pos];
-							/* an untouched index[] slot holds 0 (qoi.h:393): only the all-zero pixel can hit it */
-							const bool hit = Tin_flag[tid] ? (Tin_val[tid] == pvv) : (pvv == 0u);
-							if (hit) atomicOr(&hitw[pos >> 5], 1u << (pos & 31u));
-						}
-					}
-					bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
-					const uint32_t changed = (hitw[i0 >> 5] >> (i0 & 31u)) & 0xFFFFu; /* pixels that turned into hits */
-					hitbits |= changed;
-					if (!defer) {
-						/* patch the pixels that turned into INDEX ops (qoi.h:432-434) */
-#pragma unroll
-						for (int j = 0; j < 16; j++) {
-							if ((changed >> j) & 1u) {
-								ttotal -= (code[j] & 7u) - 1u;
-								code[j] = 1u | (qoi_slot(v[j]) << 8);
-							}
-						}
-						break;
-					}
-					lnr_glob = wlnr_in[0];
-				}
-				/* run pixels between the last non-run pixel and my first pixel */
-				const uint32_t c = (uint32_t)((int32_t)(ti.px0 + i0) - 1 - lnr_glob);
-				int32_t r = (c == 0u) ? -1 : (int32_t)((c - 1u) % 62u); /* (k-1) % 62 of the previous pixel */
-				uint32_t before = pprev;
-				ttotal = 0;
-				cand = INT_MAX;
-#pragma unroll
-				for (int j = 0; j < 16; j++) {
-					const uint32_t gi = ti.px0 + i0 + j;
-					uint32_t cd = 0;
-					if (full || i0 + j < ti.n_valid) {
-						if ((nrbits >> j) & 1u) {
-							r = -1;
-							if (track_cand && cand == INT_MAX) cand = (int32_t)(i0 + j);
-							const uint32_t h = qoi_slot(v[j]);
-							bool hit;
-							if (pass == 0) {
-								/* nearest earlier non-run pixel with my slot: my own 64-pixel word first, else the nearest
-								   earlier non-empty word of row h (second-level bits) */
-								const uint64_t *row = (const uint64_t *)(cells + h * QOI_CELL_ROW);
-								int g = (int)grp;
-								uint64_t w = row[g] & ((1ull << (bitbase + j)) - 1ull);
-								if (WALK) {
-									while (w == 0ull && g > 0) {
-										g--;
-										w = row[g];
-									}
-								} else if (w == 0ull) {
-									const uint64_t sm = summary[h] & ((1ull << grp) - 1ull);
-									if (sm) {
-										g = hi_bit64(sm);
-										w = row[g];
-									}
-								}
-								if (w) {
-									hit = pxv[g * 64 + hi_bit64(w)] == v[j];
-								} else {
-									Fpos[h] = (uint16_t)(i0 + j); /* first pixel of this slot in the tile: phase R decides */
-									hit = false;
-								}
-								hitbits |= (hit ? 1u : 0u) << j;
-							} else {
-								hit = (hitbits >> j) & 1u;
-							}
-							if (hit) cd = 1u | (h << 8); /* qoi.h:432-434 */
-							else cd = classify(v[j], before);
-						} else {
-							/* run pixel (qoi.h:415-421): a byte leaves at run length 62, at the image end, or when the run ends */
-							r = (r == 61) ? 0 : r + 1;
-							if (track_cand && r == 0 && cand == INT_MAX) cand = (int32_t)(i0 + j);
-							const uint32_t nx = (j == 15) ? pnext : v[j < 15 ? j + 1 : 15];
-							if (r == 61 || (last_tile && gi == ti.npx - 1u) || nx != v[j]) cd = 1u | ((0xC0u | (uint32_t)r) << 8);
-						}
-					}
-					code[j] = cd;
-					ttotal += cd & 7u;
-					before = v[j];
-				}
-			}
-			if (track_cand && cand != INT_MAX) atomicMin((int *)&misc[MISC_RS_CAND], cand);
-			/* block scan of the per-thread byte counts */
-			uint32_t incl = ttotal;
-#pragma unroll
-			for (int dlt = 1; dlt < 32; dlt <<= 1) {
-				const uint32_t o = __shfl_up_sync(QOI_FULL_MASK, incl, dlt);
-				if (lane >= (uint32_t)dlt) incl += o;
-			}
-			if (lane == 31) wtot[warp] = incl;
-			__syncwarp();
-			bar_arrive(BAR_C_DONE, QOI_N_CS);
-
-			bar_sync(BAR_B_READY, QOI_N_CS);
-			/* ---- phase W: op bytes -> staging (alignment congruent to the destination) ---- */
-			const uint32_t tile_base = misc[MISC_TILE_BASE];
-			const int32_t rs_cand = (int32_t)misc[MISC_RS_CAND];
-			const uint32_t padb = (uint32_t)((uintptr_t)(gstream + tile_base) & 15u);
-			{
-				uint32_t woff = incl - ttotal; /* exclusive inside the warp */
-				for (uint32_t w = 0; w < warp; w++) woff += wtot[w];
-				unsigned char *o = stage + padb + woff;
-				if (track_cand) { /* decoder restart point of this tile: the owner of pixel rs_cand records where its op starts */
-					const int32_t jr = rs_cand - (int32_t)i0;
-					if (jr >= 0 && jr < 16) {
-						uint32_t off = woff, before = pprev;
-#pragma unroll
-						for (int j = 0; j < 16; j++) {
-							if (j < jr) {
-								off += code[j] & 7u;
-								before = v[j];
-							}
-						}
-						P.st.rs_px[t] = (int32_t)(ti.px0 + (uint32_t)rs_cand);
-						P.st.rs_byte[t] = (int32_t)(tile_base + off);
-						P.st.rs_prev[t] = before;
-					}
-					if (tid == 0 && rs_cand == INT_MAX) P.st.rs_px[t] = -1;
-				}
-#pragma unroll
-				for (int j = 0; j < 16; j++) {
-					const uint32_t cd = code[j];
-					const uint32_t sz = cd & 7u;
-					if (sz) {
-						o[0] = (uint8_t)(cd >> 8);
-						if (sz >= 2) {
-							o[1] = (uint8_t)(cd >> 16);
-							if (sz >= 4) {
-								o[2] = (uint8_t)(v[j] >> 8);
-								o[3] = (uint8_t)(v[j] >> 16);
-								if (sz == 5) o[4] = (uint8_t)(v[j] >> 24);
-							}
-						}
-						o += sz;
-					}
-				}
-			}
-			__syncwarp();
-			bar_arrive(BAR_W_DONE, QOI_N_CS);
+			F = Fn;
+			cur ^= 1;
 		}
-		cur ^= 1;
+		/* the last CTA to finish rearms the ticket for the next launch */
+		if (lane == 0) {
+			const uint32_t done = atomicAdd(&P.st.ticket[1], 1u);
+			if (done == gridDim.x - 1u) {
+				P.st.ticket[0] = 0;
+				P.st.ticket[1] = 0;
+			}
+		}
+		return;
 	}
 
-	/* the last CTA to finish rearms the ticket for the next launch */
-	__syncthreads();
-	if (loader && lane == 0) { /* this thread issued the bulk stores */
-		tma_store_wait_all();
-		const uint32_t done = atomicAdd(&P.st.ticket[1], 1u);
-		if (done == gridDim.x - 1u) {
-			P.st.ticket[0] = 0;
-			P.st.ticket[1] = 0;
+	/* =============================== compute warps =============================== */
+	const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
+	const uint32_t wbase = warp * (uint32_t)QOI_WARP_PX;
+	uint2 *wtab = wtab_all + warp * 64;
+	uint32_t *tin = (uint32_t *)(smem + L::OFF_TIN) + warp * 64;
+	unsigned char *slab = smem + L::OFF_SLAB + warp * L::SLAB_BYTES;
+	int cur = 0;
+	uint32_t parity = 0;
+	while (true) {
+		mbar_wait(mbar, parity); /* info record and pixels of the tile have landed */
+		parity ^= 1u;
+		const TileInfo *ti = infos + cur;
+		if (ti->tile < 0) break;
+		const uint32_t t = (uint32_t)ti->tile;
+		const uint32_t nv = ti->n_valid, px0 = ti->px0, npx = ti->npx;
+
+		if (EXPAND) {
+			/* ---- phase E: raw bytes at raw[sh + CH * i] -> RGBA words (lane = pixel, two aligned words + funnel shift) ---- */
+			const uint32_t *raw32 = (const uint32_t *)(smem + L::OFF_RAW);
+			const uint32_t sh = ti->sh;
+			for (uint32_t i = tid; i < nv; i += QOI_ENC_COMPUTE) {
+				const uint32_t b = sh + i * CH;
+				const uint32_t x = __funnelshift_r(raw32[b >> 2], raw32[(b >> 2) + 1], (b & 3u) * 8u);
+				pix[i] = CH == 4 ? x : ((x & 0x00FFFFFFu) | 0xFF000000u);
+			}
+			if (tid == 0) {
+				pix[-1] = ti->nbr_prev;
+				pix[QOI_TILE_PX] = ti->nbr_next;
+			}
+			bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
 		}
+
+		/* ---- pass A: last non-run pixel of every hash slot in my chunk; rows only meet in the table ---- */
+		wtab[lane] = make_uint2(0u, 0u);
+		wtab[lane + 32] = make_uint2(0u, 0u);
+		__syncwarp();
+		{
+			int32_t last_nr = -1; /* tile-local index of the chunk's last non-run pixel so far (uniform) */
+#pragma unroll 4
+			for (int s = 0; s < QOI_WARP_ROWS; s++) {
+				const uint32_t rb0 = wbase + (uint32_t)s * 32u;
+				if (rb0 >= nv) break; /* uniform */
+				const uint32_t il = rb0 + lane;
+				const uint32_t v = pix[il], p = pix[(int)il - 1];
+				const bool nonrun = il < nv && v != p; /* qoi.h:415 */
+				const uint32_t nr = __ballot_sync(QOI_FULL_MASK, nonrun);
+				if (nr) { /* uniform: a row of run pixels touches nothing */
+					const uint32_t h = qoi_slot(v);
+					const uint32_t m = __match_any_sync(QOI_FULL_MASK, nonrun ? h : 64u + lane);
+					if (nonrun && (m & gt) == 0u) wtab[h] = make_uint2(v, 1u); /* the row's last pixel of its slot */
+					last_nr = (int32_t)(rb0 + 31u - (uint32_t)__clz((int)nr));
+					__syncwarp(); /* the next row's stores to the same slot come after these */
+				}
+			}
+			if (lane == 0) wlnr[warp] = last_nr;
+		}
+		__syncwarp();
+		bar_arrive(BAR_A_DONE, QOI_N_CS);
+
+		bar_sync(BAR_T_READY, QOI_N_CS); /* every warp's table is final; index[] before the tile and the run carry are in shared memory */
+		/* ---- phase M: index[] before my chunk = nearest earlier warp that wrote the slot, else the tile's incoming table ---- */
+#pragma unroll
+		for (int q = 0; q < 2; q++) {
+			const uint32_t sl = lane + 32u * q;
+			uint32_t val = Tins[sl];
+#pragma unroll
+			for (int w2 = 0; w2 < QOI_ENC_WARPS - 1; w2++) {
+				if ((uint32_t)w2 < warp) {
+					const uint2 e = wtab_all[w2 * 64 + sl];
+					if (e.y) val = e.x;
+				}
+			}
+			tin[sl] = val;
+		}
+		int32_t lnr = (int32_t)misc[MISC_LNR_IN]; /* last non-run pixel before the current row (image coordinates; -1: none since the image start) */
+#pragma unroll
+		for (int w2 = 0; w2 < QOI_ENC_WARPS - 1; w2++)
+			if ((uint32_t)w2 < warp && wlnr[w2] >= 0) lnr = (int32_t)px0 + wlnr[w2];
+		__syncwarp();
+
+		/* ---- pass B: ops and bytes, row by row; the table is exact from the first pixel on ---- */
+		uint32_t off = 0;               /* bytes in my slab so far (uniform) */
+		int32_t rs_cand = INT_MAX;      /* warp 0: the tile's first pixel at which an op starts = decoder restart point */
+		uint32_t rs_off = 0xFFFFFFFFu;  /* its byte offset in the slab, in the lane that owns the pixel */
+		uint32_t rs_prev = 0;
+		const bool last_tile = px0 + nv == npx;
+#pragma unroll 2
+		for (int s = 0; s < QOI_WARP_ROWS; s++) {
+			const uint32_t rb0 = wbase + (uint32_t)s * 32u;
+			if (rb0 >= nv) break; /* uniform */
+			const uint32_t il = rb0 + lane;
+			const uint32_t v = pix[il], p = pix[(int)il - 1], nx = pix[il + 1];
+			const bool valid = il < nv;
+			const bool nonrun = valid && v != p; /* qoi.h:415 */
+			const uint32_t nr = __ballot_sync(QOI_FULL_MASK, nonrun);
+			const uint32_t vmask = (nv - rb0 >= 32u) ? 0xFFFFFFFFu : ((1u << (nv - rb0)) - 1u);
+			uint32_t size = 0, b0 = 0, b1 = 0;
+			bool opstart = nonrun;
+			if (nr) { /* uniform */
+				const uint32_t h = qoi_slot(v);
+				const uint32_t m = __match_any_sync(QOI_FULL_MASK, nonrun ? h : 64u + lane);
+				const uint32_t lower = m & lt;
+				const uint32_t tv = tin[h];                                              /* index[] as the rows before left it */
+				const uint32_t pv = __shfl_sync(QOI_FULL_MASK, v, 31 - __clz((int)lower)); /* nearest same-slot pixel of this row (garbage if none) */
+				const bool hit = (lower ? pv : tv) == v;                                 /* qoi.h:432 */
+				__syncwarp();
+				if (nonrun && (m & gt) == 0u) tin[h] = v;                                /* qoi.h:436 (a hit stores the value that is there already) */
+				uint32_t cs, c0, c1;
+				classify(v, p, cs, c0, c1);
+				if (nonrun) {
+					size = hit ? 1u : cs;
+					b0 = hit ? h : c0; /* QOI_OP_INDEX | slot, qoi.h:433 */
+					b1 = c1;
+				}
+			}
+			if (nr != vmask) { /* uniform: the row has run pixels (qoi.h:415-421) */
+				const uint32_t below = nr & lt;
+				const int32_t lnr_i = below ? (int32_t)(px0 + rb0 + 31u - (uint32_t)__clz((int)below)) : lnr;
+				const uint32_t gi = px0 + il;
+				const uint32_t r = (gi - (uint32_t)lnr_i - 1u) % 62u; /* (position in the run - 1) % 62 */
+				if (valid && !nonrun) {
+					/* a byte leaves at run length 62, at the image end, or when the run ends */
+					size = (r == 61u || nx != v || (last_tile && gi == npx - 1u)) ? 1u : 0u;
+					b0 = 0xC0u | r;
+					opstart = r == 0u;
+				}
+			}
+			/* byte offsets inside the row: sizes are 0, 1, 2, 4 or 5 -> three bit planes */
+			const uint32_t s1 = __ballot_sync(QOI_FULL_MASK, size & 1u), s2 = __ballot_sync(QOI_FULL_MASK, size & 2u),
+			               s4 = __ballot_sync(QOI_FULL_MASK, size & 4u);
+			const uint32_t ex = (uint32_t)__popc(s1 & lt) + 2u * (uint32_t)__popc(s2 & lt) + 4u * (uint32_t)__popc(s4 & lt);
+			if (warp == 0 && s < 2 && rs_cand == INT_MAX) { /* a RUN op covers <= 62 pixels: the restart point lies in the first two rows */
+				const uint32_t starts = __ballot_sync(QOI_FULL_MASK, valid && opstart);
+				if (starts) {
+					const uint32_t first = (uint32_t)__ffs((int)starts) - 1u;
+					rs_cand = (int32_t)(rb0 + first);
+					if (lane == first) {
+						rs_off = off + ex;
+						rs_prev = p;
+					}
+				}
+			}
+			unsigned char *o = slab + off + ex;
+			if (size) {
+				o[0] = (uint8_t)b0;
+				if (size >= 2u) {
+					o[1] = (uint8_t)b1;
+					if (size >= 4u) {
+						o[2] = (uint8_t)(v >> 8);
+						o[3] = (uint8_t)(v >> 16);
+						if (size == 5u) o[4] = (uint8_t)(v >> 24);
+					}
+				}
+			}
+			off += (uint32_t)__popc(s1) + 2u * (uint32_t)__popc(s2) + 4u * (uint32_t)__popc(s4);
+			if (nr) lnr = (int32_t)(px0 + rb0 + 31u - (uint32_t)__clz((int)nr));
+			__syncwarp();
+		}
+		if (lane == 0) wtot[warp] = off;
+		uint8_t *gstream = P.streams + ti->stream_off;
+		__syncwarp();
+		bar_arrive(BAR_B_DONE, QOI_N_CS);
+
+		bar_sync(BAR_B_READY, QOI_N_CS);
+		/* ---- phase C: my slab -> tile base + bytes of the warps before me (byte-shifted 16-byte copy) ---- */
+		{
+			uint32_t woff = misc[MISC_TILE_BASE];
+#pragma unroll
+			for (int w2 = 0; w2 < QOI_ENC_WARPS - 1; w2++)
+				if ((uint32_t)w2 < warp) woff += wtot[w2];
+			if (warp == 0) { /* restart record: the lane that owns the restart pixel knows where its op starts */
+				if (rs_off != 0xFFFFFFFFu) {
+					P.st.rs_px[t] = (int32_t)px0 + rs_cand;
+					P.st.rs_byte[t] = (int32_t)(woff + rs_off);
+					P.st.rs_prev[t] = rs_prev;
+				}
+				if (lane == 0 && rs_cand == INT_MAX) P.st.rs_px[t] = -1;
+			}
+			uint8_t *gdst = gstream + woff;
+			const uint32_t total = off;
+			uint32_t head = (16u - (uint32_t)((uintptr_t)gdst & 15u)) & 15u; /* bytes up to the first aligned 16 */
+			if (head > total) head = total;
+			const uint32_t nvec = (total - head) >> 4;
+			if (lane < head) gdst[lane] = slab[lane];
+			const uint32_t *s32 = (const uint32_t *)slab + (head >> 2);
+			const uint32_t shf = (head & 3u) * 8u;
+			for (uint32_t k = lane; k < nvec; k += 32u) {
+				const uint32_t *w = s32 + 4u * k;
+				const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+				uint4 q;
+				q.x = __funnelshift_r(w0, w1, shf);
+				q.y = __funnelshift_r(w1, w2, shf);
+				q.z = __funnelshift_r(w2, w3, shf);
+				q.w = __funnelshift_r(w3, w4, shf);
+				st_stream_u4((uint4 *)(gdst + head + 16u * k), q);
+			}
+			const uint32_t tail0 = head + 16u * nvec;
+			if (tail0 + lane < total) gdst[tail0 + lane] = slab[tail0 + lane]; /* fewer than 16 bytes */
+		}
+		__syncwarp();
+		cur ^= 1;
 	}
 }
 

@@ -21,7 +21,6 @@
 #include "../include/qoi_gpu.h"
 #include "qoi_dec.cuh"
 #include "qoi_enc.cuh"
-#include "qoi_enc4.cuh"
 #include "qoi_fdec.cuh"
 #include "qoi_plan.h"
 
@@ -36,21 +35,7 @@ struct qoi_gpu_ctx {
 	cudaStream_t stream = nullptr;                 /* kernels of the host-buffer entry points */
 	cudaStream_t s_h2d = nullptr, s_d2h = nullptr; /* one stream per copy direction: PCIe is full duplex */
 	char err[256] = {0};
-	int enc_blocks_per_sm[3] = {0, 0, 0}; /* <4,false>, <4,true>, <3,true> */
-#ifdef QOI_EXP_EARLYW
-	bool enc_earlyw = false;              /* experimental build only (experiments/encoder_earlyw.patch): QOI_GPU_ENC=earlyw | earlyw-mid */
-#endif
-#ifdef QOI_EXP_MID
-	bool enc_mid = false;                 /* experimental build only (experiments/encoder_mid.patch): QOI_GPU_ENC=mid | earlyw-mid */
-#endif
-	bool dec_half = false;                /* experimental: indexed decode with two lanes per tile (QOI_GPU_DEC=half); only used when the
-	                                         index was written by a slab-mode encoder */
-	int enc_striped = 0;                  /* experimental encoder of qoi_enc4.cuh: 1 + index into g_enc4[] (QOI_GPU_ENC=striped | slab | ...);
-	                                         emulator-tested, off by default */
-	bool read_ahead = false;              /* experimental: ring word read one call ahead (QOI_GPU_REFILL=ahead); indexed decoder only */
-	bool refill_uni = true;               /* decoders' stream reader: warp-uniform refill (default) or lane-driven (QOI_GPU_REFILL=lane) */
-	bool walk = true;                     /* look-up variant: word walk (default; 8% faster on photo content) or second-level
-	                                         bits (QOI_GPU_LOOKUP=summary; 20% faster on run-dominated content) */
+	int enc_blocks_per_sm[3] = {0, 0, 0}; /* resident CTAs per SM of qoi_encode_kernel<4,false>, <4,true>, <3,true> */
 };
 
 struct qoi_gpu_plan {
@@ -73,7 +58,6 @@ struct qoi_gpu_plan {
 	std::vector<qoi_gpu_plan *> chunks;
 	std::vector<int> chunk_first;
 	std::vector<cudaEvent_t> ev_in, ev_k;
-	bool index_has_mid = false; /* the last encode on this plan also wrote the mid-tile restart records */
 	int index_owner = 0; /* who holds the restart index of the last encode: 0 nobody, 1 this plan, 2 the chunks */
 	/* scratch of the foreign-stream decoder (qoi_fdec.cuh), allocated on first use */
 	unsigned char *d_fstate = nullptr;
@@ -94,78 +78,25 @@ static_assert(QOI_FFIX_SMEM <= 48 * 1024 && QOI_FCHAIN_SMEM <= 48 * 1024 && QOI_
 static int fdec_setup(qoi_gpu_ctx *ctx) {
 	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
 	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
-	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
-	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
 	return QOI_GPU_OK;
 }
 
 template <int CH, bool EXPAND>
 static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
 	using L = qoienc::Layout<CH, EXPAND>;
-	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-#ifdef QOI_EXP_EARLYW
-	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-#endif
-#ifdef QOI_EXP_MID
-	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-#endif
+	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+	/* many small CTAs per SM: ask for the largest shared-memory carve-out */
+	CK(ctx, cudaFuncSetAttribute(qoienc::qoi_encode_kernel<CH, EXPAND>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	int nb = 0;
-	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qoienc::qoi_encode_kernel<CH, EXPAND, false>, QOI_ENC_THREADS, L::TOTAL));
-	*out = nb > 0 ? nb : 1;
-	return QOI_GPU_OK;
-}
-
-/* experimental encoders of qoi_enc4.cuh, one row per QOI_GPU_ENC value; fn[variant]: 0 = <4, zero-copy>, 1 = <4, EXPAND>, 2 = <3, EXPAND> */
-typedef void (*Enc4Kernel)(const QoiEncParams);
-struct Enc4Mode {
-	const char *name;
-	bool slab; /* writes the mid-tile restart records (QoiTileState::mid_*) */
-	Enc4Kernel fn[3];
-	int smem[3];
-};
-#define ENC4_ROW(name, MATCH, EARLYW, SLAB, PIPE, COMPACT)                                                                \
-	{name, SLAB,                                                                                                          \
-	 {qoienc4::qoi_encode_striped_kernel<4, false, MATCH, EARLYW, SLAB, PIPE, COMPACT>,                                     \
-	  qoienc4::qoi_encode_striped_kernel<4, true, MATCH, EARLYW, SLAB, PIPE, COMPACT>,                                      \
-	  qoienc4::qoi_encode_striped_kernel<3, true, MATCH, EARLYW, SLAB, PIPE, COMPACT>},                                     \
-	 {qoienc4::PickLayout<4, false, COMPACT>::type::TOTAL, qoienc4::PickLayout<4, true, COMPACT>::type::TOTAL,              \
-	  qoienc4::PickLayout<3, true, COMPACT>::type::TOTAL}}
-static const Enc4Mode g_enc4[] = {
-    ENC4_ROW("striped", false, false, false, false, false),        /* lane-per-pixel rows, six-ballot slot matching */
-    ENC4_ROW("striped-match", true, false, false, false, false),   /* ... match.any */
-    ENC4_ROW("striped-earlyw", false, true, false, false, false),  /* ... phase W before the output offset is known */
-    ENC4_ROW("slab", false, false, true, false, false),            /* rolled loops, op bytes into per-warp slabs */
-    ENC4_ROW("slab-match", true, false, true, false, false),
-    ENC4_ROW("slab-pipe", true, false, true, true, false),         /* ... copy-out behind the next tile's index pass */
-    ENC4_ROW("slab-pipe-ballot", false, false, true, true, false),
-    ENC4_ROW("slab4", true, false, true, false, true),             /* ... compact layout: one pixel buffer, 4 CTAs per SM */
-    ENC4_ROW("slab4-pipe", true, false, true, true, true),
-};
-#undef ENC4_ROW
-
-static int enc_striped_setup(qoi_gpu_ctx *ctx) {
-	const Enc4Mode &m = g_enc4[ctx->enc_striped - 1];
-	for (int v = 0; v < 3; v++) {
-		CK(ctx, cudaFuncSetAttribute((const void *)m.fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, m.smem[v]));
-		int nb = 0;
-		CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)m.fn[v], QOI_ENC_THREADS, (size_t)m.smem[v]));
-		ctx->enc_blocks_per_sm[v] = nb > 0 ? nb : 1; /* the grid must not exceed what is co-resident (look-back) */
-	}
+	CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qoienc::qoi_encode_kernel<CH, EXPAND>, QOI_ENC_THREADS, L::TOTAL));
+	*out = nb > 0 ? nb : 1; /* the grid must not exceed what is co-resident (look-back) */
 	return QOI_GPU_OK;
 }
 
 template <int OUT_CH, int BLOCK>
-static void launch_decode(const QoiDecParams &D, cudaStream_t s, int uni) { /* 0 lane-driven refill, 1 warp-uniform, 2 + word read ahead, 3 two lanes per tile */
+static void launch_decode(const QoiDecParams &D, cudaStream_t s) {
 	const uint32_t grid = (D.n_jobs + BLOCK - 1) / BLOCK;
-	if (uni == 3) {
-		qoidec::qoi_decode_kernel<OUT_CH, BLOCK, true, false, true><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
-		return;
-	}
-	if (uni == 2) qoidec::qoi_decode_kernel<OUT_CH, BLOCK, true, true><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
-	else if (uni) qoidec::qoi_decode_kernel<OUT_CH, BLOCK, true, false><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
-	else qoidec::qoi_decode_kernel<OUT_CH, BLOCK, false, false><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
+	qoidec::qoi_decode_kernel<OUT_CH, BLOCK, true, false><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
 }
 
 extern "C" {
@@ -195,33 +126,13 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 		delete c;
 		return QOI_GPU_E_CUDA;
 	}
-	{
-		const char *w = getenv("QOI_GPU_LOOKUP");
-		if (w && !strcmp(w, "summary")) c->walk = false;
-		const char *rf = getenv("QOI_GPU_REFILL");
-		if (rf && !strcmp(rf, "lane")) c->refill_uni = false;
-		if (rf && !strcmp(rf, "ahead")) c->read_ahead = true;
-		const char *ev = getenv("QOI_GPU_ENC");
-#ifdef QOI_EXP_EARLYW
-		if (ev && (!strcmp(ev, "earlyw") || !strcmp(ev, "earlyw-mid"))) c->enc_earlyw = true;
-#endif
-#ifdef QOI_EXP_MID
-		if (ev && (!strcmp(ev, "mid") || !strcmp(ev, "earlyw-mid"))) c->enc_mid = true;
-#endif
-		const char *dv = getenv("QOI_GPU_DEC");
-		if (dv && !strcmp(dv, "half")) c->dec_half = true;
-		for (size_t k = 0; ev && k < sizeof g_enc4 / sizeof g_enc4[0]; k++)
-			if (!strcmp(ev, g_enc4[k].name)) c->enc_striped = (int)k + 1;
-	}
 	int rc = enc_occupancy<4, false>(c, &c->enc_blocks_per_sm[0]);
 	if (!rc) rc = enc_occupancy<4, true>(c, &c->enc_blocks_per_sm[1]);
 	if (!rc) rc = enc_occupancy<3, true>(c, &c->enc_blocks_per_sm[2]);
 	if (!rc) rc = fdec_setup(c);
-	if (!rc && c->enc_striped) rc = enc_striped_setup(c);
 	if (rc) {
 		fprintf(stderr, "qoi_gpu: kernel setup failed: %s\n", c->err);
-		cudaStreamDestroy(c->stream);
-		delete c;
+		qoi_gpu_ctx_destroy(c);
 		return rc;
 	}
 	*out = c;
@@ -325,43 +236,12 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	const int variant = p->geom.channels == 3 ? 2 : (zero_copy ? 0 : 1);
 	uint32_t grid = (uint32_t)(ctx->sm_count * ctx->enc_blocks_per_sm[variant]);
 	if (grid > P.n_tiles) grid = P.n_tiles;
-	if (ctx->enc_striped) { /* experimental, QOI_GPU_ENC=<a name of g_enc4[]> */
-		const Enc4Mode &m = g_enc4[ctx->enc_striped - 1];
-		m.fn[variant]<<<grid, QOI_ENC_THREADS, (size_t)m.smem[variant], s>>>(P);
-#ifdef QOI_EXP_MID
-	} else if (ctx->enc_mid) { /* experimental build only, QOI_GPU_ENC=mid | earlyw-mid: the shipped encoder + mid-tile restart records */
-		if (ctx->enc_earlyw) {
-			if (variant == 0) qoienc::qoi_encode_kernel<4, false, true, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-			else if (variant == 1) qoienc::qoi_encode_kernel<4, true, true, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-			else qoienc::qoi_encode_kernel<3, true, true, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
-		} else {
-			if (variant == 0) qoienc::qoi_encode_kernel<4, false, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-			else if (variant == 1) qoienc::qoi_encode_kernel<4, true, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-			else qoienc::qoi_encode_kernel<3, true, true, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
-		}
-#endif
-#ifdef QOI_EXP_EARLYW
-	} else if (ctx->enc_earlyw) { /* experimental build only, QOI_GPU_ENC=earlyw */
-		if (variant == 0) qoienc::qoi_encode_kernel<4, false, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-		else if (variant == 1) qoienc::qoi_encode_kernel<4, true, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-		else qoienc::qoi_encode_kernel<3, true, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
-#endif
-	} else if (ctx->walk) {
-		if (variant == 0) qoienc::qoi_encode_kernel<4, false, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-		else if (variant == 1) qoienc::qoi_encode_kernel<4, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-		else qoienc::qoi_encode_kernel<3, true, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
-	} else {
-		if (variant == 0) qoienc::qoi_encode_kernel<4, false, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
-		else if (variant == 1) qoienc::qoi_encode_kernel<4, true, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
-		else qoienc::qoi_encode_kernel<3, true, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
-	}
+	if (variant == 0) qoienc::qoi_encode_kernel<4, false><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, false>::TOTAL, s>>>(P);
+	else if (variant == 1) qoienc::qoi_encode_kernel<4, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<4, true>::TOTAL, s>>>(P);
+	else qoienc::qoi_encode_kernel<3, true><<<grid, QOI_ENC_THREADS, qoienc::Layout<3, true>::TOTAL, s>>>(P);
 	g_launches++;
 	CK(ctx, cudaGetLastError());
 	p->index_owner = 1;
-	p->index_has_mid = ctx->enc_striped && g_enc4[ctx->enc_striped - 1].slab;
-#ifdef QOI_EXP_MID
-	if (ctx->enc_mid && !ctx->enc_striped) p->index_has_mid = true;
-#endif
 	return QOI_GPU_OK;
 }
 
@@ -399,13 +279,8 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 		qoifdec::fzero_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
 		for (int r = 0; r < QOI_FDEC_ROUNDS; r++) {
 			F.round = (uint32_t)r;
-			if (F.out_channels == 4) {
-				if (ctx->refill_uni) qoifdec::fdecode_kernel<4, true><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
-				else qoifdec::fdecode_kernel<4, false><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
-			} else {
-				if (ctx->refill_uni) qoifdec::fdecode_kernel<3, true><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
-				else qoifdec::fdecode_kernel<3, false><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
-			}
+			if (F.out_channels == 4) qoifdec::fdecode_kernel<4, true><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
+			else qoifdec::fdecode_kernel<3, true><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
 			if (r + 1 < QOI_FDEC_ROUNDS) qoifdec::fverify_kernel<<<F.n_images * QOI_FVER_CHUNKS, 32, 0, s>>>(F);
 		}
 		F.round = QOI_FDEC_ROUNDS - 1; /* reads what the last verify pass wrote */
@@ -429,15 +304,13 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 	D.use_index = 1;
 	D.st = p->st;
 	/* few segments: narrow blocks so that they spread over the SMs */
-	const bool half = ctx->dec_half && p->index_has_mid; /* experimental: job = 2 * tile + half */
-	if (half) D.n_jobs *= 2;
 	const bool narrow = D.n_jobs < (uint32_t)ctx->sm_count * 128u * 2u;
 	if (D.out_channels == 4) {
-		if (narrow) launch_decode<4, 32>(D, s, half ? 3 : ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
-		else launch_decode<4, 128>(D, s, half ? 3 : ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
+		if (narrow) launch_decode<4, 32>(D, s);
+		else launch_decode<4, 128>(D, s);
 	} else {
-		if (narrow) launch_decode<3, 32>(D, s, half ? 3 : ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
-		else launch_decode<3, 128>(D, s, half ? 3 : ctx->refill_uni ? (ctx->read_ahead ? 2 : 1) : 0);
+		if (narrow) launch_decode<3, 32>(D, s);
+		else launch_decode<3, 128>(D, s);
 	}
 	g_launches++;
 	CK(ctx, cudaGetLastError());

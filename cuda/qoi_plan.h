@@ -104,8 +104,9 @@ static inline int qoi_plan_geometry(QoiPlanGeom &g, int n, const QoiDescPOD *des
 	return 0;
 }
 
+#define QOI_STATE_ARRAYS 7
 struct QoiStateLayout {
-	size_t off[13];
+	size_t off[QOI_STATE_ARRAYS];
 	size_t total;
 };
 
@@ -113,8 +114,8 @@ static inline QoiStateLayout qoi_state_layout(uint32_t n_tiles) {
 	QoiStateLayout L;
 	size_t o = 0;
 	const size_t T = n_tiles;
-	const size_t sizes[13] = {16, T * 512, T * 32, T * 512, T * 32, T * 8, T * 4, T * 4, T * 4, T * 512, T * 4, T * 4, T * 4};
-	for (int i = 0; i < 13; i++) {
+	const size_t sizes[QOI_STATE_ARRAYS] = {16, T * 512, T * 32, T * 8, T * 4, T * 4, T * 4};
+	for (int i = 0; i < QOI_STATE_ARRAYS; i++) {
 		L.off[i] = o;
 		o += (sizes[i] + 255) & ~(size_t)255;
 	}
@@ -124,18 +125,12 @@ static inline QoiStateLayout qoi_state_layout(uint32_t n_tiles) {
 
 static inline void qoi_state_bind(QoiTileState &st, unsigned char *base, const QoiStateLayout &L) {
 	st.ticket = (uint32_t *)(base + L.off[0]);
-	st.agg_ent = (uint64_t *)(base + L.off[1]);
-	st.agg_sum = (uint64_t *)(base + L.off[2]);
-	st.inc_ent = (uint64_t *)(base + L.off[3]);
-	st.inc_sum = (uint64_t *)(base + L.off[4]);
-	st.byte_state = (uint64_t *)(base + L.off[5]);
-	st.rs_px = (int32_t *)(base + L.off[6]);
-	st.rs_byte = (int32_t *)(base + L.off[7]);
-	st.rs_prev = (uint32_t *)(base + L.off[8]);
-	st.mid_ent = (uint64_t *)(base + L.off[9]);
-	st.mid_px = (int32_t *)(base + L.off[10]);
-	st.mid_byte = (int32_t *)(base + L.off[11]);
-	st.mid_prev = (uint32_t *)(base + L.off[12]);
+	st.ent = (uint64_t *)(base + L.off[1]);
+	st.sum = (uint64_t *)(base + L.off[2]);
+	st.byte_state = (uint64_t *)(base + L.off[3]);
+	st.rs_px = (int32_t *)(base + L.off[4]);
+	st.rs_byte = (int32_t *)(base + L.off[5]);
+	st.rs_prev = (uint32_t *)(base + L.off[6]);
 }
 
 /* ------------------------------------------------------------------ foreign-stream decoder scratch (qoi_fdec.cuh) */

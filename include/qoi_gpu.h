@@ -42,7 +42,7 @@ extern "C" {
 #define QOI_GPU_E_NOMEM   3
 #define QOI_GPU_E_STREAM  4 /* a stream header does not match the plan (device-side check) */
 
-#define QOI_GPU_TILE_PX   4096 /* pixels per encoder tile == pixels per indexed decode segment */
+#define QOI_GPU_TILE_PX   2048 /* pixels per encoder tile == pixels per indexed decode segment */
 
 typedef struct qoi_gpu_ctx qoi_gpu_ctx;
 typedef struct qoi_gpu_plan qoi_gpu_plan;

@@ -6,7 +6,7 @@ import numpy as np
 
 QOI_SRGB = 0
 QOI_LINEAR = 1
-TILE_PX = 4096
+TILE_PX = 2048
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # QOI_GPU_LIB selects another build of the same C ABI (experiments/build_exp.py writes libqoi_gpu_exp.so for A/B runs);

@@ -10,7 +10,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "qoi_b200", "libqoi_gpu.so")
 SOURCES = [os.path.join(ROOT, "cuda", f) for f in
-           ("qoi_gpu.cu", "qoi_enc.cuh", "qoi_enc4.cuh", "qoi_dec.cuh", "qoi_fdec.cuh", "qoi_dev.cuh", "qoi_common.h", "qoi_plan.h")] + \
+           ("qoi_gpu.cu", "qoi_enc.cuh", "qoi_dec.cuh", "qoi_fdec.cuh", "qoi_dev.cuh", "qoi_common.h", "qoi_plan.h")] + \
           [os.path.join(ROOT, "include", f) for f in ("qoi.h", "qoi_gpu.h")]
 
 NVCC_FLAGS = [

@@ -21,7 +21,6 @@
 #define QOI_EMU 1
 #include "qoi_dec.cuh"
 #include "qoi_enc.cuh"
-#include "qoi_enc4.cuh"
 #include "qoi_fdec.cuh"
 #include "qoi_plan.h"
 
@@ -49,37 +48,12 @@ static std::vector<unsigned char> read_file(const char *path) {
 template <int CH, bool EXPAND>
 static void run_encode(const QoiEncParams &P, unsigned grid, unsigned seed) {
 	using L = qoienc::Layout<CH, EXPAND>;
-	const char *ev = getenv("QOI_EMU_ENC"); /* experimental striped encoder (cuda/qoi_enc4.cuh): striped | striped-match */
-#ifdef QOI_EXP_MID /* experimental build only (experiments/encoder_mid.patch, on top of earlyw) */
-	if (ev && !strcmp(ev, "mid")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc::qoi_encode_kernel<CH, EXPAND, true, false, true>(P); }, seed); return; }
-	if (ev && !strcmp(ev, "earlyw-mid")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc::qoi_encode_kernel<CH, EXPAND, true, true, true>(P); }, seed); return; }
-#endif
-#ifdef QOI_EXP_EARLYW /* experimental build only (experiments/encoder_earlyw.patch) */
-	if (ev && !strcmp(ev, "earlyw")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc::qoi_encode_kernel<CH, EXPAND, true, true>(P); }, seed); return; }
-#endif
-	if (ev && !strcmp(ev, "striped")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, false>(P); }, seed); return; }
-	if (ev && !strcmp(ev, "striped-earlyw")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, false, true>(P); }, seed); return; }
-	if (ev && !strcmp(ev, "slab")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, false, false, true>(P); }, seed); return; }
-	if (ev && !strcmp(ev, "slab-pipe")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true, false, true, true>(P); }, seed); return; }
-	if (ev && !strcmp(ev, "slab4")) { using LC = qoienc4::LayoutC<CH, EXPAND>; qemu::launch(grid, QOI_ENC_THREADS, (size_t)LC::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true, false, true, false, true>(P); }, seed); return; }
-	if (ev && !strcmp(ev, "slab4-pipe")) { using LC = qoienc4::LayoutC<CH, EXPAND>; qemu::launch(grid, QOI_ENC_THREADS, (size_t)LC::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true, false, true, true, true>(P); }, seed); return; }
-	if (ev && !strcmp(ev, "slab-pipe-ballot")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, false, false, true, true>(P); }, seed); return; }
-	if (ev && !strcmp(ev, "slab-match")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true, false, true>(P); }, seed); return; }
-	if (ev && !strcmp(ev, "striped-match")) { qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc4::qoi_encode_striped_kernel<CH, EXPAND, true>(P); }, seed); return; }
-	qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { if (getenv("QOI_GPU_LOOKUP") && !strcmp(getenv("QOI_GPU_LOOKUP"), "summary")) qoienc::qoi_encode_kernel<CH, EXPAND, false>(P); else qoienc::qoi_encode_kernel<CH, EXPAND, true>(P); }, seed);
+	qemu::launch(grid, QOI_ENC_THREADS, (size_t)L::TOTAL, [&]() { qoienc::qoi_encode_kernel<CH, EXPAND>(P); }, seed);
 }
 
 static void run_decode(const QoiDecParams &P, unsigned seed) {
 	unsigned grid = (P.n_jobs + QOI_DEC_THREADS - 1) / QOI_DEC_THREADS;
 	size_t smem = QOI_DEC_SMEM_WORDS * QOI_DEC_THREADS * 4;
-	if (getenv("QOI_EMU_DEC") && !strcmp(getenv("QOI_EMU_DEC"), "half") && P.use_index) { /* two lanes per tile; needs a slab-mode encoder's index */
-		QoiDecParams H = P;
-		H.n_jobs = 2 * P.n_jobs;
-		grid = (H.n_jobs + QOI_DEC_THREADS - 1) / QOI_DEC_THREADS;
-		if (P.out_channels == 4) qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, true, false, true>(H); }, seed);
-		else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true, false, true>(H); }, seed);
-		return;
-	}
 	if (P.out_channels == 4) qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_ahead()) qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, true, true>(P); else if (emu_uni()) qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, true, false>(P); else qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, false, false>(P); }, seed);
 	else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_ahead()) qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true, true>(P); else if (emu_uni()) qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true, false>(P); else qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, false, false>(P); }, seed);
 }
@@ -206,11 +180,6 @@ int main(int argc, char **argv) {
 					if (got[olen] != 0xEE || (soff[i] && got[-1] != 0xEE)) { printf("FAIL encode image %d: wrote outside its stream\n", i); return 1; }
 					free(ref);
 				}
-			}
-			if (getenv("QOI_EMU_HALFSTAT")) { /* how many tiles carry a second restart point (slab-mode encoders only) */
-				unsigned have = 0;
-				for (uint32_t tt = 0; tt < g.n_tiles; tt++) have += P.st.mid_px[tt] >= 0;
-				fprintf(stderr, "mid restart points: %u of %u tiles\n", have, g.n_tiles);
 			}
 			/* decode what we wrote: with the restart index, then as a foreign stream */
 			for (int use_index = 1; use_index >= (getenv("QOI_EMU_SKIP_FOREIGN") ? 1 : 0); use_index--) { /* encoder-variant runs skip the any-stream decoder */

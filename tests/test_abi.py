@@ -35,7 +35,8 @@ def test_binding_covers_the_abi():
 
 
 def test_kernels_are_blackwell_native():
-    """SASS evidence that the hot path uses bulk async copies (TMA, UBLKCP) both ways, mbarriers, named barriers and dp4a."""
+    """SASS evidence that the hot path uses bulk async copies (TMA, UBLKCP) for the pixel tiles, mbarriers, named barriers,
+    match.any and dp4a."""
     import qoi_b200
 
     try:
@@ -44,7 +45,7 @@ def test_kernels_are_blackwell_native():
         import pytest
         pytest.skip("cuobjdump not available")
     assert "sm_100a" in sass
-    for needle in ("UBLKCP.S.G", "UBLKCP.G.S", "SYNCS.", "BAR.ARV", "IDP.4A"):
+    for needle in ("UBLKCP.S.G", "SYNCS.", "BAR.ARV", "IDP.4A", "MATCH.ANY"):
         assert needle in sass, needle
 
 

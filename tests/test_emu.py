@@ -27,73 +27,22 @@ def run_enc(emu, img, w, h, ch, n, grid, seed, mis, extra_variants=()):
     with tempfile.NamedTemporaryFile(suffix=".raw") as f:
         f.write(np.ascontiguousarray(img, dtype=np.uint8).tobytes())
         f.flush()
-        for lookup in ("walk", "summary"):  # both look-up variants of the encoder (QOI_GPU_LOOKUP)
-            # ... and the foreign decoder's verify pass with one range per stream / with several
-            # ... and the decoders' stream reader with warp-uniform / lane-driven refill
-            env = dict(os.environ, QOI_GPU_LOOKUP=lookup, QOI_EMU_FVER_MIN_RANGE="1024" if lookup == "walk" else "3",
-                       QOI_EMU_REFILL="uniform" if lookup == "walk" else "lane")
+        # the foreign decoder's verify pass with one range per stream / with several, and the decoders' stream reader
+        # with warp-uniform / lane-driven refill
+        for cfg in ({"QOI_EMU_FVER_MIN_RANGE": "1024", "QOI_EMU_REFILL": "uniform"}, {"QOI_EMU_FVER_MIN_RANGE": "3", "QOI_EMU_REFILL": "lane"}):
             r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
-                               capture_output=True, text=True, timeout=300, env=env)
-            assert r.returncode == 0 and r.stdout.startswith("PASS"), lookup + ": " + r.stdout + r.stderr[-2000:]
-        for extra in extra_variants:  # experimental kernel variants that are off by default
-            r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
-                               capture_output=True, text=True, timeout=300, env=dict(os.environ, **extra))
-            assert r.returncode == 0 and r.stdout.startswith("PASS"), str(extra) + ": " + r.stdout + r.stderr[-2000:]
-
-
-@pytest.mark.parametrize("dist", range(8))
-def test_emulated_distributions(emu, cpu, dist):
-    ahead = ({"QOI_EMU_REFILL": "ahead"},)  # indexed decoder reading its ring one word ahead (QOI_GPU_REFILL=ahead)
-    run_enc(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0, ahead)
-    run_enc(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist, ahead)
-
-
-# cuda/qoi_enc4.cuh (QOI_GPU_ENC=striped | striped-match | striped-earlyw); the tests below alternate between the first two ...
-STRIPED = ({"QOI_EMU_ENC": "striped"}, {"QOI_EMU_ENC": "striped-match"})
-PIPE = ({"QOI_EMU_ENC": "slab-pipe"}, {"QOI_EMU_ENC": "slab-pipe-ballot"})  # slab mode with the copy-out behind the next tile's index pass
-COMPACT = ({"QOI_EMU_ENC": "slab4"}, {"QOI_EMU_ENC": "slab4-pipe"})  # slab mode in the compact layout (one pixel buffer, 4 CTAs per SM)
-SLAB = ({"QOI_EMU_ENC": "slab"}, {"QOI_EMU_ENC": "slab-match"})  # the rolled "slab" mode of the same kernel (QOI_GPU_ENC=slab | slab-match)
-STRIPED_EARLYW = ({"QOI_EMU_ENC": "striped-earlyw"},)  # ... and run this one on a subset
-
-
-def run_variants(emu, img, w, h, ch, n, grid, seed, mis, variants):
-    """Only the experimental variants (the default kernels are covered by run_enc)."""
-    with tempfile.NamedTemporaryFile(suffix=".raw") as f:
-        f.write(np.ascontiguousarray(img, dtype=np.uint8).tobytes())
-        f.flush()
-        for extra in variants:
+                               capture_output=True, text=True, timeout=300, env=dict(os.environ, **cfg))
+            assert r.returncode == 0 and r.stdout.startswith("PASS"), str(cfg) + ": " + r.stdout + r.stderr[-2000:]
+        for extra in extra_variants:
             r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
                                capture_output=True, text=True, timeout=300, env=dict(os.environ, QOI_EMU_SKIP_FOREIGN="1", **extra))
             assert r.returncode == 0 and r.stdout.startswith("PASS"), str(extra) + ": " + r.stdout + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("dist", range(8))
-def test_emulated_striped_encoder_distributions(emu, cpu, dist):
-    """The experimental lane-per-pixel encoder: streams bit exact, its restart index decodes, nothing written out of bounds."""
-    four = STRIPED + SLAB + PIPE + COMPACT
-    run_variants(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0, four)
-    run_variants(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist, four)
-    if True:
-        run_variants(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 30 + dist, 0, STRIPED_EARLYW)
-        run_variants(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 40 + dist, dist, STRIPED_EARLYW)
-
-
-def test_emulated_striped_encoder_stress_and_runs(emu, cpu):
-    rng = np.random.default_rng(7)
-    for it in range(18):
-        w = int(rng.integers(60, 300)); h = int(rng.integers(20, 120)); ch = int(rng.integers(3, 5)); n = int(rng.integers(1, 4))
-        img = np.concatenate([q.stress_image(rng, w * h, ch, it % 6) for _ in range(n)])
-        nine = STRIPED + SLAB + STRIPED_EARLYW + PIPE + COMPACT
-        run_variants(emu, img, w, h, ch, n, int(rng.integers(1, 5)), it + 1, int(rng.integers(0, 17)) if it % 2 else 0, (nine[it % 9], nine[(it + 4) % 9], COMPACT[it % 2]))
-    n = 40000  # runs that cross warp chunks, tiles and the 62 boundary; runs from the image start (qoi.h:396-399)
-    a = np.zeros((n, 4), dtype=np.uint8); a[:, 3] = 255
-    b = np.zeros((n, 4), dtype=np.uint8)
-    c = np.zeros((n, 4), dtype=np.uint8); c[:, 3] = 255; c[n // 2:] = (9, 9, 9, 255); c[-5:] = (0, 0, 0, 255)
-    d = np.full((n, 4), 200, dtype=np.uint8); d[12345] = (1, 2, 3, 4)
-    for k, img in enumerate((a, b, c, d)):
-        nine = STRIPED + SLAB + STRIPED_EARLYW + PIPE + COMPACT
-        run_variants(emu, img.reshape(-1), 400, 100, 4, 1, 4, 3, 0, nine[k::4] + COMPACT[1:])
-        run_variants(emu, np.ascontiguousarray(img[:, :3]).reshape(-1), 400, 100, 3, 1, 3, 4, 5, nine[(k + 2) % 4::4] + PIPE[:1])
+def test_emulated_distributions(emu, cpu, dist):
+    run_enc(emu, cpu.batch(2, 160, 130, 4, dist), 160, 130, 4, 2, 3, 10 + dist, 0)
+    run_enc(emu, cpu.batch(2, 131, 97, 3, dist), 131, 97, 3, 2, 2, 20 + dist, dist)
 
 
 def test_emulated_stress(emu, cpu):
@@ -140,23 +89,28 @@ def test_emulated_foreign_decode(emu, cpu):
 
 
 def test_emulated_many_tiles(emu, cpu):
-    """512 x 512 images (64 tiles each) on 6 CTAs: look-back windows of many in-flight predecessors, for the shipped encoder
-    and every variant."""
-    img = cpu.batch(1, 512, 512, 4, 4)
-    run_variants(emu, img, 512, 512, 4, 1, 6, 7, 0, ({"QOI_GPU_LOOKUP": "walk"}, STRIPED[0], COMPACT[1]))
-    pal = cpu.batch(1, 512, 300, 3, 6)
-    run_variants(emu, pal, 512, 300, 3, 1, 5, 9, 3, (SLAB[0], PIPE[1]))
-    for grid in (1, 2, 7):  # the pipelined hand-offs with one CTA, with fewer CTAs than images, with more CTAs than tiles in flight
-        run_variants(emu, cpu.batch(5, 256, 64, 4, 6), 256, 64, 4, 5, grid, 3 + grid, 5, PIPE[:1] + COMPACT)
+    """Images of many tiles on few CTAs: look-back windows of many in-flight predecessors, sparse tables (palette), more
+    images than CTAs and more CTAs than tiles in flight; indexed decode only (the any-stream decoder has its own tests)."""
+    fast = ({},)
+    with_index_only = lambda img, w, h, ch, n, grid, seed, mis: run_enc_only(emu, img, w, h, ch, n, grid, seed, mis)
+    with_index_only(cpu.batch(1, 512, 512, 4, 4), 512, 512, 4, 1, 6, 7, 0)
+    with_index_only(cpu.batch(1, 512, 300, 3, 6), 512, 300, 3, 1, 5, 9, 3)
+    with_index_only(cpu.batch(1, 700, 400, 4, 7), 700, 400, 4, 1, 9, 2, 0)  # 137 tiles of runs only: window look-back over > 32 tiles
+    for grid in (1, 2, 7):
+        with_index_only(cpu.batch(5, 256, 64, 4, 6), 256, 64, 4, 5, grid, 3 + grid, 5)
 
 
-def test_emulated_two_lanes_per_tile_decode(emu, cpu):
-    """QOI_GPU_DEC=half: the slab-mode encoders also leave a restart point at every tile's mid point (table = merge of the first
-    four warps' tables with the incoming one); the indexed decoder then runs job = 2 * tile + half.  Shapes around the mid
-    point, runs crossing it, partial tiles."""
-    half = lambda v: dict(v, QOI_EMU_DEC="half")
-    for k, (w, h, ch, n, dist) in enumerate([(160, 130, 4, 2, 4), (131, 97, 3, 2, 3), (400, 100, 4, 1, 7), (2048, 1, 4, 3, 4), (2049, 1, 4, 3, 4),
-                                             (2110, 1, 3, 2, 7), (2047, 3, 4, 2, 2), (512, 512, 4, 1, 0), (256, 64, 4, 5, 6), (300, 200, 3, 2, 5)]):
-        img = cpu.batch(n, w, h, ch, dist)
-        variants = (SLAB + PIPE + COMPACT)
-        run_variants(emu, img, w, h, ch, n, 1 + k % 4, k + 1, (0, 5, 3)[k % 3] if ch == 4 else 1 + k % 3, (half(variants[k % 6]), half(variants[(k + 3) % 6])))
+def run_enc_only(emu, img, w, h, ch, n, grid, seed, mis):
+    with tempfile.NamedTemporaryFile(suffix=".raw") as f:
+        f.write(np.ascontiguousarray(img, dtype=np.uint8).tobytes())
+        f.flush()
+        r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
+                           capture_output=True, text=True, timeout=600, env=dict(os.environ, QOI_EMU_SKIP_FOREIGN="1"))
+        assert r.returncode == 0 and r.stdout.startswith("PASS"), r.stdout + r.stderr[-2000:]
+
+
+def test_emulated_tile_edges(emu, cpu):
+    """Shapes around the tile (2048 px) and warp-chunk (512 px) boundaries, runs crossing them, partial last tiles."""
+    for k, (w, h, ch, n, dist) in enumerate([(2048, 1, 4, 3, 4), (2049, 1, 4, 3, 4), (2110, 1, 3, 2, 7), (2047, 3, 4, 2, 2), (513, 4, 4, 2, 5),
+                                             (511, 5, 3, 2, 3), (4096, 1, 4, 1, 7), (4097, 1, 3, 1, 7), (1, 1, 4, 4, 4), (33, 1, 3, 3, 0), (300, 200, 3, 2, 5)]):
+        run_enc_only(emu, cpu.batch(n, w, h, ch, dist), w, h, ch, n, 1 + k % 4, k + 1, (0, 5, 3)[k % 3] if ch == 4 else 1 + k % 3)
