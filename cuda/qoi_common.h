@@ -69,7 +69,7 @@ struct QoiEncParams {
 	int32_t *lens;
 	const QoiImgMeta *imgs;
 	const uint32_t *tile_img; /* [n_tiles] image that owns each tile */
-	const uint32_t *tile_order; /* [n_tiles] ticket -> tile: images interleaved so that in-flight tiles spread over the batch */
+	const uint64_t *tile_order; /* [n_tiles] ticket -> tile | image << 32: images interleaved so that in-flight tiles spread over the batch */
 	uint32_t n_images;
 	uint32_t n_tiles;
 	uint32_t epoch; /* 1 .. 2^30-1, different for every launch that shares the state arrays */

@@ -96,13 +96,14 @@ struct Layout {
 	static constexpr int OFF_WTAB = OFF_SLAB + QOI_ENC_WARPS * SLAB_BYTES; /* uint2 [warps][64]: last non-run pixel per slot in the warp's chunk {value, written} */
 	static constexpr int OFF_TIN = OFF_WTAB + QOI_ENC_WARPS * 64 * 8;      /* u32 [warps][64]: the warp's running index[] in pass B */
 	static constexpr int OFF_TINS = OFF_TIN + QOI_ENC_WARPS * 64 * 4;      /* u32 [64]: index[] before the tile (service warp) */
-	static constexpr int OFF_MBAR = OFF_TINS + 64 * 4;                     /* u64 */
+	static constexpr int OFF_ROWS = OFF_TINS + 64 * 4;                     /* uint4 [warps][rows]: what pass A found out about each row: non-run, hit, unknown lanes */
+	static constexpr int OFF_MBAR = OFF_ROWS + QOI_ENC_WARPS * QOI_WARP_ROWS * 16; /* u64 */
 	static constexpr int OFF_INFO = OFF_MBAR + 16;                         /* TileInfo [2] */
 	static constexpr int OFF_WTOT = OFF_INFO + 2 * (int)sizeof(TileInfo);  /* u32 [warps] bytes per slab */
 	static constexpr int OFF_WLNR = OFF_WTOT + QOI_ENC_WARPS * 4;          /* i32 [warps] last non-run pixel of the chunk (tile coordinates, -1: none) */
 	static constexpr int OFF_MISC = OFF_WLNR + QOI_ENC_WARPS * 4;          /* u32 [4] */
 	static constexpr int TOTAL = OFF_MISC + 16;
-	static_assert(SLAB_BYTES % 16 == 0 && OFF_SLAB % 16 == 0 && OFF_WTAB % 8 == 0 && OFF_MBAR % 8 == 0 && OFF_INFO % 16 == 0, "alignment");
+	static_assert(SLAB_BYTES % 16 == 0 && OFF_SLAB % 16 == 0 && OFF_WTAB % 8 == 0 && OFF_ROWS % 16 == 0 && OFF_MBAR % 8 == 0 && OFF_INFO % 16 == 0, "alignment");
 };
 
 /* misc[] slots */
@@ -120,18 +121,23 @@ struct Fetch {
 	bool any;
 };
 
-/* step 1: take a ticket; which tile, which image (touches no shared memory, so it can run a whole tile ahead) */
-__device__ __forceinline__ void fetch_ticket(const QoiEncParams &P, Fetch &F) {
-	const uint32_t lane = lane_id();
+/* step 1: take a ticket -- only when the tile can start as soon as its pixels are there.  (Round 1 and the first version of
+   this kernel took it a whole tile ahead: the predecessor of a running tile could then still be queued behind another tile
+   of its CTA, and every look-back waited for tiles that had not even started -- ~20 us per tile whatever the content.) */
+__device__ __forceinline__ uint32_t ticket_take(const QoiEncParams &P) {
 	uint32_t tk = 0;
-	if (lane == 0) tk = atomicAdd(&P.st.ticket[0], 1u);
-	tk = __shfl_sync(QOI_FULL_MASK, tk, 0);
+	if (lane_id() == 0) tk = atomicAdd(&P.st.ticket[0], 1u);
+	return tk; /* valid in lane 0 */
+}
+__device__ __forceinline__ void ticket_resolve(const QoiEncParams &P, uint32_t tk_lane0, Fetch &F) {
+	const uint32_t tk = __shfl_sync(QOI_FULL_MASK, tk_lane0, 0);
 	F.any = tk < P.n_tiles;
 	F.tile = 0;
 	F.img = 0;
 	if (F.any) {
-		F.tile = P.tile_order[tk]; /* ascending inside every image, images interleaved */
-		F.img = P.tile_img[F.tile];
+		const uint64_t rec = P.tile_order[tk]; /* ascending inside every image, images interleaved */
+		F.tile = (uint32_t)rec;
+		F.img = (uint32_t)(rec >> 32);
 	}
 }
 
@@ -207,27 +213,61 @@ __device__ __forceinline__ void fetch_issue(const QoiEncParams &P, unsigned char
 	}
 }
 
+/* one byte to shared memory under a predicate, without a branch (the op bytes of a row: up to five stores per lane) */
+__device__ __forceinline__ void sts_u8_if(bool pred, unsigned char *addr, uint32_t val) {
+#ifdef QOI_EMU
+	if (pred) *addr = (unsigned char)val;
+#else
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "setp.ne.u32 p, %0, 0;\n\t"
+	    "@p st.shared.u8 [%1], %2;\n\t}" ::"r"((uint32_t)pred),
+	    "r"(smem_addr(addr)), "r"(val)
+	    : "memory");
+#endif
+}
+
+/* the lanes of the row whose 6-bit key equals mine: six ballots.  (match.any does this in one instruction, but that
+   instruction holds the ADU pipe for ~50 cycles per warp on sm_100a -- measured, profiles/r2_enc_v1 -- and two of them per
+   row made the whole kernel ADU-bound.) */
+__device__ __forceinline__ uint32_t same_key_lanes(uint32_t key) {
+	uint32_t differ = 0;
+#pragma unroll
+	for (int b = 0; b < 6; b++) {
+		const bool bit = (key >> b) & 1u;
+		const uint32_t plane = __ballot_sync(QOI_FULL_MASK, bit);
+		differ |= bit ? ~plane : plane;
+	}
+	return ~differ;
+}
+
 /* ---------------------------------------------------------------- op of one non-run pixel that is not an INDEX hit */
-/* qoi.h:438-474, branch free, on packed r | g<<8 | b<<16 | a<<24 words.  size 1 DIFF, 2 LUMA, 4 RGB, 5 RGBA;
+/* qoi.h:438-474, branch free, on packed r | g<<8 | b<<16 | a<<24 words.  The op class comes back as predicates (the byte
+   offsets are ballots of them): DIFF (1 byte), LUMA (2), neither = RGB (4) or, if alpha changed, RGBA (5).
    b0 = first byte, b1 = second byte (LUMA's second byte, or r for RGB / RGBA whose g, b, a follow from v). */
-__device__ __forceinline__ void classify(uint32_t v, uint32_t p, uint32_t &size, uint32_t &b0, uint32_t &b1) {
+struct OpClass {
+	bool diff, luma, a_eq;
+	uint32_t b0, b1;
+};
+__device__ __forceinline__ OpClass classify(uint32_t v, uint32_t p) {
+	OpClass c;
 	/* per-channel difference mod 256 (qoi.h:439-441), no borrows between bytes */
 	const uint32_t d = ((v | 0x80808080u) - (p & 0x7F7F7F7Fu)) ^ ((v ^ ~p) & 0x80808080u);
-	const bool a_eq = d < 0x01000000u; /* alpha unchanged (qoi.h:438) */
+	c.a_eq = d < 0x01000000u; /* alpha unchanged (qoi.h:438) */
 	/* DIFF (qoi.h:446-451): dr+2, dg+2, db+2 all in 0..3 */
 	const uint32_t t = ((d & 0x7F7F7F7Fu) + 0x00020202u) ^ (d & 0x80808080u);
-	const bool is_diff = (t & 0xFFFCFCFCu) == 0u;
+	c.diff = (t & 0xFFFCFCFCu) == 0u;
 	const uint32_t diff_b = 0x40u | ((t << 4) & 0x30u) | ((t >> 6) & 0x0Cu) | ((t >> 16) & 0x03u);
 	/* LUMA (qoi.h:443-444, 453-459): vg in -32..31, vr-vg and vb-vg in -8..7, all as wrapped signed bytes */
 	const uint32_t dg = (d >> 8) & 0xFFu;
 	const uint32_t g32 = (dg + 32u) & 0xFFu;
 	/* two 16-bit lanes: 0x108 + d_c - dg never borrows; the low byte of each lane is (d_c - dg + 8) mod 256 */
 	const uint32_t t2 = (((d & 0x00FF00FFu) | 0x01000100u) + 0x00080008u - dg * 0x00010001u) & 0x00FF00FFu;
-	const bool is_luma = a_eq && g32 < 64u && (t2 & 0x00F000F0u) == 0u;
+	c.luma = !c.diff && c.a_eq && g32 < 64u && (t2 & 0x00F000F0u) == 0u;
 	const uint32_t luma_b1 = ((t2 & 0xFu) << 4) | (t2 >> 16);
-	size = is_diff ? 1u : (is_luma ? 2u : (a_eq ? 4u : 5u));
-	b0 = is_diff ? diff_b : (is_luma ? (0x80u | g32) : (a_eq ? 0xFEu : 0xFFu)); /* qoi.h:461-473 */
-	b1 = is_luma ? luma_b1 : (v & 0xFFu);
+	c.b0 = c.diff ? diff_b : (c.luma ? (0x80u | g32) : (c.a_eq ? 0xFEu : 0xFFu)); /* qoi.h:461-473 */
+	c.b1 = c.luma ? luma_b1 : (v & 0xFFu);
+	return c;
 }
 
 /* ---------------------------------------------------------------- service warp: table / run look-back over a 32-tile window */
@@ -307,6 +347,10 @@ __device__ __forceinline__ void table_lookback(const QoiEncParams &P, uint32_t t
 	}
 }
 
+/* compile-time flags for the row bodies of pass B */
+struct Yes { static constexpr bool value = true; };
+struct No { static constexpr bool value = false; };
+
 /* ---------------------------------------------------------------- the kernel */
 #ifndef QOI_ENC_MIN_BLOCKS
 #define QOI_ENC_MIN_BLOCKS 9 /* register budget: 40 (45 warps fit in 64 K registers) */
@@ -316,7 +360,10 @@ template <int CH, bool EXPAND>
 __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encode_kernel(const QoiEncParams P) {
 	using L = Layout<CH, EXPAND>;
 	QOI_DYNAMIC_SMEM(smem);
-	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u;
+	/* through a shuffle so that the compiler knows the warp index (and every branch on it) is uniform: without that it guards
+	   each warp-wide instruction of the row loops with a divergence check */
+	const uint32_t warp = __shfl_sync(QOI_FULL_MASK, tid >> 5, 0);
 	const bool service = warp == QOI_ENC_WARPS;
 	uint64_t *mbar = (uint64_t *)(smem + L::OFF_MBAR);
 	TileInfo *infos = (TileInfo *)(smem + L::OFF_INFO);
@@ -337,14 +384,12 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 	if (service) {
 		/* =============================== service warp =============================== */
 		Fetch F;
-		fetch_ticket(P, F);
+		ticket_resolve(P, ticket_take(P), F);
 		fetch_issue<CH, EXPAND>(P, smem, F, 0);
 		int cur = 0;
 		while (F.any) {
 			const TileInfo *ti = infos + cur;
 			const uint32_t t = F.tile;
-			Fetch Fn;
-			fetch_ticket(P, Fn); /* a whole tile ahead: its three dependent round trips hide behind pass A */
 			const uint32_t first_tile = ti->first_tile, px0 = ti->px0;
 
 			bar_sync(BAR_A_DONE, QOI_N_CS); /* the per-warp tables and wlnr[] of this tile are complete */
@@ -396,7 +441,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 			}
 
 			bar_sync(BAR_B_DONE, QOI_N_CS); /* slab sizes are in wtot[]; nobody reads the pixel buffer any more */
-			fetch_issue<CH, EXPAND>(P, smem, Fn, cur ^ 1);
+			const uint32_t tk_next = ticket_take(P); /* in flight while the offset look-back runs */
 			/* ---- phase B: output offset look-back, 32 predecessors per probe ---- */
 			uint32_t total = 0;
 #pragma unroll
@@ -437,23 +482,30 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 			}
 			__syncwarp();
 			bar_arrive(BAR_B_READY, QOI_N_CS);
+			/* the next tile: which one, its info record, its pixels on their way */
+			Fetch Fn;
+			ticket_resolve(P, tk_next, Fn);
+			const uint32_t img_cur = ti->img, npx_cur = ti->npx, nv_cur = ti->n_valid;
+			const uint64_t so_cur = ti->stream_off;
+			const uint32_t w_cur = ti->width, h_cur = ti->height, cc_cur = ti->chan_cs;
+			fetch_issue<CH, EXPAND>(P, smem, Fn, cur ^ 1);
 			{
-				uint8_t *gstream = P.streams + ti->stream_off;
+				uint8_t *gstream = P.streams + so_cur;
 				if (t == first_tile && lane < QOI_HEADER_BYTES) { /* header, qoi.h:384-388 */
 					const uint32_t k = lane;
 					uint8_t b;
 					if (k < 4) b = (uint8_t)("qoif"[k]);
-					else if (k < 8) b = (uint8_t)(ti->width >> (8 * (7 - k)));
-					else if (k < 12) b = (uint8_t)(ti->height >> (8 * (11 - k)));
-					else if (k == 12) b = (uint8_t)(ti->chan_cs & 0xFFu);
-					else b = (uint8_t)(ti->chan_cs >> 8);
+					else if (k < 8) b = (uint8_t)(w_cur >> (8 * (7 - k)));
+					else if (k < 12) b = (uint8_t)(h_cur >> (8 * (11 - k)));
+					else if (k == 12) b = (uint8_t)(cc_cur & 0xFFu);
+					else b = (uint8_t)(cc_cur >> 8);
 					gstream[k] = b;
 				}
-				if (ti->px0 + ti->n_valid == ti->npx && lane >= 16 && lane < 16 + QOI_END_BYTES + 1) { /* end marker, length: qoi.h:480-484 */
+				if (px0 + nv_cur == npx_cur && lane >= 16 && lane < 16 + QOI_END_BYTES + 1) { /* end marker, length: qoi.h:480-484 */
 					const uint32_t k = lane - 16;
 					const uint32_t fin = excl + total;
 					if (k < QOI_END_BYTES) gstream[fin + k] = (k == QOI_END_BYTES - 1) ? 1 : 0;
-					else P.lens[ti->img] = (int32_t)(fin + QOI_END_BYTES);
+					else P.lens[img_cur] = (int32_t)(fin + QOI_END_BYTES);
 				}
 			}
 			F = Fn;
@@ -476,13 +528,15 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 	uint2 *wtab = wtab_all + warp * 64;
 	uint32_t *tin = (uint32_t *)(smem + L::OFF_TIN) + warp * 64;
 	unsigned char *slab = smem + L::OFF_SLAB + warp * L::SLAB_BYTES;
+	uint4 *rows = (uint4 *)(smem + L::OFF_ROWS) + warp * QOI_WARP_ROWS;
+	const uint32_t lanebit = 1u << lane;
 	int cur = 0;
 	uint32_t parity = 0;
 	while (true) {
 		mbar_wait(mbar, parity); /* info record and pixels of the tile have landed */
 		parity ^= 1u;
 		const TileInfo *ti = infos + cur;
-		if (ti->tile < 0) break;
+		if (__ballot_sync(QOI_FULL_MASK, ti->tile < 0)) break; /* (a vote, so that the exit is visibly uniform) */
 		const uint32_t t = (uint32_t)ti->tile;
 		const uint32_t nv = ti->n_valid, px0 = ti->px0, npx = ti->npx;
 
@@ -502,27 +556,37 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 			bar_sync(BAR_COMPUTE, QOI_ENC_COMPUTE);
 		}
 
-		/* ---- pass A: last non-run pixel of every hash slot in my chunk; rows only meet in the table ---- */
+		/* ---- pass A: everything about the INDEX look-up that my chunk can know on its own.  Per row: non-run mask, hash slot,
+		   the row's lanes with my slot; a pixel with an earlier same-slot pixel in the chunk (this row: shuffle, rows before:
+		   the warp's table) is a known hit or miss, a slot's first pixel in the chunk stays UNKNOWN until the table before
+		   the chunk is there.  The table ends up holding the chunk's last non-run pixel per slot = its aggregate. ---- */
 		wtab[lane] = make_uint2(0u, 0u);
 		wtab[lane + 32] = make_uint2(0u, 0u);
 		__syncwarp();
 		{
 			int32_t last_nr = -1; /* tile-local index of the chunk's last non-run pixel so far (uniform) */
-#pragma unroll 4
-			for (int s = 0; s < QOI_WARP_ROWS; s++) {
-				const uint32_t rb0 = wbase + (uint32_t)s * 32u;
-				if (rb0 >= nv) break; /* uniform */
-				const uint32_t il = rb0 + lane;
-				const uint32_t v = pix[il], p = pix[(int)il - 1];
+			const uint32_t *px = pix + wbase + lane;
+			uint32_t il = wbase + lane;
+#pragma unroll 2
+			for (int s = 0; s < QOI_WARP_ROWS; s++, px += 32, il += 32u) {
+				const uint32_t v = px[0], p = px[-1];
 				const bool nonrun = il < nv && v != p; /* qoi.h:415 */
 				const uint32_t nr = __ballot_sync(QOI_FULL_MASK, nonrun);
+				uint32_t hb = 0, ub = 0;
 				if (nr) { /* uniform: a row of run pixels touches nothing */
 					const uint32_t h = qoi_slot(v);
-					const uint32_t m = __match_any_sync(QOI_FULL_MASK, nonrun ? h : 64u + lane);
-					if (nonrun && (m & gt) == 0u) wtab[h] = make_uint2(v, 1u); /* the row's last pixel of its slot */
-					last_nr = (int32_t)(rb0 + 31u - (uint32_t)__clz((int)nr));
-					__syncwarp(); /* the next row's stores to the same slot come after these */
+					const uint32_t m = same_key_lanes(h) & nr;
+					const uint32_t lower = m & lt;
+					const uint2 e = wtab[h];                                                 /* as the rows before left it */
+					const uint32_t pv = __shfl_sync(QOI_FULL_MASK, v, 31 - __clz((int)lower)); /* nearest same-slot pixel of this row (garbage if none) */
+					const bool known = lower != 0u || e.y != 0u;
+					hb = __ballot_sync(QOI_FULL_MASK, nonrun && known && (lower ? pv : e.x) == v); /* qoi.h:432 */
+					ub = __ballot_sync(QOI_FULL_MASK, nonrun && !known);
+					if (nonrun && (m & gt) == 0u) wtab[h] = make_uint2(v, 1u); /* qoi.h:436: the row's last pixel of its slot */
+					last_nr = (int32_t)(il - lane + 31u - (uint32_t)__clz((int)nr));
 				}
+				if (lane == 0) rows[s] = make_uint4(nr, hb, ub, 0u);
+				__syncwarp(); /* the next row reads the table after these stores */
 			}
 			if (lane == 0) wlnr[warp] = last_nr;
 		}
@@ -550,83 +614,92 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 			if ((uint32_t)w2 < warp && wlnr[w2] >= 0) lnr = (int32_t)px0 + wlnr[w2];
 		__syncwarp();
 
-		/* ---- pass B: ops and bytes, row by row; the table is exact from the first pixel on ---- */
+		/* ---- pass B: ops and bytes.  The rows are independent now (tin[] is read only); only the byte offset and the run
+		   carry go from row to row.  One straight-line body per kind of row (non-run pixels only / run pixels only / both),
+		   picked by a uniform branch, so that the op classes stay predicates from classify() to the stores. ---- */
 		uint32_t off = 0;               /* bytes in my slab so far (uniform) */
 		int32_t rs_cand = INT_MAX;      /* warp 0: the tile's first pixel at which an op starts = decoder restart point */
 		uint32_t rs_off = 0xFFFFFFFFu;  /* its byte offset in the slab, in the lane that owns the pixel */
 		uint32_t rs_prev = 0;
-		const bool last_tile = px0 + nv == npx;
-#pragma unroll 2
-		for (int s = 0; s < QOI_WARP_ROWS; s++) {
-			const uint32_t rb0 = wbase + (uint32_t)s * 32u;
-			if (rb0 >= nv) break; /* uniform */
-			const uint32_t il = rb0 + lane;
-			const uint32_t v = pix[il], p = pix[(int)il - 1], nx = pix[il + 1];
-			const bool valid = il < nv;
-			const bool nonrun = valid && v != p; /* qoi.h:415 */
-			const uint32_t nr = __ballot_sync(QOI_FULL_MASK, nonrun);
-			const uint32_t vmask = (nv - rb0 >= 32u) ? 0xFFFFFFFFu : ((1u << (nv - rb0)) - 1u);
-			uint32_t size = 0, b0 = 0, b1 = 0;
-			bool opstart = nonrun;
-			if (nr) { /* uniform */
-				const uint32_t h = qoi_slot(v);
-				const uint32_t m = __match_any_sync(QOI_FULL_MASK, nonrun ? h : 64u + lane);
-				const uint32_t lower = m & lt;
-				const uint32_t tv = tin[h];                                              /* index[] as the rows before left it */
-				const uint32_t pv = __shfl_sync(QOI_FULL_MASK, v, 31 - __clz((int)lower)); /* nearest same-slot pixel of this row (garbage if none) */
-				const bool hit = (lower ? pv : tv) == v;                                 /* qoi.h:432 */
-				__syncwarp();
-				if (nonrun && (m & gt) == 0u) tin[h] = v;                                /* qoi.h:436 (a hit stores the value that is there already) */
-				uint32_t cs, c0, c1;
-				classify(v, p, cs, c0, c1);
-				if (nonrun) {
-					size = hit ? 1u : cs;
-					b0 = hit ? h : c0; /* QOI_OP_INDEX | slot, qoi.h:433 */
-					b1 = c1;
+		const uint32_t last_px = px0 + nv == npx ? npx - 1u : 0xFFFFFFFFu; /* the image's last pixel, if it lies in this tile */
+		{
+			const uint32_t *px = pix + wbase + lane;
+			uint32_t gi = px0 + wbase + lane;      /* my pixel's index in the image */
+			int32_t left = (int32_t)nv - (int32_t)wbase; /* valid pixels from this row on */
+			auto row = [&](auto has_nonrun, auto has_run, int s, const uint4 ri, uint32_t vmask) {
+				constexpr bool NR = decltype(has_nonrun)::value, RUN = decltype(has_run)::value;
+				const uint32_t nr = ri.x;
+				const uint32_t v = px[0], p = px[-1];
+				const bool nonrun = (nr & lanebit) != 0u;
+				bool one = false, two = false, four = false, five = false; /* op sizes: 1 | 2 | 4 (+1) */
+				bool opstart = true;
+				uint32_t b0 = 0, b1 = 0;
+				if (NR) {
+					const uint32_t h = qoi_slot(v);
+					bool hit = (ri.y & lanebit) != 0u;
+					if (ri.z) { /* uniform: a slot's first pixel in my chunk -- qoi.h:432 against index[] before the chunk */
+						if ((ri.z & lanebit) && tin[h] == v) hit = true;
+					}
+					const OpClass c = classify(v, p);
+					one = nonrun && (hit || c.diff);
+					two = nonrun && !hit && c.luma;
+					four = nonrun && !hit && !c.diff && !c.luma;
+					five = four && !c.a_eq;
+					b0 = hit ? h : c.b0; /* QOI_OP_INDEX | slot, qoi.h:433 */
+					b1 = c.b1;
 				}
-			}
-			if (nr != vmask) { /* uniform: the row has run pixels (qoi.h:415-421) */
-				const uint32_t below = nr & lt;
-				const int32_t lnr_i = below ? (int32_t)(px0 + rb0 + 31u - (uint32_t)__clz((int)below)) : lnr;
-				const uint32_t gi = px0 + il;
-				const uint32_t r = (gi - (uint32_t)lnr_i - 1u) % 62u; /* (position in the run - 1) % 62 */
-				if (valid && !nonrun) {
+				if (RUN) { /* qoi.h:415-421 */
+					const uint32_t nx = px[1];
+					const uint32_t below = nr & lt;
+					const uint32_t lnr_i = below ? (gi - lane + 31u - (uint32_t)__clz((int)below)) : (uint32_t)lnr;
+					const uint32_t r = (gi - lnr_i - 1u) % 62u; /* (position in the run - 1) % 62 */
+					const bool isrun = !nonrun && (vmask & lanebit) != 0u;
 					/* a byte leaves at run length 62, at the image end, or when the run ends */
-					size = (r == 61u || nx != v || (last_tile && gi == npx - 1u)) ? 1u : 0u;
-					b0 = 0xC0u | r;
-					opstart = r == 0u;
-				}
-			}
-			/* byte offsets inside the row: sizes are 0, 1, 2, 4 or 5 -> three bit planes */
-			const uint32_t s1 = __ballot_sync(QOI_FULL_MASK, size & 1u), s2 = __ballot_sync(QOI_FULL_MASK, size & 2u),
-			               s4 = __ballot_sync(QOI_FULL_MASK, size & 4u);
-			const uint32_t ex = (uint32_t)__popc(s1 & lt) + 2u * (uint32_t)__popc(s2 & lt) + 4u * (uint32_t)__popc(s4 & lt);
-			if (warp == 0 && s < 2 && rs_cand == INT_MAX) { /* a RUN op covers <= 62 pixels: the restart point lies in the first two rows */
-				const uint32_t starts = __ballot_sync(QOI_FULL_MASK, valid && opstart);
-				if (starts) {
-					const uint32_t first = (uint32_t)__ffs((int)starts) - 1u;
-					rs_cand = (int32_t)(rb0 + first);
-					if (lane == first) {
-						rs_off = off + ex;
-						rs_prev = p;
+					if (isrun) {
+						one = r == 61u || nx != v || gi == last_px;
+						b0 = 0xC0u | r;
+						opstart = r == 0u;
 					}
 				}
-			}
-			unsigned char *o = slab + off + ex;
-			if (size) {
-				o[0] = (uint8_t)b0;
-				if (size >= 2u) {
-					o[1] = (uint8_t)b1;
-					if (size >= 4u) {
-						o[2] = (uint8_t)(v >> 8);
-						o[3] = (uint8_t)(v >> 16);
-						if (size == 5u) o[4] = (uint8_t)(v >> 24);
+				/* byte offsets inside the row: sizes are 0, 1, 2, 4 or 5 -> three bit planes */
+				const uint32_t s1 = __ballot_sync(QOI_FULL_MASK, one || five);
+				const uint32_t s2 = NR ? __ballot_sync(QOI_FULL_MASK, two) : 0u;
+				const uint32_t s4 = NR ? __ballot_sync(QOI_FULL_MASK, four) : 0u;
+				const uint32_t ex = (uint32_t)__popc(s1 & lt) + (NR ? 2u * (uint32_t)__popc(s2 & lt) + 4u * (uint32_t)__popc(s4 & lt) : 0u);
+				if (warp == 0 && s < 2 && rs_cand == INT_MAX) { /* a RUN op covers <= 62 pixels: the restart point lies in the first two rows */
+					const uint32_t starts = __ballot_sync(QOI_FULL_MASK, opstart && (vmask & lanebit));
+					if (starts) {
+						const uint32_t first = (uint32_t)__ffs((int)starts) - 1u;
+						rs_cand = (int32_t)((uint32_t)s * 32u + first);
+						if (lane == first) {
+							rs_off = off + ex;
+							rs_prev = p;
+						}
 					}
 				}
+				unsigned char *o = slab + off + ex;
+				if (one || two || four) o[0] = (uint8_t)b0;
+				if (NR) {
+					if (two || four) o[1] = (uint8_t)b1;
+					if (four) o[2] = (uint8_t)(v >> 8);
+					if (four) o[3] = (uint8_t)(v >> 16);
+					if (five) o[4] = (uint8_t)(v >> 24);
+				}
+				off += (uint32_t)__popc(s1) + (NR ? 2u * (uint32_t)__popc(s2) + 4u * (uint32_t)__popc(s4) : 0u);
+				if (NR) lnr = (int32_t)(gi - lane + 31u - (uint32_t)__clz((int)nr));
+			};
+#pragma unroll 1
+			for (int s = 0; s < QOI_WARP_ROWS; s++, px += 32, gi += 32u, left -= 32) {
+				const uint4 ri = rows[s];
+				const uint32_t vmask = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+				if (ri.x == vmask) {
+					if (vmask) row(Yes(), No(), s, ri, vmask); /* every pixel starts an op of its own */
+				} else if (ri.x == 0u) {
+					row(No(), Yes(), s, ri, vmask);
+				} else {
+					row(Yes(), Yes(), s, ri, vmask);
+				}
 			}
-			off += (uint32_t)__popc(s1) + 2u * (uint32_t)__popc(s2) + 4u * (uint32_t)__popc(s4);
-			if (nr) lnr = (int32_t)(px0 + rb0 + 31u - (uint32_t)__clz((int)nr));
-			__syncwarp();
 		}
 		if (lane == 0) wtot[warp] = off;
 		uint8_t *gstream = P.streams + ti->stream_off;

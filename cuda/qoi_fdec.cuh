@@ -724,9 +724,22 @@ __global__ void __launch_bounds__(32) ffix_kernel(const QoiFParams P) {
 	const uint32_t live = P.f.n_live[img];
 	const uint32_t rd = fsel_rd(P) * P.n_images + img;
 	const uint32_t ver = P.f.verified[rd];
-	if (ver >= live) return; /* everything verified (also: rejected or empty stream) */
 	const QoiImgMeta m = P.imgs[img];
 	const uint8_t *s = P.streams + m.stream_off;
+	if (live == 0u) {
+		/* a valid header with no chunk bytes at all: the reference's loop (qoi.h:540-587) never parses an op, every pixel
+		   is the start colour {0,0,0,255} (qoi.h:534-537).  A rejected header leaves the output untouched. */
+		if (stream_ok(m, s, P.lens[img])) {
+			uint8_t *o = P.out + m.dec_off;
+			if (OUT_CH == 4) {
+				for (uint32_t i = lane; i < m.npx; i += 32u) ((uint32_t *)o)[i] = 0xFF000000u;
+			} else {
+				for (uint64_t i = lane; i < (uint64_t)m.npx * 3u; i += 32u) o[i] = 0;
+			}
+		}
+		return;
+	}
+	if (ver >= live) return; /* everything verified */
 	const int32_t stop = P.lens[img] - QOI_END_BYTES;
 	const uintptr_t s_lo = (uintptr_t)s & ~(uintptr_t)3, s_hi = ((uintptr_t)s + (uintptr_t)P.lens[img] + 3u) & ~(uintptr_t)3;
 	const uint32_t base = P.f.seg_base[img];

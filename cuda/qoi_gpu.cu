@@ -44,7 +44,7 @@ struct qoi_gpu_plan {
 	QoiStateLayout layout;
 	QoiImgMeta *d_metas = nullptr;
 	uint32_t *d_tile_img = nullptr;
-	uint32_t *d_tile_order = nullptr;
+	uint64_t *d_tile_order = nullptr;
 	unsigned char *d_state = nullptr;
 	QoiTileState st;
 	uint32_t epoch = 0;
@@ -62,6 +62,20 @@ struct qoi_gpu_plan {
 	/* scratch of the foreign-stream decoder (qoi_fdec.cuh), allocated on first use */
 	unsigned char *d_fstate = nullptr;
 	QoiFLayout flayout;
+};
+
+/* every entry point runs on its context's device and leaves the caller's current device as it found it */
+struct DeviceGuard {
+	int prev = -1;
+	bool changed = false;
+	explicit DeviceGuard(int want) {
+		if (cudaGetDevice(&prev) == cudaSuccess && prev != want) changed = cudaSetDevice(want) == cudaSuccess;
+	}
+	~DeviceGuard() {
+		if (changed) cudaSetDevice(prev);
+	}
+	DeviceGuard(const DeviceGuard &) = delete;
+	DeviceGuard &operator=(const DeviceGuard &) = delete;
 };
 
 #define CK(ctx, call)                                                                         \
@@ -117,13 +131,14 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 	qoi_gpu_ctx *c = new (std::nothrow) qoi_gpu_ctx;
 	if (!c) return QOI_GPU_E_NOMEM;
 	c->device = device;
-	cudaError_t e = cudaSetDevice(device);
+	DeviceGuard guard(device);
+	cudaError_t e = cudaSuccess;
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking);
 	if (e != cudaSuccess) {
-		delete c;
+		qoi_gpu_ctx_destroy(c);
 		return QOI_GPU_E_CUDA;
 	}
 	int rc = enc_occupancy<4, false>(c, &c->enc_blocks_per_sm[0]);
@@ -141,7 +156,7 @@ int qoi_gpu_ctx_create(qoi_gpu_ctx **out, int device) {
 
 void qoi_gpu_ctx_destroy(qoi_gpu_ctx *c) {
 	if (!c) return;
-	cudaSetDevice(c->device);
+	DeviceGuard guard(c->device);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
 	if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -170,15 +185,17 @@ int qoi_gpu_plan_create(qoi_gpu_ctx *ctx, qoi_gpu_plan **out, int n, const qoi_d
 	for (const QoiImgMeta &m : p->geom.metas)
 		if (m.pix_off & 15u) p->pix_off_aligned16 = false;
 	p->layout = qoi_state_layout(p->geom.n_tiles);
-	cudaError_t e = cudaSetDevice(ctx->device);
-	if (e == cudaSuccess) e = cudaMalloc(&p->d_metas, sizeof(QoiImgMeta) * (size_t)n);
+	DeviceGuard guard(ctx->device);
+	cudaError_t e = cudaMalloc(&p->d_metas, sizeof(QoiImgMeta) * (size_t)n);
 	if (e == cudaSuccess) e = cudaMalloc(&p->d_tile_img, sizeof(uint32_t) * (size_t)p->geom.n_tiles);
 	if (e == cudaSuccess) e = cudaMemcpy(p->d_tile_img, p->geom.tile_img.data(), sizeof(uint32_t) * (size_t)p->geom.n_tiles, cudaMemcpyHostToDevice);
-	if (e == cudaSuccess) e = cudaMalloc(&p->d_tile_order, sizeof(uint32_t) * (size_t)p->geom.n_tiles);
-	if (e == cudaSuccess) e = cudaMemcpy(p->d_tile_order, p->geom.tile_order.data(), sizeof(uint32_t) * (size_t)p->geom.n_tiles, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMalloc(&p->d_tile_order, sizeof(uint64_t) * (size_t)p->geom.n_tiles);
+	if (e == cudaSuccess) e = cudaMemcpy(p->d_tile_order, p->geom.tile_order.data(), sizeof(uint64_t) * (size_t)p->geom.n_tiles, cudaMemcpyHostToDevice);
 	if (e == cudaSuccess) e = cudaMalloc(&p->d_state, p->layout.total);
 	if (e == cudaSuccess) e = cudaMemset(p->d_state, 0, p->layout.total);
 	if (e == cudaSuccess) e = cudaMemcpy(p->d_metas, p->geom.metas.data(), sizeof(QoiImgMeta) * (size_t)n, cudaMemcpyHostToDevice);
+	/* the copies above ran on the legacy stream; the kernels run on non-blocking streams that are not ordered against it */
+	if (e == cudaSuccess) e = cudaDeviceSynchronize();
 	if (e != cudaSuccess) {
 		snprintf(ctx->err, sizeof ctx->err, "plan allocation: %s", cudaGetErrorString(e));
 		qoi_gpu_plan_destroy(p);
@@ -191,7 +208,7 @@ int qoi_gpu_plan_create(qoi_gpu_ctx *ctx, qoi_gpu_plan **out, int n, const qoi_d
 
 void qoi_gpu_plan_destroy(qoi_gpu_plan *p) {
 	if (!p) return;
-	cudaSetDevice(p->ctx->device);
+	DeviceGuard guard(p->ctx->device);
 	cudaFree(p->d_metas);
 	cudaFree(p->d_tile_img);
 	cudaFree(p->d_fstate);
@@ -215,7 +232,7 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 	if (!p || !d_pixels || !d_streams || !d_lens) return QOI_GPU_E_ARG;
 	qoi_gpu_ctx *ctx = p->ctx;
 	cudaStream_t s = (cudaStream_t)cuda_stream;
-	CK(ctx, cudaSetDevice(ctx->device));
+	DeviceGuard guard(ctx->device);
 	if (++p->epoch >= (1u << 30) - 1u) { /* status words carry a 30-bit epoch */
 		CK(ctx, cudaMemsetAsync(p->d_state, 0, p->layout.total, s));
 		p->epoch = 1;
@@ -248,19 +265,22 @@ int qoi_gpu_encode(qoi_gpu_plan *p, const void *d_pixels, void *d_streams, int32
 int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens, void *d_decoded, int use_index,
                    int32_t *d_status, void *cuda_stream) {
 	if (!p || !d_streams || !d_lens || !d_decoded) return QOI_GPU_E_ARG;
-	if (use_index && p->epoch == 0) return QOI_GPU_E_ARG; /* no encode has written the index yet */
+	/* the restart index must be the one the last encode of THESE streams left in THIS plan (qoi_gpu_encode, or an index
+	   imported with qoi_gpu_index_import); qoi_gpu_encode_host leaves it in the chunk sub-plans instead */
+	if (use_index && p->index_owner != 1) return QOI_GPU_E_ARG;
 	qoi_gpu_ctx *ctx = p->ctx;
 	cudaStream_t s = (cudaStream_t)cuda_stream;
-	CK(ctx, cudaSetDevice(ctx->device));
+	DeviceGuard guard(ctx->device);
 	if (!use_index) {
 		/* any stream: exact parse scan, speculative segment decode, verification, exact fix-up (qoi_fdec.cuh) */
 		static_assert(QOI_FSEG_BYTES_HOST == QOI_FSEG_BYTES, "segment size");
 		if (!p->d_fstate) {
 			p->flayout = qoi_fstate_layout(p->geom);
 			CK(ctx, cudaMalloc(&p->d_fstate, p->flayout.total));
-			CK(ctx, cudaMemset(p->d_fstate, 0, p->flayout.total));
-			CK(ctx, cudaMemcpy(p->d_fstate + p->flayout.off[0], p->flayout.seg_base.data(), p->flayout.seg_base.size() * sizeof(uint32_t),
-			                   cudaMemcpyHostToDevice));
+			/* on the launching stream, so that the kernels below are ordered behind the initialisation (seg_base lives in the plan) */
+			CK(ctx, cudaMemsetAsync(p->d_fstate, 0, p->flayout.total, s));
+			CK(ctx, cudaMemcpyAsync(p->d_fstate + p->flayout.off[0], p->flayout.seg_base.data(), p->flayout.seg_base.size() * sizeof(uint32_t),
+			                        cudaMemcpyHostToDevice, s));
 		}
 		qoifdec::QoiFParams F;
 		memset(&F, 0, sizeof F);
@@ -350,28 +370,46 @@ static int plan_chunks(qoi_gpu_plan *p) {
 		descs[(size_t)i].channels = m.channels; descs[(size_t)i].colorspace = m.colorspace;
 		po[(size_t)i] = m.pix_off; so[(size_t)i] = m.stream_off; dof[(size_t)i] = m.dec_off;
 	}
-	for (int c = 0; c < k; c++) {
+	/* built into locals and committed only when every piece exists: a half-built list would be taken for complete by the next call */
+	std::vector<qoi_gpu_plan *> subs;
+	std::vector<int> firsts;
+	std::vector<cudaEvent_t> e_in, e_k;
+	int rc = QOI_GPU_OK;
+	for (int c = 0; c < k && !rc; c++) {
 		const int first = (int)((int64_t)n * c / k), last = (int)((int64_t)n * (c + 1) / k);
 		qoi_gpu_plan *sub = nullptr;
-		int rc = qoi_gpu_plan_create(ctx, &sub, last - first, descs.data() + first, po.data() + first, so.data() + first, dof.data() + first,
-		                             p->geom.dec_channels);
-		if (rc) return rc;
-		p->chunks.push_back(sub);
-		p->chunk_first.push_back(first);
-		cudaEvent_t e1, e2;
-		CK(ctx, cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-		CK(ctx, cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-		p->ev_in.push_back(e1);
-		p->ev_k.push_back(e2);
+		rc = qoi_gpu_plan_create(ctx, &sub, last - first, descs.data() + first, po.data() + first, so.data() + first, dof.data() + first,
+		                         p->geom.dec_channels);
+		if (rc) break;
+		subs.push_back(sub);
+		firsts.push_back(first);
+		cudaEvent_t e1 = nullptr, e2 = nullptr;
+		if (cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess) {
+			if (e1) cudaEventDestroy(e1);
+			rc = QOI_GPU_E_CUDA;
+			break;
+		}
+		e_in.push_back(e1);
+		e_k.push_back(e2);
 	}
-	p->chunk_first.push_back(n);
+	if (rc) {
+		for (qoi_gpu_plan *sp : subs) qoi_gpu_plan_destroy(sp);
+		for (cudaEvent_t e : e_in) cudaEventDestroy(e);
+		for (cudaEvent_t e : e_k) cudaEventDestroy(e);
+		return rc;
+	}
+	firsts.push_back(n);
+	p->chunks.swap(subs);
+	p->chunk_first.swap(firsts);
+	p->ev_in.swap(e_in);
+	p->ev_k.swap(e_k);
 	return QOI_GPU_OK;
 }
 
 int qoi_gpu_encode_host(qoi_gpu_plan *p, const void *h_pixels, void *h_streams, int32_t *h_lens) {
 	if (!p || !h_pixels || !h_streams || !h_lens) return QOI_GPU_E_ARG;
 	qoi_gpu_ctx *ctx = p->ctx;
-	CK(ctx, cudaSetDevice(ctx->device));
+	DeviceGuard guard(ctx->device);
 	int rc = plan_mirrors(p);
 	if (!rc) rc = plan_chunks(p);
 	if (rc) return rc;
@@ -413,7 +451,7 @@ int qoi_gpu_decode_host(qoi_gpu_plan *p, const void *h_streams, const int32_t *h
 	if (!p || !h_streams || !h_lens || !h_decoded) return QOI_GPU_E_ARG;
 	if (use_index && p->index_owner == 0) return QOI_GPU_E_ARG;
 	qoi_gpu_ctx *ctx = p->ctx;
-	CK(ctx, cudaSetDevice(ctx->device));
+	DeviceGuard guard(ctx->device);
 	int rc = plan_mirrors(p);
 	if (!rc) rc = plan_chunks(p);
 	if (rc) return rc;
@@ -511,6 +549,7 @@ void *qoi_encode(const void *data, const qoi_desc *desc, int *out_len) {
 	std::lock_guard<std::mutex> lock(g_mu);
 	qoi_gpu_ctx *ctx = global_ctx();
 	if (!ctx) return NULL;
+	DeviceGuard guard(ctx->device);
 	qoi_gpu_plan *p = global_plan(ctx, &d, d.channels);
 	if (!p || plan_mirrors(p)) return NULL;
 	cudaStream_t s = ctx->stream;
@@ -548,6 +587,7 @@ void *qoi_decode(const void *data, int size, qoi_desc *desc, int channels) {
 	std::lock_guard<std::mutex> lock(g_mu);
 	qoi_gpu_ctx *ctx = global_ctx();
 	if (!ctx) return NULL;
+	DeviceGuard guard(ctx->device);
 	qoi_gpu_plan *p = global_plan(ctx, &d, out_ch);
 	if (!p || plan_mirrors(p)) return NULL;
 	cudaStream_t s = ctx->stream;

@@ -37,7 +37,7 @@ static inline size_t qoi_max_foreign_stream(const QoiDescPOD &d) {
 struct QoiPlanGeom {
 	std::vector<QoiImgMeta> metas;
 	std::vector<uint32_t> tile_img; /* image index of every tile */
-	std::vector<uint32_t> tile_order; /* ticket -> tile (round robin over the images, ascending inside an image) */
+	std::vector<uint64_t> tile_order; /* ticket -> tile | image << 32 (round robin over the images, ascending inside an image) */
 	uint32_t n_tiles = 0;
 	uint64_t total_px = 0;
 	int channels = 0;
@@ -99,7 +99,7 @@ static inline int qoi_plan_geometry(QoiPlanGeom &g, int n, const QoiDescPOD *des
 		}
 		for (uint32_t k = 0; k < max_tiles; k++)
 			for (int i = 0; i < n; i++)
-				if (k < nts[(size_t)i]) g.tile_order.push_back(g.metas[(size_t)i].first_tile + k);
+				if (k < nts[(size_t)i]) g.tile_order.push_back((uint64_t)(g.metas[(size_t)i].first_tile + k) | ((uint64_t)(uint32_t)i << 32));
 	}
 	return 0;
 }

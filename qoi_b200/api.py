@@ -109,6 +109,9 @@ def encode(pixels, desc):
     """qoi_encode (reference qoi.h:278): pixels = uint8 array / bytes of w*h*channels; returns bytes or None."""
     buf = np.ascontiguousarray(np.frombuffer(pixels, dtype=np.uint8) if isinstance(pixels, (bytes, bytearray)) else pixels,
                                dtype=np.uint8)
+    # the C function trusts the pointer (it has no length argument, qoi.h:278): refuse a short buffer here
+    if 3 <= desc.channels <= 4 and buf.size < desc.width * desc.height * desc.channels:
+        raise ValueError(f"pixel buffer holds {buf.size} bytes, the desc needs {desc.width * desc.height * desc.channels}")
     n = C.c_int(0)
     p = lib().qoi_encode(buf.ctypes.data, C.byref(desc), C.byref(n))
     if not p:
@@ -221,28 +224,15 @@ def _addr(x):
 
 
 def pinned_array(nbytes):
-    """uint8 numpy view over pinned host memory from qoi_gpu_host_alloc (kept alive by the returned array's base)."""
+    """uint8 numpy array over pinned host memory from qoi_gpu_host_alloc.  The memory is released when the array (and
+    every view of it) has been garbage collected: the ctypes buffer the array is built on carries a finalizer."""
+    import weakref
+
     p = lib().qoi_gpu_host_alloc(nbytes)
     if not p:
         raise QoiGpuError("qoi_gpu_host_alloc failed")
     buf = (C.c_ubyte * nbytes).from_address(p)
+    weakref.finalize(buf, lib().qoi_gpu_host_free, p)  # numpy keeps `buf` alive as the base of the array and its views
     arr = np.frombuffer(buf, dtype=np.uint8)
-
-    class _Owner:
-        def __init__(self, ptr, keep):
-            self.ptr, self.keep = ptr, keep
-
-        def __del__(self):
-            try:
-                lib().qoi_gpu_host_free(self.ptr)
-            except Exception:
-                pass
-
-    arr_owner = _Owner(p, buf)
-    arr = arr.view()
     arr.flags.writeable = True
-    _PINNED_OWNERS[arr.ctypes.data] = arr_owner
     return arr
-
-
-_PINNED_OWNERS = {}

@@ -78,6 +78,8 @@ def test_emulated_foreign_decode(emu, cpu):
         assert r.returncode == 0 and r.stdout.startswith("PASS"), str(env_extra) + r.stdout + r.stderr[-2000:]
 
     small = [q.foreign_stream(rng, 900, 4, w=30, h=30, truncate=(i % 4 == 0)) for i in range(40)]
+    # header + end marker only, and a single op byte: no live segment / one tiny segment (qoi.h:540-587 fills with the colour)
+    small += [q.header(30, 30, 4) + ops + q.END_MARK for ops in (b"", b"\x37", b"\xfe\x05\x06\x07", b"\xc5")]
     run(small, 30, 30, {})
     run(small, 30, 30, {"QOI_EMU_REFILL": "lane"})
     # streams of many segments (random op soup: the speculation rarely holds, the fix-up does the work), with

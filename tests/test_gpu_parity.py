@@ -129,6 +129,16 @@ def test_foreign_streams(gpu, cpu):
             pa, da = chk.decode(s, c)
             pb, db = qb.decode(s, c)
             assert pb is not None and (pa == pb).all() and bytes(da) == bytes(db), (it, c)
+    # a valid header with no chunk bytes at all, and with a single op: every pixel is the start colour / that op's colour
+    # (qoi.h:540-587 never parses past size - 8); a previous decode must not shine through
+    for (w, h, ch) in [(30, 30, 4), (30, 30, 3), (7, 1, 4)]:
+        qb.decode(q.foreign_stream(rng, w * h, ch, w=w, h=h), 4)  # leaves other pixels in the cached plan's output buffer
+        for ops in (b"", b"\x37", b"\xfe\x05\x06\x07", b"\xc5"):
+            s = q.header(w, h, ch) + ops + q.END_MARK
+            for c in (0, 3, 4):
+                pa, da = chk.decode(s, c)
+                pb, db = qb.decode(s, c)
+                assert pa is not None and pb is not None and (pa == pb).all() and bytes(da) == bytes(db), (w, h, ch, ops, c)
     # arbitrary bytes after a valid header never crash and match the reference (the qoifuzz.c contract)
     for it in range(60):
         body = bytes(rng.integers(0, 256, size=int(rng.integers(9, 400)), dtype=np.uint8))

@@ -112,6 +112,20 @@ def test_oracle_equals_reference_on_foreign_streams(cpu):
             assert pa is not None and (pa == pb).all() and bytes(da) == bytes(db), it
 
 
+@needs_ref
+def test_oracle_equals_reference_on_header_only_streams(cpu):
+    """a valid header with zero or one op: qoi.h:540-587 fills the image with the start colour / that op's colour"""
+    for (w, h, ch) in [(30, 30, 4), (30, 30, 3), (1, 1, 4)]:
+        for ops in (b"", b"\x37", b"\xfe\x05\x06\x07", b"\xc5"):
+            s = q.header(w, h, ch) + ops + q.END_MARK
+            for c in (0, 3, 4):
+                pa, da = cpu.ref.decode(s, c)
+                pb, db = cpu.oracle.decode(s, c)
+                assert pa is not None and (pa == pb).all() and bytes(da) == bytes(db), (w, h, ch, ops, c)
+    pa, _ = cpu.ref.decode(q.header(3, 1, 4) + q.END_MARK, 4)
+    assert pa.tolist() == [0, 0, 0, 255] * 3
+
+
 def test_roundtrip_configs0(cpu):
     """BASELINE.json configs[0]: 256x256 RGBA encode -> decode round trip on the CPU, bit exact (qoibench.c:410-417)."""
     img = cpu.image(256, 256, 4, 4)
