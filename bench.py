@@ -5,7 +5,7 @@ Metric (BASELINE.json): Gpixels/s of an encode + decode round trip over a batch 
 4096x4096 RGBA images, per-GPU batch fixed (weak scaling), 1/2/4/8 GPUs, next to the fraction of the
 HBM roofline of the dominant kernel and the reference qoi.h timed on the host cores.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--dist D] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config headline|1080p_rgb_1024|8192_rgba_32|sweep] [--batch B] [--dist D] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One JSON line on stdout (rank 0).  A "step" = qoi_gpu_encode of the whole batch followed by
@@ -29,9 +29,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "Gpixels/s encode+decode round trip, 4096x4096 RGBA batch"
+# BASELINE.json configs that are bench lines here (the others are parity-test cases): name -> (w, h, channels, images per GPU)
+CONFIGS = {
+    "headline": (4096, 4096, 4, 32),          # the configuration the metric is quoted on
+    "1080p_rgb_1024": (1920, 1080, 3, 1024),  # configs[2]: batch of 1024 synthetic 1920x1080 RGB images, decode to 4 channels
+    "8192_rgba_32": (8192, 8192, 4, 32),      # configs[3] per-GPU share: 256 x 8192x8192 RGBA over 8 GPUs
+}
+SWEEP_SIZES = [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]  # configs[4]: size sweep x channels 3/4
 W = H = 4096
 CH = 4
-METRIC = "Gpixels/s encode+decode round trip, 4096x4096 RGBA batch"
 DIST_NAMES = ["noise_rgba", "noise_opaque", "gradient", "grad2", "photo", "tiles32", "palette16", "const0"]
 
 
@@ -79,6 +86,10 @@ def load_cpu_codec():
 
 class DescC(C.Structure):
     _fields_ = [("width", C.c_uint), ("height", C.c_uint), ("channels", C.c_ubyte), ("colorspace", C.c_ubyte)]
+
+
+def workload_name(n):
+    return f"{n} x {W}x{H} {'RGBA' if CH == 4 else 'RGB'} per GPU, encode+decode round trip (decode to 4 channels)"
 
 
 def cpu_round_trip(eb, db, threads, pixels, n, keep_streams, keep_lens, slot):
@@ -164,7 +175,8 @@ def measured_peak():
 
 
 def recorded_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists."""
+    """dram bytes per launch of the two kernels from the committed ncu capture (a RECORDED value of the headline workload,
+    not a measurement of this run: bench.py never runs under a profiler)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
@@ -174,13 +186,64 @@ def recorded_traffic():
     return None
 
 
+def pcie_ceiling(torch, nbytes=1 << 30):
+    """bare pinned cudaMemcpyAsync of nbytes: host->device alone, device->host alone, both at once (GB/s per direction).
+    The e2e leg moves the same bytes both ways at the same time; this is its ceiling on this box."""
+    try:
+        h_a = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        h_b = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        d_a = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        d_b = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def timed(fn, reps=3):
+            fn(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps
+
+        def h2d():
+            with torch.cuda.stream(s1):
+                d_a.copy_(h_a, non_blocking=True)
+
+        def d2h():
+            with torch.cuda.stream(s2):
+                h_b.copy_(d_b, non_blocking=True)
+
+        def both():
+            h2d(); d2h()
+
+        t1, t2, t3 = timed(h2d), timed(d2h), timed(both)
+        return {"h2d_gbs": nbytes / t1 / 1e9, "d2h_gbs": nbytes / t2 / 1e9, "both_gbs_per_direction": nbytes / t3 / 1e9, "bytes": nbytes}
+    except Exception as e:  # an extra; never let it stop the line
+        return {"error": repr(e)}
+
+
+def config_dict(args, world):
+    """identical in both arms (the driver compares them): only what follows from the command line"""
+    n = args.batch
+    pixel_bytes = n * W * H * CH
+    return {"workload": workload_name(n), "name": args.config, "width": W, "height": H, "channels": CH, "batch_per_gpu": n,
+            "global_batch": n * world, "distribution": DIST_NAMES[args.dist], "decode_channels": 4,
+            "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
+            "l2": (f"inputs {pixel_bytes >> 20} MiB per GPU per step, larger than the 126 MB L2 (no flush needed)" if pixel_bytes > (126 << 20)
+                   else "inputs smaller than L2: a 256 MiB buffer is written between timed steps (outside the step's events)"),
+            "decode_path": "segment-parallel with the encoder's restart index (side table, 0.13 B/px, outside the bit-exact stream); "
+                           "roofline.decode_foreign is the any-stream path"}
+
+
 def run_reference_arm(args, rank, world):
     """--impl reference: the reference's CPU implementation on the host cores, all threads, same config."""
     if rank != 0:
         return
     kind, eb, db, threads = load_cpu_codec()
     synth = load_synth()
-    n = max(args.batch, threads)  # images are the only parallel axis of qoi.h: give every host thread one
+    # images are the only parallel axis of qoi.h: give every host thread one; bounded so that a step stays within seconds
+    n = max(min(args.batch, 2 * threads), threads)
+    while n > threads and n * W * H > (1 << 32):
+        n -= 1
     pixels = np.empty(n * W * H * CH, dtype=np.uint8)
     synth.qoi_synth_batch(pixels.ctypes.data, W * H * CH, n, W, H, CH, args.dist, 0)
     slot = W * H * (CH + 1) + 22
@@ -196,14 +259,14 @@ def run_reference_arm(args, rank, world):
     total = t_enc + t_dec
     px = n * W * H * args.steps
     value = px / total / 1e9
-    sample = (f"{n} x {W}x{H} RGBA images per step (max(per-GPU batch, host threads)), OpenMP over images, "
+    sample = (f"{n} x {W}x{H}x{CH} images per step (a bounded sample of the workload: host threads, at most the per-GPU batch "
+              f"if that is larger), OpenMP over images, "
               "malloc+free inside the call as qoibench.c:446-450,471-481")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gpx/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{W}x{H} RGBA batch, encode+decode round trip", "batch_per_gpu": args.batch,
-                   "distribution": DIST_NAMES[args.dist], "decode_channels": 4},
+        "config": config_dict(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": "Gpx/s", "cores": threads, "kind": kind, "sample": sample,
                          "encode_gpx": px / t_enc / 1e9, "decode_gpx": px / t_dec / 1e9},
         "e2e": {"value": value, "unit": "Gpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -239,7 +302,7 @@ def c_api_single_image(h_pix, args):
 
     sp = c_encode()                          # first calls build the cached plan and its scratch (untimed)
     libc.free(c_decode(sp))
-    reps = 3
+    reps = 5
     t0 = time.perf_counter()
     for _ in range(reps):
         libc.free(sp)
@@ -253,14 +316,15 @@ def c_api_single_image(h_pix, args):
     back = np.frombuffer(C.string_at(q, W * H * 4), dtype=np.uint8)
     libc.free(q)
     libc.free(sp)
-    if not np.array_equal(back, one):
+    same = np.array_equal(back, one) if CH == 4 else np.array_equal(back.reshape(-1, 4)[:, :3], one.reshape(-1, 3))
+    if not same:
         raise RuntimeError("C API round trip mismatch")
     kind1, eb1, db1, _t = load_cpu_codec()
     k1 = np.empty(W * H * (CH + 1) + 22, dtype=np.uint8)
     l1 = np.zeros(1, dtype=np.int32)
     cpu_round_trip(eb1, db1, 1, one, 1, k1, l1, k1.size)
     te1, td1 = cpu_round_trip(eb1, db1, 1, one, 1, k1, l1, k1.size)
-    c_api = {"image": f"{W}x{H} RGBA {DIST_NAMES[args.dist]}", "qoi_encode_ms": 1e3 * (t1 - t0) / reps,
+    c_api = {"image": f"{W}x{H}x{CH} {DIST_NAMES[args.dist]}", "qoi_encode_ms": 1e3 * (t1 - t0) / reps,
              "qoi_decode_ms": 1e3 * (t2 - t1) / reps, "cpu_kind": kind1, "cpu_qoi_encode_ms": 1e3 * te1,
              "cpu_qoi_decode_ms": 1e3 * td1,
              "note": "single calls of the reference API, host pointers in and out, copies and the any-stream decoder inside"}
@@ -297,42 +361,19 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU (weak scaling)")
-    ap.add_argument("--dist", type=int, default=4, help="synthetic distribution id (4 = photo, headline)")
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+def set_workload(w, h, ch):
+    global W, H, CH
+    W, H, CH = w, h, ch
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    if args.impl == "reference":
-        run_reference_arm(args, rank, world)
-        return
-
-    import torch
-
+def run_b200(args, rank, world, local_rank, torch, dist, emit=True):
+    """one workload on this rank's GPU; rank 0 returns (and prints) the JSON line"""
     import qoi_b200
     from qoi_b200.api import pinned_array
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
-    torch.cuda.set_device(local_rank)
+    dist_on = world > 1
     full_affinity = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa_node(local_rank)  # before the context and the pinned buffers exist
-    dist_on = world > 1
-    if dist_on:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
     n = args.batch
     img_bytes = W * H * CH
     synth = load_synth()
@@ -351,8 +392,12 @@ def main():
     d_lens = torch.zeros(n, dtype=torch.int32, device="cuda")
     d_dec = torch.empty(plan.decoded_bytes, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
+    small = plan.pixel_bytes <= (126 << 20)  # inputs fit into L2: flush between timed steps
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if small else None
 
     def step(events=None):
+        if flush is not None:
+            flush.fill_(1)
         if events is not None:
             events[0].record()
         plan.encode(d_pix.data_ptr(), d_streams.data_ptr(), d_lens.data_ptr(), stream)
@@ -367,12 +412,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def decoded_equals_input():
+        if CH == 4:
+            return torch.equal(d_dec, d_pix)
+        a = d_dec.view(-1, 4)
+        return bool((a[:, :3] == d_pix.view(-1, 3)).all()) and bool((a[:, 3] == 255).all())
+
     sampler = ClockSampler(local_rank) if rank == 0 else None  # started early, cut to the timed window later
     # ---- warm-up + correctness of the round trip (untimed)
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    if not torch.equal(d_dec, d_pix):
+    if not decoded_equals_input():
         raise SystemExit("round trip mismatch: decode(encode(x)) != x")
     lens = d_lens.cpu().numpy().astype(np.int64)
     enc_bytes = int(lens.sum())
@@ -394,30 +445,35 @@ def main():
     launches = qoi_b200.launch_count() - launches0
     wall_end = time.time()
     clocks = sampler.stop(wall_begin, wall_end) if sampler else None
-    total_ms = t_start.elapsed_time(t_stop)
     enc_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     dec_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    total_ms = t_start.elapsed_time(t_stop) if flush is None else (enc_ms + dec_ms) * args.steps  # the L2 flush is not part of a step
 
     # ---- e2e: same step through the host-buffer C ABI, pinned host memory, copies inside
-    h_streams = pinned_array(plan.stream_bytes)
-    h_lens = np.zeros(n, dtype=np.int32)
-    h_dec = pinned_array(plan.decoded_bytes)
+    e2e_s, h2d, d2h = None, 0, 0
+    h_streams = h_lens = None
+    if args.e2e_steps > 0:
+        h_streams = pinned_array(plan.stream_bytes)
+        h_lens = np.zeros(n, dtype=np.int32)
+        h_dec = pinned_array(plan.decoded_bytes)
 
-    def e2e_step():
-        plan.encode_host(h_pix, h_streams, h_lens)
-        plan.decode_host(h_streams, h_lens, h_dec, use_index=True)
+        def e2e_step():
+            plan.encode_host(h_pix, h_streams, h_lens)
+            plan.decode_host(h_streams, h_lens, h_dec, use_index=True)
 
-    e2e_step()
-    if not np.array_equal(h_dec, h_pix):
-        raise SystemExit("e2e round trip mismatch")
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
         e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    h2d = plan.pixel_bytes + enc_bytes + 4 * n
-    d2h = enc_bytes + plan.decoded_bytes + 4 * n
+        ok = np.array_equal(h_dec, h_pix) if CH == 4 else (np.array_equal(h_dec.reshape(-1, 4)[:, :3], h_pix.reshape(-1, 3)))
+        if not ok:
+            raise SystemExit("e2e round trip mismatch")
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        h2d = plan.pixel_bytes + enc_bytes + 4 * n
+        d2h = enc_bytes + plan.decoded_bytes + 4 * n
+        del h_dec
 
     # ---- foreign-stream decode (no restart index, the path qoi_decode of the C API takes): reported beside the headline, not part of it
     fe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -427,16 +483,34 @@ def main():
     fe[1].record()
     torch.cuda.synchronize()
     foreign_ms = fe[0].elapsed_time(fe[1])
+    if not decoded_equals_input():
+        raise SystemExit("any-stream decode mismatch")
+
+    # ---- N > 1: every rank checks one of ITS streams against the CPU codec (sharding must not change bytes)
+    shard_ok = 1.0
+    if dist_on:
+        kind_, eb_, db_, _t = load_cpu_codec()
+        k1 = np.empty(W * H * (CH + 1) + 22, dtype=np.uint8)
+        l1 = np.zeros(1, dtype=np.int32)
+        pick = (rank * 7) % n
+        one = np.ascontiguousarray(h_pix[pick * img_bytes:(pick + 1) * img_bytes])
+        cpu_round_trip(eb_, db_, 1, one, 1, k1, l1, k1.size)
+        o = int(plan.stream_off[pick])
+        got = d_streams[o:o + int(l1[0])].cpu().numpy()
+        shard_ok = 1.0 if (int(lens[pick]) == int(l1[0]) and np.array_equal(got, k1[:int(l1[0])])) else 0.0
 
     # ---- max over ranks
-    vals = torch.tensor([total_ms, enc_ms, dec_ms, e2e_s * 1e3, foreign_ms], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([total_ms, enc_ms, dec_ms, (e2e_s or 0.0) * 1e3, foreign_ms, 1.0 - shard_ok], dtype=torch.float64, device="cuda")
     sums = torch.tensor([float(enc_bytes), float(launches)], dtype=torch.float64, device="cuda")
     if dist_on:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)  # sizes exchange (the only collective; outside the timed region)
-    total_ms, enc_ms, dec_ms, e2e_ms, foreign_ms = [float(x) for x in vals.tolist()]
+    total_ms, enc_ms, dec_ms, e2e_ms, foreign_ms, shard_bad = [float(x) for x in vals.tolist()]
     enc_bytes_all, launches_all = [float(x) for x in sums.tolist()]
+    if shard_bad:
+        raise SystemExit("a rank's stream differs from the CPU codec's (sharding changed bytes)")
 
+    line = None
     if rank == 0:
         px_all = px_rank * world
         ms_per_step = total_ms / args.steps
@@ -446,17 +520,23 @@ def main():
         dec_alg = enc_bytes + px_rank * 4           # bytes one decode launch must move (read e B/px + write 4 B/px)
         enc_gbs = enc_alg / (enc_ms * 1e-3) / 1e9
         dec_gbs = dec_alg / (dec_ms * 1e-3) / 1e9
+        rt_gbs = (enc_alg + dec_alg) / ((enc_ms + dec_ms) * 1e-3) / 1e9
+        for_gbs = dec_alg / (foreign_ms * 1e-3) / 1e9
         dominant = "decode" if dec_ms >= enc_ms else "encode"
-        traffic = recorded_traffic()
+        traffic = recorded_traffic() if args.config == "headline" else None
+        tsrc = "recorded profiles/traffic.json (ncu --set full of the headline workload; not measured in this run)" if traffic else None
         roofline = {
-            "bound": "hbm", "kernel": "qoi_decode_kernel<4,128>" if dominant == "decode" else "qoi_encode_kernel<4,false>",
+            "bound": "hbm", "kernel": "qoi_decode_kernel<4,128>" if dominant == "decode" else f"qoi_encode_kernel<{CH},{'false' if CH == 4 else 'true'}>",
             "achieved": dec_gbs if dominant == "decode" else enc_gbs, "peak": peak, "unit": "GB/s",
             "frac": (dec_gbs if dominant == "decode" else enc_gbs) / peak, "peak_source": peak_src,
-            "traffic": (traffic or {}).get(dominant),
+            "traffic": (traffic or {}).get(dominant), "traffic_source": tsrc,
             "encode": {"ms": enc_ms, "achieved": enc_gbs, "frac": enc_gbs / peak, "algorithmic_bytes": enc_alg,
                        "gpx_per_s": px_rank / (enc_ms * 1e-3) / 1e9, "traffic": (traffic or {}).get("encode")},
             "decode": {"ms": dec_ms, "achieved": dec_gbs, "frac": dec_gbs / peak, "algorithmic_bytes": dec_alg,
                        "gpx_per_s": px_rank / (dec_ms * 1e-3) / 1e9, "traffic": (traffic or {}).get("decode")},
+            "round_trip": {"ms": enc_ms + dec_ms, "achieved": rt_gbs, "frac": rt_gbs / peak, "algorithmic_bytes": enc_alg + dec_alg},
+            "decode_foreign": {"ms": foreign_ms, "achieved": for_gbs, "frac": for_gbs / peak, "gpx_per_s": px_rank / (foreign_ms * 1e-3) / 1e9,
+                               "note": "same streams decoded WITHOUT the restart index: the path qoi_decode / qoi_read take (cuda/qoi_fdec.cuh)"},
         }
         cpu_baseline = None
         try:
@@ -466,44 +546,120 @@ def main():
         if world == 1 and not args.no_cpu:
             kind, eb, db, threads = load_cpu_codec()
             slot = W * H * (CH + 1) + 22
-            keep = np.empty(n * slot, dtype=np.uint8)
-            klens = np.zeros(n, dtype=np.int32)
-            cpu_round_trip(eb, db, threads, h_pix, min(n, threads), keep, klens, slot)  # first-touch warm-up
-            te, td = cpu_round_trip(eb, db, threads, h_pix, n, keep, klens, slot)
-            ok = all(np.array_equal(keep[i * slot:i * slot + int(klens[i])], h_streams[int(plan.stream_off[i]):int(plan.stream_off[i]) + int(klens[i])]) for i in range(n))
-            if not ok or not np.array_equal(klens, h_lens):
+            # a bounded sample: one image per host thread (images are qoi.h's only parallel axis), at most the batch
+            m = min(n, threads)
+            keep = np.empty(m * slot, dtype=np.uint8)
+            klens = np.zeros(m, dtype=np.int32)
+            cpu_round_trip(eb, db, threads, h_pix, m, keep, klens, slot)  # first-touch warm-up
+            te, td = cpu_round_trip(eb, db, threads, h_pix, m, keep, klens, slot)
+            gpu_streams = d_streams.cpu().numpy()
+            ok = all(int(lens[i]) == int(klens[i]) and
+                     np.array_equal(keep[i * slot:i * slot + int(klens[i])], gpu_streams[int(plan.stream_off[i]):int(plan.stream_off[i]) + int(klens[i])])
+                     for i in range(m))
+            if not ok:
                 raise SystemExit("GPU streams differ from the CPU codec's")
-            cpu_baseline = {"value": px_rank / (te + td) / 1e9, "unit": "Gpx/s", "cores": min(threads, n), "kind": kind,
-                            "sample": f"{n} x {W}x{H} RGBA images, one encode+decode pass, OpenMP over images; GPU streams verified identical",
-                            "encode_gpx": px_rank / te / 1e9, "decode_gpx": px_rank / td / 1e9}
+            # column A of BASELINE.md section 3: one thread, one image
+            k1 = np.empty(slot, dtype=np.uint8)
+            l1 = np.zeros(1, dtype=np.int32)
+            cpu_round_trip(eb, db, 1, h_pix, 1, k1, l1, slot)
+            te1, td1 = cpu_round_trip(eb, db, 1, h_pix, 1, k1, l1, slot)
+            cpu_baseline = {"value": m * W * H / (te + td) / 1e9, "unit": "Gpx/s", "cores": min(threads, m), "kind": kind,
+                            "sample": f"{m} x {W}x{H}x{CH} images (one per host thread, at most the batch), one encode+decode pass after a warm-up pass, "
+                                      "OpenMP over images, malloc+free inside the call (qoibench.c:446-450,471-481); GPU streams of these images verified identical",
+                            "encode_gpx": m * W * H / te / 1e9, "decode_gpx": m * W * H / td / 1e9,
+                            "single_thread": {"value": W * H / (te1 + td1) / 1e9, "encode_gpx": W * H / te1 / 1e9, "decode_gpx": W * H / td1 / 1e9,
+                                              "sample": "one image, one thread"}}
         try:
             c_api = c_api_single_image(h_pix, args) if (world == 1 and not args.no_cpu) else None
         except Exception as e:  # the headline line must not depend on this extra
             c_api = {"error": repr(e)}
-        knobs = {k: v for k, v in os.environ.items() if k.startswith("QOI_GPU_")}  # A/B switches in effect (none by default)
+        pcie = pcie_ceiling(torch) if (args.e2e_steps > 0 and not args.no_pcie) else None
+        knobs = {k: v for k, v in os.environ.items() if k.startswith("QOI_GPU_")}
+        e2e = None
+        if e2e_s is not None:
+            e2e = {"value": px_all / (e2e_ms * 1e-3) / 1e9, "unit": "Gpx/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": e2e_ms, "api": "qoi_gpu_encode_host + qoi_gpu_decode_host (pinned host buffers)",
+                   "gbs_per_direction": h2d / (e2e_ms * 1e-3) / 1e9}
+            if pcie and "both_gbs_per_direction" in pcie:
+                e2e["pcie_ceiling"] = pcie
+                e2e["frac_of_pcie_ceiling"] = e2e["gbs_per_direction"] / pcie["both_gbs_per_direction"]
         line = {
-            "metric": METRIC, "value": value, "unit": "Gpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if args.config == "headline" else f"Gpixels/s encode+decode round trip, {W}x{H}x{CH} batch",
+            "value": value, "unit": "Gpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{W}x{H} RGBA batch, encode+decode round trip", "batch_per_gpu": n,
-                       "global_batch": n * world, "distribution": DIST_NAMES[args.dist], "decode_channels": 4,
-                       "encoded_bytes_per_px": e_bpp, "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
-                       "l2": f"inputs {plan.pixel_bytes >> 20} MiB per GPU per step, larger than the 126 MB L2 (no flush needed)",
-                       "numa": numa,
-                       "decode_path": "segment-parallel with the encoder's restart index (side table, 0.07 B/px, outside the bit-exact stream)"},
+            "config": config_dict(args, world),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "e2e": {"value": px_all / (e2e_ms * 1e-3) / 1e9, "unit": "Gpx/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "api": "qoi_gpu_encode_host + qoi_gpu_decode_host (pinned host buffers)"},
+            "e2e": e2e,
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "extra": {"decode_foreign_stream_gpx_per_s": px_rank / (foreign_ms * 1e-3) / 1e9,
-                      "decode_foreign_note": "same streams decoded WITHOUT the restart index (any-stream path: parse scan + speculative segments + exact fix-up, cuda/qoi_fdec.cuh)",
-                      "encoded_bytes_all_ranks": enc_bytes_all, "c_api_single_image": c_api,
-                      "library": os.path.basename(qoi_b200.library_path()), "knobs": knobs},
+            "extra": {"encoded_bytes_per_px": e_bpp, "numa": numa, "encoded_bytes_all_ranks": enc_bytes_all, "c_api_single_image": c_api,
+                      "library": os.path.basename(qoi_b200.library_path()), "knobs": knobs,
+                      "shard_check": "every rank compared one of its streams with the CPU codec" if dist_on else None},
         }
-        print(json.dumps(line), flush=True)
-    if dist_on:
+        if emit:
+            print(json.dumps(line), flush=True)
+    plan.close()
+    ctx.close()
+    del d_pix, d_streams, d_dec, h_pix, h_streams
+    torch.cuda.empty_cache()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="headline", choices=sorted(CONFIGS) + ["sweep"],
+                    help="headline (default): 32 x 4096x4096 RGBA per GPU; 1080p_rgb_1024: BASELINE configs[2]; 8192_rgba_32: configs[3] per-GPU share; "
+                         "sweep: configs[4], one JSON line per size x channels")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (weak scaling); 0 = the config's own")
+    ap.add_argument("--dist", type=int, default=4, help="synthetic distribution id (4 = photo, headline)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-pcie", action="store_true", help="skip the bare-copy PCIe ceiling measurement")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.config != "sweep":
+        w, h, ch, nb = CONFIGS[args.config]
+        set_workload(w, h, ch)
+        if not args.batch:
+            args.batch = nb
+    if args.impl == "reference":
+        if args.config == "sweep":
+            raise SystemExit("--impl reference runs one configuration (not the sweep)")
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.config == "sweep":
+        # configs[4]: sizes 64^2 .. 16384^2 x channels 3/4, batch chosen so that a point holds ~1 Gpx (capped), one line per point
+        user_batch = args.batch
+        for ch in (3, 4):
+            for sz in SWEEP_SIZES:
+                set_workload(sz, sz, ch)
+                args.batch = user_batch or max(1, min(4096, (1 << 30) // (sz * sz)))
+                args.config = "sweep"
+                run_b200(args, rank, world, local_rank, torch, dist)
+    else:
+        run_b200(args, rank, world, local_rank, torch, dist)
+    if dist is not None:
         dist.destroy_process_group()
 
 

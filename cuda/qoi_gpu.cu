@@ -14,8 +14,11 @@
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../include/qoi_gpu.h"
@@ -36,6 +39,10 @@ struct qoi_gpu_ctx {
 	cudaStream_t s_h2d = nullptr, s_d2h = nullptr; /* one stream per copy direction: PCIe is full duplex */
 	char err[256] = {0};
 	int enc_blocks_per_sm[3] = {0, 0, 0}; /* resident CTAs per SM of qoi_encode_kernel<4,false>, <4,true>, <3,true> */
+	/* pinned staging of the four reference entry points (pageable caller memory <-> device), grown on demand */
+	unsigned char *h_stage = nullptr;
+	size_t h_stage_bytes = 0;
+	std::vector<cudaEvent_t> stage_events;
 };
 
 struct qoi_gpu_plan {
@@ -160,6 +167,8 @@ void qoi_gpu_ctx_destroy(qoi_gpu_ctx *c) {
 	if (c->stream) cudaStreamDestroy(c->stream);
 	if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
 	if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+	if (c->h_stage) cudaFreeHost(c->h_stage);
+	for (cudaEvent_t e : c->stage_events) cudaEventDestroy(e);
 	delete c;
 }
 
@@ -337,6 +346,113 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 	return QOI_GPU_OK;
 }
 
+/* ------------------------------------------------------------------ restart index as a side-car */
+struct QoiIndexHeader {
+	uint32_t magic;   /* "QOIX" */
+	uint32_t version; /* 1 */
+	uint32_t tile_px;
+	uint32_t n_images;
+	uint32_t n_tiles;
+	uint32_t reserved;
+};
+struct QoiIndexImage {
+	uint32_t width, height;
+	uint32_t channels_cs; /* channels | colorspace << 8 */
+	uint32_t first_tile;
+};
+#define QOI_INDEX_MAGIC 0x58494F51u /* 'Q','O','I','X' little endian */
+
+/* blob: header, n_images x QoiIndexImage, rs_px[n_tiles], rs_byte[n_tiles], rs_prev[n_tiles], index[n_tiles][64] (u32 values) */
+size_t qoi_gpu_index_bytes(const qoi_gpu_plan *p) {
+	if (!p) return 0;
+	return sizeof(QoiIndexHeader) + p->geom.metas.size() * sizeof(QoiIndexImage) + (size_t)p->geom.n_tiles * (12 + 256);
+}
+
+int qoi_gpu_index_export(qoi_gpu_plan *p, void *h_index, size_t capacity, void *cuda_stream) {
+	if (!p || !h_index || capacity < qoi_gpu_index_bytes(p)) return QOI_GPU_E_ARG;
+	if (p->index_owner != 1) return QOI_GPU_E_ARG; /* no encode (or import) has left an index in this plan */
+	qoi_gpu_ctx *ctx = p->ctx;
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	DeviceGuard guard(ctx->device);
+	const size_t T = p->geom.n_tiles, N = p->geom.metas.size();
+	unsigned char *o = (unsigned char *)h_index;
+	QoiIndexHeader h = {QOI_INDEX_MAGIC, 1u, QOI_TILE_PX, (uint32_t)N, (uint32_t)T, 0u};
+	memcpy(o, &h, sizeof h);
+	o += sizeof h;
+	for (size_t i = 0; i < N; i++) {
+		const QoiImgMeta &m = p->geom.metas[i];
+		QoiIndexImage im = {m.width, m.height, (uint32_t)m.channels | ((uint32_t)m.colorspace << 8), m.first_tile};
+		memcpy(o, &im, sizeof im);
+		o += sizeof im;
+	}
+	std::vector<uint64_t> ent(T * 64);
+	CK(ctx, cudaMemcpyAsync(o, p->st.rs_px, T * 4, cudaMemcpyDeviceToHost, s));
+	CK(ctx, cudaMemcpyAsync(o + T * 4, p->st.rs_byte, T * 4, cudaMemcpyDeviceToHost, s));
+	CK(ctx, cudaMemcpyAsync(o + T * 8, p->st.rs_prev, T * 4, cudaMemcpyDeviceToHost, s));
+	CK(ctx, cudaMemcpyAsync(ent.data(), p->st.ent, T * 512, cudaMemcpyDeviceToHost, s));
+	CK(ctx, cudaStreamSynchronize(s));
+	uint32_t *vals = (uint32_t *)(o + T * 12); /* the blob's arrays are 4-byte aligned if h_index is */
+	if ((uintptr_t)vals & 3u) {
+		for (size_t k = 0; k < T * 64; k++) {
+			const uint32_t v = (uint32_t)(ent[k] >> 32);
+			memcpy((unsigned char *)vals + 4 * k, &v, 4);
+		}
+	} else {
+		for (size_t k = 0; k < T * 64; k++) vals[k] = (uint32_t)(ent[k] >> 32);
+	}
+	return QOI_GPU_OK;
+}
+
+int qoi_gpu_index_import(qoi_gpu_plan *p, const void *h_index, size_t bytes, void *cuda_stream) {
+	if (!p || !h_index || bytes < sizeof(QoiIndexHeader)) return QOI_GPU_E_ARG;
+	const unsigned char *o = (const unsigned char *)h_index;
+	QoiIndexHeader h;
+	memcpy(&h, o, sizeof h);
+	const size_t T = p->geom.n_tiles, N = p->geom.metas.size();
+	if (h.magic != QOI_INDEX_MAGIC || h.version != 1u || h.tile_px != QOI_TILE_PX || h.n_images != N || h.n_tiles != T) return QOI_GPU_E_ARG;
+	if (bytes < qoi_gpu_index_bytes(p)) return QOI_GPU_E_ARG;
+	o += sizeof h;
+	for (size_t i = 0; i < N; i++) {
+		const QoiImgMeta &m = p->geom.metas[i];
+		QoiIndexImage im;
+		memcpy(&im, o, sizeof im);
+		o += sizeof im;
+		if (im.width != m.width || im.height != m.height || im.channels_cs != ((uint32_t)m.channels | ((uint32_t)m.colorspace << 8)) ||
+		    im.first_tile != m.first_tile)
+			return QOI_GPU_E_ARG;
+	}
+	/* restart points must lie inside their image (a damaged side-car must not send a lane outside the buffers) */
+	std::vector<int32_t> rs((size_t)T * 2);
+	memcpy(rs.data(), o, T * 8);
+	for (size_t i = 0; i < N; i++) {
+		const QoiImgMeta &m = p->geom.metas[i];
+		const size_t nt = ((size_t)m.npx + QOI_TILE_PX - 1) / QOI_TILE_PX;
+		const QoiDescPOD d = {m.width, m.height, m.channels, m.colorspace};
+		for (size_t k = 0; k < nt; k++) {
+			const int32_t px = rs[m.first_tile + k], by = rs[T + m.first_tile + k];
+			if (px < 0) continue; /* no op starts in this tile */
+			if ((uint32_t)px < k * QOI_TILE_PX || (uint32_t)px >= m.npx || by < QOI_HEADER_BYTES || (size_t)by >= qoi_max_foreign_stream(d)) return QOI_GPU_E_ARG;
+		}
+	}
+	qoi_gpu_ctx *ctx = p->ctx;
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	DeviceGuard guard(ctx->device);
+	std::vector<uint64_t> ent(T * 64);
+	const unsigned char *vals = o + T * 12;
+	for (size_t k = 0; k < T * 64; k++) {
+		uint32_t v;
+		memcpy(&v, vals + 4 * k, 4);
+		ent[k] = ((uint64_t)v << 32) | 1ull; /* epoch field 0: a later encode on this plan treats the words as unpublished */
+	}
+	CK(ctx, cudaMemcpyAsync(p->st.rs_px, o, T * 4, cudaMemcpyHostToDevice, s));
+	CK(ctx, cudaMemcpyAsync(p->st.rs_byte, o + T * 4, T * 4, cudaMemcpyHostToDevice, s));
+	CK(ctx, cudaMemcpyAsync(p->st.rs_prev, o + T * 8, T * 4, cudaMemcpyHostToDevice, s));
+	CK(ctx, cudaMemcpyAsync(p->st.ent, ent.data(), T * 512, cudaMemcpyHostToDevice, s));
+	CK(ctx, cudaStreamSynchronize(s));
+	p->index_owner = 1;
+	return QOI_GPU_OK;
+}
+
 /* ------------------------------------------------------------------ host-buffer forms */
 static int plan_mirrors(qoi_gpu_plan *p) {
 	qoi_gpu_ctx *ctx = p->ctx;
@@ -505,6 +621,151 @@ void qoi_gpu_host_free(void *p) {
 	if (p) cudaFreeHost(p);
 }
 
+/* ------------------------------------------------------------------ staged copies for pageable caller memory */
+/*
+ * qoi_encode / qoi_decode take and return ordinary malloc'ed memory (qoi.h:276,287; callers free() the result).  A plain
+ * cudaMemcpy from pageable memory is staged by the driver with one host thread at 5-10 GB/s -- 22 ms for a 4096^2 RGBA
+ * image and its stream, against ~2 ms of PCIe time.  Here a few persistent host threads copy 4 MiB chunks between the
+ * caller's buffer and a pinned staging buffer while the DMA of the chunks already copied is in flight; the result buffer's
+ * first-touch page faults are spread over the same threads.  QOI_GPU_HOST_THREADS (1..64) sets their number (default 8).
+ */
+class HostPool {
+public:
+	static HostPool &get() {
+		static HostPool pool;
+		return pool;
+	}
+	/* fn(i) for every i in [0, n); the calling thread works too; returns when all are done */
+	void run(int n, const std::function<void(int)> &fn) {
+		if (n <= 0) return;
+		if (workers_.empty() || n == 1) {
+			for (int i = 0; i < n; i++) fn(i);
+			return;
+		}
+		std::unique_lock<std::mutex> lk(mu_);
+		fn_ = &fn;
+		n_ = n;
+		next_.store(0);
+		left_ = n;
+		gen_++;
+		cv_.notify_all();
+		lk.unlock();
+		work();
+		lk.lock();
+		done_cv_.wait(lk, [&] { return left_ == 0; });
+		fn_ = nullptr;
+	}
+
+private:
+	HostPool() {
+		int want = 8;
+		const char *e = getenv("QOI_GPU_HOST_THREADS");
+		if (e && atoi(e) >= 1 && atoi(e) <= 64) want = atoi(e);
+		const unsigned hw = std::thread::hardware_concurrency();
+		if (hw && (unsigned)want > hw) want = (int)hw;
+		for (int i = 1; i < want; i++) workers_.emplace_back([this] { loop(); });
+	}
+	~HostPool() {
+		{
+			std::lock_guard<std::mutex> lk(mu_);
+			stop_ = true;
+			gen_++;
+		}
+		cv_.notify_all();
+		for (std::thread &t : workers_) t.join();
+	}
+	void work() {
+		while (true) {
+			const int i = next_.fetch_add(1);
+			if (i >= n_) break;
+			(*fn_)(i);
+			std::lock_guard<std::mutex> lk(mu_);
+			if (--left_ == 0) done_cv_.notify_all();
+		}
+	}
+	void loop() {
+		uint64_t seen = 0;
+		while (true) {
+			{
+				std::unique_lock<std::mutex> lk(mu_);
+				cv_.wait(lk, [&] { return gen_ != seen; });
+				seen = gen_;
+				if (stop_) return;
+			}
+			work();
+		}
+	}
+	std::vector<std::thread> workers_;
+	std::mutex mu_;
+	std::condition_variable cv_, done_cv_;
+	const std::function<void(int)> *fn_ = nullptr;
+	int n_ = 0, left_ = 0;
+	std::atomic<int> next_{0};
+	uint64_t gen_ = 0;
+	bool stop_ = false;
+};
+
+#define QOI_STAGE_CHUNK ((size_t)4 << 20)
+#define QOI_STAGE_MAX_CHUNKS 64
+
+static int stage_reserve(qoi_gpu_ctx *ctx, size_t bytes) {
+	if (ctx->h_stage_bytes >= bytes) return QOI_GPU_OK;
+	if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+	ctx->h_stage = nullptr;
+	ctx->h_stage_bytes = 0;
+	const size_t want = (bytes + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
+	CK(ctx, cudaMallocHost(&ctx->h_stage, want));
+	ctx->h_stage_bytes = want;
+	return QOI_GPU_OK;
+}
+
+static size_t stage_chunk_bytes(size_t bytes) {
+	size_t c = QOI_STAGE_CHUNK;
+	while ((bytes + c - 1) / c > QOI_STAGE_MAX_CHUNKS) c *= 2;
+	return c;
+}
+
+/* pageable host -> device, through ctx->h_stage + stage_off; the DMAs are queued on s (the workers enqueue their own chunk) */
+static int staged_h2d(qoi_gpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, size_t stage_off, cudaStream_t s) {
+	if (!bytes) return QOI_GPU_OK;
+	const size_t c = stage_chunk_bytes(bytes);
+	const int n = (int)((bytes + c - 1) / c);
+	std::atomic<int> failed{0};
+	const int dev = ctx->device;
+	HostPool::get().run(n, [&](int i) {
+		const size_t off = (size_t)i * c, len = bytes - off < c ? bytes - off : c;
+		memcpy(ctx->h_stage + stage_off + off, (const unsigned char *)h_src + off, len);
+		cudaSetDevice(dev); /* the current device is per thread */
+		if (cudaMemcpyAsync((unsigned char *)d_dst + off, ctx->h_stage + stage_off + off, len, cudaMemcpyHostToDevice, s) != cudaSuccess) failed = 1;
+	});
+	return failed ? QOI_GPU_E_CUDA : QOI_GPU_OK;
+}
+
+/* device -> pageable host: chunked DMAs into the staging buffer, each followed by an event; the workers wait for their
+   chunk's event and copy it out.  Synchronous: returns when h_dst is complete. */
+static int staged_d2h(qoi_gpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, size_t stage_off, cudaStream_t s) {
+	if (!bytes) return QOI_GPU_OK;
+	const size_t c = stage_chunk_bytes(bytes);
+	const int n = (int)((bytes + c - 1) / c);
+	while ((int)ctx->stage_events.size() < n) {
+		cudaEvent_t e;
+		CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		ctx->stage_events.push_back(e);
+	}
+	for (int i = 0; i < n; i++) {
+		const size_t off = (size_t)i * c, len = bytes - off < c ? bytes - off : c;
+		CK(ctx, cudaMemcpyAsync(ctx->h_stage + stage_off + off, (const unsigned char *)d_src + off, len, cudaMemcpyDeviceToHost, s));
+		CK(ctx, cudaEventRecord(ctx->stage_events[(size_t)i], s));
+	}
+	std::atomic<int> failed{0};
+	HostPool::get().run(n, [&](int i) {
+		const size_t off = (size_t)i * c, len = bytes - off < c ? bytes - off : c;
+		if (cudaEventSynchronize(ctx->stage_events[(size_t)i]) != cudaSuccess) failed = 1;
+		memcpy((unsigned char *)h_dst + off, ctx->h_stage + stage_off + off, len);
+	});
+	return failed ? QOI_GPU_E_CUDA : QOI_GPU_OK;
+}
+
 /* ------------------------------------------------------------------ the reference's own entry points */
 static std::mutex g_mu;
 static qoi_gpu_ctx *g_ctx = nullptr;
@@ -554,14 +815,15 @@ void *qoi_encode(const void *data, const qoi_desc *desc, int *out_len) {
 	if (!p || plan_mirrors(p)) return NULL;
 	cudaStream_t s = ctx->stream;
 	const size_t nbytes = (size_t)d.width * d.height * d.channels;
-	if (cudaMemcpyAsync(p->d_pixels, data, nbytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return NULL;
+	if (stage_reserve(ctx, qoi_max_stream(pod) > nbytes ? qoi_max_stream(pod) : nbytes)) return NULL;
+	if (staged_h2d(ctx, p->d_pixels, data, nbytes, 0, s)) return NULL;
 	if (qoi_gpu_encode(p, p->d_pixels, p->d_streams, p->d_lens, s) != QOI_GPU_OK) return NULL;
 	if (cudaMemcpyAsync(p->h_lens_pinned, p->d_lens, sizeof(int32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess) return NULL;
 	if (cudaStreamSynchronize(s) != cudaSuccess) return NULL;
 	const int len = p->h_lens_pinned[0];
 	void *out = malloc((size_t)len);
 	if (!out) return NULL;
-	if (cudaMemcpyAsync(out, p->d_streams, (size_t)len, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+	if (staged_d2h(ctx, out, p->d_streams, (size_t)len, 0, s)) { /* the staging buffer is free again: the kernel has consumed the pixels */
 		free(out);
 		return NULL;
 	}
@@ -597,14 +859,14 @@ void *qoi_decode(const void *data, int size, qoi_desc *desc, int channels) {
 	int eff_size = size;
 	if (up > cap) { up = cap; eff_size = (int)cap; }
 	const size_t out_bytes = (size_t)d.width * d.height * (size_t)out_ch;
+	if (stage_reserve(ctx, out_bytes > up ? out_bytes : up)) return NULL;
 	void *out = malloc(out_bytes);
 	if (!out) return NULL;
 	p->h_lens_pinned[0] = eff_size;
-	bool ok = cudaMemcpyAsync(p->d_streams, data, up, cudaMemcpyHostToDevice, s) == cudaSuccess &&
+	bool ok = staged_h2d(ctx, p->d_streams, data, up, 0, s) == QOI_GPU_OK &&
 	          cudaMemcpyAsync(p->d_lens, p->h_lens_pinned, sizeof(int32_t), cudaMemcpyHostToDevice, s) == cudaSuccess &&
 	          qoi_gpu_decode(p, p->d_streams, p->d_lens, p->d_decoded, 0, nullptr, s) == QOI_GPU_OK &&
-	          cudaMemcpyAsync(out, p->d_decoded, out_bytes, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
-	          cudaStreamSynchronize(s) == cudaSuccess;
+	          staged_d2h(ctx, out, p->d_decoded, out_bytes, 0, s) == QOI_GPU_OK; /* stream-ordered behind the kernels, which have read the staged stream */
 	if (!ok) {
 		free(out);
 		return NULL;

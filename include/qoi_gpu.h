@@ -105,6 +105,21 @@ int qoi_gpu_encode_host(qoi_gpu_plan *plan, const void *h_pixels, void *h_stream
 int qoi_gpu_decode_host(qoi_gpu_plan *plan, const void *h_streams, const int32_t *h_lens, void *h_decoded,
                         int use_index);
 
+/*
+ * Restart index as a side-car.  The index the last qoi_gpu_encode left in the plan -- per 2048-pixel tile:
+ * where its first op starts (pixel, stream offset, colour before it) and the reference decoder's index[64] at that point --
+ * can be copied out and stored next to the .qoi files (0.13 bytes per pixel; the streams themselves stay bit exact and
+ * decode anywhere without it).  A plan of the same geometry that imports it decodes those streams with use_index = 1,
+ * i.e. at the segment-parallel speed, after they have been read back from disk.
+ *   qoi_gpu_index_bytes   size of the blob for this plan's geometry
+ *   qoi_gpu_index_export  device -> host blob (HOST pointer, capacity >= qoi_gpu_index_bytes); needs an index in the plan
+ *   qoi_gpu_index_import  host blob -> plan; QOI_GPU_E_ARG if the blob does not describe this plan's images
+ * Both are synchronous on cuda_stream.
+ */
+size_t qoi_gpu_index_bytes(const qoi_gpu_plan *plan);
+int qoi_gpu_index_export(qoi_gpu_plan *plan, void *h_index, size_t capacity, void *cuda_stream);
+int qoi_gpu_index_import(qoi_gpu_plan *plan, const void *h_index, size_t bytes, void *cuda_stream);
+
 /* pinned host memory for the *_host calls */
 void *qoi_gpu_host_alloc(size_t bytes);
 void qoi_gpu_host_free(void *p);

@@ -76,6 +76,12 @@ def lib():
     L.qoi_gpu_host_alloc.argtypes = [C.c_size_t]
     L.qoi_gpu_host_free.argtypes = [vp]
     L.qoi_gpu_launch_count.restype = C.c_uint64
+    L.qoi_gpu_index_bytes.restype = C.c_size_t
+    L.qoi_gpu_index_bytes.argtypes = [vp]
+    L.qoi_gpu_index_export.restype = C.c_int
+    L.qoi_gpu_index_export.argtypes = [vp, vp, C.c_size_t, vp]
+    L.qoi_gpu_index_import.restype = C.c_int
+    L.qoi_gpu_index_import.argtypes = [vp, vp, C.c_size_t, vp]
     _lib = L
     return L
 
@@ -207,6 +213,17 @@ class Plan:
     def decode(self, d_streams, d_lens, d_decoded, use_index=True, d_status=None, stream=0):
         _check(lib().qoi_gpu_decode(self._h, d_streams, d_lens, d_decoded, 1 if use_index else 0, d_status, stream),
                self.ctx._h, "qoi_gpu_decode")
+
+    # restart index as a side-car (include/qoi_gpu.h qoi_gpu_index_*): bytes out, bytes in
+    def export_index(self, stream=0):
+        n = int(lib().qoi_gpu_index_bytes(self._h))
+        buf = np.empty(n, dtype=np.uint8)
+        _check(lib().qoi_gpu_index_export(self._h, buf.ctypes.data, n, stream), self.ctx._h, "qoi_gpu_index_export")
+        return buf.tobytes()
+
+    def import_index(self, blob, stream=0):
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        _check(lib().qoi_gpu_index_import(self._h, buf.ctypes.data, buf.size, stream), self.ctx._h, "qoi_gpu_index_import")
 
     # host buffers: numpy arrays (or raw addresses)
     def encode_host(self, h_pixels, h_streams, h_lens):

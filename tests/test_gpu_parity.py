@@ -297,6 +297,98 @@ def test_config2_small_batch_1080p_rgb(gpu, cpu):
     run_batch(gpu, cpu, [(1920, 1080, 3)] * 8, 4, dec_ch=4)
 
 
+def test_config2_batch_of_256_spans_waves(gpu, cpu):
+    """configs[2] at a batch that fills the machine several times over (256 x 1920x1080 RGB = 259 k tiles): encode + both
+    decodes on the device, round trip on every image, streams of a sample of images byte for byte against the CPU."""
+    qb, torch, ctx = gpu
+    chk = cpu.best()
+    n, w, h = 256, 1920, 1080
+    plan = qb.Plan(ctx, [qb.Desc(w, h, 3, 0)] * n, decoded_channels=3)
+    host = cpu.batch(n, w, h, 3, 4)
+    d_pix = dev_u8(torch, host)
+    d_streams = torch.empty(plan.stream_bytes, dtype=torch.uint8, device="cuda")
+    d_lens = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_dec = torch.zeros(plan.decoded_bytes, dtype=torch.uint8, device="cuda")
+    plan.encode(d_pix.data_ptr(), d_streams.data_ptr(), d_lens.data_ptr())
+    for use_index in (True, False):
+        d_dec.zero_()
+        plan.decode(d_streams.data_ptr(), d_lens.data_ptr(), d_dec.data_ptr(), use_index=use_index)
+        torch.cuda.synchronize()
+        assert torch.equal(d_dec, d_pix), use_index
+    lens = d_lens.cpu().numpy()
+    for i in (0, 1, 77, 128, 255):
+        want = chk.encode(host[i * w * h * 3:(i + 1) * w * h * 3], w, h, 3)
+        o = int(plan.stream_off[i])
+        assert lens[i] == len(want) and d_streams[o:o + len(want)].cpu().numpy().tobytes() == want, i
+    plan.close()
+
+
+def test_index_sidecar_through_disk(gpu, cpu, tmp_path):
+    """the restart index leaves the plan as a side-car, the streams and the side-car go to disk, a NEW plan
+    reads both back and decodes with use_index -- same pixels as the reference decoder gives for the stored streams."""
+    qb, torch, ctx = gpu
+    chk = cpu.best()
+    whc = [(700, 400, 4), (2048, 3, 4), (64, 64, 4), (1000, 777, 4), (1, 1, 4)]
+    descs = [qb.Desc(w, h, c, 0) for (w, h, c) in whc]
+    plan = qb.Plan(ctx, descs, decoded_channels=4)
+    host = np.concatenate([cpu.image(w, h, c, (4, 7, 6, 3, 0)[i], i) for i, (w, h, c) in enumerate(whc)])
+    d_pix = dev_u8(torch, host)
+    d_streams = torch.zeros(plan.stream_bytes, dtype=torch.uint8, device="cuda")
+    d_lens = torch.zeros(plan.n, dtype=torch.int32, device="cuda")
+    with pytest.raises(qb.QoiGpuError):
+        plan.export_index()  # nothing encoded yet
+    plan.encode(d_pix.data_ptr(), d_streams.data_ptr(), d_lens.data_ptr())
+    blob = plan.export_index()
+    lens = d_lens.cpu().numpy()
+    streams = d_streams.cpu().numpy()
+    for i in range(plan.n):
+        o = int(plan.stream_off[i])
+        (tmp_path / f"img{i}.qoi").write_bytes(streams[o:o + lens[i]].tobytes())
+    (tmp_path / "batch.qoix").write_bytes(blob)
+    plan.close()
+    # a fresh plan, everything from disk
+    plan2 = qb.Plan(ctx, descs, decoded_channels=4)
+    h_streams = np.zeros(plan2.stream_bytes, dtype=np.uint8)
+    h_lens = np.zeros(plan2.n, dtype=np.int32)
+    for i in range(plan2.n):
+        data = (tmp_path / f"img{i}.qoi").read_bytes()
+        assert data == chk.encode(host[int(plan2.pixel_off[i]):int(plan2.pixel_off[i]) + whc[i][0] * whc[i][1] * 4], *whc[i])
+        o = int(plan2.stream_off[i])
+        h_streams[o:o + len(data)] = np.frombuffer(data, dtype=np.uint8)
+        h_lens[i] = len(data)
+    d_streams2 = dev_u8(torch, h_streams)
+    d_lens2 = torch.from_numpy(h_lens).cuda()
+    d_dec = torch.zeros(plan2.decoded_bytes, dtype=torch.uint8, device="cuda")
+    with pytest.raises(qb.QoiGpuError):
+        plan2.decode(d_streams2.data_ptr(), d_lens2.data_ptr(), d_dec.data_ptr(), use_index=True)  # no index in this plan yet
+    with pytest.raises(qb.QoiGpuError):
+        plan2.import_index(blob[:-8])  # truncated side-car
+    bad = bytearray(blob); bad[8] ^= 0xFF
+    with pytest.raises(qb.QoiGpuError):
+        plan2.import_index(bytes(bad))  # another tile size
+    plan2.import_index((tmp_path / "batch.qoix").read_bytes())
+    plan2.decode(d_streams2.data_ptr(), d_lens2.data_ptr(), d_dec.data_ptr(), use_index=True)
+    torch.cuda.synchronize()
+    assert torch.equal(d_dec, d_pix)
+    assert len(blob) <= 0.14 * sum(w * h for (w, h, c) in whc) + 4096  # ~0.13 B/px
+    plan2.close()
+
+
+def test_c_api_large_image_through_staging(gpu, cpu):
+    """qoi_encode / qoi_decode on an image of many staging chunks (8192 x 4096 RGBA = 128 MiB in 4 MiB pieces over the host
+    threads): stream equal to the CPU's, pixels back."""
+    qb, _, _ = gpu
+    chk = cpu.best()
+    w, h = 8192, 4096
+    img = cpu.image(w, h, 4, 4)
+    got = qb.encode(img, qb.Desc(w, h, 4, 0))
+    assert got == chk.encode(img, w, h, 4)
+    px, d = qb.decode(got, 4)
+    assert px is not None and (px == img).all() and (d.width, d.height) == (w, h)
+    px3, _ = qb.decode(got, 3)
+    assert (px3.reshape(-1, 3) == img.reshape(-1, 4)[:, :3]).all()
+
+
 def test_roundtrip_8192_device_resident(gpu, cpu):
     """BASELINE.json configs[3] image size: 8192x8192 RGBA, checked by the size-independent property
     decode(encode(x)) == x on the device, plus out_len against the CPU for one image."""
