@@ -28,6 +28,26 @@ def find_nvcc():
     raise RuntimeError("nvcc not found: cannot build libqoi_gpu.so (there is no CPU fallback)")
 
 
+MULTI_LIB = os.path.join(ROOT, "qoi_b200", "libqoi_gpu_nccl.so")
+MULTI_SOURCES = [os.path.join(ROOT, "cuda", "qoi_gpu_multi.cu"), os.path.join(ROOT, "include", "qoi_gpu_multi.h"), os.path.join(ROOT, "include", "qoi_gpu.h")]
+
+
+def build_multi(force=False):
+    """libqoi_gpu_nccl.so: the multi-device layer (include/qoi_gpu_multi.h) on top of libqoi_gpu.so's public C API + NCCL.
+    Host code only; a separate library so that the codec library itself does not depend on NCCL."""
+    if not force and os.path.exists(MULTI_LIB) and all(os.path.getmtime(s) <= os.path.getmtime(MULTI_LIB) for s in MULTI_SOURCES + [LIB]):
+        return MULTI_LIB
+    cmd = [find_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "-o", MULTI_LIB,
+           os.path.join(ROOT, "cuda", "qoi_gpu_multi.cu"), "-L" + os.path.join(ROOT, "qoi_b200"), "-lqoi_gpu", "-lnccl",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    if os.path.exists("/usr/bin/g++"):
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed (multi-device layer):\n" + res.stdout + res.stderr)
+    return MULTI_LIB
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True

@@ -34,6 +34,19 @@ def test_binding_covers_the_abi():
     assert C.sizeof(qoi_b200.Desc) == 12  # reference sizeof(qoi_desc), SURVEY.md probe P1
 
 
+def test_multi_device_library_exports_its_header():
+    """include/qoi_gpu_multi.h: every declared entry point is exported by libqoi_gpu_nccl.so (no calls: needs GPUs + NCCL)."""
+    import re
+    from qoi_b200 import multi as qm
+
+    L = qm.lib()
+    text = open(os.path.join(ROOT, "include", "qoi_gpu_multi.h")).read()
+    names = set(re.findall(r"\b(qoi_gpu_m[a-z_]+)\s*\(", text))
+    assert {"qoi_gpu_mctx_create", "qoi_gpu_mplan_create", "qoi_gpu_mencode", "qoi_gpu_mdecode", "qoi_gpu_mplan_shard"} <= names
+    for n in names:
+        assert hasattr(L, n), n
+
+
 def test_kernels_are_blackwell_native():
     """SASS evidence that the hot path uses bulk async copies (TMA, UBLKCP) for the pixel tiles, mbarriers, named barriers,
     warp votes and dp4a -- and no match.any (~50 ADU cycles per warp on sm_100a, profiles/r2_enc_v1)."""
