@@ -35,6 +35,16 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+/* the two halves of arrive.expect_tx: announce the bytes first (so that the bulk copy can be issued at once), arrive later
+   (release: everything this thread -- and, after a __syncwarp, its warp -- wrote to shared memory before is visible to the waiters) */
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+/* pull one 128-byte line into L2 (no register result, no waiting) */
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 	uint32_t ok;
 	asm volatile(
@@ -171,6 +181,13 @@ static inline void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
 	b->arrivals_left--;
 	emubar_check(b);
 }
+static inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { ((EmuBar *)bar)->tx += (int32_t)bytes; }
+static inline void mbar_arrive(uint64_t *bar) {
+	EmuBar *b = (EmuBar *)bar;
+	b->arrivals_left--;
+	emubar_check(b);
+}
+static inline void prefetch_l2(const void *) {}
 static inline bool mbar_try_wait(uint64_t *bar, uint32_t parity) { return ((EmuBar *)bar)->phase != (uint8_t)parity; }
 static inline void mbar_wait(uint64_t *bar, uint32_t parity) {
 	while (!mbar_try_wait(bar, parity)) qemu::yield("mbarrier wait");

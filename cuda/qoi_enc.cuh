@@ -32,21 +32,25 @@
  *
  *   compute warps (4)                                     service warp
  *   -----------------                                     ------------
- *   wait tile (mbarrier: info record + pixels)            ticket for the NEXT tile (atomic + two dependent loads)
+ *   wait tile k (mbarrier: info record + pixels)
  *   E  (EXPAND) raw bytes -> RGBA words
- *   A  per row: non-run mask, slot, last writer
- *      of each slot -> the warp's table
+ *   A  per row: non-run mask, slot, same-slot lanes
+ *      (six ballots), hit / miss / unknown per pixel,
+ *      last writer of each slot -> the warp's table
  *        ------- A_DONE ------->                          T  tile aggregate published; 32-tile window look-back for
- *                                                            the incoming table and the last non-run index;
- *        <------ T_READY -------                             inclusive record published
+ *   C  copy-out of tile k-1: its slab -> stream              the incoming table and the last non-run index;
+ *      (shifted 16-byte copy), restart record             <- B_READY(k-1)
+ *        <------ T_READY -------                             inclusive record published; ticket for tile k+1
  *   M  my chunk's incoming table = nearest earlier
  *      warp that wrote the slot, else the tile's
  *   B  per row: INDEX / RUN / DIFF / LUMA / RGB / RGBA
  *      exactly like qoi.h:415-474, bytes -> slab
- *        ------- B_DONE ------->                          bulk copy of the NEXT tile's pixels; output-offset
- *        <------ B_READY -------                          look-back (32 tiles per probe); header / end marker / length
- *   C  slab -> stream (shifted 16-byte copy),
- *      restart record of the tile
+ *        ------- B_DONE ------->                          bulk copy of tile k+1's pixels; output-offset look-back of
+ *                                                          tile k (32 tiles per probe) -> B_READY(k); header / end marker
+ *
+ * The copy-out of a tile waits for its output offset; it runs one tile late, behind the NEXT tile's pass A, so that the
+ * offset look-back (and most of the table look-back) is hidden behind work instead of a barrier (profiles/r2_enc_v2: a third
+ * of all warp samples sat at B_READY, a fifth at T_READY).
  */
 #pragma once
 #include <limits.h>
@@ -99,15 +103,15 @@ struct Layout {
 	static constexpr int OFF_ROWS = OFF_TINS + 64 * 4;                     /* uint4 [warps][rows]: what pass A found out about each row: non-run, hit, unknown lanes */
 	static constexpr int OFF_MBAR = OFF_ROWS + QOI_ENC_WARPS * QOI_WARP_ROWS * 16; /* u64 */
 	static constexpr int OFF_INFO = OFF_MBAR + 16;                         /* TileInfo [2] */
-	static constexpr int OFF_WTOT = OFF_INFO + 2 * (int)sizeof(TileInfo);  /* u32 [warps] bytes per slab */
-	static constexpr int OFF_WLNR = OFF_WTOT + QOI_ENC_WARPS * 4;          /* i32 [warps] last non-run pixel of the chunk (tile coordinates, -1: none) */
+	static constexpr int OFF_WTOT = OFF_INFO + 2 * (int)sizeof(TileInfo);  /* u32 [2][warps] bytes per slab, by tile parity (a tile's copy-out runs during the next tile) */
+	static constexpr int OFF_WLNR = OFF_WTOT + 2 * QOI_ENC_WARPS * 4;      /* i32 [warps] last non-run pixel of the chunk (tile coordinates, -1: none) */
 	static constexpr int OFF_MISC = OFF_WLNR + QOI_ENC_WARPS * 4;          /* u32 [4] */
 	static constexpr int TOTAL = OFF_MISC + 16;
 	static_assert(SLAB_BYTES % 16 == 0 && OFF_SLAB % 16 == 0 && OFF_WTAB % 8 == 0 && OFF_ROWS % 16 == 0 && OFF_MBAR % 8 == 0 && OFF_INFO % 16 == 0, "alignment");
 };
 
 /* misc[] slots */
-enum { MISC_TILE_BASE = 0, MISC_LNR_IN = 1 };
+enum { MISC_TILE_BASE = 0 /* [2], by tile parity */, MISC_LNR_IN = 2 };
 
 __device__ __forceinline__ uint64_t pack_bytes(uint32_t epoch, uint32_t state, uint32_t v) {
 	return ((uint64_t)epoch << 34) | ((uint64_t)state << 32) | v;
@@ -119,6 +123,7 @@ __device__ __forceinline__ uint64_t pack_sum(uint32_t epoch, uint32_t payload) {
 struct Fetch {
 	uint32_t tile, img;
 	bool any;
+	QoiImgMeta m; /* read with the ticket, a pass ahead of the bulk copy */
 };
 
 /* step 1: take a ticket -- only when the tile can start as soon as its pixels are there.  (Round 1 and the first version of
@@ -129,6 +134,7 @@ __device__ __forceinline__ uint32_t ticket_take(const QoiEncParams &P) {
 	if (lane_id() == 0) tk = atomicAdd(&P.st.ticket[0], 1u);
 	return tk; /* valid in lane 0 */
 }
+template <int CH>
 __device__ __forceinline__ void ticket_resolve(const QoiEncParams &P, uint32_t tk_lane0, Fetch &F) {
 	const uint32_t tk = __shfl_sync(QOI_FULL_MASK, tk_lane0, 0);
 	F.any = tk < P.n_tiles;
@@ -138,6 +144,15 @@ __device__ __forceinline__ void ticket_resolve(const QoiEncParams &P, uint32_t t
 		const uint64_t rec = P.tile_order[tk]; /* ascending inside every image, images interleaved */
 		F.tile = (uint32_t)rec;
 		F.img = (uint32_t)(rec >> 32);
+		F.m = P.imgs[F.img];
+		/* the tile's pixels (and the pixel before / after them) on their way into L2: the bulk copy that follows a pass
+		   later then takes an L2 round trip, not a DRAM one, while the compute warps wait for it */
+		const uint32_t px0 = (F.tile - F.m.first_tile) * QOI_TILE_PX;
+		const uint32_t n_valid = (F.m.npx - px0) < (uint32_t)QOI_TILE_PX ? (F.m.npx - px0) : (uint32_t)QOI_TILE_PX;
+		const uint8_t *gsrc = P.pixels + F.m.pix_off + (uint64_t)px0 * CH;
+		const uint8_t *lo = px0 ? gsrc - CH : gsrc, *hi = gsrc + (size_t)n_valid * CH + (px0 + n_valid < F.m.npx ? CH : 0);
+		const uintptr_t l0 = (uintptr_t)lo & ~(uintptr_t)127;
+		for (uintptr_t a = l0 + 128u * lane_id(); a < (uintptr_t)hi; a += 128u * 32u) prefetch_l2((const void *)a);
 	}
 }
 
@@ -156,7 +171,7 @@ __device__ __forceinline__ void fetch_issue(const QoiEncParams &P, unsigned char
 		}
 		return;
 	}
-	const QoiImgMeta m = P.imgs[F.img];
+	const QoiImgMeta &m = F.m;
 	const uint32_t t_in = F.tile - m.first_tile;
 	const uint32_t px0 = t_in * QOI_TILE_PX;
 	const uint32_t n_valid = (m.npx - px0) < (uint32_t)QOI_TILE_PX ? (m.npx - px0) : (uint32_t)QOI_TILE_PX;
@@ -167,6 +182,11 @@ __device__ __forceinline__ void fetch_issue(const QoiEncParams &P, unsigned char
 	const uint32_t lo_off = (sh + 15u) & ~15u;
 	const uint32_t hi_off = (sh + nbytes) & ~15u;
 	const uint32_t tma_bytes = hi_off > lo_off ? hi_off - lo_off : 0u;
+	/* the bulk copy first: everything below runs while it is in flight.  The phase cannot complete before lane 0's arrive. */
+	if (lane == 0 && tma_bytes) {
+		mbar_expect_tx(mbar, tma_bytes);
+		tma_load_1d_hint(data + lo_off, gsrc + (lo_off - sh), tma_bytes, mbar, l2_evict_first_policy());
+	}
 	/* the <16-byte fragments on either side of the 16-byte aligned interior */
 	const uint32_t a_lo = sh, a_hi = tma_bytes ? lo_off : sh + nbytes;
 	const uint32_t b_lo = tma_bytes ? hi_off : 0u, b_hi = tma_bytes ? sh + nbytes : 0u;
@@ -207,10 +227,7 @@ __device__ __forceinline__ void fetch_issue(const QoiEncParams &P, unsigned char
 		info->chan_cs = (uint32_t)m.channels | ((uint32_t)m.colorspace << 8);
 	}
 	__syncwarp(); /* lanes 0/1 and the fragment lanes wrote shared memory that lane 0's arrive releases */
-	if (lane == 0) {
-		mbar_arrive_expect_tx(mbar, tma_bytes);
-		if (tma_bytes) tma_load_1d_hint(data + lo_off, gsrc + (lo_off - sh), tma_bytes, mbar, l2_evict_first_policy());
-	}
+	if (lane == 0) mbar_arrive(mbar);
 }
 
 /* one byte to shared memory under a predicate, without a branch (the op bytes of a row: up to five stores per lane) */
@@ -231,14 +248,37 @@ __device__ __forceinline__ void sts_u8_if(bool pred, unsigned char *addr, uint32
    instruction holds the ADU pipe for ~50 cycles per warp on sm_100a -- measured, profiles/r2_enc_v1 -- and two of them per
    row made the whole kernel ADU-bound.) */
 __device__ __forceinline__ uint32_t same_key_lanes(uint32_t key) {
+#ifdef QOI_EMU
 	uint32_t differ = 0;
-#pragma unroll
 	for (int b = 0; b < 6; b++) {
-		const bool bit = (key >> b) & 1u;
+		const bool bit = (key & (1u << b)) != 0u;
 		const uint32_t plane = __ballot_sync(QOI_FULL_MASK, bit);
-		differ |= bit ? ~plane : plane;
+		differ |= plane ^ (bit ? 0xFFFFFFFFu : 0u);
 	}
 	return ~differ;
+#else
+	/* four instructions per bit (mask test with a predicate result, vote, select, one LOP3 for differ |= plane ^ mine); left to
+	   itself the compiler shifts the bit down, masks it, compares it and negates it -- six */
+	uint32_t differ = 0;
+#define QOI_KEY_BIT(MASK)                                                                    \
+	asm volatile(                                                                            \
+	    "{\n\t.reg .pred p;\n\t.reg .b32 t, pl, mn;\n\t"                                     \
+	    "and.b32 t, %1, " #MASK ";\n\t"                                                       \
+	    "setp.ne.u32 p, t, 0;\n\t"                                                            \
+	    "vote.sync.ballot.b32 pl, p, 0xffffffff;\n\t"                                         \
+	    "selp.b32 mn, 0xffffffff, 0, p;\n\t"                                                  \
+	    "lop3.b32 %0, %0, pl, mn, 0xF6;\n\t}"                                                 \
+	    : "+r"(differ)                                                                       \
+	    : "r"(key))
+	QOI_KEY_BIT(1);
+	QOI_KEY_BIT(2);
+	QOI_KEY_BIT(4);
+	QOI_KEY_BIT(8);
+	QOI_KEY_BIT(16);
+	QOI_KEY_BIT(32);
+#undef QOI_KEY_BIT
+	return ~differ;
+#endif
 }
 
 /* ---------------------------------------------------------------- op of one non-run pixel that is not an INDEX hit */
@@ -247,7 +287,7 @@ __device__ __forceinline__ uint32_t same_key_lanes(uint32_t key) {
    b0 = first byte, b1 = second byte (LUMA's second byte, or r for RGB / RGBA whose g, b, a follow from v). */
 struct OpClass {
 	bool diff, luma, a_eq;
-	uint32_t b0, b1;
+	uint32_t diff_b, luma_b0, luma_b1;
 };
 __device__ __forceinline__ OpClass classify(uint32_t v, uint32_t p) {
 	OpClass c;
@@ -257,16 +297,17 @@ __device__ __forceinline__ OpClass classify(uint32_t v, uint32_t p) {
 	/* DIFF (qoi.h:446-451): dr+2, dg+2, db+2 all in 0..3 */
 	const uint32_t t = ((d & 0x7F7F7F7Fu) + 0x00020202u) ^ (d & 0x80808080u);
 	c.diff = (t & 0xFFFCFCFCu) == 0u;
-	const uint32_t diff_b = 0x40u | ((t << 4) & 0x30u) | ((t >> 6) & 0x0Cu) | ((t >> 16) & 0x03u);
-	/* LUMA (qoi.h:443-444, 453-459): vg in -32..31, vr-vg and vb-vg in -8..7, all as wrapped signed bytes */
-	const uint32_t dg = (d >> 8) & 0xFFu;
-	const uint32_t g32 = (dg + 32u) & 0xFFu;
-	/* two 16-bit lanes: 0x108 + d_c - dg never borrows; the low byte of each lane is (d_c - dg + 8) mod 256 */
-	const uint32_t t2 = (((d & 0x00FF00FFu) | 0x01000100u) + 0x00080008u - dg * 0x00010001u) & 0x00FF00FFu;
-	c.luma = !c.diff && c.a_eq && g32 < 64u && (t2 & 0x00F000F0u) == 0u;
-	const uint32_t luma_b1 = ((t2 & 0xFu) << 4) | (t2 >> 16);
-	c.b0 = c.diff ? diff_b : (c.luma ? (0x80u | g32) : (c.a_eq ? 0xFEu : 0xFFu)); /* qoi.h:461-473 */
-	c.b1 = c.luma ? luma_b1 : (v & 0xFFu);
+	/* three 2-bit fields at bits 0, 8, 16 -> one 6-bit field: the multiplier drops them next to each other at bits 16..21 */
+	c.diff_b = 0x40u | ((((t & 0x00030303u) * 0x00100401u) >> 16) & 0x3Fu);
+	/* LUMA (qoi.h:443-444, 453-459): vg in -32..31, vr-vg and vb-vg in -8..7.  Signed dot products of the difference
+	   bytes give vg + 32, vr - vg + 8, vb - vg + 8 in one instruction each (FMA pipe; the ALU pipe is this kernel's limit).
+	   qoi.h wraps vr - vg to a signed char; with vg in -32..31 the wrapped value is in -8..7 exactly when the unwrapped
+	   one is, and the other cases are not LUMA anyway. */
+	const uint32_t g32 = (uint32_t)__dp4a((int)d, 0x00000100, 32);
+	const uint32_t tr = (uint32_t)__dp4a((int)d, 0x0000FF01, 8), tb = (uint32_t)__dp4a((int)d, 0x0001FF00, 8);
+	c.luma = !c.diff && c.a_eq && g32 < 64u && (tr | tb) < 16u;
+	c.luma_b0 = 0x80u | g32;
+	c.luma_b1 = tr * 16u + tb; /* (dr-dg+8) << 4 | (db-dg+8) */
 	return c;
 }
 
@@ -384,9 +425,10 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 	if (service) {
 		/* =============================== service warp =============================== */
 		Fetch F;
-		ticket_resolve(P, ticket_take(P), F);
+		ticket_resolve<CH>(P, ticket_take(P), F);
 		fetch_issue<CH, EXPAND>(P, smem, F, 0);
 		int cur = 0;
+		uint32_t par = 0; /* tile parity of this CTA: which copy of wtot[] / misc[] belongs to the tile */
 		while (F.any) {
 			const TileInfo *ti = infos + cur;
 			const uint32_t t = F.tile;
@@ -440,12 +482,21 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 				st_relaxed_u64(&P.st.sum[(size_t)t * QOI_SUM_WORDS + QOI_SUM_INC_LNR], pack_sum(epoch, (uint32_t)inc_lnr));
 			}
 
-			bar_sync(BAR_B_DONE, QOI_N_CS); /* slab sizes are in wtot[]; nobody reads the pixel buffer any more */
-			const uint32_t tk_next = ticket_take(P); /* in flight while the offset look-back runs */
+			/* the next tile's ticket: taken while the compute warps are in pass B, so the tile starts a fixed, short time
+			   after its ticket (a ticket taken a whole tile ahead lets a predecessor tile sit unstarted behind another tile of
+			   its CTA while its successors already look back for it) */
+			Fetch Fn;
+			ticket_resolve<CH>(P, ticket_take(P), Fn);
+			const uint32_t img_cur = ti->img, npx_cur = ti->npx, nv_cur = ti->n_valid;
+			const uint64_t so_cur = ti->stream_off;
+			const uint32_t w_cur = ti->width, h_cur = ti->height, cc_cur = ti->chan_cs;
+
+			bar_sync(BAR_B_DONE, QOI_N_CS); /* slab sizes are in wtot[par]; nobody reads the pixel buffer any more */
+			fetch_issue<CH, EXPAND>(P, smem, Fn, cur ^ 1); /* its info record, its pixels on their way */
 			/* ---- phase B: output offset look-back, 32 predecessors per probe ---- */
 			uint32_t total = 0;
 #pragma unroll
-			for (int w = 0; w < QOI_ENC_WARPS; w++) total += wtot[w];
+			for (int w = 0; w < QOI_ENC_WARPS; w++) total += wtot[par * QOI_ENC_WARPS + w];
 			uint32_t excl = QOI_HEADER_BYTES;
 			if (t != first_tile) {
 				if (lane == 0) st_relaxed_u64(&P.st.byte_state[t], pack_bytes(epoch, QOI_ST_AGG, total));
@@ -478,17 +529,10 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 			}
 			if (lane == 0) {
 				st_relaxed_u64(&P.st.byte_state[t], pack_bytes(epoch, QOI_ST_INC, excl + total));
-				misc[MISC_TILE_BASE] = excl;
+				misc[MISC_TILE_BASE + par] = excl;
 			}
 			__syncwarp();
 			bar_arrive(BAR_B_READY, QOI_N_CS);
-			/* the next tile: which one, its info record, its pixels on their way */
-			Fetch Fn;
-			ticket_resolve(P, tk_next, Fn);
-			const uint32_t img_cur = ti->img, npx_cur = ti->npx, nv_cur = ti->n_valid;
-			const uint64_t so_cur = ti->stream_off;
-			const uint32_t w_cur = ti->width, h_cur = ti->height, cc_cur = ti->chan_cs;
-			fetch_issue<CH, EXPAND>(P, smem, Fn, cur ^ 1);
 			{
 				uint8_t *gstream = P.streams + so_cur;
 				if (t == first_tile && lane < QOI_HEADER_BYTES) { /* header, qoi.h:384-388 */
@@ -508,6 +552,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 					else P.lens[img_cur] = (int32_t)(fin + QOI_END_BYTES);
 				}
 			}
+			par ^= 1u;
 			F = Fn;
 			cur ^= 1;
 		}
@@ -532,6 +577,48 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 	const uint32_t lanebit = 1u << lane;
 	int cur = 0;
 	uint32_t parity = 0;
+	/* the tile whose op bytes sit in my slab, waiting for its output offset (copied out one tile late, see the header) */
+	bool c_valid = false;
+	uint32_t c_t = 0, c_bytes = 0, c_px0 = 0, c_par = 0, c_rs_off = 0xFFFFFFFFu, c_rs_prev = 0;
+	int32_t c_rs_cand = INT_MAX;
+	uint8_t *c_gstream = nullptr;
+	/* ---- phase C: my slab -> tile base + bytes of the warps before me (byte-shifted 16-byte copy), restart record ---- */
+	auto copy_out = [&]() {
+		bar_sync(BAR_B_READY, QOI_N_CS); /* that tile's output offset is in misc[] */
+		uint32_t woff = misc[MISC_TILE_BASE + c_par];
+#pragma unroll
+		for (int w2 = 0; w2 < QOI_ENC_WARPS - 1; w2++)
+			if ((uint32_t)w2 < warp) woff += wtot[c_par * QOI_ENC_WARPS + w2];
+		if (warp == 0) { /* restart record: the lane that owns the restart pixel knows where its op starts */
+			if (c_rs_off != 0xFFFFFFFFu) {
+				P.st.rs_px[c_t] = (int32_t)c_px0 + c_rs_cand;
+				P.st.rs_byte[c_t] = (int32_t)(woff + c_rs_off);
+				P.st.rs_prev[c_t] = c_rs_prev;
+			}
+			if (lane == 0 && c_rs_cand == INT_MAX) P.st.rs_px[c_t] = -1;
+		}
+		uint8_t *gdst = c_gstream + woff;
+		const uint32_t total = c_bytes;
+		uint32_t head = (16u - (uint32_t)((uintptr_t)gdst & 15u)) & 15u; /* bytes up to the first aligned 16 */
+		if (head > total) head = total;
+		const uint32_t nvec = (total - head) >> 4;
+		if (lane < head) gdst[lane] = slab[lane];
+		const uint32_t *s32 = (const uint32_t *)slab + (head >> 2);
+		const uint32_t shf = (head & 3u) * 8u;
+		for (uint32_t k = lane; k < nvec; k += 32u) {
+			const uint32_t *w = s32 + 4u * k;
+			const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+			uint4 q;
+			q.x = __funnelshift_r(w0, w1, shf);
+			q.y = __funnelshift_r(w1, w2, shf);
+			q.z = __funnelshift_r(w2, w3, shf);
+			q.w = __funnelshift_r(w3, w4, shf);
+			st_stream_u4((uint4 *)(gdst + head + 16u * k), q);
+		}
+		const uint32_t tail0 = head + 16u * nvec;
+		if (tail0 + lane < total) gdst[tail0 + lane] = slab[tail0 + lane]; /* fewer than 16 bytes */
+		__syncwarp(); /* the slab is free for the next tile's pass B */
+	};
 	while (true) {
 		mbar_wait(mbar, parity); /* info record and pixels of the tile have landed */
 		parity ^= 1u;
@@ -570,8 +657,10 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 #pragma unroll 2
 			for (int s = 0; s < QOI_WARP_ROWS; s++, px += 32, il += 32u) {
 				const uint32_t v = px[0], p = px[-1];
-				const bool nonrun = il < nv && v != p; /* qoi.h:415 */
+				const bool valid = il < nv;
+				const bool nonrun = valid && v != p; /* qoi.h:415 */
 				const uint32_t nr = __ballot_sync(QOI_FULL_MASK, nonrun);
+				const uint32_t vm = __ballot_sync(QOI_FULL_MASK, valid);
 				uint32_t hb = 0, ub = 0;
 				if (nr) { /* uniform: a row of run pixels touches nothing */
 					const uint32_t h = qoi_slot(v);
@@ -585,13 +674,15 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 					if (nonrun && (m & gt) == 0u) wtab[h] = make_uint2(v, 1u); /* qoi.h:436: the row's last pixel of its slot */
 					last_nr = (int32_t)(il - lane + 31u - (uint32_t)__clz((int)nr));
 				}
-				if (lane == 0) rows[s] = make_uint4(nr, hb, ub, 0u);
+				if (lane == 0) rows[s] = make_uint4(nr, hb, ub, vm);
 				__syncwarp(); /* the next row reads the table after these stores */
 			}
 			if (lane == 0) wlnr[warp] = last_nr;
 		}
 		__syncwarp();
 		bar_arrive(BAR_A_DONE, QOI_N_CS);
+
+		if (c_valid) copy_out(); /* the tile before this one leaves while the service warp looks back for this one */
 
 		bar_sync(BAR_T_READY, QOI_N_CS); /* every warp's table is final; index[] before the tile and the run carry are in shared memory */
 		/* ---- phase M: index[] before my chunk = nearest earlier warp that wrote the slot, else the tile's incoming table ---- */
@@ -625,28 +716,30 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 		{
 			const uint32_t *px = pix + wbase + lane;
 			uint32_t gi = px0 + wbase + lane;      /* my pixel's index in the image */
-			int32_t left = (int32_t)nv - (int32_t)wbase; /* valid pixels from this row on */
-			auto row = [&](auto has_nonrun, auto has_run, int s, const uint4 ri, uint32_t vmask) {
-				constexpr bool NR = decltype(has_nonrun)::value, RUN = decltype(has_run)::value;
-				const uint32_t nr = ri.x;
+			auto row = [&](auto has_nonrun, auto has_run, auto is_head, int s, const uint4 ri) {
+				constexpr bool NR = decltype(has_nonrun)::value, RUN = decltype(has_run)::value, HEAD = decltype(is_head)::value;
+				const uint32_t nr = ri.x, vmask = ri.w;
 				const uint32_t v = px[0], p = px[-1];
 				const bool nonrun = (nr & lanebit) != 0u;
-				bool one = false, two = false, four = false, five = false; /* op sizes: 1 | 2 | 4 (+1) */
+				/* op classes of my pixel (at most one is set): INDEX hit, DIFF, LUMA, RGB / RGBA, RUN byte */
+				bool c_hit = false, c_diff = false, c_luma = false, c_abs = false, c_a5 = false, c_run = false;
 				bool opstart = true;
-				uint32_t b0 = 0, b1 = 0;
+				uint32_t h = 0, b_diff = 0, b_luma0 = 0, b1 = 0, b_run = 0;
 				if (NR) {
-					const uint32_t h = qoi_slot(v);
+					h = qoi_slot(v);
 					bool hit = (ri.y & lanebit) != 0u;
 					if (ri.z) { /* uniform: a slot's first pixel in my chunk -- qoi.h:432 against index[] before the chunk */
 						if ((ri.z & lanebit) && tin[h] == v) hit = true;
 					}
 					const OpClass c = classify(v, p);
-					one = nonrun && (hit || c.diff);
-					two = nonrun && !hit && c.luma;
-					four = nonrun && !hit && !c.diff && !c.luma;
-					five = four && !c.a_eq;
-					b0 = hit ? h : c.b0; /* QOI_OP_INDEX | slot, qoi.h:433 */
-					b1 = c.b1;
+					c_hit = nonrun && hit;
+					c_diff = nonrun && !hit && c.diff;
+					c_luma = nonrun && !hit && c.luma;
+					c_abs = nonrun && !hit && !c.diff && !c.luma;
+					c_a5 = c_abs && !c.a_eq;
+					b_diff = c.diff_b;
+					b_luma0 = c.luma_b0;
+					b1 = c.luma ? c.luma_b1 : v; /* second byte: LUMA's, or r of RGB / RGBA (only the low byte is stored) */
 				}
 				if (RUN) { /* qoi.h:415-421 */
 					const uint32_t nx = px[1];
@@ -655,18 +748,16 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 					const uint32_t r = (gi - lnr_i - 1u) % 62u; /* (position in the run - 1) % 62 */
 					const bool isrun = !nonrun && (vmask & lanebit) != 0u;
 					/* a byte leaves at run length 62, at the image end, or when the run ends */
-					if (isrun) {
-						one = r == 61u || nx != v || gi == last_px;
-						b0 = 0xC0u | r;
-						opstart = r == 0u;
-					}
+					c_run = isrun && (r == 61u || nx != v || gi == last_px);
+					b_run = 0xC0u | r;
+					if (isrun) opstart = r == 0u;
 				}
 				/* byte offsets inside the row: sizes are 0, 1, 2, 4 or 5 -> three bit planes */
-				const uint32_t s1 = __ballot_sync(QOI_FULL_MASK, one || five);
-				const uint32_t s2 = NR ? __ballot_sync(QOI_FULL_MASK, two) : 0u;
-				const uint32_t s4 = NR ? __ballot_sync(QOI_FULL_MASK, four) : 0u;
+				const uint32_t s1 = __ballot_sync(QOI_FULL_MASK, c_hit || c_diff || c_run || c_a5);
+				const uint32_t s2 = NR ? __ballot_sync(QOI_FULL_MASK, c_luma) : 0u;
+				const uint32_t s4 = NR ? __ballot_sync(QOI_FULL_MASK, c_abs) : 0u;
 				const uint32_t ex = (uint32_t)__popc(s1 & lt) + (NR ? 2u * (uint32_t)__popc(s2 & lt) + 4u * (uint32_t)__popc(s4 & lt) : 0u);
-				if (warp == 0 && s < 2 && rs_cand == INT_MAX) { /* a RUN op covers <= 62 pixels: the restart point lies in the first two rows */
+				if (HEAD && rs_cand == INT_MAX) { /* a RUN op covers <= 62 pixels: the restart point lies in the tile's first two rows */
 					const uint32_t starts = __ballot_sync(QOI_FULL_MASK, opstart && (vmask & lanebit));
 					if (starts) {
 						const uint32_t first = (uint32_t)__ffs((int)starts) - 1u;
@@ -677,74 +768,61 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 						}
 					}
 				}
+				/* the op bytes: one predicated byte store per case (the LSU pipe has room, the ALU pipe that a chain of
+				   selects would use has not) */
 				unsigned char *o = slab + off + ex;
-				if (one || two || four) o[0] = (uint8_t)b0;
+				if (RUN && c_run) o[0] = (uint8_t)b_run;
 				if (NR) {
-					if (two || four) o[1] = (uint8_t)b1;
-					if (four) o[2] = (uint8_t)(v >> 8);
-					if (four) o[3] = (uint8_t)(v >> 16);
-					if (five) o[4] = (uint8_t)(v >> 24);
+					if (c_hit) o[0] = (uint8_t)h; /* QOI_OP_INDEX | slot, qoi.h:433 */
+					if (c_diff) o[0] = (uint8_t)b_diff;
+					if (c_luma) o[0] = (uint8_t)b_luma0;
+					if (c_abs) o[0] = c_a5 ? (uint8_t)0xFF : (uint8_t)0xFE; /* qoi.h:461-473 */
+					if (c_luma || c_abs) o[1] = (uint8_t)b1;
+					if (c_abs) o[2] = (uint8_t)__umulhi(v, 1u << 24); /* v >> 8 on the FMA pipe */
+					if (c_abs) o[3] = (uint8_t)__umulhi(v, 1u << 16);
+					if (c_a5) o[4] = (uint8_t)__umulhi(v, 1u << 8);
 				}
 				off += (uint32_t)__popc(s1) + (NR ? 2u * (uint32_t)__popc(s2) + 4u * (uint32_t)__popc(s4) : 0u);
 				if (NR) lnr = (int32_t)(gi - lane + 31u - (uint32_t)__clz((int)nr));
 			};
-#pragma unroll 1
-			for (int s = 0; s < QOI_WARP_ROWS; s++, px += 32, gi += 32u, left -= 32) {
+			auto pick = [&](auto is_head, int s) {
 				const uint4 ri = rows[s];
-				const uint32_t vmask = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
-				if (ri.x == vmask) {
-					if (vmask) row(Yes(), No(), s, ri, vmask); /* every pixel starts an op of its own */
+				if (ri.x == ri.w) {
+					if (ri.w) row(Yes(), No(), is_head, s, ri); /* every pixel starts an op of its own */
 				} else if (ri.x == 0u) {
-					row(No(), Yes(), s, ri, vmask);
+					row(No(), Yes(), is_head, s, ri);
 				} else {
-					row(Yes(), Yes(), s, ri, vmask);
+					row(Yes(), Yes(), is_head, s, ri);
 				}
+				px += 32;
+				gi += 32u;
+			};
+			int s0 = 0;
+			if (warp == 0) { /* uniform: the decoder's restart point of the tile is found in warp 0's first two rows */
+				pick(Yes(), 0);
+				pick(Yes(), 1);
+				s0 = 2;
 			}
+#pragma unroll 1
+			for (int s = s0; s < QOI_WARP_ROWS; s++) pick(No(), s);
 		}
-		if (lane == 0) wtot[warp] = off;
-		uint8_t *gstream = P.streams + ti->stream_off;
+		const uint32_t tpar = (parity ^ 1u) & 1u; /* 0 for the CTA's first tile, like the service warp's `par` */
+		if (lane == 0) wtot[tpar * QOI_ENC_WARPS + warp] = off;
+		c_valid = true;
+		c_t = t;
+		c_bytes = off;
+		c_px0 = px0;
+		c_par = tpar;
+		c_rs_off = rs_off;
+		c_rs_prev = rs_prev;
+		c_rs_cand = rs_cand;
+		c_gstream = P.streams + ti->stream_off;
 		__syncwarp();
 		bar_arrive(BAR_B_DONE, QOI_N_CS);
-
-		bar_sync(BAR_B_READY, QOI_N_CS);
-		/* ---- phase C: my slab -> tile base + bytes of the warps before me (byte-shifted 16-byte copy) ---- */
-		{
-			uint32_t woff = misc[MISC_TILE_BASE];
-#pragma unroll
-			for (int w2 = 0; w2 < QOI_ENC_WARPS - 1; w2++)
-				if ((uint32_t)w2 < warp) woff += wtot[w2];
-			if (warp == 0) { /* restart record: the lane that owns the restart pixel knows where its op starts */
-				if (rs_off != 0xFFFFFFFFu) {
-					P.st.rs_px[t] = (int32_t)px0 + rs_cand;
-					P.st.rs_byte[t] = (int32_t)(woff + rs_off);
-					P.st.rs_prev[t] = rs_prev;
-				}
-				if (lane == 0 && rs_cand == INT_MAX) P.st.rs_px[t] = -1;
-			}
-			uint8_t *gdst = gstream + woff;
-			const uint32_t total = off;
-			uint32_t head = (16u - (uint32_t)((uintptr_t)gdst & 15u)) & 15u; /* bytes up to the first aligned 16 */
-			if (head > total) head = total;
-			const uint32_t nvec = (total - head) >> 4;
-			if (lane < head) gdst[lane] = slab[lane];
-			const uint32_t *s32 = (const uint32_t *)slab + (head >> 2);
-			const uint32_t shf = (head & 3u) * 8u;
-			for (uint32_t k = lane; k < nvec; k += 32u) {
-				const uint32_t *w = s32 + 4u * k;
-				const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-				uint4 q;
-				q.x = __funnelshift_r(w0, w1, shf);
-				q.y = __funnelshift_r(w1, w2, shf);
-				q.z = __funnelshift_r(w2, w3, shf);
-				q.w = __funnelshift_r(w3, w4, shf);
-				st_stream_u4((uint4 *)(gdst + head + 16u * k), q);
-			}
-			const uint32_t tail0 = head + 16u * nvec;
-			if (tail0 + lane < total) gdst[tail0 + lane] = slab[tail0 + lane]; /* fewer than 16 bytes */
-		}
-		__syncwarp();
 		cur ^= 1;
 	}
+	if (c_valid) copy_out(); /* the CTA's last tile */
 }
+
 
 }  // namespace qoienc

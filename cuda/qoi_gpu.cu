@@ -94,11 +94,10 @@ struct DeviceGuard {
 		}                                                                                     \
 	} while (0)
 
-static_assert(QOI_FFIX_SMEM <= 48 * 1024 && QOI_FCHAIN_SMEM <= 48 * 1024 && QOI_FVER_CHUNKS_HOST == QOI_FVER_CHUNKS && QOI_FDEC_ROUNDS < 60, "these kernels are launched without a shared-memory opt-in");
-/* the speculative decoder's blocks need more than the default 48 KB of dynamic shared memory */
+static_assert(QOI_FFALL_SMEM <= 48 * 1024 && QOI_FCHAIN_SMEM <= 48 * 1024 && QOI_FCHUNK_HOST == QOI_FCHUNK && QOI_FROUNDS < 60, "these kernels are launched without a shared-memory opt-in");
+/* the state-round blocks need more than the default 48 KB of dynamic shared memory */
 static int fdec_setup(qoi_gpu_ctx *ctx) {
-	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
-	CK(ctx, cudaFuncSetAttribute(qoifdec::fdecode_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
+	if (QOI_FDEC_SMEM > 48 * 1024) CK(ctx, cudaFuncSetAttribute(qoifdec::fstate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QOI_FDEC_SMEM));
 	return QOI_GPU_OK;
 }
 
@@ -281,43 +280,49 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 	cudaStream_t s = (cudaStream_t)cuda_stream;
 	DeviceGuard guard(ctx->device);
 	if (!use_index) {
-		/* any stream: exact parse scan, speculative segment decode, verification, exact fix-up (qoi_fdec.cuh) */
+		/* any stream: build the restart index (parse, state rounds, scans, fall-back; qoi_fdec.cuh), then decode with it below */
 		static_assert(QOI_FSEG_BYTES_HOST == QOI_FSEG_BYTES, "segment size");
 		if (!p->d_fstate) {
 			p->flayout = qoi_fstate_layout(p->geom);
 			CK(ctx, cudaMalloc(&p->d_fstate, p->flayout.total));
-			/* on the launching stream, so that the kernels below are ordered behind the initialisation (seg_base lives in the plan) */
+			/* on the launching stream, so that the kernels below are ordered behind the initialisation (the host arrays live in the plan) */
 			CK(ctx, cudaMemsetAsync(p->d_fstate, 0, p->flayout.total, s));
 			CK(ctx, cudaMemcpyAsync(p->d_fstate + p->flayout.off[0], p->flayout.seg_base.data(), p->flayout.seg_base.size() * sizeof(uint32_t),
+			                        cudaMemcpyHostToDevice, s));
+			CK(ctx, cudaMemcpyAsync(p->d_fstate + p->flayout.off[1], p->flayout.chunk_base.data(), p->flayout.chunk_base.size() * sizeof(uint32_t),
 			                        cudaMemcpyHostToDevice, s));
 		}
 		qoifdec::QoiFParams F;
 		memset(&F, 0, sizeof F);
 		F.streams = (const uint8_t *)d_streams;
 		F.lens = d_lens;
-		F.out = (uint8_t *)d_decoded;
 		F.status = d_status;
 		F.imgs = p->d_metas;
 		F.n_images = (uint32_t)p->geom.metas.size();
 		F.n_segs = p->flayout.n_segs;
-		F.out_channels = p->geom.dec_channels;
+		F.n_chunks = p->flayout.n_chunks;
+		F.st = p->st;
 		qoifdec::fstate_bind(F.f, p->d_fstate, p->flayout.off);
 		const uint32_t gs = (F.n_segs + QOI_FDEC_THREADS - 1) / QOI_FDEC_THREADS;
 		qoifdec::fparse_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
 		qoifdec::fchain_kernel<<<F.n_images, 32, QOI_FCHAIN_SMEM, s>>>(F);
 		qoifdec::fzero_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
-		for (int r = 0; r < QOI_FDEC_ROUNDS; r++) {
+		for (int r = 0; r < QOI_FROUNDS; r++) {
 			F.round = (uint32_t)r;
-			if (F.out_channels == 4) qoifdec::fdecode_kernel<4, true><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
-			else qoifdec::fdecode_kernel<3, true><<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
-			if (r + 1 < QOI_FDEC_ROUNDS) qoifdec::fverify_kernel<<<F.n_images * QOI_FVER_CHUNKS, 32, 0, s>>>(F);
+			const int last = r + 1 == QOI_FROUNDS;
+			qoifdec::fstate_kernel<<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
+			qoifdec::fscan_a_kernel<<<F.n_chunks, QOI_FSCAN_THREADS, 0, s>>>(F);
+			qoifdec::fscan_b_kernel<<<F.n_images, QOI_FSCAN_THREADS, 0, s>>>(F);
+			qoifdec::fcheck_kernel<<<F.n_chunks, QOI_FSCAN_THREADS, QOI_FCHECK_SMEM, s>>>(F, last);
+			qoifdec::fapply_kernel<<<F.n_chunks, QOI_FSCAN_THREADS, QOI_FCHECK_SMEM, s>>>(F, last);
+			qoifdec::frearm_kernel<<<(F.n_images + 127) / 128, 128, 0, s>>>(F);
 		}
-		F.round = QOI_FDEC_ROUNDS - 1; /* reads what the last verify pass wrote */
-		if (F.out_channels == 4) qoifdec::ffix_kernel<4><<<F.n_images, 32, QOI_FFIX_SMEM, s>>>(F);
-		else qoifdec::ffix_kernel<3><<<F.n_images, 32, QOI_FFIX_SMEM, s>>>(F);
-		g_launches += 3 + 2 * QOI_FDEC_ROUNDS;
+		qoifdec::ffall_kernel<<<F.n_images, 32, QOI_FFALL_SMEM, s>>>(F);
+		qoifdec::fcompose_kernel<<<(p->geom.n_tiles * 64u + 127u) / 128u, 128, 0, s>>>(F, p->geom.n_tiles, p->d_tile_img);
+		g_launches += 5 + 6 * QOI_FROUNDS;
 		CK(ctx, cudaGetLastError());
-		return QOI_GPU_OK;
+		p->index_owner = 1; /* the plan now holds the restart index of THESE streams (it can be exported as a side-car) */
+		d_status = nullptr; /* reported by fchain_kernel */
 	}
 	QoiDecParams D;
 	memset(&D, 0, sizeof D);

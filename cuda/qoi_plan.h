@@ -135,12 +135,14 @@ static inline void qoi_state_bind(QoiTileState &st, unsigned char *base, const Q
 
 /* ------------------------------------------------------------------ foreign-stream decoder scratch (qoi_fdec.cuh) */
 #define QOI_FSEG_BYTES_HOST 4096 /* must equal QOI_FSEG_BYTES */
-#define QOI_FVER_CHUNKS_HOST 8 /* must equal QOI_FVER_CHUNKS */
+#define QOI_FCHUNK_HOST 64       /* must equal QOI_FCHUNK: segments per scan chunk */
+#define QOI_F_ARRAYS 30
 
 struct QoiFLayout {
-	std::vector<uint32_t> seg_base; /* [n + 1] */
-	uint32_t n_segs = 0;
-	size_t off[22];
+	std::vector<uint32_t> seg_base;   /* [n + 1] first segment of each image (capacity) */
+	std::vector<uint32_t> chunk_base; /* [n + 1] first scan chunk of each image */
+	uint32_t n_segs = 0, n_chunks = 0;
+	size_t off[QOI_F_ARRAYS];
 	size_t total = 0;
 };
 
@@ -148,18 +150,27 @@ static inline QoiFLayout qoi_fstate_layout(const QoiPlanGeom &g) {
 	QoiFLayout L;
 	const size_t n = g.metas.size();
 	L.seg_base.resize(n + 1);
-	uint64_t segs = 0;
+	L.chunk_base.resize(n + 1);
+	uint64_t segs = 0, chunks = 0;
 	for (size_t i = 0; i < n; i++) {
 		L.seg_base[i] = (uint32_t)segs;
+		L.chunk_base[i] = (uint32_t)chunks;
 		const uint64_t worst = (uint64_t)g.metas[i].npx * 5u; /* longest chunk area a decoder can consume */
-		segs += (worst + QOI_FSEG_BYTES_HOST - 1) / QOI_FSEG_BYTES_HOST + 1;
+		const uint64_t s_img = (worst + QOI_FSEG_BYTES_HOST - 1) / QOI_FSEG_BYTES_HOST + 1;
+		segs += s_img;
+		chunks += (s_img + QOI_FCHUNK_HOST - 1) / QOI_FCHUNK_HOST;
 	}
 	L.seg_base[n] = (uint32_t)segs;
+	L.chunk_base[n] = (uint32_t)chunks;
 	L.n_segs = (uint32_t)segs;
-	const size_t S = segs, N = n;
-	const size_t sizes[22] = {(N + 1) * 4, S * 20, S * 8, S, S * 4, N * 4, S * 4, S * 256, S * 4, S * 256, S * 8, S * 8, S * 4, S, N * 8, N * 8, N * 512, S * 128, S * 4, 256, N * 2 * QOI_FVER_CHUNKS_HOST * 65 * 4, N * 12};
+	L.n_chunks = (uint32_t)chunks;
+	const size_t S = segs, N = n, C = chunks, TL = g.n_tiles;
+	const size_t sizes[QOI_F_ARRAYS] = {(N + 1) * 4, (N + 1) * 4, S * 20, S * 8,      S,         S * 4,     N * 4,     S * 4,
+	                                    S * 256,     S * 4,       S * 256, S * 8,      S * 8,     S * 4,     S,         S * 4,
+	                                    64 * 4,      C * 256,     C * 8,   C * 8,      C * 256,   C * 4,     N * 4 * 2, N * 4,
+	                                    S * 8,       S * 20,      S * 4,   TL * 8,     TL * 4,    N * 65 * 4};
 	size_t o = 0;
-	for (int k = 0; k < 22; k++) {
+	for (int k = 0; k < QOI_F_ARRAYS; k++) {
 		L.off[k] = o;
 		o += (sizes[k] + 255) & ~(size_t)255;
 	}

@@ -37,9 +37,22 @@ def build_multi(force=False):
     Host code only; a separate library so that the codec library itself does not depend on NCCL."""
     if not force and os.path.exists(MULTI_LIB) and all(os.path.getmtime(s) <= os.path.getmtime(MULTI_LIB) for s in MULTI_SOURCES + [LIB]):
         return MULTI_LIB
-    cmd = [find_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "-o", MULTI_LIB,
-           os.path.join(ROOT, "cuda", "qoi_gpu_multi.cu"), "-L" + os.path.join(ROOT, "qoi_b200"), "-lqoi_gpu", "-lnccl",
-           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    # One NCCL per process: PyTorch loads the libnccl.so.2 of the nvidia-nccl wheel; a second, older copy with the same SONAME
+    # loaded first would be handed to torch as well and miss symbols.  So link against that copy when it exists (same file for
+    # both), else the system library.
+    nccl_inc, nccl_lib = [], ["-lnccl"]
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        base = list(spec.submodule_search_locations)[0] if spec and spec.submodule_search_locations else None
+        if base and os.path.exists(os.path.join(base, "lib", "libnccl.so.2")):
+            nccl_inc = ["-I" + os.path.join(base, "include")]
+            nccl_lib = ["-Xlinker", os.path.join(base, "lib", "libnccl.so.2"), "-Xlinker", "-rpath", "-Xlinker", os.path.join(base, "lib")]
+    except Exception:
+        pass
+    cmd = [find_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "-o", MULTI_LIB] + nccl_inc + \
+          [os.path.join(ROOT, "cuda", "qoi_gpu_multi.cu"), "-L" + os.path.join(ROOT, "qoi_b200"), "-lqoi_gpu"] + nccl_lib + \
+          ["-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
     if os.path.exists("/usr/bin/g++"):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
     res = subprocess.run(cmd, capture_output=True, text=True)

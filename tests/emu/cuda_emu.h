@@ -388,6 +388,10 @@ static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
 	for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xFF) * ((b >> (8 * i)) & 0xFF);
 	return c;
 }
+static inline int __dp4a(int a, int b, int c) { /* signed bytes x signed bytes */
+	for (int i = 0; i < 4; i++) c += (int)(int8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i));
+	return c;
+}
 static inline unsigned __vsub4(unsigned a, unsigned b) {
 	unsigned r = 0;
 	for (int i = 0; i < 4; i++) r |= ((((a >> (8 * i)) & 0xFF) - ((b >> (8 * i)) & 0xFF)) & 0xFF) << (8 * i);

@@ -58,50 +58,66 @@ static void run_decode(const QoiDecParams &P, unsigned seed) {
 	else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_ahead()) qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true, true>(P); else if (emu_uni()) qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true, false>(P); else qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, false, false>(P); }, seed);
 }
 
-/* the foreign-stream pipeline exactly as qoi_gpu_decode enqueues it */
-static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned seed, int rounds = QOI_FDEC_ROUNDS) {
-	static_assert(QOI_FSEG_BYTES_HOST == QOI_FSEG_BYTES, "segment size");
+/* the foreign-stream pipeline exactly as qoi_gpu_decode enqueues it: build the restart index, then the tile decoder */
+static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned seed, int rounds = QOI_FROUNDS) {
+	static_assert(QOI_FSEG_BYTES_HOST == QOI_FSEG_BYTES && QOI_FCHUNK_HOST == QOI_FCHUNK, "segment / chunk size");
 	QoiFLayout FL = qoi_fstate_layout(g);
 	std::vector<unsigned char> store(FL.total + 256, 0x5A);
 	unsigned char *base = (unsigned char *)(((uintptr_t)store.data() + 255) & ~(uintptr_t)255);
+	memset(base, 0, FL.total);
 	memcpy(base + FL.off[0], FL.seg_base.data(), FL.seg_base.size() * 4);
+	memcpy(base + FL.off[1], FL.chunk_base.data(), FL.chunk_base.size() * 4);
+	/* the index goes where the plan keeps it; a caller without one (mode `dec`) gets a scratch copy */
+	QoiStateLayout SL = qoi_state_layout(g.n_tiles);
+	std::vector<unsigned char> idx_store;
+	QoiTileState st = D.st;
+	if (!st.ent) {
+		idx_store.assign(SL.total + 256, 0x3C);
+		qoi_state_bind(st, (unsigned char *)(((uintptr_t)idx_store.data() + 255) & ~(uintptr_t)255), SL);
+	}
 	qoifdec::QoiFParams F;
 	memset(&F, 0, sizeof F);
-	F.streams = D.streams; F.lens = D.lens; F.out = D.out; F.status = D.status; F.imgs = D.imgs;
-	F.n_images = D.n_images; F.n_segs = FL.n_segs; F.out_channels = D.out_channels;
+	F.streams = D.streams; F.lens = D.lens; F.status = D.status; F.imgs = D.imgs;
+	F.n_images = D.n_images; F.n_segs = FL.n_segs; F.n_chunks = FL.n_chunks;
+	F.st = st;
 	qoifdec::fstate_bind(F.f, base, FL.off);
-	const unsigned gs = (FL.n_segs + QOI_FDEC_THREADS - 1) / QOI_FDEC_THREADS, gi = (D.n_images + 31) / 32;
+	const unsigned gs = (FL.n_segs + QOI_FDEC_THREADS - 1) / QOI_FDEC_THREADS;
 	qemu::launch(gs, QOI_FDEC_THREADS, 0, [&]() { qoifdec::fparse_kernel(F); }, seed);
 	qemu::launch(D.n_images, 32, QOI_FCHAIN_SMEM, [&]() { qoifdec::fchain_kernel(F); }, seed);
 	qemu::launch(gs, QOI_FDEC_THREADS, 0, [&]() { qoifdec::fzero_kernel(F); }, seed);
-	int extra = 0;
 	for (int r = 0; r < rounds; r++) {
 		F.round = (uint32_t)r;
-		if (D.out_channels == 4) qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { if (emu_uni()) qoifdec::fdecode_kernel<4, true>(F); else qoifdec::fdecode_kernel<4, false>(F); }, seed);
-		else qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { if (emu_uni()) qoifdec::fdecode_kernel<3, true>(F); else qoifdec::fdecode_kernel<3, false>(F); }, seed);
-		if (r + 1 < rounds) qemu::launch(D.n_images * QOI_FVER_CHUNKS, 32, 0, [&]() { qoifdec::fverify_kernel(F); }, seed);
-		if (getenv("QOI_EMU_FTRACE")) {
+		const int last = r + 1 == rounds;
+		qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { qoifdec::fstate_kernel(F); }, seed);
+		qemu::launch(FL.n_chunks, QOI_FSCAN_THREADS, 0, [&]() { qoifdec::fscan_a_kernel(F); }, seed);
+		qemu::launch(D.n_images, QOI_FSCAN_THREADS, 0, [&]() { qoifdec::fscan_b_kernel(F); }, seed);
+		qemu::launch(FL.n_chunks, QOI_FSCAN_THREADS, QOI_FCHECK_SMEM, [&]() { qoifdec::fcheck_kernel(F, last); }, seed);
+		qemu::launch(FL.n_chunks, QOI_FSCAN_THREADS, QOI_FCHECK_SMEM, [&]() { qoifdec::fapply_kernel(F, last); }, seed);
+		qemu::launch((D.n_images + 127) / 128, 128, 0, [&]() { qoifdec::frearm_kernel(F); }, seed);
+		if (getenv("QOI_EMU_FTRACE2")) {
 			for (uint32_t i = 0; i < D.n_images; i++) {
-				fprintf(stderr, "round %d image %u verified %u/%u redo:", r, i, F.f.verified[((uint32_t)r & 1u) * D.n_images + i], F.f.n_live[i]);
-				for (uint32_t j = 0; j < F.f.n_live[i]; j++) if (F.f.redo[F.f.seg_base[i] + j]) fprintf(stderr, " %u", j);
+				fprintf(stderr, "round %d image %u flagged:", r, i);
+				for (uint32_t j = 0; j < F.f.n_live[i]; j++) if (F.f.flag[F.f.seg_base[i] + j]) fprintf(stderr, " %u(%u)", j, F.f.flag[F.f.seg_base[i] + j]);
 				fprintf(stderr, "\n");
 			}
 		}
-	}
-	if (getenv("QOI_EMU_FSTATS")) { /* how much is left for the sequential fix-up (an extra verify pass only marks; ffix stays exact) */
-		F.round = (uint32_t)(rounds - 1);
-		qemu::launch(D.n_images * QOI_FVER_CHUNKS, 32, 0, [&]() { qoifdec::fverify_kernel(F); }, seed);
-		extra = 1;
-		const uint32_t sel = (uint32_t)(rounds - 1) & 1u;
-		for (uint32_t i = 0; i < D.n_images; i++) {
-			uint32_t bad = 0;
-			for (uint32_t j = 0; j < F.f.n_live[i]; j++) bad += F.f.redo[F.f.seg_base[i] + j] ? 1 : 0;
-			fprintf(stderr, "image %u: %u live segments, verified prefix %u, %u segments left to the fix-up after %d rounds\n", i, F.f.n_live[i], F.f.verified[sel * D.n_images + i], bad, rounds);
+		if (getenv("QOI_EMU_FTRACE")) {
+			for (uint32_t i = 0; i < D.n_images; i++)
+				fprintf(stderr, "round %d image %u: %u live segments, %u to walk again, bad_dep %u\n", r, i, F.f.n_live[i], F.f.n_list[r + 1],
+				        F.f.bad_cnt[((uint32_t)r & 1u) * D.n_images + i]);
 		}
 	}
-	F.round = (uint32_t)(rounds - 1 + extra); /* reads what the last verify pass wrote */
-	if (D.out_channels == 4) qemu::launch(D.n_images, 32, QOI_FFIX_SMEM, [&]() { qoifdec::ffix_kernel<4>(F); }, seed);
-	else qemu::launch(D.n_images, 32, QOI_FFIX_SMEM, [&]() { qoifdec::ffix_kernel<3>(F); }, seed);
+	if (getenv("QOI_EMU_FSTATS"))
+		for (uint32_t i = 0; i < D.n_images; i++)
+			fprintf(stderr, "image %u: %u live segments, fall-back from segment %u after %d rounds\n", i, F.f.n_live[i], F.f.first_bad[i], rounds);
+	qemu::launch(D.n_images, 32, QOI_FFALL_SMEM, [&]() { qoifdec::ffall_kernel(F); }, seed);
+	qemu::launch((g.n_tiles * 64u + 127u) / 128u, 128, 0, [&]() { qoifdec::fcompose_kernel(F, g.n_tiles, D.tile_img); }, seed);
+	QoiDecParams I = D;
+	I.use_index = 1;
+	I.n_jobs = g.n_tiles;
+	I.status = nullptr; /* fchain_kernel reported it */
+	I.st = st;
+	run_decode(I, seed);
 }
 
 static int first_diff(const unsigned char *a, const unsigned char *b, size_t n) {
@@ -199,7 +215,7 @@ int main(int argc, char **argv) {
 				D.use_index = use_index;
 				D.st = P.st;
 				if (use_index) run_decode(D, seed);
-				else run_foreign(D, g, seed, getenv("QOI_EMU_FROUNDS") ? atoi(getenv("QOI_EMU_FROUNDS")) : QOI_FDEC_ROUNDS);
+				else run_foreign(D, g, seed, getenv("QOI_EMU_FROUNDS") ? atoi(getenv("QOI_EMU_FROUNDS")) : QOI_FROUNDS);
 				for (int i = 0; i < n; i++) {
 					QoiDescPOD dd;
 					unsigned char *ref = (unsigned char *)ora_decode(streams.data() + soff[i], lens[i], &dd, dec_ch);
@@ -249,7 +265,7 @@ int main(int argc, char **argv) {
 			D.n_jobs = (uint32_t)n;
 			D.out_channels = dec_ch;
 			D.use_index = 0;
-			run_foreign(D, g, seed, getenv("QOI_EMU_FROUNDS") ? atoi(getenv("QOI_EMU_FROUNDS")) : QOI_FDEC_ROUNDS);
+			run_foreign(D, g, seed, getenv("QOI_EMU_FROUNDS") ? atoi(getenv("QOI_EMU_FROUNDS")) : QOI_FROUNDS);
 			for (int i = 0; i < n; i++) {
 				QoiDescPOD dd;
 				unsigned char *ref = (unsigned char *)ora_decode(file.data() + soff[i], lens[i], &dd, dec_ch);
