@@ -79,14 +79,15 @@ struct QoiFState {
 	uint64_t *o_taint;  /* [segs] ... with a value that derives from the guess (incoming colour or a guessed slot) */
 	uint64_t *rbw;      /* [segs] slots of the guess read before the segment wrote them */
 	uint32_t *dep;      /* [segs] bit 0: the result depends on the incoming r,g,b; bit 1: ... on the incoming alpha;
-	                       bit 2: the colour after the segment derives from the guess */
+	                       bits 2,3: r,g,b / alpha of the colour after the segment derive from the guess;
+	                       bits 4,5: ... and do so as "incoming colour + deltas" (DIFF / LUMA / RUN ops only) */
 	uint8_t *flag;      /* [segs] QOI_FF_* of the last check */
 	uint32_t *list;     /* [segs] segments to walk in the next round */
 	uint32_t *n_list;   /* [64] length of that list per round */
 	/* scan */
 	uint32_t *a_tab;    /* [chunks][64] last value written per slot inside the chunk */
 	uint64_t *a_wr;     /* [chunks] slots written inside the chunk */
-	uint64_t *a_px;     /* [chunks] colour after the chunk | 1 << 32 if the chunk has a live segment */
+	uint64_t *a_px;     /* [chunks] the chunk's colour map (seg_colour_map composed over its segments) */
 	uint32_t *p_tab;    /* [chunks][64] index[] before the chunk */
 	uint32_t *p_px;     /* [chunks] colour before the chunk */
 	uint32_t *bad_cnt;  /* [2][n_images] segments with QOI_FF_DEP in the check of this round / the round before (by round parity) */
@@ -361,6 +362,9 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 	   two bits, so that an INDEX op of a slot the segment filled itself inherits them */
 	bool t_rgb = true, t_a = true, dep_rgb = false, dep_a = false;
 	uint64_t tm_rgb = 0, tm_a = 0;
+	/* ... and, if it does: through anything but DIFF / LUMA / RUN ops on the incoming colour?  While it does not, the colour
+	   is "incoming colour + a sum of deltas that do not depend on the guess", which the scan can re-base exactly. */
+	bool d_rgb = false, d_a = false;
 	uint32_t pos = P.f.px_start[g];                                          /* pixel the next op starts at */
 	/* The restart record of a tile belongs to the first op that starts at or behind the tile's first pixel.  `tb` = the next
 	   tile boundary no op has started behind yet; fchain_kernel knows where every segment's last op starts, so the first
@@ -461,6 +465,8 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 		const bool i_rgb = !own_slot || ((tm_rgb >> t6) & 1ull), i_a = !own_slot || ((tm_a >> t6) & 1ull);
 		t_rgb = is_idx ? i_rgb : ((is_rgb || is_rgba) ? false : t_rgb);
 		t_a = is_idx ? i_a : (is_rgba ? false : t_a);
+		d_rgb = is_idx ? i_rgb : ((is_rgb || is_rgba) ? false : d_rgb); /* through index[]: no longer a plain sum of deltas */
+		d_a = is_idx ? i_a : (is_rgba ? false : d_a);
 		/* every op yields at least one pixel of the new colour; while that colour derives from the guessed COLOUR the result
 		   depends on it (a colour that derives from a guessed slot is covered by rbw; counting it here too only makes the
 		   check stricter) */
@@ -486,7 +492,8 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 	P.f.o_wr[g] = wr;
 	P.f.o_taint[g] = (tm_rgb | tm_a) & wr;
 	P.f.rbw[g] = rbw;
-	P.f.dep[g] = (dep_rgb ? 1u : 0u) | (dep_a ? 2u : 0u) | ((t_rgb || t_a) ? 4u : 0u);
+	/* bits 2,3: r,g,b / alpha of the final colour derive from the guess; bits 4,5: ... as incoming colour + deltas only */
+	P.f.dep[g] = (dep_rgb ? 1u : 0u) | (dep_a ? 2u : 0u) | (t_rgb ? 4u : 0u) | (t_a ? 8u : 0u) | ((t_rgb && !d_rgb) ? 16u : 0u) | ((t_a && !d_a) ? 32u : 0u);
 	{
 		uint32_t *dst = P.f.o_tab + (size_t)g * 64;
 #pragma unroll 8
@@ -500,10 +507,41 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
    INDEX ops copies its guess around, and untrusted copies would push every wrong guess one segment further per round. */
 __device__ __forceinline__ bool seg_gives(const QoiFParams &P, uint32_t g, uint32_t t) {
 	const bool trust = (P.f.flag[g] & QOI_FF_TRUST) != 0u;
-	if (t < 64u) return ((P.f.o_wr[g] >> t) & 1ull) && (trust || !((P.f.o_taint[g] >> t) & 1ull));
-	return trust || !(P.f.dep[g] & 4u);
+	return ((P.f.o_wr[g] >> t) & 1ull) && (trust || !((P.f.o_taint[g] >> t) & 1ull));
 }
-
+/* The colour is not "last writer": a segment of DIFF / LUMA / RUN ops adds a known delta to whatever colour enters it.  So
+   the colour's scan composes maps  colour -> (r,g,b: constant c | + d) x (alpha: constant c | unchanged), one per segment.
+   A map word: value bytes (constant or delta per channel), bit 32: r,g,b constant, bit 33: alpha constant. */
+__device__ __forceinline__ uint64_t seg_colour_map(const QoiFParams &P, uint32_t g) {
+	const uint32_t d = P.f.dep[g], o = P.f.o_px[g], gi = P.f.g_px[g];
+	const bool trust = (P.f.flag[g] & QOI_FF_TRUST) != 0u;
+	uint64_t m = 0;
+	uint32_t v = 0;
+	/* r,g,b: from the segment's own bytes, or derived through index[] and trusted -> constant; incoming + deltas -> add;
+	   derived through index[] from a guess that did not hold -> unknown: pass the incoming colour on (delta 0) */
+	if (!(d & 4u) || (!(d & 16u) && trust)) { m |= 1ull << 32; v |= o & 0x00FFFFFFu; }
+	else if (d & 16u) v |= (((o | 0x80808080u) - (gi & 0x7F7F7F7Fu)) ^ ((o ^ ~gi) & 0x80808080u)) & 0x00FFFFFFu; /* o - guess, per byte */
+	/* alpha: no op changes it relatively */
+	if (!(d & 8u) || (!(d & 32u) && trust)) { m |= 1ull << 33; v |= o & 0xFF000000u; }
+	return m | v;
+}
+__device__ __forceinline__ uint32_t colour_apply(uint64_t map, uint32_t px) {
+	const uint32_t v = (uint32_t)map;
+	const uint32_t rgb = (map >> 32) & 1ull ? (v & 0x00FFFFFFu) : (add_bytes(px, v & 0x00FFFFFFu) & 0x00FFFFFFu);
+	const uint32_t a = (map >> 33) & 1ull ? (v & 0xFF000000u) : (px & 0xFF000000u);
+	return rgb | a;
+}
+/* first `a`, then `b` */
+__device__ __forceinline__ uint64_t colour_compose(uint64_t a, uint64_t b) {
+	const uint32_t va = (uint32_t)a, vb = (uint32_t)b;
+	uint64_t m = 0;
+	uint32_t v = 0;
+	if ((b >> 32) & 1ull) { m |= 1ull << 32; v |= vb & 0x00FFFFFFu; }
+	else { m |= a & (1ull << 32); v |= add_bytes(va, vb & 0x00FFFFFFu) & 0x00FFFFFFu; }
+	if ((b >> 33) & 1ull) { m |= 1ull << 33; v |= vb & 0xFF000000u; }
+	else { m |= a & (1ull << 33); v |= va & 0xFF000000u; }
+	return m | v;
+}
 /* a: per chunk of QOI_FCHUNK segments, thread = slot (thread 64 = the colour): the chunk's last value per slot */
 __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_a_kernel(const QoiFParams P) {
 	const uint32_t c = blockIdx.x, t = threadIdx.x;
@@ -528,9 +566,8 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_a_kernel(const QoiFPa
 		const uint32_t b = __ballot_sync(QOI_FULL_MASK, wrote);
 		if ((t & 31u) == 0u) ((uint32_t *)(P.f.a_wr + c))[t >> 5] = b; /* low / high half of the 64-bit mask */
 	} else if (t == 64u) {
-		uint64_t v = 0;
-		for (uint32_t j = 0; j < j1 - j0; j++)
-			if (seg_gives(P, g0 + j, 64u)) v = (uint64_t)P.f.o_px[g0 + j] | (1ull << 32);
+		uint64_t v = 0; /* identity: + 0, alpha unchanged */
+		for (uint32_t j = 0; j < j1 - j0; j++) v = colour_compose(v, seg_colour_map(P, g0 + j));
 		P.f.a_px[c] = v;
 	}
 }
@@ -552,7 +589,7 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_b_kernel(const QoiFPa
 		uint32_t px = 0xFF000000u;
 		for (uint32_t lc = 0; lc < nch; lc++) {
 			P.f.p_px[c0 + lc] = px;
-			if (P.f.a_px[c0 + lc] >> 32) px = (uint32_t)P.f.a_px[c0 + lc];
+			px = colour_apply(P.f.a_px[c0 + lc], px);
 		}
 	}
 }
@@ -572,7 +609,11 @@ __device__ __forceinline__ void walk_chunk(const QoiFParams &P, uint32_t c, uint
 	for (uint32_t j = 0; j < n; j++) {
 		const uint32_t g = g0 + j;
 		body(img, j0 + j, j, g, T);
-		if (t <= 64u && seg_gives(P, g, t)) T = t < 64u ? P.f.o_tab[(size_t)g * 64 + t] : P.f.o_px[g];
+		if (t < 64u) {
+			if (seg_gives(P, g, t)) T = P.f.o_tab[(size_t)g * 64 + t];
+		} else if (t == 64u) {
+			T = colour_apply(seg_colour_map(P, g), T);
+		}
 	}
 }
 
