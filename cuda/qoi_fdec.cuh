@@ -42,12 +42,11 @@ namespace qoifdec {
 using namespace qoidev;
 
 #define QOI_FSEG_BYTES 4096
-#define QOI_FROUNDS 8   /* state rounds before the sequential fall-back */
+#define QOI_FROUNDS 16  /* state rounds before the sequential fall-back */
 #define QOI_FCHUNK 64   /* segments per scan chunk */
 #define QOI_FDEC_THREADS 128
 #define QOI_FSCAN_THREADS 96 /* 64 slot threads + the colour thread (thread 64); a multiple of 32 */
 #define QOI_FDEC_SMEM ((64 + QOI_DEC_RING_WORDS) * QOI_FDEC_THREADS * 4) /* per lane: index[64], stream ring */
-#define QOI_FCHAIN_SMEM ((32 * 5 + 32 * 2 + 32 + 32 + 32 * 5 + 32 + 8) * 4)
 #define QOI_FFALL_SMEM ((64 + QOI_FSEG_BYTES / 4 + 8) * 4) /* index[], one staged segment */
 #define QOI_FCHECK_SMEM (QOI_FCHUNK * 4)
 
@@ -90,7 +89,7 @@ struct QoiFState {
 	uint64_t *a_px;     /* [chunks] the chunk's colour map (seg_colour_map composed over its segments) */
 	uint32_t *p_tab;    /* [chunks][64] index[] before the chunk */
 	uint32_t *p_px;     /* [chunks] colour before the chunk */
-	uint32_t *bad_cnt;  /* [2][n_images] segments with QOI_FF_DEP in the check of this round / the round before (by round parity) */
+	uint32_t *bad_cnt;  /* [3][n_images]; plane 2: the stream has settled (a check found nothing), later rounds skip it; planes 0,1: segments with QOI_FF_DEP in the check of this round / the round before (by round parity) */
 	uint32_t *first_bad;/* [n_images] first segment the last check flagged (n_live if none): where the fall-back starts */
 	/* per tile of the plan: which slots of the restart record's index[] the segment had written when it dropped the record
 	   (the others are filled from the segment's exact incoming state at the end), and which segment that was */
@@ -229,85 +228,111 @@ __device__ __forceinline__ uint32_t chunk_image(const QoiFParams &P, uint32_t c)
 	return lo;
 }
 
-/* ------------------------------------------------------------------ 1b. chain: one warp per stream */
-/* The composition itself is sequential (skip -> exit skip), but it only touches two small words per segment: the
-   lanes fetch the maps of 32 segments at a time into shared memory, lane 0 composes them there, the lanes write the
-   results back coalesced.  Also resets what the state rounds accumulate per image and marks every tile of the image as
+/* ------------------------------------------------------------------ 1b. chain: one CTA per stream */
+/* Composing the maps (skip -> exit skip, + pixels) is associative: thread t composes the maps of its block of consecutive
+   segments for all 5 entry skips, thread 0 chains the QOI_FCHAIN_THREADS block maps from the stream's start (skip 0,
+   pixel 0), then every thread walks its block again from its now known start and writes the per-segment results.  (Round
+   2's first version chained 32 segments at a time through one lane: 1.3 ms for a 4096x4096 photograph, more than the
+   state round it feeds.)  Also resets what the state rounds accumulate per image and marks every tile of the image as
    "no op starts here" (the state rounds overwrite the tiles in which one does). */
-__global__ void __launch_bounds__(32) fchain_kernel(const QoiFParams P) {
+#define QOI_FCHAIN_THREADS 512
+#define QOI_FCHAIN_SMEM ((QOI_FCHAIN_THREADS * 8 + 8) * 4)
+__global__ void __launch_bounds__(QOI_FCHAIN_THREADS) fchain_kernel(const QoiFParams P) {
 	QOI_DYNAMIC_SMEM(smem); /* QOI_FCHAIN_SMEM */
-	uint32_t *s_cnt = (uint32_t *)smem, *s_exit = s_cnt + 32 * 5, *s_entry = s_exit + 32 * 2, *s_px = s_entry + 32;
-	uint32_t *s_last = s_px + 32, *s_tb = s_last + 32 * 5;
-	uint32_t *s_state = s_tb + 32; /* skip, px, live, next tb0 */
+	uint32_t *s_map = (uint32_t *)smem;                  /* [thread][8]: exit skip per entry skip (packed), 5 pixel counts; then: start skip, start pixel */
+	uint32_t *s_live = s_map + QOI_FCHAIN_THREADS * 8;   /* live segments; pixels of the whole stream */
 	const uint32_t img = blockIdx.x;
-	const uint32_t lane = threadIdx.x;
+	const uint32_t t = threadIdx.x;
 	if (img >= P.n_images) return;
 	const QoiImgMeta m = P.imgs[img];
 	const uint8_t *s = P.streams + m.stream_off;
 	const int32_t size = P.lens[img];
 	const bool ok = stream_ok(m, s, size);
-	if (lane == 0 && P.status) P.status[img] = ok ? 0 : 4; /* QOI_GPU_E_STREAM */
-	if (lane == 0) { s_state[0] = 0; s_state[1] = 0; s_state[2] = 0; s_state[3] = 0; }
-	__syncwarp();
+	if (t == 0 && P.status) P.status[img] = ok ? 0 : 4; /* QOI_GPU_E_STREAM */
+	if (t == 0) s_live[0] = 0;
 	const uint32_t tiles = (m.npx + QOI_TILE_PX - 1) / QOI_TILE_PX;
-	for (uint32_t t = lane; t < tiles; t += 32) P.st.rs_px[m.first_tile + t] = -1;
-	if (ok) {
-		const int32_t stop = size - QOI_END_BYTES;
-		const uint32_t base = P.f.seg_base[img];
-		const uint32_t nseg = stop > QOI_HEADER_BYTES ? (uint32_t)((stop - QOI_HEADER_BYTES + QOI_FSEG_BYTES - 1) / QOI_FSEG_BYTES) : 0u;
-		for (uint32_t j0 = 0; j0 < nseg; j0 += 32) {
-			const uint32_t nb = nseg - j0 < 32u ? nseg - j0 : 32u;
-			if (lane < nb) {
-				const uint32_t g = base + j0 + lane;
+	for (uint32_t k = t; k < tiles; k += QOI_FCHAIN_THREADS) P.st.rs_px[m.first_tile + k] = -1;
+	const int32_t stop = size - QOI_END_BYTES;
+	const uint32_t base = P.f.seg_base[img];
+	const uint32_t nseg = (ok && stop > QOI_HEADER_BYTES) ? (uint32_t)((stop - QOI_HEADER_BYTES + QOI_FSEG_BYTES - 1) / QOI_FSEG_BYTES) : 0u;
+	const uint32_t per = (nseg + QOI_FCHAIN_THREADS - 1) / QOI_FCHAIN_THREADS;
+	const uint32_t j_lo = t * per < nseg ? t * per : nseg, j_hi = j_lo + per < nseg ? j_lo + per : nseg;
+	{ /* my block's map */
+		uint32_t sk[5] = {0u, 1u, 2u, 3u, 4u}, px[5] = {0u, 0u, 0u, 0u, 0u};
+		for (uint32_t j = j_lo; j < j_hi; j++) {
+			const uint32_t g = base + j;
+			const uint2 e = *(const uint2 *)(P.f.exit_skip + (size_t)g * 8);
 #pragma unroll
-				for (int k = 0; k < 5; k++) {
-					s_cnt[lane * 5 + k] = P.f.px_cnt[(size_t)g * 5 + k];
-					s_last[lane * 5 + k] = P.f.last_rel[(size_t)g * 5 + k];
-				}
-				const uint2 e = *(const uint2 *)(P.f.exit_skip + (size_t)g * 8);
-				s_exit[lane * 2] = e.x;
-				s_exit[lane * 2 + 1] = e.y;
+			for (int k = 0; k < 5; k++) {
+				px[k] += P.f.px_cnt[(size_t)g * 5 + sk[k]];
+				sk[k] = (sk[k] < 4u ? (e.x >> (8u * sk[k])) : e.y) & 0xFFu;
 			}
-			__syncwarp();
-			if (lane == 0) {
-				uint32_t skip = s_state[0], px = s_state[1], live = s_state[2], tbn = s_state[3];
-				for (uint32_t k = 0; k < nb; k++) {
-					if (px >= m.npx) { s_entry[k] = 0xFFu; continue; } /* all pixels already produced: dead segment */
-					s_entry[k] = skip;
-					s_px[k] = px;
-					s_tb[k] = tbn; /* the stream's very first op owns tile 0's record: 0 for segment 0 */
-					/* the tile boundaries behind this segment's last op start belong to later ops */
-					if (s_cnt[k * 5 + skip]) tbn = ((px + s_last[k * 5 + skip]) / QOI_TILE_PX + 1u) * QOI_TILE_PX;
-					px += s_cnt[k * 5 + skip];
-					skip = (skip < 4 ? (s_exit[k * 2] >> (8 * skip)) : s_exit[k * 2 + 1]) & 0xFFu;
-					live = j0 + k + 1;
-				}
-				s_state[0] = skip; s_state[1] = px; s_state[2] = live; s_state[3] = tbn;
-			}
-			__syncwarp();
-			if (lane < nb && s_entry[lane] != 0xFFu) {
-				const uint32_t g = base + j0 + lane;
-				P.f.entry[g] = (uint8_t)s_entry[lane];
-				P.f.px_start[g] = s_px[lane];
-				P.f.tb0[g] = s_tb[lane];
-				P.f.g_px[g] = 0xFF000000u; /* round-0 guess: the reference's initial state (qoi.h:533-537); exact for segment 0 */
-				P.f.flag[g] = (j0 + lane == 0u) ? (uint8_t)QOI_FF_TRUST : (uint8_t)0;
-			}
-			__syncwarp();
-			if (s_state[1] >= m.npx) break;
 		}
-		if (lane == 0 && s_state[2] == 0u) {
+		s_map[t * 8] = sk[0] | (sk[1] << 4) | (sk[2] << 8) | (sk[3] << 12) | (sk[4] << 16);
+#pragma unroll
+		for (int k = 0; k < 5; k++) s_map[t * 8 + 1 + k] = px[k];
+	}
+	__syncthreads();
+	if (t == 0) { /* the stream starts at an op (skip 0), pixel 0 */
+		uint32_t skip = 0, px = 0;
+		for (uint32_t k = 0; k < QOI_FCHAIN_THREADS; k++) {
+			const uint32_t e = s_map[k * 8], c = s_map[k * 8 + 1 + skip];
+			s_map[k * 8 + 6] = skip;
+			s_map[k * 8 + 7] = px;
+			px += c;
+			skip = (e >> (4u * skip)) & 0xFu;
+		}
+	}
+	__syncthreads();
+	{
+		uint32_t skip = s_map[t * 8 + 6], px = s_map[t * 8 + 7];
+		/* the tile boundaries behind a segment's last op start belong to later ops: tb0 of the segment behind it */
+		uint32_t tbn = 0; /* the stream's very first op owns tile 0's record */
+		if (j_lo > 0u && j_lo < nseg) { /* from the segment before my block: its entry skip is my start state seen backwards -- recompute it */
+			/* walk the last segment of the previous block: its start state is not stored, so thread t - 1's block is replayed
+			   from ITS start; cheap (per <= a few dozen) and only the last step is needed */
+			uint32_t ps = s_map[(t - 1) * 8 + 6], pp = s_map[(t - 1) * 8 + 7];
+			const uint32_t q_lo = (t - 1) * per;
+			for (uint32_t j = q_lo; j < j_lo; j++) {
+				const uint32_t g = base + j;
+				const uint2 e = *(const uint2 *)(P.f.exit_skip + (size_t)g * 8);
+				const uint32_t c = P.f.px_cnt[(size_t)g * 5 + ps];
+				if (j + 1 == j_lo && c && pp < m.npx) tbn = ((pp + P.f.last_rel[(size_t)g * 5 + ps]) / QOI_TILE_PX + 1u) * QOI_TILE_PX;
+				pp += c;
+				ps = (ps < 4u ? (e.x >> (8u * ps)) : e.y) & 0xFFu;
+			}
+		}
+		uint32_t live = 0;
+		for (uint32_t j = j_lo; j < j_hi; j++) {
+			if (px >= m.npx) break; /* all pixels already produced: this and every later segment is dead */
+			const uint32_t g = base + j;
+			const uint2 e = *(const uint2 *)(P.f.exit_skip + (size_t)g * 8);
+			const uint32_t c = P.f.px_cnt[(size_t)g * 5 + skip];
+			P.f.entry[g] = (uint8_t)skip;
+			P.f.px_start[g] = px;
+			P.f.tb0[g] = tbn;
+			P.f.g_px[g] = 0xFF000000u; /* round-0 guess: the reference's initial state (qoi.h:533-537); exact for segment 0 */
+			P.f.flag[g] = j == 0u ? (uint8_t)QOI_FF_TRUST : (uint8_t)0;
+			if (c) tbn = ((px + P.f.last_rel[(size_t)g * 5 + skip]) / QOI_TILE_PX + 1u) * QOI_TILE_PX;
+			px += c;
+			skip = (skip < 4u ? (e.x >> (8u * skip)) : e.y) & 0xFFu;
+			live = j + 1u;
+		}
+		if (live) atomicMax((int *)&s_live[0], (int)live);
+	}
+	__syncthreads();
+	if (t == 0) {
+		const uint32_t live = s_live[0];
+		if (ok && live == 0u) {
 			/* a valid header and not one op: the reference's loop never parses, every pixel is the start colour
 			   (qoi.h:534-544).  One restart record at pixel 0 makes the tile decoder produce exactly that. */
 			P.st.rs_px[m.first_tile] = 0;
 			P.st.rs_byte[m.first_tile] = QOI_HEADER_BYTES;
 			P.st.rs_prev[m.first_tile] = 0xFF000000u;
 		}
-	}
-	if (lane == 0) {
-		P.f.n_live[img] = s_state[2];
-		P.f.bad_cnt[img] = P.f.bad_cnt[P.n_images + img] = 0;
-		P.f.first_bad[img] = s_state[2];
+		P.f.n_live[img] = live;
+		P.f.bad_cnt[img] = P.f.bad_cnt[P.n_images + img] = P.f.bad_cnt[2u * P.n_images + img] = 0;
+		P.f.first_bad[img] = live;
 	}
 }
 
@@ -362,6 +387,11 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 	   two bits, so that an INDEX op of a slot the segment filled itself inherits them */
 	bool t_rgb = true, t_a = true, dep_rgb = false, dep_a = false;
 	uint64_t tm_rgb = 0, tm_a = 0;
+	/* ... and from the guessed COLOUR in particular (c_*, per slot cm_*): only that makes the segment depend on the colour --
+	   a colour read out of a guessed slot is covered by rbw, and a stream of INDEX ops must not wait for its predecessor's
+	   last colour */
+	bool c_rgb = true, c_a = true;
+	uint64_t cm_rgb = 0, cm_a = 0;
 	/* ... and, if it does: through anything but DIFF / LUMA / RUN ops on the incoming colour?  While it does not, the colour
 	   is "incoming colour + a sum of deltas that do not depend on the guess", which the scan can re-base exactly. */
 	bool d_rgb = false, d_a = false;
@@ -467,11 +497,13 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 		t_a = is_idx ? i_a : (is_rgba ? false : t_a);
 		d_rgb = is_idx ? i_rgb : ((is_rgb || is_rgba) ? false : d_rgb); /* through index[]: no longer a plain sum of deltas */
 		d_a = is_idx ? i_a : (is_rgba ? false : d_a);
+		const bool ic_rgb = own_slot && ((cm_rgb >> t6) & 1ull), ic_a = own_slot && ((cm_a >> t6) & 1ull);
+		c_rgb = is_idx ? ic_rgb : ((is_rgb || is_rgba) ? false : c_rgb);
+		c_a = is_idx ? ic_a : (is_rgba ? false : c_a);
 		/* every op yields at least one pixel of the new colour; while that colour derives from the guessed COLOUR the result
-		   depends on it (a colour that derives from a guessed slot is covered by rbw; counting it here too only makes the
-		   check stricter) */
-		dep_rgb = dep_rgb || t_rgb;
-		dep_a = dep_a || t_a;
+		   depends on it */
+		dep_rgb = dep_rgb || c_rgb;
+		dep_a = dep_a || c_a;
 		px = npx;
 		rd.buf >>= 8u * len;
 		rd.avail -= len;
@@ -482,12 +514,14 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 		wr |= hb;
 		tm_rgb = t_rgb ? (tm_rgb | hb) : (tm_rgb & ~hb);
 		tm_a = t_a ? (tm_a | hb) : (tm_a & ~hb);
+		cm_rgb = c_rgb ? (cm_rgb | hb) : (cm_rgb & ~hb);
+		cm_a = c_a ? (cm_a | hb) : (cm_a & ~hb);
 		pos += npix;
 		refill();
 	}
 	/* the colour that leaves the segment (and the pixels a truncated stream leaves over, qoi.h:544) may still be the incoming one */
-	dep_rgb = dep_rgb || t_rgb;
-	dep_a = dep_a || t_a;
+	dep_rgb = dep_rgb || c_rgb;
+	dep_a = dep_a || c_a;
 	P.f.o_px[g] = px;
 	P.f.o_wr[g] = wr;
 	P.f.o_taint[g] = (tm_rgb | tm_a) & wr;
@@ -502,6 +536,8 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 }
 
 /* ------------------------------------------------------------------ 3. last-writer scan over the segments of every stream */
+/* a stream whose check found every segment trusted and in agreement is exact: the rounds that follow leave it alone */
+__device__ __forceinline__ bool stream_settled(const QoiFParams &P, uint32_t img) { return P.f.bad_cnt[2u * P.n_images + img] != 0u; }
 /* Does segment g determine word t of the state behind it (t < 64: index[t], t == 64: the colour)?  What the segment wrote from
    its own bytes always does; what it derived from its guess only if that guess held (QOI_FF_TRUST) -- a stream of nothing but
    INDEX ops copies its guess around, and untrusted copies would push every wrong guess one segment further per round. */
@@ -547,6 +583,7 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_a_kernel(const QoiFPa
 	const uint32_t c = blockIdx.x, t = threadIdx.x;
 	if (c >= P.n_chunks) return;
 	const uint32_t img = chunk_image(P, c);
+	if (stream_settled(P, img)) return;
 	const uint32_t lc = c - P.f.chunk_base[img];
 	const uint32_t live = P.f.n_live[img];
 	const uint32_t j0 = lc * QOI_FCHUNK;
@@ -575,7 +612,7 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_a_kernel(const QoiFPa
 /* b: per stream, thread = slot: exclusive prefix over its chunks, from the reference's initial state (qoi.h:533-537) */
 __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_b_kernel(const QoiFParams P) {
 	const uint32_t img = blockIdx.x, t = threadIdx.x;
-	if (img >= P.n_images) return;
+	if (img >= P.n_images || stream_settled(P, img)) return;
 	const uint32_t live = P.f.n_live[img];
 	const uint32_t nch = (live + QOI_FCHUNK - 1) / QOI_FCHUNK;
 	const uint32_t c0 = P.f.chunk_base[img];
@@ -623,7 +660,7 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fcheck_kernel(const QoiFPar
 	QOI_DYNAMIC_SMEM(smem); /* QOI_FCHECK_SMEM */
 	uint32_t *s_dep = (uint32_t *)smem;
 	const uint32_t c = blockIdx.x, t = threadIdx.x;
-	if (c >= P.n_chunks) return;
+	if (c >= P.n_chunks || stream_settled(P, chunk_image(P, c))) return;
 	if (t < QOI_FCHUNK) s_dep[t] = 0u;
 	__syncthreads();
 	uint32_t img_of = 0, j_first = 0, n_seen = 0, g_first = 0;
@@ -663,6 +700,12 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fapply_kernel(const QoiFPar
 	uint32_t *s_redo = (uint32_t *)smem;
 	const uint32_t c = blockIdx.x, t = threadIdx.x;
 	if (c >= P.n_chunks) return;
+	{
+		/* the check of this round found nothing wrong in the stream: this is its last pass, whatever the round */
+		const uint32_t img = chunk_image(P, c);
+		if (stream_settled(P, img)) return;
+		if (P.f.bad_cnt[(P.round & 1u) * P.n_images + img] == 0u) last = 1;
+	}
 	if (t < QOI_FCHUNK) s_redo[t] = 0u;
 	__syncthreads();
 	uint32_t n_seen = 0, g_first = 0;
@@ -687,7 +730,9 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fapply_kernel(const QoiFPar
 }
 __global__ void __launch_bounds__(128) frearm_kernel(const QoiFParams P) { /* the counter the NEXT check adds to */
 	const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-	if (i < P.n_images) P.f.bad_cnt[((P.round + 1u) & 1u) * P.n_images + i] = 0u;
+	if (i >= P.n_images) return;
+	if (P.f.bad_cnt[(P.round & 1u) * P.n_images + i] == 0u) P.f.bad_cnt[2u * P.n_images + i] = 1u; /* settled */
+	P.f.bad_cnt[((P.round + 1u) & 1u) * P.n_images + i] = 0u;
 }
 
 /* ------------------------------------------------------------------ 4. fall-back: one exact walk per unsettled stream */

@@ -305,7 +305,7 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 		qoifdec::fstate_bind(F.f, p->d_fstate, p->flayout.off);
 		const uint32_t gs = (F.n_segs + QOI_FDEC_THREADS - 1) / QOI_FDEC_THREADS;
 		qoifdec::fparse_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
-		qoifdec::fchain_kernel<<<F.n_images, 32, QOI_FCHAIN_SMEM, s>>>(F);
+		qoifdec::fchain_kernel<<<F.n_images, QOI_FCHAIN_THREADS, QOI_FCHAIN_SMEM, s>>>(F);
 		qoifdec::fzero_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
 		for (int r = 0; r < QOI_FROUNDS; r++) {
 			F.round = (uint32_t)r;

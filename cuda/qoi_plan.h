@@ -167,7 +167,7 @@ static inline QoiFLayout qoi_fstate_layout(const QoiPlanGeom &g) {
 	const size_t S = segs, N = n, C = chunks, TL = g.n_tiles;
 	const size_t sizes[QOI_F_ARRAYS] = {(N + 1) * 4, (N + 1) * 4, S * 20, S * 8,      S,         S * 4,     N * 4,     S * 4,
 	                                    S * 256,     S * 4,       S * 256, S * 8,      S * 8,     S * 4,     S,         S * 4,
-	                                    64 * 4,      C * 256,     C * 8,   C * 8,      C * 256,   C * 4,     N * 4 * 2, N * 4,
+	                                    64 * 4,      C * 256,     C * 8,   C * 8,      C * 256,   C * 4,     N * 4 * 3, N * 4,
 	                                    S * 8,       S * 20,      S * 4,   TL * 8,     TL * 4,    N * 65 * 4};
 	size_t o = 0;
 	for (int k = 0; k < QOI_F_ARRAYS; k++) {

@@ -83,7 +83,7 @@ static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned se
 	qoifdec::fstate_bind(F.f, base, FL.off);
 	const unsigned gs = (FL.n_segs + QOI_FDEC_THREADS - 1) / QOI_FDEC_THREADS;
 	qemu::launch(gs, QOI_FDEC_THREADS, 0, [&]() { qoifdec::fparse_kernel(F); }, seed);
-	qemu::launch(D.n_images, 32, QOI_FCHAIN_SMEM, [&]() { qoifdec::fchain_kernel(F); }, seed);
+	qemu::launch(D.n_images, QOI_FCHAIN_THREADS, QOI_FCHAIN_SMEM, [&]() { qoifdec::fchain_kernel(F); }, seed);
 	qemu::launch(gs, QOI_FDEC_THREADS, 0, [&]() { qoifdec::fzero_kernel(F); }, seed);
 	for (int r = 0; r < rounds; r++) {
 		F.round = (uint32_t)r;
