@@ -17,9 +17,8 @@
  *      colour before, index[]) into the plan's index -- the same record the encoder leaves.
  *   3. scan + check (parallel).  "State before segment j" is a last-writer scan over the segments' results (per slot: the
  *      nearest earlier segment that wrote it; the colour: the previous segment's): fscan_a / fscan_b, 64 segments per
- *      chunk.  fcheck_kernel compares every segment's guess with the scanned state on what the segment depended on;
- *      fapply_kernel gives the segments that disagree the scanned state as their new guess and lists them for the next
- *      round.  A round in which nothing disagrees is a proof by induction that every result is exact (segment 0 starts
+ *      chunk.  fverify_kernel compares every segment's guess with the scanned state on what the segment depended on,
+ *      gives the segments that disagree the scanned state as their new guess and lists them for the next round.  A round in which nothing disagrees is a proof by induction that every result is exact (segment 0 starts
  *      from the reference's initial state).  One more round then re-walks the segments whose guess differs from the exact
  *      state in ANY slot, so that the restart records they left are exact in all 64 slots.
  *   4. fall back (exact, sequential): streams that have not settled after QOI_FROUNDS rounds (content whose colours are one
@@ -41,16 +40,15 @@
 namespace qoifdec {
 using namespace qoidev;
 
-#define QOI_FSEG_BYTES 4096
-#define QOI_FROUNDS 16  /* state rounds before the sequential fall-back */
+#define QOI_FSEG_BYTES 1024
+#define QOI_FROUNDS 24  /* state rounds before the sequential fall-back */
 #define QOI_FCHUNK 64   /* segments per scan chunk */
 #define QOI_FDEC_THREADS 128
 #define QOI_FSCAN_THREADS 96 /* 64 slot threads + the colour thread (thread 64); a multiple of 32 */
 #define QOI_FDEC_SMEM ((64 + QOI_DEC_RING_WORDS) * QOI_FDEC_THREADS * 4) /* per lane: index[64], stream ring */
 #define QOI_FFALL_SMEM ((64 + QOI_FSEG_BYTES / 4 + 8) * 4) /* index[], one staged segment */
-#define QOI_FCHECK_SMEM (QOI_FCHUNK * 4)
 
-/* flag[] bits (fcheck -> fapply) */
+/* flag[] bits (fverify_kernel) */
 #define QOI_FF_DEP 1u  /* the guess disagrees with the scanned state on something the segment depended on */
 #define QOI_FF_TRUST 4u /* the segment's last walk started from a guess that held on everything it depended on: what it derived from
                            the guess can be trusted (segment 0 always: its "guess" is the reference's initial state) */
@@ -89,8 +87,9 @@ struct QoiFState {
 	uint64_t *a_px;     /* [chunks] the chunk's colour map (seg_colour_map composed over its segments) */
 	uint32_t *p_tab;    /* [chunks][64] index[] before the chunk */
 	uint32_t *p_px;     /* [chunks] colour before the chunk */
-	uint32_t *bad_cnt;  /* [3][n_images]; plane 2: the stream has settled (a check found nothing), later rounds skip it; planes 0,1: segments with QOI_FF_DEP in the check of this round / the round before (by round parity) */
-	uint32_t *first_bad;/* [n_images] first segment the last check flagged (n_live if none): where the fall-back starts */
+	uint32_t *bad_cnt;  /* [4][n_images]: 0,1: segments the check of an even / odd round could not prove; 2: the stream has settled;
+	                       3: the last round that looked at the stream */
+	uint32_t *first_bad;/* [2][n_images] first unproven segment of that check (by round parity): where the fall-back starts */
 	/* per tile of the plan: which slots of the restart record's index[] the segment had written when it dropped the record
 	   (the others are filled from the segment's exact incoming state at the end), and which segment that was */
 	uint64_t *rec_wr;
@@ -331,8 +330,8 @@ __global__ void __launch_bounds__(QOI_FCHAIN_THREADS) fchain_kernel(const QoiFPa
 			P.st.rs_prev[m.first_tile] = 0xFF000000u;
 		}
 		P.f.n_live[img] = live;
-		P.f.bad_cnt[img] = P.f.bad_cnt[P.n_images + img] = P.f.bad_cnt[2u * P.n_images + img] = 0;
-		P.f.first_bad[img] = live;
+		P.f.bad_cnt[img] = P.f.bad_cnt[P.n_images + img] = P.f.bad_cnt[2u * P.n_images + img] = P.f.bad_cnt[3u * P.n_images + img] = 0;
+		P.f.first_bad[img] = P.f.first_bad[P.n_images + img] = live;
 	}
 }
 
@@ -355,7 +354,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 	constexpr int B = QOI_FDEC_THREADS;
 	uint32_t *tab = (uint32_t *)smem + threadIdx.x; /* tab[slot * B] */
 	uint32_t *ring = tab + 64 * B;                  /* ring[word * B] */
-	/* round 0: lane k takes segment k; later rounds: the k-th entry of the list the last fapply left */
+	/* round 0: lane k takes segment k; later rounds: the k-th entry of the list the last fverify_kernel left */
 	const uint32_t k = blockIdx.x * B + threadIdx.x;
 	uint32_t g;
 	if (P.round == 0u) {
@@ -536,8 +535,14 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 }
 
 /* ------------------------------------------------------------------ 3. last-writer scan over the segments of every stream */
-/* a stream whose check found every segment trusted and in agreement is exact: the rounds that follow leave it alone */
-__device__ __forceinline__ bool stream_settled(const QoiFParams &P, uint32_t img) { return P.f.bad_cnt[2u * P.n_images + img] != 0u; }
+/* Per stream and round: bad_cnt planes 0,1 = segments the check of an even / odd round could not prove, plane 2 = the stream
+   has settled (a check proved every segment: exact by induction from segment 0), plane 3 = the last round that looked at
+   the stream; first_bad planes 0,1 = the first unproven segment of that check.  A settled stream is skipped from then on,
+   so extra rounds cost the slow streams' time only. */
+__device__ __forceinline__ bool stream_settled(const QoiFParams &P, uint32_t img) {
+	if (P.f.bad_cnt[2u * P.n_images + img] != 0u) return true;
+	return P.round > 0u && P.f.bad_cnt[((P.round - 1u) & 1u) * P.n_images + img] == 0u;
+}
 /* Does segment g determine word t of the state behind it (t < 64: index[t], t == 64: the colour)?  What the segment wrote from
    its own bytes always does; what it derived from its guess only if that guess held (QOI_FF_TRUST) -- a stream of nothing but
    INDEX ops copies its guess around, and untrusted copies would push every wrong guess one segment further per round. */
@@ -578,6 +583,30 @@ __device__ __forceinline__ uint64_t colour_compose(uint64_t a, uint64_t b) {
 	else { m |= a & (1ull << 33); v |= va & 0xFF000000u; }
 	return m | v;
 }
+/* one segment's contribution to thread t's word of the state, fetched ahead of its use (the walks below are chains of
+   selects; the loads do not depend on them and are issued eight segments at a time) */
+struct SegWord {
+	uint32_t v;   /* t < 64: the slot's value after the segment */
+	bool gives;   /* ... and whether it determines the slot */
+	uint64_t map; /* t == 64: the colour map */
+};
+__device__ __forceinline__ SegWord seg_word(const QoiFParams &P, uint32_t g, uint32_t t) {
+	SegWord w;
+	w.v = 0; w.gives = false; w.map = 0;
+	if (t < 64u) {
+		w.gives = seg_gives(P, g, t);
+		w.v = P.f.o_tab[(size_t)g * 64 + t];
+	} else if (t == 64u) {
+		w.map = seg_colour_map(P, g);
+	}
+	return w;
+}
+__device__ __forceinline__ uint32_t seg_advance(const SegWord &w, uint32_t t, uint32_t T) {
+	if (t < 64u) return w.gives ? w.v : T;
+	return t == 64u ? colour_apply(w.map, T) : T;
+}
+#define QOI_FWALK_BATCH 8
+
 /* a: per chunk of QOI_FCHUNK segments, thread = slot (thread 64 = the colour): the chunk's last value per slot */
 __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_a_kernel(const QoiFParams P) {
 	const uint32_t c = blockIdx.x, t = threadIdx.x;
@@ -588,155 +617,263 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_a_kernel(const QoiFPa
 	const uint32_t live = P.f.n_live[img];
 	const uint32_t j0 = lc * QOI_FCHUNK;
 	if (j0 >= live) return; /* beyond the stream: never looked at */
-	const uint32_t j1 = j0 + QOI_FCHUNK < live ? j0 + QOI_FCHUNK : live;
+	const uint32_t n = (j0 + QOI_FCHUNK < live ? j0 + QOI_FCHUNK : live) - j0;
 	const uint32_t g0 = P.f.seg_base[img] + j0;
-	if (t < 64u) {
-		uint32_t val = 0;
-		bool wrote = false;
-		for (uint32_t j = 0; j < j1 - j0; j++) {
-			if (seg_gives(P, g0 + j, t)) {
-				val = P.f.o_tab[(size_t)(g0 + j) * 64 + t];
-				wrote = true;
+	uint32_t val = 0;
+	bool wrote = false;
+	uint64_t cmap = 0; /* identity: + 0, alpha unchanged */
+	for (uint32_t jb = 0; jb < n; jb += QOI_FWALK_BATCH) {
+		SegWord w[QOI_FWALK_BATCH];
+#pragma unroll
+		for (int k = 0; k < QOI_FWALK_BATCH; k++)
+			if (jb + k < n) w[k] = seg_word(P, g0 + jb + k, t);
+#pragma unroll
+		for (int k = 0; k < QOI_FWALK_BATCH; k++) {
+			if (jb + k < n) {
+				if (t < 64u) {
+					if (w[k].gives) { val = w[k].v; wrote = true; }
+				} else if (t == 64u) {
+					cmap = colour_compose(cmap, w[k].map);
+				}
 			}
 		}
+	}
+	if (t < 64u) {
 		P.f.a_tab[(size_t)c * 64 + t] = val;
 		const uint32_t b = __ballot_sync(QOI_FULL_MASK, wrote);
 		if ((t & 31u) == 0u) ((uint32_t *)(P.f.a_wr + c))[t >> 5] = b; /* low / high half of the 64-bit mask */
 	} else if (t == 64u) {
-		uint64_t v = 0; /* identity: + 0, alpha unchanged */
-		for (uint32_t j = 0; j < j1 - j0; j++) v = colour_compose(v, seg_colour_map(P, g0 + j));
-		P.f.a_px[c] = v;
+		P.f.a_px[c] = cmap;
 	}
 }
 
-/* b: per stream, thread = slot: exclusive prefix over its chunks, from the reference's initial state (qoi.h:533-537) */
-__global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_b_kernel(const QoiFParams P) {
+/* b: per stream: exclusive prefix over its chunks, from the reference's initial state (qoi.h:533-537).  A 4096x4096
+   photograph has ~800 chunks: QOI_FSCANB_GROUPS groups of 64 slot threads each take a run of consecutive chunks (last value
+   inside the run, then the groups before it, then the run again writing the prefixes); the last warp does the same for the
+   colour maps with 32 runs. */
+#define QOI_FSCANB_GROUPS 15
+#define QOI_FSCANB_THREADS (QOI_FSCANB_GROUPS * 64 + 32)
+#define QOI_FSCANB_SMEM ((QOI_FSCANB_GROUPS * 64 * 2 + 32 * 2 + 8) * 4)
+__global__ void __launch_bounds__(QOI_FSCANB_THREADS) fscan_b_kernel(const QoiFParams P) {
+	QOI_DYNAMIC_SMEM(smem);
+	uint32_t *s_val = (uint32_t *)smem, *s_wr = s_val + QOI_FSCANB_GROUPS * 64;
+	uint64_t *s_map = (uint64_t *)(s_wr + QOI_FSCANB_GROUPS * 64);
 	const uint32_t img = blockIdx.x, t = threadIdx.x;
-	if (img >= P.n_images || stream_settled(P, img)) return;
+	if (img >= P.n_images) return;
+	if (stream_settled(P, img)) { /* uniform over the CTA: every thread reads the same words */
+		if (t == 0) P.f.bad_cnt[2u * P.n_images + img] = 1u;
+		return;
+	}
+	if (t == 0) { /* what this round's check accumulates */
+		P.f.bad_cnt[(P.round & 1u) * P.n_images + img] = 0u;
+		P.f.first_bad[(P.round & 1u) * P.n_images + img] = 0x7FFFFFFFu;
+		P.f.bad_cnt[3u * P.n_images + img] = P.round;
+	}
 	const uint32_t live = P.f.n_live[img];
 	const uint32_t nch = (live + QOI_FCHUNK - 1) / QOI_FCHUNK;
 	const uint32_t c0 = P.f.chunk_base[img];
-	if (t < 64u) {
+	if (t < QOI_FSCANB_GROUPS * 64u) {
+		const uint32_t sl = t & 63u, grp = t >> 6;
+		const uint32_t per = (nch + QOI_FSCANB_GROUPS - 1) / QOI_FSCANB_GROUPS;
+		const uint32_t lo = grp * per < nch ? grp * per : nch, hi = lo + per < nch ? lo + per : nch;
 		uint32_t val = 0;
-		for (uint32_t lc = 0; lc < nch; lc++) {
-			P.f.p_tab[(size_t)(c0 + lc) * 64 + t] = val;
-			if ((P.f.a_wr[c0 + lc] >> t) & 1ull) val = P.f.a_tab[(size_t)(c0 + lc) * 64 + t];
+		bool wrote = false;
+		for (uint32_t lc = lo; lc < hi; lc += 4) {
+			uint32_t v[4];
+			uint64_t m[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+				if (lc + k < hi) { m[k] = P.f.a_wr[c0 + lc + k]; v[k] = P.f.a_tab[(size_t)(c0 + lc + k) * 64 + sl]; }
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+				if (lc + k < hi && ((m[k] >> sl) & 1ull)) { val = v[k]; wrote = true; }
 		}
-	} else if (t == 64u) {
-		uint32_t px = 0xFF000000u;
-		for (uint32_t lc = 0; lc < nch; lc++) {
+		s_val[t] = val;
+		s_wr[t] = wrote ? 1u : 0u;
+		__syncthreads();
+		val = 0; /* index[] starts zeroed (qoi.h:533) */
+		for (int q = (int)grp - 1; q >= 0; q--)
+			if (s_wr[q * 64 + sl]) { val = s_val[q * 64 + sl]; break; }
+		__syncthreads();
+		for (uint32_t lc = lo; lc < hi; lc += 4) {
+			uint32_t v[4];
+			uint64_t m[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+				if (lc + k < hi) { m[k] = P.f.a_wr[c0 + lc + k]; v[k] = P.f.a_tab[(size_t)(c0 + lc + k) * 64 + sl]; }
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				if (lc + k < hi) {
+					P.f.p_tab[(size_t)(c0 + lc + k) * 64 + sl] = val;
+					if ((m[k] >> sl) & 1ull) val = v[k];
+				}
+			}
+		}
+	} else {
+		const uint32_t q = t - QOI_FSCANB_GROUPS * 64u; /* 0..31 */
+		const uint32_t per = (nch + 31u) / 32u;
+		const uint32_t lo = q * per < nch ? q * per : nch, hi = lo + per < nch ? lo + per : nch;
+		uint64_t cm = 0;
+		for (uint32_t lc = lo; lc < hi; lc++) cm = colour_compose(cm, P.f.a_px[c0 + lc]);
+		s_map[q] = cm;
+		__syncthreads();
+		uint32_t px = 0xFF000000u; /* qoi.h:534-537 */
+		for (uint32_t k = 0; k < q; k++) px = colour_apply(s_map[k], px);
+		__syncthreads();
+		for (uint32_t lc = lo; lc < hi; lc++) {
 			P.f.p_px[c0 + lc] = px;
 			px = colour_apply(P.f.a_px[c0 + lc], px);
 		}
 	}
 }
 
-/* the walk fcheck and fapply share: state before every segment of the chunk, in order */
-template <typename Body>
-__device__ __forceinline__ void walk_chunk(const QoiFParams &P, uint32_t c, uint32_t t, Body body) {
+/* c: every segment's guess against the scanned state, on what the segment depended on; a segment that disagrees gets the
+   scanned state as its new guess and is listed for the next round's walk.  `last`: the check after the final round -- no
+   new guesses (behind the proven prefix the guesses must stay what the results belong to: the fall-back decides per segment
+   whether its last walk stands). */
+#define QOI_FVERIFY_SMEM ((QOI_FCHUNK * 65 + 8) * 4)
+__global__ void __launch_bounds__(QOI_FSCAN_THREADS) fverify_kernel(const QoiFParams P, int last) {
+	QOI_DYNAMIC_SMEM(smem);
+	uint32_t *s_T = (uint32_t *)smem;           /* [segment of the chunk][65]: the scanned state before it */
+	uint32_t *s_dep = s_T + QOI_FCHUNK * 65;    /* [2]: segments with a disagreement (64-bit mask) */
+	const uint32_t c = blockIdx.x, t = threadIdx.x;
+	if (c >= P.n_chunks) return;
 	const uint32_t img = chunk_image(P, c);
+	if (stream_settled(P, img)) return;
 	const uint32_t lc = c - P.f.chunk_base[img];
 	const uint32_t live = P.f.n_live[img];
 	const uint32_t j0 = lc * QOI_FCHUNK;
 	if (j0 >= live) return;
 	const uint32_t n = (j0 + QOI_FCHUNK < live ? j0 + QOI_FCHUNK : live) - j0;
 	const uint32_t g0 = P.f.seg_base[img] + j0;
-	/* my word of the running state: index[t] for t < 64, the colour for thread 64 */
+	if (t < 2u) s_dep[t] = 0u;
+	__syncthreads();
 	uint32_t T = t < 64u ? P.f.p_tab[(size_t)c * 64 + t] : (t == 64u ? P.f.p_px[c] : 0u);
-	for (uint32_t j = 0; j < n; j++) {
-		const uint32_t g = g0 + j;
-		body(img, j0 + j, j, g, T);
-		if (t < 64u) {
-			if (seg_gives(P, g, t)) T = P.f.o_tab[(size_t)g * 64 + t];
-		} else if (t == 64u) {
-			T = colour_apply(seg_colour_map(P, g), T);
+	uint32_t mis_lo = 0, mis_hi = 0;
+	for (uint32_t jb = 0; jb < n; jb += QOI_FWALK_BATCH) {
+		SegWord w[QOI_FWALK_BATCH];
+		uint32_t gv[QOI_FWALK_BATCH], need[QOI_FWALK_BATCH]; /* my word of the guess; the bits of it the segment depended on */
+#pragma unroll
+		for (int k = 0; k < QOI_FWALK_BATCH; k++) {
+			if (jb + k < n) {
+				const uint32_t g = g0 + jb + k;
+				w[k] = seg_word(P, g, t);
+				gv[k] = 0; need[k] = 0;
+				if (t < 64u) {
+					gv[k] = P.f.g_tab[(size_t)g * 64 + t];
+					need[k] = ((P.f.rbw[g] >> t) & 1ull) ? 0xFFFFFFFFu : 0u;
+				} else if (t == 64u) {
+					const uint32_t d = P.f.dep[g];
+					gv[k] = P.f.g_px[g];
+					need[k] = ((d & 1u) ? 0x00FFFFFFu : 0u) | ((d & 2u) ? 0xFF000000u : 0u);
+				}
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < QOI_FWALK_BATCH; k++) {
+			if (jb + k < n) {
+				const uint32_t j = jb + k;
+				if (t <= 64u) s_T[j * 65 + t] = T;
+				if ((gv[k] ^ T) & need[k]) {
+					if (j < 32u) mis_lo |= 1u << j;
+					else mis_hi |= 1u << (j - 32u);
+				}
+				T = seg_advance(w[k], t, T);
+			}
 		}
 	}
-}
-
-/* c: every segment's guess against the scanned state, on what the segment depended on.  `last`: the check after the final
-   round -- the fall-back walk starts at the first segment that is not proven yet. */
-__global__ void __launch_bounds__(QOI_FSCAN_THREADS) fcheck_kernel(const QoiFParams P, int last) {
-	QOI_DYNAMIC_SMEM(smem); /* QOI_FCHECK_SMEM */
-	uint32_t *s_dep = (uint32_t *)smem;
-	const uint32_t c = blockIdx.x, t = threadIdx.x;
-	if (c >= P.n_chunks || stream_settled(P, chunk_image(P, c))) return;
-	if (t < QOI_FCHUNK) s_dep[t] = 0u;
-	__syncthreads();
-	uint32_t img_of = 0, j_first = 0, n_seen = 0, g_first = 0;
-	walk_chunk(P, c, t, [&](uint32_t img, uint32_t jj, uint32_t j, uint32_t g, uint32_t T) {
-		bool dep = false;
-		if (t < 64u) {
-			dep = ((P.f.rbw[g] >> t) & 1ull) && P.f.g_tab[(size_t)g * 64 + t] != T;
-		} else if (t == 64u) {
-			const uint32_t x = P.f.g_px[g] ^ T, d = P.f.dep[g];
-			dep = ((d & 1u) && (x & 0x00FFFFFFu)) || ((d & 2u) && (x & 0xFF000000u));
-		}
-		const uint32_t bd = __ballot_sync(QOI_FULL_MASK, dep);
-		if ((t & 31u) == 0u && bd) atomicOr(&s_dep[j], 1u);
-		if (j == 0) { img_of = img; j_first = jj; g_first = g; }
-		n_seen = j + 1;
-	});
-	__syncthreads();
-	if (t < n_seen) {
+#pragma unroll
+	for (int d = 16; d >= 1; d >>= 1) {
+		mis_lo |= __shfl_xor_sync(QOI_FULL_MASK, mis_lo, d);
+		mis_hi |= __shfl_xor_sync(QOI_FULL_MASK, mis_hi, d);
+	}
+	if ((t & 31u) == 0u) {
+		if (mis_lo) atomicOr(&s_dep[0], mis_lo);
+		if (mis_hi) atomicOr(&s_dep[1], mis_hi);
+	}
+	__syncthreads(); /* also: the flags are read by the walk above and changed only behind it */
+	const uint32_t dep_lo = s_dep[0], dep_hi = s_dep[1];
+	if (t < 64u) { /* thread = segment of the chunk (two warps) */
+		const bool in = t < n;
+		const bool isdep = in && (((t < 32u ? dep_lo : dep_hi) >> (t & 31u)) & 1u);
 		/* A segment that was not trusted when the state was scanned had its guess-derived results left out: agreeing with
 		   such a state proves nothing yet.  The induction "segment 0 is exact; a segment whose guess agrees with the exact
-		   state before it is exact" only runs over a prefix in which every segment was trusted AND agrees -- the fall-back
-		   (after the last round) starts at the first segment that breaks the prefix. */
-		const bool was_trusted = (P.f.flag[g_first + t] & QOI_FF_TRUST) != 0u;
-		const uint32_t f = s_dep[t] ? QOI_FF_DEP : QOI_FF_TRUST;
-		P.f.flag[g_first + t] = (uint8_t)f;
+		   state before it is exact" only runs over a prefix in which every segment was trusted AND agrees. */
+		const bool was_trusted = in && (P.f.flag[g0 + (in ? t : 0u)] & QOI_FF_TRUST) != 0u;
+		const bool bad = in && (isdep || !was_trusted);
+		/* the next walk starts from the scanned state: trust what it derives from it until a check says otherwise */
+		if (in) P.f.flag[g0 + t] = (uint8_t)((isdep && last) ? QOI_FF_DEP : QOI_FF_TRUST);
 		const uint32_t par = P.round & 1u;
-		if ((f & QOI_FF_DEP) || !was_trusted) atomicAdd(&P.f.bad_cnt[par * P.n_images + img_of], 1u);
-		if (last && ((f & QOI_FF_DEP) || !was_trusted)) atomicMin((int *)&P.f.first_bad[img_of], (int)(j_first + t));
+		const uint32_t bb = __ballot_sync(QOI_FULL_MASK, bad);
+		if (bb && (t & 31u) == 0u) {
+			atomicAdd(&P.f.bad_cnt[par * P.n_images + img], (uint32_t)__popc(bb));
+			atomicMin((int *)&P.f.first_bad[par * P.n_images + img], (int)(j0 + (t & 32u) + (uint32_t)__ffs((int)bb) - 1u));
+		}
+		const uint32_t rb = __ballot_sync(QOI_FULL_MASK, isdep && !last);
+		if (rb) {
+			uint32_t at = 0;
+			if ((t & 31u) == 0u) at = atomicAdd(&P.f.n_list[P.round + 1u], (uint32_t)__popc(rb));
+			at = __shfl_sync(QOI_FULL_MASK, at, 0);
+			if (isdep && !last) P.f.list[at + (uint32_t)__popc(rb & ((1u << (t & 31u)) - 1u))] = g0 + t;
+		}
+	}
+	if (!last && t <= 64u) {
+		for (uint32_t half = 0; half < 2u; half++) {
+			uint32_t mk = half ? dep_hi : dep_lo;
+			while (mk) {
+				const uint32_t j = half * 32u + (uint32_t)__ffs((int)mk) - 1u;
+				mk &= mk - 1u;
+				if (t < 64u) P.f.g_tab[(size_t)(g0 + j) * 64 + t] = s_T[j * 65 + t];
+				else P.f.g_px[g0 + j] = s_T[j * 65 + 64];
+			}
+		}
 	}
 }
 
-/* d: new guesses.  A segment whose dependencies disagree is walked again with the scanned state.  After the last round
-   every segment of the proven prefix gets the scanned state in all 64 slots -- the exact state before the segment, which
-   fcompose_kernel needs for the slots a restart record's segment had not written -- and the fall-back walk its start state. */
-__global__ void __launch_bounds__(QOI_FSCAN_THREADS) fapply_kernel(const QoiFParams P, int last) {
-	QOI_DYNAMIC_SMEM(smem); /* QOI_FCHECK_SMEM */
-	uint32_t *s_redo = (uint32_t *)smem;
+/* d: after the rounds.  Every segment of the proven prefix gets the scanned state in all 64 slots -- the exact state before
+   the segment, which fcompose_kernel needs for the slots a restart record's segment had not written -- and the fall-back
+   walk its start state.  (A settled stream's scan results are still in place: nothing touched them since.) */
+__device__ __forceinline__ uint32_t stream_first_bad(const QoiFParams &P, uint32_t img) {
+	const uint32_t par = P.f.bad_cnt[3u * P.n_images + img] & 1u;
+	const uint32_t fb = P.f.first_bad[par * P.n_images + img], live = P.f.n_live[img];
+	return fb < live ? fb : live;
+}
+__global__ void __launch_bounds__(QOI_FSCAN_THREADS) ffinal_kernel(const QoiFParams P) {
 	const uint32_t c = blockIdx.x, t = threadIdx.x;
 	if (c >= P.n_chunks) return;
-	{
-		/* the check of this round found nothing wrong in the stream: this is its last pass, whatever the round */
-		const uint32_t img = chunk_image(P, c);
-		if (stream_settled(P, img)) return;
-		if (P.f.bad_cnt[(P.round & 1u) * P.n_images + img] == 0u) last = 1;
+	const uint32_t img = chunk_image(P, c);
+	const uint32_t lc = c - P.f.chunk_base[img];
+	const uint32_t live = P.f.n_live[img];
+	const uint32_t j0 = lc * QOI_FCHUNK;
+	if (j0 >= live) return;
+	const uint32_t fb = stream_first_bad(P, img);
+	if (j0 > fb) return; /* nothing proven in this chunk, and the fall-back does not start here */
+	const uint32_t n = (j0 + QOI_FCHUNK < live ? j0 + QOI_FCHUNK : live) - j0;
+	const uint32_t g0 = P.f.seg_base[img] + j0;
+	uint32_t T = t < 64u ? P.f.p_tab[(size_t)c * 64 + t] : (t == 64u ? P.f.p_px[c] : 0u);
+	for (uint32_t jb = 0; jb < n; jb += QOI_FWALK_BATCH) {
+		SegWord w[QOI_FWALK_BATCH];
+#pragma unroll
+		for (int k = 0; k < QOI_FWALK_BATCH; k++)
+			if (jb + k < n) w[k] = seg_word(P, g0 + jb + k, t);
+#pragma unroll
+		for (int k = 0; k < QOI_FWALK_BATCH; k++) {
+			if (jb + k < n) {
+				const uint32_t jj = j0 + jb + k, g = g0 + jb + k;
+				if (jj < fb) {
+					if (t < 64u) P.f.g_tab[(size_t)g * 64 + t] = T;
+					else if (t == 64u) P.f.g_px[g] = T;
+				} else if (jj == fb && t <= 64u) {
+					P.f.x_state[(size_t)img * 65 + t] = T; /* where the fall-back walk starts */
+				}
+				T = seg_advance(w[k], t, T);
+			}
+		}
 	}
-	if (t < QOI_FCHUNK) s_redo[t] = 0u;
-	__syncthreads();
-	uint32_t n_seen = 0, g_first = 0;
-	walk_chunk(P, c, t, [&](uint32_t img, uint32_t jj, uint32_t j, uint32_t g, uint32_t T) {
-		const bool redo = (P.f.flag[g] & QOI_FF_DEP) != 0u;
-		const uint32_t fb = last ? P.f.first_bad[img] : 0u;
-		if (last ? jj < fb : redo) { /* last: the proven prefix only -- behind it the guesses must stay what the results belong to */
-			if (t < 64u) P.f.g_tab[(size_t)g * 64 + t] = T;
-			else if (t == 64u) P.f.g_px[g] = T;
-		}
-		if (last && jj == fb && t <= 64u) P.f.x_state[(size_t)img * 65 + t] = T; /* where the fall-back walk starts */
-		if (redo && !last && t == 64u) {
-			P.f.list[atomicAdd(&P.f.n_list[P.round + 1u], 1u)] = g;
-			s_redo[j] = 1u;
-		}
-		if (j == 0) g_first = g;
-		n_seen = j + 1;
-	});
-	__syncthreads(); /* the flags are read by the walk above: changed only behind it */
-	/* a segment's next walk starts from the scanned state: trust what it derives from it until a check says otherwise */
-	if (t < n_seen && s_redo[t]) P.f.flag[g_first + t] = (uint8_t)QOI_FF_TRUST;
-}
-__global__ void __launch_bounds__(128) frearm_kernel(const QoiFParams P) { /* the counter the NEXT check adds to */
-	const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-	if (i >= P.n_images) return;
-	if (P.f.bad_cnt[(P.round & 1u) * P.n_images + i] == 0u) P.f.bad_cnt[2u * P.n_images + i] = 1u; /* settled */
-	P.f.bad_cnt[((P.round + 1u) & 1u) * P.n_images + i] = 0u;
 }
 
 /* ------------------------------------------------------------------ 4. fall-back: one exact walk per unsettled stream */
-/* From the first segment the last check could not prove (the last fapply left the exact state before it in x_state:
+/* From the first segment the last check could not prove (ffinal_kernel left the exact state before it in x_state:
    everything before it is proven) to the end of the stream, with the exact state in shared memory.  A segment whose last walk started
    from a guess that agrees with the exact state on everything it depended on is taken over as it is (its results advance
    the state; it gets the exact state as its guess, for fcompose_kernel); any other segment is decoded on the spot: lane 0
@@ -750,7 +887,7 @@ __global__ void __launch_bounds__(32) ffall_kernel(const QoiFParams P) {
 	const uint32_t lane = threadIdx.x;
 	if (img >= P.n_images) return;
 	const uint32_t live = P.f.n_live[img];
-	const uint32_t fb = P.f.first_bad[img];
+	const uint32_t fb = stream_first_bad(P, img);
 	if (fb >= live) return; /* everything proven (also: rejected or empty stream) */
 	const QoiImgMeta m = P.imgs[img];
 	const uint8_t *s = P.streams + m.stream_off;

@@ -312,14 +312,13 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 			const int last = r + 1 == QOI_FROUNDS;
 			qoifdec::fstate_kernel<<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
 			qoifdec::fscan_a_kernel<<<F.n_chunks, QOI_FSCAN_THREADS, 0, s>>>(F);
-			qoifdec::fscan_b_kernel<<<F.n_images, QOI_FSCAN_THREADS, 0, s>>>(F);
-			qoifdec::fcheck_kernel<<<F.n_chunks, QOI_FSCAN_THREADS, QOI_FCHECK_SMEM, s>>>(F, last);
-			qoifdec::fapply_kernel<<<F.n_chunks, QOI_FSCAN_THREADS, QOI_FCHECK_SMEM, s>>>(F, last);
-			qoifdec::frearm_kernel<<<(F.n_images + 127) / 128, 128, 0, s>>>(F);
+			qoifdec::fscan_b_kernel<<<F.n_images, QOI_FSCANB_THREADS, QOI_FSCANB_SMEM, s>>>(F);
+			qoifdec::fverify_kernel<<<F.n_chunks, QOI_FSCAN_THREADS, QOI_FVERIFY_SMEM, s>>>(F, last);
 		}
+		qoifdec::ffinal_kernel<<<F.n_chunks, QOI_FSCAN_THREADS, 0, s>>>(F);
 		qoifdec::ffall_kernel<<<F.n_images, 32, QOI_FFALL_SMEM, s>>>(F);
 		qoifdec::fcompose_kernel<<<(p->geom.n_tiles * 64u + 127u) / 128u, 128, 0, s>>>(F, p->geom.n_tiles, p->d_tile_img);
-		g_launches += 5 + 6 * QOI_FROUNDS;
+		g_launches += 6 + 4 * QOI_FROUNDS;
 		CK(ctx, cudaGetLastError());
 		p->index_owner = 1; /* the plan now holds the restart index of THESE streams (it can be exported as a side-car) */
 		d_status = nullptr; /* reported by fchain_kernel */

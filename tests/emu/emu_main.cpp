@@ -90,10 +90,8 @@ static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned se
 		const int last = r + 1 == rounds;
 		qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { qoifdec::fstate_kernel(F); }, seed);
 		qemu::launch(FL.n_chunks, QOI_FSCAN_THREADS, 0, [&]() { qoifdec::fscan_a_kernel(F); }, seed);
-		qemu::launch(D.n_images, QOI_FSCAN_THREADS, 0, [&]() { qoifdec::fscan_b_kernel(F); }, seed);
-		qemu::launch(FL.n_chunks, QOI_FSCAN_THREADS, QOI_FCHECK_SMEM, [&]() { qoifdec::fcheck_kernel(F, last); }, seed);
-		qemu::launch(FL.n_chunks, QOI_FSCAN_THREADS, QOI_FCHECK_SMEM, [&]() { qoifdec::fapply_kernel(F, last); }, seed);
-		qemu::launch((D.n_images + 127) / 128, 128, 0, [&]() { qoifdec::frearm_kernel(F); }, seed);
+		qemu::launch(D.n_images, QOI_FSCANB_THREADS, QOI_FSCANB_SMEM, [&]() { qoifdec::fscan_b_kernel(F); }, seed);
+		qemu::launch(FL.n_chunks, QOI_FSCAN_THREADS, QOI_FVERIFY_SMEM, [&]() { qoifdec::fverify_kernel(F, last); }, seed);
 		if (getenv("QOI_EMU_FTRACE2")) {
 			for (uint32_t i = 0; i < D.n_images; i++) {
 				fprintf(stderr, "round %d image %u flagged:", r, i);
@@ -109,7 +107,8 @@ static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned se
 	}
 	if (getenv("QOI_EMU_FSTATS"))
 		for (uint32_t i = 0; i < D.n_images; i++)
-			fprintf(stderr, "image %u: %u live segments, fall-back from segment %u after %d rounds\n", i, F.f.n_live[i], F.f.first_bad[i], rounds);
+			fprintf(stderr, "image %u: %u live segments, fall-back from segment %u after %d rounds\n", i, F.f.n_live[i], qoifdec::stream_first_bad(F, i), rounds);
+	qemu::launch(FL.n_chunks, QOI_FSCAN_THREADS, 0, [&]() { qoifdec::ffinal_kernel(F); }, seed);
 	qemu::launch(D.n_images, 32, QOI_FFALL_SMEM, [&]() { qoifdec::ffall_kernel(F); }, seed);
 	qemu::launch((g.n_tiles * 64u + 127u) / 128u, 128, 0, [&]() { qoifdec::fcompose_kernel(F, g.n_tiles, D.tile_img); }, seed);
 	QoiDecParams I = D;
