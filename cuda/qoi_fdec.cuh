@@ -43,12 +43,14 @@ using namespace qoidev;
 #define QOI_FSEG_BYTES 1024
 #define QOI_FROUNDS 24  /* state rounds before the sequential fall-back */
 #define QOI_FCHUNK 64   /* segments per scan chunk */
-#define QOI_FDEC_THREADS 128
+#define QOI_FDEC_THREADS 64
 #define QOI_FSCAN_THREADS 96 /* 64 slot threads + the colour thread (thread 64); a multiple of 32 */
-#define QOI_FDEC_SMEM ((64 + QOI_DEC_RING_WORDS) * QOI_FDEC_THREADS * 4) /* per lane: index[64], stream ring */
+#define QOI_FDEC_SMEM ((64 + 16 + QOI_DEC_RING_WORDS) * QOI_FDEC_THREADS * 4) /* per lane: index[64], 64 flag bytes, stream ring */
 #define QOI_FFALL_SMEM ((64 + QOI_FSEG_BYTES / 4 + 8) * 4) /* index[], one staged segment */
 
 /* flag[] bits (fverify_kernel) */
+#define QOI_FCONT_LIST 4096u /* a round with at most this many listed segments lets the walks continue into the next segment */
+#define QOI_FCONT_MAX 48u    /* ... this many segments at most */
 #define QOI_FF_DEP 1u  /* the guess disagrees with the scanned state on something the segment depended on */
 #define QOI_FF_TRUST 4u /* the segment's last walk started from a guess that held on everything it depended on: what it derived from
                            the guess can be trusted (segment 0 always: its "guess" is the reference's initial state) */
@@ -94,6 +96,7 @@ struct QoiFState {
 	   (the others are filled from the segment's exact incoming state at the end), and which segment that was */
 	uint64_t *rec_wr;
 	uint32_t *rs_seg;
+	uint32_t *claim;    /* [segs] (epoch << 8 | round + 1) of the last walk that took the segment over by continuing into it */
 	uint32_t *x_state;  /* [n_images][65] exact index[] and colour before the first unproven segment (for the fall-back) */
 };
 
@@ -106,6 +109,7 @@ struct QoiFParams {
 	uint32_t n_segs;   /* capacity over all images */
 	uint32_t n_chunks; /* capacity */
 	uint32_t round;    /* state round of this launch (0 = every live segment, from the reference's initial state) */
+	uint32_t epoch;    /* counts the decode calls on the plan (claim[] is never cleared) */
 	QoiFState f;
 	QoiTileState st;   /* the plan's restart index: rs_px / rs_byte / rs_prev / ent are (re)written here */
 };
@@ -353,7 +357,8 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 	QOI_DYNAMIC_SMEM(smem);
 	constexpr int B = QOI_FDEC_THREADS;
 	uint32_t *tab = (uint32_t *)smem + threadIdx.x; /* tab[slot * B] */
-	uint32_t *ring = tab + 64 * B;                  /* ring[word * B] */
+	uint32_t *flg = tab + 64 * B;                   /* flg[word * B]: one byte per slot (below) */
+	uint32_t *ring = flg + 16 * B;                  /* ring[word * B] */
 	/* round 0: lane k takes segment k; later rounds: the k-th entry of the list the last fverify_kernel left */
 	const uint32_t k = blockIdx.x * B + threadIdx.x;
 	uint32_t g;
@@ -365,14 +370,22 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 		g = P.f.list[k];
 	}
 	const uint32_t img = seg_image(P, g);
-	const uint32_t j = g - P.f.seg_base[img];
+	uint32_t j = g - P.f.seg_base[img];
 	const uint32_t live = P.f.n_live[img];
 	if (j >= live) return;
 	const QoiImgMeta m = P.imgs[img];
 	const uint8_t *s = P.streams + m.stream_off;
 	const int32_t stop = P.lens[img] - QOI_END_BYTES;
-	const int32_t begin = QOI_HEADER_BYTES + (int32_t)j * QOI_FSEG_BYTES;
-	const int32_t end = begin + QOI_FSEG_BYTES < stop ? begin + QOI_FSEG_BYTES : stop;
+	int32_t begin = QOI_HEADER_BYTES + (int32_t)j * QOI_FSEG_BYTES;
+	int32_t end = begin + QOI_FSEG_BYTES < stop ? begin + QOI_FSEG_BYTES : stop;
+	/* Late rounds list a handful of segments, typically the front of a chain: a smooth region whose colours all hang on the
+	   colour that entered it settles one segment per round, and a round costs three more launches.  So when the list is
+	   short a walk does not stop at its segment's end: while the state it arrives with disagrees with the NEXT segment's
+	   guess on what that segment depended on, it takes the next segment over (new guess = the state it holds) and goes on.
+	   claim[] keeps two walks of one round off the same segment. */
+	const uint32_t claim_tag = (P.epoch << 8) | (P.round + 1u);
+	const bool cont = P.round >= 2u && P.f.n_list[P.round] <= QOI_FCONT_LIST;
+	if (cont && atomicExch(&P.f.claim[g], claim_tag) == claim_tag) return; /* a walk that started earlier got here first */
 
 	uint32_t px = P.f.g_px[g];
 	{
@@ -380,20 +393,34 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 #pragma unroll 8
 		for (int q = 0; q < 64; q++) tab[q * B] = src[q];
 	}
-	uint64_t wr = 0, rbw = 0;
-	/* does the current colour derive from the guess (the colour that entered the segment, or a guessed index[] slot read
-	   before the segment wrote it)?  r,g,b and alpha separately (an RGB op replaces only r,g,b); per written slot the same
-	   two bits, so that an INDEX op of a slot the segment filled itself inherits them */
-	bool t_rgb = true, t_a = true, dep_rgb = false, dep_a = false;
-	uint64_t tm_rgb = 0, tm_a = 0;
-	/* ... and from the guessed COLOUR in particular (c_*, per slot cm_*): only that makes the segment depend on the colour --
-	   a colour read out of a guessed slot is covered by rbw, and a stream of INDEX ops must not wait for its predecessor's
-	   last colour */
-	bool c_rgb = true, c_a = true;
-	uint64_t cm_rgb = 0, cm_a = 0;
-	/* ... and, if it does: through anything but DIFF / LUMA / RUN ops on the incoming colour?  While it does not, the colour
-	   is "incoming colour + a sum of deltas that do not depend on the guess", which the scan can re-base exactly. */
-	bool d_rgb = false, d_a = false;
+	uint64_t rbw;
+	/* What the current colour derives from, one bit each (cf), r,g,b and alpha separately (an RGB op replaces only r,g,b):
+	     T_*: from the guess at all (the colour that entered the segment, or a guessed index[] slot read before the segment
+	          wrote it);
+	     C_*: from the guessed COLOUR in particular -- only that makes the segment depend on the incoming colour (a colour
+	          read out of a guessed slot is covered by rbw, and a stream of INDEX ops must not wait for its predecessor's last
+	          colour);
+	     D_*: ... through index[], i.e. not as "incoming colour + deltas of DIFF / LUMA / RUN ops", which the scan can
+	          re-base exactly.
+	   Every slot the segment writes keeps W | T_* | C_* of the colour stored there in a byte of flg[], so that an INDEX op
+	   of a slot the segment filled itself inherits them. */
+	constexpr uint32_t F_W = 1u, F_TRGB = 2u, F_TA = 4u, F_CRGB = 8u, F_CA = 16u, F_DRGB = 32u, F_DA = 64u;
+	uint32_t cf, depacc;
+	auto flag_byte = [&](uint32_t slot) -> uint8_t * { return (uint8_t *)(flg + (slot >> 2) * B) + (slot & 3u); };
+	/* the W bits / (T_RGB | T_A) bits of all 64 slots as masks */
+	auto gather = [&](uint64_t &wr, uint64_t &taint) {
+		wr = 0; taint = 0;
+#pragma unroll 4
+		for (int q = 0; q < 16; q++) {
+			const uint32_t w = flg[q * B];
+			const uint32_t wb = w & 0x01010101u;                                 /* W of slots 4q .. 4q+3 at bits 0,8,16,24 */
+			const uint32_t tb4 = ((w >> 1) | (w >> 2)) & 0x01010101u;
+			const uint32_t wn = (wb | (wb >> 7) | (wb >> 14) | (wb >> 21)) & 0xFu; /* ... at bits 0..3 */
+			const uint32_t tn = (tb4 | (tb4 >> 7) | (tb4 >> 14) | (tb4 >> 21)) & 0xFu;
+			wr |= (uint64_t)wn << (4 * q);
+			taint |= (uint64_t)tn << (4 * q);
+		}
+	};
 	uint32_t pos = P.f.px_start[g];                                          /* pixel the next op starts at */
 	/* The restart record of a tile belongs to the first op that starts at or behind the tile's first pixel.  `tb` = the next
 	   tile boundary no op has started behind yet; fchain_kernel knows where every segment's last op starts, so the first
@@ -451,7 +478,11 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 		P.st.rs_px[T] = (int32_t)pos;
 		P.st.rs_byte[T] = rd.p;
 		P.st.rs_prev[T] = px;
-		P.f.rec_wr[T] = wr;
+		{
+			uint64_t wr, taint;
+			gather(wr, taint);
+			P.f.rec_wr[T] = wr;
+		}
 		P.f.rs_seg[T] = g;
 		if (tb) { /* qoi_decode_kernel reads index[] of tile T from the record of tile T - 1; tile 0 starts from zeros */
 			uint4 *dst = (uint4 *)(P.st.ent + (size_t)(T - 1) * 64);
@@ -460,6 +491,12 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 		}
 		tb += QOI_TILE_PX;
 	};
+	for (uint32_t steps = 0;; steps++) {
+	rbw = 0;
+	cf = F_TRGB | F_TA | F_CRGB | F_CA;
+	depacc = 0;
+#pragma unroll
+	for (int q = 0; q < 16; q++) flg[q * B] = 0u;
 	while (rd.p < end && pos < m.npx) { /* qoi.h:540,544: no op is parsed once every pixel is there */
 		if (rd.avail < 5u) { /* an op needs at most 5 bytes */
 			rd.buf |= (uint64_t)next_word() << (8u * rd.avail);
@@ -489,48 +526,70 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 		const uint32_t len = is_rgba ? 5u : (is_rgb ? 4u : (top == 2u ? 2u : 1u));
 		const uint32_t npix = (top == 3u && tag < 0xFEu) ? t6 + 1u : 1u; /* a RUN op yields run + 1 pixels (qoi.h:541-543,573-575) */
 		/* where the new colour comes from */
-		const bool own_slot = ((wr >> t6) & 1ull) != 0ull;
+		uint8_t *fb_t = flag_byte(t6);
+		const uint32_t fbv = *fb_t;
+		const bool own_slot = (fbv & F_W) != 0u;
 		if (is_idx && !own_slot) rbw |= 1ull << t6; /* the guessed index[] is used */
-		const bool i_rgb = !own_slot || ((tm_rgb >> t6) & 1ull), i_a = !own_slot || ((tm_a >> t6) & 1ull);
-		t_rgb = is_idx ? i_rgb : ((is_rgb || is_rgba) ? false : t_rgb);
-		t_a = is_idx ? i_a : (is_rgba ? false : t_a);
-		d_rgb = is_idx ? i_rgb : ((is_rgb || is_rgba) ? false : d_rgb); /* through index[]: no longer a plain sum of deltas */
-		d_a = is_idx ? i_a : (is_rgba ? false : d_a);
-		const bool ic_rgb = own_slot && ((cm_rgb >> t6) & 1ull), ic_a = own_slot && ((cm_a >> t6) & 1ull);
-		c_rgb = is_idx ? ic_rgb : ((is_rgb || is_rgba) ? false : c_rgb);
-		c_a = is_idx ? ic_a : (is_rgba ? false : c_a);
+		/* INDEX: what the slot's colour derived from (through index[]: D = T), or a guessed slot */
+		const uint32_t cf_idx = own_slot ? ((fbv & (F_TRGB | F_TA | F_CRGB | F_CA)) | ((fbv & (F_TRGB | F_TA)) << 4)) : (F_TRGB | F_TA | F_DRGB | F_DA);
+		uint32_t ncf = is_rgb ? (cf & (F_TA | F_CA | F_DA)) : cf; /* RGB: r,g,b from the stream, alpha kept; DIFF / LUMA / RUN: unchanged */
+		ncf = is_rgba ? 0u : ncf;
+		cf = is_idx ? cf_idx : ncf;
 		/* every op yields at least one pixel of the new colour; while that colour derives from the guessed COLOUR the result
 		   depends on it */
-		dep_rgb = dep_rgb || c_rgb;
-		dep_a = dep_a || c_a;
+		depacc |= cf;
 		px = npx;
 		rd.buf >>= 8u * len;
 		rd.avail -= len;
 		rd.p += (int32_t)len;
 		const uint32_t h = qoi_slot(px);
 		tab[h * B] = px; /* qoi.h:577 */
-		const uint64_t hb = 1ull << h;
-		wr |= hb;
-		tm_rgb = t_rgb ? (tm_rgb | hb) : (tm_rgb & ~hb);
-		tm_a = t_a ? (tm_a | hb) : (tm_a & ~hb);
-		cm_rgb = c_rgb ? (cm_rgb | hb) : (cm_rgb & ~hb);
-		cm_a = c_a ? (cm_a | hb) : (cm_a & ~hb);
+		*flag_byte(h) = (uint8_t)(F_W | (cf & (F_TRGB | F_TA | F_CRGB | F_CA)));
 		pos += npix;
 		refill();
 	}
 	/* the colour that leaves the segment (and the pixels a truncated stream leaves over, qoi.h:544) may still be the incoming one */
-	dep_rgb = dep_rgb || c_rgb;
-	dep_a = dep_a || c_a;
+	depacc |= cf;
+	{
+		uint64_t wr, taint;
+		gather(wr, taint);
+		P.f.o_wr[g] = wr;
+		P.f.o_taint[g] = taint & wr;
+	}
 	P.f.o_px[g] = px;
-	P.f.o_wr[g] = wr;
-	P.f.o_taint[g] = (tm_rgb | tm_a) & wr;
 	P.f.rbw[g] = rbw;
-	/* bits 2,3: r,g,b / alpha of the final colour derive from the guess; bits 4,5: ... as incoming colour + deltas only */
-	P.f.dep[g] = (dep_rgb ? 1u : 0u) | (dep_a ? 2u : 0u) | (t_rgb ? 4u : 0u) | (t_a ? 8u : 0u) | ((t_rgb && !d_rgb) ? 16u : 0u) | ((t_a && !d_a) ? 32u : 0u);
+	/* bits 0,1: the result depends on the incoming r,g,b / alpha; bits 2,3: r,g,b / alpha of the final colour derive from the
+	   guess; bits 4,5: ... as incoming colour + deltas only */
+	P.f.dep[g] = ((depacc & F_CRGB) ? 1u : 0u) | ((depacc & F_CA) ? 2u : 0u) | ((cf & F_TRGB) ? 4u : 0u) | ((cf & F_TA) ? 8u : 0u) |
+	             (((cf & (F_TRGB | F_DRGB)) == F_TRGB) ? 16u : 0u) | (((cf & (F_TA | F_DA)) == F_TA) ? 32u : 0u);
 	{
 		uint32_t *dst = P.f.o_tab + (size_t)g * 64;
 #pragma unroll 8
 		for (int q = 0; q < 64; q++) dst[q] = tab[q * B];
+	}
+	if (!cont || steps + 1u >= QOI_FCONT_MAX || j + 1u >= live) break;
+	{ /* does the next segment's last walk stand with the state this one arrives with? */
+		const uint32_t gn = g + 1u;
+		const uint32_t dn = P.f.dep[gn];
+		const uint32_t pmask = ((dn & 1u) ? 0x00FFFFFFu : 0u) | ((dn & 2u) ? 0xFF000000u : 0u);
+		bool differs = ((P.f.g_px[gn] ^ px) & pmask) != 0u;
+		uint64_t need = P.f.rbw[gn];
+		while (need && !differs) {
+			const uint32_t q = (uint32_t)__ffsll((long long)need) - 1u;
+			need &= need - 1ull;
+			differs = P.f.g_tab[(size_t)gn * 64 + q] != tab[q * B];
+		}
+		if (!differs) break;
+		if (atomicExch(&P.f.claim[gn], claim_tag) == claim_tag) break;
+		g = gn;
+		j++;
+		begin += QOI_FSEG_BYTES; /* the reader, pos and tb simply go on: this segment's first op is where the last one's ended */
+		end = begin + QOI_FSEG_BYTES < stop ? begin + QOI_FSEG_BYTES : stop;
+		P.f.g_px[g] = px;
+		uint32_t *dst = P.f.g_tab + (size_t)g * 64;
+#pragma unroll 8
+		for (int q = 0; q < 64; q++) dst[q] = tab[q * B];
+	}
 	}
 }
 
@@ -1030,6 +1089,7 @@ static inline void fstate_bind(QoiFState &f, unsigned char *base, const size_t *
 	f.a_px = (uint64_t *)(base + off[19]);
 	f.p_tab = (uint32_t *)(base + off[20]);
 	f.p_px = (uint32_t *)(base + off[21]);
+	f.claim = (uint32_t *)(base + off[30]);
 	f.bad_cnt = (uint32_t *)(base + off[22]);
 	f.first_bad = (uint32_t *)(base + off[23]);
 	f.o_taint = (uint64_t *)(base + off[24]);

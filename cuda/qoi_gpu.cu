@@ -55,6 +55,7 @@ struct qoi_gpu_plan {
 	unsigned char *d_state = nullptr;
 	QoiTileState st;
 	uint32_t epoch = 0;
+	uint32_t fepoch = 0; /* any-stream decodes on this plan (QoiFParams::epoch) */
 	bool pix_off_aligned16 = true;
 	/* lazily allocated device mirrors for the *_host entry points */
 	unsigned char *d_pixels = nullptr, *d_streams = nullptr, *d_decoded = nullptr;
@@ -302,6 +303,7 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 		F.n_segs = p->flayout.n_segs;
 		F.n_chunks = p->flayout.n_chunks;
 		F.st = p->st;
+		F.epoch = (++p->fepoch) & 0x00FFFFFFu;
 		qoifdec::fstate_bind(F.f, p->d_fstate, p->flayout.off);
 		const uint32_t gs = (F.n_segs + QOI_FDEC_THREADS - 1) / QOI_FDEC_THREADS;
 		qoifdec::fparse_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);

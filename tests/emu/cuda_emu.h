@@ -369,6 +369,7 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
 	uint64_t both = ((uint64_t)b << 32) | a;
 	unsigned r = 0;
@@ -415,5 +416,6 @@ static inline void __nanosleep(unsigned) { qemu::yield("spin wait"); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; qemu::progress++; return o; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; qemu::progress++; return o; }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; qemu::progress++; return o; }
+static inline unsigned atomicExch(unsigned *p, unsigned v) { unsigned o = *p; *p = v; qemu::progress++; return o; }
 static inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; qemu::progress++; return o; }
 static inline int atomicMax(int *p, int v) { int o = *p; if (v > o) *p = v; qemu::progress++; return o; }

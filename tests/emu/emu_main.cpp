@@ -80,6 +80,7 @@ static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned se
 	F.streams = D.streams; F.lens = D.lens; F.status = D.status; F.imgs = D.imgs;
 	F.n_images = D.n_images; F.n_segs = FL.n_segs; F.n_chunks = FL.n_chunks;
 	F.st = st;
+	F.epoch = 1;
 	qoifdec::fstate_bind(F.f, base, FL.off);
 	const unsigned gs = (FL.n_segs + QOI_FDEC_THREADS - 1) / QOI_FDEC_THREADS;
 	qemu::launch(gs, QOI_FDEC_THREADS, 0, [&]() { qoifdec::fparse_kernel(F); }, seed);
