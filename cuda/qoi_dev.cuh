@@ -49,10 +49,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 	uint32_t ok;
 	asm volatile(
 	    "{\n\t.reg .pred p;\n\t"
-	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t" /* %3: let the warp stay suspended up to this many ns instead of spinning (round 2: 13 % of the encoder's issued instructions were this loop) */
 	    "selp.u32 %0, 1, 0, p;\n\t}"
 	    : "=r"(ok)
-	    : "r"(smem_addr(bar)), "r"(parity)
+	    : "r"(smem_addr(bar)), "r"(parity), "r"(200000u)
 	    : "memory");
 	return ok != 0;
 }

@@ -79,7 +79,8 @@ struct QoiFState {
 	uint64_t *rbw;      /* [segs] slots of the guess read before the segment wrote them */
 	uint32_t *dep;      /* [segs] bit 0: the result depends on the incoming r,g,b; bit 1: ... on the incoming alpha;
 	                       bits 2,3: r,g,b / alpha of the colour after the segment derive from the guess;
-	                       bits 4,5: ... and do so as "incoming colour + deltas" (DIFF / LUMA / RUN ops only) */
+	                       bits 4,5: ... and do so as "incoming colour + deltas" (DIFF / LUMA / RUN ops only);
+	                       bit 6: the walk read a guessed slot that can only be an initial zero (see fstate_kernel) */
 	uint8_t *flag;      /* [segs] QOI_FF_* of the last check */
 	uint32_t *list;     /* [segs] segments to walk in the next round */
 	uint32_t *n_list;   /* [64] length of that list per round */
@@ -238,12 +239,13 @@ __device__ __forceinline__ uint32_t chunk_image(const QoiFParams &P, uint32_t c)
    2's first version chained 32 segments at a time through one lane: 1.3 ms for a 4096x4096 photograph, more than the
    state round it feeds.)  Also resets what the state rounds accumulate per image and marks every tile of the image as
    "no op starts here" (the state rounds overwrite the tiles in which one does). */
-#define QOI_FCHAIN_THREADS 512
-#define QOI_FCHAIN_SMEM ((QOI_FCHAIN_THREADS * 8 + 8) * 4)
+#define QOI_FCHAIN_THREADS 1024
+#define QOI_FCHAIN_SMEM ((QOI_FCHAIN_THREADS * 8 + 32 * 8 + 8) * 4)
 __global__ void __launch_bounds__(QOI_FCHAIN_THREADS) fchain_kernel(const QoiFParams P) {
 	QOI_DYNAMIC_SMEM(smem); /* QOI_FCHAIN_SMEM */
 	uint32_t *s_map = (uint32_t *)smem;                  /* [thread][8]: exit skip per entry skip (packed), 5 pixel counts; then: start skip, start pixel */
-	uint32_t *s_live = s_map + QOI_FCHAIN_THREADS * 8;   /* live segments; pixels of the whole stream */
+	uint32_t *s_grp = s_map + QOI_FCHAIN_THREADS * 8;    /* [32][8]: the same for groups of 32 threads */
+	uint32_t *s_live = s_grp + 32 * 8;                   /* live segments */
 	const uint32_t img = blockIdx.x;
 	const uint32_t t = threadIdx.x;
 	if (img >= P.n_images) return;
@@ -276,12 +278,40 @@ __global__ void __launch_bounds__(QOI_FCHAIN_THREADS) fchain_kernel(const QoiFPa
 		for (int k = 0; k < 5; k++) s_map[t * 8 + 1 + k] = px[k];
 	}
 	__syncthreads();
+	if (t < 32u) { /* the maps of 32 consecutive threads, composed */
+		uint32_t sk[5] = {0u, 1u, 2u, 3u, 4u}, px[5] = {0u, 0u, 0u, 0u, 0u};
+		for (uint32_t q = 0; q < 32u; q++) {
+			const uint32_t *mp = s_map + (t * 32u + q) * 8;
+			const uint32_t e = mp[0];
+#pragma unroll
+			for (int k = 0; k < 5; k++) {
+				px[k] += mp[1 + sk[k]];
+				sk[k] = (e >> (4u * sk[k])) & 0xFu;
+			}
+		}
+		s_grp[t * 8] = sk[0] | (sk[1] << 4) | (sk[2] << 8) | (sk[3] << 12) | (sk[4] << 16);
+#pragma unroll
+		for (int k = 0; k < 5; k++) s_grp[t * 8 + 1 + k] = px[k];
+	}
+	__syncthreads();
 	if (t == 0) { /* the stream starts at an op (skip 0), pixel 0 */
 		uint32_t skip = 0, px = 0;
-		for (uint32_t k = 0; k < QOI_FCHAIN_THREADS; k++) {
-			const uint32_t e = s_map[k * 8], c = s_map[k * 8 + 1 + skip];
-			s_map[k * 8 + 6] = skip;
-			s_map[k * 8 + 7] = px;
+		for (uint32_t q = 0; q < 32u; q++) {
+			const uint32_t e = s_grp[q * 8], c = s_grp[q * 8 + 1 + skip];
+			s_grp[q * 8 + 6] = skip;
+			s_grp[q * 8 + 7] = px;
+			px += c;
+			skip = (e >> (4u * skip)) & 0xFu;
+		}
+	}
+	__syncthreads();
+	if (t < 32u) {
+		uint32_t skip = s_grp[t * 8 + 6], px = s_grp[t * 8 + 7];
+		for (uint32_t q = 0; q < 32u; q++) {
+			uint32_t *mp = s_map + (t * 32u + q) * 8;
+			const uint32_t e = mp[0], c = mp[1 + skip];
+			mp[6] = skip;
+			mp[7] = px;
 			px += c;
 			skip = (e >> (4u * skip)) & 0xFu;
 		}
@@ -289,23 +319,10 @@ __global__ void __launch_bounds__(QOI_FCHAIN_THREADS) fchain_kernel(const QoiFPa
 	__syncthreads();
 	{
 		uint32_t skip = s_map[t * 8 + 6], px = s_map[t * 8 + 7];
-		/* the tile boundaries behind a segment's last op start belong to later ops: tb0 of the segment behind it */
-		uint32_t tbn = 0; /* the stream's very first op owns tile 0's record */
-		if (j_lo > 0u && j_lo < nseg) { /* from the segment before my block: its entry skip is my start state seen backwards -- recompute it */
-			/* walk the last segment of the previous block: its start state is not stored, so thread t - 1's block is replayed
-			   from ITS start; cheap (per <= a few dozen) and only the last step is needed */
-			uint32_t ps = s_map[(t - 1) * 8 + 6], pp = s_map[(t - 1) * 8 + 7];
-			const uint32_t q_lo = (t - 1) * per;
-			for (uint32_t j = q_lo; j < j_lo; j++) {
-				const uint32_t g = base + j;
-				const uint2 e = *(const uint2 *)(P.f.exit_skip + (size_t)g * 8);
-				const uint32_t c = P.f.px_cnt[(size_t)g * 5 + ps];
-				if (j + 1 == j_lo && c && pp < m.npx) tbn = ((pp + P.f.last_rel[(size_t)g * 5 + ps]) / QOI_TILE_PX + 1u) * QOI_TILE_PX;
-				pp += c;
-				ps = (ps < 4u ? (e.x >> (8u * ps)) : e.y) & 0xFFu;
-			}
-		}
 		uint32_t live = 0;
+		/* The tile boundaries behind a segment's last op start belong to later ops: every segment writes tb0 of the segment
+		   BEHIND it (the stream's very first op owns tile 0's record: 0 for segment 0). */
+		if (t == 0 && nseg) P.f.tb0[base] = 0u;
 		for (uint32_t j = j_lo; j < j_hi; j++) {
 			if (px >= m.npx) break; /* all pixels already produced: this and every later segment is dead */
 			const uint32_t g = base + j;
@@ -313,10 +330,10 @@ __global__ void __launch_bounds__(QOI_FCHAIN_THREADS) fchain_kernel(const QoiFPa
 			const uint32_t c = P.f.px_cnt[(size_t)g * 5 + skip];
 			P.f.entry[g] = (uint8_t)skip;
 			P.f.px_start[g] = px;
-			P.f.tb0[g] = tbn;
 			P.f.g_px[g] = 0xFF000000u; /* round-0 guess: the reference's initial state (qoi.h:533-537); exact for segment 0 */
 			P.f.flag[g] = j == 0u ? (uint8_t)QOI_FF_TRUST : (uint8_t)0;
-			if (c) tbn = ((px + P.f.last_rel[(size_t)g * 5 + skip]) / QOI_TILE_PX + 1u) * QOI_TILE_PX;
+			/* a segment without an op start (only the last one can be that short) leaves the boundary where it was: nothing behind it reads it */
+			if (j + 1u < nseg) P.f.tb0[g + 1u] = c ? ((px + P.f.last_rel[(size_t)g * 5 + skip]) / QOI_TILE_PX + 1u) * QOI_TILE_PX : 0u;
 			px += c;
 			skip = (skip < 4u ? (e.x >> (8u * skip)) : e.y) & 0xFFu;
 			live = j + 1u;
@@ -335,7 +352,7 @@ __global__ void __launch_bounds__(QOI_FCHAIN_THREADS) fchain_kernel(const QoiFPa
 		}
 		P.f.n_live[img] = live;
 		P.f.bad_cnt[img] = P.f.bad_cnt[P.n_images + img] = P.f.bad_cnt[2u * P.n_images + img] = P.f.bad_cnt[3u * P.n_images + img] = 0;
-		P.f.first_bad[img] = P.f.first_bad[P.n_images + img] = live;
+		P.f.first_bad[img] = P.f.first_bad[P.n_images + img] = 0x7FFFFFFFu;
 	}
 }
 
@@ -406,6 +423,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 	   of a slot the segment filled itself inherits them. */
 	constexpr uint32_t F_W = 1u, F_TRGB = 2u, F_TA = 4u, F_CRGB = 8u, F_CA = 16u, F_DRGB = 32u, F_DA = 64u;
 	uint32_t cf, depacc;
+	bool suspect;
 	auto flag_byte = [&](uint32_t slot) -> uint8_t * { return (uint8_t *)(flg + (slot >> 2) * B) + (slot & 3u); };
 	/* the W bits / (T_RGB | T_A) bits of all 64 slots as masks */
 	auto gather = [&](uint64_t &wr, uint64_t &taint) {
@@ -495,6 +513,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 	rbw = 0;
 	cf = F_TRGB | F_TA | F_CRGB | F_CA;
 	depacc = 0;
+	suspect = false;
 #pragma unroll
 	for (int q = 0; q < 16; q++) flg[q * B] = 0u;
 	while (rd.p < end && pos < m.npx) { /* qoi.h:540,544: no op is parsed once every pixel is there */
@@ -530,8 +549,15 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 		const uint32_t fbv = *fb_t;
 		const bool own_slot = (fbv & F_W) != 0u;
 		if (is_idx && !own_slot) rbw |= 1ull << t6; /* the guessed index[] is used */
-		/* INDEX: what the slot's colour derived from (through index[]: D = T), or a guessed slot */
-		const uint32_t cf_idx = own_slot ? ((fbv & (F_TRGB | F_TA | F_CRGB | F_CA)) | ((fbv & (F_TRGB | F_TA)) << 4)) : (F_TRGB | F_TA | F_DRGB | F_DA);
+		/* index[t] only ever holds a colour that hashes to t, or the initial zero (qoi.h:533,577): a guessed slot whose value
+		   does not hash to its own number is an initial zero -- which an encoder never refers to (only a hand-made stream
+		   does).  Almost certainly the guess is wrong there, and {0,0,0,0} would put alpha 0 into everything this segment
+		   derives from it: mark the walk, so that it is not trusted on a mere re-walk (seg_trusted). */
+		suspect = suspect || (is_idx && !own_slot && qoi_slot(idxv) != t6);
+		/* INDEX of a slot the segment filled itself: the stored colour's provenance (from the incoming colour -> still
+		   incoming colour + deltas; from a guessed slot -> D); of a guessed slot: D */
+		const uint32_t own_t = fbv & (F_TRGB | F_TA), own_c = (fbv & (F_CRGB | F_CA)) >> 2;
+		const uint32_t cf_idx = own_slot ? ((fbv & (F_TRGB | F_TA | F_CRGB | F_CA)) | ((own_t & ~own_c) << 4)) : (F_TRGB | F_TA | F_DRGB | F_DA);
 		uint32_t ncf = is_rgb ? (cf & (F_TA | F_CA | F_DA)) : cf; /* RGB: r,g,b from the stream, alpha kept; DIFF / LUMA / RUN: unchanged */
 		ncf = is_rgba ? 0u : ncf;
 		cf = is_idx ? cf_idx : ncf;
@@ -561,7 +587,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 	/* bits 0,1: the result depends on the incoming r,g,b / alpha; bits 2,3: r,g,b / alpha of the final colour derive from the
 	   guess; bits 4,5: ... as incoming colour + deltas only */
 	P.f.dep[g] = ((depacc & F_CRGB) ? 1u : 0u) | ((depacc & F_CA) ? 2u : 0u) | ((cf & F_TRGB) ? 4u : 0u) | ((cf & F_TA) ? 8u : 0u) |
-	             (((cf & (F_TRGB | F_DRGB)) == F_TRGB) ? 16u : 0u) | (((cf & (F_TA | F_DA)) == F_TA) ? 32u : 0u);
+	             (((cf & (F_TRGB | F_DRGB)) == F_TRGB) ? 16u : 0u) | (((cf & (F_TA | F_DA)) == F_TA) ? 32u : 0u) | (suspect ? 64u : 0u);
 	{
 		uint32_t *dst = P.f.o_tab + (size_t)g * 64;
 #pragma unroll 8
@@ -605,16 +631,30 @@ __device__ __forceinline__ bool stream_settled(const QoiFParams &P, uint32_t img
 /* Does segment g determine word t of the state behind it (t < 64: index[t], t == 64: the colour)?  What the segment wrote from
    its own bytes always does; what it derived from its guess only if that guess held (QOI_FF_TRUST) -- a stream of nothing but
    INDEX ops copies its guess around, and untrusted copies would push every wrong guess one segment further per round. */
-__device__ __forceinline__ bool seg_gives(const QoiFParams &P, uint32_t g, uint32_t t) {
-	const bool trust = (P.f.flag[g] & QOI_FF_TRUST) != 0u;
+/* A walk that started from a guess which held on everything it depended on is trusted; a fresh re-walk is trusted ahead of
+   its check (QOI_FF_TRUST) -- unless it read an initial-zero slot (dep bit 6): then only once it lies inside the proven
+   prefix of its stream (g < gpe; segment 0 always does). */
+__device__ __forceinline__ bool seg_trusted(const QoiFParams &P, uint32_t g, uint32_t gpe) {
+	return (P.f.flag[g] & QOI_FF_TRUST) != 0u && (!(P.f.dep[g] & 64u) || g < gpe);
+}
+/* proven prefix of a stream, as a global segment index: what the check of the round before established */
+__device__ __forceinline__ uint32_t stream_proven_end(const QoiFParams &P, uint32_t img) {
+	const uint32_t base = P.f.seg_base[img];
+	if (P.round == 0u) return base + 1u;
+	const uint32_t key = P.f.first_bad[((P.round - 1u) & 1u) * P.n_images + img]; /* 2 * segment + (not a disagreement) */
+	const uint32_t pe = (key >> 1) + (key & 1u);
+	return base + (pe > 1u ? pe : 1u);
+}
+__device__ __forceinline__ bool seg_gives(const QoiFParams &P, uint32_t g, uint32_t t, uint32_t gpe) {
+	const bool trust = seg_trusted(P, g, gpe);
 	return ((P.f.o_wr[g] >> t) & 1ull) && (trust || !((P.f.o_taint[g] >> t) & 1ull));
 }
 /* The colour is not "last writer": a segment of DIFF / LUMA / RUN ops adds a known delta to whatever colour enters it.  So
    the colour's scan composes maps  colour -> (r,g,b: constant c | + d) x (alpha: constant c | unchanged), one per segment.
    A map word: value bytes (constant or delta per channel), bit 32: r,g,b constant, bit 33: alpha constant. */
-__device__ __forceinline__ uint64_t seg_colour_map(const QoiFParams &P, uint32_t g) {
+__device__ __forceinline__ uint64_t seg_colour_map(const QoiFParams &P, uint32_t g, uint32_t gpe) {
 	const uint32_t d = P.f.dep[g], o = P.f.o_px[g], gi = P.f.g_px[g];
-	const bool trust = (P.f.flag[g] & QOI_FF_TRUST) != 0u;
+	const bool trust = seg_trusted(P, g, gpe);
 	uint64_t m = 0;
 	uint32_t v = 0;
 	/* r,g,b: from the segment's own bytes, or derived through index[] and trusted -> constant; incoming + deltas -> add;
@@ -649,14 +689,14 @@ struct SegWord {
 	bool gives;   /* ... and whether it determines the slot */
 	uint64_t map; /* t == 64: the colour map */
 };
-__device__ __forceinline__ SegWord seg_word(const QoiFParams &P, uint32_t g, uint32_t t) {
+__device__ __forceinline__ SegWord seg_word(const QoiFParams &P, uint32_t g, uint32_t t, uint32_t gpe) {
 	SegWord w;
 	w.v = 0; w.gives = false; w.map = 0;
 	if (t < 64u) {
-		w.gives = seg_gives(P, g, t);
+		w.gives = seg_gives(P, g, t, gpe);
 		w.v = P.f.o_tab[(size_t)g * 64 + t];
 	} else if (t == 64u) {
-		w.map = seg_colour_map(P, g);
+		w.map = seg_colour_map(P, g, gpe);
 	}
 	return w;
 }
@@ -678,6 +718,7 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_a_kernel(const QoiFPa
 	if (j0 >= live) return; /* beyond the stream: never looked at */
 	const uint32_t n = (j0 + QOI_FCHUNK < live ? j0 + QOI_FCHUNK : live) - j0;
 	const uint32_t g0 = P.f.seg_base[img] + j0;
+	const uint32_t gpe = stream_proven_end(P, img);
 	uint32_t val = 0;
 	bool wrote = false;
 	uint64_t cmap = 0; /* identity: + 0, alpha unchanged */
@@ -685,7 +726,7 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_a_kernel(const QoiFPa
 		SegWord w[QOI_FWALK_BATCH];
 #pragma unroll
 		for (int k = 0; k < QOI_FWALK_BATCH; k++)
-			if (jb + k < n) w[k] = seg_word(P, g0 + jb + k, t);
+			if (jb + k < n) w[k] = seg_word(P, g0 + jb + k, t, gpe);
 #pragma unroll
 		for (int k = 0; k < QOI_FWALK_BATCH; k++) {
 			if (jb + k < n) {
@@ -805,6 +846,7 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fverify_kernel(const QoiFPa
 	if (j0 >= live) return;
 	const uint32_t n = (j0 + QOI_FCHUNK < live ? j0 + QOI_FCHUNK : live) - j0;
 	const uint32_t g0 = P.f.seg_base[img] + j0;
+	const uint32_t gpe = stream_proven_end(P, img);
 	if (t < 2u) s_dep[t] = 0u;
 	__syncthreads();
 	uint32_t T = t < 64u ? P.f.p_tab[(size_t)c * 64 + t] : (t == 64u ? P.f.p_px[c] : 0u);
@@ -816,7 +858,7 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fverify_kernel(const QoiFPa
 		for (int k = 0; k < QOI_FWALK_BATCH; k++) {
 			if (jb + k < n) {
 				const uint32_t g = g0 + jb + k;
-				w[k] = seg_word(P, g, t);
+				w[k] = seg_word(P, g, t, gpe);
 				gv[k] = 0; need[k] = 0;
 				if (t < 64u) {
 					gv[k] = P.f.g_tab[(size_t)g * 64 + t];
@@ -858,15 +900,19 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fverify_kernel(const QoiFPa
 		/* A segment that was not trusted when the state was scanned had its guess-derived results left out: agreeing with
 		   such a state proves nothing yet.  The induction "segment 0 is exact; a segment whose guess agrees with the exact
 		   state before it is exact" only runs over a prefix in which every segment was trusted AND agrees. */
-		const bool was_trusted = in && (P.f.flag[g0 + (in ? t : 0u)] & QOI_FF_TRUST) != 0u;
+		const bool was_trusted = in && seg_trusted(P, g0 + (in ? t : 0u), gpe);
 		const bool bad = in && (isdep || !was_trusted);
 		/* the next walk starts from the scanned state: trust what it derives from it until a check says otherwise */
 		if (in) P.f.flag[g0 + t] = (uint8_t)((isdep && last) ? QOI_FF_DEP : QOI_FF_TRUST);
 		const uint32_t par = P.round & 1u;
 		const uint32_t bb = __ballot_sync(QOI_FULL_MASK, bad);
+		/* the first unproven segment, and whether it merely was not trusted (then it is exact itself -- everything before it
+		   is proven and it agrees -- and the prefix ends behind it): key = 2 * segment + that */
+		const uint32_t fl = bb ? (uint32_t)__ffs((int)bb) - 1u : 0u;
+		const uint32_t db = __shfl_sync(QOI_FULL_MASK, isdep ? 1u : 0u, fl);
 		if (bb && (t & 31u) == 0u) {
 			atomicAdd(&P.f.bad_cnt[par * P.n_images + img], (uint32_t)__popc(bb));
-			atomicMin((int *)&P.f.first_bad[par * P.n_images + img], (int)(j0 + (t & 32u) + (uint32_t)__ffs((int)bb) - 1u));
+			atomicMin((int *)&P.f.first_bad[par * P.n_images + img], (int)(2u * (j0 + (t & 32u) + fl) + (db ? 0u : 1u)));
 		}
 		const uint32_t rb = __ballot_sync(QOI_FULL_MASK, isdep && !last);
 		if (rb) {
@@ -894,7 +940,7 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fverify_kernel(const QoiFPa
    walk its start state.  (A settled stream's scan results are still in place: nothing touched them since.) */
 __device__ __forceinline__ uint32_t stream_first_bad(const QoiFParams &P, uint32_t img) {
 	const uint32_t par = P.f.bad_cnt[3u * P.n_images + img] & 1u;
-	const uint32_t fb = P.f.first_bad[par * P.n_images + img], live = P.f.n_live[img];
+	const uint32_t fb = P.f.first_bad[par * P.n_images + img] >> 1, live = P.f.n_live[img]; /* (key, see fverify_kernel) */
 	return fb < live ? fb : live;
 }
 __global__ void __launch_bounds__(QOI_FSCAN_THREADS) ffinal_kernel(const QoiFParams P) {
@@ -909,12 +955,13 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) ffinal_kernel(const QoiFPar
 	if (j0 > fb) return; /* nothing proven in this chunk, and the fall-back does not start here */
 	const uint32_t n = (j0 + QOI_FCHUNK < live ? j0 + QOI_FCHUNK : live) - j0;
 	const uint32_t g0 = P.f.seg_base[img] + j0;
+	const uint32_t gpe = P.f.seg_base[img] + (fb > 1u ? fb : 1u); /* every segment before fb is proven */
 	uint32_t T = t < 64u ? P.f.p_tab[(size_t)c * 64 + t] : (t == 64u ? P.f.p_px[c] : 0u);
 	for (uint32_t jb = 0; jb < n; jb += QOI_FWALK_BATCH) {
 		SegWord w[QOI_FWALK_BATCH];
 #pragma unroll
 		for (int k = 0; k < QOI_FWALK_BATCH; k++)
-			if (jb + k < n) w[k] = seg_word(P, g0 + jb + k, t);
+			if (jb + k < n) w[k] = seg_word(P, g0 + jb + k, t, gpe);
 #pragma unroll
 		for (int k = 0; k < QOI_FWALK_BATCH; k++) {
 			if (jb + k < n) {
