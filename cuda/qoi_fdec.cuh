@@ -41,7 +41,7 @@ namespace qoifdec {
 using namespace qoidev;
 
 #define QOI_FSEG_BYTES 1024
-#define QOI_FROUNDS 24  /* state rounds before the sequential fall-back */
+#define QOI_FROUNDS 16  /* state rounds before the sequential fall-back */
 #define QOI_FCHUNK 64   /* segments per scan chunk */
 #define QOI_FDEC_THREADS 64
 #define QOI_FSCAN_THREADS 96 /* 64 slot threads + the colour thread (thread 64); a multiple of 32 */
@@ -84,6 +84,7 @@ struct QoiFState {
 	uint8_t *flag;      /* [segs] QOI_FF_* of the last check */
 	uint32_t *list;     /* [segs] segments to walk in the next round */
 	uint32_t *n_list;   /* [64] length of that list per round */
+	uint32_t *active;   /* [64] streams a round's scan still looked at (0: every later launch returns at once) */
 	/* scan */
 	uint32_t *a_tab;    /* [chunks][64] last value written per slot inside the chunk */
 	uint64_t *a_wr;     /* [chunks] slots written inside the chunk */
@@ -264,13 +265,18 @@ __global__ void __launch_bounds__(QOI_FCHAIN_THREADS) fchain_kernel(const QoiFPa
 	const uint32_t j_lo = t * per < nseg ? t * per : nseg, j_hi = j_lo + per < nseg ? j_lo + per : nseg;
 	{ /* my block's map */
 		uint32_t sk[5] = {0u, 1u, 2u, 3u, 4u}, px[5] = {0u, 0u, 0u, 0u, 0u};
-		for (uint32_t j = j_lo; j < j_hi; j++) {
+#pragma unroll 4
+		for (uint32_t j = j_lo; j < j_hi; j++) { /* all five counts are fetched whatever the skips turn out to be: the loads of several segments overlap */
 			const uint32_t g = base + j;
 			const uint2 e = *(const uint2 *)(P.f.exit_skip + (size_t)g * 8);
+			uint32_t c[5];
+#pragma unroll
+			for (int k = 0; k < 5; k++) c[k] = P.f.px_cnt[(size_t)g * 5 + k];
 #pragma unroll
 			for (int k = 0; k < 5; k++) {
-				px[k] += P.f.px_cnt[(size_t)g * 5 + sk[k]];
-				sk[k] = (sk[k] < 4u ? (e.x >> (8u * sk[k])) : e.y) & 0xFFu;
+				const uint32_t q = sk[k];
+				px[k] += q == 0u ? c[0] : q == 1u ? c[1] : q == 2u ? c[2] : q == 3u ? c[3] : c[4];
+				sk[k] = (q < 4u ? (e.x >> (8u * q)) : e.y) & 0xFFu;
 			}
 		}
 		s_map[t * 8] = sk[0] | (sk[1] << 4) | (sk[2] << 8) | (sk[3] << 12) | (sk[4] << 16);
@@ -323,17 +329,22 @@ __global__ void __launch_bounds__(QOI_FCHAIN_THREADS) fchain_kernel(const QoiFPa
 		/* The tile boundaries behind a segment's last op start belong to later ops: every segment writes tb0 of the segment
 		   BEHIND it (the stream's very first op owns tile 0's record: 0 for segment 0). */
 		if (t == 0 && nseg) P.f.tb0[base] = 0u;
+#pragma unroll 4
 		for (uint32_t j = j_lo; j < j_hi; j++) {
-			if (px >= m.npx) break; /* all pixels already produced: this and every later segment is dead */
 			const uint32_t g = base + j;
 			const uint2 e = *(const uint2 *)(P.f.exit_skip + (size_t)g * 8);
-			const uint32_t c = P.f.px_cnt[(size_t)g * 5 + skip];
+			uint32_t c5[5], l5[5];
+#pragma unroll
+			for (int k = 0; k < 5; k++) { c5[k] = P.f.px_cnt[(size_t)g * 5 + k]; l5[k] = P.f.last_rel[(size_t)g * 5 + k]; }
+			if (px >= m.npx) break; /* all pixels already produced: this and every later segment is dead */
+			const uint32_t c = skip == 0u ? c5[0] : skip == 1u ? c5[1] : skip == 2u ? c5[2] : skip == 3u ? c5[3] : c5[4];
+			const uint32_t lr = skip == 0u ? l5[0] : skip == 1u ? l5[1] : skip == 2u ? l5[2] : skip == 3u ? l5[3] : l5[4];
 			P.f.entry[g] = (uint8_t)skip;
 			P.f.px_start[g] = px;
 			P.f.g_px[g] = 0xFF000000u; /* round-0 guess: the reference's initial state (qoi.h:533-537); exact for segment 0 */
 			P.f.flag[g] = j == 0u ? (uint8_t)QOI_FF_TRUST : (uint8_t)0;
 			/* a segment without an op start (only the last one can be that short) leaves the boundary where it was: nothing behind it reads it */
-			if (j + 1u < nseg) P.f.tb0[g + 1u] = c ? ((px + P.f.last_rel[(size_t)g * 5 + skip]) / QOI_TILE_PX + 1u) * QOI_TILE_PX : 0u;
+			if (j + 1u < nseg) P.f.tb0[g + 1u] = c ? ((px + lr) / QOI_TILE_PX + 1u) * QOI_TILE_PX : 0u;
 			px += c;
 			skip = (skip < 4u ? (e.x >> (8u * skip)) : e.y) & 0xFFu;
 			live = j + 1u;
@@ -359,7 +370,7 @@ __global__ void __launch_bounds__(QOI_FCHAIN_THREADS) fchain_kernel(const QoiFPa
 /* round-0 guess of index[]: zeros (qoi.h:533); list counters */
 __global__ void __launch_bounds__(QOI_FDEC_THREADS) fzero_kernel(const QoiFParams P) {
 	const uint32_t g = blockIdx.x * QOI_FDEC_THREADS + threadIdx.x;
-	if (g < 64u) P.f.n_list[g] = 0u;
+	if (g < 64u) P.f.n_list[g] = P.f.active[g] = 0u;
 	if (g >= P.n_segs) return;
 	const uint32_t img = seg_image(P, g);
 	if (g - P.f.seg_base[img] >= P.f.n_live[img]) return;
@@ -370,22 +381,8 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fzero_kernel(const QoiFParam
 
 /* ------------------------------------------------------------------ 2. state round: one lane per segment, one trip per OP */
 /* index[] in shared memory [slot][thread] like qoi_decode_kernel; stream bytes through the same chunked reader. */
-__global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFParams P) {
-	QOI_DYNAMIC_SMEM(smem);
+__device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, uint32_t *tab, uint32_t *flg, uint32_t *ring) {
 	constexpr int B = QOI_FDEC_THREADS;
-	uint32_t *tab = (uint32_t *)smem + threadIdx.x; /* tab[slot * B] */
-	uint32_t *flg = tab + 64 * B;                   /* flg[word * B]: one byte per slot (below) */
-	uint32_t *ring = flg + 16 * B;                  /* ring[word * B] */
-	/* round 0: lane k takes segment k; later rounds: the k-th entry of the list the last fverify_kernel left */
-	const uint32_t k = blockIdx.x * B + threadIdx.x;
-	uint32_t g;
-	if (P.round == 0u) {
-		if (k >= P.n_segs) return;
-		g = k;
-	} else {
-		if (k >= P.f.n_list[P.round]) return;
-		g = P.f.list[k];
-	}
 	const uint32_t img = seg_image(P, g);
 	uint32_t j = g - P.f.seg_base[img];
 	const uint32_t live = P.f.n_live[img];
@@ -619,6 +616,18 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFPara
 	}
 }
 
+/* round 0: lane k takes segment k; later rounds: the k-th entry of the list the last fverify_kernel left (late rounds are
+   launched with a small grid and stride over it) */
+__global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFParams P) {
+	QOI_DYNAMIC_SMEM(smem);
+	constexpr int B = QOI_FDEC_THREADS;
+	uint32_t *tab = (uint32_t *)smem + threadIdx.x; /* tab[slot * B] */
+	uint32_t *flg = tab + 64 * B;                   /* flg[word * B]: one byte per slot */
+	uint32_t *ring = flg + 16 * B;                  /* ring[word * B] */
+	const uint32_t n = P.round == 0u ? P.n_segs : P.f.n_list[P.round];
+	for (uint32_t k = blockIdx.x * B + threadIdx.x; k < n; k += gridDim.x * B) fstate_walk(P, P.round == 0u ? k : P.f.list[k], tab, flg, ring);
+}
+
 /* ------------------------------------------------------------------ 3. last-writer scan over the segments of every stream */
 /* Per stream and round: bad_cnt planes 0,1 = segments the check of an even / odd round could not prove, plane 2 = the stream
    has settled (a check proved every segment: exact by induction from segment 0), plane 3 = the last round that looked at
@@ -644,10 +653,6 @@ __device__ __forceinline__ uint32_t stream_proven_end(const QoiFParams &P, uint3
 	const uint32_t key = P.f.first_bad[((P.round - 1u) & 1u) * P.n_images + img]; /* 2 * segment + (not a disagreement) */
 	const uint32_t pe = (key >> 1) + (key & 1u);
 	return base + (pe > 1u ? pe : 1u);
-}
-__device__ __forceinline__ bool seg_gives(const QoiFParams &P, uint32_t g, uint32_t t, uint32_t gpe) {
-	const bool trust = seg_trusted(P, g, gpe);
-	return ((P.f.o_wr[g] >> t) & 1ull) && (trust || !((P.f.o_taint[g] >> t) & 1ull));
 }
 /* The colour is not "last writer": a segment of DIFF / LUMA / RUN ops adds a known delta to whatever colour enters it.  So
    the colour's scan composes maps  colour -> (r,g,b: constant c | + d) x (alpha: constant c | unchanged), one per segment.
@@ -682,34 +687,39 @@ __device__ __forceinline__ uint64_t colour_compose(uint64_t a, uint64_t b) {
 	else { m |= a & (1ull << 33); v |= va & 0xFF000000u; }
 	return m | v;
 }
-/* one segment's contribution to thread t's word of the state, fetched ahead of its use (the walks below are chains of
-   selects; the loads do not depend on them and are issued eight segments at a time) */
-struct SegWord {
-	uint32_t v;   /* t < 64: the slot's value after the segment */
-	bool gives;   /* ... and whether it determines the slot */
-	uint64_t map; /* t == 64: the colour map */
+/* What the walks over a chunk need to know about each of its (up to 64) segments, gathered once per chunk by one thread per
+   segment: which slots the segment determines, its colour map, which words of its guess it depended on.  The walks
+   themselves then fetch only index[] words (eight segments ahead of the chain of selects that consumes them). */
+struct ChunkMeta {
+	uint64_t gives[QOI_FCHUNK]; /* slots the segment determines (written, and from its own bytes or trusted) */
+	uint64_t cmap[QOI_FCHUNK];  /* colour map */
+	uint64_t rbw[QOI_FCHUNK];   /* guessed slots it depended on */
+	uint32_t gpx[QOI_FCHUNK];   /* guessed colour */
+	uint32_t need[QOI_FCHUNK];  /* ... and the bits of it the segment depended on */
+	uint32_t stale[QOI_FCHUNK]; /* (fverify) 1: was not trusted when gathered */
 };
-__device__ __forceinline__ SegWord seg_word(const QoiFParams &P, uint32_t g, uint32_t t, uint32_t gpe) {
-	SegWord w;
-	w.v = 0; w.gives = false; w.map = 0;
-	if (t < 64u) {
-		w.gives = seg_gives(P, g, t, gpe);
-		w.v = P.f.o_tab[(size_t)g * 64 + t];
-	} else if (t == 64u) {
-		w.map = seg_colour_map(P, g, gpe);
+#define QOI_FMETA_SMEM ((int)sizeof(qoifdec::ChunkMeta))
+__device__ __forceinline__ void chunk_meta(const QoiFParams &P, ChunkMeta *M, uint32_t g0, uint32_t n, uint32_t gpe, uint32_t t) {
+	if (t < n) {
+		const uint32_t g = g0 + t;
+		const bool trust = seg_trusted(P, g, gpe);
+		const uint64_t wr = P.f.o_wr[g], ta = P.f.o_taint[g];
+		const uint32_t d = P.f.dep[g];
+		M->gives[t] = trust ? wr : (wr & ~ta);
+		M->cmap[t] = seg_colour_map(P, g, gpe);
+		M->rbw[t] = P.f.rbw[g];
+		M->gpx[t] = P.f.g_px[g];
+		M->need[t] = ((d & 1u) ? 0x00FFFFFFu : 0u) | ((d & 2u) ? 0xFF000000u : 0u);
+		M->stale[t] = trust ? 0u : 1u;
 	}
-	return w;
-}
-__device__ __forceinline__ uint32_t seg_advance(const SegWord &w, uint32_t t, uint32_t T) {
-	if (t < 64u) return w.gives ? w.v : T;
-	return t == 64u ? colour_apply(w.map, T) : T;
+	__syncthreads();
 }
 #define QOI_FWALK_BATCH 8
+/* every round after the first looks at the streams the check before it left unsettled; active[r] counts them */
+__device__ __forceinline__ bool round_idle(const QoiFParams &P) { return P.round > 0u && P.f.active[P.round - 1u] == 0u; }
 
 /* a: per chunk of QOI_FCHUNK segments, thread = slot (thread 64 = the colour): the chunk's last value per slot */
-__global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_a_kernel(const QoiFParams P) {
-	const uint32_t c = blockIdx.x, t = threadIdx.x;
-	if (c >= P.n_chunks) return;
+__device__ __forceinline__ void fscan_a_chunk(const QoiFParams &P, ChunkMeta *M, uint32_t c, uint32_t t) {
 	const uint32_t img = chunk_image(P, c);
 	if (stream_settled(P, img)) return;
 	const uint32_t lc = c - P.f.chunk_base[img];
@@ -718,33 +728,33 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_a_kernel(const QoiFPa
 	if (j0 >= live) return; /* beyond the stream: never looked at */
 	const uint32_t n = (j0 + QOI_FCHUNK < live ? j0 + QOI_FCHUNK : live) - j0;
 	const uint32_t g0 = P.f.seg_base[img] + j0;
-	const uint32_t gpe = stream_proven_end(P, img);
-	uint32_t val = 0;
-	bool wrote = false;
-	uint64_t cmap = 0; /* identity: + 0, alpha unchanged */
-	for (uint32_t jb = 0; jb < n; jb += QOI_FWALK_BATCH) {
-		SegWord w[QOI_FWALK_BATCH];
-#pragma unroll
-		for (int k = 0; k < QOI_FWALK_BATCH; k++)
-			if (jb + k < n) w[k] = seg_word(P, g0 + jb + k, t, gpe);
-#pragma unroll
-		for (int k = 0; k < QOI_FWALK_BATCH; k++) {
-			if (jb + k < n) {
-				if (t < 64u) {
-					if (w[k].gives) { val = w[k].v; wrote = true; }
-				} else if (t == 64u) {
-					cmap = colour_compose(cmap, w[k].map);
-				}
-			}
-		}
-	}
+	chunk_meta(P, M, g0, n, stream_proven_end(P, img), t);
 	if (t < 64u) {
+		uint32_t val = 0;
+		bool wrote = false;
+		for (uint32_t jb = 0; jb < n; jb += QOI_FWALK_BATCH) {
+			uint32_t v[QOI_FWALK_BATCH];
+#pragma unroll
+			for (int k = 0; k < QOI_FWALK_BATCH; k++)
+				if (jb + k < n) v[k] = P.f.o_tab[(size_t)(g0 + jb + k) * 64 + t];
+#pragma unroll
+			for (int k = 0; k < QOI_FWALK_BATCH; k++)
+				if (jb + k < n && ((M->gives[jb + k] >> t) & 1ull)) { val = v[k]; wrote = true; }
+		}
 		P.f.a_tab[(size_t)c * 64 + t] = val;
 		const uint32_t b = __ballot_sync(QOI_FULL_MASK, wrote);
 		if ((t & 31u) == 0u) ((uint32_t *)(P.f.a_wr + c))[t >> 5] = b; /* low / high half of the 64-bit mask */
 	} else if (t == 64u) {
-		P.f.a_px[c] = cmap;
+		uint64_t cm = 0; /* identity: + 0, alpha unchanged */
+		for (uint32_t j = 0; j < n; j++) cm = colour_compose(cm, M->cmap[j]);
+		P.f.a_px[c] = cm;
 	}
+	__syncthreads(); /* M is reused by the next chunk of this CTA */
+}
+__global__ void __launch_bounds__(QOI_FSCAN_THREADS) fscan_a_kernel(const QoiFParams P) {
+	QOI_DYNAMIC_SMEM(smem); /* QOI_FMETA_SMEM */
+	if (round_idle(P)) return;
+	for (uint32_t c = blockIdx.x; c < P.n_chunks; c += gridDim.x) fscan_a_chunk(P, (ChunkMeta *)smem, c, threadIdx.x);
 }
 
 /* b: per stream: exclusive prefix over its chunks, from the reference's initial state (qoi.h:533-537).  A 4096x4096
@@ -759,12 +769,13 @@ __global__ void __launch_bounds__(QOI_FSCANB_THREADS) fscan_b_kernel(const QoiFP
 	uint32_t *s_val = (uint32_t *)smem, *s_wr = s_val + QOI_FSCANB_GROUPS * 64;
 	uint64_t *s_map = (uint64_t *)(s_wr + QOI_FSCANB_GROUPS * 64);
 	const uint32_t img = blockIdx.x, t = threadIdx.x;
-	if (img >= P.n_images) return;
+	if (img >= P.n_images || round_idle(P)) return;
 	if (stream_settled(P, img)) { /* uniform over the CTA: every thread reads the same words */
 		if (t == 0) P.f.bad_cnt[2u * P.n_images + img] = 1u;
 		return;
 	}
 	if (t == 0) { /* what this round's check accumulates */
+		atomicAdd(&P.f.active[P.round], 1u);
 		P.f.bad_cnt[(P.round & 1u) * P.n_images + img] = 0u;
 		P.f.first_bad[(P.round & 1u) * P.n_images + img] = 0x7FFFFFFFu;
 		P.f.bad_cnt[3u * P.n_images + img] = P.round;
@@ -831,13 +842,8 @@ __global__ void __launch_bounds__(QOI_FSCANB_THREADS) fscan_b_kernel(const QoiFP
    scanned state as its new guess and is listed for the next round's walk.  `last`: the check after the final round -- no
    new guesses (behind the proven prefix the guesses must stay what the results belong to: the fall-back decides per segment
    whether its last walk stands). */
-#define QOI_FVERIFY_SMEM ((QOI_FCHUNK * 65 + 8) * 4)
-__global__ void __launch_bounds__(QOI_FSCAN_THREADS) fverify_kernel(const QoiFParams P, int last) {
-	QOI_DYNAMIC_SMEM(smem);
-	uint32_t *s_T = (uint32_t *)smem;           /* [segment of the chunk][65]: the scanned state before it */
-	uint32_t *s_dep = s_T + QOI_FCHUNK * 65;    /* [2]: segments with a disagreement (64-bit mask) */
-	const uint32_t c = blockIdx.x, t = threadIdx.x;
-	if (c >= P.n_chunks) return;
+#define QOI_FVERIFY_SMEM (QOI_FMETA_SMEM + (QOI_FCHUNK * 65 + 8) * 4)
+__device__ __forceinline__ void fverify_chunk(const QoiFParams &P, ChunkMeta *M, uint32_t *s_T, uint32_t *s_dep, uint32_t c, uint32_t t, int last) {
 	const uint32_t img = chunk_image(P, c);
 	if (stream_settled(P, img)) return;
 	const uint32_t lc = c - P.f.chunk_base[img];
@@ -846,41 +852,41 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fverify_kernel(const QoiFPa
 	if (j0 >= live) return;
 	const uint32_t n = (j0 + QOI_FCHUNK < live ? j0 + QOI_FCHUNK : live) - j0;
 	const uint32_t g0 = P.f.seg_base[img] + j0;
-	const uint32_t gpe = stream_proven_end(P, img);
 	if (t < 2u) s_dep[t] = 0u;
-	__syncthreads();
+	chunk_meta(P, M, g0, n, stream_proven_end(P, img), t);
 	uint32_t T = t < 64u ? P.f.p_tab[(size_t)c * 64 + t] : (t == 64u ? P.f.p_px[c] : 0u);
 	uint32_t mis_lo = 0, mis_hi = 0;
-	for (uint32_t jb = 0; jb < n; jb += QOI_FWALK_BATCH) {
-		SegWord w[QOI_FWALK_BATCH];
-		uint32_t gv[QOI_FWALK_BATCH], need[QOI_FWALK_BATCH]; /* my word of the guess; the bits of it the segment depended on */
+	if (t < 64u) {
+		for (uint32_t jb = 0; jb < n; jb += QOI_FWALK_BATCH) {
+			uint32_t v[QOI_FWALK_BATCH], gv[QOI_FWALK_BATCH];
 #pragma unroll
-		for (int k = 0; k < QOI_FWALK_BATCH; k++) {
-			if (jb + k < n) {
-				const uint32_t g = g0 + jb + k;
-				w[k] = seg_word(P, g, t, gpe);
-				gv[k] = 0; need[k] = 0;
-				if (t < 64u) {
-					gv[k] = P.f.g_tab[(size_t)g * 64 + t];
-					need[k] = ((P.f.rbw[g] >> t) & 1ull) ? 0xFFFFFFFFu : 0u;
-				} else if (t == 64u) {
-					const uint32_t d = P.f.dep[g];
-					gv[k] = P.f.g_px[g];
-					need[k] = ((d & 1u) ? 0x00FFFFFFu : 0u) | ((d & 2u) ? 0xFF000000u : 0u);
+			for (int k = 0; k < QOI_FWALK_BATCH; k++) {
+				if (jb + k < n) {
+					v[k] = P.f.o_tab[(size_t)(g0 + jb + k) * 64 + t];
+					gv[k] = P.f.g_tab[(size_t)(g0 + jb + k) * 64 + t];
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < QOI_FWALK_BATCH; k++) {
+				if (jb + k < n) {
+					const uint32_t j = jb + k;
+					s_T[j * 65 + t] = T;
+					if (((M->rbw[j] >> t) & 1ull) && gv[k] != T) {
+						if (j < 32u) mis_lo |= 1u << j;
+						else mis_hi |= 1u << (j - 32u);
+					}
+					if ((M->gives[j] >> t) & 1ull) T = v[k];
 				}
 			}
 		}
-#pragma unroll
-		for (int k = 0; k < QOI_FWALK_BATCH; k++) {
-			if (jb + k < n) {
-				const uint32_t j = jb + k;
-				if (t <= 64u) s_T[j * 65 + t] = T;
-				if ((gv[k] ^ T) & need[k]) {
-					if (j < 32u) mis_lo |= 1u << j;
-					else mis_hi |= 1u << (j - 32u);
-				}
-				T = seg_advance(w[k], t, T);
+	} else if (t == 64u) {
+		for (uint32_t j = 0; j < n; j++) {
+			s_T[j * 65 + 64] = T;
+			if ((M->gpx[j] ^ T) & M->need[j]) {
+				if (j < 32u) mis_lo |= 1u << j;
+				else mis_hi |= 1u << (j - 32u);
 			}
+			T = colour_apply(M->cmap[j], T);
 		}
 	}
 #pragma unroll
@@ -892,7 +898,7 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fverify_kernel(const QoiFPa
 		if (mis_lo) atomicOr(&s_dep[0], mis_lo);
 		if (mis_hi) atomicOr(&s_dep[1], mis_hi);
 	}
-	__syncthreads(); /* also: the flags are read by the walk above and changed only behind it */
+	__syncthreads();
 	const uint32_t dep_lo = s_dep[0], dep_hi = s_dep[1];
 	if (t < 64u) { /* thread = segment of the chunk (two warps) */
 		const bool in = t < n;
@@ -900,7 +906,7 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fverify_kernel(const QoiFPa
 		/* A segment that was not trusted when the state was scanned had its guess-derived results left out: agreeing with
 		   such a state proves nothing yet.  The induction "segment 0 is exact; a segment whose guess agrees with the exact
 		   state before it is exact" only runs over a prefix in which every segment was trusted AND agrees. */
-		const bool was_trusted = in && seg_trusted(P, g0 + (in ? t : 0u), gpe);
+		const bool was_trusted = in && M->stale[in ? t : 0u] == 0u;
 		const bool bad = in && (isdep || !was_trusted);
 		/* the next walk starts from the scanned state: trust what it derives from it until a check says otherwise */
 		if (in) P.f.flag[g0 + t] = (uint8_t)((isdep && last) ? QOI_FF_DEP : QOI_FF_TRUST);
@@ -933,6 +939,15 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) fverify_kernel(const QoiFPa
 			}
 		}
 	}
+	__syncthreads(); /* shared memory is reused by the next chunk of this CTA */
+}
+__global__ void __launch_bounds__(QOI_FSCAN_THREADS) fverify_kernel(const QoiFParams P, int last) {
+	QOI_DYNAMIC_SMEM(smem); /* QOI_FVERIFY_SMEM */
+	if (round_idle(P)) return;
+	ChunkMeta *M = (ChunkMeta *)smem;
+	uint32_t *s_T = (uint32_t *)(smem + QOI_FMETA_SMEM); /* [segment of the chunk][65]: the scanned state before it */
+	uint32_t *s_dep = s_T + QOI_FCHUNK * 65;             /* [2]: segments with a disagreement (64-bit mask) */
+	for (uint32_t c = blockIdx.x; c < P.n_chunks; c += gridDim.x) fverify_chunk(P, M, s_T, s_dep, c, threadIdx.x, last);
 }
 
 /* d: after the rounds.  Every segment of the proven prefix gets the scanned state in all 64 slots -- the exact state before
@@ -944,6 +959,8 @@ __device__ __forceinline__ uint32_t stream_first_bad(const QoiFParams &P, uint32
 	return fb < live ? fb : live;
 }
 __global__ void __launch_bounds__(QOI_FSCAN_THREADS) ffinal_kernel(const QoiFParams P) {
+	QOI_DYNAMIC_SMEM(smem); /* QOI_FMETA_SMEM */
+	ChunkMeta *M = (ChunkMeta *)smem;
 	const uint32_t c = blockIdx.x, t = threadIdx.x;
 	if (c >= P.n_chunks) return;
 	const uint32_t img = chunk_image(P, c);
@@ -955,25 +972,30 @@ __global__ void __launch_bounds__(QOI_FSCAN_THREADS) ffinal_kernel(const QoiFPar
 	if (j0 > fb) return; /* nothing proven in this chunk, and the fall-back does not start here */
 	const uint32_t n = (j0 + QOI_FCHUNK < live ? j0 + QOI_FCHUNK : live) - j0;
 	const uint32_t g0 = P.f.seg_base[img] + j0;
-	const uint32_t gpe = P.f.seg_base[img] + (fb > 1u ? fb : 1u); /* every segment before fb is proven */
+	chunk_meta(P, M, g0, n, P.f.seg_base[img] + (fb > 1u ? fb : 1u), t); /* every segment before fb is proven */
 	uint32_t T = t < 64u ? P.f.p_tab[(size_t)c * 64 + t] : (t == 64u ? P.f.p_px[c] : 0u);
-	for (uint32_t jb = 0; jb < n; jb += QOI_FWALK_BATCH) {
-		SegWord w[QOI_FWALK_BATCH];
+	if (t < 64u) {
+		for (uint32_t jb = 0; jb < n; jb += QOI_FWALK_BATCH) {
+			uint32_t v[QOI_FWALK_BATCH];
 #pragma unroll
-		for (int k = 0; k < QOI_FWALK_BATCH; k++)
-			if (jb + k < n) w[k] = seg_word(P, g0 + jb + k, t, gpe);
+			for (int k = 0; k < QOI_FWALK_BATCH; k++)
+				if (jb + k < n) v[k] = P.f.o_tab[(size_t)(g0 + jb + k) * 64 + t];
 #pragma unroll
-		for (int k = 0; k < QOI_FWALK_BATCH; k++) {
-			if (jb + k < n) {
-				const uint32_t jj = j0 + jb + k, g = g0 + jb + k;
-				if (jj < fb) {
-					if (t < 64u) P.f.g_tab[(size_t)g * 64 + t] = T;
-					else if (t == 64u) P.f.g_px[g] = T;
-				} else if (jj == fb && t <= 64u) {
-					P.f.x_state[(size_t)img * 65 + t] = T; /* where the fall-back walk starts */
+			for (int k = 0; k < QOI_FWALK_BATCH; k++) {
+				if (jb + k < n) {
+					const uint32_t jj = j0 + jb + k, g = g0 + jb + k;
+					if (jj < fb) P.f.g_tab[(size_t)g * 64 + t] = T;
+					else if (jj == fb) P.f.x_state[(size_t)img * 65 + t] = T; /* where the fall-back walk starts */
+					if ((M->gives[jb + k] >> t) & 1ull) T = v[k];
 				}
-				T = seg_advance(w[k], t, T);
 			}
+		}
+	} else if (t == 64u) {
+		for (uint32_t j = 0; j < n; j++) {
+			const uint32_t jj = j0 + j;
+			if (jj < fb) P.f.g_px[g0 + j] = T;
+			else if (jj == fb) P.f.x_state[(size_t)img * 65 + 64] = T;
+			T = colour_apply(M->cmap[j], T);
 		}
 	}
 }
@@ -1137,6 +1159,7 @@ static inline void fstate_bind(QoiFState &f, unsigned char *base, const size_t *
 	f.p_tab = (uint32_t *)(base + off[20]);
 	f.p_px = (uint32_t *)(base + off[21]);
 	f.claim = (uint32_t *)(base + off[30]);
+	f.active = (uint32_t *)(base + off[31]);
 	f.bad_cnt = (uint32_t *)(base + off[22]);
 	f.first_bad = (uint32_t *)(base + off[23]);
 	f.o_taint = (uint64_t *)(base + off[24]);

@@ -309,15 +309,20 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 		qoifdec::fparse_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
 		qoifdec::fchain_kernel<<<F.n_images, QOI_FCHAIN_THREADS, QOI_FCHAIN_SMEM, s>>>(F);
 		qoifdec::fzero_kernel<<<gs, QOI_FDEC_THREADS, 0, s>>>(F);
+		/* rounds 0..2 move most of the segments; later rounds usually find every stream settled (each launch then returns at
+		   once: active[]) or walk a handful of segments: a grid of a few CTAs per SM striding over the work keeps an idle
+		   round at a few microseconds */
+		const uint32_t small = (uint32_t)ctx->sm_count * 4u;
 		for (int r = 0; r < QOI_FROUNDS; r++) {
 			F.round = (uint32_t)r;
 			const int last = r + 1 == QOI_FROUNDS;
-			qoifdec::fstate_kernel<<<gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
-			qoifdec::fscan_a_kernel<<<F.n_chunks, QOI_FSCAN_THREADS, 0, s>>>(F);
+			const uint32_t g_seg = r < 3 ? gs : (gs < small ? gs : small), g_chk = r < 3 ? F.n_chunks : (F.n_chunks < small ? F.n_chunks : small);
+			qoifdec::fstate_kernel<<<g_seg, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
+			qoifdec::fscan_a_kernel<<<g_chk, QOI_FSCAN_THREADS, QOI_FMETA_SMEM, s>>>(F);
 			qoifdec::fscan_b_kernel<<<F.n_images, QOI_FSCANB_THREADS, QOI_FSCANB_SMEM, s>>>(F);
-			qoifdec::fverify_kernel<<<F.n_chunks, QOI_FSCAN_THREADS, QOI_FVERIFY_SMEM, s>>>(F, last);
+			qoifdec::fverify_kernel<<<g_chk, QOI_FSCAN_THREADS, QOI_FVERIFY_SMEM, s>>>(F, last);
 		}
-		qoifdec::ffinal_kernel<<<F.n_chunks, QOI_FSCAN_THREADS, 0, s>>>(F);
+		qoifdec::ffinal_kernel<<<F.n_chunks, QOI_FSCAN_THREADS, QOI_FMETA_SMEM, s>>>(F);
 		qoifdec::ffall_kernel<<<F.n_images, 32, QOI_FFALL_SMEM, s>>>(F);
 		qoifdec::fcompose_kernel<<<(p->geom.n_tiles * 64u + 127u) / 128u, 128, 0, s>>>(F, p->geom.n_tiles, p->d_tile_img);
 		g_launches += 6 + 4 * QOI_FROUNDS;

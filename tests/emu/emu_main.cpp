@@ -89,10 +89,10 @@ static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned se
 	for (int r = 0; r < rounds; r++) {
 		F.round = (uint32_t)r;
 		const int last = r + 1 == rounds;
-		qemu::launch(gs, QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { qoifdec::fstate_kernel(F); }, seed);
-		qemu::launch(FL.n_chunks, QOI_FSCAN_THREADS, 0, [&]() { qoifdec::fscan_a_kernel(F); }, seed);
+		qemu::launch(r < 3 ? gs : (gs < 5u ? gs : 5u), QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { qoifdec::fstate_kernel(F); }, seed);
+		qemu::launch(r < 3 ? FL.n_chunks : (FL.n_chunks < 7u ? FL.n_chunks : 7u), QOI_FSCAN_THREADS, QOI_FMETA_SMEM, [&]() { qoifdec::fscan_a_kernel(F); }, seed);
 		qemu::launch(D.n_images, QOI_FSCANB_THREADS, QOI_FSCANB_SMEM, [&]() { qoifdec::fscan_b_kernel(F); }, seed);
-		qemu::launch(FL.n_chunks, QOI_FSCAN_THREADS, QOI_FVERIFY_SMEM, [&]() { qoifdec::fverify_kernel(F, last); }, seed);
+		qemu::launch(r < 3 ? FL.n_chunks : (FL.n_chunks < 7u ? FL.n_chunks : 7u), QOI_FSCAN_THREADS, QOI_FVERIFY_SMEM, [&]() { qoifdec::fverify_kernel(F, last); }, seed);
 		if (getenv("QOI_EMU_FTRACE2")) {
 			for (uint32_t i = 0; i < D.n_images; i++) {
 				fprintf(stderr, "round %d image %u flagged:", r, i);
@@ -109,7 +109,7 @@ static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned se
 	if (getenv("QOI_EMU_FSTATS"))
 		for (uint32_t i = 0; i < D.n_images; i++)
 			fprintf(stderr, "image %u: %u live segments, fall-back from segment %u after %d rounds\n", i, F.f.n_live[i], qoifdec::stream_first_bad(F, i), rounds);
-	qemu::launch(FL.n_chunks, QOI_FSCAN_THREADS, 0, [&]() { qoifdec::ffinal_kernel(F); }, seed);
+	qemu::launch(FL.n_chunks, QOI_FSCAN_THREADS, QOI_FMETA_SMEM, [&]() { qoifdec::ffinal_kernel(F); }, seed);
 	qemu::launch(D.n_images, 32, QOI_FFALL_SMEM, [&]() { qoifdec::ffall_kernel(F); }, seed);
 	qemu::launch((g.n_tiles * 64u + 127u) / 128u, 128, 0, [&]() { qoifdec::fcompose_kernel(F, g.n_tiles, D.tile_img); }, seed);
 	QoiDecParams I = D;
