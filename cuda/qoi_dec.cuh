@@ -46,7 +46,54 @@ __device__ __forceinline__ uint32_t add_bytes(uint32_t a, uint32_t b) {
 }
 
 #define QOI_DEC_RING_WORDS 16 /* two 32-byte chunks per lane */
-#define QOI_DEC_SMEM_WORDS (64 + QOI_DEC_RING_WORDS)
+#define QOI_DEC_LUT_BYTES 4096 /* 256 x uint4: what an op's first byte says, see op_lut_entry() */
+#define QOI_DEC_SMEM_BYTES(BLOCK) (QOI_DEC_LUT_BYTES + (64 + QOI_DEC_RING_WORDS) * (BLOCK) * 4)
+
+/*
+ * Everything an op's first byte determines (qoi.h:547-575), tabulated once per block: the decoders are bound by the ALU
+ * pipe (profiles/r2_enc_v3: 70 % of its peak, 64 ALU instructions per pixel when the fields are picked apart with shifts
+ * and masks), the LSU pipe has room, and one 16-byte shared-memory load replaces ~30 of them.
+ *   x  r,b delta in 16-bit fields: r | b << 16 (DIFF: field - 2; LUMA: vg - 8, the nibbles of the second byte are added)
+ *   y  byte 0: g delta (DIFF: field - 2; LUMA: vg), byte 1: op length in bytes, byte 2: pixels of a RUN op AFTER its first
+ *   z  0x000F000F for LUMA (the second byte's nibbles count), else 0
+ *   w  bits the new colour takes straight from the four bytes behind the tag: RGB 0x00FFFFFF, RGBA 0xFFFFFFFF, else 0
+ * A relative op is then  r,b: (px & 0x00FF00FF) + x + nibbles,  g: ((px >> 8) & 0x00FF00FF) + g delta  (16-bit fields: no
+ * carry crosses a channel, the low byte of each field is the sum mod 256, qoi.h:563-571) and one PRMT picks the four low
+ * bytes; RUN and INDEX have zero deltas (INDEX takes index[] instead, selected afterwards).
+ */
+__device__ __forceinline__ uint4 op_lut_entry(uint32_t tag) {
+	uint4 e = make_uint4(0u, 0u, 0u, 0u);
+	const uint32_t top = tag >> 6;
+	uint32_t len = 1u, run = 0u, dg = 0u;
+	if (tag == 0xFEu) { len = 4u; e.w = 0x00FFFFFFu; }
+	else if (tag == 0xFFu) { len = 5u; e.w = 0xFFFFFFFFu; }
+	else if (top == 1u) { /* QOI_OP_DIFF, qoi.h:561-565 */
+		const uint32_t dr = (((tag >> 4) & 3u) - 2u) & 0xFFu, db = ((tag & 3u) - 2u) & 0xFFu;
+		dg = (((tag >> 2) & 3u) - 2u) & 0xFFu;
+		e.x = dr | (db << 16);
+	} else if (top == 2u) { /* QOI_OP_LUMA, qoi.h:566-572 */
+		const uint32_t vg = (tag & 0x3Fu) - 32u;
+		const uint32_t rb = (vg - 8u) & 0xFFu;
+		dg = vg & 0xFFu;
+		e.x = rb | (rb << 16);
+		e.z = 0x000F000Fu;
+		len = 2u;
+	} else if (top == 3u) { /* QOI_OP_RUN, qoi.h:573-575: run + 1 pixels */
+		run = tag & 0x3Fu;
+	}
+	e.y = dg | (len << 8) | (run << 16);
+	return e;
+}
+
+/* the new colour of the op `tag` with the four bytes `pay` behind it, index[tag & 63] = idxv, colour before = px */
+__device__ __forceinline__ uint32_t op_colour(uint32_t tag, uint32_t pay, uint4 L, uint32_t idxv, uint32_t px) {
+	const uint32_t nib = ((((pay & 0xFFu) * 0x00100001u) >> 4) & L.z); /* LUMA: dr_dg at bits 0..3, db_dg at bits 16..19 */
+	const uint32_t E = __byte_perm(px, 0u, 0x4240u) + L.x + nib;       /* r, b in 16-bit fields */
+	const uint32_t O = __byte_perm(px, 0u, 0x4341u) + __dp4a(L.y, 0x00000001u, 0u); /* g, a */
+	uint32_t npx = __byte_perm(E, O, 0x6240u);                          /* low bytes of the four fields */
+	npx = (pay & L.w) | (npx & ~L.w);                                   /* RGB keeps alpha, RGBA replaces all (qoi.h:547-557) */
+	return tag < 0x40u ? idxv : npx;                                    /* QOI_OP_INDEX, qoi.h:558-560 */
+}
 
 struct Reader {
 	uint64_t buf;       /* the next `avail` stream bytes, lowest byte first */
@@ -77,10 +124,13 @@ __device__ __forceinline__ void load_chunk(Reader &rd) {
 	rd.gp += 2;
 }
 
-template <int OUT_CH, int BLOCK, bool UNI, bool PRE>
+template <int OUT_CH, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P) {
 	QOI_DYNAMIC_SMEM(smem);
-	uint32_t *tab = (uint32_t *)smem + threadIdx.x;  /* tab[slot * BLOCK] */
+	uint4 *lut = (uint4 *)smem;
+	for (uint32_t k = threadIdx.x; k < 256u; k += BLOCK) lut[k] = op_lut_entry(k);
+	__syncthreads(); /* before any lane leaves */
+	uint32_t *tab = (uint32_t *)(smem + QOI_DEC_LUT_BYTES) + threadIdx.x;  /* tab[slot * BLOCK] */
 	uint32_t *ring = tab + 64 * BLOCK;               /* ring[word * BLOCK] */
 	const uint32_t job_id = blockIdx.x * BLOCK + threadIdx.x;
 	if (job_id >= P.n_jobs) return;
@@ -153,31 +203,20 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 		rd.buf = 0;
 		rd.avail = 0;
 	}
-	/* next 4 stream bytes from the ring; when a ring half has been used up, park the in-flight chunk there and fetch the next */
-	/* PRE (experimental, needs UNI; off by default, not yet measured): the ring word is read one call ahead, so that the
-	   shared-memory latency is off the parse chain.  The word after the current one is always in the ring: the chunk
-	   behind the reader's is parked by the refill() of the trip in which the reader entered its chunk. */
-	uint32_t ahead = 0;
+	/* next 4 stream bytes from the ring */
 	auto next_word = [&]() -> uint32_t {
-		const uint32_t w = PRE ? ahead : ring[(rd.wi & (QOI_DEC_RING_WORDS - 1)) * BLOCK];
+		const uint32_t w = ring[(rd.wi & (QOI_DEC_RING_WORDS - 1)) * BLOCK];
 		rd.wi++;
-		if (PRE) ahead = ring[(rd.wi & (QOI_DEC_RING_WORDS - 1)) * BLOCK];
-		if (!UNI && (rd.wi & 7u) == 0u) { /* lane-driven refill: the half just read is free */
-			uint32_t *r = ring + ((rd.wi - 8u) & (QOI_DEC_RING_WORDS - 1)) * BLOCK;
-			r[0 * BLOCK] = rd.pa.x; r[1 * BLOCK] = rd.pa.y; r[2 * BLOCK] = rd.pa.z; r[3 * BLOCK] = rd.pa.w;
-			r[4 * BLOCK] = rd.pb.x; r[5 * BLOCK] = rd.pb.y; r[6 * BLOCK] = rd.pb.z; r[7 * BLOCK] = rd.pb.w;
-			load_chunk(rd);
-		}
 		return w;
 	};
-	/* Warp-uniform refill (UNI): called once per loop trip (at most 4 pixels = 20 stream bytes) by all lanes together.
+	/* Warp-uniform refill: called once per loop trip (at most 4 pixels = 20 stream bytes) by all lanes together.
 	   Chunk `filled` is parked in registers; it goes into ring half (filled & 1) as soon as the reader has left chunk
 	   filled - 2, and the next chunk is put in flight.  Doing this at the same instruction for all lanes matters: the
 	   scoreboard tracks the parked registers per warp, so with lane-driven refills every lane's refill waited for the
 	   load another lane had just issued (37 % of the decoder's stall samples in round 1). */
 	uint32_t filled = 2;
 	auto refill = [&]() {
-		if (UNI && (rd.wi >> 3) + 1u >= filled) {
+		if ((rd.wi >> 3) + 1u >= filled) {
 			uint32_t *r = ring + ((filled & 1u) * 8u) * BLOCK;
 			r[0 * BLOCK] = rd.pa.x; r[1 * BLOCK] = rd.pa.y; r[2 * BLOCK] = rd.pa.z; r[3 * BLOCK] = rd.pa.w;
 			r[4 * BLOCK] = rd.pb.x; r[5 * BLOCK] = rd.pb.y; r[6 * BLOCK] = rd.pb.z; r[7 * BLOCK] = rd.pb.w;
@@ -185,18 +224,32 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 			load_chunk(rd);
 		}
 	};
+#ifndef QOI_DEC_READER
+#define QOI_DEC_READER 1
+#endif
+#if QOI_DEC_READER == 2
+	/* two-word window: w0 holds the op's first byte at byte offset bo (0..3), w1 the four bytes behind w0 -- an op's five bytes */
+	uint32_t bo = (uint32_t)((uintptr_t)(s + p0) & 3u);
+	uint32_t w0 = next_word(), w1 = next_word();
+#else
 	{ /* prime the window with the word that holds byte p0 */
-		if (PRE) ahead = ring[(rd.wi & (QOI_DEC_RING_WORDS - 1)) * BLOCK];
 		const uint32_t mis = (uint32_t)((uintptr_t)(s + p0) & 3u);
 		rd.buf = (uint64_t)(next_word() >> (8u * mis));
 		rd.avail = 4u - mis;
 	}
+#endif
 	uint32_t run = 0;
 
 	/* one pixel: qoi.h:541-578.  Lanes of a warp sit in different op types all the time, so the op itself is
 	   evaluated branch-free (every candidate result is computed, selects pick one); only the refill branches. */
 	auto step = [&]() -> uint32_t {
 		const bool parse = (run == 0u) && (rd.p < stop);
+#if QOI_DEC_READER == 2
+		const uint32_t sh = bo * 8u;
+		const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = w1 >> sh;
+		const uint32_t tag = lo & 0xFFu;
+		const uint32_t pay = __funnelshift_r(lo, hi, 8u); /* the four bytes after the tag */
+#else
 		if (parse && rd.avail < 5u) { /* an op needs at most 5 bytes */
 			rd.buf |= (uint64_t)next_word() << (8u * rd.avail);
 			rd.avail += 4u;
@@ -207,27 +260,30 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 		}
 		const uint32_t tag = (uint32_t)rd.buf & 0xFFu;
 		const uint32_t pay = (uint32_t)(rd.buf >> 8); /* the four bytes after the tag */
-		const uint32_t top = tag >> 6;
-		const bool is_rgb = tag == 0xFEu, is_rgba = tag == 0xFFu; /* qoi.h:547-557 are tested before the 2-bit tags */
-		const uint32_t idxv = tab[(tag & 63u) * BLOCK];           /* qoi.h:558-560 */
-		/* qoi.h:561-565: each channel += field - 2, wrapping (LUT 0,1,2,3 -> -2,-1,0,+1) */
-		const uint32_t sel = ((tag >> 4) & 3u) | (((tag >> 2) & 3u) << 4) | ((tag & 3u) << 8) | 0x4000u;
-		const uint32_t dadd = __byte_perm(0x0100FFFEu, 0u, sel);
-		/* qoi.h:566-572 */
-		const uint32_t vg = (tag & 0x3Fu) + 224u; /* -32 mod 256 */
-		const uint32_t rb = vg + 248u;            /* vg - 8 */
-		const uint32_t ladd = ((rb + ((pay >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((rb + (pay & 0xFu)) & 0xFFu) << 16);
-		const uint32_t rel = add_bytes(px, top == 1u ? dadd : ladd);
-		uint32_t npx = top == 0u ? idxv : rel;
-		npx = top == 3u ? px : npx;                                            /* RUN keeps the colour (qoi.h:573-575) */
-		npx = is_rgb ? ((px & 0xFF000000u) | (pay & 0x00FFFFFFu)) : npx;
-		npx = is_rgba ? pay : npx;
-		const uint32_t len = is_rgba ? 5u : (is_rgb ? 4u : (top == 2u ? 2u : 1u));
-		const uint32_t nrun = (top == 3u && tag < 0xFEu) ? (tag & 0x3Fu) : 0u;
+#endif
+		const uint4 L = lut[tag];
+		const uint32_t idxv = tab[(tag & 63u) * BLOCK]; /* qoi.h:558-560 */
+		const uint32_t npx = op_colour(tag, pay, L, idxv, px);
+		const uint32_t len = __dp4a(L.y, 0x00000100u, 0u);
+		const uint32_t nrun = __dp4a(L.y, 0x00010000u, 0u);
 		if (parse) {
 			px = npx;
+#if QOI_DEC_READER == 2
+			bo += len;
+			if (bo >= 4u) {
+				w0 = w1;
+				w1 = next_word();
+				bo -= 4u;
+				if (bo >= 4u) { /* a five-byte op that started at offset 3 */
+					w0 = w1;
+					w1 = next_word();
+					bo -= 4u;
+				}
+			}
+#else
 			rd.buf >>= 8u * len;
 			rd.avail -= len;
+#endif
 			rd.p += (int32_t)len;
 			tab[qoi_slot(px) * BLOCK] = px; /* qoi.h:577 */
 			run = nrun;

@@ -671,6 +671,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 					const bool known = lower != 0u || e.y != 0u;
 					hb = __ballot_sync(QOI_FULL_MASK, nonrun && known && (lower ? pv : e.x) == v); /* qoi.h:432 */
 					ub = __ballot_sync(QOI_FULL_MASK, nonrun && !known);
+					__syncwarp(); /* every lane has read the table (the votes above need each lane's e, but only this orders memory: racecheck) */
 					if (nonrun && (m & gt) == 0u) wtab[h] = make_uint2(v, 1u); /* qoi.h:436: the row's last pixel of its slot */
 					last_nr = (int32_t)(il - lane + 31u - (uint32_t)__clz((int)nr));
 				}

@@ -45,11 +45,18 @@ using namespace qoidev;
 #define QOI_FCHUNK 64   /* segments per scan chunk */
 #define QOI_FDEC_THREADS 64
 #define QOI_FSCAN_THREADS 96 /* 64 slot threads + the colour thread (thread 64); a multiple of 32 */
-#define QOI_FDEC_SMEM ((64 + 16 + QOI_DEC_RING_WORDS) * QOI_FDEC_THREADS * 4) /* per lane: index[64], 64 flag bytes, stream ring */
+#define QOI_FSTATE_THREADS 128 /* state rounds: the op table (qoidec::op_lut_entry, 4 KB) is shared by more lanes */
+#define QOI_FDEC_SMEM (QOI_DEC_LUT_BYTES + (64 + 16 + QOI_DEC_RING_WORDS) * QOI_FSTATE_THREADS * 4) /* op table; per lane: index[64], 64 flag bytes, stream ring */
 #define QOI_FFALL_SMEM ((64 + QOI_FSEG_BYTES / 4 + 8) * 4) /* index[], one staged segment */
 
 /* flag[] bits (fverify_kernel) */
-#define QOI_FCONT_LIST 4096u /* a round with at most this many listed segments lets the walks continue into the next segment */
+#define QOI_FCONT_LIST 4096u /* a round with at most this many listed segments lets the walks continue into the next segment ... */
+#ifndef QOI_FCONT_SHIFT
+#define QOI_FCONT_SHIFT 5    /* ... or at most n_segs >> this many: the limit has to grow with the batch.  (A fixed 4096 was right for
+                                32 x 4096^2 and a cliff for anything larger: 32 x 8192^2 and 1024 x 1080p kept lists of a few
+                                thousand segments per round, never continued, ran out of rounds and fell back to the sequential
+                                walk -- 2.1 s and 142 ms, profiles/r2_state/bench_other_configs.txt.) */
+#endif
 #define QOI_FCONT_MAX 48u    /* ... this many segments at most */
 #define QOI_FF_DEP 1u  /* the guess disagrees with the scanned state on something the segment depended on */
 #define QOI_FF_TRUST 4u /* the segment's last walk started from a guess that held on everything it depended on: what it derived from
@@ -381,8 +388,8 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fzero_kernel(const QoiFParam
 
 /* ------------------------------------------------------------------ 2. state round: one lane per segment, one trip per OP */
 /* index[] in shared memory [slot][thread] like qoi_decode_kernel; stream bytes through the same chunked reader. */
-__device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, uint32_t *tab, uint32_t *flg, uint32_t *ring) {
-	constexpr int B = QOI_FDEC_THREADS;
+__device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, const uint4 *lut, uint32_t *tab, uint32_t *flg, uint32_t *ring) {
+	constexpr int B = QOI_FSTATE_THREADS;
 	const uint32_t img = seg_image(P, g);
 	uint32_t j = g - P.f.seg_base[img];
 	const uint32_t live = P.f.n_live[img];
@@ -398,7 +405,8 @@ __device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, uin
 	   guess on what that segment depended on, it takes the next segment over (new guess = the state it holds) and goes on.
 	   claim[] keeps two walks of one round off the same segment. */
 	const uint32_t claim_tag = (P.epoch << 8) | (P.round + 1u);
-	const bool cont = P.round >= 2u && P.f.n_list[P.round] <= QOI_FCONT_LIST;
+	const uint32_t cont_limit = (P.n_segs >> QOI_FCONT_SHIFT) > QOI_FCONT_LIST ? (P.n_segs >> QOI_FCONT_SHIFT) : QOI_FCONT_LIST;
+	const bool cont = P.round >= 2u && P.f.n_list[P.round] <= cont_limit;
 	if (cont && atomicExch(&P.f.claim[g], claim_tag) == claim_tag) return; /* a walk that started earlier got here first */
 
 	uint32_t px = P.f.g_px[g];
@@ -528,19 +536,11 @@ __device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, uin
 		const uint32_t top = tag >> 6, t6 = tag & 63u;
 		const bool is_rgb = tag == 0xFEu, is_rgba = tag == 0xFFu;   /* qoi.h:547-557 are tested before the 2-bit tags */
 		const bool is_idx = top == 0u;
+		const uint4 L = lut[tag];                                    /* what the first byte says (qoidec::op_lut_entry) */
 		const uint32_t idxv = tab[t6 * B];                           /* qoi.h:558-560 */
-		const uint32_t sel = ((tag >> 4) & 3u) | (((tag >> 2) & 3u) << 4) | ((tag & 3u) << 8) | 0x4000u;
-		const uint32_t dadd = __byte_perm(0x0100FFFEu, 0u, sel);     /* qoi.h:561-565 */
-		const uint32_t vg = t6 + 224u;
-		const uint32_t rb = vg + 248u;
-		const uint32_t ladd = ((rb + ((pay >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((rb + (pay & 0xFu)) & 0xFFu) << 16); /* qoi.h:566-572 */
-		const uint32_t rel = add_bytes(px, top == 1u ? dadd : ladd);
-		uint32_t npx = is_idx ? idxv : rel;
-		npx = top == 3u ? px : npx;                                  /* RUN keeps the colour (qoi.h:573-575) */
-		npx = is_rgb ? ((px & 0xFF000000u) | (pay & 0x00FFFFFFu)) : npx;
-		npx = is_rgba ? pay : npx;
-		const uint32_t len = is_rgba ? 5u : (is_rgb ? 4u : (top == 2u ? 2u : 1u));
-		const uint32_t npix = (top == 3u && tag < 0xFEu) ? t6 + 1u : 1u; /* a RUN op yields run + 1 pixels (qoi.h:541-543,573-575) */
+		const uint32_t npx = qoidec::op_colour(tag, pay, L, idxv, px); /* qoi.h:547-575 */
+		const uint32_t len = __dp4a(L.y, 0x00000100u, 0u);
+		const uint32_t npix = __dp4a(L.y, 0x00010000u, 0u) + 1u;     /* a RUN op yields run + 1 pixels (qoi.h:541-543,573-575) */
 		/* where the new colour comes from */
 		uint8_t *fb_t = flag_byte(t6);
 		const uint32_t fbv = *fb_t;
@@ -618,14 +618,17 @@ __device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, uin
 
 /* round 0: lane k takes segment k; later rounds: the k-th entry of the list the last fverify_kernel left (late rounds are
    launched with a small grid and stride over it) */
-__global__ void __launch_bounds__(QOI_FDEC_THREADS) fstate_kernel(const QoiFParams P) {
+__global__ void __launch_bounds__(QOI_FSTATE_THREADS) fstate_kernel(const QoiFParams P) {
 	QOI_DYNAMIC_SMEM(smem);
-	constexpr int B = QOI_FDEC_THREADS;
-	uint32_t *tab = (uint32_t *)smem + threadIdx.x; /* tab[slot * B] */
+	constexpr int B = QOI_FSTATE_THREADS;
+	uint4 *lut = (uint4 *)smem;
+	for (uint32_t k = threadIdx.x; k < 256u; k += B) lut[k] = qoidec::op_lut_entry(k);
+	__syncthreads();
+	uint32_t *tab = (uint32_t *)(smem + QOI_DEC_LUT_BYTES) + threadIdx.x; /* tab[slot * B] */
 	uint32_t *flg = tab + 64 * B;                   /* flg[word * B]: one byte per slot */
 	uint32_t *ring = flg + 16 * B;                  /* ring[word * B] */
 	const uint32_t n = P.round == 0u ? P.n_segs : P.f.n_list[P.round];
-	for (uint32_t k = blockIdx.x * B + threadIdx.x; k < n; k += gridDim.x * B) fstate_walk(P, P.round == 0u ? k : P.f.list[k], tab, flg, ring);
+	for (uint32_t k = blockIdx.x * B + threadIdx.x; k < n; k += gridDim.x * B) fstate_walk(P, P.round == 0u ? k : P.f.list[k], lut, tab, flg, ring);
 }
 
 /* ------------------------------------------------------------------ 3. last-writer scan over the segments of every stream */

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -117,7 +118,7 @@ static int enc_occupancy(qoi_gpu_ctx *ctx, int *out) {
 template <int OUT_CH, int BLOCK>
 static void launch_decode(const QoiDecParams &D, cudaStream_t s) {
 	const uint32_t grid = (D.n_jobs + BLOCK - 1) / BLOCK;
-	qoidec::qoi_decode_kernel<OUT_CH, BLOCK, true, false><<<grid, BLOCK, QOI_DEC_SMEM_WORDS * BLOCK * 4, s>>>(D);
+	qoidec::qoi_decode_kernel<OUT_CH, BLOCK><<<grid, BLOCK, QOI_DEC_SMEM_BYTES(BLOCK), s>>>(D);
 }
 
 extern "C" {
@@ -316,8 +317,9 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 		for (int r = 0; r < QOI_FROUNDS; r++) {
 			F.round = (uint32_t)r;
 			const int last = r + 1 == QOI_FROUNDS;
-			const uint32_t g_seg = r < 3 ? gs : (gs < small ? gs : small), g_chk = r < 3 ? F.n_chunks : (F.n_chunks < small ? F.n_chunks : small);
-			qoifdec::fstate_kernel<<<g_seg, QOI_FDEC_THREADS, QOI_FDEC_SMEM, s>>>(F);
+			const uint32_t gst = (F.n_segs + QOI_FSTATE_THREADS - 1) / QOI_FSTATE_THREADS;
+			const uint32_t g_st = r < 3 ? gst : (gst < small ? gst : small), g_chk = r < 3 ? F.n_chunks : (F.n_chunks < small ? F.n_chunks : small);
+			qoifdec::fstate_kernel<<<g_st, QOI_FSTATE_THREADS, QOI_FDEC_SMEM, s>>>(F);
 			qoifdec::fscan_a_kernel<<<g_chk, QOI_FSCAN_THREADS, QOI_FMETA_SMEM, s>>>(F);
 			qoifdec::fscan_b_kernel<<<F.n_images, QOI_FSCANB_THREADS, QOI_FSCANB_SMEM, s>>>(F);
 			qoifdec::fverify_kernel<<<g_chk, QOI_FSCAN_THREADS, QOI_FVERIFY_SMEM, s>>>(F, last);
@@ -354,6 +356,18 @@ int qoi_gpu_decode(qoi_gpu_plan *p, const void *d_streams, const int32_t *d_lens
 	}
 	g_launches++;
 	CK(ctx, cudaGetLastError());
+	return QOI_GPU_OK;
+}
+
+int qoi_gpu_plan_fstats(qoi_gpu_plan *p, uint32_t out[128]) {
+	if (!p || !out || !p->d_fstate) return QOI_GPU_E_ARG;
+	qoi_gpu_ctx *ctx = p->ctx;
+	DeviceGuard guard(ctx->device);
+	qoifdec::QoiFState f;
+	qoifdec::fstate_bind(f, p->d_fstate, p->flayout.off);
+	CK(ctx, cudaDeviceSynchronize());
+	CK(ctx, cudaMemcpy(out, f.n_list, 64 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	CK(ctx, cudaMemcpy(out + 64, f.active, 64 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	return QOI_GPU_OK;
 }
 
@@ -638,7 +652,8 @@ void qoi_gpu_host_free(void *p) {
  * cudaMemcpy from pageable memory is staged by the driver with one host thread at 5-10 GB/s -- 22 ms for a 4096^2 RGBA
  * image and its stream, against ~2 ms of PCIe time.  Here a few persistent host threads copy 4 MiB chunks between the
  * caller's buffer and a pinned staging buffer while the DMA of the chunks already copied is in flight; the result buffer's
- * first-touch page faults are spread over the same threads.  QOI_GPU_HOST_THREADS (1..64) sets their number (default 8).
+ * first-touch page faults are spread over the same threads.  QOI_GPU_HOST_THREADS (1..64) sets their number (default 16).
+ * QOI_GPU_TRACE=1 prints the stage times of every qoi_encode / qoi_decode call to stderr.
  */
 class HostPool {
 public:
@@ -669,7 +684,7 @@ public:
 
 private:
 	HostPool() {
-		int want = 8;
+		int want = 16;
 		const char *e = getenv("QOI_GPU_HOST_THREADS");
 		if (e && atoi(e) >= 1 && atoi(e) <= 64) want = atoi(e);
 		const unsigned hw = std::thread::hardware_concurrency();
@@ -715,6 +730,51 @@ private:
 	uint64_t gen_ = 0;
 	bool stop_ = false;
 };
+
+
+/* stage timing of the reference entry points (QOI_GPU_TRACE=1): where a single-image call spends its time */
+struct Trace {
+	bool on;
+	std::chrono::steady_clock::time_point t0, last;
+	char line[512];
+	int n = 0;
+	explicit Trace(const char *what) {
+		static const bool enabled = getenv("QOI_GPU_TRACE") != nullptr;
+		on = enabled;
+		if (on) {
+			t0 = last = std::chrono::steady_clock::now();
+			n = snprintf(line, sizeof line, "qoi_gpu trace %s:", what);
+		}
+	}
+	void mark(const char *stage) {
+		if (!on) return;
+		const auto now = std::chrono::steady_clock::now();
+		n += snprintf(line + n, sizeof line - (size_t)n, " %s %.3f", stage, std::chrono::duration<double, std::milli>(now - last).count());
+		if (n > (int)sizeof line - 64) n = (int)sizeof line - 64;
+		last = now;
+	}
+	~Trace() {
+		if (on) fprintf(stderr, "%s | total %.3f ms\n", line, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+	}
+};
+
+/* First touch of a freshly malloc'ed result buffer: the kernel zeroes every page on its first write (a 64 MiB image: 16 k
+   faults, ~8 ms on one thread).  The pool touches the pages in parallel while the DMA and the kernels of the same call run,
+   so that the copy-out afterwards lands in mapped pages.  Only whole pages inside [p, p + bytes) are written (one zero byte
+   each; the buffer's content is undefined at this point anyway). */
+static void pretouch(void *p, size_t bytes) {
+	const size_t page = 4096;
+	const uintptr_t lo = ((uintptr_t)p + page - 1) & ~(uintptr_t)(page - 1), hi = ((uintptr_t)p + bytes) & ~(uintptr_t)(page - 1);
+	if (hi <= lo) return;
+	const size_t npages = (hi - lo) / page;
+	const size_t per = 512; /* 2 MiB per task */
+	const int tasks = (int)((npages + per - 1) / per);
+	HostPool::get().run(tasks, [&](int i) {
+		volatile unsigned char *q = (volatile unsigned char *)(lo + (size_t)i * per * page);
+		const size_t n = (size_t)i * per + per <= npages ? per : npages - (size_t)i * per;
+		for (size_t k = 0; k < n; k++) q[k * page] = 0;
+	});
+}
 
 #define QOI_STAGE_CHUNK ((size_t)4 << 20)
 #define QOI_STAGE_MAX_CHUNKS 64
@@ -784,6 +844,7 @@ static bool g_ctx_failed = false;
 static qoi_gpu_plan *g_plan = nullptr;
 static qoi_desc g_plan_desc;
 static int g_plan_dec_ch = 0;
+static size_t g_last_len = 0; /* bytes of the last stream qoi_encode produced with g_plan */
 
 static qoi_gpu_ctx *global_ctx() {
 	if (!g_ctx && !g_ctx_failed) {
@@ -805,6 +866,7 @@ static qoi_gpu_plan *global_plan(qoi_gpu_ctx *ctx, const qoi_desc *d, int dec_ch
 	const uint64_t zero = 0;
 	if (qoi_gpu_plan_create(ctx, &g_plan, 1, d, &zero, &zero, &zero, dec_ch) != QOI_GPU_OK) return nullptr;
 	memset(&g_plan_desc, 0, sizeof g_plan_desc);
+	g_last_len = 0;
 	g_plan_desc = *d;
 	g_plan_dec_ch = dec_ch;
 	return g_plan;
@@ -825,19 +887,31 @@ void *qoi_encode(const void *data, const qoi_desc *desc, int *out_len) {
 	qoi_gpu_plan *p = global_plan(ctx, &d, d.channels);
 	if (!p || plan_mirrors(p)) return NULL;
 	cudaStream_t s = ctx->stream;
+	Trace tr("qoi_encode");
 	const size_t nbytes = (size_t)d.width * d.height * d.channels;
-	if (stage_reserve(ctx, qoi_max_stream(pod) > nbytes ? qoi_max_stream(pod) : nbytes)) return NULL;
-	if (staged_h2d(ctx, p->d_pixels, data, nbytes, 0, s)) return NULL;
-	if (qoi_gpu_encode(p, p->d_pixels, p->d_streams, p->d_lens, s) != QOI_GPU_OK) return NULL;
-	if (cudaMemcpyAsync(p->h_lens_pinned, p->d_lens, sizeof(int32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess) return NULL;
-	if (cudaStreamSynchronize(s) != cudaSuccess) return NULL;
-	const int len = p->h_lens_pinned[0];
-	void *out = malloc((size_t)len);
+	const size_t max_size = qoi_max_stream(pod);
+	if (stage_reserve(ctx, max_size > nbytes ? max_size : nbytes)) return NULL;
+	/* the reference allocates the worst case as well (qoi.h:374-379); untouched pages cost nothing */
+	void *out = malloc(max_size);
 	if (!out) return NULL;
-	if (staged_d2h(ctx, out, p->d_streams, (size_t)len, 0, s)) { /* the staging buffer is free again: the kernel has consumed the pixels */
+	tr.mark("setup");
+	bool ok = staged_h2d(ctx, p->d_pixels, data, nbytes, 0, s) == QOI_GPU_OK;
+	tr.mark("h2d_copy");
+	ok = ok && qoi_gpu_encode(p, p->d_pixels, p->d_streams, p->d_lens, s) == QOI_GPU_OK &&
+	     cudaMemcpyAsync(p->h_lens_pinned, p->d_lens, sizeof(int32_t), cudaMemcpyDeviceToHost, s) == cudaSuccess;
+	/* while the DMA and the kernel run: map the pages the stream will most likely need (as long as the last one of this plan) */
+	if (ok) pretouch(out, g_last_len && g_last_len < max_size ? g_last_len : nbytes / 2 + nbytes / 4);
+	tr.mark("pretouch");
+	ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+	tr.mark("sync");
+	const int len = ok ? p->h_lens_pinned[0] : 0;
+	ok = ok && staged_d2h(ctx, out, p->d_streams, (size_t)len, 0, s) == QOI_GPU_OK; /* the staging buffer is free again: the kernel has consumed the pixels */
+	tr.mark("d2h_copy");
+	if (!ok) {
 		free(out);
 		return NULL;
 	}
+	g_last_len = (size_t)len;
 	*out_len = len; /* written only on success, qoi.h:484 */
 	return out;
 }
@@ -871,13 +945,20 @@ void *qoi_decode(const void *data, int size, qoi_desc *desc, int channels) {
 	if (up > cap) { up = cap; eff_size = (int)cap; }
 	const size_t out_bytes = (size_t)d.width * d.height * (size_t)out_ch;
 	if (stage_reserve(ctx, out_bytes > up ? out_bytes : up)) return NULL;
+	Trace tr("qoi_decode");
 	void *out = malloc(out_bytes);
 	if (!out) return NULL;
 	p->h_lens_pinned[0] = eff_size;
-	bool ok = staged_h2d(ctx, p->d_streams, data, up, 0, s) == QOI_GPU_OK &&
-	          cudaMemcpyAsync(p->d_lens, p->h_lens_pinned, sizeof(int32_t), cudaMemcpyHostToDevice, s) == cudaSuccess &&
-	          qoi_gpu_decode(p, p->d_streams, p->d_lens, p->d_decoded, 0, nullptr, s) == QOI_GPU_OK &&
-	          staged_d2h(ctx, out, p->d_decoded, out_bytes, 0, s) == QOI_GPU_OK; /* stream-ordered behind the kernels, which have read the staged stream */
+	tr.mark("setup");
+	bool ok = staged_h2d(ctx, p->d_streams, data, up, 0, s) == QOI_GPU_OK;
+	tr.mark("h2d_copy");
+	ok = ok && cudaMemcpyAsync(p->d_lens, p->h_lens_pinned, sizeof(int32_t), cudaMemcpyHostToDevice, s) == cudaSuccess &&
+	     qoi_gpu_decode(p, p->d_streams, p->d_lens, p->d_decoded, 0, nullptr, s) == QOI_GPU_OK;
+	tr.mark("launch");
+	if (ok) pretouch(out, out_bytes); /* while the DMA and the kernels run */
+	tr.mark("pretouch");
+	ok = ok && staged_d2h(ctx, out, p->d_decoded, out_bytes, 0, s) == QOI_GPU_OK; /* stream-ordered behind the kernels, which have read the staged stream */
+	tr.mark("d2h_copy");
 	if (!ok) {
 		free(out);
 		return NULL;

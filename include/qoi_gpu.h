@@ -124,6 +124,12 @@ int qoi_gpu_index_import(qoi_gpu_plan *plan, const void *h_index, size_t bytes, 
 void *qoi_gpu_host_alloc(size_t bytes);
 void qoi_gpu_host_free(void *p);
 
+/* Diagnostics of the last qoi_gpu_decode(use_index = 0) on the plan: out[r] = segments state round r walked (r < 60;
+   out[0] = 0 stands for "all"), out[64 + r] = streams round r's scan still had to look at (0: settled, later launches return
+   at once).  A non-zero count in the last round means streams were finished by the sequential fall-back.  Synchronises the
+   device.  QOI_GPU_E_ARG if the plan has never decoded a foreign stream. */
+int qoi_gpu_plan_fstats(qoi_gpu_plan *plan, uint32_t out[128]);
+
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t qoi_gpu_launch_count(void);
 

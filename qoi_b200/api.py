@@ -76,6 +76,8 @@ def lib():
     L.qoi_gpu_host_alloc.argtypes = [C.c_size_t]
     L.qoi_gpu_host_free.argtypes = [vp]
     L.qoi_gpu_launch_count.restype = C.c_uint64
+    L.qoi_gpu_plan_fstats.restype = C.c_int
+    L.qoi_gpu_plan_fstats.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.qoi_gpu_index_bytes.restype = C.c_size_t
     L.qoi_gpu_index_bytes.argtypes = [vp]
     L.qoi_gpu_index_export.restype = C.c_int

@@ -85,5 +85,18 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """A second build of the same library with other compile-time settings, for A/B timing with bench/enc_ab in one GPU
+    session (qoi_b200/libqoi_gpu_<name>.so; never loaded by the package)."""
+    out = os.path.join(ROOT, "qoi_b200", f"libqoi_gpu_{name}.so")
+    cmd = [find_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out, os.path.join(ROOT, "cuda", "qoi_gpu.cu")]
+    if os.path.exists("/usr/bin/g++"):
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))

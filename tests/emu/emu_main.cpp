@@ -29,10 +29,6 @@ void *ora_encode(const void *data, const QoiDescPOD *desc, int *out_len);
 void *ora_decode(const void *data, int size, QoiDescPOD *desc, int channels);
 }
 
-/* which stream-reader refill the decoders use (QOI_EMU_REFILL=lane selects the lane-driven one) */
-static bool emu_ahead() { const char *e = getenv("QOI_EMU_REFILL"); return e && !strcmp(e, "ahead"); }
-static bool emu_uni() { const char *e = getenv("QOI_EMU_REFILL"); return !(e && !strcmp(e, "lane")); }
-
 static std::vector<unsigned char> read_file(const char *path) {
 	FILE *f = fopen(path, "rb");
 	if (!f) { fprintf(stderr, "cannot open %s\n", path); exit(2); }
@@ -53,9 +49,9 @@ static void run_encode(const QoiEncParams &P, unsigned grid, unsigned seed) {
 
 static void run_decode(const QoiDecParams &P, unsigned seed) {
 	unsigned grid = (P.n_jobs + QOI_DEC_THREADS - 1) / QOI_DEC_THREADS;
-	size_t smem = QOI_DEC_SMEM_WORDS * QOI_DEC_THREADS * 4;
-	if (P.out_channels == 4) qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_ahead()) qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, true, true>(P); else if (emu_uni()) qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, true, false>(P); else qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS, false, false>(P); }, seed);
-	else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { if (emu_ahead()) qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true, true>(P); else if (emu_uni()) qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, true, false>(P); else qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS, false, false>(P); }, seed);
+	size_t smem = QOI_DEC_SMEM_BYTES(QOI_DEC_THREADS);
+	if (P.out_channels == 4) qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { qoidec::qoi_decode_kernel<4, QOI_DEC_THREADS>(P); }, seed);
+	else qemu::launch(grid, QOI_DEC_THREADS, smem, [&]() { qoidec::qoi_decode_kernel<3, QOI_DEC_THREADS>(P); }, seed);
 }
 
 /* the foreign-stream pipeline exactly as qoi_gpu_decode enqueues it: build the restart index, then the tile decoder */
@@ -89,7 +85,8 @@ static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned se
 	for (int r = 0; r < rounds; r++) {
 		F.round = (uint32_t)r;
 		const int last = r + 1 == rounds;
-		qemu::launch(r < 3 ? gs : (gs < 5u ? gs : 5u), QOI_FDEC_THREADS, QOI_FDEC_SMEM, [&]() { qoifdec::fstate_kernel(F); }, seed);
+		const unsigned gst = (FL.n_segs + QOI_FSTATE_THREADS - 1) / QOI_FSTATE_THREADS;
+		qemu::launch(r < 3 ? gst : (gst < 5u ? gst : 5u), QOI_FSTATE_THREADS, QOI_FDEC_SMEM, [&]() { qoifdec::fstate_kernel(F); }, seed);
 		qemu::launch(r < 3 ? FL.n_chunks : (FL.n_chunks < 7u ? FL.n_chunks : 7u), QOI_FSCAN_THREADS, QOI_FMETA_SMEM, [&]() { qoifdec::fscan_a_kernel(F); }, seed);
 		qemu::launch(D.n_images, QOI_FSCANB_THREADS, QOI_FSCANB_SMEM, [&]() { qoifdec::fscan_b_kernel(F); }, seed);
 		qemu::launch(r < 3 ? FL.n_chunks : (FL.n_chunks < 7u ? FL.n_chunks : 7u), QOI_FSCAN_THREADS, QOI_FVERIFY_SMEM, [&]() { qoifdec::fverify_kernel(F, last); }, seed);

@@ -27,12 +27,9 @@ def run_enc(emu, img, w, h, ch, n, grid, seed, mis, extra_variants=()):
     with tempfile.NamedTemporaryFile(suffix=".raw") as f:
         f.write(np.ascontiguousarray(img, dtype=np.uint8).tobytes())
         f.flush()
-        # the foreign decoder's verify pass with one range per stream / with several, and the decoders' stream reader
-        # with warp-uniform / lane-driven refill
-        for cfg in ({"QOI_EMU_FVER_MIN_RANGE": "1024", "QOI_EMU_REFILL": "uniform"}, {"QOI_EMU_FVER_MIN_RANGE": "3", "QOI_EMU_REFILL": "lane"}):
-            r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
-                               capture_output=True, text=True, timeout=300, env=dict(os.environ, **cfg))
-            assert r.returncode == 0 and r.stdout.startswith("PASS"), str(cfg) + ": " + r.stdout + r.stderr[-2000:]
+        r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and r.stdout.startswith("PASS"), r.stdout + r.stderr[-2000:]
         for extra in extra_variants:
             r = subprocess.run([emu, "enc", str(w), str(h), str(ch), str(n), str(grid), str(seed), str(mis), f.name],
                                capture_output=True, text=True, timeout=300, env=dict(os.environ, QOI_EMU_SKIP_FOREIGN="1", **extra))
@@ -81,13 +78,11 @@ def test_emulated_foreign_decode(emu, cpu):
     # header + end marker only, and a single op byte: no live segment / one tiny segment (qoi.h:540-587 fills with the colour)
     small += [q.header(30, 30, 4) + ops + q.END_MARK for ops in (b"", b"\x37", b"\xfe\x05\x06\x07", b"\xc5")]
     run(small, 30, 30, {})
-    run(small, 30, 30, {"QOI_EMU_REFILL": "lane"})
     # streams of many segments (random op soup: the speculation rarely holds, the fix-up does the work), with
     # different numbers of speculative rounds (both parities of the pass-buffered state)
     big = [q.foreign_stream(rng, 40000, 4, w=200, h=200, truncate=(i == 2)) for i in range(4)]
     for rounds in ("1", "2", "3", "6", "9"):
         run(big, 200, 200, {"QOI_EMU_FROUNDS": rounds})
-        run(big, 200, 200, {"QOI_EMU_FROUNDS": rounds, "QOI_EMU_FVER_MIN_RANGE": "2"})  # several verify ranges per stream
 
 
 def test_emulated_many_tiles(emu, cpu):

@@ -30,6 +30,7 @@ typedef void (*fn_plan_destroy)(qoi_gpu_plan *);
 typedef int (*fn_encode)(qoi_gpu_plan *, const void *, void *, int32_t *, void *);
 typedef int (*fn_decode)(qoi_gpu_plan *, const void *, const int32_t *, void *, int, int32_t *, void *);
 typedef const char *(*fn_err)(const qoi_gpu_ctx *);
+typedef int (*fn_fstats)(qoi_gpu_plan *, uint32_t *);
 typedef void *(*fn_cpu_encode)(const void *, const qoi_desc *, int *);
 
 int main(int argc, char **argv) {
@@ -43,6 +44,7 @@ int main(int argc, char **argv) {
 	fn_encode encode = (fn_encode)dlsym(lib, "qoi_gpu_encode");
 	fn_decode decode = (fn_decode)dlsym(lib, "qoi_gpu_decode");
 	fn_err last_error = (fn_err)dlsym(lib, "qoi_gpu_last_error");
+	fn_fstats fstats = (fn_fstats)dlsym(lib, "qoi_gpu_plan_fstats");
 	if (!ctx_create || !plan_create || !encode || !decode) { printf("missing symbols\n"); return 2; }
 	/* CPU checker (test infrastructure): the compiled reference if it travelled with the repository, else the restatement */
 	fn_cpu_encode cpu_encode = NULL;
@@ -138,6 +140,14 @@ int main(int argc, char **argv) {
 		printf("dist %d  e=%.3f B/px  encode %7.3f ms (%6.1f Gpx/s, %5.0f GB/s)  indexed decode %7.3f ms (%6.1f Gpx/s, %5.0f GB/s)", dist, bytes / px,
 		       enc / runs, px / (enc / runs * 1e6), (px * CH + bytes) / (enc / runs * 1e6), dec / runs, px / (dec / runs * 1e6), (px * 4 + bytes) / (dec / runs * 1e6));
 		if (with_foreign) printf("  foreign decode %8.3f ms (%6.1f Gpx/s) %s", fdec / 2, px / (fdec / 2 * 1e6), rtf ? "ok" : "*** MISMATCH ***");
+		if (with_foreign && fstats && getenv("ENC_AB_FSTATS")) { /* segments walked / streams unsettled per state round */
+			uint32_t fs[128];
+			if (fstats(plan, fs) == QOI_GPU_OK) {
+				printf("\n    rounds:");
+				for (int r = 1; r < 20 && (fs[r] || fs[64 + r - 1]); r++) printf(" %d:%u/%u", r, fs[r], fs[64 + r - 1]);
+				printf("  (segments walked / streams unsettled before)\n   ");
+			}
+		}
 		printf("  streams %s  round trip %s\n", cpu_encode ? (same ? "== checker" : "*** DIFFER ***") : "(unchecked)", rt ? "ok" : "*** MISMATCH ***");
 		fflush(stdout);
 		bad += !same || !rt || !rtf;
