@@ -154,6 +154,42 @@ __device__ __forceinline__ int32_t op_len(uint32_t tag) { return (tag == 0xFEu) 
 __device__ __forceinline__ uint32_t op_px(uint32_t tag) { return ((tag >> 6) == 3u && tag < 0xFEu) ? (tag & 0x3Fu) + 1u : 1u; }
 
 /* ------------------------------------------------------------------ 1a. parse: one thread per segment */
+/* The walk needs one byte per op.  Lanes of a warp sit in 32 different segments, so a byte load per op costs 32 sector
+   look-ups per warp instruction and the kernel was bound by exactly that (1.2 ms for 32 x 4096^2 photographs, more than a
+   third of a state round).  The bytes come in 16-byte pieces instead: one aligned load serves ~5 ops; the piece is kept
+   in four registers and the byte picked with selects.  Only whole 16-byte pieces inside the stream's own bytes are loaded
+   that way; the ragged ends are read byte by byte. */
+struct ByteWin {
+	const uint8_t *s;     /* stream */
+	uintptr_t lo16, hi16; /* [lo16, hi16): the 16-byte aligned pieces that lie inside [s, s + size) */
+	int32_t size;
+	int32_t base;         /* stream offset of q's first byte; INT_MIN/2: nothing loaded */
+	uint4 q;
+	__device__ __forceinline__ void init(const uint8_t *stream, int32_t sz) {
+		s = stream;
+		size = sz;
+		lo16 = ((uintptr_t)stream + 15u) & ~(uintptr_t)15;
+		hi16 = ((uintptr_t)stream + (uintptr_t)sz) & ~(uintptr_t)15;
+		base = -0x40000000;
+		q = make_uint4(0u, 0u, 0u, 0u);
+	}
+	__device__ __forceinline__ uint32_t get(int32_t p) {
+		uint32_t d = (uint32_t)(p - base);
+		if (d >= 16u) {
+			const uintptr_t a = ((uintptr_t)s + (uintptr_t)p) & ~(uintptr_t)15;
+			if (a >= lo16 && a + 16u <= hi16) {
+				q = __ldg((const uint4 *)a);
+				base = (int32_t)(a - (uintptr_t)s);
+				d = (uint32_t)(p - base);
+			} else {
+				return s[p]; /* a ragged end of the stream */
+			}
+		}
+		const uint32_t w = (d & 8u) ? ((d & 4u) ? q.w : q.z) : ((d & 4u) ? q.y : q.x);
+		return (w >> (8u * (d & 3u))) & 0xFFu;
+	}
+};
+
 __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFParams P) {
 	const uint32_t g = blockIdx.x * QOI_FDEC_THREADS + threadIdx.x;
 	if (g >= P.n_segs) return;
@@ -166,6 +202,8 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 	const int32_t begin = QOI_HEADER_BYTES + (int32_t)(g - P.f.seg_base[img]) * QOI_FSEG_BYTES;
 	if (begin >= stop) return; /* beyond the stream */
 	const int32_t end = begin + QOI_FSEG_BYTES < stop ? begin + QOI_FSEG_BYTES : stop;
+	ByteWin bw;
+	bw.init(s, size);
 	/* Walk 0 is made in full.  Walks 1..4 usually fall onto an op boundary of walk 0 within a few ops and are the same
 	   from there on: walk 0 remembers its op starts inside the first 128 bytes (bitmap), the others stop as soon as they
 	   land on one and take walk 0's tail.  A walk that stays out of phase (e.g. a stream of two-byte ops entered at
@@ -181,7 +219,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 			if (off < 64u) seen_lo |= 1ull << off;
 			else seen_hi |= 1ull << (off - 64u);
 		}
-		const uint32_t tag = s[p0];
+		const uint32_t tag = bw.get(p0);
 		p0 += op_len(tag);
 		total0 += op_px(tag);
 	}
@@ -197,7 +235,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 		while (p < near) {
 			const uint32_t off = (uint32_t)(p - begin);
 			if (((off < 64u ? seen_lo : seen_hi) >> (off & 63u)) & 1ull) { merged = true; break; }
-			const uint32_t tag = s[p];
+			const uint32_t tag = bw.get(p);
 			p += op_len(tag);
 			lastk = cnt;
 			cnt += op_px(tag);
@@ -207,7 +245,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 			/* pixels walk 0 produced before the meeting point */
 			uint32_t before = 0;
 			for (int32_t q = begin; q < p;) {
-				const uint32_t tag = s[q];
+				const uint32_t tag = bw.get(q);
 				q += op_len(tag);
 				before += op_px(tag);
 			}
@@ -216,7 +254,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 			ex = exit0;
 		} else {
 			while (p < end) {
-				const uint32_t tag = s[p];
+				const uint32_t tag = bw.get(p);
 				p += op_len(tag);
 				lastk = cnt;
 				cnt += op_px(tag);
@@ -386,6 +424,14 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fzero_kernel(const QoiFParam
 	for (int k = 0; k < 16; k++) t[k] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+/* proven prefix of a stream, as a global segment index: what the check of the round before established */
+__device__ __forceinline__ uint32_t stream_proven_end(const QoiFParams &P, uint32_t img) {
+	const uint32_t base = P.f.seg_base[img];
+	if (P.round == 0u) return base + 1u;
+	const uint32_t key = P.f.first_bad[((P.round - 1u) & 1u) * P.n_images + img]; /* 2 * segment + (not a disagreement) */
+	const uint32_t pe = (key >> 1) + (key & 1u);
+	return base + (pe > 1u ? pe : 1u);
+}
 /* ------------------------------------------------------------------ 2. state round: one lane per segment, one trip per OP */
 /* index[] in shared memory [slot][thread] like qoi_decode_kernel; stream bytes through the same chunked reader. */
 __device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, const uint4 *lut, uint32_t *tab, uint32_t *flg, uint32_t *ring) {
@@ -406,7 +452,12 @@ __device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, con
 	   claim[] keeps two walks of one round off the same segment. */
 	const uint32_t claim_tag = (P.epoch << 8) | (P.round + 1u);
 	const uint32_t cont_limit = (P.n_segs >> QOI_FCONT_SHIFT) > QOI_FCONT_LIST ? (P.n_segs >> QOI_FCONT_SHIFT) : QOI_FCONT_LIST;
-	const bool cont = P.round >= 2u && P.f.n_list[P.round] <= cont_limit;
+	/* Only the walk of the stream's FIRST UNPROVEN segment continues: everything before it is proven, so its guess is the exact
+	   state and what it arrives with is exact too.  Any other walk may have started from a wrong guess; letting it overwrite
+	   its successors' guesses dragged wrong state down the stream 48 segments per round with the correction 48 segments
+	   behind -- an opaque stream (every segment depends on the incoming alpha) that once guessed alpha 0 never settled:
+	   6 of 512 1080p photographs and every 8192^2 one went to the sequential fall-back (profiles/r2_state). */
+	const bool cont = P.round >= 2u && P.f.n_list[P.round] <= cont_limit && g == stream_proven_end(P, img);
 	if (cont && atomicExch(&P.f.claim[g], claim_tag) == claim_tag) return; /* a walk that started earlier got here first */
 
 	uint32_t px = P.f.g_px[g];
@@ -648,14 +699,6 @@ __device__ __forceinline__ bool stream_settled(const QoiFParams &P, uint32_t img
    prefix of its stream (g < gpe; segment 0 always does). */
 __device__ __forceinline__ bool seg_trusted(const QoiFParams &P, uint32_t g, uint32_t gpe) {
 	return (P.f.flag[g] & QOI_FF_TRUST) != 0u && (!(P.f.dep[g] & 64u) || g < gpe);
-}
-/* proven prefix of a stream, as a global segment index: what the check of the round before established */
-__device__ __forceinline__ uint32_t stream_proven_end(const QoiFParams &P, uint32_t img) {
-	const uint32_t base = P.f.seg_base[img];
-	if (P.round == 0u) return base + 1u;
-	const uint32_t key = P.f.first_bad[((P.round - 1u) & 1u) * P.n_images + img]; /* 2 * segment + (not a disagreement) */
-	const uint32_t pe = (key >> 1) + (key & 1u);
-	return base + (pe > 1u ? pe : 1u);
 }
 /* The colour is not "last writer": a segment of DIFF / LUMA / RUN ops adds a known delta to whatever colour enters it.  So
    the colour's scan composes maps  colour -> (r,g,b: constant c | + d) x (alpha: constant c | unchanged), one per segment.

@@ -368,6 +368,18 @@ int qoi_gpu_plan_fstats(qoi_gpu_plan *p, uint32_t out[128]) {
 	CK(ctx, cudaDeviceSynchronize());
 	CK(ctx, cudaMemcpy(out, f.n_list, 64 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	CK(ctx, cudaMemcpy(out + 64, f.active, 64 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	/* out[120..127]: the first images whose stream went to the fall-back (1 + image index; 0: none) */
+	const size_t n = p->geom.metas.size();
+	std::vector<uint32_t> planes(4 * n), fbad(2 * n), live(n);
+	CK(ctx, cudaMemcpy(planes.data(), f.bad_cnt, 4 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	CK(ctx, cudaMemcpy(fbad.data(), f.first_bad, 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	CK(ctx, cudaMemcpy(live.data(), f.n_live, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	int k = 0;
+	for (int i = 120; i < 128; i++) out[i] = 0;
+	for (size_t i = 0; i < n && k < 8; i++) {
+		const uint32_t par = planes[3 * n + i] & 1u;
+		if ((fbad[par * n + i] >> 1) < live[i]) out[120 + k++] = (uint32_t)i + 1u;
+	}
 	return QOI_GPU_OK;
 }
 

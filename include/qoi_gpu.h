@@ -126,8 +126,8 @@ void qoi_gpu_host_free(void *p);
 
 /* Diagnostics of the last qoi_gpu_decode(use_index = 0) on the plan: out[r] = segments state round r walked (r < 60;
    out[0] = 0 stands for "all"), out[64 + r] = streams round r's scan still had to look at (0: settled, later launches return
-   at once).  A non-zero count in the last round means streams were finished by the sequential fall-back.  Synchronises the
-   device.  QOI_GPU_E_ARG if the plan has never decoded a foreign stream. */
+   at once); out[120..127] = 1 + index of the first images whose streams were finished by the sequential fall-back (0: none).
+   Synchronises the device.  QOI_GPU_E_ARG if the plan has never decoded a foreign stream. */
 int qoi_gpu_plan_fstats(qoi_gpu_plan *plan, uint32_t out[128]);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */

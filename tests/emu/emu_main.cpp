@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -95,6 +96,27 @@ static void run_foreign(const QoiDecParams &D, const QoiPlanGeom &g, unsigned se
 				fprintf(stderr, "round %d image %u flagged:", r, i);
 				for (uint32_t j = 0; j < F.f.n_live[i]; j++) if (F.f.flag[F.f.seg_base[i] + j]) fprintf(stderr, " %u(%u)", j, F.f.flag[F.f.seg_base[i] + j]);
 				fprintf(stderr, "\n");
+			}
+		}
+		if (getenv("QOI_EMU_FTRACE3")) { /* the segments listed for the next round, with what they depend on */
+			const uint32_t nl = F.f.n_list[r + 1];
+			fprintf(stderr, "round %d: first_bad key %u, %u listed:", r, F.f.first_bad[((uint32_t)r & 1u) * D.n_images], nl);
+			std::vector<uint32_t> l(F.f.list, F.f.list + nl);
+			std::sort(l.begin(), l.end());
+			for (uint32_t k = 0; k < nl && k < 24; k++)
+				fprintf(stderr, " %u[dep %x rbw %llx gpx %08x]", l[k], F.f.dep[l[k]], (unsigned long long)F.f.rbw[l[k]], F.f.g_px[l[k]]);
+			fprintf(stderr, "\n");
+		}
+		if (getenv("QOI_EMU_FWIN")) { /* "lo-hi": every segment of the window after this round's check */
+			unsigned lo = 0, hi = 0;
+			sscanf(getenv("QOI_EMU_FWIN"), "%u-%u", &lo, &hi);
+			const uint32_t nl = F.f.n_list[r + 1];
+			fprintf(stderr, "round %d window:\n", r);
+			for (uint32_t g = lo; g <= hi && g < F.f.n_live[0]; g++) {
+				bool listed = false;
+				for (uint32_t k = 0; k < nl; k++) listed = listed || F.f.list[k] == g;
+				fprintf(stderr, "  seg %u%s flag %u dep %02x rbw %016llx taint %016llx wr %016llx g_px %08x o_px %08x claim %x\n", g, listed ? " LISTED" : "", F.f.flag[g], F.f.dep[g],
+				        (unsigned long long)F.f.rbw[g], (unsigned long long)F.f.o_taint[g], (unsigned long long)F.f.o_wr[g], F.f.g_px[g], F.f.o_px[g], F.f.claim[g]);
 			}
 		}
 		if (getenv("QOI_EMU_FTRACE")) {

@@ -88,7 +88,7 @@ int main(int argc, char **argv) {
 	int bad = 0;
 	for (int a = 6; a < argc; a++) {
 		const int dist = atoi(argv[a]);
-		qoi_synth_batch(h_pix, img, n, (uint32_t)W, (uint32_t)H, CH, dist, 0);
+		qoi_synth_batch(h_pix, img, n, (uint32_t)W, (uint32_t)H, CH, dist, getenv("ENC_AB_FIRST") ? (uint32_t)atoi(getenv("ENC_AB_FIRST")) : 0u);
 		CK(cudaMemcpy(d_pix, h_pix, img * n, cudaMemcpyHostToDevice));
 		CK(cudaMemset(d_str, 0xEE, slot * n));
 		float enc = 0, dec = 0, fdec = 0;
@@ -145,7 +145,9 @@ int main(int argc, char **argv) {
 			if (fstats(plan, fs) == QOI_GPU_OK) {
 				printf("\n    rounds:");
 				for (int r = 1; r < 20 && (fs[r] || fs[64 + r - 1]); r++) printf(" %d:%u/%u", r, fs[r], fs[64 + r - 1]);
-				printf("  (segments walked / streams unsettled before)\n   ");
+				printf("  (segments walked / streams unsettled before)");
+				for (int q = 120; q < 128; q++) if (fs[q]) printf("%s%u", q == 120 ? "  fall-back for images " : ",", fs[q] - 1u);
+				printf("\n   ");
 			}
 		}
 		printf("  streams %s  round trip %s\n", cpu_encode ? (same ? "== checker" : "*** DIFFER ***") : "(unchecked)", rt ? "ok" : "*** MISMATCH ***");
