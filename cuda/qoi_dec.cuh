@@ -50,9 +50,13 @@ __device__ __forceinline__ uint32_t add_bytes(uint32_t a, uint32_t b) {
 #define QOI_DEC_SMEM_BYTES(BLOCK) (QOI_DEC_LUT_BYTES + (64 + QOI_DEC_RING_WORDS) * (BLOCK) * 4)
 
 /*
- * Everything an op's first byte determines (qoi.h:547-575), tabulated once per block: the decoders are bound by the ALU
- * pipe (profiles/r2_enc_v3: 70 % of its peak, 64 ALU instructions per pixel when the fields are picked apart with shifts
- * and masks), the LSU pipe has room, and one 16-byte shared-memory load replaces ~30 of them.
+ * Everything an op's first byte determines (qoi.h:547-575), tabulated once per block: with the fields picked apart by
+ * shifts and masks the decoders spent 64 ALU instructions per pixel (ALU pipe at 70 % of its peak, profiles/r2_enc_v2);
+ * one 16-byte shared-memory load replaces ~30 of them.  What bounds the kernel after that is the L1 data pipe (one pass
+ * per distinct line a warp-wide access touches; shared-memory passes count too): 70 % busy whatever the instruction count
+ * (profiles/r2_dec_lut, r2_dec_256).  A 4-byte table with arithmetic masks, and a software-pipelined op fetch, were
+ * measured and are not here: they move the load between the ALU and that pipe without shortening the kernel; 256-bit
+ * global accesses (ld_nc_256 / st_256) halve the passes and took the photo batch from 2.45 to 1.94 ms.
  *   x  r,b delta in 16-bit fields: r | b << 16 (DIFF: field - 2; LUMA: vg - 8, the nibbles of the second byte are added)
  *   y  byte 0: g delta (DIFF: field - 2; LUMA: vg), byte 1: op length in bytes, byte 2: pixels of a RUN op AFTER its first
  *   z  0x000F000F for LUMA (the second byte's nibbles count), else 0
@@ -109,8 +113,7 @@ struct Reader {
 __device__ __forceinline__ void load_chunk(Reader &rd) {
 	const uintptr_t a = (uintptr_t)rd.gp;
 	if (a >= rd.lo && a + 32 <= rd.hi) {
-		rd.pa = __ldg(rd.gp);
-		rd.pb = __ldg(rd.gp + 1);
+		ld_nc_256(rd.gp, rd.pa, rd.pb);
 	} else {
 		uint32_t w[8];
 #pragma unroll
@@ -224,55 +227,7 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 			load_chunk(rd);
 		}
 	};
-#ifndef QOI_DEC_READER
-#define QOI_DEC_READER 3
-#endif
 	uint32_t run = 0;
-#if QOI_DEC_READER == 3
-	/* Software-pipelined op fetch.  The op table made the decoder 26 % shorter and not a microsecond faster
-	   (profiles/r2_dec_lut: short_scoreboard 3.75 cycles per issue): with the op's length coming out of the table, every step
-	   was a chain  stream word -> tag -> table load -> length -> next tag.  Here the length comes from the tag by arithmetic, the
-	   stream words are read three ahead (w0 holds the op's first byte at byte offset bo, w1 the rest of its five bytes, w2
-	   is on its way), and the NEXT op's tag, payload and table entry are fetched while the current op's colour is computed:
-	   no shared-memory load sits between an op and its successor any more. */
-	uint32_t bo = (uint32_t)((uintptr_t)(s + p0) & 3u);
-	uint32_t w0 = next_word(), w1 = next_word(), w2 = next_word();
-	uint32_t tag, pay;
-	uint4 L;
-	auto fetch_op = [&]() {
-		const uint32_t sh = bo * 8u;
-		const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = w1 >> sh;
-		tag = lo & 0xFFu;
-		pay = __funnelshift_r(lo, hi, 8u); /* the four bytes after the tag */
-		L = lut[tag];
-	};
-	fetch_op();
-	auto step = [&]() -> uint32_t {
-		const bool parse = (run == 0u) && (rd.p < stop);
-		if (parse) {
-			const uint32_t ctag = tag, cpay = pay;
-			const uint4 cL = L;
-			const uint32_t idxv = tab[(ctag & 63u) * BLOCK]; /* qoi.h:558-560 */
-			/* op length from the tag alone: 0xFE 4, 0xFF 5, 10xxxxxx 2, else 1 */
-			const uint32_t len = ctag >= 0xFEu ? ctag - 0xFAu : ((ctag & 0xC0u) == 0x80u ? 2u : 1u);
-			bo += len;
-			rd.p += (int32_t)len;
-			while (bo >= 4u) { /* at most twice (a five-byte op that started at offset 3) */
-				w0 = w1;
-				w1 = w2;
-				w2 = next_word();
-				bo -= 4u;
-			}
-			fetch_op(); /* the next op, whenever it will be parsed */
-			px = op_colour(ctag, cpay, cL, idxv, px);
-			tab[qoi_slot(px) * BLOCK] = px; /* qoi.h:577 */
-			run = __dp4a(cL.y, 0x00010000u, 0u);
-		} else if (run > 0u) {
-			run--;
-		}
-		return px;
-	};
-#else
 	{ /* prime the window with the word that holds byte p0 */
 		const uint32_t mis = (uint32_t)((uintptr_t)(s + p0) & 3u);
 		rd.buf = (uint64_t)(next_word() >> (8u * mis));
@@ -310,7 +265,6 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 		}
 		return px;
 	};
-#endif
 
 	uint8_t *obase = P.out + m.dec_off;
 	uint32_t i = px_begin;
@@ -320,6 +274,21 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 		while (i < px_end && (!vec_ok || (i & 3u))) { /* head (or everything, if the destination is not 16-byte aligned) */
 			o32[i] = step();
 			i++;
+			refill();
+		}
+		if (vec_ok && i + 4 <= px_end && (((uintptr_t)(o32 + i)) & 31u)) { /* up to a 32-byte boundary */
+			const uint32_t a = step(), b = step(), c = step(), d = step();
+			*(uint4 *)(o32 + i) = make_uint4(a, b, c, d);
+			i += 4;
+			refill();
+		}
+		while (i + 8 <= px_end) { /* eight pixels = one 32-byte sector per lane and store */
+			uint4 lo, hi;
+			lo.x = step(); lo.y = step(); lo.z = step(); lo.w = step();
+			refill(); /* once per four pixels (<= 20 stream bytes): the ring holds two chunks */
+			hi.x = step(); hi.y = step(); hi.z = step(); hi.w = step();
+			st_256(o32 + i, lo, hi);
+			i += 8;
 			refill();
 		}
 		while (i + 4 <= px_end) {

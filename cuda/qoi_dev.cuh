@@ -97,6 +97,20 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
 __device__ __forceinline__ void st_stream_u4(uint4 *p, uint4 v) {
 	asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+/* 256-bit accesses (sm_100: LDG.E.256 / STG.E.256): one lane moves a whole 32-byte sector with one instruction.  The decoders'
+   lanes each stream their own segment and their own tile, so a warp-wide access touches 32 different lines whatever its width
+   -- and costs the L1 data pipe one pass per line: twice the width is half the passes (profiles/r2_dec_lut: that pipe, at 70 %,
+   is what bounds the decoder).  32-byte aligned addresses. */
+__device__ __forceinline__ void ld_nc_256(const void *p, uint4 &a, uint4 &b) {
+	asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+	             : "l"(p));
+}
+__device__ __forceinline__ void st_256(void *p, uint4 a, uint4 b) {
+	asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z),
+	             "r"(b.w)
+	             : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 /* wait until all committed bulk stores of this thread have finished READING shared memory */
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -215,6 +229,8 @@ static inline void tma_load_1d_hint(void *d, const void *s_, uint32_t n, uint64_
 static inline void tma_store_1d_hint(void *d, const void *s_, uint32_t n, uint64_t) { tma_store_1d(d, s_, n); }
 static inline uint4 ld_stream_u4(const uint4 *p) { return *p; }
 static inline void st_stream_u4(uint4 *p, uint4 v) { *p = v; }
+static inline void ld_nc_256(const void *p, uint4 &a, uint4 &b) { a = ((const uint4 *)p)[0]; b = ((const uint4 *)p)[1]; }
+static inline void st_256(void *p, uint4 a, uint4 b) { ((uint4 *)p)[0] = a; ((uint4 *)p)[1] = b; }
 static inline void tma_store_commit() {}
 static inline void tma_store_wait_read() {}
 static inline void tma_store_wait_all() {}

@@ -601,7 +601,7 @@ __device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, con
 		   does not hash to its own number is an initial zero -- which an encoder never refers to (only a hand-made stream
 		   does).  Almost certainly the guess is wrong there, and {0,0,0,0} would put alpha 0 into everything this segment
 		   derives from it: mark the walk, so that it is not trusted on a mere re-walk (seg_trusted). */
-		suspect = suspect || (is_idx && !own_slot && qoi_slot(idxv) != t6);
+		suspect = suspect || (is_idx && !own_slot && (qoi_slot(idxv) != t6 || idxv == 0u)); /* slot 0's zero hashes to 0: as much a guess as the others */
 		/* INDEX of a slot the segment filled itself: the stored colour's provenance (from the incoming colour -> still
 		   incoming colour + deltas; from a guessed slot -> D); of a guessed slot: D */
 		const uint32_t own_t = fbv & (F_TRGB | F_TA), own_c = (fbv & (F_CRGB | F_CA)) >> 2;
