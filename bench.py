@@ -303,16 +303,21 @@ def c_api_single_image(h_pix, args):
     sp = c_encode()                          # first calls build the cached plan and its scratch (untimed)
     libc.free(c_decode(sp))
     reps = 5
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    t_enc = t_dec = t_free = 0.0
+    q = None
+    for _ in range(reps):               # the calls and the caller's free() of their results are timed apart
+        t0 = time.perf_counter()
         libc.free(sp)
-        sp = c_encode()
-    t1 = time.perf_counter()
-    for _ in range(reps):
-        q = c_decode(sp)
-        if _ + 1 < reps:
+        if q:
             libc.free(q)
-    t2 = time.perf_counter()
+        t1 = time.perf_counter()
+        sp = c_encode()
+        t2 = time.perf_counter()
+        q = c_decode(sp)
+        t3 = time.perf_counter()
+        t_free += t1 - t0
+        t_enc += t2 - t1
+        t_dec += t3 - t2
     back = np.frombuffer(C.string_at(q, W * H * 4), dtype=np.uint8)
     libc.free(q)
     libc.free(sp)
@@ -324,10 +329,12 @@ def c_api_single_image(h_pix, args):
     l1 = np.zeros(1, dtype=np.int32)
     cpu_round_trip(eb1, db1, 1, one, 1, k1, l1, k1.size)
     te1, td1 = cpu_round_trip(eb1, db1, 1, one, 1, k1, l1, k1.size)
-    c_api = {"image": f"{W}x{H}x{CH} {DIST_NAMES[args.dist]}", "qoi_encode_ms": 1e3 * (t1 - t0) / reps,
-             "qoi_decode_ms": 1e3 * (t2 - t1) / reps, "cpu_kind": kind1, "cpu_qoi_encode_ms": 1e3 * te1,
-             "cpu_qoi_decode_ms": 1e3 * td1,
-             "note": "single calls of the reference API, host pointers in and out, copies and the any-stream decoder inside"}
+    c_api = {"image": f"{W}x{H}x{CH} {DIST_NAMES[args.dist]}", "qoi_encode_ms": 1e3 * t_enc / reps,
+             "qoi_decode_ms": 1e3 * t_dec / reps, "free_of_both_results_ms": 1e3 * t_free / reps,
+             "cpu_kind": kind1, "cpu_qoi_encode_ms": 1e3 * te1, "cpu_qoi_decode_ms": 1e3 * td1,
+             "note": "single calls of the reference API, host pointers in and out, copies and the any-stream decoder inside; the caller's "
+                     "free() of the two malloc'ed results (munmap of 64 + 80 MiB whose pages the library's pool threads touched) is timed apart; "
+                     "the CPU columns include malloc + free inside the call as qoibench.c:446-450,471-481 times them"}
     return c_api
 
 

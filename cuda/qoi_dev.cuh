@@ -106,6 +106,12 @@ __device__ __forceinline__ void ld_nc_256(const void *p, uint4 &a, uint4 &b) {
 	             : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
 	             : "l"(p));
 }
+__device__ __forceinline__ void ld_256(const void *p, uint4 &a, uint4 &b) {
+	asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+	             : "l"(p)
+	             : "memory");
+}
 __device__ __forceinline__ void st_256(void *p, uint4 a, uint4 b) {
 	asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z),
 	             "r"(b.w)
@@ -230,6 +236,7 @@ static inline void tma_store_1d_hint(void *d, const void *s_, uint32_t n, uint64
 static inline uint4 ld_stream_u4(const uint4 *p) { return *p; }
 static inline void st_stream_u4(uint4 *p, uint4 v) { *p = v; }
 static inline void ld_nc_256(const void *p, uint4 &a, uint4 &b) { a = ((const uint4 *)p)[0]; b = ((const uint4 *)p)[1]; }
+static inline void ld_256(const void *p, uint4 &a, uint4 &b) { a = ((const uint4 *)p)[0]; b = ((const uint4 *)p)[1]; }
 static inline void st_256(void *p, uint4 a, uint4 b) { ((uint4 *)p)[0] = a; ((uint4 *)p)[1] = b; }
 static inline void tma_store_commit() {}
 static inline void tma_store_wait_read() {}

@@ -154,42 +154,8 @@ __device__ __forceinline__ int32_t op_len(uint32_t tag) { return (tag == 0xFEu) 
 __device__ __forceinline__ uint32_t op_px(uint32_t tag) { return ((tag >> 6) == 3u && tag < 0xFEu) ? (tag & 0x3Fu) + 1u : 1u; }
 
 /* ------------------------------------------------------------------ 1a. parse: one thread per segment */
-/* The walk needs one byte per op.  Lanes of a warp sit in 32 different segments, so a byte load per op costs 32 sector
-   look-ups per warp instruction and the kernel was bound by exactly that (1.2 ms for 32 x 4096^2 photographs, more than a
-   third of a state round).  The bytes come in 16-byte pieces instead: one aligned load serves ~5 ops; the piece is kept
-   in four registers and the byte picked with selects.  Only whole 16-byte pieces inside the stream's own bytes are loaded
-   that way; the ragged ends are read byte by byte. */
-struct ByteWin {
-	const uint8_t *s;     /* stream */
-	uintptr_t lo16, hi16; /* [lo16, hi16): the 16-byte aligned pieces that lie inside [s, s + size) */
-	int32_t size;
-	int32_t base;         /* stream offset of q's first byte; INT_MIN/2: nothing loaded */
-	uint4 q;
-	__device__ __forceinline__ void init(const uint8_t *stream, int32_t sz) {
-		s = stream;
-		size = sz;
-		lo16 = ((uintptr_t)stream + 15u) & ~(uintptr_t)15;
-		hi16 = ((uintptr_t)stream + (uintptr_t)sz) & ~(uintptr_t)15;
-		base = -0x40000000;
-		q = make_uint4(0u, 0u, 0u, 0u);
-	}
-	__device__ __forceinline__ uint32_t get(int32_t p) {
-		uint32_t d = (uint32_t)(p - base);
-		if (d >= 16u) {
-			const uintptr_t a = ((uintptr_t)s + (uintptr_t)p) & ~(uintptr_t)15;
-			if (a >= lo16 && a + 16u <= hi16) {
-				q = __ldg((const uint4 *)a);
-				base = (int32_t)(a - (uintptr_t)s);
-				d = (uint32_t)(p - base);
-			} else {
-				return s[p]; /* a ragged end of the stream */
-			}
-		}
-		const uint32_t w = (d & 8u) ? ((d & 4u) ? q.w : q.z) : ((d & 4u) ? q.y : q.x);
-		return (w >> (8u * (d & 3u))) & 0xFFu;
-	}
-};
-
+/* (Reading the bytes as 16-byte pieces held in registers, the byte picked with selects, was measured: 1.80 ms instead of 1.22 ms
+   for 32 x 4096^2 photographs -- the selects cost more than the sector look-ups of plain byte loads, which mostly hit L1.) */
 __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFParams P) {
 	const uint32_t g = blockIdx.x * QOI_FDEC_THREADS + threadIdx.x;
 	if (g >= P.n_segs) return;
@@ -202,8 +168,6 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 	const int32_t begin = QOI_HEADER_BYTES + (int32_t)(g - P.f.seg_base[img]) * QOI_FSEG_BYTES;
 	if (begin >= stop) return; /* beyond the stream */
 	const int32_t end = begin + QOI_FSEG_BYTES < stop ? begin + QOI_FSEG_BYTES : stop;
-	ByteWin bw;
-	bw.init(s, size);
 	/* Walk 0 is made in full.  Walks 1..4 usually fall onto an op boundary of walk 0 within a few ops and are the same
 	   from there on: walk 0 remembers its op starts inside the first 128 bytes (bitmap), the others stop as soon as they
 	   land on one and take walk 0's tail.  A walk that stays out of phase (e.g. a stream of two-byte ops entered at
@@ -219,7 +183,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 			if (off < 64u) seen_lo |= 1ull << off;
 			else seen_hi |= 1ull << (off - 64u);
 		}
-		const uint32_t tag = bw.get(p0);
+		const uint32_t tag = s[p0];
 		p0 += op_len(tag);
 		total0 += op_px(tag);
 	}
@@ -235,7 +199,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 		while (p < near) {
 			const uint32_t off = (uint32_t)(p - begin);
 			if (((off < 64u ? seen_lo : seen_hi) >> (off & 63u)) & 1ull) { merged = true; break; }
-			const uint32_t tag = bw.get(p);
+			const uint32_t tag = s[p];
 			p += op_len(tag);
 			lastk = cnt;
 			cnt += op_px(tag);
@@ -245,7 +209,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 			/* pixels walk 0 produced before the meeting point */
 			uint32_t before = 0;
 			for (int32_t q = begin; q < p;) {
-				const uint32_t tag = bw.get(q);
+				const uint32_t tag = s[q];
 				q += op_len(tag);
 				before += op_px(tag);
 			}
@@ -254,7 +218,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 			ex = exit0;
 		} else {
 			while (p < end) {
-				const uint32_t tag = bw.get(p);
+				const uint32_t tag = s[p];
 				p += op_len(tag);
 				lastk = cnt;
 				cnt += op_px(tag);
@@ -419,9 +383,9 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fzero_kernel(const QoiFParam
 	if (g >= P.n_segs) return;
 	const uint32_t img = seg_image(P, g);
 	if (g - P.f.seg_base[img] >= P.f.n_live[img]) return;
-	uint4 *t = (uint4 *)(P.f.g_tab + (size_t)g * 64);
+	uint32_t *t = P.f.g_tab + (size_t)g * 64;
 #pragma unroll
-	for (int k = 0; k < 16; k++) t[k] = make_uint4(0u, 0u, 0u, 0u);
+	for (int k = 0; k < 8; k++) st_256(t + 8 * k, make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u));
 }
 
 /* proven prefix of a stream, as a global segment index: what the check of the round before established */
@@ -432,6 +396,29 @@ __device__ __forceinline__ uint32_t stream_proven_end(const QoiFParams &P, uint3
 	const uint32_t pe = (key >> 1) + (key & 1u);
 	return base + (pe > 1u ? pe : 1u);
 }
+/* a lane's index[] (shared memory, tab[slot * B]) <-> 64 consecutive words in global memory, eight slots per 256-bit access:
+   the lanes of a warp work on 32 different segments, so every access costs the L1 data pipe one pass per lane whatever its
+   width -- word by word, the 512 bytes a walk reads and leaves per segment were more passes than its ops */
+template <int B>
+__device__ __forceinline__ void tab_load_256(uint32_t *tab, const uint32_t *src) {
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		uint4 a, b;
+		ld_256(src + 8 * k, a, b);
+		uint32_t *t = tab + (8 * k) * B;
+		t[0 * B] = a.x; t[1 * B] = a.y; t[2 * B] = a.z; t[3 * B] = a.w;
+		t[4 * B] = b.x; t[5 * B] = b.y; t[6 * B] = b.z; t[7 * B] = b.w;
+	}
+}
+template <int B>
+__device__ __forceinline__ void tab_store_256(uint32_t *dst, const uint32_t *tab) {
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		const uint32_t *t = tab + (8 * k) * B;
+		st_256(dst + 8 * k, make_uint4(t[0 * B], t[1 * B], t[2 * B], t[3 * B]), make_uint4(t[4 * B], t[5 * B], t[6 * B], t[7 * B]));
+	}
+}
+
 /* ------------------------------------------------------------------ 2. state round: one lane per segment, one trip per OP */
 /* index[] in shared memory [slot][thread] like qoi_decode_kernel; stream bytes through the same chunked reader. */
 __device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, const uint4 *lut, uint32_t *tab, uint32_t *flg, uint32_t *ring) {
@@ -461,11 +448,7 @@ __device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, con
 	if (cont && atomicExch(&P.f.claim[g], claim_tag) == claim_tag) return; /* a walk that started earlier got here first */
 
 	uint32_t px = P.f.g_px[g];
-	{
-		const uint32_t *src = P.f.g_tab + (size_t)g * 64;
-#pragma unroll 8
-		for (int q = 0; q < 64; q++) tab[q * B] = src[q];
-	}
+	tab_load_256<B>(tab, P.f.g_tab + (size_t)g * 64);
 	uint64_t rbw;
 	/* What the current colour derives from, one bit each (cf), r,g,b and alpha separately (an RGB op replaces only r,g,b):
 	     T_*: from the guess at all (the colour that entered the segment, or a guessed index[] slot read before the segment
@@ -559,9 +542,10 @@ __device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, con
 		}
 		P.f.rs_seg[T] = g;
 		if (tb) { /* qoi_decode_kernel reads index[] of tile T from the record of tile T - 1; tile 0 starts from zeros */
-			uint4 *dst = (uint4 *)(P.st.ent + (size_t)(T - 1) * 64);
+			uint64_t *dst = P.st.ent + (size_t)(T - 1) * 64;
 #pragma unroll 4
-			for (int q = 0; q < 32; q++) dst[q] = make_uint4(1u, tab[(2 * q) * B], 1u, tab[(2 * q + 1) * B]); /* value << 32 | 1, two slots */
+			for (int q = 0; q < 16; q++) /* value << 32 | 1, four slots per store */
+				st_256(dst + 4 * q, make_uint4(1u, tab[(4 * q) * B], 1u, tab[(4 * q + 1) * B]), make_uint4(1u, tab[(4 * q + 2) * B], 1u, tab[(4 * q + 3) * B]));
 		}
 		tb += QOI_TILE_PX;
 	};
@@ -636,11 +620,7 @@ __device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, con
 	   guess; bits 4,5: ... as incoming colour + deltas only */
 	P.f.dep[g] = ((depacc & F_CRGB) ? 1u : 0u) | ((depacc & F_CA) ? 2u : 0u) | ((cf & F_TRGB) ? 4u : 0u) | ((cf & F_TA) ? 8u : 0u) |
 	             (((cf & (F_TRGB | F_DRGB)) == F_TRGB) ? 16u : 0u) | (((cf & (F_TA | F_DA)) == F_TA) ? 32u : 0u) | (suspect ? 64u : 0u);
-	{
-		uint32_t *dst = P.f.o_tab + (size_t)g * 64;
-#pragma unroll 8
-		for (int q = 0; q < 64; q++) dst[q] = tab[q * B];
-	}
+	tab_store_256<B>(P.f.o_tab + (size_t)g * 64, tab);
 	if (!cont || steps + 1u >= QOI_FCONT_MAX || j + 1u >= live) break;
 	{ /* does the next segment's last walk stand with the state this one arrives with? */
 		const uint32_t gn = g + 1u;
@@ -660,9 +640,7 @@ __device__ __forceinline__ void fstate_walk(const QoiFParams &P, uint32_t g, con
 		begin += QOI_FSEG_BYTES; /* the reader, pos and tb simply go on: this segment's first op is where the last one's ended */
 		end = begin + QOI_FSEG_BYTES < stop ? begin + QOI_FSEG_BYTES : stop;
 		P.f.g_px[g] = px;
-		uint32_t *dst = P.f.g_tab + (size_t)g * 64;
-#pragma unroll 8
-		for (int q = 0; q < 64; q++) dst[q] = tab[q * B];
+		tab_store_256<B>(P.f.g_tab + (size_t)g * 64, tab);
 	}
 	}
 }
