@@ -99,6 +99,27 @@ __device__ __forceinline__ uint32_t op_colour(uint32_t tag, uint32_t pay, uint4 
 	return tag < 0x40u ? idxv : npx;                                    /* QOI_OP_INDEX, qoi.h:558-560 */
 }
 
+#ifdef QOI_DEC_LUT64
+/* the same table in 8 bytes per op: the two masks are rebuilt on the FMA pipe from flag bytes that ride in the unused
+   bytes of x (byte 1: RGBA, byte 3: RGB or RGBA -- they add into the gaps between the 16-bit fields, which the final PRMT
+   drops) and of y (byte 3: LUMA) */
+__device__ __forceinline__ uint2 op_lut64_entry(uint32_t tag) {
+	const uint4 e = op_lut_entry(tag);
+	uint2 r;
+	r.x = e.x | (e.w == 0xFFFFFFFFu ? 0x00000100u : 0u) | (e.w ? 0x01000000u : 0u);
+	r.y = (e.y & 0x00FFFFFFu) | (e.z ? 0x01000000u : 0u);
+	return r;
+}
+__device__ __forceinline__ uint4 op_lut64_expand(uint2 e) {
+	uint4 L;
+	L.x = e.x;
+	L.y = e.y;
+	L.z = __dp4a(e.y, 0x01000000u, 0u) * 0x000F000Fu;
+	L.w = __dp4a(e.x, 0x01000000u, 0u) * 0x00FFFFFFu + __dp4a(e.x, 0x00000100u, 0u) * 0xFF000000u;
+	return L;
+}
+#endif
+
 struct Reader {
 	uint64_t buf;       /* the next `avail` stream bytes, lowest byte first */
 	uint32_t avail;
@@ -130,8 +151,13 @@ __device__ __forceinline__ void load_chunk(Reader &rd) {
 template <int OUT_CH, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P) {
 	QOI_DYNAMIC_SMEM(smem);
+#ifdef QOI_DEC_LUT64
+	uint2 *lut = (uint2 *)smem;
+	for (uint32_t k = threadIdx.x; k < 256u; k += BLOCK) lut[k] = op_lut64_entry(k);
+#else
 	uint4 *lut = (uint4 *)smem;
 	for (uint32_t k = threadIdx.x; k < 256u; k += BLOCK) lut[k] = op_lut_entry(k);
+#endif
 	__syncthreads(); /* before any lane leaves */
 	uint32_t *tab = (uint32_t *)(smem + QOI_DEC_LUT_BYTES) + threadIdx.x;  /* tab[slot * BLOCK] */
 	uint32_t *ring = tab + 64 * BLOCK;               /* ring[word * BLOCK] */
@@ -248,7 +274,11 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 		}
 		const uint32_t tag = (uint32_t)rd.buf & 0xFFu;
 		const uint32_t pay = (uint32_t)(rd.buf >> 8); /* the four bytes after the tag */
+#ifdef QOI_DEC_LUT64
+		const uint4 L = op_lut64_expand(lut[tag]);
+#else
 		const uint4 L = lut[tag];
+#endif
 		const uint32_t idxv = tab[(tag & 63u) * BLOCK]; /* qoi.h:558-560 */
 		const uint32_t npx = op_colour(tag, pay, L, idxv, px);
 		const uint32_t len = __dp4a(L.y, 0x00000100u, 0u);

@@ -9,7 +9,7 @@ QOI_LINEAR = 1
 TILE_PX = 2048
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# QOI_GPU_LIB selects another build of the same C ABI (experiments/build_exp.py writes libqoi_gpu_exp.so for A/B runs);
+# QOI_GPU_LIB selects another build of the same C ABI (qoi_b200.build.build_variant writes libqoi_gpu_<name>.so for A/B runs);
 # it is still a CUDA library with no CPU path, and bench.py records the override in its JSON line.
 _LIB_PATH = os.environ.get("QOI_GPU_LIB") or os.path.join(_HERE, "libqoi_gpu.so")
 _lib = None
