@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t add_bytes(uint32_t a, uint32_t b) {
  * shifts and masks the decoders spent 64 ALU instructions per pixel (ALU pipe at 70 % of its peak, profiles/r2_enc_v2);
  * one 16-byte shared-memory load replaces ~30 of them.  What bounds the kernel after that is the L1 data pipe (one pass
  * per distinct line a warp-wide access touches; shared-memory passes count too): 70 % busy whatever the instruction count
- * (profiles/r2_dec_lut, r2_dec_256).  A 4-byte table with arithmetic masks, and a software-pipelined op fetch, were
+ * (profiles/r2_dec_lut, r2_dec_256).  4- and 8-byte tables with rebuilt masks, and a software-pipelined op fetch, were
  * measured and are not here: they move the load between the ALU and that pipe without shortening the kernel; 256-bit
  * global accesses (ld_nc_256 / st_256) halve the passes and took the photo batch from 2.45 to 1.94 ms.
  *   x  r,b delta in 16-bit fields: r | b << 16 (DIFF: field - 2; LUMA: vg - 8, the nibbles of the second byte are added)
@@ -99,27 +99,6 @@ __device__ __forceinline__ uint32_t op_colour(uint32_t tag, uint32_t pay, uint4 
 	return tag < 0x40u ? idxv : npx;                                    /* QOI_OP_INDEX, qoi.h:558-560 */
 }
 
-#ifdef QOI_DEC_LUT64
-/* the same table in 8 bytes per op: the two masks are rebuilt on the FMA pipe from flag bytes that ride in the unused
-   bytes of x (byte 1: RGBA, byte 3: RGB or RGBA -- they add into the gaps between the 16-bit fields, which the final PRMT
-   drops) and of y (byte 3: LUMA) */
-__device__ __forceinline__ uint2 op_lut64_entry(uint32_t tag) {
-	const uint4 e = op_lut_entry(tag);
-	uint2 r;
-	r.x = e.x | (e.w == 0xFFFFFFFFu ? 0x00000100u : 0u) | (e.w ? 0x01000000u : 0u);
-	r.y = (e.y & 0x00FFFFFFu) | (e.z ? 0x01000000u : 0u);
-	return r;
-}
-__device__ __forceinline__ uint4 op_lut64_expand(uint2 e) {
-	uint4 L;
-	L.x = e.x;
-	L.y = e.y;
-	L.z = __dp4a(e.y, 0x01000000u, 0u) * 0x000F000Fu;
-	L.w = __dp4a(e.x, 0x01000000u, 0u) * 0x00FFFFFFu + __dp4a(e.x, 0x00000100u, 0u) * 0xFF000000u;
-	return L;
-}
-#endif
-
 struct Reader {
 	uint64_t buf;       /* the next `avail` stream bytes, lowest byte first */
 	uint32_t avail;
@@ -151,13 +130,8 @@ __device__ __forceinline__ void load_chunk(Reader &rd) {
 template <int OUT_CH, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P) {
 	QOI_DYNAMIC_SMEM(smem);
-#ifdef QOI_DEC_LUT64
-	uint2 *lut = (uint2 *)smem;
-	for (uint32_t k = threadIdx.x; k < 256u; k += BLOCK) lut[k] = op_lut64_entry(k);
-#else
 	uint4 *lut = (uint4 *)smem;
 	for (uint32_t k = threadIdx.x; k < 256u; k += BLOCK) lut[k] = op_lut_entry(k);
-#endif
 	__syncthreads(); /* before any lane leaves */
 	uint32_t *tab = (uint32_t *)(smem + QOI_DEC_LUT_BYTES) + threadIdx.x;  /* tab[slot * BLOCK] */
 	uint32_t *ring = tab + 64 * BLOCK;               /* ring[word * BLOCK] */
@@ -274,11 +248,7 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 		}
 		const uint32_t tag = (uint32_t)rd.buf & 0xFFu;
 		const uint32_t pay = (uint32_t)(rd.buf >> 8); /* the four bytes after the tag */
-#ifdef QOI_DEC_LUT64
-		const uint4 L = op_lut64_expand(lut[tag]);
-#else
 		const uint4 L = lut[tag];
-#endif
 		const uint32_t idxv = tab[(tag & 63u) * BLOCK]; /* qoi.h:558-560 */
 		const uint32_t npx = op_colour(tag, pay, L, idxv, px);
 		const uint32_t len = __dp4a(L.y, 0x00000100u, 0u);

@@ -22,8 +22,9 @@
  *   - small CTAs (4 compute warps + 1 service warp, ~22 KB of shared memory, <= 40 registers): ~10 CTAs = 10 tiles
  *     in flight per SM, so one CTA's look-back wait is another CTA's compute time;
  *   - lane = pixel.  A warp owns 512 consecutive pixels and walks them as 16 rows of 32; every step of qoi.h's state
- *     machine is a warp-wide operation (ballot = non-run mask, match.any = lanes with my hash slot, shuffle = the
- *     same-slot predecessor inside the row, one shared-memory word per slot for the rows before);
+ *     machine is a warp-wide operation (ballot = non-run mask; lanes with my hash slot = match.any or six ballots of the
+ *     slot's bits, alternating so that neither the ADU nor the ALU pipe carries them alone; shuffle = the same-slot
+ *     predecessor inside the row, one shared-memory word per slot for the rows before);
  *   - two light passes instead of defer-and-patch.  Pass A only finds the last writer of every slot in each warp's
  *     chunk (no look-ups); the tile aggregate is published, the service warp looks back for the incoming table, and
  *     pass B runs with an EXACT table from its first pixel: look-up, op selection, sizes (three ballots + popc, no
@@ -246,7 +247,8 @@ __device__ __forceinline__ void sts_u8_if(bool pred, unsigned char *addr, uint32
 
 /* the lanes of the row whose 6-bit key equals mine: six ballots.  (match.any does this in one instruction, but that
    instruction holds the ADU pipe for ~50 cycles per warp on sm_100a -- measured, profiles/r2_enc_v1 -- and two of them per
-   row made the whole kernel ADU-bound.) */
+   row made the whole kernel ADU-bound; pass A now uses it on every other row, see there.) */
+#define QOI_ENC_MATCH_ROWS 2 /* rows of every four whose slot match is a match.any */
 __device__ __forceinline__ uint32_t same_key_lanes(uint32_t key) {
 #ifdef QOI_EMU
 	uint32_t differ = 0;
@@ -654,7 +656,7 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 			int32_t last_nr = -1; /* tile-local index of the chunk's last non-run pixel so far (uniform) */
 			const uint32_t *px = pix + wbase + lane;
 			uint32_t il = wbase + lane;
-#pragma unroll 2
+#pragma unroll 4
 			for (int s = 0; s < QOI_WARP_ROWS; s++, px += 32, il += 32u) {
 				const uint32_t v = px[0], p = px[-1];
 				const bool valid = il < nv;
@@ -664,7 +666,15 @@ __global__ void __launch_bounds__(QOI_ENC_THREADS, QOI_ENC_MIN_BLOCKS) qoi_encod
 				uint32_t hb = 0, ub = 0;
 				if (nr) { /* uniform: a row of run pixels touches nothing */
 					const uint32_t h = qoi_slot(v);
+#ifdef QOI_EMU
 					const uint32_t m = same_key_lanes(h) & nr;
+#else
+					/* the row's lanes with my slot: match.any on two rows of every four, six ballots on the other two.  Both give
+					   the same mask; one runs on the ADU pipe (~50 cycles per warp), the other is 19 ALU-pipe instructions --
+					   alone either pipe is the kernel's limit (ALU 75 % with ballots only, ADU 73 % with match.any only:
+					   4.42 / 4.37 ms), mixed 1:1 they share the load: 4.12 ms (profiles/r2_enc_v4) */
+					const uint32_t m = ((s & 3) < QOI_ENC_MATCH_ROWS ? __match_any_sync(QOI_FULL_MASK, h) : same_key_lanes(h)) & nr;
+#endif
 					const uint32_t lower = m & lt;
 					const uint2 e = wtab[h];                                                 /* as the rows before left it */
 					const uint32_t pv = __shfl_sync(QOI_FULL_MASK, v, 31 - __clz((int)lower)); /* nearest same-slot pixel of this row (garbage if none) */

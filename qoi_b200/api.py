@@ -216,6 +216,14 @@ class Plan:
         _check(lib().qoi_gpu_decode(self._h, d_streams, d_lens, d_decoded, 1 if use_index else 0, d_status, stream),
                self.ctx._h, "qoi_gpu_decode")
 
+    def fstats(self):
+        """diagnostics of the last decode(use_index=False): (walks per state round, unsettled streams per round,
+        indices of the first images that went to the sequential fall-back)"""
+        out = (C.c_uint32 * 128)()
+        _check(lib().qoi_gpu_plan_fstats(self._h, out), self.ctx._h, "qoi_gpu_plan_fstats")
+        v = list(out)
+        return v[:60], v[64:124][:56], [x - 1 for x in v[120:128] if x]
+
     # restart index as a side-car (include/qoi_gpu.h qoi_gpu_index_*): bytes out, bytes in
     def export_index(self, stream=0):
         n = int(lib().qoi_gpu_index_bytes(self._h))

@@ -111,3 +111,24 @@ def test_emulated_tile_edges(emu, cpu):
     for k, (w, h, ch, n, dist) in enumerate([(2048, 1, 4, 3, 4), (2049, 1, 4, 3, 4), (2110, 1, 3, 2, 7), (2047, 3, 4, 2, 2), (513, 4, 4, 2, 5),
                                              (511, 5, 3, 2, 3), (4096, 1, 4, 1, 7), (4097, 1, 3, 1, 7), (1, 1, 4, 4, 4), (33, 1, 3, 3, 0), (300, 200, 3, 2, 5)]):
         run_enc_only(emu, cpu.batch(n, w, h, ch, dist), w, h, ch, n, 1 + k % 4, k + 1, (0, 5, 3)[k % 3] if ch == 4 else 1 + k % 3)
+
+
+def test_emulated_anystream_settles_without_fallback(emu, cpu):
+    """Regression of the round-2 convergence defects: photo image 111 of the 1920x1080 RGB set once guessed
+    alpha 0 out of slot 0's initial zero and dragged it down the stream 48 segments per round -- 16 rounds were not enough and
+    the stream went to the sequential fall-back (from segment 2009 of 6486).  It has to settle by itself, within a few rounds."""
+    w, h, ch = 1920, 1080, 3
+    img = cpu.image(w, h, ch, 4, 111)
+    with tempfile.NamedTemporaryFile(suffix=".raw") as f:
+        f.write(img.tobytes())
+        f.flush()
+        r = subprocess.run([emu, "enc", str(w), str(h), str(ch), "1", "4", "1", "0", f.name], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, QOI_EMU_FSTATS="1", QOI_EMU_FTRACE="1"))
+    assert r.returncode == 0 and r.stdout.startswith("PASS"), r.stdout + r.stderr[-2000:]
+    stats = [ln for ln in r.stderr.splitlines() if "fall-back from segment" in ln]
+    assert stats, r.stderr[-2000:]
+    words = stats[0].split()
+    live, first = int(words[2]), int(words[words.index("segment") + 1])
+    assert first == live, stats[0]           # nothing left for the fall-back
+    walks = [int(ln.split(",")[1].split()[0]) for ln in r.stderr.splitlines() if ln.startswith("round ") and "to walk again" in ln]
+    assert walks[:16].index(0) <= 5, walks   # no segment listed after at most five rounds

@@ -323,6 +323,30 @@ def test_config2_batch_of_256_spans_waves(gpu, cpu):
     plan.close()
 
 
+def test_anystream_settles_without_fallback(gpu, cpu):
+    """Round-2 regression: streams that are not the headline shape must settle in the state rounds too.
+    64 x 1920x1080 RGB photographs with image indices 96..159 (index 111 once dragged a wrong alpha down its stream and went
+    to the sequential fall-back) and one 8192x8192 RGBA image (4 x the segments of a 4096^2 one): decoded as foreign
+    streams, pixels equal to the input, no image reported by qoi_gpu_plan_fstats."""
+    qb, torch, ctx = gpu
+    for (n, w, h, ch, first) in ((64, 1920, 1080, 3, 96), (1, 8192, 8192, 4, 23)):
+        plan = qb.Plan(ctx, [qb.Desc(w, h, ch, 0)] * n, decoded_channels=ch)
+        host = cpu.batch(n, w, h, ch, 4, first=first)
+        d_pix = dev_u8(torch, host)
+        d_streams = torch.empty(plan.stream_bytes, dtype=torch.uint8, device="cuda")
+        d_lens = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_dec = torch.zeros(plan.decoded_bytes, dtype=torch.uint8, device="cuda")
+        plan.encode(d_pix.data_ptr(), d_streams.data_ptr(), d_lens.data_ptr())
+        plan.decode(d_streams.data_ptr(), d_lens.data_ptr(), d_dec.data_ptr(), use_index=False)
+        torch.cuda.synchronize()
+        assert torch.equal(d_dec, d_pix), (w, h)
+        walks, unsettled, fell_back = plan.fstats()
+        assert fell_back == [], (w, h, fell_back, walks[:17])
+        assert unsettled[8] == 0, (w, h, unsettled[:17])   # everything settled well before the 16th round
+        plan.close()
+        del d_pix, d_streams, d_dec
+
+
 def test_index_sidecar_through_disk(gpu, cpu, tmp_path):
     """the restart index leaves the plan as a side-car, the streams and the side-car go to disk, a NEW plan
     reads both back and decodes with use_index -- same pixels as the reference decoder gives for the stored streams."""
