@@ -176,8 +176,13 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 		for (int k = 0; k < 64; k++) tab[k * BLOCK] = 0;
 	} else {
 		const uint64_t *src = P.st.ent + (size_t)(job - 1) * 64; /* [63:32] value; 0 in a slot nothing has been stored to yet */
-#pragma unroll 8
-		for (int k = 0; k < 64; k++) tab[k * BLOCK] = (uint32_t)(src[k] >> 32);
+#pragma unroll 4
+		for (int q = 0; q < 16; q++) { /* four 8-byte entries per 256-bit load (the record is 512-byte aligned) */
+			uint4 a, b;
+			ld_nc_256(src + 4 * q, a, b);
+			uint32_t *t = tab + (4 * q) * BLOCK;
+			t[0 * BLOCK] = a.y; t[1 * BLOCK] = a.w; t[2 * BLOCK] = b.y; t[3 * BLOCK] = b.w;
+		}
 		/* the reference DEcoder also stores the current colour after a RUN op (qoi.h:577); the ENcoder's
 		   table does not see the leading run of the start colour.  Only slot 53 can differ, and only
 		   until a pixel hashing to 53 is coded. */
