@@ -60,18 +60,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 	while (!mbar_try_wait(bar, parity)) {
 	}
 }
-/* global -> shared bulk copy (1-D TMA); both addresses 16-byte aligned, bytes a multiple of 16, bytes > 0 */
-__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
-	             "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
-	             : "memory");
-}
-/* shared -> global bulk copy; same alignment rules; completion tracked by the bulk group */
-__device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {
-	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes)
-	             : "memory");
-}
-/* L2 eviction policy for data that is touched exactly once (pixels in, streams out): keeps the look-back records,
+/* global -> shared bulk copy (1-D TMA, tma_load_1d_hint below): both addresses 16-byte aligned, bytes a multiple of 16, bytes > 0.
+   L2 eviction policy for data that is touched exactly once (pixels in, streams out): keeps the look-back records,
    the restart index and the instruction stream resident in L2 while gigabytes stream through */
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
 	uint64_t pol;
@@ -83,17 +73,7 @@ __device__ __forceinline__ void tma_load_1d_hint(void *dst_smem, const void *src
 	             "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
 	             : "memory");
 }
-__device__ __forceinline__ void tma_store_1d_hint(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t pol) {
-	asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes),
-	             "l"(pol)
-	             : "memory");
-}
-/* streaming (evict-first) 16-byte global accesses for the decoder */
-__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
-	uint4 v;
-	asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-	return v;
-}
+/* streaming (evict-first) 16-byte global store (the encoder's copy-out) */
 __device__ __forceinline__ void st_stream_u4(uint4 *p, uint4 v) {
 	asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -116,30 +96,6 @@ __device__ __forceinline__ void st_256(void *p, uint4 a, uint4 b) {
 	asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z),
 	             "r"(b.w)
 	             : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-/* wait until all committed bulk stores of this thread have finished READING shared memory */
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-/* wait until they are complete (writes performed) */
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-/* order generic-proxy shared-memory writes before a following bulk store */
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
-	uint32_t v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p) {
-	uint64_t v;
-	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v) {
-	asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
 	uint64_t v;
@@ -225,27 +181,12 @@ static inline void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t by
 	b->tx -= (int32_t)bytes;
 	emubar_check(b);
 }
-static inline void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {
-	emu_check_bulk(dst_gmem, src_smem, bytes);
-	memcpy(dst_gmem, src_smem, bytes);
-	qemu::progress++;
-}
 static inline uint64_t l2_evict_first_policy() { return 0; }
 static inline void tma_load_1d_hint(void *d, const void *s_, uint32_t n, uint64_t *bar, uint64_t) { tma_load_1d(d, s_, n, bar); }
-static inline void tma_store_1d_hint(void *d, const void *s_, uint32_t n, uint64_t) { tma_store_1d(d, s_, n); }
-static inline uint4 ld_stream_u4(const uint4 *p) { return *p; }
 static inline void st_stream_u4(uint4 *p, uint4 v) { *p = v; }
 static inline void ld_nc_256(const void *p, uint4 &a, uint4 &b) { a = ((const uint4 *)p)[0]; b = ((const uint4 *)p)[1]; }
 static inline void ld_256(const void *p, uint4 &a, uint4 &b) { a = ((const uint4 *)p)[0]; b = ((const uint4 *)p)[1]; }
 static inline void st_256(void *p, uint4 a, uint4 b) { ((uint4 *)p)[0] = a; ((uint4 *)p)[1] = b; }
-static inline void tma_store_commit() {}
-static inline void tma_store_wait_read() {}
-static inline void tma_store_wait_all() {}
-static inline void fence_proxy_async_smem() {}
-static inline uint32_t ld_acquire_u32(const uint32_t *p) { return *p; }
-static inline void st_release_u32(uint32_t *p, uint32_t v) { *p = v; qemu::progress++; }
-static inline uint64_t ld_acquire_u64(const uint64_t *p) { return *p; }
-static inline void st_release_u64(uint64_t *p, uint64_t v) { *p = v; qemu::progress++; }
 static inline uint64_t ld_relaxed_u64(const uint64_t *p) { return *p; }
 static inline void st_relaxed_u64(uint64_t *p, uint64_t v) { *p = v; qemu::progress++; }
 static inline void bar_sync(uint32_t id, uint32_t nthreads) { qemu::named_barrier(id, nthreads, true); }

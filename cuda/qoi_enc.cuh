@@ -231,20 +231,6 @@ __device__ __forceinline__ void fetch_issue(const QoiEncParams &P, unsigned char
 	if (lane == 0) mbar_arrive(mbar);
 }
 
-/* one byte to shared memory under a predicate, without a branch (the op bytes of a row: up to five stores per lane) */
-__device__ __forceinline__ void sts_u8_if(bool pred, unsigned char *addr, uint32_t val) {
-#ifdef QOI_EMU
-	if (pred) *addr = (unsigned char)val;
-#else
-	asm volatile(
-	    "{\n\t.reg .pred p;\n\t"
-	    "setp.ne.u32 p, %0, 0;\n\t"
-	    "@p st.shared.u8 [%1], %2;\n\t}" ::"r"((uint32_t)pred),
-	    "r"(smem_addr(addr)), "r"(val)
-	    : "memory");
-#endif
-}
-
 /* the lanes of the row whose 6-bit key equals mine: six ballots.  (match.any does this in one instruction, but that
    instruction holds the ADU pipe for ~50 cycles per warp on sm_100a -- measured, profiles/r2_enc_v1 -- and two of them per
    row made the whole kernel ADU-bound; pass A now uses it on every other row, see there.) */
