@@ -316,6 +316,27 @@ __global__ void __launch_bounds__(BLOCK) qoi_decode_kernel(const QoiDecParams P)
 			i++;
 			refill();
 		}
+		const bool wide_ok = ((uintptr_t)obase & 7u) == 0;
+		if (wide_ok && (i & 4u) && i + 4 <= px_end) { /* up to a multiple of 8 pixels: 24-byte groups are 8-byte aligned */
+			const uint32_t a = step(), b = step(), c = step(), d = step();
+			uint32_t *o = (uint32_t *)(obase + (size_t)i * 3);
+			o[0] = (a & 0x00FFFFFFu) | (b << 24);
+			o[1] = ((b >> 8) & 0x0000FFFFu) | (c << 16);
+			o[2] = ((c >> 16) & 0x000000FFu) | (d << 8);
+			i += 4;
+			refill();
+		}
+		while (wide_ok && i + 8 <= px_end) { /* 8 pixels = 24 bytes = three 8-byte stores (a third of the passes of six word stores) */
+			const uint32_t a = step(), b = step(), c = step(), d = step();
+			refill();
+			const uint32_t e = step(), f = step(), g = step(), h = step();
+			uint2 *o = (uint2 *)(obase + (size_t)i * 3);
+			o[0] = make_uint2((a & 0x00FFFFFFu) | (b << 24), ((b >> 8) & 0x0000FFFFu) | (c << 16));
+			o[1] = make_uint2(((c >> 16) & 0x000000FFu) | (d << 8), (e & 0x00FFFFFFu) | (f << 24));
+			o[2] = make_uint2(((f >> 8) & 0x0000FFFFu) | (g << 16), ((g >> 16) & 0x000000FFu) | (h << 8));
+			i += 8;
+			refill();
+		}
 		while (i + 4 <= px_end) { /* 4 pixels = 12 bytes = three aligned words */
 			const uint32_t a = step(), b = step(), c = step(), d = step();
 			uint32_t *o = (uint32_t *)(obase + (size_t)i * 3);
