@@ -275,6 +275,28 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def all_threads_sample(cpu_baseline, eb, db, threads, h_pix, n, m, img_bytes, slot):
+    """cpu_baseline with every host thread busy, as in the --impl reference arm: one image per thread, the batch's images
+    repeated (qoi.h codes one image per call: images are its only parallel axis).  The batch-sized pass stays in
+    cpu_baseline.batch_sample; skipped when the buffers would not fit, and never allowed to cost the line."""
+    try:
+        if threads <= m or threads * (img_bytes + slot) > (24 << 30):
+            return
+        reps_px = np.concatenate([h_pix[:n * img_bytes]] * ((threads + n - 1) // n))[:threads * img_bytes]
+        kk = np.empty(threads * slot, dtype=np.uint8)
+        kl = np.zeros(threads, dtype=np.int32)
+        cpu_round_trip(eb, db, threads, reps_px, threads, kk, kl, slot)
+        tea, tda = cpu_round_trip(eb, db, threads, reps_px, threads, kk, kl, slot)
+        cpu_baseline["batch_sample"] = {k: cpu_baseline[k] for k in ("value", "cores", "sample", "encode_gpx", "decode_gpx")}
+        cpu_baseline.update({"value": threads * W * H / (tea + tda) / 1e9, "cores": threads,
+                             "sample": f"{threads} x {W}x{H}x{CH} images (one per host thread: the batch's images repeated), one encode+decode pass "
+                                       "after a warm-up pass, OpenMP over images, malloc+free inside the call (qoibench.c:446-450,471-481); the "
+                                       "GPU streams of the batch were verified identical on the batch_sample pass",
+                             "encode_gpx": threads * W * H / tea / 1e9, "decode_gpx": threads * W * H / tda / 1e9})
+    except Exception as e:
+        cpu_baseline["all_threads_error"] = repr(e)
+
+
 def c_api_single_image(h_pix, args):
     """extra.c_api_single_image: the four-function drop-in itself, one image per call (see the note in the result)."""
     # the four-function drop-in itself, called the way qoibench.c calls qoi.h: one image per call, pageable
@@ -576,6 +598,7 @@ def run_b200(args, rank, world, local_rank, torch, dist, emit=True):
                             "encode_gpx": m * W * H / te / 1e9, "decode_gpx": m * W * H / td / 1e9,
                             "single_thread": {"value": W * H / (te1 + td1) / 1e9, "encode_gpx": W * H / te1 / 1e9, "decode_gpx": W * H / td1 / 1e9,
                                               "sample": "one image, one thread"}}
+            all_threads_sample(cpu_baseline, eb, db, threads, h_pix, n, m, img_bytes, slot)
         try:
             c_api = c_api_single_image(h_pix, args) if (world == 1 and not args.no_cpu) else None
         except Exception as e:  # the headline line must not depend on this extra

@@ -59,7 +59,9 @@ int main(int argc, char **argv) {
 	}
 	const int n = atoi(argv[2]), W = atoi(argv[3]), H = atoi(argv[4]), CH = atoi(argv[5]), runs = 5;
 	const int with_foreign = getenv("ENC_AB_FOREIGN") != NULL;
-	const size_t img = (size_t)W * H * CH, dimg = (size_t)W * H * 4;
+	/* decode to 4 channels like qoibench.c:446-450, or to the image's own count with ENC_AB_DEC_CH=3 (RGB input only) */
+	const int DCH = (CH == 3 && getenv("ENC_AB_DEC_CH") && atoi(getenv("ENC_AB_DEC_CH")) == 3) ? 3 : 4;
+	const size_t img = (size_t)W * H * CH, dimg = (size_t)W * H * DCH;
 	qoi_desc *descs = (qoi_desc *)calloc((size_t)n, sizeof(qoi_desc));
 	uint64_t *poff = (uint64_t *)calloc((size_t)n, 8), *soff = (uint64_t *)calloc((size_t)n, 8);
 	size_t slot = 0;
@@ -83,7 +85,7 @@ int main(int argc, char **argv) {
 	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
 	qoi_gpu_ctx *ctx = NULL;
 	qoi_gpu_plan *plan = NULL;
-	if (ctx_create(&ctx, 0) != QOI_GPU_OK || plan_create(ctx, &plan, n, descs, poff, soff, NULL, 4) != QOI_GPU_OK) { printf("setup failed\n"); return 2; }
+	if (ctx_create(&ctx, 0) != QOI_GPU_OK || plan_create(ctx, &plan, n, descs, poff, soff, NULL, DCH) != QOI_GPU_OK) { printf("setup failed\n"); return 2; }
 	printf("library %s, checker %s, %d x %dx%dx%d\n", argv[1], cpu_name, n, W, H, CH);
 	int bad = 0;
 	for (int a = 6; a < argc; a++) {
@@ -108,7 +110,7 @@ int main(int argc, char **argv) {
 		CK(cudaMemcpy(l_got, d_len, 4u * n, cudaMemcpyDeviceToHost));
 		CK(cudaMemcpy(h_dec, d_dec, dimg * n, cudaMemcpyDeviceToHost));
 		int rt = 1, rtf = 1, same = 1;
-		if (CH == 4) rt = memcmp(h_dec, h_pix, img * n) == 0;
+		if (CH == DCH) rt = memcmp(h_dec, h_pix, img * n) == 0;
 		else for (size_t k = 0; k < (size_t)W * H * n && rt; k++) rt = h_dec[4 * k] == h_pix[3 * k] && h_dec[4 * k + 1] == h_pix[3 * k + 1] && h_dec[4 * k + 2] == h_pix[3 * k + 2] && h_dec[4 * k + 3] == 255;
 		if (with_foreign) {
 			for (int r = 0; r <= 2; r++) {
@@ -122,7 +124,7 @@ int main(int argc, char **argv) {
 				if (r) fdec += z;
 			}
 			CK(cudaMemcpy(h_dec, d_dec, dimg * n, cudaMemcpyDeviceToHost));
-			if (CH == 4) rtf = memcmp(h_dec, h_pix, img * n) == 0;
+			if (CH == DCH) rtf = memcmp(h_dec, h_pix, img * n) == 0;
 			else for (size_t k = 0; k < (size_t)W * H * n && rtf; k++) rtf = h_dec[4 * k] == h_pix[3 * k] && h_dec[4 * k + 1] == h_pix[3 * k + 1] && h_dec[4 * k + 2] == h_pix[3 * k + 2] && h_dec[4 * k + 3] == 255;
 		}
 		double bytes = 0;
