@@ -61,6 +61,7 @@ using namespace qoidev;
 #define QOI_FF_DEP 1u  /* the guess disagrees with the scanned state on something the segment depended on */
 #define QOI_FF_TRUST 4u /* the segment's last walk started from a guess that held on everything it depended on: what it derived from
                            the guess can be trusted (segment 0 always: its "guess" is the reference's initial state) */
+#define QOI_FF_CGUESS 8u /* round 0 only: the guessed colour is the replayed tail of the segment before (fzero_kernel), not the default */
 
 struct QoiFState {
 	/* geometry (host written) */
@@ -70,6 +71,7 @@ struct QoiFState {
 	uint32_t *px_cnt;   /* [segs][5] pixels produced when entered with skip s */
 	uint8_t *exit_skip; /* [segs][8] (5 used) */
 	uint32_t *last_rel; /* [segs][5] pixels produced before the segment's LAST op starts */
+	uint16_t *last_abs; /* [segs] offset of the last RGB / RGBA op that starts in the segment (walk 0), 0xFFFF: none */
 	/* chain result */
 	uint8_t *entry;     /* [segs] distance from the segment start to its first op */
 	uint32_t *px_start; /* [segs] first pixel of the segment */
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 	const int32_t near = begin + 128 < end ? begin + 128 : end;
 	uint64_t seen_lo = 0, seen_hi = 0;
 	uint32_t total0 = 0, last0 = 0; /* last0: pixels before the last op */
+	uint32_t abs0 = 0xFFFFu;        /* where the segment's last RGB / RGBA op starts (fguess_kernel) */
 	int32_t p0 = begin;
 	while (p0 < end) {
 		last0 = total0;
@@ -184,9 +187,11 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFPara
 			else seen_hi |= 1ull << (off - 64u);
 		}
 		const uint32_t tag = s[p0];
+		if (tag >= 0xFEu) abs0 = (uint32_t)(p0 - begin);
 		p0 += op_len(tag);
 		total0 += op_px(tag);
 	}
+	P.f.last_abs[g] = (uint16_t)abs0;
 	const uint32_t exit0 = (uint32_t)(p0 - end);
 	P.f.px_cnt[(size_t)g * 5] = total0;
 	P.f.last_rel[(size_t)g * 5] = last0;
@@ -386,6 +391,40 @@ __global__ void __launch_bounds__(QOI_FDEC_THREADS) fzero_kernel(const QoiFParam
 	uint32_t *t = P.f.g_tab + (size_t)g * 64;
 #pragma unroll
 	for (int k = 0; k < 8; k++) st_256(t + 8 * k, make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u));
+	/* Round-0 guess of the colour that enters the segment.  The reference's start colour is right for segment 0 only; for
+	   the others the colour that LEAVES the segment before is usually known from that segment's own bytes: replay its tail
+	   from its last RGB / RGBA op (fparse_kernel noted where it starts) -- DIFF, LUMA and RUN ops only add to it; an INDEX
+	   op on the way, or no absolute op at all, leaves the default.  r,g,b are then exact and alpha is whatever an RGBA op
+	   said, else opaque; it is a guess like any other (a walk of the segment before that does not pass through that op
+	   start makes it wrong, the check finds out), but most walks of round 0 now start on the right colour and what they
+	   derive from it survives the first check. */
+	const uint32_t j = g - P.f.seg_base[img];
+	if (j == 0u) return;
+	const uint32_t off = P.f.last_abs[g - 1u];
+	if (off == 0xFFFFu) return;
+	const QoiImgMeta m = P.imgs[img];
+	const uint8_t *s = P.streams + m.stream_off;
+	const int32_t mine = QOI_HEADER_BYTES + (int32_t)j * QOI_FSEG_BYTES; /* the ops that start before this belong to the segment before */
+	int32_t p = mine - QOI_FSEG_BYTES + (int32_t)off;
+	uint32_t tag = s[p];
+	uint32_t px = (uint32_t)s[p + 1] | ((uint32_t)s[p + 2] << 8) | ((uint32_t)s[p + 3] << 16) | (tag == 0xFFu ? (uint32_t)s[p + 4] << 24 : 0xFF000000u);
+	p += op_len(tag);
+	bool known = true;
+	while (p < mine && known) {
+		tag = s[p];
+		const uint32_t top = tag >> 6;
+		if (top == 0u || tag >= 0xFEu) known = false; /* INDEX: the colour comes out of index[]; (an absolute op cannot follow the last one) */
+		else if (top == 1u) px = add_bytes(px, ((((tag >> 4) & 3u) - 2u) & 0xFFu) | (((((tag >> 2) & 3u) - 2u) & 0xFFu) << 8) | ((((tag & 3u) - 2u) & 0xFFu) << 16)); /* qoi.h:561-565 */
+		else if (top == 2u) { /* qoi.h:566-572 */
+			const uint32_t b2 = s[p + 1], vg = (tag & 0x3Fu) - 32u;
+			px = add_bytes(px, ((vg - 8u + ((b2 >> 4) & 0xFu)) & 0xFFu) | ((vg & 0xFFu) << 8) | (((vg - 8u + (b2 & 0xFu)) & 0xFFu) << 16));
+		}
+		p += op_len(tag);
+	}
+	if (known) {
+		P.f.g_px[g] = px;
+		P.f.flag[g] = (uint8_t)QOI_FF_CGUESS;
+	}
 }
 
 /* proven prefix of a stream, as a global segment index: what the check of the round before established */
@@ -676,7 +715,13 @@ __device__ __forceinline__ bool stream_settled(const QoiFParams &P, uint32_t img
    its check (QOI_FF_TRUST) -- unless it read an initial-zero slot (dep bit 6): then only once it lies inside the proven
    prefix of its stream (g < gpe; segment 0 always does). */
 __device__ __forceinline__ bool seg_trusted(const QoiFParams &P, uint32_t g, uint32_t gpe) {
-	return (P.f.flag[g] & QOI_FF_TRUST) != 0u && (!(P.f.dep[g] & 64u) || g < gpe);
+	const uint32_t fl = P.f.flag[g], d = P.f.dep[g];
+	if ((fl & QOI_FF_TRUST) != 0u && (!(d & 64u) || g < gpe)) return true;
+	/* Round 0: a walk that depended on nothing but a replayed colour (no guessed slot read, no initial zero) is as good as
+	   one whose guess a check has confirmed -- its colour came from the stream's own bytes.  Trusting it lets the first
+	   scan see its writes, so that the segments listed for round 1 get guesses that already hold (without it the same
+	   segments were walked in round 1 AND round 2).  Sound: the check still compares its guess with the scanned state. */
+	return P.round == 0u && (fl & QOI_FF_CGUESS) != 0u && P.f.rbw[g] == 0ull && !(d & 64u);
 }
 /* The colour is not "last writer": a segment of DIFF / LUMA / RUN ops adds a known delta to whatever colour enters it.  So
    the colour's scan composes maps  colour -> (r,g,b: constant c | + d) x (alpha: constant c | unchanged), one per segment.
@@ -1192,6 +1237,7 @@ static inline void fstate_bind(QoiFState &f, unsigned char *base, const size_t *
 	f.rec_wr = (uint64_t *)(base + off[27]);
 	f.rs_seg = (uint32_t *)(base + off[28]);
 	f.x_state = (uint32_t *)(base + off[29]);
+	f.last_abs = (uint16_t *)(base + off[32]);
 }
 
 }  // namespace qoifdec

@@ -136,7 +136,7 @@ static inline void qoi_state_bind(QoiTileState &st, unsigned char *base, const Q
 /* ------------------------------------------------------------------ foreign-stream decoder scratch (qoi_fdec.cuh) */
 #define QOI_FSEG_BYTES_HOST 1024 /* must equal QOI_FSEG_BYTES */
 #define QOI_FCHUNK_HOST 64       /* must equal QOI_FCHUNK: segments per scan chunk */
-#define QOI_F_ARRAYS 32
+#define QOI_F_ARRAYS 33
 
 struct QoiFLayout {
 	std::vector<uint32_t> seg_base;   /* [n + 1] first segment of each image (capacity) */
@@ -169,7 +169,7 @@ static inline QoiFLayout qoi_fstate_layout(const QoiPlanGeom &g) {
 	                                    S * 256,     S * 4,       S * 256, S * 8,      S * 8,     S * 4,     S,         S * 4,
 	                                    64 * 4,      C * 256,     C * 8,   C * 8,      C * 256,   C * 4,     N * 4 * 4, N * 4 * 2,
 	                                    S * 8,       S * 20,      S * 4,   TL * 8,     TL * 4,    N * 65 * 4,
-	                                    S * 4,       64 * 4};
+	                                    S * 4,       64 * 4,      S * 2};
 	size_t o = 0;
 	for (int k = 0; k < QOI_F_ARRAYS; k++) {
 		L.off[k] = o;
