@@ -156,8 +156,9 @@ __device__ __forceinline__ int32_t op_len(uint32_t tag) { return (tag == 0xFEu) 
 __device__ __forceinline__ uint32_t op_px(uint32_t tag) { return ((tag >> 6) == 3u && tag < 0xFEu) ? (tag & 0x3Fu) + 1u : 1u; }
 
 /* ------------------------------------------------------------------ 1a. parse: one thread per segment */
-/* (Reading the bytes as 16-byte pieces held in registers, the byte picked with selects, was measured: 1.80 ms instead of 1.22 ms
-   for 32 x 4096^2 photographs -- the selects cost more than the sector look-ups of plain byte loads, which mostly hit L1.) */
+/* (Measured alternatives for the byte fetch of walk 0, 32 x 4096^2 photographs, plain byte loads = 1.22 ms: 16-byte pieces held
+   in registers with the byte picked by selects 1.80 ms; the decoders' chunk ring in shared memory (256-bit loads, one
+   shared-memory read per op) 1.61 ms -- the byte loads mostly hit L1 and cost fewer instructions than either.) */
 __global__ void __launch_bounds__(QOI_FDEC_THREADS) fparse_kernel(const QoiFParams P) {
 	const uint32_t g = blockIdx.x * QOI_FDEC_THREADS + threadIdx.x;
 	if (g >= P.n_segs) return;
