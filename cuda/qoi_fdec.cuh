@@ -11,8 +11,9 @@
  *      (bytes to skip at exit, pixels produced)" for the 5 possible entry skips.  fparse_kernel tabulates the map,
  *      fchain_kernel composes the maps along each stream: every segment's true first op and first pixel.
  *   2. state rounds (parallel, O(ops), no pixels).  fstate_kernel walks a segment's ops from a GUESSED state (colour,
- *      index[]) and records the state it ends with (last value written per slot, the colour) and what that result depended
- *      on: which guessed slots were read before the segment wrote them, whether the incoming r,g,b / alpha mattered.
+ *      index[]; round 0: index[] zeroed as the reference starts, the colour replayed from the tail of the segment before
+ *      -- fzero_kernel) and records the state it ends with (last value written per slot, the colour) and what that result
+ *      depended on: which guessed slots were read before the segment wrote them, whether the incoming r,g,b / alpha mattered.
  *      Whenever an op starts at or behind a 2048-pixel tile boundary it drops a restart record (pixel, stream offset,
  *      colour before, index[]) into the plan's index -- the same record the encoder leaves.
  *   3. scan + check (parallel).  "State before segment j" is a last-writer scan over the segments' results (per slot: the
