@@ -9,7 +9,9 @@
  * or oracle/liboracle.so is present -- the first and last image's stream compared byte for byte with the CPU checker.
  * The library is loaded with dlopen so that several builds (e.g. different launch bounds) can be timed in one session.
  */
+#ifndef _GNU_SOURCE
 #define _GNU_SOURCE
+#endif
 #include <cuda_runtime_api.h>
 #include <dlfcn.h>
 #include <stdint.h>
